@@ -1,0 +1,177 @@
+/*
+ * zopt_b200 -- C ABI of the B200-native LQR / iLQR / DDP / LQR-MPC solver.
+ *
+ * This is the drop-in boundary for the hot path of zprihoda/zopt.  The reference
+ * is pure Python (JAX); it has no FFI of its own, so each entry point below names
+ * the reference *function* it replaces (file:line under the reference tree).  The
+ * Python mirror in zopt_b200/*.py binds these with ctypes.
+ *
+ * Conventions
+ *   - Every function returns int32: 0 = OK, <0 = argument error, >0 = CUDA error
+ *     code.  zb_last_error() returns the thread-local message of the last failure.
+ *     Numerical non-success (converged=false, NaN) is data, not an error.
+ *   - All pointers are DEVICE pointers on `device`; work is enqueued on `stream`
+ *     (a cudaStream_t) and the call returns without synchronising.  The caller
+ *     owns every buffer; the library keeps no pointer after return.
+ *   - dtype: ZB_F32 or ZB_F64; every floating-point buffer of a call has that type.
+ *   - Dense matrices are row-major and contiguous; batches / time series are
+ *     described by element strides (zb_arr), so a time-invariant or batch-shared
+ *     operand is passed with stride 0 and never materialised.
+ *   - Public layouts follow the reference index order with one leading batch
+ *     axis: L is (Bsz,N,m,n), xTraj (Bsz,N+1,n), uTraj (Bsz,N,m).
+ */
+#ifndef ZOPT_B200_H
+#define ZOPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ZB_API __attribute__((visibility("default")))
+#else
+#define ZB_API
+#endif
+
+#define ZB_F32 0
+#define ZB_F64 1
+
+#define ZB_MAX_N 16 /* generic kernels: state dimension limit */
+#define ZB_MAX_M 8  /* generic kernels: control dimension limit */
+
+/* strided view of a batch (and optionally a time series) of dense row-major blocks */
+typedef struct zb_arr {
+    const void* ptr;  /* device pointer to block [b=0][k=0] */
+    int64_t stride_b; /* elements between consecutive problems; 0 = shared by the whole batch */
+    int64_t stride_t; /* elements between consecutive time steps; 0 = time-invariant */
+} zb_arr;
+
+/* dynamics model of the iLQR/DDP/rollout entry points (the reference takes a Python callable,
+ * ilqrUtils.py:260-268; a kernel cannot trace a lambda, so models are registered kinds) */
+#define ZB_MODEL_LINEAR 0    /* x+ = A x + B u            (tests/test_ilqrUtils.py:167-196) */
+#define ZB_MODEL_QUADCOPTER 1 /* x+ = x + dt*inertialDynamics(x,u,wind)  (zopt/quadcopter.py:116-144, demos/iterativeLqr.py:35) */
+
+typedef struct zb_model {
+    int32_t kind;  /* ZB_MODEL_* */
+    int32_t n, m;  /* state / control dimension (quadcopter: 12, 4) */
+    int32_t has_wind;
+    double dt;         /* quadcopter: Euler step */
+    double wind[3];    /* quadcopter: wind_ned */
+    zb_arr A, B;       /* linear: (n,n) and (n,m) blocks, stride_t ignored */
+} zb_model;
+
+/* cost of the iLQR/DDP entry points: running x'Qx + u'Ru, terminal x'Qf x (demos/iterativeLqr.py:12-13,36-37) */
+typedef struct zb_cost {
+    zb_arr Q, R, Qf; /* (n,n), (m,m), (n,n) blocks, stride_t ignored */
+} zb_cost;
+
+ZB_API int32_t zb_version(void);
+ZB_API int32_t zb_last_error(char* buf, size_t len);
+/* number of SMs / device name probe (used by bench.py to size batches) */
+ZB_API int32_t zb_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, size_t* total_mem);
+
+/* ---- zopt/lqrUtils.py:144-173  discreteFiniteHorizonLqr(A,B,Q,R,N) -> L -------------------------
+ * A,B,Q,R are time series with T >= N rows; terminal value is row T-1 of Q (lqrUtils.py:172).
+ * L_out (Bsz,N,m,n); V0_out (Bsz,n,n) optional (NULL to skip): value matrix after the last step. */
+ZB_API int32_t zb_lqr_dfh(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
+                   int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, void* L_out,
+                   void* V0_out);
+
+/* ---- zopt/lqrUtils.py:207-262  bilinearAffineLqr(A,B,d,Q,R,H,q,r,q0,N) -> (L,l) ------------------
+ * L_out (Bsz,N,m,n), l_out (Bsz,N,m). */
+ZB_API int32_t zb_lqr_bilinear(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
+                        int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* d, const zb_arr* Q,
+                        const zb_arr* R, const zb_arr* H, const zb_arr* q, const zb_arr* r, const zb_arr* q0,
+                        void* L_out, void* l_out);
+
+/* ---- zopt/quadcopter.py:116-144 inertialDynamics, :179-201 linearize (12-state form used by
+ * demos/lqrMpc.py:26-28 and demos/iterativeLqr.py:35) -------------------------------------------
+ * x (Bsz,12), u (Bsz,4) contiguous.  xdot_out (Bsz,12) = F(x,u,wind).
+ * linearize: A_out (Bsz,12,12) = I*(dt!=0) + (dt?dt:1)*dF/dx ; B_out (Bsz,12,4) = (dt?dt:1)*dF/du.
+ * hess: H_out (Bsz,12,12) = sum_i lam_i d2F_i/dx2 (times dt if dt != 0). */
+ZB_API int32_t zb_quad_dynamics(int32_t dtype, int32_t device, void* stream, int64_t Bsz, const void* x, const void* u,
+                         const double* wind_ned /* host, 3 values or NULL */, void* xdot_out);
+ZB_API int32_t zb_quad_linearize(int32_t dtype, int32_t device, void* stream, int64_t Bsz, const void* x, const void* u,
+                          const double* wind_ned, double dt, void* A_out, void* B_out);
+ZB_API int32_t zb_quad_hess_contract(int32_t dtype, int32_t device, void* stream, int64_t Bsz, const void* x,
+                              const void* u, const double* wind_ned, double dt, const void* lam, void* H_out);
+
+/* ---- zopt/ilqrUtils.py:33-66 trajectoryRollout + pytrees.py:215-220 AffinePolicy.__call__ --------
+ * u_k = alpha*l_k + L_k (x_k - xPrev_k) + uPrev_k ; x_{k+1} = f(x_k,u_k).
+ * x0 (Bsz,n); l (Bsz,N,m); L (Bsz,N,m,n); xPrev (Bsz,N+1,n); uPrev (Bsz,N,m); alpha host scalar.
+ * Outputs xTraj (Bsz,N+1,n), uTraj (Bsz,N,m); J_out optional (Bsz): cost of the rollout under `cost`
+ * (pytrees.py:40-55), cost may be NULL when J_out is NULL. */
+ZB_API int32_t zb_ilqr_rollout(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, const zb_model* model,
+                        const zb_cost* cost, const void* x0, const void* l, const void* L, const void* xPrev,
+                        const void* uPrev, double alpha, void* xTraj, void* uTraj, void* J_out);
+
+/* ---- zopt/ilqrUtils.py:116-150 forwardPass2: 16 rollouts at alpha = 0.5^j, argmin of the cost ----
+ * J_out (Bsz), alpha_idx_out (Bsz) int32 (optional), Jall_out (Bsz,16) optional. */
+ZB_API int32_t zb_ilqr_forward_pass(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N,
+                             const zb_model* model, const zb_cost* cost, const void* x0, const void* l,
+                             const void* L, const void* xPrev, const void* uPrev, void* xTraj, void* uTraj,
+                             void* J_out, int32_t* alpha_idx_out, void* Jall_out);
+
+/* ---- zopt/ilqrUtils.py:153-181 riccatiStep_ilqr/backwardPass_ilqr, :184-214 _ddp ------------------
+ * Explicit-pytree form (stacked AffineDynamics / QuadraticCostFunction / QuadraticValueFunction leaves,
+ * pytrees.py:84-204).  second_order != 0 adds the eigen-clamped v_x.f_zz block (ilqrUtils.py:237-251);
+ * f_xx (n,n,n), f_ux (n,m,n), f_uu (n,m,m) blocks then required.
+ * Outputs: l_out (Bsz,N,m), L_out (Bsz,N,m,n); optional value function after the last step:
+ * v_out (Bsz), vx_out (Bsz,n), vxx_out (Bsz,n,n). */
+ZB_API int32_t zb_ilqr_backward(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t n, int32_t m,
+                         int32_t second_order, const zb_arr* f_x, const zb_arr* f_u, const zb_arr* f_xx,
+                         const zb_arr* f_ux, const zb_arr* f_uu, const zb_arr* c, const zb_arr* c_x,
+                         const zb_arr* c_u, const zb_arr* c_xx, const zb_arr* c_ux, const zb_arr* c_uu,
+                         const zb_arr* v, const zb_arr* v_x, const zb_arr* v_xx, void* l_out, void* L_out,
+                         void* v_out, void* vx_out, void* vxx_out);
+
+/* ---- zopt/ilqrUtils.py:217-219 ensurePositiveDefinite: V max(eig,eps) V' of symmetric (p,p) blocks,
+ * p <= ZB_MAX_N + ZB_MAX_M.  in/out (Bsz,p,p) contiguous (may alias). */
+ZB_API int32_t zb_pd_clamp(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t p, double eps, const void* in,
+                    void* out);
+
+/* ---- zopt/ilqrUtils.py:260-327 iterativeLqr, :330-397 differentialDynamicProgramming -------------
+ * Whole solve for a registered model/cost: initial rollout, then up to maxIter iterations of
+ * {linearise along the trajectory, condition, backward pass, 16-way forward pass}; per-problem
+ * convergence |J - J_new| <= tol freezes that problem (ilqrUtils.py:301-303,318).
+ * x0 (Bsz,n), uGuess (Bsz,N,m).  Outputs xTraj (Bsz,N+1,n), uTraj (Bsz,N,m), L_out (Bsz,N,m,n),
+ * J_out (Bsz), converged_out (Bsz) uint8, iters_out (Bsz) int32,
+ * alpha_log (Bsz,maxIter) int32 optional (-1 = iteration not run), J_log (Bsz,maxIter+1) optional.
+ * workspace: device scratch of zb_ilqr_workspace_bytes(...) bytes. */
+ZB_API size_t zb_ilqr_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m);
+ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t second_order,
+                      const zb_model* model, const zb_cost* cost, const void* x0, const void* uGuess,
+                      int32_t maxIter, double tol, void* xTraj, void* uTraj, void* L_out, void* J_out,
+                      uint8_t* converged_out, int32_t* iters_out, int32_t* alpha_log, void* J_log,
+                      void* workspace, size_t workspace_bytes);
+
+/* ---- zopt/mpcUtils.py:12-81 lqrMpc(A,B,Q,R,N,x_lb,x_ub,u_lb,u_ub,Qf).solve(x0) --------------------
+ * min sum_{k<N} x'Qx + u'Ru + x_N'Qf x_N  s.t. x+ = Ax + Bu, x_lb<=x_k<=x_ub (k=0..N), u_lb<=u_k<=u_ub.
+ * Bounds may be +-inf.  When no bound can bind the solve is the exact Riccati sweep + rollout;
+ * otherwise ADMM (the OSQP splitting) whose linear solve is a Riccati sweep.
+ * status_out (Bsz) int8: 0 optimal, 1 optimal_inaccurate (max_iter hit), 2 infeasible.
+ * iters_out (Bsz) int32 ADMM iterations (0 on the unconstrained path). */
+typedef struct zb_admm_opts {
+    int32_t max_iter;   /* default 4000 */
+    int32_t check_every; /* default 25 */
+    double rho, sigma, alpha; /* 0.1, 1e-6, 1.6 */
+    double eps_abs, eps_rel;   /* 1e-3, 1e-3 */
+} zb_admm_opts;
+ZB_API size_t zb_mpc_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m);
+ZB_API int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t n, int32_t m,
+                         const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, const zb_arr* Qf,
+                         const zb_arr* x_lb, const zb_arr* x_ub, const zb_arr* u_lb, const zb_arr* u_ub,
+                         int32_t bounded, const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj,
+                         void* uTraj, int8_t* status_out, int32_t* iters_out, void* workspace,
+                         size_t workspace_bytes);
+
+/* ---- roofline denominators: dependent-FMA throughput probe; returns achieved FLOP/s ------------ */
+ZB_API int32_t zb_peak_fma(int32_t dtype, int32_t device, double* flops_per_s_out, double* sm_clock_mhz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZOPT_B200_H */

@@ -91,7 +91,8 @@ def backwardPass_ilqr(dynamics, cost, Vf):  # ilqrUtils.py:176-181
 
 
 def ensurePositiveDefinite(a, eps=1e-3):  # ilqrUtils.py:217-219
-    w, v = torch.linalg.eigh(a)
+    # jnp.linalg.eigh defaults to symmetrize_input=True, i.e. it factors (a + a^T)/2
+    w, v = torch.linalg.eigh(0.5 * (a + a.T))
     return (v * torch.clamp(w, min=eps)) @ v.T
 
 

@@ -1,0 +1,618 @@
+// C ABI entry points (include/zopt_b200.h) and the generic one-thread-per-problem kernels.
+// The (n,m)=(12,4) fast kernels live in lqr_fast.cuh / ilqr_fast.cuh and are dispatched from here.
+#include "zb_common.cuh"
+#include "lqr_fast.cuh"
+
+using namespace zb;
+
+// =================================================================================================
+// generic kernels: one thread per problem
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_lqr_generic(LqrP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b < P.Bsz) lqr_problem<T>(P, b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_bilinear_generic(BilinP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b < P.Bsz) bilinear_problem<T>(P, b);
+}
+
+struct QuadP {
+    long long Bsz;
+    const void *x, *u, *lam;
+    void *o1, *o2;
+    double dt, wind[3];
+    int has_wind;
+};
+
+template <typename T>
+__global__ void k_quad_dynamics(QuadP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= P.Bsz) return;
+    T x[12], u[4], xd[12], w[3] = {T(P.wind[0]), T(P.wind[1]), T(P.wind[2])};
+    for (int i = 0; i < 12; ++i) x[i] = reinterpret_cast<const T*>(P.x)[b * 12 + i];
+    for (int i = 0; i < 4; ++i) u[i] = reinterpret_cast<const T*>(P.u)[b * 4 + i];
+    quad_F<T>(x, u, w, P.has_wind != 0, xd);
+    for (int i = 0; i < 12; ++i) reinterpret_cast<T*>(P.o1)[b * 12 + i] = xd[i];
+}
+
+template <typename T>
+__global__ void k_quad_linearize(QuadP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= P.Bsz) return;
+    T x[12], u[4], fx[144], fu[48], w[3] = {T(P.wind[0]), T(P.wind[1]), T(P.wind[2])};
+    for (int i = 0; i < 12; ++i) x[i] = reinterpret_cast<const T*>(P.x)[b * 12 + i];
+    for (int i = 0; i < 4; ++i) u[i] = reinterpret_cast<const T*>(P.u)[b * 4 + i];
+    quad_lin<T>(x, u, w, P.has_wind != 0, T(P.dt), fx, fu);
+    T* A = reinterpret_cast<T*>(P.o1) + b * 144;
+    for (int i = 0; i < 144; ++i) A[i] = fx[i];
+    if (P.o2) {
+        T* B = reinterpret_cast<T*>(P.o2) + b * 48;
+        for (int i = 0; i < 48; ++i) B[i] = fu[i];
+    }
+}
+
+template <typename T>
+__global__ void k_quad_hess(QuadP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= P.Bsz) return;
+    T x[12], u[4], lam[12], H[144], w[3] = {T(P.wind[0]), T(P.wind[1]), T(P.wind[2])};
+    for (int i = 0; i < 12; ++i) x[i] = reinterpret_cast<const T*>(P.x)[b * 12 + i];
+    for (int i = 0; i < 4; ++i) u[i] = reinterpret_cast<const T*>(P.u)[b * 4 + i];
+    for (int i = 0; i < 12; ++i) lam[i] = reinterpret_cast<const T*>(P.lam)[b * 12 + i];
+    quad_hess<T>(x, u, w, P.has_wind != 0, T(P.dt), lam, H);
+    T* o = reinterpret_cast<T*>(P.o1) + b * 144;
+    for (int i = 0; i < 144; ++i) o[i] = H[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_rollout(RollP P, double alpha) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= P.Bsz) return;
+    T J = rollout_core<T>(P, b, T(alpha), true);
+    if (P.J) reinterpret_cast<T*>(P.J)[b] = J;
+}
+
+// forwardPass2 phase 1: 16 threads per problem, one step size each, cost only (ilqrUtils.py:139-146)
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_forward_costs(RollP P, void* Jall, const uint8_t* done) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long b = t >> 4;
+    int j = (int)(t & 15);
+    if (b >= P.Bsz) return;
+    if (done && done[b]) return;
+    T alpha = T(1);
+    for (int i = 0; i < j; ++i) alpha *= T(0.5);  // 0.5**j exactly (ilqrUtils.py:145)
+    T J = rollout_core<T>(P, b, alpha, false);
+    reinterpret_cast<T*>(Jall)[b * 16 + j] = J;
+}
+
+// forwardPass2 phase 2: argmin over the 16 costs, re-run the winning rollout and store it
+// (ilqrUtils.py:147-150), plus the solver's bookkeeping (ilqrUtils.py:318-321) when `S.J` is set.
+struct CommitP {
+    void* J;             // (Bsz) current cost, updated in place (null for the bare forwardPass2 entry point)
+    uint8_t* converged;  // (Bsz)
+    int32_t* iters;      // (Bsz)
+    int32_t* alpha_log;  // (Bsz,maxIter) or null
+    void* J_log;         // (Bsz,maxIter+1) or null
+    int it, maxIter;
+    double tol;
+    void* J_out;         // bare entry point: (Bsz)
+    int32_t* idx_out;    // bare entry point: (Bsz) or null
+};
+
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_forward_commit(RollP P, const void* Jall, CommitP S) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= P.Bsz) return;
+    if (S.converged && S.J && S.converged[b]) return;
+    const T* Ja = reinterpret_cast<const T*>(Jall) + b * 16;
+    int idx = argmin16<T>(Ja);
+    T alpha = T(1);
+    for (int i = 0; i < idx; ++i) alpha *= T(0.5);
+    rollout_core<T>(P, b, alpha, true);
+    T Jn = Ja[idx];
+    if (S.J) {
+        T* J = reinterpret_cast<T*>(S.J);
+        T dJ = J[b] - Jn;
+        S.converged[b] = (fabs(dJ) <= T(S.tol)) ? 1 : 0;  // NaN compares false, as in the reference
+        J[b] = Jn;
+        S.iters[b] = S.it + 1;
+        if (S.alpha_log) S.alpha_log[b * (long long)S.maxIter + S.it] = idx;
+        if (S.J_log) reinterpret_cast<T*>(S.J_log)[b * (long long)(S.maxIter + 1) + S.it + 1] = Jn;
+    } else {
+        reinterpret_cast<T*>(S.J_out)[b] = Jn;
+        if (S.idx_out) S.idx_out[b] = idx;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_backward(BackP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b < P.Bsz) backward_problem<T>(P, b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_pd_clamp(long long Bsz, int p, double eps, const void* in, void* out) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= Bsz) return;
+    T S[ZB_PD_MAX * ZB_PD_MAX], W[ZB_PD_MAX * ZB_PD_MAX];
+    const T* src = reinterpret_cast<const T*>(in) + b * (long long)p * p;
+    for (int i = 0; i < p * p; ++i) S[i] = src[i];
+    pd_clamp<T>(S, W, p, T(eps));
+    T* dst = reinterpret_cast<T*>(out) + b * (long long)p * p;
+    for (int i = 0; i < p * p; ++i) dst[i] = S[i];
+}
+
+// iLQR/DDP solve: conditioned cost blocks (ilqrUtils.py:312-313), constant for quadratic costs
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_solve_prep(long long Bsz, int n, int m, Cost C, double eps, void* Czz, void* Vfxx) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= Bsz) return;
+    const int p = n + m;
+    T S[ZB_PD_MAX * ZB_PD_MAX], W[ZB_PD_MAX * ZB_PD_MAX];
+    const T* Q = C.Q.at<T>(b);
+    const T* R = C.R.at<T>(b);
+    const T* Qf = C.Qf.at<T>(b);
+    for (int i = 0; i < p * p; ++i) S[i] = T(0);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) S[i * p + j] = Q[i * n + j] + Q[j * n + i];
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) S[(n + i) * p + n + j] = R[i * m + j] + R[j * m + i];
+    pd_clamp<T>(S, W, p, T(eps));
+    T* o = reinterpret_cast<T*>(Czz) + b * (long long)p * p;
+    for (int i = 0; i < p * p; ++i) o[i] = S[i];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) S[i * n + j] = Qf[i * n + j] + Qf[j * n + i];
+    pd_clamp<T>(S, W, n, T(eps));
+    o = reinterpret_cast<T*>(Vfxx) + b * (long long)n * n;
+    for (int i = 0; i < n * n; ++i) o[i] = S[i];
+}
+
+// initial rollout u_k = uGuess_k (ilqrUtils.py:292-298) and solver state initialisation
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_solve_init(RollP P, const void* uGuess, void* J, uint8_t* converged, int32_t* iters,
+                             int32_t* alpha_log, void* J_log, int maxIter) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= P.Bsz) return;
+    const int n = P.M.n, m = P.M.m, N = P.N;
+    const T* x0 = reinterpret_cast<const T*>(P.x0) + b * n;
+    const T* ug = reinterpret_cast<const T*>(uGuess) + b * (long long)N * m;
+    T* xT = reinterpret_cast<T*>(P.xTraj) + b * (long long)(N + 1) * n;
+    T* uT = reinterpret_cast<T*>(P.uTraj) + b * (long long)N * m;
+    const T* Q = P.C.Q.at<T>(b);
+    const T* R = P.C.R.at<T>(b);
+    T x[NX], u[NU];
+    T Jc = T(0);
+    for (int i = 0; i < n; ++i) x[i] = x0[i];
+    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < m; ++i) u[i] = ug[(long long)k * m + i];
+        for (int i = 0; i < n; ++i) xT[(long long)k * n + i] = x[i];
+        for (int i = 0; i < m; ++i) uT[(long long)k * m + i] = u[i];
+        Jc += quad_form<T>(Q, x, n) + quad_form<T>(R, u, m);
+        model_step<T>(P.M, b, x, u, x);
+    }
+    for (int i = 0; i < n; ++i) xT[(long long)N * n + i] = x[i];
+    Jc += quad_form<T>(P.C.Qf.at<T>(b), x, n);
+    reinterpret_cast<T*>(J)[b] = Jc;
+    converged[b] = 0;
+    iters[b] = 0;
+    if (alpha_log)
+        for (int i = 0; i < maxIter; ++i) alpha_log[b * (long long)maxIter + i] = -1;
+    if (J_log) {
+        T* jl = reinterpret_cast<T*>(J_log) + b * (long long)(maxIter + 1);
+        jl[0] = Jc;
+        for (int i = 1; i <= maxIter; ++i) jl[i] = Jc * T(0) + T(NAN);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_solve_backward(SolveBackP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b < P.Bsz) solve_backward_problem<T>(P, b);
+}
+
+// lqrMpc.solve without active bounds: exact Riccati sweep + linear rollout (mpcUtils.py:47-59)
+struct MpcP {
+    long long Bsz;
+    int N, n, m;
+    Arr A, B, Q, R, Qf;
+    const void* x0;
+    void *u0, *xTraj, *uTraj, *gains;  // gains: workspace (Bsz,N,m,n)
+    int8_t* status;
+    int32_t* iters;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_mpc_riccati(MpcP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= P.Bsz) return;
+    const int n = P.n, m = P.m, N = P.N;
+    const T *A = P.A.at<T>(b), *B = P.B.at<T>(b), *Q = P.Q.at<T>(b), *R = P.R.at<T>(b), *Qf = P.Qf.at<T>(b);
+    T V[NX * NX], L[NU * NX];
+    for (int i = 0; i < n * n; ++i) V[i] = Qf[i];
+    T* G = reinterpret_cast<T*>(P.gains) + b * (long long)N * m * n;
+    for (int k = N - 1; k >= 0; --k) {
+        lqr_joseph_step<T>(n, m, A, B, Q, R, V, L);
+        for (int i = 0; i < m * n; ++i) G[(long long)k * m * n + i] = L[i];
+    }
+    const T* x0 = reinterpret_cast<const T*>(P.x0) + b * n;
+    T* xT = reinterpret_cast<T*>(P.xTraj) + b * (long long)(N + 1) * n;
+    T* uT = reinterpret_cast<T*>(P.uTraj) + b * (long long)N * m;
+    T x[NX], u[NU], xn[NX];
+    for (int i = 0; i < n; ++i) x[i] = x0[i];
+    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < n; ++i) xT[(long long)k * n + i] = x[i];
+        for (int i = 0; i < m; ++i) {
+            T s = T(0);
+            for (int j = 0; j < n; ++j) s += G[((long long)k * m + i) * n + j] * x[j];
+            u[i] = -s;
+            uT[(long long)k * m + i] = u[i];
+        }
+        for (int i = 0; i < n; ++i) {
+            T s = T(0);
+            for (int j = 0; j < n; ++j) s += A[i * n + j] * x[j];
+            for (int j = 0; j < m; ++j) s += B[i * m + j] * u[j];
+            xn[i] = s;
+        }
+        for (int i = 0; i < n; ++i) x[i] = xn[i];
+    }
+    for (int i = 0; i < n; ++i) xT[(long long)N * n + i] = x[i];
+    T* u0 = reinterpret_cast<T*>(P.u0) + b * m;
+    for (int i = 0; i < m; ++i) u0[i] = uT[i];
+    P.status[b] = 0;
+    if (P.iters) P.iters[b] = 0;
+}
+
+// dependent-FMA throughput probe (roofline denominator)
+template <typename T, int ILP>
+__global__ void k_peak_fma(T* out, int iters) {
+    T a[ILP];
+    const T b = T(1.0000001), c = T(1e-7);
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) a[i] = T(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) a[i] = a[i] * b + c;
+    }
+    T s = T(0);
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += a[i];
+    if (s == T(-1)) out[0] = s;
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#define ZB_DISPATCH(dtype, KERNEL, grid, block, stream, ...)                              \
+    do {                                                                                    \
+        if ((dtype) == ZB_F32) KERNEL<float><<<(grid), (block), 0, (cudaStream_t)(stream)>>>(__VA_ARGS__);  \
+        else KERNEL<double><<<(grid), (block), 0, (cudaStream_t)(stream)>>>(__VA_ARGS__);   \
+        ZB_CUDA(cudaGetLastError());                                                        \
+    } while (0)
+
+extern "C" {
+
+int32_t zb_version(void) { return 100; }
+
+int32_t zb_last_error(char* buf, size_t len) {
+    if (!buf || len == 0) return -1;
+    strncpy(buf, err_buf(), len - 1);
+    buf[len - 1] = 0;
+    return 0;
+}
+
+int32_t zb_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, size_t* total_mem) {
+    cudaDeviceProp p;
+    ZB_CUDA(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return 0;
+}
+
+int32_t zb_lqr_dfh(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
+                   int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, void* L_out,
+                   void* V0_out) {
+    int32_t rc = check_dims(dtype, Bsz, n, m);
+    if (rc) return rc;
+    ZB_ARG(N >= 0 && T >= 1 && T >= N, "need T >= N >= 0 and T >= 1 (got N=%d, T=%d)", N, T);
+    ZB_ARG(A && B && Q && R && A->ptr && B->ptr && Q->ptr && R->ptr, "A, B, Q, R must be non-NULL");
+    ZB_ARG(L_out != nullptr || N == 0, "L_out is NULL");
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    LqrP P{Bsz, N, T, n, m, to_arr(A), to_arr(B), to_arr(Q), to_arr(R), L_out, V0_out};
+    if (lqr_fast_eligible(dtype, P)) return lqr_fast_launch(dtype, P, (cudaStream_t)stream);
+    ZB_DISPATCH(dtype, k_lqr_generic, gen_grid(Bsz), GEN_THREADS, stream, P);
+    return 0;
+}
+
+int32_t zb_lqr_bilinear(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
+                        int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* d, const zb_arr* Q,
+                        const zb_arr* R, const zb_arr* H, const zb_arr* q, const zb_arr* r, const zb_arr* q0,
+                        void* L_out, void* l_out) {
+    int32_t rc = check_dims(dtype, Bsz, n, m);
+    if (rc) return rc;
+    ZB_ARG(N >= 0 && T >= 1 && T >= N, "need T >= N >= 0 and T >= 1 (got N=%d, T=%d)", N, T);
+    ZB_ARG(A && B && d && Q && R && H && q && r && q0, "NULL operand");
+    ZB_ARG(A->ptr && B->ptr && d->ptr && Q->ptr && R->ptr && H->ptr && q->ptr && r->ptr && q0->ptr, "NULL operand pointer");
+    ZB_ARG((L_out && l_out) || N == 0, "NULL output");
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    BilinP P{Bsz, N, T, n, m, to_arr(A), to_arr(B), to_arr(d), to_arr(Q), to_arr(R), to_arr(H), to_arr(q), to_arr(r),
+             to_arr(q0), L_out, l_out};
+    ZB_DISPATCH(dtype, k_bilinear_generic, gen_grid(Bsz), GEN_THREADS, stream, P);
+    return 0;
+}
+
+static int32_t quad_common(int32_t dtype, int64_t Bsz, const void* x, const void* u, const double* wind, QuadP& P) {
+    ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "bad dtype %d", dtype);
+    ZB_ARG(Bsz >= 0, "negative batch size");
+    ZB_ARG(x && u, "x/u NULL");
+    P.Bsz = Bsz;
+    P.x = x;
+    P.u = u;
+    P.lam = nullptr;
+    P.o1 = P.o2 = nullptr;
+    P.dt = 0;
+    P.has_wind = 0;
+    for (int i = 0; i < 3; ++i) {
+        P.wind[i] = wind ? wind[i] : 0.0;
+        if (P.wind[i] != 0.0) P.has_wind = 1;
+    }
+    return 0;
+}
+
+int32_t zb_quad_dynamics(int32_t dtype, int32_t device, void* stream, int64_t Bsz, const void* x, const void* u,
+                         const double* wind_ned, void* xdot_out) {
+    QuadP P;
+    int32_t rc = quad_common(dtype, Bsz, x, u, wind_ned, P);
+    if (rc) return rc;
+    ZB_ARG(xdot_out, "output NULL");
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    P.o1 = xdot_out;
+    ZB_DISPATCH(dtype, k_quad_dynamics, (unsigned)((Bsz + 127) / 128), 128, stream, P);
+    return 0;
+}
+
+int32_t zb_quad_linearize(int32_t dtype, int32_t device, void* stream, int64_t Bsz, const void* x, const void* u,
+                          const double* wind_ned, double dt, void* A_out, void* B_out) {
+    QuadP P;
+    int32_t rc = quad_common(dtype, Bsz, x, u, wind_ned, P);
+    if (rc) return rc;
+    ZB_ARG(A_out, "A_out NULL");
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    P.o1 = A_out;
+    P.o2 = B_out;
+    P.dt = dt;
+    ZB_DISPATCH(dtype, k_quad_linearize, (unsigned)((Bsz + 63) / 64), 64, stream, P);
+    return 0;
+}
+
+int32_t zb_quad_hess_contract(int32_t dtype, int32_t device, void* stream, int64_t Bsz, const void* x,
+                              const void* u, const double* wind_ned, double dt, const void* lam, void* H_out) {
+    QuadP P;
+    int32_t rc = quad_common(dtype, Bsz, x, u, wind_ned, P);
+    if (rc) return rc;
+    ZB_ARG(lam && H_out, "lam/H_out NULL");
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    P.o1 = H_out;
+    P.lam = lam;
+    P.dt = dt;
+    ZB_DISPATCH(dtype, k_quad_hess, (unsigned)((Bsz + 63) / 64), 64, stream, P);
+    return 0;
+}
+
+static int32_t roll_common(int32_t dtype, int64_t Bsz, int32_t N, const zb_model* model, const zb_cost* cost,
+                           bool need_cost, RollP& P) {
+    ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "bad dtype %d", dtype);
+    ZB_ARG(Bsz >= 0 && N >= 0, "negative size");
+    int32_t rc = to_model(model, P.M);
+    if (rc) return rc;
+    P.Bsz = Bsz;
+    P.N = N;
+    P.C = to_cost(cost);
+    P.has_cost = (cost != nullptr);
+    if (need_cost) ZB_ARG(cost && cost->Q.ptr && cost->R.ptr && cost->Qf.ptr, "cost (Q,R,Qf) required");
+    return 0;
+}
+
+int32_t zb_ilqr_rollout(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, const zb_model* model,
+                        const zb_cost* cost, const void* x0, const void* l, const void* L, const void* xPrev,
+                        const void* uPrev, double alpha, void* xTraj, void* uTraj, void* J_out) {
+    RollP P;
+    int32_t rc = roll_common(dtype, Bsz, N, model, cost, J_out != nullptr, P);
+    if (rc) return rc;
+    ZB_ARG(x0 && xTraj && (N == 0 || (l && L && xPrev && uPrev && uTraj)), "NULL operand");
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    P.x0 = x0; P.l = l; P.L = L; P.xPrev = xPrev; P.uPrev = uPrev;
+    P.xTraj = xTraj; P.uTraj = uTraj; P.J = J_out;
+    if (!J_out) P.has_cost = 0;
+    ZB_DISPATCH(dtype, k_rollout, gen_grid(Bsz), GEN_THREADS, stream, P, alpha);
+    return 0;
+}
+
+int32_t zb_ilqr_forward_pass(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N,
+                             const zb_model* model, const zb_cost* cost, const void* x0, const void* l,
+                             const void* L, const void* xPrev, const void* uPrev, void* xTraj, void* uTraj,
+                             void* J_out, int32_t* alpha_idx_out, void* Jall_out) {
+    RollP P;
+    int32_t rc = roll_common(dtype, Bsz, N, model, cost, true, P);
+    if (rc) return rc;
+    ZB_ARG(x0 && xTraj && J_out && Jall_out && (N == 0 || (l && L && xPrev && uPrev && uTraj)), "NULL operand");
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    P.x0 = x0; P.l = l; P.L = L; P.xPrev = xPrev; P.uPrev = uPrev;
+    P.xTraj = xTraj; P.uTraj = uTraj; P.J = nullptr;
+    ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall_out, (const uint8_t*)nullptr);
+    CommitP S{};
+    S.J_out = J_out;
+    S.idx_out = alpha_idx_out;
+    ZB_DISPATCH(dtype, k_forward_commit, gen_grid(Bsz), GEN_THREADS, stream, P, (const void*)Jall_out, S);
+    return 0;
+}
+
+int32_t zb_ilqr_backward(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t n, int32_t m,
+                         int32_t second_order, const zb_arr* f_x, const zb_arr* f_u, const zb_arr* f_xx,
+                         const zb_arr* f_ux, const zb_arr* f_uu, const zb_arr* c, const zb_arr* c_x,
+                         const zb_arr* c_u, const zb_arr* c_xx, const zb_arr* c_ux, const zb_arr* c_uu,
+                         const zb_arr* v, const zb_arr* v_x, const zb_arr* v_xx, void* l_out, void* L_out,
+                         void* v_out, void* vx_out, void* vxx_out) {
+    int32_t rc = check_dims(dtype, Bsz, n, m);
+    if (rc) return rc;
+    ZB_ARG(N >= 0, "negative N");
+    ZB_ARG(f_x && f_u && c && c_x && c_u && c_xx && c_ux && c_uu && v && v_x && v_xx, "NULL operand");
+    ZB_ARG(!second_order || (f_xx && f_ux && f_uu && f_xx->ptr && f_ux->ptr && f_uu->ptr), "DDP needs f_xx, f_ux, f_uu");
+    ZB_ARG((l_out && L_out) || N == 0, "NULL output");
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    BackP P{Bsz, N, n, m, second_order, to_arr(f_x), to_arr(f_u), to_arr(f_xx), to_arr(f_ux), to_arr(f_uu), to_arr(c),
+            to_arr(c_x), to_arr(c_u), to_arr(c_xx), to_arr(c_ux), to_arr(c_uu), to_arr(v), to_arr(v_x), to_arr(v_xx),
+            l_out, L_out, v_out, vx_out, vxx_out, 1e-3};
+    ZB_DISPATCH(dtype, k_backward, gen_grid(Bsz), GEN_THREADS, stream, P);
+    return 0;
+}
+
+int32_t zb_pd_clamp(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t p, double eps, const void* in,
+                    void* out) {
+    ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "bad dtype %d", dtype);
+    ZB_ARG(p >= 1 && p <= ZB_PD_MAX, "p must be in [1,%d] (got %d)", ZB_PD_MAX, p);
+    ZB_ARG(Bsz >= 0 && in && out, "bad operand");
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    ZB_DISPATCH(dtype, k_pd_clamp, gen_grid(Bsz), GEN_THREADS, stream, (long long)Bsz, p, eps, in, out);
+    return 0;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t zb_ilqr_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m) {
+    size_t e = dtype == ZB_F64 ? 8 : 4;
+    size_t p = (size_t)(n + m);
+    return align256(e * Bsz * N * m) + align256(e * Bsz * 16) + align256(e * Bsz * p * p) + align256(e * Bsz * n * n) + 256;
+}
+
+int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t second_order,
+                      const zb_model* model, const zb_cost* cost, const void* x0, const void* uGuess,
+                      int32_t maxIter, double tol, void* xTraj, void* uTraj, void* L_out, void* J_out,
+                      uint8_t* converged_out, int32_t* iters_out, int32_t* alpha_log, void* J_log,
+                      void* workspace, size_t workspace_bytes) {
+    RollP P;
+    int32_t rc = roll_common(dtype, Bsz, N, model, cost, true, P);
+    if (rc) return rc;
+    ZB_ARG(maxIter >= 0, "negative maxIter");
+    ZB_ARG(x0 && uGuess && xTraj && uTraj && L_out && J_out && converged_out && iters_out, "NULL operand");
+    const int n = P.M.n, m = P.M.m, p = n + m;
+    size_t need = zb_ilqr_workspace_bytes(dtype, Bsz, N, n, m);
+    ZB_ARG(workspace && workspace_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    const size_t e = dtype == ZB_F64 ? 8 : 4;
+    char* w = reinterpret_cast<char*>(workspace);
+    void* l_ws = w;  w += align256(e * Bsz * N * m);
+    void* Jall = w;  w += align256(e * Bsz * 16);
+    void* Czz = w;   w += align256(e * Bsz * p * p);
+    void* Vfxx = w;
+    cudaStream_t s = (cudaStream_t)stream;
+    // policy.L = 0 before the first iteration (ilqrUtils.py:293)
+    ZB_CUDA(cudaMemsetAsync(L_out, 0, e * Bsz * N * m * n, s));
+    P.x0 = x0; P.l = l_ws; P.L = L_out; P.xPrev = xTraj; P.uPrev = uTraj;
+    P.xTraj = xTraj; P.uTraj = uTraj; P.J = nullptr;
+    ZB_DISPATCH(dtype, k_solve_prep, gen_grid(Bsz), GEN_THREADS, stream, (long long)Bsz, n, m, P.C, 1e-3, Czz, Vfxx);
+    ZB_DISPATCH(dtype, k_solve_init, gen_grid(Bsz), GEN_THREADS, stream, P, uGuess, J_out, converged_out, iters_out,
+                alpha_log, J_log, (int)maxIter);
+    SolveBackP Bk{Bsz, N, second_order, P.M, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
+    for (int it = 0; it < maxIter; ++it) {
+        ZB_DISPATCH(dtype, k_solve_backward, gen_grid(Bsz), GEN_THREADS, stream, Bk);
+        ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall, (const uint8_t*)converged_out);
+        CommitP S{J_out, converged_out, iters_out, alpha_log, J_log, it, (int)maxIter, tol, nullptr, nullptr};
+        ZB_DISPATCH(dtype, k_forward_commit, gen_grid(Bsz), GEN_THREADS, stream, P, (const void*)Jall, S);
+    }
+    return 0;
+}
+
+size_t zb_mpc_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m) {
+    size_t e = dtype == ZB_F64 ? 8 : 4;
+    return align256(e * Bsz * N * m * n) + 256;
+}
+
+int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t n, int32_t m,
+                         const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, const zb_arr* Qf,
+                         const zb_arr* x_lb, const zb_arr* x_ub, const zb_arr* u_lb, const zb_arr* u_ub,
+                         int32_t bounded, const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj,
+                         void* uTraj, int8_t* status_out, int32_t* iters_out, void* workspace,
+                         size_t workspace_bytes) {
+    int32_t rc = check_dims(dtype, Bsz, n, m);
+    if (rc) return rc;
+    ZB_ARG(N >= 1, "N must be >= 1");
+    ZB_ARG(A && B && Q && R && Qf && A->ptr && B->ptr && Q->ptr && R->ptr && Qf->ptr, "NULL operand");
+    ZB_ARG(x0 && u0_out && xTraj && uTraj && status_out, "NULL operand");
+    size_t need = zb_mpc_workspace_bytes(dtype, Bsz, N, n, m);
+    ZB_ARG(workspace && workspace_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    if (bounded) return fail(-3, "box-constrained lqrMpc (ADMM tier) is not implemented yet");
+    (void)x_lb; (void)x_ub; (void)u_lb; (void)u_ub; (void)opts;
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    MpcP P{Bsz, N, n, m, to_arr(A), to_arr(B), to_arr(Q), to_arr(R), to_arr(Qf), x0, u0_out, xTraj, uTraj, workspace,
+           status_out, iters_out};
+    ZB_DISPATCH(dtype, k_mpc_riccati, gen_grid(Bsz), GEN_THREADS, stream, P);
+    return 0;
+}
+
+int32_t zb_peak_fma(int32_t dtype, int32_t device, double* flops_per_s_out, double* sm_clock_mhz_out) {
+    ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "bad dtype %d", dtype);
+    ZB_ARG(flops_per_s_out, "NULL output");
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    cudaDeviceProp prop;
+    ZB_CUDA(cudaGetDeviceProperties(&prop, device));
+    void* out;
+    ZB_CUDA(cudaMalloc(&out, 64));
+    cudaEvent_t e0, e1;
+    ZB_CUDA(cudaEventCreate(&e0));
+    ZB_CUDA(cudaEventCreate(&e1));
+    const int ILP = 8, threads = 256, blocks = prop.multiProcessorCount * 8;
+    const int iters = dtype == ZB_F32 ? 4096 : 2048;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        ZB_CUDA(cudaEventRecord(e0));
+        if (dtype == ZB_F32) k_peak_fma<float, ILP><<<blocks, threads>>>((float*)out, iters);
+        else k_peak_fma<double, ILP><<<blocks, threads>>>((double*)out, iters);
+        ZB_CUDA(cudaEventRecord(e1));
+        ZB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        ZB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * ILP * 8 * (double)iters * threads * (double)blocks;
+        double f = flops / (ms * 1e-3);
+        if (rep > 0 && f > best) best = f;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *flops_per_s_out = best;
+    if (sm_clock_mhz_out) *sm_clock_mhz_out = prop.clockRate / 1000.0;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+"""
+Discrete finite-horizon LQR -- mirror of zopt/lqrUtils.py:144-173 and :207-262.
+
+Same names, argument order and return values as the reference.  Batched convention:
+every array may carry one extra leading axis `Bsz`; operands without it are shared by the batch.
+Returns torch CUDA tensors; dtype follows the inputs (fp32 only when every input is fp32).
+"""
+import torch
+
+from ._lib import View, check, dcode, lib, pick_device, pick_dtype, ptr, stream_ptr, to_dev
+
+
+def _prep(arrs, core_ndims):
+    """Move to device, find the batch size.  core_ndims[i] = ndim of the un-batched operand."""
+    device = pick_device(*arrs)
+    dtype = pick_dtype(*arrs)
+    ts = [to_dev(a, dtype, device) for a in arrs]
+    Bsz, batched = None, []
+    for t, nd in zip(ts, core_ndims):
+        if t.ndim == nd:
+            batched.append(False)
+        elif t.ndim == nd + 1:
+            batched.append(True)
+            if t.shape[0] != 1:
+                if Bsz is not None and Bsz != t.shape[0]:
+                    raise ValueError(f"inconsistent batch sizes {Bsz} and {t.shape[0]}")
+                Bsz = t.shape[0]
+        else:
+            raise ValueError(f"expected {nd} or {nd + 1} dimensions, got shape {tuple(t.shape)}")
+    any_batched = any(batched)
+    if Bsz is None:
+        Bsz = 1
+    return device, dtype, ts, batched, any_batched, Bsz
+
+
+def discreteFiniteHorizonLqr(A, B, Q, R, N, return_value=False):
+    """
+    Finite-horizon LQR gains by the backward Riccati recursion (zopt/lqrUtils.py:144-173).
+
+    Arguments
+    ---------
+        A : (T,n,n) or (Bsz,T,n,n), time along the axis before the matrix: `A[k]`
+        B : (T,n,m) or (Bsz,T,n,m)
+        Q : (T,n,n) or (Bsz,T,n,n); the terminal value is `Q[-1]` (lqrUtils.py:172)
+        R : (T,m,m) or (Bsz,T,m,m)
+        N : horizon (T >= N)
+
+    Returns
+    -------
+        L : (N,m,n) or (Bsz,N,m,n) gains, `u = -L[k] x`
+    """
+    device, dtype, (A, B, Q, R), batched, any_b, Bsz = _prep([A, B, Q, R], [3, 3, 3, 3])
+    n, m = B.shape[-2], B.shape[-1]
+    N = int(N)
+    Ts = [t.shape[-3] for t in (A, B, Q, R)]
+    T = Q.shape[-3]
+    if A.shape[-2:] != (n, n) or Q.shape[-2:] != (n, n) or R.shape[-2:] != (m, m):
+        raise ValueError("inconsistent matrix shapes")
+    if min(Ts[0], Ts[1], Ts[3]) < N or T < max(N, 1):
+        raise ValueError(f"time axis shorter than the horizon N={N}")
+    vA, vB, vQ, vR = (View(t, 2, True, b) for t, b in zip((A, B, Q, R), batched))
+    L = torch.empty((Bsz, N, m, n), dtype=dtype, device=device)
+    V0 = torch.empty((Bsz, n, n), dtype=dtype, device=device) if return_value else None
+    check(lib.zb_lqr_dfh(dcode(dtype), device.index, stream_ptr(device), Bsz, N, T, n, m, vA.ref(), vB.ref(), vQ.ref(),
+                         vR.ref(), ptr(L), ptr(V0)))
+    if not any_b:
+        L = L[0]
+        V0 = V0[0] if return_value else None
+    return (L, V0) if return_value else L
+
+
+def bilinearAffineLqr(A, B, d, Q, R, H, q, r, q0, N):
+    """
+    Finite-horizon LQR with bilinear cost and affine dynamics (zopt/lqrUtils.py:207-262).
+
+    Shapes as the reference, each optionally with a leading batch axis:
+    A (N,n,n) B (N,n,m) d (N,n) Q (N,n,n) R (N,m,m) H (N,m,n) q (N,n) r (N,m) q0 (N,)
+
+    Returns
+    -------
+        L : (N,m,n) gains, l : (N,m) offsets
+    """
+    device, dtype, ts, batched, any_b, Bsz = _prep([A, B, d, Q, R, H, q, r, q0], [3, 3, 2, 3, 3, 3, 2, 2, 1])
+    A, B, d, Q, R, H, q, r, q0 = ts
+    n, m = B.shape[-2], B.shape[-1]
+    N = int(N)
+    T = Q.shape[-3]
+    if q.shape[-2] != T or q0.shape[-1] != T:
+        raise ValueError("Q, q and q0 must have the same time length (the initial carry is their last row)")
+    blocks = [2, 2, 1, 2, 2, 2, 1, 1, 0]
+    views = [View(t, k, True, b) for t, k, b in zip(ts, blocks, batched)]
+    L = torch.empty((Bsz, N, m, n), dtype=dtype, device=device)
+    l = torch.empty((Bsz, N, m), dtype=dtype, device=device)
+    check(lib.zb_lqr_bilinear(dcode(dtype), device.index, stream_ptr(device), Bsz, N, T, n, m, *[v.ref() for v in views],
+                              ptr(L), ptr(l)))
+    if not any_b:
+        return L[0], l[0]
+    return L, l
+
+
+def proportionalFeedbackController(x, x0, u0, K):
+    """zopt/lqrUtils.py:266-269: `u = -K (x - x0) + u0`; no controller states."""
+    control = -K @ (x - x0) + u0
+    return control, control.new_zeros(0)
