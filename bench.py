@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""
+Benchmark of the hot path -- contract in the task statement / DESIGN.md "Measurement".
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on that fits one GPU):
+  batched quadcopter LQR-MPC solve, n=12 m=4 N=50, 65,536 problems per GPU, fp32.
+One "step" = for every problem i: linearise the Euler quadcopter at xbar_i (CUDA kernel), then
+`lqrMpc(A_i,B_i,Q_i,R_i,N,Qf=10 Q_i).solve(x0_i)` with infinite bounds = a full Riccati sweep (gains
+recomputed every step, nothing cached) + the closed-loop plan rollout.  Metric: solves/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+N>1 is launched by torchrun, one rank per GPU; the batch is sharded (each rank owns its own 65,536
+problems: weak scaling), no collective on the data path; timing = barrier + sync on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_HORIZON, NX, NU = 50, 12, 4
+FLOP_PER_SOLVE = 657067.0  # 50 x 13,141 dense as-written flop of the Riccati step (no symmetry discount)
+METRIC = "quadcopter_lqr_mpc_solves_per_s"
+UNIT = "solves/s"
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_problem(Bsz, rank):
+    from zopt_b200 import configs
+    d = configs.cfg2(Bsz=Bsz, seed=1234 + 2 + 1000 * rank)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_step(xbar, ubar, qd, rd, N, dt, threads):
+    """The oracle (port of the reference's algorithm) on host cores: autodiff linearisation (the reference uses
+    jax.jacobian), batched Riccati recursion, linear closed-loop rollout.  torch-CPU fp64, all host threads."""
+    from oracle.quadcopter import Quadcopter
+    torch.set_num_threads(threads)
+    ac = Quadcopter()
+    f = ac.eulerStep(dt)
+    xb, ub = torch.as_tensor(xbar), torch.as_tensor(ubar)
+    A, B = torch.func.vmap(torch.func.jacrev(f, argnums=(0, 1)))(xb, ub)
+    Q, R = torch.diag_embed(torch.as_tensor(qd)), torch.diag_embed(torch.as_tensor(rd))
+    V = 10 * Q
+    Ls = []
+    Bt = B.transpose(1, 2)
+    for k in range(N):  # lqrUtils.py:167-170
+        BtV = Bt @ V
+        L = torch.linalg.solve(R + BtV @ B, BtV @ A)
+        Acl = A - B @ L
+        V = Q + L.transpose(1, 2) @ R @ L + Acl.transpose(1, 2) @ V @ Acl
+        Ls.append(L)
+    Ls = Ls[::-1]
+    x = xb
+    xs, us = [x], []
+    for k in range(N):
+        u = -(Ls[k] @ x.unsqueeze(-1)).squeeze(-1)
+        x = (A @ x.unsqueeze(-1)).squeeze(-1) + (B @ u.unsqueeze(-1)).squeeze(-1)
+        xs.append(x)
+        us.append(u)
+    return torch.stack(xs, 1), torch.stack(us, 1)
+
+
+def time_cpu(sample, steps, warmup, rank=0):
+    d = make_problem(sample, rank)
+    threads = os.cpu_count() or 1
+    args = (d["xbar"], d["ubar"], d["qdiag"], d["rdiag"], d["N"], d["dt"], threads)
+    for _ in range(warmup):
+        cpu_step(*args)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(*args)
+    el = time.perf_counter() - t0
+    return sample * steps / el, el / steps, threads
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    sample = args.cpu_sample
+    val, sec, threads = time_cpu(sample, args.steps, min(args.warmup, 1))
+    cb = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+          "sample": f"{sample} problems of the same cfg-2 workload per step (torch-CPU fp64 oracle port; JAX is not installed)"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(sample), "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(Bsz):
+    return {"workload": "cfg2: batched quadcopter LQR-MPC solve (linearise + Riccati sweep N=50 + plan rollout), n=12 m=4, "
+                        f"{Bsz} problems per GPU", "n": NX, "m": NU, "N": N_HORIZON, "batch_per_gpu": Bsz,
+            "parallelism": "batch sharded over GPUs, no collective",
+            "l2": "working set per step (gains 9.6 KB + plan 3.2 KB + A,B,Q,R 1.4 KB per problem) is ~0.9 GB >> 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from zopt_b200 import _lib
+    from zopt_b200.mpcUtils import lqrMpc
+    from zopt_b200.quadcopter import Quadcopter
+
+    Bsz = args.batch
+    d = make_problem(Bsz, rank)
+    f32 = torch.float32
+    # host (pinned) inputs of one step: the states to solve from
+    x0_host = torch.as_tensor(d["xbar"], dtype=f32).pin_memory()
+    xbar = torch.as_tensor(d["xbar"], dtype=f32, device=dev)
+    ubar = torch.as_tensor(d["ubar"], dtype=f32, device=dev)
+    Q = torch.diag_embed(torch.as_tensor(d["qdiag"], dtype=f32, device=dev))
+    R = torch.diag_embed(torch.as_tensor(d["rdiag"], dtype=f32, device=dev))
+    Qf = 10 * Q
+    inf_n, inf_m = torch.full((NX,), float("inf")), torch.full((NU,), float("inf"))
+    ac = Quadcopter()
+    N, dt = d["N"], d["dt"]
+
+    def step(x0_dev):
+        A, B = ac.linearizeInertial(xbar, ubar, dt)
+        prob = lqrMpc(A, B, Q, R, N, -inf_n, inf_n, -inf_m, inf_m, Qf=Qf)
+        return prob.solve(x0_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        out = step(xbar)
+    barrier()
+
+    # --- kernel-resident timing: inputs already in HBM -----------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step(xbar)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # --- dominant kernel alone (the Riccati sweep + rollout launch), events on the launching stream
+    A, B = ac.linearizeInertial(xbar, ubar, dt)
+    prob = lqrMpc(A, B, Q, R, N, -inf_n, inf_n, -inf_m, inf_m, Qf=Qf)
+    kms = []
+    for _ in range(max(3, min(args.steps, 20))):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        prob.solve(xbar)
+        k1.record()
+        torch.cuda.synchronize(dev)
+        kms.append(k0.elapsed_time(k1))
+    k_ms = float(np.mean(kms))
+
+    # --- end to end through the public API with host buffers -----------------------------------
+    host_out = None
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        x0d = x0_host.to(dev, non_blocking=True)
+        u, traj, status = step(x0d)
+        host_out = (u.cpu(), traj.xTraj.cpu(), traj.uTraj.cpu(), status.cpu())
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    h2d = x0_host.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in host_out)
+
+    times = torch.tensor([ms, e2e_ms, k_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, k_ms = (float(v) for v in times.cpu())
+
+    if rank == 0:
+        total = Bsz * world
+        value = total * args.steps / (ms * 1e-3)
+        e2e_val = total * args.steps / (e2e_ms * 1e-3)
+        import ctypes as C
+        peak32, clk = C.c_double(0), C.c_double(0)
+        _lib.check(_lib.lib.zb_peak_fma(0, local_rank, C.byref(peak32), C.byref(clk)))
+        ach_tf = FLOP_PER_SOLVE * Bsz / (k_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = (1456 + 9600 * 2 + 3248) * Bsz  # in: A,B,Q,R,Qf,x0; gains written + re-read; plan written (fp32)
+        roof = {"bound": "fp32_fma", "achieved": ach_tf, "peak": peak32.value / 1e12, "unit": "TFLOP/s",
+                "frac": ach_tf / (peak32.value / 1e12), "traffic": None,
+                "peak_source": "zb_peak_fma dependent-FMA probe measured in this run (MEASURED_PEAKS.json has no FP32 CUDA-core figure)",
+                "kernel": "lqrMpc.solve launch (Riccati sweep + rollout)", "kernel_ms": k_ms,
+                "algorithmic_flop_per_solve": FLOP_PER_SOLVE,
+                "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
+        cpu_val, cpu_sec, threads = time_cpu(args.cpu_sample, 1, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(Bsz), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": 2 * args.steps, "roofline": roof,
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{args.cpu_sample} problems of the same workload, 1 step ({cpu_sec:.1f} s), torch-CPU fp64 oracle port"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=4096)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,108 @@
+"""
+CPU-side checks: the C-ABI library loads and exports every symbol include/zopt_b200.h declares, the
+ctypes table mirrors the header, argument errors are reported without touching a GPU, and the
+product path refuses to run without CUDA (no CPU fallback).
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "zopt_b200.h")).read()
+    return re.findall(r"^ZB_API\s+\w+\s+(zb_\w+)\(", src, flags=re.M)
+
+
+def test_library_exports_every_declared_symbol():
+    from zopt_b200 import _lib
+    names = _declared()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(_lib.lib, name), f"{name} declared in include/zopt_b200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    assert _lib.lib.zb_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    from zopt_b200 import _lib
+    assert C.sizeof(_lib.ZbArr) == 24
+    assert C.sizeof(_lib.ZbModel) == 4 * 4 + 8 + 24 + 2 * 24
+    assert C.sizeof(_lib.ZbCost) == 72
+    assert C.sizeof(_lib.ZbAdmmOpts) == 8 + 5 * 8
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from zopt_b200 import _lib
+    a = _lib.ZbArr(1, 0, 0)
+    rc = _lib.lib.zb_lqr_dfh(0, 0, None, 1, 2, 2, 17, 1, C.byref(a), C.byref(a), C.byref(a), C.byref(a), None, None)
+    assert rc < 0 and "n must be" in _lib.last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+    rc = _lib.lib.zb_lqr_dfh(5, 0, None, 1, 2, 2, 2, 1, C.byref(a), C.byref(a), C.byref(a), C.byref(a), None, None)
+    assert rc < 0 and "dtype" in _lib.last_error()
+    rc = _lib.lib.zb_pd_clamp(1, 0, None, 1, 99, 1e-3, None, None)
+    assert rc < 0
+    m = _lib.ZbModel()
+    m.kind = 7
+    rc = _lib.lib.zb_ilqr_rollout(1, 0, None, 1, 1, C.byref(m), None, None, None, None, None, None, 1.0, None, None, None)
+    assert rc == -2
+    with pytest.raises(TypeError):
+        _lib.check(rc)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    I = np.repeat(np.eye(2)[None], 2, axis=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        discreteFiniteHorizonLqr(I, I, I, I, 2)
+
+
+def test_unregistered_callables_raise_typeerror():
+    from zopt_b200.models import LinearDynamics, QuadraticCost, require_cost, require_model
+    with pytest.raises(TypeError):
+        require_model(lambda x, u: x + u)
+    with pytest.raises(TypeError):
+        require_cost(lambda x, u: x @ x, lambda x: x @ x)
+    dyn = LinearDynamics(np.eye(2), np.eye(2))
+    assert require_model(dyn) is dyn
+    # registered objects stay callable like the lambdas they replace
+    x, u = torch.tensor([1., 2.], dtype=torch.float64), torch.tensor([3., 4.], dtype=torch.float64)
+    assert torch.equal(dyn(x, u), x + u)
+    assert float(QuadraticCost(np.eye(2), 2 * np.eye(2))(x, u)) == 5 + 50
+
+
+def test_pytree_semantics():  # container half of reference tests/test_pytrees.py (no GPU needed)
+    from zopt_b200 import pytrees
+    T = lambda v: torch.as_tensor(np.asarray(v, dtype=np.float64))
+    traj = pytrees.Trajectory(torch.arange(15).reshape(5, 3), torch.arange(8).reshape(4, 2))
+    assert torch.equal(traj[2].xTraj, torch.arange(15).reshape(5, 3)[2])
+    V = pytrees.QuadraticValueFunction(T(1.), T([2., 3]), T([[4., 5], [6, 7]]))
+    assert float(V(T([8., 9]))) == pytest.approx(851.5)
+    Cq = pytrees.QuadraticCostFunction(T(0.), T([1, 2]), T([2, 1]), torch.eye(2, dtype=torch.float64),
+                                       torch.ones((2, 2), dtype=torch.float64), torch.eye(2, dtype=torch.float64))
+    assert float(Cq(T([1., 2]), T([3., 4]))) == pytest.approx(51.0)
+    dyn = pytrees.AffineDynamics(T([1, 1]), T([[2, 3], [4, 5]]), T([[6], [7]]))
+    assert dyn(T([1, 2]), T([2])).numpy() == pytest.approx(np.array([21, 29]))
+    qd = pytrees.QuadraticDynamics(torch.zeros(2, dtype=torch.float64), torch.eye(2, dtype=torch.float64),
+                                   torch.eye(2, dtype=torch.float64), torch.stack([torch.eye(2), 2 * torch.eye(2)]).double(),
+                                   torch.zeros((2, 2, 2), dtype=torch.float64),
+                                   torch.stack([torch.eye(2), 2 * torch.eye(2)]).double())
+    assert torch.equal(qd(T([1, 0]), T([0, 1])), T([2., 3]))
+    pol = pytrees.AffinePolicy(T([1, 2]), T([[1, 2], [3, 4]]))
+    assert torch.equal(pol(T([1, 2])), T([6, 13]))
+    l = torch.arange(6, dtype=torch.float64).reshape(2, 3)
+    L = torch.arange(12, dtype=torch.float64).reshape(2, 3, 2)
+    pol = pytrees.AffinePolicy(l, L)
+    assert torch.equal(pol(torch.zeros(2, dtype=torch.float64), k=0, alpha=0.5), 0.5 * l[0])
+    for tree, args in ((pol, (torch.zeros(2, dtype=torch.float64),)),):
+        with pytest.raises(ValueError):
+            tree(*args)
+    dJ = pytrees.QuadraticDeltaCost(1, 2)
+    assert dJ(1) == 3 and dJ(0.5) == 1

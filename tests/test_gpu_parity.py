@@ -1,0 +1,483 @@
+"""
+GPU parity tests (-m gpu): the CUDA path, called through the public Python mirror of the reference API
+(which binds the C ABI of include/zopt_b200.h with ctypes), against the oracle on the same seeded inputs,
+against the reference's known-answer tests, and against the frozen golden fixtures.
+
+Tolerances: per-array max-norm relative error, fp64 1e-10, fp32 1e-5;
+multi-iteration iLQR/DDP in fp32: x,u 2e-5, L 1e-4 after the step-size sequence matched.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ilqr as oilqr  # noqa: E402
+from oracle import lqr as olqr  # noqa: E402
+from oracle import pytrees as opt  # noqa: E402
+from oracle.quadcopter import Quadcopter as OQuadcopter  # noqa: E402
+from zopt_b200 import configs  # noqa: E402
+
+
+def relerr(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+def per_problem_relerr(a, b):
+    a = a.detach().cpu().numpy().astype(np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    ax = tuple(range(1, a.ndim))
+    return np.max(np.abs(a - b), axis=ax) / np.max(np.abs(b), axis=ax)
+
+
+TOL = {torch.float64: 1e-10, torch.float32: 1e-5}
+DT = [torch.float64, torch.float32]
+cuda = lambda a, dt=torch.float64: torch.as_tensor(np.asarray(a), dtype=dt, device="cuda")
+
+
+def quad_linearized(xbar, ubar, dt=0.1):
+    ac = OQuadcopter()
+    f = ac.eulerStep(dt)
+    A, B = torch.func.vmap(torch.func.jacrev(f, argnums=(0, 1)))(torch.as_tensor(xbar), torch.as_tensor(ubar))
+    return A.numpy(), B.numpy()
+
+
+# =============================================================================================== lqrUtils
+def test_lqr_known_answer_reference_shapes():  # reference tests/test_lqrUtils.py:61-69, un-batched call
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    N = 2
+    I = np.repeat(np.eye(2)[None], N, axis=0)
+    K = discreteFiniteHorizonLqr(I, I, I, I, N)
+    assert K.shape == (N, 2, 2) and K.is_cuda and K.dtype == torch.float64
+    assert K[1].cpu().numpy() == pytest.approx(0.5 * np.eye(2))
+    assert K[0].cpu().numpy() == pytest.approx(0.6 * np.eye(2))
+
+
+def test_bilinear_known_answer():  # reference tests/test_lqrUtils.py:82-98
+    from zopt_b200.lqrUtils import bilinearAffineLqr
+    N = 2
+    I = np.repeat(np.eye(2)[None], N, axis=0)
+    one = np.ones((N, 2))
+    K, k = bilinearAffineLqr(I, I, one, I, I, I, one, one, np.ones(N), N)
+    assert K[1].cpu().numpy() == pytest.approx(np.eye(2)) and K[0].cpu().numpy() == pytest.approx(np.eye(2))
+    assert k[1].cpu().numpy() == pytest.approx(1.5 * np.ones(2)) and k[0].cpu().numpy() == pytest.approx(np.ones(2))
+
+
+def _cfg2_arrays(Bsz, time_axis):
+    d = configs.cfg2(Bsz=Bsz)
+    A, B = quad_linearized(d["xbar"], d["ubar"])
+    N = d["N"]
+    Q, R = configs.diag_embed(d["qdiag"]), configs.diag_embed(d["rdiag"])
+    return d, A, B, Q, R, N
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("materialised", [False, True])
+def test_lqr_cfg2_vs_oracle(dt, materialised):
+    """cfg 2 (n=12, m=4, N=50): time-invariant operands passed as stride-0 views (fast path) or materialised"""
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    Bsz = 300  # not a multiple of the CTA tile: exercises the ragged tail
+    d, A, B, Q, R, N = _cfg2_arrays(Bsz, True)
+    Qk = np.repeat(Q[:, None], N + 1, axis=1)
+    Qk[:, N] *= 10
+    Lref, Vref = olqr.discreteFiniteHorizonLqr_batched(np.repeat(A[:, None], N, 1), np.repeat(B[:, None], N, 1), Qk,
+                                                       np.repeat(R[:, None], N, 1), N, return_value=True)
+    Ad, Bd, Rd, Qd = cuda(A, dt), cuda(B, dt), cuda(R, dt), cuda(Qk, dt)
+    if materialised:
+        Ak, Bk, Rk = (t[:, None].expand(-1, N, -1, -1).contiguous() for t in (Ad, Bd, Rd))
+    else:
+        Ak, Bk, Rk = (t[:, None].expand(-1, N, -1, -1) for t in (Ad, Bd, Rd))
+    L, V0 = discreteFiniteHorizonLqr(Ak, Bk, Qd, Rk, N, return_value=True)
+    assert L.shape == (Bsz, N, 4, 12) and L.dtype == dt
+    assert per_problem_relerr(L, Lref).max() < TOL[dt]
+    assert per_problem_relerr(V0, Vref).max() < TOL[dt]
+
+
+def test_lqr_demo_and_double_integrator():
+    """cfg 1a (the real demo, n=8 m=4 N=100, incl. the Q[-1] terminal quirk) and cfg 1b (double integrator)"""
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    from zopt_b200.quadcopter import Quadcopter
+    ac, oac = Quadcopter(), OQuadcopter()
+    xTrim, uTrim = np.zeros(8), configs.U_TRIM
+    A, B = ac.linearize(xTrim, uTrim, dt=0.1)
+    Ao, Bo = oac.linearize(xTrim, uTrim, dt=0.1)
+    assert relerr(A, Ao) < 1e-12 and relerr(B, Bo) < 1e-12
+    N = 100
+    Qk, Rk = configs.cfg1_demo_weights(N)
+    Ak, Bk = A[None].expand(N, 8, 8), B[None].expand(N, 8, 4)
+    K = discreteFiniteHorizonLqr(Ak, Bk, Qk, Rk, N)
+    Kref = olqr.discreteFiniteHorizonLqr(np.repeat(Ao.numpy()[None], N, 0), np.repeat(Bo.numpy()[None], N, 0), Qk, Rk, N)
+    assert K.shape == (N, 4, 8) and relerr(K, Kref) < 1e-10
+    Ak, Bk, Qk, Rk, N = configs.cfg1_double_integrator()
+    K = discreteFiniteHorizonLqr(Ak, Bk, Qk, Rk, N)
+    assert relerr(K, olqr.discreteFiniteHorizonLqr(Ak, Bk, Qk, Rk, N)) < 1e-10
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_lqr_time_varying_random(dt):
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    rng = np.random.default_rng(0)
+    for (n, m, N, T, Bsz) in ((5, 3, 7, 9, 4), (12, 4, 20, 20, 70), (16, 8, 3, 3, 2), (1, 1, 4, 5, 1)):
+        A = rng.normal(size=(Bsz, T, n, n)) * 0.5 / np.sqrt(n)
+        B = rng.normal(size=(Bsz, T, n, m))
+        spd = lambda k: (lambda M: M @ M.T / k + np.eye(k))(rng.normal(size=(k, k)))
+        Q = np.stack([[spd(n) for _ in range(T)] for _ in range(Bsz)])
+        R = np.stack([[spd(m) for _ in range(T)] for _ in range(Bsz)])
+        Lref = olqr.discreteFiniteHorizonLqr_batched(A, B, Q, R, N)
+        L = discreteFiniteHorizonLqr(cuda(A, dt), cuda(B, dt), cuda(Q, dt), cuda(R, dt), N)
+        assert per_problem_relerr(L, Lref).max() < TOL[dt], (n, m)
+
+
+def test_lqr_edge_cases():
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    I = np.repeat(np.eye(2)[None], 3, axis=0)
+    assert discreteFiniteHorizonLqr(I, I, I, I, 0).shape == (0, 2, 2)  # empty horizon
+    empty = torch.zeros((0, 3, 2, 2), device="cuda", dtype=torch.float64)
+    assert discreteFiniteHorizonLqr(empty, empty, empty, empty, 3).shape == (0, 3, 2, 2)  # empty batch
+    with pytest.raises(ValueError):
+        discreteFiniteHorizonLqr(I, I, I, I, 4)  # horizon longer than the arrays
+    big = np.zeros((1, 17, 17))
+    with pytest.raises(ValueError):
+        discreteFiniteHorizonLqr(big, big, big, big, 1)  # n > ZB_MAX_N
+    # NaN passthrough is data, not an error
+    In = I.copy()
+    In[0, 0, 0] = np.nan
+    assert torch.isnan(discreteFiniteHorizonLqr(In, I, I, I, 3)).any()
+
+
+def test_bilinear_random_vs_oracle():
+    from zopt_b200.lqrUtils import bilinearAffineLqr
+    rng = np.random.default_rng(1)
+    n, m, N, Bsz = 8, 4, 100, 5  # the demo's sizes (demos/bilinearLqrControl.py:21-43)
+    ac = OQuadcopter()
+    A0, B0 = (t.numpy() for t in ac.linearize(np.zeros(8), configs.U_TRIM, dt=0.1))
+    A = np.repeat(np.repeat(A0[None, None], N, 1), Bsz, 0)
+    Bm = np.repeat(np.repeat(B0[None, None], N, 1), Bsz, 0)
+    d = rng.normal(size=(Bsz, N, n)) * 0.01
+    Q = np.repeat(np.repeat(np.eye(n)[None, None], N, 1), Bsz, 0)
+    R = np.repeat(np.repeat(np.eye(m)[None, None], N, 1), Bsz, 0)
+    Hm = 0.2 * rng.normal(size=(Bsz, N, m, n))
+    q = 0.1 * np.repeat(np.repeat(np.array([1., -1, 0, 0, 0, 0, 0, 0])[None, None], N, 1), Bsz, 0)
+    r = rng.normal(size=(Bsz, N, m)) * 0.1
+    q0 = rng.normal(size=(Bsz, N))
+    Lr, lr = olqr.bilinearAffineLqr_batched(A, Bm, d, Q, R, Hm, q, r, q0, N)
+    for dt in DT:
+        L, l = bilinearAffineLqr(*(cuda(t, dt) for t in (A, Bm, d, Q, R, Hm, q, r, q0)), N)
+        assert per_problem_relerr(L, Lr).max() < TOL[dt] and per_problem_relerr(l, lr).max() < TOL[dt]
+    # shared (un-batched) operands broadcast over a batched one
+    L, l = bilinearAffineLqr(A[0], Bm[0], d, Q[0], R[0], Hm, q[0], r, q0, N)
+    assert per_problem_relerr(L, Lr).max() < 1e-10
+
+
+# =============================================================================================== quadcopter
+@pytest.mark.parametrize("wind", [None, (3.0, 1.0, 0.0)])
+@pytest.mark.parametrize("dt", DT)
+def test_quadcopter_vs_autodiff(dt, wind):
+    from zopt_b200.quadcopter import Quadcopter, quad_hess_contract
+    rng = np.random.default_rng(7)
+    Bsz = 64
+    x = configs.quad_states(rng, Bsz)
+    u = np.tile(configs.U_TRIM, (Bsz, 1)) + rng.normal(size=(Bsz, 4))
+    lam = rng.normal(size=(Bsz, 12))
+    oac = OQuadcopter()
+    wt = None if wind is None else torch.tensor(wind, dtype=torch.float64)
+    F = lambda xx, uu: oac.inertialDynamics(xx, uu, wt)
+    xt, ut = torch.as_tensor(x), torch.as_tensor(u)
+    Fref = torch.func.vmap(F)(xt, ut)
+    Jx, Ju = torch.func.vmap(torch.func.jacrev(F, argnums=(0, 1)))(xt, ut)
+    Href = np.einsum('bi,bijk->bjk', lam, torch.func.vmap(torch.func.hessian(F, argnums=0))(xt, ut).numpy())
+    ac = Quadcopter()
+    tol = 1e-12 if dt == torch.float64 else 2e-6
+    assert relerr(ac.inertialDynamics(cuda(x, dt), cuda(u, dt), wind), Fref) < tol
+    A, B = ac.linearizeInertial(cuda(x, dt), cuda(u, dt), dt=0, wind_ned=wind)
+    assert relerr(A, Jx) < tol and relerr(B, Ju) < tol
+    A, B = ac.linearizeInertial(cuda(x, dt), cuda(u, dt), dt=0.1, wind_ned=wind)
+    assert relerr(A, torch.eye(12) + 0.1 * Jx) < tol and relerr(B, 0.1 * Ju) < tol
+    assert relerr(quad_hess_contract(cuda(x, dt), cuda(u, dt), wind, 0.0, cuda(lam, dt)), Href) < tol
+
+
+def test_quadcopter_known_answers():  # reference tests/test_quadcopter.py:12-116
+    from zopt_b200.quadcopter import Quadcopter
+    ac = Quadcopter()
+    th = np.pi / 6
+    c, s, t = np.cos(th), np.sin(th), np.tan(th)
+    assert ac._bodyToInertialRotationMatrix(th, 0., 0.).numpy() == pytest.approx(np.array([[1, 0, 0], [0, c, -s], [0, s, c]]))
+    assert ac._bodyToInertialRotationMatrix(0., 0., th).numpy() == pytest.approx(np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]]))
+    assert ac._bodyRatesToEulerRatesRotationMatrix(0., th).numpy() == pytest.approx(np.array([[1, 0, t], [0, 1, 0], [0, 0, 1 / c]]))
+    xDot = ac.rigidBodyDynamics(np.zeros(9), np.zeros(4))
+    assert xDot.cpu().numpy() == pytest.approx(np.array([0, 0, 9.807, 0, 0, 0, 0, 0]))
+    assert ac.rigidBodyDynamics(np.zeros(9), configs.U_TRIM).cpu().numpy() == pytest.approx(np.zeros(8))
+    state = np.zeros(12)
+    assert ac.inertialDynamics(state, configs.U_TRIM).cpu().numpy() == pytest.approx(np.zeros(12))
+    state[0:3] = [0.1, 0.2, 0.3]
+    assert ac.inertialDynamics(state, configs.U_TRIM)[9:].cpu().numpy() == pytest.approx(np.array([0.1, 0.2, 0.3]))
+    state[8] = np.pi / 2
+    assert ac.inertialDynamics(state, configs.U_TRIM)[9:].cpu().numpy() == pytest.approx(np.array([-0.2, 0.1, 0.3]))
+    for uvw0 in (np.zeros(3), np.array([0.1, 0.2, 0.3])):
+        x0, u0 = ac.trim(uvw0)
+        assert x0[0:3] == pytest.approx(uvw0)
+        assert ac.rigidBodyDynamics(x0, u0).cpu().numpy() == pytest.approx(np.zeros(8), abs=1e-3)
+    A, B = ac.linearize(np.zeros(8), configs.U_TRIM, dt=1)
+    assert A.shape == (8, 8) and B.shape == (8, 4) and not (torch.isnan(A).any() or torch.isnan(B).any())
+    # wind in the body frame (the oracle's rigidBodyDynamics takes it directly)
+    wb = np.array([0.5, -0.2, 0.1])
+    xs = np.array([0.3, -0.1, 0.2, 0.1, 0.05, -0.02, 0.2, -0.3])
+    ref = OQuadcopter().rigidBodyDynamics(xs, configs.U_TRIM, torch.as_tensor(wb))
+    assert relerr(ac.rigidBodyDynamics(xs, configs.U_TRIM, wb), ref) < 1e-12
+
+
+# =============================================================================================== ilqrUtils pieces
+@pytest.mark.parametrize("p", [1, 4, 12, 16, 24])
+@pytest.mark.parametrize("dt", DT)
+def test_ensurePositiveDefinite(p, dt):
+    from zopt_b200.ilqrUtils import ensurePositiveDefinite
+    rng = np.random.default_rng(p)
+    S = rng.normal(size=(16, p, p))
+    S = S + np.swapaxes(S, 1, 2)
+    S[0] = 0
+    out = ensurePositiveDefinite(cuda(S, dt))
+    ref = np.stack([oilqr.ensurePositiveDefinite(torch.as_tensor(s)).numpy() for s in S])
+    assert per_problem_relerr(out[1:], ref[1:]).max() < (1e-11 if dt == torch.float64 else 1e-5)
+    assert out[0].cpu().numpy() == pytest.approx(1e-3 * np.eye(p))
+
+
+def test_riccati_step_known_answers():  # reference tests/test_ilqrUtils.py:56-81 (exact ==), :110-135 (rel 1e-3)
+    from zopt_b200.ilqrUtils import riccatiStep_ddp, riccatiStep_ilqr
+    from zopt_b200 import pytrees
+    A = B = np.eye(2)
+    f = np.zeros(2)
+    cost = (0., np.zeros(2), np.zeros(2), np.eye(2), np.zeros((2, 2)), np.eye(2))
+    value = (0., np.zeros(2), np.eye(2))
+    valueOut, policy = riccatiStep_ilqr((f, A, B), cost, value)
+    assert isinstance(valueOut, pytrees.QuadraticValueFunction) and isinstance(policy, pytrees.AffinePolicy)
+    assert valueOut.v == 0
+    assert torch.all(valueOut.v_x == 0) and torch.all(policy.l == 0)
+    assert torch.all(valueOut.v_xx.cpu() == 1.5 * torch.eye(2, dtype=torch.float64))
+    assert torch.all(policy.L.cpu() == -0.5 * torch.eye(2, dtype=torch.float64))
+    z = np.zeros((2, 2, 2))
+    valueOut, policy = riccatiStep_ddp((f, A, B, z, z, z), cost, value)
+    assert valueOut.v == 0
+    assert valueOut.v_xx.cpu().numpy() == pytest.approx(1.5 * np.eye(2), rel=1e-3)
+    assert policy.L.cpu().numpy() == pytest.approx(-0.5 * np.eye(2), rel=1e-3)
+    assert float(policy.L[0, 0]) == pytest.approx(-1 / 2.001, rel=1e-12)
+
+
+@pytest.mark.parametrize("second_order", [False, True])
+def test_backward_pass_random_pytrees(second_order):
+    from zopt_b200 import ilqrUtils, pytrees
+    rng = np.random.default_rng(3 + int(second_order))
+    Bsz, N, n, m = 3, 6, 5, 3
+    spd = lambda k: (lambda M: M @ M.T + np.eye(k))(rng.normal(size=(k, k)))
+    f_x = rng.normal(size=(Bsz, N, n, n)) * 0.5
+    f_u = rng.normal(size=(Bsz, N, n, m))
+    sym = lambda t: t + np.swapaxes(t, -1, -2)
+    f_xx, f_ux, f_uu = sym(rng.normal(size=(Bsz, N, n, n, n)) * 0.1), rng.normal(size=(Bsz, N, n, m, n)) * 0.1, \
+        sym(rng.normal(size=(Bsz, N, n, m, m)) * 0.1)
+    c, c_x, c_u = rng.normal(size=(Bsz, N)), rng.normal(size=(Bsz, N, n)), rng.normal(size=(Bsz, N, m))
+    czz = np.stack([[spd(n + m) for _ in range(N)] for _ in range(Bsz)])
+    c_xx, c_ux, c_uu = czz[..., :n, :n].copy(), czz[..., n:, :n].copy(), czz[..., n:, n:].copy()
+    v, v_x, v_xx = rng.normal(size=(Bsz,)), rng.normal(size=(Bsz, n)), np.stack([spd(n) for _ in range(Bsz)])
+    f = np.zeros((Bsz, N, n))
+    T = torch.as_tensor
+    cost = pytrees.QuadraticCostFunction(*(cuda(t) for t in (c, c_x, c_u, c_xx, c_ux, c_uu)))
+    Vf = pytrees.QuadraticValueFunction(cuda(v), cuda(v_x), cuda(v_xx))
+    if second_order:
+        pol = ilqrUtils.backwardPass_ddp(pytrees.QuadraticDynamics(*(cuda(t) for t in (f, f_x, f_u, f_xx, f_ux, f_uu))), cost, Vf)
+    else:
+        pol = ilqrUtils.backwardPass_ilqr(pytrees.AffineDynamics(cuda(f), cuda(f_x), cuda(f_u)), cost, Vf)
+    assert isinstance(pol, pytrees.AffinePolicy) and pol.L.shape == (Bsz, N, m, n)
+    for b in range(Bsz):
+        ocost = opt.QuadraticCostFunction(T(c[b]), T(c_x[b]), T(c_u[b]), T(c_xx[b]), T(c_ux[b]), T(c_uu[b]))
+        oVf = opt.QuadraticValueFunction(T(v[b]), T(v_x[b]), T(v_xx[b]))
+        if second_order:
+            ref = oilqr.backwardPass_ddp(opt.QuadraticDynamics(T(f[b]), T(f_x[b]), T(f_u[b]), T(f_xx[b]), T(f_ux[b]), T(f_uu[b])), ocost, oVf)
+        else:
+            ref = oilqr.backwardPass_ilqr(opt.AffineDynamics(T(f[b]), T(f_x[b]), T(f_u[b])), ocost, oVf)
+        assert relerr(pol.l[b], ref.l) < 1e-9 and relerr(pol.L[b], ref.L) < 1e-9
+    # un-batched (reference-shaped) call
+    b = 0
+    cost0 = pytrees.QuadraticCostFunction(*(cuda(t[b]) for t in (c, c_x, c_u, c_xx, c_ux, c_uu)))
+    if not second_order:
+        pol0 = ilqrUtils.backwardPass_ilqr(pytrees.AffineDynamics(cuda(f[b]), cuda(f_x[b]), cuda(f_u[b])), cost0,
+                                           pytrees.QuadraticValueFunction(cuda(v[b]), cuda(v_x[b]), cuda(v_xx[b])))
+        assert pol0.L.shape == (N, m, n) and relerr(pol0.L, pol.L[b]) == 0
+
+
+def test_trajectoryRollout_known_answer():  # reference tests/test_ilqrUtils.py:7-22 (f = x+u, policy alpha*k)
+    from zopt_b200.ilqrUtils import trajectoryRollout
+    from zopt_b200.models import LinearDynamics
+    from zopt_b200.pytrees import AffinePolicy, Trajectory
+    N = 3
+    dyn = LinearDynamics(np.eye(1), np.eye(1))
+    policy = AffinePolicy(np.arange(3.0).reshape(3, 1), np.zeros((3, 1, 1)))
+    prev = Trajectory(np.zeros((N + 1, 1)), np.zeros((N, 1)))
+    xT, uT = trajectoryRollout(np.zeros(1), dyn, policy, prev)
+    assert torch.all(xT.cpu() == torch.tensor([0., 0, 1, 3])[:, None]) and torch.all(uT.cpu() == torch.tensor([0., 1, 2])[:, None])
+    xT, uT = trajectoryRollout(np.zeros(1), dyn, policy, prev, alpha=0.5)
+    assert torch.all(xT.cpu() == torch.tensor([0., 0, 0.5, 1.5])[:, None]) and torch.all(uT.cpu() == torch.tensor([0., 0.5, 1])[:, None])
+    with pytest.raises(TypeError):  # arbitrary callables cannot run on the GPU; no CPU fallback
+        trajectoryRollout(np.zeros(1), lambda x, u: x + u, policy, prev)
+
+
+def _quad_problem(N, Bsz, seed, R_scale=1.0, spread=10.0):
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((Bsz, 12))
+    x0[:, 9:12] = rng.uniform(-spread, spread, (Bsz, 3))
+    return x0, np.tile(configs.U_TRIM, (N, 1)), np.eye(12), R_scale * np.eye(4), 10 * np.eye(12)
+
+
+def _oracle_fns(Q, R, Qf, dt=0.1, wind=None):
+    ac = OQuadcopter()
+    Qt, Rt, Qft = torch.as_tensor(Q), torch.as_tensor(R), torch.as_tensor(Qf)
+    return ac.eulerStep(dt, wind), (lambda x, u: x @ Qt @ x + u @ Rt @ u), (lambda x: x @ Qft @ x)
+
+
+@pytest.mark.parametrize("wind", [None, (3.0, 1.0, 0.0)])
+def test_rollout_and_forwardPass2_quadcopter(wind):
+    from zopt_b200.ilqrUtils import forwardPass2, trajectoryRollout
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    from zopt_b200.pytrees import AffinePolicy, CostFunction, Trajectory
+    N, Bsz = 25, 5
+    x0, uG, Q, R, Qf = _quad_problem(N, Bsz, 11)
+    rng = np.random.default_rng(5)
+    l = rng.normal(size=(Bsz, N, 4)) * 0.3
+    L = rng.normal(size=(Bsz, N, 4, 12)) * 0.05
+    xP = rng.normal(size=(Bsz, N + 1, 12)) * 0.1
+    xP[:, :, 9:12] += x0[:, None, 9:12]
+    uP = uG[None] + rng.normal(size=(Bsz, N, 4)) * 0.1
+    dyn, rc, tc = _oracle_fns(Q, R, Qf, wind=None if wind is None else torch.tensor(wind, dtype=torch.float64))
+    model = QuadcopterEuler(0.1, wind)
+    costFun = CostFunction(QuadraticCost(Q, R), QuadraticTerminalCost(Qf))
+    T = torch.as_tensor
+    pol, prev = AffinePolicy(cuda(l), cuda(L)), Trajectory(cuda(xP), cuda(uP))
+    tr = trajectoryRollout(cuda(x0), model, pol, prev, alpha=0.25)
+    traj2, J, idx, Jall = forwardPass2(cuda(x0), model, costFun, pol, prev, return_index=True)
+    for b in range(Bsz):
+        ro = oilqr.trajectoryRollout(T(x0[b]), dyn, opt.AffinePolicy(T(l[b]), T(L[b])), opt.Trajectory(T(xP[b]), T(uP[b])), alpha=0.25)
+        assert relerr(tr.xTraj[b], ro.xTraj) < 1e-11 and relerr(tr.uTraj[b], ro.uTraj) < 1e-11
+        to, Jo, io, Jao = oilqr.forwardPass2(T(x0[b]), dyn, opt.CostFunction(rc, tc), opt.AffinePolicy(T(l[b]), T(L[b])),
+                                             opt.Trajectory(T(xP[b]), T(uP[b])), return_all=True)
+        assert int(idx[b]) == io and relerr(Jall[b], Jao) < 1e-11
+        assert relerr(traj2.xTraj[b], to.xTraj) < 1e-11 and relerr(traj2.uTraj[b], to.uTraj) < 1e-11
+        assert abs(float(J[b]) - float(Jo)) < 1e-11 * abs(float(Jo))
+
+
+# =============================================================================================== solvers
+@pytest.mark.parametrize("second_order", [False, True])
+def test_solvers_linear_known_answer(second_order):  # reference tests/test_ilqrUtils.py:167-196: `assert converged`
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import LinearDynamics, QuadraticCost, QuadraticTerminalCost
+    from zopt_b200.pytrees import Trajectory
+    I = np.eye(2)
+    solver = ilqrUtils.differentialDynamicProgramming if second_order else ilqrUtils.iterativeLqr
+    x0, uGuess = np.array([2., 1]), np.zeros((3, 2))
+    trajectory, L, J, converged, log = solver(LinearDynamics(I, I), QuadraticCost(I, I), QuadraticTerminalCost(I), x0, uGuess,
+                                              return_log=True)
+    assert bool(converged) and isinstance(trajectory, Trajectory)
+    assert trajectory.xTraj.shape == (4, 2) and L.shape == (3, 2, 2)
+    osolver = oilqr.differentialDynamicProgramming if second_order else oilqr.iterativeLqr
+    A = torch.eye(2, dtype=torch.float64)
+    olog = []
+    tr, Lr, Jr, cr = osolver(lambda x, u: A @ x + A @ u, lambda x, u: x @ A @ x + u @ A @ u, lambda x: x @ A @ x,
+                             torch.as_tensor(x0), torch.as_tensor(uGuess), log=olog)
+    assert int(log["iters"]) == len(olog) - 1
+    assert [e["alpha_idx"] for e in olog[1:]] == log["alpha_idx"][:int(log["iters"])].tolist()
+    assert relerr(trajectory.xTraj, tr.xTraj) < 1e-10 and relerr(L, Lr) < 1e-10 and abs(float(J) - float(Jr)) < 1e-10 * float(Jr)
+    with pytest.raises(TypeError):
+        solver(lambda x, u: x + u, QuadraticCost(I, I), QuadraticTerminalCost(I), x0, uGuess)
+
+
+@pytest.mark.parametrize("second_order,R_scale,spread", [(False, 1.0, 10.0), (True, 0.2, 5.0)])
+def test_solvers_quadcopter_vs_oracle_fp64(second_order, R_scale, spread):
+    """iLQR / DDP on the quadcopter, N=30, 3 forced iterations: step-size sequence first, then x, u, L, J at 1e-10"""
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    N, Bsz, iters = 30, 4, 3
+    x0, uG, Q, R, Qf = _quad_problem(N, Bsz, 21 + int(second_order), R_scale, spread)
+    solver = ilqrUtils.differentialDynamicProgramming if second_order else ilqrUtils.iterativeLqr
+    traj, L, J, conv, log = solver(QuadcopterEuler(0.1), QuadraticCost(Q, R), QuadraticTerminalCost(Qf), cuda(x0), uG,
+                                   maxIter=iters, tol=-1.0, return_log=True)
+    assert traj.xTraj.shape == (Bsz, N + 1, 12) and L.shape == (Bsz, N, 4, 12) and J.shape == (Bsz,) and conv.shape == (Bsz,)
+    dyn, rc, tc = _oracle_fns(Q, R, Qf)
+    osolver = oilqr.differentialDynamicProgramming if second_order else oilqr.iterativeLqr
+    for b in range(Bsz):
+        olog = []
+        tr, Lr, Jr, cr = osolver(dyn, rc, tc, torch.as_tensor(x0[b]), torch.as_tensor(uG), maxIter=iters, tol=-1.0, log=olog)
+        assert [e["alpha_idx"] for e in olog[1:]] == log["alpha_idx"][b].tolist()
+        assert relerr(log["J"][b], np.array([e["J"] for e in olog])) < 1e-10
+        assert relerr(traj.xTraj[b], tr.xTraj) < 1e-10 and relerr(traj.uTraj[b], tr.uTraj) < 1e-10
+        assert relerr(L[b], Lr) < 1e-10
+        assert not bool(conv[b]) and int(log["iters"][b]) == iters
+
+
+def test_solver_fp32_and_convergence_flags():
+    """fp32 run against the fp64 oracle: step-size sequences compared first, mismatches counted (never dropped);
+    matching problems gated at x,u 2e-5 and L 1e-4.  Also per-problem convergence freeze."""
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    N, Bsz, iters = 30, 6, 3
+    x0, uG, Q, R, Qf = _quad_problem(N, Bsz, 33)
+    args = (QuadcopterEuler(0.1), QuadraticCost(Q, R), QuadraticTerminalCost(Qf))
+    t64, L64, J64, c64, log64 = ilqrUtils.iterativeLqr(*args, cuda(x0), uG, maxIter=iters, tol=-1.0, return_log=True)
+    t32, L32, J32, c32, log32 = ilqrUtils.iterativeLqr(*args, cuda(x0, torch.float32), cuda(uG, torch.float32),
+                                                       maxIter=iters, tol=-1.0, return_log=True)
+    assert t32.xTraj.dtype == torch.float32
+    same = (log64["alpha_idx"] == log32["alpha_idx"]).all(dim=1).cpu().numpy()
+    assert same.sum() >= Bsz - 1, f"step-size sequence mismatches: {Bsz - same.sum()} of {Bsz}"
+    for b in np.nonzero(same)[0]:
+        assert relerr(t32.xTraj[b], t64.xTraj[b]) < 2e-5 and relerr(t32.uTraj[b], t64.uTraj[b]) < 2e-5
+        assert relerr(L32[b], L64[b]) < 1e-4
+    # huge tolerance: every problem converges after exactly one iteration and is frozen there
+    t1, L1, J1, c1, log1 = ilqrUtils.iterativeLqr(*args, cuda(x0), uG, maxIter=5, tol=1e12, return_log=True)
+    assert bool(c1.all()) and log1["iters"].tolist() == [1] * Bsz
+    assert (log1["alpha_idx"][:, 1:] == -1).all()
+    ta, La, Ja, ca, _ = ilqrUtils.iterativeLqr(*args, cuda(x0), uG, maxIter=1, tol=-1.0, return_log=True)
+    assert relerr(t1.xTraj, ta.xTraj) == 0 and relerr(L1, La) == 0
+    # maxIter = 0: the initial rollout, zero gains, not converged
+    t0, L0, J0, c0 = ilqrUtils.iterativeLqr(*args, cuda(x0), uG, maxIter=0)
+    assert not bool(c0.any()) and float(L0.abs().max()) == 0 and relerr(t0.uTraj[0], uG) == 0
+
+
+# =============================================================================================== mpcUtils
+def test_lqrMpc_reference_test_problem():  # reference tests/test_mpcUtils.py:8-23: status == "optimal"
+    from zopt_b200.mpcUtils import lqrMpc
+    I = np.eye(2)
+    inf = np.full(2, np.inf)
+    prob = lqrMpc(I, I, I, I, 2, -inf, inf, -inf, inf)
+    u, traj, status = prob.solve(np.ones(2))
+    assert status == "optimal"
+    # derived golden: bounds inactive => Riccati rollout u=[[-.6,-.6],[-.2,-.2]], x=[[1,1],[.4,.4],[.2,.2]]
+    assert traj.uTraj.cpu().numpy() == pytest.approx(np.array([[-0.6, -0.6], [-0.2, -0.2]]))
+    assert traj.xTraj.cpu().numpy() == pytest.approx(np.array([[1, 1], [0.4, 0.4], [0.2, 0.2]]))
+    assert u.cpu().numpy() == pytest.approx(np.array([-0.6, -0.6]))
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_lqrMpc_unbounded_equals_riccati(dt):
+    from zopt_b200.mpcUtils import lqrMpc
+    Bsz = 100
+    d, A, B, Q, R, N = _cfg2_arrays(Bsz, False)
+    inf12, inf4 = np.full(12, np.inf), np.full(4, np.inf)
+    prob = lqrMpc(cuda(A, dt), cuda(B, dt), cuda(Q, dt), cuda(R, dt), N, -inf12, inf12, -inf4, inf4, Qf=cuda(10 * Q, dt))
+    u, traj, status = prob.solve(cuda(d["xbar"], dt))
+    assert u.shape == (Bsz, 4) and traj.xTraj.shape == (Bsz, N + 1, 12) and (status == 0).all()
+    # oracle: Riccati with terminal 10Q (note: a proper terminal weight, not the Q[-1] quirk) + linear rollout
+    Qk = np.repeat(Q[:, None], N + 1, axis=1)
+    Qk[:, N] *= 10
+    Lref = olqr.discreteFiniteHorizonLqr_batched(np.repeat(A[:, None], N, 1), np.repeat(B[:, None], N, 1), Qk,
+                                                 np.repeat(R[:, None], N, 1), N)
+    x = d["xbar"].copy()
+    xs, us = [x], []
+    for k in range(N):
+        uk = -np.einsum('bij,bj->bi', Lref[:, k], x)
+        x = np.einsum('bij,bj->bi', A, x) + np.einsum('bij,bj->bi', B, uk)
+        xs.append(x)
+        us.append(uk)
+    tol = 1e-10 if dt == torch.float64 else 2e-5
+    assert per_problem_relerr(traj.xTraj, np.stack(xs, 1)).max() < tol
+    assert per_problem_relerr(traj.uTraj, np.stack(us, 1)).max() < tol
+    assert relerr(u, us[0]) < tol

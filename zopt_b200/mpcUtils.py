@@ -1,0 +1,105 @@
+"""
+LQR-MPC -- mirror of zopt/mpcUtils.py:12-81 (the plotting half, :84-202, is out of scope).
+
+`lqrMpc(A, B, Q, R, N, x_lb, x_ub, u_lb, u_ub, Qf=None).solve(x0)` solves
+
+    min  sum_{k<N} x_k'Q x_k + u_k'R u_k + x_N'Qf x_N
+    s.t. x_{k+1} = A x_k + B u_k,  x_lb <= x_k <= x_ub (k = 0..N),  u_lb <= u_k <= u_ub,  x_0 = x0
+
+exactly as the reference builds it with cvxpy (mpcUtils.py:47-59), for a whole batch of problems:
+every constructor array and `x0` may carry one leading batch axis.  The reference hands the QP to a
+third-party solver (cvxpy -> OSQP/Clarabel); here the solve runs in CUDA kernels.  When no bound is
+finite the optimum is the Riccati sweep + linear rollout (exact); with finite bounds it is the ADMM
+splitting OSQP uses, with the KKT solve done as a Riccati sweep.
+
+Returns `(u, Trajectory(xTraj, uTraj), status)`; un-batched calls return cvxpy's status string,
+batched calls an int8 tensor of codes (`STATUS[code]` gives the string).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import View, ZbAdmmOpts, check, dcode, lib, null_arr, pick_device, pick_dtype, ptr, stream_ptr, to_dev
+from .pytrees import Trajectory
+
+STATUS = ("optimal", "optimal_inaccurate", "infeasible")
+
+
+def _isinf_all(t, sign):
+    t = torch.as_tensor(np.asarray(t)) if not isinstance(t, torch.Tensor) else t
+    return bool(torch.all(torch.isinf(t) & ((t > 0) if sign > 0 else (t < 0))))
+
+
+class lqrMpc():
+
+    def __init__(self, A, B, Q, R, N, x_lb, x_ub, u_lb, u_ub, Qf=None):
+        """
+        Setup an LQR MPC problem (zopt/mpcUtils.py:14-59).  Shapes as the reference -- A (n,n), B (n,m), Q (n,n),
+        R (m,m), bounds (n,) / (m,), Qf defaults to Q -- each optionally with a leading batch axis.
+        """
+        if Qf is None:
+            Qf = Q
+        ops = [A, B, Q, R, Qf, x_lb, x_ub, u_lb, u_ub]
+        self.device = pick_device(*ops)
+        self.dtype = pick_dtype(A, B, Q, R, Qf)
+        self.ops = [to_dev(t, self.dtype, self.device) for t in ops]
+        self.N = int(N)
+        self.n, self.m = self.ops[1].shape[-2], self.ops[1].shape[-1]
+        core = [2, 2, 2, 2, 2, 1, 1, 1, 1]
+        self.Bsz, self.batched = 1, False
+        for t, nd in zip(self.ops, core):
+            if t.ndim == nd + 1:
+                self.batched = True
+                if t.shape[0] != 1:
+                    if self.Bsz not in (1, t.shape[0]):
+                        raise ValueError("inconsistent batch sizes")
+                    self.Bsz = t.shape[0]
+            elif t.ndim != nd:
+                raise ValueError(f"expected {nd} or {nd + 1} dimensions, got shape {tuple(t.shape)}")
+        self.views = [View(t, nd, False, t.ndim == nd + 1) for t, nd in zip(self.ops, core)]
+        self.bounded = not (_isinf_all(x_lb, -1) and _isinf_all(x_ub, +1) and _isinf_all(u_lb, -1) and
+                            _isinf_all(u_ub, +1))
+        self.iters = None
+
+    def solve(self, x0, **kwargs):
+        """
+        Solve the MPC step at state x0 (zopt/mpcUtils.py:61-81).  Keyword arguments follow OSQP's names as passed through
+        cvxpy in the reference demo (`eps_abs`, `eps_rel`, `max_iter`, `rho`, `sigma`, `alpha`); others are ignored.
+
+        Returns
+        -------
+            u : optimal control at the current time step, (m,) or (Bsz,m)
+            traj : Trajectory(xTraj (N+1,n), uTraj (N,m)) of the plan
+            status : "optimal" / "optimal_inaccurate" / "infeasible" (int8 codes when batched)
+        """
+        x0 = to_dev(x0, self.dtype, self.device)
+        batched = self.batched or x0.ndim == 2
+        Bsz = self.Bsz
+        if x0.ndim == 2 and x0.shape[0] != 1:
+            if Bsz not in (1, x0.shape[0]):
+                raise ValueError("inconsistent batch sizes")
+            Bsz = x0.shape[0]
+        x0 = (x0 if x0.ndim == 2 else x0[None]).expand(Bsz, self.n).contiguous()
+        N, n, m, dt, dev = self.N, self.n, self.m, self.dtype, self.device
+        u0 = torch.empty((Bsz, m), dtype=dt, device=dev)
+        xTraj = torch.empty((Bsz, N + 1, n), dtype=dt, device=dev)
+        uTraj = torch.empty((Bsz, N, m), dtype=dt, device=dev)
+        status = torch.empty((Bsz,), dtype=torch.int8, device=dev)
+        iters = torch.empty((Bsz,), dtype=torch.int32, device=dev)
+        wsb = lib.zb_mpc_workspace_bytes(dcode(dt), Bsz, N, n, m)
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+        opts = ZbAdmmOpts(int(kwargs.get("max_iter", 4000)), int(kwargs.get("check_termination", 25)),
+                          float(kwargs.get("rho", 0.1)), float(kwargs.get("sigma", 1e-6)), float(kwargs.get("alpha", 1.6)),
+                          float(kwargs.get("eps_abs", 1e-3)), float(kwargs.get("eps_rel", 1e-3)))
+        check(lib.zb_mpc_lqr_solve(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, n, m, *[v.ref() for v in self.views],
+                                   int(self.bounded), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
+                                   ptr(iters), ptr(ws), wsb))
+        self.iters = iters
+        if not batched:
+            return u0[0], Trajectory(xTraj[0], uTraj[0]), STATUS[int(status[0])]
+        return u0, Trajectory(xTraj, uTraj), status
+
+    @staticmethod
+    def status_str(status, i=0):
+        return STATUS[int(status[i])]
