@@ -165,9 +165,11 @@ def test_bilinear_random_vs_oracle():
     r = rng.normal(size=(Bsz, N, m)) * 0.1
     q0 = rng.normal(size=(Bsz, N))
     Lr, lr = olqr.bilinearAffineLqr_batched(A, Bm, d, Q, R, Hm, q, r, q0, N)
-    for dt in DT:
+    # fp32 gate is 1e-4 here, not 1e-5: the as-written recursion (lqrUtils.py:251, no Joseph form) run in fp32 with
+    # NumPy/LAPACK on this very N=100 problem is itself 2.2e-5 (L) / 3.7e-5 (l) away from fp64 (DESIGN.md "Tolerances").
+    for dt, tol in ((torch.float64, 1e-10), (torch.float32, 1e-4)):
         L, l = bilinearAffineLqr(*(cuda(t, dt) for t in (A, Bm, d, Q, R, Hm, q, r, q0)), N)
-        assert per_problem_relerr(L, Lr).max() < TOL[dt] and per_problem_relerr(l, lr).max() < TOL[dt]
+        assert per_problem_relerr(L, Lr).max() < tol and per_problem_relerr(l, lr).max() < tol
     # shared (un-batched) operands broadcast over a batched one
     L, l = bilinearAffineLqr(A[0], Bm[0], d, Q[0], R[0], Hm, q[0], r, q0, N)
     assert per_problem_relerr(L, Lr).max() < 1e-10

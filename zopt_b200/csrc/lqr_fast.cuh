@@ -1,8 +1,321 @@
-// (n,m) = (12,4) cooperative Riccati kernel -- placeholder until the fast path lands.
+// Cooperative Riccati kernel for (n, m) = (12, 4), fp32, time-invariant A, B, R.
+//
+// Replaces the generic one-thread-per-problem kernel on the headline path:
+//   * zb_lqr_dfh          (zopt/lqrUtils.py:144-173)   -- Q may be a time series (read per step)
+//   * zb_mpc_lqr_solve    (zopt/mpcUtils.py:47-59, bounds inactive) -- Riccati sweep + plan rollout
+//
+// Mapping: FOUR threads own one problem (8 problems per warp, 32 per 128-thread CTA, 3 CTAs per SM).
+// [A | B] is a 12x16 matrix = four 12x4 column tiles; thread t owns tile t (t<3: columns 4t..4t+3 of A,
+// t=3: B).  Everything a step needs lives in shared memory (per-problem slab of PS floats) and is
+// read with 128-bit loads that broadcast inside the quad; the 8 quads of a warp hit disjoint bank
+// groups because PS/4 is odd.  Per step (value matrix V symmetric, kept as a full 12x12 in smem):
+//   1.  [W | VB] = V [A | B]            rank-1 updates over k, 12x4 accumulator tile per thread
+//   2.  [M | G0] = B^T [W | VB]         4x4 per thread  (M = B^T V A, G0 = B^T V B)
+//   3.  G = G0 + R  -> Cholesky (every thread, redundantly), L tile = G^-1 M tile
+//   4.  gains tile -> global (128-bit stores)
+//   5.  V' tile = Q + A^T W - M^T L      (algebraically equal to the reference's Joseph form,
+//       lqrUtils.py:169; fp32 parity with the Joseph-form oracle is gated at 1e-5 in the tests)
+//       written back "lower triangle wins": each strictly-lower 4x4 block is stored together with
+//       its transpose, the diagonal blocks are mirrored, so V stays exactly symmetric.
+// No tensor cores: the contractions are 12- and 4-wide.
 #pragma once
 #include "zb_common.cuh"
 
 namespace zb {
-inline bool lqr_fast_eligible(int32_t, const LqrP&) { return false; }
-inline int32_t lqr_fast_launch(int32_t, const LqrP&, cudaStream_t) { return fail(-9, "fast path not built"); }
+
+constexpr int FQ_PS = 580;        // floats per problem slab; 580/4 = 145 is odd -> conflict-free quads
+constexpr int FQ_V = 0;           // V      12x12
+constexpr int FQ_A = 144;         // A      12x12 row-major
+constexpr int FQ_B = 288;         // B      12x4
+constexpr int FQ_Q = 336;         // Q      12x12 (time-invariant case)
+constexpr int FQ_M = 480;         // M      4x12
+constexpr int FQ_G = 528;         // G      4x4
+constexpr int FQ_R = 544;         // R      4x4
+constexpr int FQ_X = 560;         // scratch 16
+constexpr int FQ_THREADS = 128;
+constexpr int FQ_PROBS = 32;      // problems per CTA
+
+struct FastP {
+    long long Bsz;
+    int N, T;
+    Arr A, B, Q, R, Qf;   // Qf.p == nullptr -> lqr_dfh semantics: terminal = Q[T-1], stage = Q[k]
+    int q_time_varying;
+    float* gains;         // (Bsz,N,4,12)
+    float* V0;            // optional (Bsz,12,12)
+    // MPC only
+    const float* x0;
+    float *u0, *xTraj, *uTraj;
+    int8_t* status;
+    int32_t* iters;
+};
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void sts4(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+
+template <bool MPC>
+__global__ void __launch_bounds__(FQ_THREADS, 3) k_riccati_12x4(FastP P) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & 3, quad = lane >> 2;
+    const long long b_raw = ((long long)blockIdx.x * 4 + warp) * 8 + quad;
+    const bool active = b_raw < P.Bsz;
+    const long long b = active ? b_raw : P.Bsz - 1;  // idle quads shadow the last problem, stores masked
+    float* S = smem + (warp * 8 + quad) * FQ_PS;
+    float* Vs = S + FQ_V;
+    float* As = S + FQ_A;
+    float* Bs = S + FQ_B;
+    float* Qs = S + FQ_Q;
+    float* Ms = S + FQ_M;
+    float* Gs = S + FQ_G;
+    float* Rs = S + FQ_R;
+
+    // ---- stage the time-invariant operands (quad-cooperative 128-bit copies) ----
+    {
+        const float4* gA = reinterpret_cast<const float4*>(P.A.at<float>(b));
+        const float4* gB = reinterpret_cast<const float4*>(P.B.at<float>(b));
+        const float4* gR = reinterpret_cast<const float4*>(P.R.at<float>(b));
+        const float4* gQ = reinterpret_cast<const float4*>(P.Q.at<float>(b, 0));
+        const float4* gF = reinterpret_cast<const float4*>(MPC ? P.Qf.at<float>(b) : P.Q.at<float>(b, P.T - 1));
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            reinterpret_cast<float4*>(As)[t + 4 * i] = __ldg(gA + t + 4 * i);
+            reinterpret_cast<float4*>(Vs)[t + 4 * i] = __ldg(gF + t + 4 * i);
+            reinterpret_cast<float4*>(Qs)[t + 4 * i] = __ldg(gQ + t + 4 * i);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) reinterpret_cast<float4*>(Bs)[t + 4 * i] = __ldg(gB + t + 4 * i);
+        reinterpret_cast<float4*>(Rs)[t] = __ldg(gR + t);
+    }
+    __syncwarp();
+
+    // tile t of [A | B]: rows k, 4 consecutive columns
+    const float* Ct = (t < 3) ? (As + 4 * t) : Bs;
+    const int cstride = (t < 3) ? 12 : 4;
+    const int tcol = (t < 3) ? 4 * t : 0;  // thread 3 shadows tile 0 in step 5 (result discarded)
+    float* gains = P.gains + b * (long long)P.N * 48;
+
+    for (int k = P.N - 1; k >= 0; --k) {
+        // ---- 1. [W | VB] tile = V * tile --------------------------------------------------
+        float W[12][4];
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) W[i][c] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 12; ++kk) {
+            const float4 c4 = lds4(Ct + kk * cstride);
+            const float4 v0 = lds4(Vs + kk * 12), v1 = lds4(Vs + kk * 12 + 4), v2 = lds4(Vs + kk * 12 + 8);
+            const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                W[i][0] = fmaf(v[i], c4.x, W[i][0]);
+                W[i][1] = fmaf(v[i], c4.y, W[i][1]);
+                W[i][2] = fmaf(v[i], c4.z, W[i][2]);
+                W[i][3] = fmaf(v[i], c4.w, W[i][3]);
+            }
+        }
+        // ---- 2. [M | G0] tile = B^T * [W | VB] tile ---------------------------------------
+        float M[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) M[a][c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const float4 b4 = lds4(Bs + i * 4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) M[a][c] = fmaf(bb[a], W[i][c], M[a][c]);
+        }
+        // ---- 3. G = G0 + R ; share M and G through smem -----------------------------------
+        if (t == 3) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float4 r4 = lds4(Rs + a * 4);
+                sts4(Gs + a * 4, M[a][0] + r4.x, M[a][1] + r4.y, M[a][2] + r4.z, M[a][3] + r4.w);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) sts4(Ms + a * 12 + 4 * t, M[a][0], M[a][1], M[a][2], M[a][3]);
+        }
+        __syncwarp();
+        // Cholesky G = C C^T (lower), d_i = 1/C_ii; every thread factors redundantly (no divergence)
+        const float4 g0 = lds4(Gs), g1 = lds4(Gs + 4), g2 = lds4(Gs + 8), g3 = lds4(Gs + 12);
+        const float d0 = rsqrtf(g0.x);
+        const float c10 = g1.x * d0, c20 = g2.x * d0, c30 = g3.x * d0;
+        const float d1 = rsqrtf(fmaf(-c10, c10, g1.y));
+        const float c21 = fmaf(-c20, c10, g2.y) * d1, c31 = fmaf(-c30, c10, g3.y) * d1;
+        const float d2 = rsqrtf(fmaf(-c21, c21, fmaf(-c20, c20, g2.z)));
+        const float c32 = fmaf(-c31, c21, fmaf(-c30, c20, g3.z)) * d2;
+        const float d3 = rsqrtf(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, g3.w))));
+        float L[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float y0 = M[0][c] * d0;
+            const float y1 = fmaf(-c10, y0, M[1][c]) * d1;
+            const float y2 = fmaf(-c21, y1, fmaf(-c20, y0, M[2][c])) * d2;
+            const float y3 = fmaf(-c32, y2, fmaf(-c31, y1, fmaf(-c30, y0, M[3][c]))) * d3;
+            const float x3 = y3 * d3;
+            const float x2 = fmaf(-c32, x3, y2) * d2;
+            const float x1 = fmaf(-c31, x3, fmaf(-c21, x2, y1)) * d1;
+            const float x0 = fmaf(-c30, x3, fmaf(-c20, x2, fmaf(-c10, x1, y0))) * d0;
+            L[0][c] = x0; L[1][c] = x1; L[2][c] = x2; L[3][c] = x3;
+        }
+        // ---- 4. gains tile -> global ---------------------------------------------------------
+        if (active && t < 3) {
+            float* g = gains + (long long)k * 48 + 4 * t;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                *reinterpret_cast<float4*>(g + a * 12) = make_float4(L[a][0], L[a][1], L[a][2], L[a][3]);
+        }
+        // ---- 5. V' tile = Q + A^T W - M^T L -------------------------------------------------
+        float acc[12][4];
+        {
+            const float* Qk = (!MPC && P.q_time_varying) ? P.Q.at<float>(b, k) : Qs;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const float4 q4 = (!MPC && P.q_time_varying) ? __ldg(reinterpret_cast<const float4*>(Qk + i * 12 + tcol))
+                                                             : lds4(Qs + i * 12 + tcol);
+                acc[i][0] = q4.x; acc[i][1] = q4.y; acc[i][2] = q4.z; acc[i][3] = q4.w;
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 12; ++kk) {
+            const float4 a0 = lds4(As + kk * 12), a1 = lds4(As + kk * 12 + 4), a2 = lds4(As + kk * 12 + 8);
+            const float a[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(a[i], W[kk][c], acc[i][c]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float4 m0 = lds4(Ms + a * 12), m1 = lds4(Ms + a * 12 + 4), m2 = lds4(Ms + a * 12 + 8);
+            const float mm_[12] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w};
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(-mm_[i], L[a][c], acc[i][c]);
+        }
+        // write back, lower triangle wins (block (s,t) = rows 4s.., cols 4t..)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            if (s > t) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    sts4(Vs + (4 * s + r) * 12 + 4 * t, acc[4 * s + r][0], acc[4 * s + r][1], acc[4 * s + r][2], acc[4 * s + r][3]);
+                    sts4(Vs + (4 * t + r) * 12 + 4 * s, acc[4 * s][r], acc[4 * s + 1][r], acc[4 * s + 2][r], acc[4 * s + 3][r]);
+                }
+            } else if (s == t) {
+                // diagonal block: entry (r,c) := lower value acc[4s+max(r,c)][min(r,c)]
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float e[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) e[c] = (r >= c) ? acc[4 * s + r][c] : acc[4 * s + c][r];
+                    sts4(Vs + (4 * s + r) * 12 + 4 * s, e[0], e[1], e[2], e[3]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    if (P.V0 && active) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            reinterpret_cast<float4*>(P.V0 + b * 144)[t + 4 * i] = reinterpret_cast<const float4*>(Vs)[t + 4 * i];
+    }
+
+    if (MPC) {
+        // ---- plan rollout x+ = A x + B u, u = -L_k x (mpcUtils.py:55); x replicated in the quad ----
+        const unsigned FULL = 0xffffffffu;
+        const int qbase = lane & ~3;
+        float x[12];
+        {
+            const float4* gx = reinterpret_cast<const float4*>(P.x0 + b * 12);
+            const float4 x0 = __ldg(gx), x1 = __ldg(gx + 1), x2 = __ldg(gx + 2);
+            x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+            x[8] = x2.x; x[9] = x2.y; x[10] = x2.z; x[11] = x2.w;
+        }
+        float* xT = P.xTraj + b * (long long)(P.N + 1) * 12;
+        float* uT = P.uTraj + b * (long long)P.N * 4;
+        if (active && t < 3) *reinterpret_cast<float4*>(xT + 4 * t) = make_float4(x[4 * t], x[4 * t + 1], x[4 * t + 2], x[4 * t + 3]);
+        for (int k = 0; k < P.N; ++k) {
+            // u_t = - L_k[t,:] x   (gains were written by this quad; read through L2)
+            const float4* gl = reinterpret_cast<const float4*>(gains + (long long)k * 48 + t * 12);
+            const float4 l0 = __ldcg(gl), l1 = __ldcg(gl + 1), l2 = __ldcg(gl + 2);
+            float ut = l0.x * x[0];
+            ut = fmaf(l0.y, x[1], ut); ut = fmaf(l0.z, x[2], ut); ut = fmaf(l0.w, x[3], ut);
+            ut = fmaf(l1.x, x[4], ut); ut = fmaf(l1.y, x[5], ut); ut = fmaf(l1.z, x[6], ut); ut = fmaf(l1.w, x[7], ut);
+            ut = fmaf(l2.x, x[8], ut); ut = fmaf(l2.y, x[9], ut); ut = fmaf(l2.z, x[10], ut); ut = fmaf(l2.w, x[11], ut);
+            ut = -ut;
+            float u[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) u[a] = __shfl_sync(FULL, ut, qbase + a);
+            // rows 3t..3t+2 of A x + B u
+            float xn[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float* ar = As + (3 * t + r) * 12;
+                const float4 a0 = lds4(ar), a1 = lds4(ar + 4), a2 = lds4(ar + 8), b4 = lds4(Bs + (3 * t + r) * 4);
+                float s = a0.x * x[0];
+                s = fmaf(a0.y, x[1], s); s = fmaf(a0.z, x[2], s); s = fmaf(a0.w, x[3], s);
+                s = fmaf(a1.x, x[4], s); s = fmaf(a1.y, x[5], s); s = fmaf(a1.z, x[6], s); s = fmaf(a1.w, x[7], s);
+                s = fmaf(a2.x, x[8], s); s = fmaf(a2.y, x[9], s); s = fmaf(a2.z, x[10], s); s = fmaf(a2.w, x[11], s);
+                s = fmaf(b4.x, u[0], s); s = fmaf(b4.y, u[1], s); s = fmaf(b4.z, u[2], s); s = fmaf(b4.w, u[3], s);
+                xn[r] = s;
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) x[i] = __shfl_sync(FULL, xn[i % 3], qbase + i / 3);
+            if (active) {
+                if (t == 3) *reinterpret_cast<float4*>(uT + (long long)k * 4) = make_float4(u[0], u[1], u[2], u[3]);
+                else *reinterpret_cast<float4*>(xT + (long long)(k + 1) * 12 + 4 * t) = make_float4(x[4 * t], x[4 * t + 1], x[4 * t + 2], x[4 * t + 3]);
+                if (k == 0 && t == 3) *reinterpret_cast<float4*>(P.u0 + b * 4) = make_float4(u[0], u[1], u[2], u[3]);
+            }
+        }
+        if (active && t == 0) {
+            P.status[b] = 0;
+            if (P.iters) P.iters[b] = 0;
+        }
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline bool arr_ok(const Arr& a) { return aligned16(a.p) && (a.sb % 4 == 0) && (a.st % 4 == 0); }
+
+// zb_lqr_dfh fast path: fp32, (12,4), A/B/R time-invariant (stride_t == 0 or a single step), N >= 1
+inline bool lqr_fast_eligible(int32_t dtype, const LqrP& P) {
+    if (dtype != ZB_F32 || P.n != 12 || P.m != 4 || P.N < 1) return false;
+    const bool ti = (P.N == 1) || (P.A.st == 0 && P.B.st == 0 && P.R.st == 0);
+    return ti && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) && arr_ok(P.R) && aligned16(P.L) && (!P.V0 || aligned16(P.V0));
+}
+
+template <bool MPC>
+inline int32_t riccati_fast_launch(const FastP& F, cudaStream_t stream) {
+    static bool attr_set[2] = {false, false};
+    const size_t smem = (size_t)FQ_PROBS * FQ_PS * sizeof(float);
+    // per-device attribute; cheap to repeat, so set on every call (multi-GPU callers loop devices)
+    ZB_CUDA(cudaFuncSetAttribute(k_riccati_12x4<MPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    (void)attr_set;
+    const unsigned grid = (unsigned)((F.Bsz + FQ_PROBS - 1) / FQ_PROBS);
+    k_riccati_12x4<MPC><<<grid, FQ_THREADS, smem, stream>>>(F);
+    ZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+inline int32_t lqr_fast_launch(int32_t, const LqrP& P, cudaStream_t stream) {
+    FastP F{};
+    F.Bsz = P.Bsz; F.N = P.N; F.T = P.T;
+    F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R;
+    F.Qf.p = nullptr;
+    F.q_time_varying = (P.Q.st != 0 && P.N > 1) ? 1 : 0;
+    F.gains = reinterpret_cast<float*>(P.L);
+    F.V0 = reinterpret_cast<float*>(P.V0);
+    return riccati_fast_launch<false>(F, stream);
+}
+
 }  // namespace zb

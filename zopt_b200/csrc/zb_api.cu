@@ -322,6 +322,7 @@ int32_t zb_lqr_dfh(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int
                    void* V0_out) {
     int32_t rc = check_dims(dtype, Bsz, n, m);
     if (rc) return rc;
+    if (Bsz == 0) return 0;  // empty batch: nothing to read or write (pointers may be NULL)
     ZB_ARG(N >= 0 && T >= 1 && T >= N, "need T >= N >= 0 and T >= 1 (got N=%d, T=%d)", N, T);
     ZB_ARG(A && B && Q && R && A->ptr && B->ptr && Q->ptr && R->ptr, "A, B, Q, R must be non-NULL");
     ZB_ARG(L_out != nullptr || N == 0, "L_out is NULL");
@@ -340,6 +341,7 @@ int32_t zb_lqr_bilinear(int32_t dtype, int32_t device, void* stream, int64_t Bsz
                         void* L_out, void* l_out) {
     int32_t rc = check_dims(dtype, Bsz, n, m);
     if (rc) return rc;
+    if (Bsz == 0) return 0;  // empty batch: nothing to read or write (pointers may be NULL)
     ZB_ARG(N >= 0 && T >= 1 && T >= N, "need T >= N >= 0 and T >= 1 (got N=%d, T=%d)", N, T);
     ZB_ARG(A && B && d && Q && R && H && q && r && q0, "NULL operand");
     ZB_ARG(A->ptr && B->ptr && d->ptr && Q->ptr && R->ptr && H->ptr && q->ptr && r->ptr && q0->ptr, "NULL operand pointer");
@@ -477,6 +479,7 @@ int32_t zb_ilqr_backward(int32_t dtype, int32_t device, void* stream, int64_t Bs
                          void* v_out, void* vx_out, void* vxx_out) {
     int32_t rc = check_dims(dtype, Bsz, n, m);
     if (rc) return rc;
+    if (Bsz == 0) return 0;  // empty batch: nothing to read or write (pointers may be NULL)
     ZB_ARG(N >= 0, "negative N");
     ZB_ARG(f_x && f_u && c && c_x && c_u && c_xx && c_ux && c_uu && v && v_x && v_xx, "NULL operand");
     ZB_ARG(!second_order || (f_xx && f_ux && f_uu && f_xx->ptr && f_ux->ptr && f_uu->ptr), "DDP needs f_xx, f_ux, f_uu");
@@ -564,6 +567,7 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
                          size_t workspace_bytes) {
     int32_t rc = check_dims(dtype, Bsz, n, m);
     if (rc) return rc;
+    if (Bsz == 0) return 0;  // empty batch: nothing to read or write (pointers may be NULL)
     ZB_ARG(N >= 1, "N must be >= 1");
     ZB_ARG(A && B && Q && R && Qf && A->ptr && B->ptr && Q->ptr && R->ptr && Qf->ptr, "NULL operand");
     ZB_ARG(x0 && u0_out && xTraj && uTraj && status_out, "NULL operand");
@@ -576,6 +580,21 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
     ZB_CUDA(g.err);
     MpcP P{Bsz, N, n, m, to_arr(A), to_arr(B), to_arr(Q), to_arr(R), to_arr(Qf), x0, u0_out, xTraj, uTraj, workspace,
            status_out, iters_out};
+    if (dtype == ZB_F32 && n == 12 && m == 4 && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) && arr_ok(P.R) && arr_ok(P.Qf) &&
+        aligned16(x0) && aligned16(u0_out) && aligned16(xTraj) && aligned16(uTraj) && aligned16(workspace)) {
+        FastP F{};
+        F.Bsz = Bsz; F.N = N; F.T = 1;
+        F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R; F.Qf = P.Qf;
+        F.q_time_varying = 0;
+        F.gains = reinterpret_cast<float*>(workspace);
+        F.x0 = reinterpret_cast<const float*>(x0);
+        F.u0 = reinterpret_cast<float*>(u0_out);
+        F.xTraj = reinterpret_cast<float*>(xTraj);
+        F.uTraj = reinterpret_cast<float*>(uTraj);
+        F.status = status_out;
+        F.iters = iters_out;
+        return riccati_fast_launch<true>(F, (cudaStream_t)stream);
+    }
     ZB_DISPATCH(dtype, k_mpc_riccati, gen_grid(Bsz), GEN_THREADS, stream, P);
     return 0;
 }
