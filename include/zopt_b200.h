@@ -151,7 +151,8 @@ ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_
 /* ---- zopt/mpcUtils.py:12-81 lqrMpc(A,B,Q,R,N,x_lb,x_ub,u_lb,u_ub,Qf).solve(x0) --------------------
  * min sum_{k<N} x'Qx + u'Ru + x_N'Qf x_N  s.t. x+ = Ax + Bu, x_lb<=x_k<=x_ub (k=0..N), u_lb<=u_k<=u_ub.
  * Bounds may be +-inf.  When no bound can bind the solve is the exact Riccati sweep + rollout;
- * otherwise ADMM (the OSQP splitting) whose linear solve is a Riccati sweep.
+ * otherwise ADMM (over-relaxed, residual-balanced rho, as OSQP) with the dynamics kept exact: the linear solve of
+ * every iteration is a vector Riccati sweep + rollout against gains factored once per rho.
  * status_out (Bsz) int8: 0 optimal, 1 optimal_inaccurate (max_iter hit), 2 infeasible.
  * iters_out (Bsz) int32 ADMM iterations (0 on the unconstrained path). */
 typedef struct zb_admm_opts {
@@ -159,6 +160,7 @@ typedef struct zb_admm_opts {
     int32_t check_every; /* default 25 */
     double rho, sigma, alpha; /* 0.1, 1e-6, 1.6 */
     double eps_abs, eps_rel;   /* 1e-3, 1e-3 */
+    double eps_prim_inf;       /* 1e-4: primal-infeasibility certificate tolerance */
 } zb_admm_opts;
 ZB_API size_t zb_mpc_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m);
 ZB_API int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t n, int32_t m,

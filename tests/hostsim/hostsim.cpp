@@ -10,6 +10,7 @@ using std::fabs;
 using std::sqrt;
 using std::sin;
 using std::cos;
+using std::fmax;
 #include "../../include/zopt_b200.h"
 #include "../../zopt_b200/csrc/zb_problems.cuh"
 
@@ -202,5 +203,24 @@ EXPORT int hs_ilqr_solve(int dtype, int64_t Bsz, int N, int second_order, const 
                              (double*)xTraj, (double*)uTraj, (double*)L, (double*)J, conv, iters, alpha_log, (double*)J_log);
     else solve<float>(Bsz, N, second_order, model, cost, (const float*)x0, (const float*)uGuess, maxIter, tol,
                       (float*)xTraj, (float*)uTraj, (float*)L, (float*)J, conv, iters, alpha_log, (float*)J_log);
+    return 0;
+}
+
+EXPORT long long hs_admm_ws_elems(int N, int n, int m) { return admm_ws_elems(N, n, m); }
+
+EXPORT int hs_mpc_admm(int dtype, int64_t Bsz, int N, int n, int m, const zb_arr* A, const zb_arr* B, const zb_arr* Q,
+                       const zb_arr* R, const zb_arr* Qf, const zb_arr* xlb, const zb_arr* xub, const zb_arr* ulb,
+                       const zb_arr* uub, const void* x0, int max_iter, int check_every, double rho, double alpha,
+                       double eps_abs, double eps_rel, double eps_inf, void* u0, void* xTraj, void* uTraj,
+                       int8_t* status, int32_t* iters, void* ws) {
+    AdmmP P{};
+    P.Bsz = Bsz; P.N = N; P.n = n; P.m = m;
+    P.A = A_(A); P.B = A_(B); P.Q = A_(Q); P.R = A_(R); P.Qf = A_(Qf);
+    P.xlb = A_(xlb); P.xub = A_(xub); P.ulb = A_(ulb); P.uub = A_(uub);
+    P.x0 = x0; P.u0 = u0; P.xTraj = xTraj; P.uTraj = uTraj; P.status = status; P.iters = iters;
+    P.ws = ws; P.ws_stride = admm_ws_elems(N, n, m);
+    P.max_iter = max_iter; P.check_every = check_every; P.rho = rho; P.alpha = alpha;
+    P.eps_abs = eps_abs; P.eps_rel = eps_rel; P.eps_inf = eps_inf;
+    for (int64_t b = 0; b < Bsz; ++b) dtype ? admm_problem<double>(P, b) : admm_problem<float>(P, b);
     return 0;
 }

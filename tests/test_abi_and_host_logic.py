@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.ZbArr) == 24
     assert C.sizeof(_lib.ZbModel) == 4 * 4 + 8 + 24 + 2 * 24
     assert C.sizeof(_lib.ZbCost) == 72
-    assert C.sizeof(_lib.ZbAdmmOpts) == 8 + 5 * 8
+    assert C.sizeof(_lib.ZbAdmmOpts) == 8 + 6 * 8
 
 
 def test_argument_errors_are_reported_without_a_gpu():

@@ -483,3 +483,49 @@ def test_lqrMpc_unbounded_equals_riccati(dt):
     assert per_problem_relerr(traj.xTraj, np.stack(xs, 1)).max() < tol
     assert per_problem_relerr(traj.uTraj, np.stack(us, 1)).max() < tol
     assert relerr(u, us[0]) < tol
+
+
+def _mpc_demo():
+    A, B = (t.numpy() for t in OQuadcopter().linearizeInertial(np.zeros(12), configs.U_TRIM, 0.1))
+    x_ub = np.array([1, 1, 1, 0.3, 0.3, 0.1, 0.5, 0.5, np.inf, np.inf, np.inf, np.inf])
+    u_ub = np.array([3.0, 3, 3, 3])
+    return A, B, np.eye(12), np.eye(4), 25, -x_ub, x_ub, -u_ub, u_ub
+
+
+def test_lqrMpc_box_constrained_vs_oracle():
+    """demos/lqrMpc.py:11-47 problem (bounds bind: 10 m offset, |v| <= 1).  Reference parity is UNPINNED for this path
+    (reference test asserts only status == "optimal"); gates: agreement with the tight-tolerance oracle QP solve,
+    KKT residuals, exact dynamics, the reference test's own assertion, infeasibility reporting."""
+    from oracle import mpc as ompc
+    from zopt_b200.mpcUtils import lqrMpc
+    A, B, Q, R, N, xlb, xub, ulb, uub = _mpc_demo()
+    rng = np.random.default_rng(4)
+    Bsz = 6
+    x0 = np.zeros((Bsz, 12))
+    x0[:, 9:12] = rng.uniform(-10, 10, (Bsz, 3))
+    x0[0, 9:12] = [10, 10, 10]
+    x0[5, 0] = 2.0  # outside the state box -> infeasible
+    prob = lqrMpc(A, B, Q, R, N, xlb, xub, ulb, uub)
+    u, traj, status = prob.solve(cuda(x0), eps_abs=1e-7, eps_rel=1e-7, max_iter=20000)
+    assert status.tolist() == [0, 0, 0, 0, 0, 2] and torch.isnan(traj.uTraj[5]).all()
+    xT, uT = traj.xTraj.cpu().numpy(), traj.uTraj.cpu().numpy()
+    for b in range(5):
+        ur0, xr, ur, st, info = ompc.solve_qp(A, B, Q, R, N, xlb, xub, ulb, uub, x0[b])
+        assert st == "optimal"
+        assert np.max(np.abs(uT[b] - ur)) < 5e-4 * max(1.0, np.max(np.abs(ur)))
+        J = sum(xT[b, k] @ Q @ xT[b, k] + uT[b, k] @ R @ uT[b, k] for k in range(N)) + xT[b, N] @ Q @ xT[b, N]
+        assert abs(J - info["J"]) < 1e-6 * info["J"]
+        k = ompc.kkt_residuals(A, B, Q, R, N, xlb, xub, ulb, uub, x0[b], uT[b])
+        assert k["stationarity"] < 1e-3 and k["primal_violation"] < 1e-5
+        assert np.max(np.abs(xT[b, 1:] - (xT[b, :-1] @ A.T + uT[b] @ B.T))) < 1e-12
+    # the demo's own solver settings (eps 1e-2) and fp32: still "optimal" and close in cost
+    u2, traj2, status2 = prob.solve(cuda(x0[:5]), eps_abs=1e-2, eps_rel=1e-2)
+    assert (status2 == 0).all()
+    prob32 = lqrMpc(*(cuda(t, torch.float32) for t in (A, B, Q, R)), N, xlb, xub, ulb, uub)
+    u3, traj3, status3 = prob32.solve(cuda(x0[:5], torch.float32))
+    assert (status3 == 0).all() and relerr(traj3.uTraj, uT[:5]) < 5e-2
+    # un-batched reference-style call (tests/test_mpcUtils.py:8-23)
+    I, one = np.eye(2), np.ones(2)
+    u, traj, status = lqrMpc(I, I, I, I, 2, -one, one, -one, one).solve(one)
+    assert status == "optimal"
+    assert traj.uTraj.cpu().numpy() == pytest.approx(np.array([[-0.6, -0.6], [-0.2, -0.2]]), abs=1e-3)

@@ -35,7 +35,7 @@ class ZbCost(C.Structure):
 
 class ZbAdmmOpts(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("check_every", C.c_int32), ("rho", C.c_double), ("sigma", C.c_double),
-                ("alpha", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double)]
+                ("alpha", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("eps_prim_inf", C.c_double)]
 
 
 _P = C.c_void_p

@@ -267,6 +267,12 @@ __global__ void __launch_bounds__(GEN_THREADS) k_mpc_riccati(MpcP P) {
     if (P.iters) P.iters[b] = 0;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_mpc_admm(AdmmP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b < P.Bsz) admm_problem<T>(P, b);
+}
+
 // dependent-FMA throughput probe (roofline denominator)
 template <typename T, int ILP>
 __global__ void k_peak_fma(T* out, int iters) {
@@ -556,7 +562,7 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
 
 size_t zb_mpc_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m) {
     size_t e = dtype == ZB_F64 ? 8 : 4;
-    return align256(e * Bsz * N * m * n) + 256;
+    return align256(e * Bsz * (size_t)admm_ws_elems(N, n, m)) + 256;  // >= the gains buffer of the unconstrained path
 }
 
 int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t n, int32_t m,
@@ -573,11 +579,26 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
     ZB_ARG(x0 && u0_out && xTraj && uTraj && status_out, "NULL operand");
     size_t need = zb_mpc_workspace_bytes(dtype, Bsz, N, n, m);
     ZB_ARG(workspace && workspace_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
-    if (bounded) return fail(-3, "box-constrained lqrMpc (ADMM tier) is not implemented yet");
-    (void)x_lb; (void)x_ub; (void)u_lb; (void)u_ub; (void)opts;
-    if (Bsz == 0) return 0;
     DeviceGuard g(device);
     ZB_CUDA(g.err);
+    if (bounded) {
+        ZB_ARG(x_lb && x_ub && u_lb && u_ub && x_lb->ptr && x_ub->ptr && u_lb->ptr && u_ub->ptr, "bounds are NULL");
+        AdmmP P{};
+        P.Bsz = Bsz; P.N = N; P.n = n; P.m = m;
+        P.A = to_arr(A); P.B = to_arr(B); P.Q = to_arr(Q); P.R = to_arr(R); P.Qf = to_arr(Qf);
+        P.xlb = to_arr(x_lb); P.xub = to_arr(x_ub); P.ulb = to_arr(u_lb); P.uub = to_arr(u_ub);
+        P.x0 = x0; P.u0 = u0_out; P.xTraj = xTraj; P.uTraj = uTraj; P.status = status_out; P.iters = iters_out;
+        P.ws = workspace; P.ws_stride = admm_ws_elems(N, n, m);
+        P.max_iter = opts && opts->max_iter > 0 ? opts->max_iter : 4000;
+        P.check_every = opts && opts->check_every > 0 ? opts->check_every : 25;
+        P.rho = opts && opts->rho > 0 ? opts->rho : 0.1;
+        P.alpha = opts && opts->alpha > 0 ? opts->alpha : 1.6;
+        P.eps_abs = opts && opts->eps_abs > 0 ? opts->eps_abs : 1e-3;
+        P.eps_rel = opts && opts->eps_rel > 0 ? opts->eps_rel : 1e-3;
+        P.eps_inf = opts && opts->eps_prim_inf > 0 ? opts->eps_prim_inf : 1e-4;
+        ZB_DISPATCH(dtype, k_mpc_admm, gen_grid(Bsz), GEN_THREADS, stream, P);
+        return 0;
+    }
     MpcP P{Bsz, N, n, m, to_arr(A), to_arr(B), to_arr(Q), to_arr(R), to_arr(Qf), x0, u0_out, xTraj, uTraj, workspace,
            status_out, iters_out};
     if (dtype == ZB_F32 && n == 12 && m == 4 && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) && arr_ok(P.R) && arr_ok(P.Qf) &&

@@ -334,4 +334,223 @@ ZB_HD void solve_backward_problem(const SolveBackP& P, long long b) {
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Box-constrained lqrMpc (zopt/mpcUtils.py:47-59) by ADMM.  The reference hands this QP to cvxpy ->
+// OSQP (third-party, not in tree); here the same splitting idea (ADMM with over-relaxation, OSQP's
+// default alpha = 1.6, residual-balancing rho) is applied with the DYNAMICS kept exact inside the
+// linear solve: each iteration minimises  sum x'Qx + u'Ru + (rho/2)||z - w + lam/rho||^2  subject to
+// x+ = Ax + Bu, x_0 = x0 -- an LQ problem whose gains depend only on rho (one Riccati sweep per rho)
+// and whose affine part is one backward vector sweep + one forward rollout per iteration -- then
+// projects onto the box and updates the multipliers.
+struct AdmmP {
+    long long Bsz;
+    int N, n, m;
+    Arr A, B, Q, R, Qf, xlb, xub, ulb, uub;
+    const void* x0;
+    void *u0, *xTraj, *uTraj;
+    int8_t* status;
+    int32_t* iters;
+    void* ws;
+    long long ws_stride;  // elements of T per problem
+    int max_iter, check_every;
+    double rho, alpha, eps_abs, eps_rel, eps_inf;
+};
+
+ZB_HD long long admm_ws_elems(int N, int n, int m) {
+    return (long long)N * m * n + (long long)N * m * m + (long long)N * m + 3LL * ((long long)(N + 1) * n + (long long)N * m);
+}
+
+// gains K_k = G^-1 B'PA and G_k^-1 for the Hessian-form LQ problem with weights (2Q + rho I, 2R + rho I, 2Qf + rho I)
+template <typename T>
+ZB_HD void admm_factor(int N, int n, int m, const T* A, const T* B, const T* Q, const T* R, const T* Qf, T rho, T* K, T* Gi) {
+    T P[NX * NX], BtP[NU * NX], G[NU * NU], Ginv[NU * NU], Kk[NU * NX], BK[NX * NX], W[NX * NX];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) P[i * n + j] = T(2) * Qf[i * n + j] + (i == j ? rho : T(0));
+    for (int k = N - 1; k >= 0; --k) {
+        mm_tn(BtP, B, P, m, n, n);
+        mm(G, BtP, B, m, n, m);
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) {
+                G[i * m + j] += T(2) * R[i * m + j] + (i == j ? rho : T(0));
+                Ginv[i * m + j] = (i == j) ? T(1) : T(0);
+            }
+        lu_solve(G, m, Ginv, m);
+        mm(W, BtP, A, m, n, n);     // B'PA (m x n), reuse W storage
+        mm(Kk, Ginv, W, m, m, n);   // K
+        for (int i = 0; i < m * n; ++i) K[(long long)k * m * n + i] = Kk[i];
+        for (int i = 0; i < m * m; ++i) Gi[(long long)k * m * m + i] = Ginv[i];
+        mm(BK, B, Kk, n, m, n);
+        for (int i = 0; i < n * n; ++i) BK[i] = A[i] - BK[i];  // Acl
+        mm(W, P, BK, n, n, n);                                  // P Acl
+        mm_tn(P, A, W, n, n, n);                                // A' P Acl
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) P[i * n + j] += T(2) * Q[i * n + j] + (i == j ? rho : T(0));
+        for (int i = 0; i < n; ++i)  // keep P exactly symmetric
+            for (int j = i + 1; j < n; ++j) {
+                T a = T(0.5) * (P[i * n + j] + P[j * n + i]);
+                P[i * n + j] = a;
+                P[j * n + i] = a;
+            }
+    }
+}
+
+template <typename T>
+ZB_HD T clampT(T v, T lo, T hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <typename T>
+ZB_HD void admm_problem(const AdmmP& P, long long b) {
+    const int N = P.N, n = P.n, m = P.m;
+    const T *A = P.A.at<T>(b), *B = P.B.at<T>(b), *Q = P.Q.at<T>(b), *R = P.R.at<T>(b), *Qf = P.Qf.at<T>(b);
+    const T *xlb = P.xlb.at<T>(b), *xub = P.xub.at<T>(b), *ulb = P.ulb.at<T>(b), *uub = P.uub.at<T>(b);
+    const T* x0 = reinterpret_cast<const T*>(P.x0) + b * n;
+    T* zx = reinterpret_cast<T*>(P.xTraj) + b * (long long)(N + 1) * n;
+    T* zu = reinterpret_cast<T*>(P.uTraj) + b * (long long)N * m;
+    T* ws = reinterpret_cast<T*>(P.ws) + b * P.ws_stride;
+    const long long nx = (long long)(N + 1) * n, nu = (long long)N * m;
+    T* K = ws;
+    T* Gi = K + (long long)N * m * n;
+    T* kff = Gi + (long long)N * m * m;
+    T* wx = kff + nu;
+    T* wu = wx + nx;
+    T* lx = wu + nu;
+    T* lu = lx + nx;
+    T* dx = lu + nu;  // delta-lambda (infeasibility certificate)
+    T* du = dx + nx;
+    const T INF = T(1) / T(0);
+    T* u0 = reinterpret_cast<T*>(P.u0) + b * m;
+
+    // x_0 = x0 is itself box-constrained in the reference QP (mpcUtils.py:56,58): outside the box = infeasible
+    bool x0_bad = false;
+    for (int i = 0; i < n; ++i) x0_bad |= !(x0[i] >= xlb[i] - T(P.eps_abs) && x0[i] <= xub[i] + T(P.eps_abs));
+    if (x0_bad) {
+        const T nan = INF - INF;
+        for (long long i = 0; i < nx; ++i) zx[i] = nan;
+        for (long long i = 0; i < nu; ++i) zu[i] = nan;
+        for (int i = 0; i < m; ++i) u0[i] = nan;
+        P.status[b] = 2;
+        if (P.iters) P.iters[b] = 0;
+        return;
+    }
+    T rho = T(P.rho);
+    const T alpha = T(P.alpha);
+    admm_factor<T>(N, n, m, A, B, Q, R, Qf, rho, K, Gi);
+    for (long long i = 0; i < nx; ++i) { wx[i] = T(0); lx[i] = T(0); }
+    for (long long i = 0; i < nu; ++i) { wu[i] = T(0); lu[i] = T(0); }
+    int status = 1, it = 0;
+    T p[NX], h[NU], x[NX], u[NU], t1[NX];
+    for (it = 1; it <= P.max_iter; ++it) {
+        // ---- z-update: backward vector sweep (linear terms -rho*(w - lam/rho) = lam - rho*w), forward rollout
+        for (int i = 0; i < n; ++i) p[i] = lx[(long long)N * n + i] - rho * wx[(long long)N * n + i];
+        for (int k = N - 1; k >= 0; --k) {
+            const T* Kk = K + (long long)k * m * n;
+            mv_t(h, B, p, m, n);
+            for (int i = 0; i < m; ++i) h[i] += lu[(long long)k * m + i] - rho * wu[(long long)k * m + i];
+            mv(kff + (long long)k * m, Gi + (long long)k * m * m, h, m, m);
+            mv_t(t1, A, p, n, n);
+            for (int i = 0; i < n; ++i) {
+                T s = T(0);
+                for (int a = 0; a < m; ++a) s += Kk[a * n + i] * h[a];
+                p[i] = (lx[(long long)k * n + i] - rho * wx[(long long)k * n + i]) + t1[i] - s;
+            }
+        }
+        for (int i = 0; i < n; ++i) x[i] = x0[i];
+        for (int k = 0; k < N; ++k) {
+            const T* Kk = K + (long long)k * m * n;
+            for (int a = 0; a < m; ++a) {
+                T s = kff[(long long)k * m + a];
+                for (int j = 0; j < n; ++j) s += Kk[a * n + j] * x[j];
+                u[a] = -s;
+            }
+            for (int i = 0; i < n; ++i) zx[(long long)k * n + i] = x[i];
+            for (int a = 0; a < m; ++a) zu[(long long)k * m + a] = u[a];
+            for (int i = 0; i < n; ++i) {
+                T s = T(0);
+                for (int j = 0; j < n; ++j) s += A[i * n + j] * x[j];
+                for (int a = 0; a < m; ++a) s += B[i * m + a] * u[a];
+                t1[i] = s;
+            }
+            for (int i = 0; i < n; ++i) x[i] = t1[i];
+        }
+        for (int i = 0; i < n; ++i) zx[(long long)N * n + i] = x[i];
+        // ---- relaxation, projection on the box, multiplier update, residuals
+        const bool chk = (it % P.check_every == 0) || it == P.max_iter;
+        T rp = T(0), rd = T(0), nz = T(0), nw = T(0), nl = T(0), ndl = T(0), S = T(0);
+        bool cert_ok = true;
+        for (int part = 0; part < 2; ++part) {
+            const long long cnt = part ? nu : nx;
+            const int dim = part ? m : n;
+            T* z = part ? zu : zx;
+            T* w = part ? wu : wx;
+            T* l = part ? lu : lx;
+            T* d = part ? du : dx;
+            const T* lb = part ? ulb : xlb;
+            const T* ub = part ? uub : xub;
+            for (long long i = 0; i < cnt; ++i) {
+                const int c = (int)(i % dim);
+                const T zi = z[i], wo = w[i];
+                const T zr = alpha * zi + (T(1) - alpha) * wo;
+                const T wn = clampT<T>(zr + l[i] / rho, lb[c], ub[c]);
+                const T dl = rho * (zr - wn);
+                l[i] += dl;
+                w[i] = wn;
+                rp = fmax(rp, fabs(zi - wn));
+                rd = fmax(rd, rho * fabs(wn - wo));
+                nz = fmax(nz, fabs(zi));
+                nw = fmax(nw, fabs(wn));
+                nl = fmax(nl, fabs(l[i]));
+                if (chk) {
+                    d[i] = dl;
+                    ndl = fmax(ndl, fabs(dl));
+                    if (dl > T(0)) { if (ub[c] == INF) cert_ok = false; else S += ub[c] * dl; }
+                    else if (dl < T(0)) { if (lb[c] == -INF) cert_ok = false; else S += lb[c] * dl; }
+                    S -= dl * zi;
+                }
+            }
+        }
+        if (chk) {
+            if (rp <= T(P.eps_abs) + T(P.eps_rel) * fmax(nz, nw) && rd <= T(P.eps_abs) + T(P.eps_rel) * nl) {
+                status = 0;
+                break;
+            }
+            // primal infeasibility certificate: delta-lambda separates the box from the dynamics' affine set
+            if (cert_ok && ndl > T(P.eps_inf) && S < -T(P.eps_inf) * ndl) {
+                T mu[NX], g = T(0);
+                for (int i = 0; i < n; ++i) mu[i] = dx[(long long)N * n + i];
+                for (int k = N - 1; k >= 0; --k) {
+                    mv_t(h, B, mu, m, n);
+                    for (int a = 0; a < m; ++a) g = fmax(g, fabs(h[a] + du[(long long)k * m + a]));
+                    mv_t(t1, A, mu, n, n);
+                    for (int i = 0; i < n; ++i) mu[i] = dx[(long long)k * n + i] + t1[i];
+                }
+                if (g <= T(P.eps_inf) * ndl) {
+                    status = 2;
+                    break;
+                }
+            }
+            // residual balancing (OSQP adapts rho the same way): refactor when the residuals are 5x apart
+            if (it < P.max_iter) {
+                const T rpn = rp / fmax(fmax(nz, nw), T(1e-10)), rdn = rd / fmax(nl, T(1e-10));
+                const T ratio = sqrt(rpn / fmax(rdn, T(1e-30)));
+                if ((ratio > T(5) || ratio < T(0.2)) && rdn > T(0)) {
+                    T rn = clampT<T>(rho * ratio, T(1e-6), T(1e6));
+                    if (rn != rho) {
+                        rho = rn;
+                        admm_factor<T>(N, n, m, A, B, Q, R, Qf, rho, K, Gi);
+                    }
+                }
+            }
+        }
+    }
+    if (it > P.max_iter) it = P.max_iter;
+    if (status == 2) {
+        const T nan = INF - INF;
+        for (long long i = 0; i < nx; ++i) zx[i] = nan;
+        for (long long i = 0; i < nu; ++i) zu[i] = nan;
+    }
+    for (int i = 0; i < m; ++i) u0[i] = zu[i];
+    P.status[b] = (int8_t)status;
+    if (P.iters) P.iters[b] = it;
+}
+
 }  // namespace zb

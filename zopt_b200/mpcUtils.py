@@ -91,7 +91,8 @@ class lqrMpc():
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         opts = ZbAdmmOpts(int(kwargs.get("max_iter", 4000)), int(kwargs.get("check_termination", 25)),
                           float(kwargs.get("rho", 0.1)), float(kwargs.get("sigma", 1e-6)), float(kwargs.get("alpha", 1.6)),
-                          float(kwargs.get("eps_abs", 1e-3)), float(kwargs.get("eps_rel", 1e-3)))
+                          float(kwargs.get("eps_abs", 1e-3)), float(kwargs.get("eps_rel", 1e-3)),
+                          float(kwargs.get("eps_prim_inf", 1e-4)))
         check(lib.zb_mpc_lqr_solve(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, n, m, *[v.ref() for v in self.views],
                                    int(self.bounded), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
                                    ptr(iters), ptr(ws), wsb))
