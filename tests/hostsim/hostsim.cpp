@@ -86,8 +86,8 @@ EXPORT int hs_rollout(int dtype, int64_t Bsz, int N, const zb_model* model, cons
                       void* uTraj, void* J) {
     RollP P = R_(Bsz, N, model, J ? cost : nullptr, x0, l, L, xPrev, uPrev, xTraj, uTraj);
     for (int64_t b = 0; b < Bsz; ++b) {
-        if (dtype) { double v = rollout_core<double>(P, b, alpha, true); if (J) ((double*)J)[b] = v; }
-        else { float v = rollout_core<float>(P, b, (float)alpha, true); if (J) ((float*)J)[b] = v; }
+        if (dtype) { double v = rollout_any<double>(P, b, alpha, true); if (J) ((double*)J)[b] = v; }
+        else { float v = rollout_any<float>(P, b, (float)alpha, true); if (J) ((float*)J)[b] = v; }
     }
     return 0;
 }
@@ -98,12 +98,12 @@ static void fwd(const RollP& P, T* J, int32_t* idx, T* Jall) {
         for (int j = 0; j < 16; ++j) {
             T alpha = T(1);
             for (int i = 0; i < j; ++i) alpha *= T(0.5);
-            Jall[b * 16 + j] = rollout_core<T>(P, b, alpha, false);
+            Jall[b * 16 + j] = rollout_any<T>(P, b, alpha, false);
         }
         int k = argmin16<T>(Jall + b * 16);
         T alpha = T(1);
         for (int i = 0; i < k; ++i) alpha *= T(0.5);
-        rollout_core<T>(P, b, alpha, true);
+        rollout_any<T>(P, b, alpha, true);
         J[b] = Jall[b * 16 + k];
         if (idx) idx[b] = k;
     }
@@ -168,7 +168,7 @@ static void solve(int64_t Bsz, int N, int second_order, const zb_model* model, c
     // initial rollout: l = uGuess, L = 0, previous trajectory = 0, alpha = 1
     RollP P0 = R_(Bsz, N, model, cost, x0, uGuess, Lout, zx.data(), zu.data(), xTraj, uTraj);
     for (int64_t b = 0; b < Bsz; ++b) {
-        J[b] = rollout_core<T>(P0, b, T(1), true);
+        J[b] = rollout_any<T>(P0, b, T(1), true);
         conv[b] = 0; iters[b] = 0;
         if (alpha_log) for (int i = 0; i < maxIter; ++i) alpha_log[b * maxIter + i] = -1;
         if (J_log) { J_log[b * (maxIter + 1)] = J[b]; for (int i = 1; i <= maxIter; ++i) J_log[b * (maxIter + 1) + i] = NAN; }
@@ -182,12 +182,12 @@ static void solve(int64_t Bsz, int N, int second_order, const zb_model* model, c
             for (int j = 0; j < 16; ++j) {
                 T alpha = T(1);
                 for (int i = 0; i < j; ++i) alpha *= T(0.5);
-                Jall[b * 16 + j] = rollout_core<T>(P, b, alpha, false);
+                Jall[b * 16 + j] = rollout_any<T>(P, b, alpha, false);
             }
             int k = argmin16<T>(&Jall[b * 16]);
             T alpha = T(1);
             for (int i = 0; i < k; ++i) alpha *= T(0.5);
-            rollout_core<T>(P, b, alpha, true);
+            rollout_any<T>(P, b, alpha, true);
             T Jn = Jall[b * 16 + k];
             conv[b] = (fabs(J[b] - Jn) <= T(tol)) ? 1 : 0;
             J[b] = Jn;

@@ -1,0 +1,362 @@
+// Cooperative iLQR backward pass for the registered quadcopter model (n=12, m=4), fp32 and fp64.
+//
+// One launch = backwardPass_ilqr (zopt/ilqrUtils.py:176-181, step :153-173) for every active problem, with
+// the expansion of ilqrUtils.py:308-313 done on the fly: f_x = I + dt*dF/dx is evaluated analytically at
+// (x_k, u_k) inside the kernel (nothing of the linearisation is materialised in HBM), c_x = (Q+Q')x_k,
+// c_u = (R+R')u_k, and the conditioned Hessians come from the per-problem block Czz / Vfxx prepared once
+// per solve (quadratic costs have constant Hessians).
+//
+// Same mapping as lqr_fast.cuh: FOUR threads per problem, [f_x | f_u] split into four 12x4 column tiles,
+// operands in a per-problem shared-memory slab read with 128-bit broadcast loads.  Per step:
+//   1.  [W | VB] = v_xx [f_x | f_u] and, in the same loop, [Q_x | Q_u] = [f_x | f_u]' v_x  (+ c_x, c_u)
+//   2.  [M | G0] = f_u' [W | VB]         ->  Q_ux = c_ux + M,  Q_uu = c_uu + G0
+//   3.  Cholesky of Q_uu;  L = -Q_uu^-1 Q_ux (own tile),  l = -Q_uu^-1 Q_u
+//   4.  l_k, L_k -> global
+//   5.  v_xx' = c_xx + f_x' W + Q_ux' L  (== Q_xx - L'Q_uu L),  v_x' = Q_x + Q_ux' l  (== Q_x - L'Q_uu l)
+//       written back "lower triangle wins" so v_xx stays exactly symmetric.
+// The algebra equals the reference's as-written expressions; parity with the oracle is gated at 1e-10 (fp64).
+#pragma once
+#include "zb_common.cuh"
+
+namespace zb {
+
+struct IlqrFastP {
+    long long Bsz;
+    int N;
+    double dt;
+    Cost C;
+    const void *xTraj, *uTraj;
+    const void* Czz;   // (Bsz,16,16)
+    const void* Vfxx;  // (Bsz,12,12)
+    const uint8_t* done;
+    void *l, *L;
+};
+
+// slab layout in elements of T
+constexpr int IQ_V = 0;        // v_xx 12x12
+constexpr int IQ_A = 144;      // f_x  12x12
+constexpr int IQ_B = 288;      // f_u  12x4
+constexpr int IQ_CXX = 336;    // c_xx 12x12 (conditioned)
+constexpr int IQ_QS = 480;     // Q+Q' 12x12
+constexpr int IQ_M = 624;      // Q_ux 4x12
+constexpr int IQ_CUX = 672;    // c_ux 4x12
+constexpr int IQ_G = 720;      // Q_uu 4x4
+constexpr int IQ_CUU = 736;    // c_uu 4x4
+constexpr int IQ_RS = 752;     // R+R' 4x4
+constexpr int IQ_VX = 768;     // v_x 12 (+4 pad)
+constexpr int IQ_XK = 784;     // x_k 12, u_k 4
+constexpr int IQ_QU = 800;     // Q_u 4
+constexpr int IQ_PS_F32 = 812;  // 812/4 = 203 odd
+constexpr int IQ_PS_F64 = 806;  // 806*8/16 = 403 odd (16-byte units)
+
+template <typename T>
+struct Vec4 {
+    T v[4];
+};
+__device__ __forceinline__ Vec4<float> ldv4(const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    return Vec4<float>{{a.x, a.y, a.z, a.w}};
+}
+__device__ __forceinline__ Vec4<double> ldv4(const double* p) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    return Vec4<double>{{a.x, a.y, b.x, b.y}};
+}
+__device__ __forceinline__ void stv4(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void stv4(double* p, double a, double b, double c, double d) {
+    *reinterpret_cast<double2*>(p) = make_double2(a, b);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
+}
+__device__ __forceinline__ float rsq(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rsq(double x) { return 1.0 / sqrt(x); }
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int PS = sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64;
+    T* smem = reinterpret_cast<T*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & 3, quad = lane >> 2;
+    const long long b_raw = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 8 + quad;
+    const bool in_range = b_raw < P.Bsz;
+    const long long b = in_range ? b_raw : P.Bsz - 1;
+    const bool active = in_range && !(P.done && P.done[b]);
+    // a warp whose 8 problems are all frozen / out of range has nothing to do
+    if (__ballot_sync(0xffffffffu, active) == 0u) return;
+    T* S = smem + (warp * 8 + quad) * PS;
+    T *Vs = S + IQ_V, *As = S + IQ_A, *Bs = S + IQ_B, *Cxx = S + IQ_CXX, *Qs = S + IQ_QS, *Ms = S + IQ_M, *Cux = S + IQ_CUX;
+    T *Gs = S + IQ_G, *Cuu = S + IQ_CUU, *Rs = S + IQ_RS, *vx = S + IQ_VX, *xk = S + IQ_XK, *Qu = S + IQ_QU;
+    const int N = P.N;
+    const T dt = T(P.dt);
+    const T* xT = reinterpret_cast<const T*>(P.xTraj) + b * (long long)(N + 1) * 12;
+    const T* uT = reinterpret_cast<const T*>(P.uTraj) + b * (long long)N * 4;
+    T* lo = reinterpret_cast<T*>(P.l) + b * (long long)N * 4;
+    T* Lo = reinterpret_cast<T*>(P.L) + b * (long long)N * 48;
+
+    // ---- one-time staging: conditioned cost blocks, Q+Q', R+R', terminal value, constant f_u ----
+    {
+        const T* Czz = reinterpret_cast<const T*>(P.Czz) + b * 256;
+        const T* Vf = reinterpret_cast<const T*>(P.Vfxx) + b * 144;
+        const T* Q = P.C.Q.at<T>(b);
+        const T* R = P.C.R.at<T>(b);
+        const T* Qf = P.C.Qf.at<T>(b);
+        for (int e = t; e < 144; e += 4) {
+            const int i = e / 12, j = e % 12;
+            Cxx[e] = Czz[i * 16 + j];
+            Qs[e] = Q[i * 12 + j] + Q[j * 12 + i];
+            Vs[e] = Vf[e];
+            As[e] = T(0);
+        }
+        for (int e = t; e < 48; e += 4) {
+            const int a = e / 12, j = e % 12;
+            Cux[e] = Czz[(12 + a) * 16 + j];
+            Bs[e] = T(0);
+        }
+        for (int e = t; e < 16; e += 4) {
+            const int a = e / 4, c = e % 4;
+            Cuu[e] = Czz[(12 + a) * 16 + 12 + c];
+            Rs[e] = R[a * 4 + c] + R[c * 4 + a];
+        }
+        __syncwarp();
+        if (t == 0) {  // f_u = dt * dF/du: [2,0] = -dt, [3,1] = [4,2] = [5,3] = +dt (quad_model_gen.cuh)
+            Bs[2 * 4 + 0] = -dt; Bs[3 * 4 + 1] = dt; Bs[4 * 4 + 2] = dt; Bs[5 * 4 + 3] = dt;
+        }
+        // v_x(N) = (Qf + Qf') x_N
+        const T* xN = xT + (long long)N * 12;
+        for (int i = t; i < 12; i += 4) {
+            T s = T(0);
+            for (int j = 0; j < 12; ++j) s += (Qf[i * 12 + j] + Qf[j * 12 + i]) * xN[j];
+            vx[i] = s;
+        }
+    }
+    __syncwarp();
+
+    const T* Ct = (t < 3) ? (As + 4 * t) : Bs;
+    const int cstride = (t < 3) ? 12 : 4;
+    const int tcol = (t < 3) ? 4 * t : 0;
+
+    for (int k = N - 1; k >= 0; --k) {
+        // ---- 0. linearise at (x_k, u_k): every thread evaluates dF/dx (no divergence), stores 3 rows ----
+        {
+            T x[12], u[4], J[144];
+            const Vec4<T> x0 = ldv4(xT + (long long)k * 12), x1 = ldv4(xT + (long long)k * 12 + 4), x2 = ldv4(xT + (long long)k * 12 + 8);
+            const Vec4<T> u0 = ldv4(uT + (long long)k * 4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { x[i] = x0.v[i]; x[4 + i] = x1.v[i]; x[8 + i] = x2.v[i]; u[i] = u0.v[i]; }
+            QuadTrig<T> tr = quad_trig(x);
+            quad_jac_x(tr, x, u, J);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                T row[12];
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    const T j0 = J[r * 12 + c], j1 = J[(3 + r) * 12 + c], j2 = J[(6 + r) * 12 + c], j3 = J[(9 + r) * 12 + c];
+                    const T jv = (t == 0) ? j0 : (t == 1) ? j1 : (t == 2) ? j2 : j3;
+                    row[c] = dt * jv;
+                }
+                // + identity: row index 3t+r, so column 3t+r gets +1
+#pragma unroll
+                for (int c = 0; c < 12; ++c) row[c] += (c == 3 * t + r) ? T(1) : T(0);
+                T* dst = As + (3 * t + r) * 12;
+                stv4(dst, row[0], row[1], row[2], row[3]);
+                stv4(dst + 4, row[4], row[5], row[6], row[7]);
+                stv4(dst + 8, row[8], row[9], row[10], row[11]);
+            }
+            {
+                const Vec4<T> mine = (t == 0) ? x0 : (t == 1) ? x1 : (t == 2) ? x2 : u0;  // x_k quarter / u_k
+                stv4(xk + 4 * t, mine.v[0], mine.v[1], mine.v[2], mine.v[3]);
+            }
+        }
+        __syncwarp();
+        // ---- 1. [W | VB] tile = v_xx * tile ;  [Q_x | Q_u] tile = tile' v_x + c_x / c_u -------------
+        T W[12][4];
+        T qv[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) W[i][c] = T(0);
+#pragma unroll
+        for (int kk = 0; kk < 12; ++kk) {
+            const Vec4<T> c4 = ldv4(Ct + kk * cstride);
+            const Vec4<T> v0 = ldv4(Vs + kk * 12), v1 = ldv4(Vs + kk * 12 + 4), v2 = ldv4(Vs + kk * 12 + 8);
+            const T vxk = vx[kk];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) qv[c] = fma(c4.v[c], vxk, qv[c]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    W[i][c] = fma(v0.v[i], c4.v[c], W[i][c]);
+                    W[4 + i][c] = fma(v1.v[i], c4.v[c], W[4 + i][c]);
+                    W[8 + i][c] = fma(v2.v[i], c4.v[c], W[8 + i][c]);
+                }
+        }
+        // c_x tile = (Q+Q')[4t..4t+3, :] x_k   /   c_u = (R+R') u_k  (thread 3)
+        if (t < 3) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const T* qrow = Qs + (4 * t + c) * 12;
+                const Vec4<T> q0 = ldv4(qrow), q1 = ldv4(qrow + 4), q2 = ldv4(qrow + 8);
+                const Vec4<T> a0 = ldv4(xk), a1 = ldv4(xk + 4), a2 = ldv4(xk + 8);
+                T s = T(0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { s = fma(q0.v[j], a0.v[j], s); s = fma(q1.v[j], a1.v[j], s); s = fma(q2.v[j], a2.v[j], s); }
+                qv[c] += s;
+            }
+        } else {
+            const Vec4<T> uu = ldv4(xk + 12);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const Vec4<T> r4 = ldv4(Rs + c * 4);
+                T s = T(0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s = fma(r4.v[j], uu.v[j], s);
+                qv[c] += s;
+            }
+        }
+        // ---- 2. [M | G0] tile = f_u' * [W | VB] tile ------------------------------------------
+        T M[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) M[a][c] = T(0);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const Vec4<T> b4 = ldv4(Bs + i * 4);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) M[a][c] = fma(b4.v[a], W[i][c], M[a][c]);
+        }
+        // ---- 3. Q_uu = c_uu + G0 (thread 3), Q_ux tile = c_ux tile + M (threads 0..2); share through smem
+        if (t == 3) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const Vec4<T> c4 = ldv4(Cuu + a * 4);
+                stv4(Gs + a * 4, M[a][0] + c4.v[0], M[a][1] + c4.v[1], M[a][2] + c4.v[2], M[a][3] + c4.v[3]);
+            }
+            stv4(Qu, qv[0], qv[1], qv[2], qv[3]);
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const Vec4<T> c4 = ldv4(Cux + a * 12 + 4 * t);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) M[a][c] += c4.v[c];
+                stv4(Ms + a * 12 + 4 * t, M[a][0], M[a][1], M[a][2], M[a][3]);
+            }
+        }
+        __syncwarp();
+        const Vec4<T> g0 = ldv4(Gs), g1 = ldv4(Gs + 4), g2 = ldv4(Gs + 8), g3 = ldv4(Gs + 12);
+        const T d0 = rsq(g0.v[0]);
+        const T c10 = g1.v[0] * d0, c20 = g2.v[0] * d0, c30 = g3.v[0] * d0;
+        const T d1 = rsq(fma(-c10, c10, g1.v[1]));
+        const T c21 = fma(-c20, c10, g2.v[1]) * d1, c31 = fma(-c30, c10, g3.v[1]) * d1;
+        const T d2 = rsq(fma(-c21, c21, fma(-c20, c20, g2.v[2])));
+        const T c32 = fma(-c31, c21, fma(-c30, c20, g3.v[2])) * d2;
+        const T d3 = rsq(fma(-c32, c32, fma(-c31, c31, fma(-c30, c30, g3.v[3]))));
+        T L[4][5];  // columns 0..3: -Q_uu^-1 Q_ux tile ; column 4: l = -Q_uu^-1 Q_u
+        const Vec4<T> qu = ldv4(Qu);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const T m0 = (c < 4) ? M[0][c] : qu.v[0], m1 = (c < 4) ? M[1][c] : qu.v[1];
+            const T m2 = (c < 4) ? M[2][c] : qu.v[2], m3 = (c < 4) ? M[3][c] : qu.v[3];
+            const T y0 = m0 * d0;
+            const T y1 = fma(-c10, y0, m1) * d1;
+            const T y2 = fma(-c21, y1, fma(-c20, y0, m2)) * d2;
+            const T y3 = fma(-c32, y2, fma(-c31, y1, fma(-c30, y0, m3))) * d3;
+            const T x3 = y3 * d3;
+            const T x2 = fma(-c32, x3, y2) * d2;
+            const T x1 = fma(-c31, x3, fma(-c21, x2, y1)) * d1;
+            const T x0 = fma(-c30, x3, fma(-c20, x2, fma(-c10, x1, y0))) * d0;
+            L[0][c] = -x0; L[1][c] = -x1; L[2][c] = -x2; L[3][c] = -x3;
+        }
+        // ---- 4. policy -> global --------------------------------------------------------------
+        if (active) {
+            if (t < 3) {
+                T* g = Lo + (long long)k * 48 + 4 * t;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) stv4(g + a * 12, L[a][0], L[a][1], L[a][2], L[a][3]);
+            } else {
+                stv4(lo + (long long)k * 4, L[0][4], L[1][4], L[2][4], L[3][4]);
+            }
+        }
+        // ---- 5. v_x' tile = Q_x + Q_ux' l ; v_xx' tile = c_xx + f_x' W + Q_ux' L  (two half-tiles of rows) ----
+        if (t < 3) {
+            T nv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) nv[c] = qv[c] + (M[0][c] * L[0][4] + M[1][c] * L[1][4] + M[2][c] * L[2][4] + M[3][c] * L[3][4]);
+            stv4(vx + 4 * t, nv[0], nv[1], nv[2], nv[3]);
+        }
+#pragma unroll
+        for (int sblk = 0; sblk < 3; ++sblk) {  // rows 4*sblk .. 4*sblk+3 of the tile = block (sblk, t)
+            T acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const Vec4<T> q4 = ldv4(Cxx + (4 * sblk + i) * 12 + tcol);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = q4.v[c];
+            }
+#pragma unroll
+            for (int kk = 0; kk < 12; ++kk) {
+                const Vec4<T> a4 = ldv4(As + kk * 12 + 4 * sblk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[i][c] = fma(a4.v[i], W[kk][c], acc[i][c]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const Vec4<T> m4 = ldv4(Ms + a * 12 + 4 * sblk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[i][c] = fma(m4.v[i], L[a][c], acc[i][c]);
+            }
+            // write back, lower triangle wins: strictly-lower blocks are stored with their transpose,
+            // diagonal blocks are mirrored, upper blocks are dropped (their transposes are authoritative)
+            if (sblk > t) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    stv4(Vs + (4 * sblk + r) * 12 + 4 * t, acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                    stv4(Vs + (4 * t + r) * 12 + 4 * sblk, acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
+                }
+            } else if (sblk == t) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    T e[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) e[c] = (r >= c) ? acc[r][c] : acc[c][r];
+                    stv4(Vs + (4 * sblk + r) * 12 + 4 * sblk, e[0], e[1], e[2], e[3]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+inline size_t ilqr_fast_smem(int32_t dtype, int warps) {
+    return (size_t)warps * 8 * (dtype == ZB_F32 ? IQ_PS_F32 * 4 : IQ_PS_F64 * 8);
+}
+
+// launch the cooperative backward pass; returns false if the configuration is not eligible
+inline bool ilqr_fast_eligible(const Model& M, int second_order) {
+    return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && !second_order;
+}
+
+inline int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream) {
+    const int warps = (dtype == ZB_F32) ? 4 : 2;  // problems per CTA: 32 (fp32) / 16 (fp64)
+    const size_t smem = ilqr_fast_smem(dtype, warps);
+    const unsigned grid = (unsigned)((P.Bsz + warps * 8 - 1) / (warps * 8));
+    if (dtype == ZB_F32) {
+        ZB_CUDA(cudaFuncSetAttribute(k_ilqr_backward_quad<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ilqr_backward_quad<float><<<grid, warps * 32, smem, stream>>>(P);
+    } else {
+        ZB_CUDA(cudaFuncSetAttribute(k_ilqr_backward_quad<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ilqr_backward_quad<double><<<grid, warps * 32, smem, stream>>>(P);
+    }
+    ZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace zb

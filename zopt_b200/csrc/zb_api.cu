@@ -2,6 +2,7 @@
 // The (n,m)=(12,4) fast kernels live in lqr_fast.cuh / ilqr_fast.cuh and are dispatched from here.
 #include "zb_common.cuh"
 #include "lqr_fast.cuh"
+#include "ilqr_fast.cuh"
 
 using namespace zb;
 
@@ -72,7 +73,7 @@ template <typename T>
 __global__ void __launch_bounds__(GEN_THREADS) k_rollout(RollP P, double alpha) {
     long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (b >= P.Bsz) return;
-    T J = rollout_core<T>(P, b, T(alpha), true);
+    T J = rollout_any<T>(P, b, T(alpha), true);
     if (P.J) reinterpret_cast<T*>(P.J)[b] = J;
 }
 
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_forward_costs(RollP P, void* Ja
     if (done && done[b]) return;
     T alpha = T(1);
     for (int i = 0; i < j; ++i) alpha *= T(0.5);  // 0.5**j exactly (ilqrUtils.py:145)
-    T J = rollout_core<T>(P, b, alpha, false);
+    T J = rollout_any<T>(P, b, alpha, false);
     reinterpret_cast<T*>(Jall)[b * 16 + j] = J;
 }
 
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_forward_commit(RollP P, const v
     int idx = argmin16<T>(Ja);
     T alpha = T(1);
     for (int i = 0; i < idx; ++i) alpha *= T(0.5);
-    rollout_core<T>(P, b, alpha, true);
+    rollout_any<T>(P, b, alpha, true);
     T Jn = Ja[idx];
     if (S.J) {
         T* J = reinterpret_cast<T*>(S.J);
@@ -551,8 +552,14 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     ZB_DISPATCH(dtype, k_solve_init, gen_grid(Bsz), GEN_THREADS, stream, P, uGuess, J_out, converged_out, iters_out,
                 alpha_log, J_log, (int)maxIter);
     SolveBackP Bk{Bsz, N, second_order, P.M, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
+    const bool fast_bwd = ilqr_fast_eligible(P.M, second_order) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out);
+    IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out};
     for (int it = 0; it < maxIter; ++it) {
-        ZB_DISPATCH(dtype, k_solve_backward, gen_grid(Bsz), GEN_THREADS, stream, Bk);
+        if (fast_bwd) {
+            rc = ilqr_fast_launch(dtype, Fb, s);
+            if (rc) return rc;
+        } else
+            ZB_DISPATCH(dtype, k_solve_backward, gen_grid(Bsz), GEN_THREADS, stream, Bk);
         ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall, (const uint8_t*)converged_out);
         CommitP S{J_out, converged_out, iters_out, alpha_log, J_log, it, (int)maxIter, tol, nullptr, nullptr};
         ZB_DISPATCH(dtype, k_forward_commit, gen_grid(Bsz), GEN_THREADS, stream, P, (const void*)Jall, S);

@@ -168,6 +168,95 @@ ZB_HD T rollout_core(const RollP& P, long long b, T alpha, bool write) {
     return J;
 }
 
+// Quadcopter specialisation of rollout_core: n = 12, m = 4 known at compile time so the state, the control and the
+// (diagonal) cost weights live in registers.  Identical arithmetic order to rollout_core; a dense Q or R falls back
+// to the row-by-row quadratic form read through L1.
+template <typename T>
+ZB_HD T rollout_quad(const RollP& P, long long b, T alpha, bool write) {
+    constexpr int n = 12, m = 4;
+    const int N = P.N;
+    const T* x0 = reinterpret_cast<const T*>(P.x0) + b * n;
+    const T* lp = reinterpret_cast<const T*>(P.l) + b * (long long)N * m;
+    const T* Lp = reinterpret_cast<const T*>(P.L) + b * (long long)N * m * n;
+    const T* xP = reinterpret_cast<const T*>(P.xPrev) + b * (long long)(N + 1) * n;
+    const T* uP = reinterpret_cast<const T*>(P.uPrev) + b * (long long)N * m;
+    T* xT = reinterpret_cast<T*>(P.xTraj) + b * (long long)(N + 1) * n;
+    T* uT = reinterpret_cast<T*>(P.uTraj) + b * (long long)N * m;
+    const T* Q = P.has_cost ? P.C.Q.at<T>(b) : nullptr;
+    const T* R = P.has_cost ? P.C.R.at<T>(b) : nullptr;
+    const T w[3] = {T(P.M.wind[0]), T(P.M.wind[1]), T(P.M.wind[2])};
+    const bool has_wind = P.M.has_wind != 0;
+    const T dt = T(P.M.dt);
+    T qd[n], rd[m];
+    bool diag = true;
+    if (P.has_cost) {
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                if (i == j) qd[i] = Q[i * n + j];
+                else diag &= (Q[i * n + j] == T(0));
+            }
+#pragma unroll
+        for (int i = 0; i < m; ++i)
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                if (i == j) rd[i] = R[i * m + j];
+                else diag &= (R[i * m + j] == T(0));
+            }
+    }
+    T x[n], u[m], xd[n];
+    T J = T(0);
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = x0[i];
+    for (int k = 0; k < N; ++k) {
+        const T* Lk = Lp + (long long)k * m * n;
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+            T s = T(0);
+#pragma unroll
+            for (int j = 0; j < n; ++j) s += Lk[i * n + j] * (x[j] - xP[(long long)k * n + j]);
+            u[i] = (alpha * lp[(long long)k * m + i] + s) + uP[(long long)k * m + i];
+        }
+        if (write) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) xT[(long long)k * n + i] = x[i];
+#pragma unroll
+            for (int i = 0; i < m; ++i) uT[(long long)k * m + i] = u[i];
+        }
+        if (P.has_cost) {
+            if (diag) {
+                T a = T(0), c = T(0);
+#pragma unroll
+                for (int i = 0; i < n; ++i) a += x[i] * (qd[i] * x[i]);
+#pragma unroll
+                for (int i = 0; i < m; ++i) c += u[i] * (rd[i] * u[i]);
+                J += a + c;
+            } else {
+                J += quad_form<T>(Q, x, n) + quad_form<T>(R, u, m);
+            }
+        }
+        QuadTrig<T> tr = quad_trig(x);
+        if (has_wind) quad_xdot_wind(tr, x, u, w, xd);
+        else quad_xdot(tr, x, u, xd);
+#pragma unroll
+        for (int i = 0; i < n; ++i) x[i] = x[i] + dt * xd[i];
+    }
+    if (write) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) xT[(long long)N * n + i] = x[i];
+    }
+    if (P.has_cost) J += quad_form<T>(P.C.Qf.at<T>(b), x, n);
+    return J;
+}
+
+// dispatch: compile-time-sized quadcopter path or the generic run-time-sized one
+template <typename T>
+ZB_HD T rollout_any(const RollP& P, long long b, T alpha, bool write) {
+    if (P.M.kind == 1) return rollout_quad<T>(P, b, alpha, write);
+    return rollout_core<T>(P, b, alpha, write);
+}
+
 // argmin with NumPy/JAX semantics: first minimum on ties, a NaN wins (ilqrUtils.py:147)
 template <typename T>
 ZB_HD int argmin16(const T* J) {

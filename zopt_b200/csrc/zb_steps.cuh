@@ -132,9 +132,15 @@ ZB_HD void ilqr_step(int n, int m, const T* f_x, const T* f_u, T c, const T* c_x
 template <typename T>
 ZB_HD QuadTrig<T> quad_trig(const T* x) {
     QuadTrig<T> tr;
+#ifdef __CUDA_ARCH__
+    sincos(x[6], &tr.sph, &tr.cph);  // overloads: sincos(double,..) / sincos(float,..) -> sincosf
+    sincos(x[7], &tr.sth, &tr.cth);
+    sincos(x[8], &tr.sps, &tr.cps);
+#else
     tr.sph = sin(x[6]); tr.cph = cos(x[6]);
     tr.sth = sin(x[7]); tr.cth = cos(x[7]);
     tr.sps = sin(x[8]); tr.cps = cos(x[8]);
+#endif
     tr.sec = T(1) / tr.cth;
     tr.tth = tr.sth * tr.sec;
     return tr;
