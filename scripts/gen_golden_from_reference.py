@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""
+Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference sources from
+/root/reference (zopt.lqrUtils, zopt.ilqrUtils, zopt.pytrees, zopt.quadcopter) on seeded inputs.
+
+`jax`/`jaxlib` are absent from this image, so the reference is imported on top of oracle/jax_shim (a minimal
+NumPy-semantics stand-in for the JAX entry points it uses, backed by torch-CPU fp64; see oracle/jax_shim/README.md).
+The formulas and control flow executed are the reference's own; the primitives are torch's.  `zopt.mpcUtils` needs
+cvxpy and a QP solver and cannot be run at all (parity unpinned for that path).
+
+Run in the build container only:  python scripts/gen_golden_from_reference.py
+The GPU box has no /root/reference; tests read the committed .npz files.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "jax_shim"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+import torch  # noqa: E402
+import jax  # noqa: E402  (the shim)
+import jax.numpy as jnp  # noqa: E402
+import zopt.ilqrUtils as ref_ilqr  # noqa: E402
+import zopt.lqrUtils as ref_lqr  # noqa: E402
+import zopt.pytrees as ref_pytrees  # noqa: E402
+from zopt.quadcopter import Quadcopter  # noqa: E402
+
+from zopt_b200 import configs  # noqa: E402
+
+assert "jax_shim" in jax.__file__ and ref_lqr.__file__.startswith("/root/reference/")
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+T = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+npy = lambda t: t.detach().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+ac = Quadcopter()
+uTrim = T(configs.U_TRIM)
+
+
+def rep(a, N):
+    return T(np.repeat(np.asarray(a)[None], N, axis=0))
+
+
+# ---- (i) cfg 1a: the demo instance of discreteFiniteHorizonLqr (demos/discreteFiniteHorizonLqr.py:13-35) -------------
+A, B = ac.linearize(T(np.zeros(8)), uTrim, dt=0.1)
+N = 100
+Qk, Rk = configs.cfg1_demo_weights(N)
+K = ref_lqr.discreteFiniteHorizonLqr(rep(npy(A), N), rep(npy(B), N), T(Qk), T(Rk), N)
+np.savez(os.path.join(OUT, "lqr_demo_n8.npz"), A=npy(A), B=npy(B), Qk=Qk, Rk=Rk, N=N, K=npy(K))
+print("lqr_demo_n8", K.shape)
+
+# ---- (ii) cfg 2: 32 random quadcopter LQR problems, n=12 m=4 N=50 ----------------------------------------------------
+d = configs.cfg2(Bsz=32)
+N = d["N"]
+As, Bs, Ls = [], [], []
+for i in range(32):
+    Aw, Bw = jax.jacobian(ac.inertialDynamics, argnums=(0, 1))(T(d["xbar"][i]), T(d["ubar"][i]))  # demos/lqrMpc.py:26-28
+    Ai, Bi = np.eye(12) + 0.1 * npy(Aw), 0.1 * npy(Bw)
+    Qi, Ri = np.diag(d["qdiag"][i]), np.diag(d["rdiag"][i])
+    Qk = np.repeat(Qi[None], N + 1, axis=0)
+    Qk[N] *= 10
+    L = ref_lqr.discreteFiniteHorizonLqr(rep(Ai, N), rep(Bi, N), T(Qk), rep(Ri, N), N)
+    As.append(Ai), Bs.append(Bi), Ls.append(npy(L))
+np.savez(os.path.join(OUT, "lqr_cfg2_32.npz"), xbar=d["xbar"], ubar=d["ubar"], qdiag=d["qdiag"], rdiag=d["rdiag"],
+         A=np.array(As), B=np.array(Bs), L=np.array(Ls), N=N)
+print("lqr_cfg2_32", np.array(Ls).shape)
+
+# ---- (iii) bilinearAffineLqr on the demo's problem with a seeded H (demos/bilinearLqrControl.py:21-43) ---------------
+rng = np.random.default_rng(1234 + 10)
+n, m, N = 8, 4, 100
+Hm = 0.2 * rng.normal(size=(N, m, n))
+dv = 0.01 * rng.normal(size=(N, n))
+qv = 0.1 * np.repeat(np.array([1., -1, 0, 0, 0, 0, 0, 0])[None], N, axis=0)
+rv = 0.05 * rng.normal(size=(N, m))
+q0 = rng.normal(size=N)
+Lb, lb = ref_lqr.bilinearAffineLqr(rep(npy(A), N), rep(npy(B), N), T(dv), rep(np.eye(n), N), rep(np.eye(m), N), T(Hm), T(qv),
+                                   T(rv), T(q0), N)
+np.savez(os.path.join(OUT, "bilinear_demo.npz"), A=npy(A), B=npy(B), d=dv, H=Hm, q=qv, r=rv, q0=q0, N=N, L=npy(Lb), l=npy(lb))
+print("bilinear_demo", Lb.shape, lb.shape)
+
+# ---- (iv) quadcopter dynamics + autodiff expansions at random points (incl. wind) -------------------------------------
+rng = np.random.default_rng(1234 + 11)
+xs = configs.quad_states(rng, 16)
+us = np.tile(configs.U_TRIM, (16, 1)) + rng.normal(size=(16, 4))
+wind = np.array([3.0, 1.0, 0.0])  # demos/iterativeLqr.py:47
+F0 = np.array([npy(ac.inertialDynamics(T(x), T(u))) for x, u in zip(xs, us)])
+Fw = np.array([npy(ac.inertialDynamics(T(x), T(u), wind_ned=T(wind))) for x, u in zip(xs, us)])
+Jx, Ju, Hxx = [], [], []
+for x, u in zip(xs, us):
+    jx, ju = jax.jacobian(ac.inertialDynamics, argnums=(0, 1))(T(x), T(u))
+    hx = jax.hessian(ac.inertialDynamics, 0)(T(x), T(u))
+    Jx.append(npy(jx)), Ju.append(npy(ju)), Hxx.append(npy(hx))
+np.savez(os.path.join(OUT, "quadcopter_points.npz"), x=xs, u=us, wind=wind, F=F0, F_wind=Fw, Jx=np.array(Jx), Ju=np.array(Ju),
+         Hxx=np.array(Hxx))
+print("quadcopter_points")
+
+# ---- (v) iLQR / DDP on the demos' problems (demos/iterativeLqr.py:22-39, demos/differentialDynamicProgramming.py:22-39) --
+dt = 0.1
+dynFun = lambda x, u: x + dt * ac.inertialDynamics(x, u)
+
+
+def run_solver(solver, x0, N, R, maxIter):
+    Q = np.eye(12)
+    Qt, Rt = T(Q), T(R)
+    costFun = lambda x, u: x.T @ Qt @ x + u.T @ Rt @ u
+    terminalCostFun = lambda x: 10 * x @ Qt @ x
+    uGuess = T(np.repeat(configs.U_TRIM[None], N, axis=0))
+    # per-iteration record by running the reference solver with maxIter = 1..k (it is deterministic)
+    Js, trajs = [], None
+    for k in range(0, maxIter + 1):
+        traj, LArr, J, conv = solver(dynFun, costFun, terminalCostFun, T(x0), uGuess, maxIter=k, tol=-1.0)
+        Js.append(float(J))
+    return dict(x0=x0, N=N, R=R, J_per_iter=np.array(Js), xTraj=npy(traj.xTraj), uTraj=npy(traj.uTraj), L=npy(LArr),
+                converged=bool(conv), maxIter=maxIter)
+
+
+x0 = np.zeros(12)
+x0[9:12] = [10, 10, 10]
+g = run_solver(ref_ilqr.iterativeLqr, x0, 40, np.eye(4), 4)
+np.savez(os.path.join(OUT, "ilqr_demo_N40_it4.npz"), **g)
+print("ilqr", g["J_per_iter"])
+x0 = np.zeros(12)
+x0[9:12] = [0, 5, 0]
+g = run_solver(ref_ilqr.differentialDynamicProgramming, x0, 40, 0.2 * np.eye(4), 3)
+np.savez(os.path.join(OUT, "ddp_demo_N40_it3.npz"), **g)
+print("ddp", g["J_per_iter"])
+
+# ---- (vi) single Riccati steps on random pytrees (riccatiStep_ilqr / riccatiStep_ddp / ensurePositiveDefinite) -------
+rng = np.random.default_rng(1234 + 12)
+n, m = 5, 3
+spd = lambda k: (lambda M: M @ M.T + np.eye(k))(rng.normal(size=(k, k)))
+f_x, f_u = rng.normal(size=(n, n)) * 0.5, rng.normal(size=(n, m))
+sym = lambda t: t + np.swapaxes(t, -1, -2)
+f_xx, f_ux, f_uu = sym(rng.normal(size=(n, n, n)) * 0.1), rng.normal(size=(n, m, n)) * 0.1, sym(rng.normal(size=(n, m, m)) * 0.1)
+czz = spd(n + m)
+c, c_x, c_u = rng.normal(), rng.normal(size=n), rng.normal(size=m)
+v, v_x, v_xx = rng.normal(), rng.normal(size=n), spd(n)
+cost = ref_pytrees.QuadraticCostFunction(T(c), T(c_x), T(c_u), T(czz[:n, :n]), T(czz[n:, :n]), T(czz[n:, n:]))
+val = ref_pytrees.QuadraticValueFunction(T(v), T(v_x), T(v_xx))
+vo1, p1 = ref_ilqr.riccatiStep_ilqr(ref_pytrees.AffineDynamics(T(np.zeros(n)), T(f_x), T(f_u)), cost, val)
+vo2, p2 = ref_ilqr.riccatiStep_ddp(ref_pytrees.QuadraticDynamics(T(np.zeros(n)), T(f_x), T(f_u), T(f_xx), T(f_ux), T(f_uu)), cost, val)
+S = sym(rng.normal(size=(16, 16)))
+np.savez(os.path.join(OUT, "riccati_steps.npz"), f_x=f_x, f_u=f_u, f_xx=f_xx, f_ux=f_ux, f_uu=f_uu, czz=czz, c=c, c_x=c_x, c_u=c_u,
+         v=v, v_x=v_x, v_xx=v_xx, ilqr_v=npy(vo1.v), ilqr_vx=npy(vo1.v_x), ilqr_vxx=npy(vo1.v_xx), ilqr_l=npy(p1.l), ilqr_L=npy(p1.L),
+         ddp_v=npy(vo2.v), ddp_vx=npy(vo2.v_x), ddp_vxx=npy(vo2.v_xx), ddp_l=npy(p2.l), ddp_L=npy(p2.L), S=S,
+         S_pd=npy(ref_ilqr.ensurePositiveDefinite(T(S))))
+print("riccati_steps")
+print("golden fixtures written to", OUT)

@@ -1,0 +1,170 @@
+"""
+Golden fixtures (tests/golden/*.npz) produced by the UNMODIFIED reference sources run on oracle/jax_shim
+(scripts/gen_golden_from_reference.py; jax itself is not installable here).  CPU tests pin the oracle against them;
+GPU tests (-m gpu) pin the CUDA path against the same files.  fp64: 1e-10 max-norm relative.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ilqr as oilqr
+from oracle import lqr as olqr
+from oracle import pytrees as opt
+from oracle.quadcopter import Quadcopter as OQuadcopter
+from zopt_b200 import configs
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+load = lambda name: np.load(os.path.join(G, name), allow_pickle=False)
+T = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+
+
+def relerr(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a.astype(np.float64) - b)) / (den if den > 0 else 1.0))
+
+
+def rep(a, N):
+    return np.repeat(np.asarray(a)[None], N, axis=0)
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs goldens (CPU)
+def test_oracle_lqr_goldens():
+    g = load("lqr_demo_n8.npz")
+    N = int(g["N"])
+    assert relerr(olqr.discreteFiniteHorizonLqr(rep(g["A"], N), rep(g["B"], N), g["Qk"], g["Rk"], N), g["K"]) < 1e-12
+    g = load("lqr_cfg2_32.npz")
+    N = int(g["N"])
+    oac = OQuadcopter()
+    for i in range(32):
+        A, B = (t.numpy() for t in oac.linearizeInertial(g["xbar"][i], g["ubar"][i], 0.1))
+        assert relerr(A, g["A"][i]) < 1e-13 and relerr(B, g["B"][i]) < 1e-13
+        Qk = rep(np.diag(g["qdiag"][i]), N + 1)
+        Qk[N] *= 10
+        L = olqr.discreteFiniteHorizonLqr(rep(A, N), rep(B, N), Qk, rep(np.diag(g["rdiag"][i]), N), N)
+        assert relerr(L, g["L"][i]) < 1e-11
+    g = load("bilinear_demo.npz")
+    N = int(g["N"])
+    L, l = olqr.bilinearAffineLqr(rep(g["A"], N), rep(g["B"], N), g["d"], rep(np.eye(8), N), rep(np.eye(4), N), g["H"], g["q"],
+                                  g["r"], g["q0"], N)
+    assert relerr(L, g["L"]) < 1e-11 and relerr(l, g["l"]) < 1e-11
+
+
+def test_oracle_quadcopter_goldens():
+    g = load("quadcopter_points.npz")
+    oac = OQuadcopter()
+    for i in range(len(g["x"])):
+        x, u = T(g["x"][i]), T(g["u"][i])
+        assert relerr(oac.inertialDynamics(x, u), g["F"][i]) < 1e-13
+        assert relerr(oac.inertialDynamics(x, u, T(g["wind"])), g["F_wind"][i]) < 1e-13
+        jx, ju = torch.func.jacrev(oac.inertialDynamics, argnums=(0, 1))(x, u)
+        assert relerr(jx, g["Jx"][i]) < 1e-13 and relerr(ju, g["Ju"][i]) < 1e-13
+
+
+def _solver_golden(name):
+    g = load(name)
+    ddp = name.startswith("ddp")
+    oac = OQuadcopter()
+    Q, R = torch.eye(12, dtype=torch.float64), T(g["R"])
+    N = int(g["N"])
+    return g, ddp, oac.eulerStep(0.1), (lambda x, u: x @ Q @ x + u @ R @ u), (lambda x: 10 * x @ Q @ x), N
+
+
+@pytest.mark.parametrize("name", ["ilqr_demo_N40_it4.npz", "ddp_demo_N40_it3.npz"])
+def test_oracle_solver_goldens(name):
+    g, ddp, dyn, rc, tc, N = _solver_golden(name)
+    log = []
+    solver = oilqr.differentialDynamicProgramming if ddp else oilqr.iterativeLqr
+    traj, L, J, conv = solver(dyn, rc, tc, T(g["x0"]), T(rep(configs.U_TRIM, N)), maxIter=int(g["maxIter"]), tol=-1.0, log=log)
+    assert relerr(np.array([e["J"] for e in log]), g["J_per_iter"]) < 1e-11
+    assert relerr(traj.xTraj, g["xTraj"]) < 1e-10 and relerr(traj.uTraj, g["uTraj"]) < 1e-10 and relerr(L, g["L"]) < 1e-10
+
+
+def test_oracle_riccati_step_goldens():
+    g = load("riccati_steps.npz")
+    n = 5
+    czz = g["czz"]
+    cost = opt.QuadraticCostFunction(T(g["c"]), T(g["c_x"]), T(g["c_u"]), T(czz[:n, :n]), T(czz[n:, :n]), T(czz[n:, n:]))
+    val = opt.QuadraticValueFunction(T(g["v"]), T(g["v_x"]), T(g["v_xx"]))
+    vo, p = oilqr.riccatiStep_ilqr(opt.AffineDynamics(torch.zeros(n), T(g["f_x"]), T(g["f_u"])), cost, val)
+    assert relerr(vo.v_xx, g["ilqr_vxx"]) < 1e-12 and relerr(vo.v_x, g["ilqr_vx"]) < 1e-12 and relerr(p.L, g["ilqr_L"]) < 1e-12
+    assert relerr(p.l, g["ilqr_l"]) < 1e-12 and abs(float(vo.v) - float(g["ilqr_v"])) < 1e-12
+    vo, p = oilqr.riccatiStep_ddp(opt.QuadraticDynamics(torch.zeros(n), T(g["f_x"]), T(g["f_u"]), T(g["f_xx"]), T(g["f_ux"]), T(g["f_uu"])),
+                                  cost, val)
+    assert relerr(vo.v_xx, g["ddp_vxx"]) < 1e-11 and relerr(p.L, g["ddp_L"]) < 1e-11 and relerr(p.l, g["ddp_l"]) < 1e-11
+    assert relerr(oilqr.ensurePositiveDefinite(T(g["S"])), g["S_pd"]) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ CUDA path vs goldens
+@pytest.mark.gpu
+def test_gpu_lqr_goldens():
+    from zopt_b200.lqrUtils import bilinearAffineLqr, discreteFiniteHorizonLqr
+    from zopt_b200.quadcopter import Quadcopter
+    g = load("lqr_demo_n8.npz")
+    N = int(g["N"])
+    assert relerr(discreteFiniteHorizonLqr(rep(g["A"], N), rep(g["B"], N), g["Qk"], g["Rk"], N), g["K"]) < 1e-10
+    g = load("lqr_cfg2_32.npz")
+    N = int(g["N"])
+    A, B = Quadcopter().linearizeInertial(g["xbar"], g["ubar"], 0.1)
+    assert relerr(A, g["A"]) < 1e-12 and relerr(B, g["B"]) < 1e-12
+    Q = configs.diag_embed(g["qdiag"])
+    Qk = np.repeat(Q[:, None], N + 1, axis=1)
+    Qk[:, N] *= 10
+    Rk = torch.as_tensor(configs.diag_embed(g["rdiag"]), device="cuda")[:, None].expand(-1, N, -1, -1)
+    for dt, tol in ((torch.float64, 1e-10), (torch.float32, 1e-5)):
+        L = discreteFiniteHorizonLqr(A[:, None].expand(-1, N, -1, -1).to(dt), B[:, None].expand(-1, N, -1, -1).to(dt),
+                                     torch.as_tensor(Qk, dtype=dt, device="cuda"), Rk.to(dt), N)
+        err = np.max(np.abs(L.double().cpu().numpy() - g["L"]), axis=(1, 2, 3)) / np.max(np.abs(g["L"]), axis=(1, 2, 3))
+        assert err.max() < tol
+    g = load("bilinear_demo.npz")
+    N = int(g["N"])
+    L, l = bilinearAffineLqr(rep(g["A"], N), rep(g["B"], N), g["d"], rep(np.eye(8), N), rep(np.eye(4), N), g["H"], g["q"], g["r"],
+                             g["q0"], N)
+    assert relerr(L, g["L"]) < 1e-10 and relerr(l, g["l"]) < 1e-10
+
+
+@pytest.mark.gpu
+def test_gpu_quadcopter_goldens():
+    from zopt_b200.quadcopter import Quadcopter, quad_hess_contract
+    g = load("quadcopter_points.npz")
+    ac = Quadcopter()
+    assert relerr(ac.inertialDynamics(g["x"], g["u"]), g["F"]) < 1e-12
+    assert relerr(ac.inertialDynamics(g["x"], g["u"], g["wind"]), g["F_wind"]) < 1e-12
+    A, B = ac.linearizeInertial(g["x"], g["u"], dt=0)
+    assert relerr(A, g["Jx"]) < 1e-12 and relerr(B, g["Ju"]) < 1e-12
+    rng = np.random.default_rng(0)
+    lam = rng.normal(size=(len(g["x"]), 12))
+    assert relerr(quad_hess_contract(g["x"], g["u"], None, 0.0, lam), np.einsum('bi,bijk->bjk', lam, g["Hxx"])) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ilqr_demo_N40_it4.npz", "ddp_demo_N40_it3.npz"])
+def test_gpu_solver_goldens(name):
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    g, ddp, _, _, _, N = _solver_golden(name)
+    solver = ilqrUtils.differentialDynamicProgramming if ddp else ilqrUtils.iterativeLqr
+    traj, L, J, conv, log = solver(QuadcopterEuler(0.1), QuadraticCost(np.eye(12), g["R"]), QuadraticTerminalCost(10 * np.eye(12)),
+                                   g["x0"], rep(configs.U_TRIM, N), maxIter=int(g["maxIter"]), tol=-1.0, return_log=True)
+    assert relerr(log["J"], g["J_per_iter"]) < 1e-10
+    assert relerr(traj.xTraj, g["xTraj"]) < 1e-10 and relerr(traj.uTraj, g["uTraj"]) < 1e-10 and relerr(L, g["L"]) < 1e-10
+    assert abs(float(J) - g["J_per_iter"][-1]) < 1e-10 * g["J_per_iter"][-1]
+
+
+@pytest.mark.gpu
+def test_gpu_riccati_step_goldens():
+    from zopt_b200 import ilqrUtils, pytrees
+    g = load("riccati_steps.npz")
+    n = 5
+    czz = g["czz"]
+    cost = pytrees.QuadraticCostFunction(g["c"], g["c_x"], g["c_u"], czz[:n, :n], czz[n:, :n], czz[n:, n:])
+    val = pytrees.QuadraticValueFunction(g["v"], g["v_x"], g["v_xx"])
+    vo, p = ilqrUtils.riccatiStep_ilqr(pytrees.AffineDynamics(np.zeros(n), g["f_x"], g["f_u"]), cost, val)
+    assert relerr(vo.v_xx, g["ilqr_vxx"]) < 1e-11 and relerr(vo.v_x, g["ilqr_vx"]) < 1e-11 and relerr(p.L, g["ilqr_L"]) < 1e-11
+    assert relerr(p.l, g["ilqr_l"]) < 1e-11 and abs(float(vo.v) - float(g["ilqr_v"])) < 1e-11 * max(1, abs(float(g["ilqr_v"])))
+    vo, p = ilqrUtils.riccatiStep_ddp(pytrees.QuadraticDynamics(np.zeros(n), g["f_x"], g["f_u"], g["f_xx"], g["f_ux"], g["f_uu"]), cost, val)
+    assert relerr(vo.v_xx, g["ddp_vxx"]) < 1e-10 and relerr(p.L, g["ddp_L"]) < 1e-10 and relerr(p.l, g["ddp_l"]) < 1e-10
+    assert relerr(ilqrUtils.ensurePositiveDefinite(g["S"]), g["S_pd"]) < 1e-11
