@@ -153,8 +153,13 @@ ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_
  * Bounds may be +-inf.  When no bound can bind the solve is the exact Riccati sweep + rollout;
  * otherwise ADMM (over-relaxed, residual-balanced rho, as OSQP) with the dynamics kept exact: the linear solve of
  * every iteration is a vector Riccati sweep + rollout against gains factored once per rho.
+ * flags: ZB_MPC_BOUNDED = at least one bound is finite (ADMM path); ZB_COST_DIAGONAL = the caller asserts that Q, R
+ * and Qf are diagonal (the fp32 (12,4) kernel then keeps 4 instead of 27 float4 of cost data per problem on chip).
  * status_out (Bsz) int8: 0 optimal, 1 optimal_inaccurate (max_iter hit), 2 infeasible.
  * iters_out (Bsz) int32 ADMM iterations (0 on the unconstrained path). */
+#define ZB_MPC_BOUNDED 1
+#define ZB_COST_DIAGONAL 2
+
 typedef struct zb_admm_opts {
     int32_t max_iter;   /* default 4000 */
     int32_t check_every; /* default 25 */
@@ -166,7 +171,7 @@ ZB_API size_t zb_mpc_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int3
 ZB_API int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t n, int32_t m,
                          const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, const zb_arr* Qf,
                          const zb_arr* x_lb, const zb_arr* x_ub, const zb_arr* u_lb, const zb_arr* u_ub,
-                         int32_t bounded, const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj,
+                         int32_t flags, const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj,
                          void* uTraj, int8_t* status_out, int32_t* iters_out, void* workspace,
                          size_t workspace_bytes);
 

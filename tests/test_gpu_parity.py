@@ -529,3 +529,35 @@ def test_lqrMpc_box_constrained_vs_oracle():
     u, traj, status = lqrMpc(I, I, I, I, 2, -one, one, -one, one).solve(one)
     assert status == "optimal"
     assert traj.uTraj.cpu().numpy() == pytest.approx(np.array([[-0.6, -0.6], [-0.2, -0.2]]), abs=1e-3)
+
+
+@pytest.mark.parametrize("dense_cost", [False, True])
+def test_fast_paths_fp32_time_invariant(dense_cost):
+    """fp32 (12,4) thread-per-problem kernel (lqr_t1.cuh): diagonal-cost and dense-cost variants, through
+    discreteFiniteHorizonLqr (fully time-invariant operands, terminal = Q) and through lqrMpc (terminal Qf), ragged batch."""
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    from zopt_b200.mpcUtils import lqrMpc
+    Bsz = 77
+    d, A, B, Q, R, N = _cfg2_arrays(Bsz, False)
+    if dense_cost:
+        rng = np.random.default_rng(3)
+        def spd(k, base):
+            M = rng.normal(size=(Bsz, k, k)) * 0.3
+            return base + M @ np.swapaxes(M, 1, 2)
+        Q, R = spd(12, Q), spd(4, R)
+    f32 = torch.float32
+    Ad, Bd, Qd, Rd = (cuda(t, f32) for t in (A, B, Q, R))
+    ex = lambda t: t[:, None].expand(-1, N, -1, -1)
+    L, V0 = discreteFiniteHorizonLqr(ex(Ad), ex(Bd), ex(Qd), ex(Rd), N, return_value=True)
+    rep = lambda t: np.repeat(t[:, None], N, 1)
+    Lref, Vref = olqr.discreteFiniteHorizonLqr_batched(rep(A), rep(B), rep(Q), rep(R), N, return_value=True)
+    assert per_problem_relerr(L, Lref).max() < 1e-5 and per_problem_relerr(V0, Vref).max() < 1e-5
+    inf12, inf4 = np.full(12, np.inf), np.full(4, np.inf)
+    prob = lqrMpc(Ad, Bd, Qd, Rd, N, -inf12, inf12, -inf4, inf4, Qf=10 * Qd)
+    assert prob.cost_diagonal == (not dense_cost)
+    u, traj, status = prob.solve(cuda(d["xbar"], f32))
+    from oracle import mpc as ompc
+    for b in (0, 13, Bsz - 1):
+        xr, ur = ompc.riccati_plan(A[b], B[b], Q[b], R[b], N, d["xbar"][b], Qf=10 * Q[b])
+        assert relerr(traj.uTraj[b], ur) < 2e-5 and relerr(traj.xTraj[b], xr) < 2e-5
+    assert (status == 0).all() and relerr(u, traj.uTraj[:, 0]) == 0

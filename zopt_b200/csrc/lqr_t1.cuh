@@ -1,0 +1,365 @@
+// Thread-per-problem Riccati kernel for (n, m) = (12, 4), fp32, time-invariant A, B, Q, R  (round-1 v2).
+//
+// Why this shape.  ncu on the first cooperative kernel (lqr_fast.cuh, 4 threads per problem) showed the
+// shared-memory pipe at 91 % and the FMA pipe at 45 %: a 128-bit shared load costs four LSU wavefronts per
+// warp whatever is broadcast, so time is set by WORDS LOADED PER THREAD, and a 12x4 accumulator tile with
+// both operands streamed gives only ~2.3 FMA per loaded word (the SM delivers 32 words/cycle against 128
+// FMA/cycle, i.e. >= 4 are needed).  Here ONE thread owns one problem and keeps the whole symmetric value
+// matrix V (78 words) in registers across the horizon:
+//   1.  W = V A in three 12x4 panels: per k one 128-bit load of the panel row feeds 48 FMAs (12 per loaded
+//       word); W -> smem.  VB = V B the same way with B's rows held in registers, G0 = B^T (V B).
+//   2.  G = G0 + R, 4x4 Cholesky (its latency hides behind step 3's FMAs).
+//   3.  One pass over the rows of A, W, B: V' = Q + A^T W (LOWER TRIANGLE ONLY: 78 accumulators = the new V,
+//       symmetry exact by construction, a third of the update's FMAs gone) and M = B^T W; then L = G^-1 M for
+//       the 12 columns and V' -= M^T L, all in registers.  (Algebraically the reference's Joseph form,
+//       lqrUtils.py:169; fp32 parity gated at 1e-5.)
+// ~4,580 FMA and ~950 loaded/stored words per problem-step (4.8 FMA/word) instead of 6,460 FMA-slots and
+// ~2,800 words.  Operands live in shared memory interleaved by lane ([float4 slot][lane]) so every 128-bit
+// access of a warp is one contiguous 512 B row: conflict-free, and no thread ever reads another thread's
+// slots -- the main loop needs no barrier.  One warp per CTA, 4 CTAs per SM (111 float4 = 1,776 B per problem).
+#pragma once
+#include "lqr_fast.cuh"
+
+namespace zb {
+namespace t1 {
+
+constexpr int X4 = 0;     // [A | B] rows: 12 rows x 4 float4 (chunk 3 = B row)
+constexpr int W4 = 48;    // W rows: 12 x 3 float4
+constexpr int Q4 = 84;    // Q, lower-triangle-covering chunks: row i has i/4+1 float4 (24 in all)
+constexpr int R4 = 108;   // R lower packed (10 words) + 2 pad
+constexpr int NF4 = 111;  // float4 slots per problem (dense cost)
+constexpr int NF4_DIAG = 88;  // diagonal cost: slots Q4..Q4+2 = diag(Q), Q4+3 = diag(R)
+constexpr int STG = 13;   // staging stride (float4) for the transposed gain store, odd -> conflict-free
+
+__host__ __device__ constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+__host__ __device__ constexpr int qoff(int i) { return i < 4 ? i : (i < 8 ? 4 + 2 * (i - 4) : 12 + 3 * (i - 8)); }
+
+#define ZB_F4(v, e) ((e) == 0 ? (v).x : (e) == 1 ? (v).y : (e) == 2 ? (v).z : (v).w)
+
+// load the lower triangle of a symmetric 12x12 (row-major, global) into v[78]
+__device__ __forceinline__ void load_sym_lower(const float* g, float* v) {
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+#pragma unroll
+        for (int c = 0; c <= i / 4; ++c) {
+            const float4 q = __ldg(g4 + i * 3 + c);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * c + e <= i) v[tri(i, 4 * c + e)] = ZB_F4(q, e);
+        }
+}
+
+// QDIAG: the caller asserts Q, R, Qf diagonal (ZB_COST_DIAGONAL): 4 float4 of cost data instead of 27, so FIVE
+// CTAs fit an SM (88 float4 = 1,408 B per problem) and 65,536 problems take 3 rounds of CTAs instead of 4.
+template <bool MPC, bool QDIAG>
+__global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
+    extern __shared__ float4 sm[];
+    const int lane = threadIdx.x;
+    const long long b_raw = (long long)blockIdx.x * 32 + lane;
+    const bool active = b_raw < P.Bsz;
+    const long long b = active ? b_raw : P.Bsz - 1;
+    float4* S = sm + lane;  // slot s of this problem: S[s * 32]
+
+    // ---- stage this problem's operands (each lane its own problem; L1 keeps the partially used lines) ----
+    {
+        const float4* gA = reinterpret_cast<const float4*>(P.A.at<float>(b));
+        const float4* gB = reinterpret_cast<const float4*>(P.B.at<float>(b));
+        const float4* gQ = reinterpret_cast<const float4*>(P.Q.at<float>(b, 0));
+        const float4* gR = reinterpret_cast<const float4*>(P.R.at<float>(b));
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) S[(X4 + k * 4 + c) * 32] = __ldg(gA + k * 3 + c);
+            S[(X4 + k * 4 + 3) * 32] = __ldg(gB + k);
+        }
+        if (QDIAG) {
+            const float* q = P.Q.at<float>(b, 0);
+            const float* r = P.R.at<float>(b);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                S[(Q4 + c) * 32] = make_float4(__ldg(q + (4 * c) * 13), __ldg(q + (4 * c + 1) * 13), __ldg(q + (4 * c + 2) * 13), __ldg(q + (4 * c + 3) * 13));
+            S[(Q4 + 3) * 32] = make_float4(__ldg(r), __ldg(r + 5), __ldg(r + 10), __ldg(r + 15));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+#pragma unroll
+                for (int c = 0; c <= k / 4; ++c) S[(Q4 + qoff(k) + c) * 32] = __ldg(gQ + k * 3 + c);
+            const float4 r0 = __ldg(gR), r1 = __ldg(gR + 1), r2 = __ldg(gR + 2), r3 = __ldg(gR + 3);
+            S[(R4 + 0) * 32] = make_float4(r0.x, r1.x, r1.y, r2.x);
+            S[(R4 + 1) * 32] = make_float4(r2.y, r2.z, r3.x, r3.y);
+            S[(R4 + 2) * 32] = make_float4(r3.z, r3.w, 0.f, 0.f);
+        }
+    }
+    float v[78];
+    if (QDIAG) {
+        const float* qf = MPC ? P.Qf.at<float>(b) : P.Q.at<float>(b, P.T - 1);
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) v[tri(i, j)] = (i == j) ? __ldg(qf + i * 13) : 0.f;
+    } else {
+        load_sym_lower(MPC ? P.Qf.at<float>(b) : P.Q.at<float>(b, P.T - 1), v);
+    }
+
+    const long long wblk = blockIdx.x;  // 32 problems per CTA
+    // MPC: gains in the workspace, layout [cta][k][12 float4][lane]; dfh: public (Bsz,N,4,12)
+    float4* gws = reinterpret_cast<float4*>(P.gains) + wblk * (long long)P.N * 12 * 32 + lane;
+    float* gpub = P.gains + (long long)blockIdx.x * 32 * (long long)P.N * 48;
+
+    for (int k = P.N - 1; k >= 0; --k) {
+        // ---- 1. [W | VB] = V [A | B] in four 12x4 panels.  ROLLED loop: one ~600-instruction body re-used four
+        //         times keeps the step's code inside the instruction cache (the fully unrolled first version
+        //         stalled 0.8 cycle/instruction on instruction fetch with one warp per scheduler).
+        float G[10];
+        float4 xfirst = S[(X4 + 0) * 32];  // row 0 of the next panel, fetched before the previous panel's epilogue
+#pragma unroll 1
+        for (int p = 0; p < 4; ++p) {
+            float acc[12][4];
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 12; ++kk) {
+                const float4 x4 = (kk == 0) ? xfirst : S[(X4 + kk * 4 + p) * 32];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    const float vik = v[tri(i, kk)];
+                    acc[i][0] = fmaf(vik, x4.x, acc[i][0]);
+                    acc[i][1] = fmaf(vik, x4.y, acc[i][1]);
+                    acc[i][2] = fmaf(vik, x4.z, acc[i][2]);
+                    acc[i][3] = fmaf(vik, x4.w, acc[i][3]);
+                }
+            }
+            xfirst = S[(X4 + ((p < 3) ? p + 1 : 0)) * 32];
+            if (p < 3) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) S[(W4 + i * 3 + p) * 32] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            } else {  // acc = V B: G = R + B^T (V B), lower triangle
+                if (QDIAG) {
+                    const float4 rd = S[(Q4 + 3) * 32];
+                    G[0] = rd.x; G[1] = 0.f; G[2] = rd.y; G[3] = 0.f; G[4] = 0.f; G[5] = rd.z; G[6] = 0.f; G[7] = 0.f; G[8] = 0.f; G[9] = rd.w;
+                } else {
+                    const float4 r0 = S[(R4 + 0) * 32], r1 = S[(R4 + 1) * 32], r2 = S[(R4 + 2) * 32];
+                    G[0] = r0.x; G[1] = r0.y; G[2] = r0.z; G[3] = r0.w; G[4] = r1.x;
+                    G[5] = r1.y; G[6] = r1.z; G[7] = r1.w; G[8] = r2.x; G[9] = r2.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    const float4 b4 = S[(X4 + i * 4 + 3) * 32];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int c = 0; c <= a; ++c) G[tri(a, c)] = fmaf(ZB_F4(b4, a), acc[i][c], G[tri(a, c)]);
+                }
+            }
+        }
+        // ---- 2. Cholesky G = C C^T (G already holds G0 + R) ------------------------------------------------
+        const float d0 = rsqrtf(G[0]);
+        const float c10 = G[1] * d0, c20 = G[3] * d0, c30 = G[6] * d0;
+        const float d1 = rsqrtf(fmaf(-c10, c10, G[2]));
+        const float c21 = fmaf(-c20, c10, G[4]) * d1, c31 = fmaf(-c30, c10, G[7]) * d1;
+        const float d2 = rsqrtf(fmaf(-c21, c21, fmaf(-c20, c20, G[5])));
+        const float c32 = fmaf(-c31, c21, fmaf(-c30, c20, G[8])) * d2;
+        const float d3 = rsqrtf(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
+        // ---- 3a. V' (lower) = Q + A^T W and M = B^T W in one pass over the rows of A, W, B ------------------
+        // (independent of the Cholesky chain above, so the scheduler can hide its latency behind these FMAs)
+        if (QDIAG) {
+            const float4 q0 = S[(Q4 + 0) * 32], q1 = S[(Q4 + 1) * 32], q2 = S[(Q4 + 2) * 32];
+            const float qd[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) v[tri(i, j)] = (i == j) ? qd[i] : 0.f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+#pragma unroll
+                for (int c = 0; c <= i / 4; ++c) {
+                    const float4 q = S[(Q4 + qoff(i) + c) * 32];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (4 * c + e <= i) v[tri(i, 4 * c + e)] = ZB_F4(q, e);
+                }
+        }
+        float M[4][12];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 12; ++j) M[a][j] = 0.f;
+        {
+            float4 ra[3], rw[3], rb;  // rows kk of A, W, B; next rows are fetched while the current ones are consumed
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + c) * 32]; rw[c] = S[(W4 + c) * 32]; }
+            rb = S[(X4 + 3) * 32];
+#pragma unroll 1
+            for (int kk = 0; kk < 12; ++kk) {
+                const float a[12] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w, ra[1].x, ra[1].y, ra[1].z, ra[1].w, ra[2].x, ra[2].y, ra[2].z, ra[2].w};
+                const float w[12] = {rw[0].x, rw[0].y, rw[0].z, rw[0].w, rw[1].x, rw[1].y, rw[1].z, rw[1].w, rw[2].x, rw[2].y, rw[2].z, rw[2].w};
+                const float4 b4 = rb;
+                const int kn = (kk < 11) ? kk + 1 : 11;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + kn * 4 + c) * 32]; rw[c] = S[(W4 + kn * 3 + c) * 32]; }
+                rb = S[(X4 + kn * 4 + 3) * 32];
+#pragma unroll
+                for (int i = 0; i < 12; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) v[tri(i, j)] = fmaf(a[i], w[j], v[tri(i, j)]);
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    M[0][j] = fmaf(b4.x, w[j], M[0][j]);
+                    M[1][j] = fmaf(b4.y, w[j], M[1][j]);
+                    M[2][j] = fmaf(b4.z, w[j], M[2][j]);
+                    M[3][j] = fmaf(b4.w, w[j], M[3][j]);
+                }
+            }
+        }
+        // ---- 2b. L = G^-1 M (12 right-hand sides) ------------------------------------------------------
+        float L[4][12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const float y0 = M[0][j] * d0;
+            const float y1 = fmaf(-c10, y0, M[1][j]) * d1;
+            const float y2 = fmaf(-c21, y1, fmaf(-c20, y0, M[2][j])) * d2;
+            const float y3 = fmaf(-c32, y2, fmaf(-c31, y1, fmaf(-c30, y0, M[3][j]))) * d3;
+            const float x3 = y3 * d3;
+            const float x2 = fmaf(-c32, x3, y2) * d2;
+            const float x1 = fmaf(-c31, x3, fmaf(-c21, x2, y1)) * d1;
+            const float x0 = fmaf(-c30, x3, fmaf(-c20, x2, fmaf(-c10, x1, y0))) * d0;
+            L[0][j] = x0; L[1][j] = x1; L[2][j] = x2; L[3][j] = x3;
+        }
+        // ---- 3b. V' -= M^T L (lower) --------------------------------------------------------------------
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) v[tri(i, j)] = fmaf(-M[a][i], L[a][j], v[tri(i, j)]);
+        // ---- 4. gains out ------------------------------------------------------------------------------
+        if (MPC) {
+            float4* g = gws + (long long)k * 12 * 32;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    g[(a * 3 + c) * 32] = make_float4(L[a][4 * c], L[a][4 * c + 1], L[a][4 * c + 2], L[a][4 * c + 3]);
+        } else {
+            // public layout (Bsz,N,4,12): transpose through smem (the W region is free now) for coalesced stores
+            float4* stg = sm + W4 * 32;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    stg[lane * STG + a * 3 + c] = make_float4(L[a][4 * c], L[a][4 * c + 1], L[a][4 * c + 2], L[a][4 * c + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 12; ++r) {
+                const int idx = r * 32 + lane, pr = idx / 12, j4 = idx - pr * 12;
+                const float4 val = stg[pr * STG + j4];
+                if ((long long)blockIdx.x * 32 + pr < P.Bsz)
+                    *reinterpret_cast<float4*>(gpub + ((long long)pr * P.N + k) * 48 + j4 * 4) = val;
+            }
+            __syncwarp();
+        }
+    }
+
+    if (P.V0 && active) {
+        float* o = P.V0 + b * 144;
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int j = 0; j < 12; ++j) o[i * 12 + j] = v[tri(i, j)];
+    }
+
+    if (MPC) {
+        // ---- plan rollout x+ = A x + B u, u = -L_k x (mpcUtils.py:55).  A, B rows from smem; the gains of the
+        //      next step are prefetched (L2) while the current step's dependent chain runs ----
+        float x[12];
+        {
+            const float4* gx = reinterpret_cast<const float4*>(P.x0 + b * 12);
+            const float4 x0 = __ldg(gx), x1 = __ldg(gx + 1), x2 = __ldg(gx + 2);
+            x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+            x[8] = x2.x; x[9] = x2.y; x[10] = x2.z; x[11] = x2.w;
+        }
+        float4* xT = reinterpret_cast<float4*>(P.xTraj + b * (long long)(P.N + 1) * 12);
+        float4* uT = reinterpret_cast<float4*>(P.uTraj + b * (long long)P.N * 4);
+        if (active) {
+            xT[0] = make_float4(x[0], x[1], x[2], x[3]); xT[1] = make_float4(x[4], x[5], x[6], x[7]); xT[2] = make_float4(x[8], x[9], x[10], x[11]);
+        }
+        // gains of steps k, k+1, k+2 are in flight in three register buffers (L2 latency ~ two steps of the chain)
+        float4 gbuf[3][12];
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {
+            const int ks = (s3 < P.N) ? s3 : P.N - 1;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) gbuf[s3][j] = __ldcg(gws + ((long long)ks * 12 + j) * 32);
+        }
+#pragma unroll 1
+        for (int k0 = 0; k0 < P.N; k0 += 3) {
+#pragma unroll
+            for (int s3 = 0; s3 < 3; ++s3) {
+                const int k = k0 + s3;
+                if (k < P.N) {
+                    float u[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const float4 l0 = gbuf[s3][a * 3], l1 = gbuf[s3][a * 3 + 1], l2 = gbuf[s3][a * 3 + 2];
+                        float s0 = l0.x * x[0], s1 = l1.x * x[4], s2 = l2.x * x[8];
+                        s0 = fmaf(l0.y, x[1], s0); s1 = fmaf(l1.y, x[5], s1); s2 = fmaf(l2.y, x[9], s2);
+                        s0 = fmaf(l0.z, x[2], s0); s1 = fmaf(l1.z, x[6], s1); s2 = fmaf(l2.z, x[10], s2);
+                        s0 = fmaf(l0.w, x[3], s0); s1 = fmaf(l1.w, x[7], s1); s2 = fmaf(l2.w, x[11], s2);
+                        u[a] = -((s0 + s1) + s2);
+                    }
+                    {
+                        const int kp = (k + 3 < P.N) ? k + 3 : P.N - 1;
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) gbuf[s3][j] = __ldcg(gws + ((long long)kp * 12 + j) * 32);
+                    }
+                    float xn[12];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        const float4 a0 = S[(X4 + i * 4 + 0) * 32], a1 = S[(X4 + i * 4 + 1) * 32], a2 = S[(X4 + i * 4 + 2) * 32], b4 = S[(X4 + i * 4 + 3) * 32];
+                        float s0 = a0.x * x[0], s1 = a1.x * x[4], s2 = a2.x * x[8], s3f = b4.x * u[0];
+                        s0 = fmaf(a0.y, x[1], s0); s1 = fmaf(a1.y, x[5], s1); s2 = fmaf(a2.y, x[9], s2); s3f = fmaf(b4.y, u[1], s3f);
+                        s0 = fmaf(a0.z, x[2], s0); s1 = fmaf(a1.z, x[6], s1); s2 = fmaf(a2.z, x[10], s2); s3f = fmaf(b4.z, u[2], s3f);
+                        s0 = fmaf(a0.w, x[3], s0); s1 = fmaf(a1.w, x[7], s1); s2 = fmaf(a2.w, x[11], s2); s3f = fmaf(b4.w, u[3], s3f);
+                        xn[i] = (s0 + s1) + (s2 + s3f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) x[i] = xn[i];
+                    if (active) {
+                        uT[k] = make_float4(u[0], u[1], u[2], u[3]);
+                        float4* xr = xT + (long long)(k + 1) * 3;
+                        xr[0] = make_float4(x[0], x[1], x[2], x[3]); xr[1] = make_float4(x[4], x[5], x[6], x[7]); xr[2] = make_float4(x[8], x[9], x[10], x[11]);
+                        if (k == 0) *reinterpret_cast<float4*>(P.u0 + b * 4) = make_float4(u[0], u[1], u[2], u[3]);
+                    }
+                }
+            }
+        }
+        if (active) {
+            P.status[b] = 0;
+            if (P.iters) P.iters[b] = 0;
+        }
+    }
+}
+
+}  // namespace t1
+
+// eligibility on top of the 4-thread kernel's: Q time-invariant and symmetric handling (lower triangle is used)
+template <bool MPC, bool QDIAG>
+inline int32_t riccati_t1_launch_impl(const FastP& F, cudaStream_t stream) {
+    const size_t smem = (size_t)(QDIAG ? t1::NF4_DIAG : t1::NF4) * 32 * sizeof(float4);
+    ZB_CUDA(cudaFuncSetAttribute(t1::k_riccati_t1<MPC, QDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((F.Bsz + 31) / 32);
+    t1::k_riccati_t1<MPC, QDIAG><<<grid, 32, smem, stream>>>(F);
+    ZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <bool MPC>
+inline int32_t riccati_t1_launch(const FastP& F, cudaStream_t stream, bool cost_diagonal = false) {
+    return cost_diagonal ? riccati_t1_launch_impl<MPC, true>(F, stream) : riccati_t1_launch_impl<MPC, false>(F, stream);
+}
+
+}  // namespace zb

@@ -3,6 +3,7 @@
 #include "zb_common.cuh"
 #include "lqr_fast.cuh"
 #include "ilqr_fast.cuh"
+#include "lqr_t1.cuh"
 
 using namespace zb;
 
@@ -337,7 +338,19 @@ int32_t zb_lqr_dfh(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int
     DeviceGuard g(device);
     ZB_CUDA(g.err);
     LqrP P{Bsz, N, T, n, m, to_arr(A), to_arr(B), to_arr(Q), to_arr(R), L_out, V0_out};
-    if (lqr_fast_eligible(dtype, P)) return lqr_fast_launch(dtype, P, (cudaStream_t)stream);
+    if (lqr_fast_eligible(dtype, P)) {
+        if (P.Q.st == 0 || P.N == 1) {  // fully time-invariant: thread-per-problem kernel (lqr_t1.cuh)
+            FastP F{};
+            F.Bsz = P.Bsz; F.N = P.N; F.T = 1;
+            F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R;
+            F.Q.st = 0;
+            if (P.N == 1 && P.Q.st != 0) { F.T = P.T; F.Q.st = P.Q.st; }
+            F.gains = reinterpret_cast<float*>(P.L);
+            F.V0 = reinterpret_cast<float*>(P.V0);
+            if (F.T == 1) return riccati_t1_launch<false>(F, (cudaStream_t)stream);
+        }
+        return lqr_fast_launch(dtype, P, (cudaStream_t)stream);
+    }
     ZB_DISPATCH(dtype, k_lqr_generic, gen_grid(Bsz), GEN_THREADS, stream, P);
     return 0;
 }
@@ -569,13 +582,14 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
 
 size_t zb_mpc_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m) {
     size_t e = dtype == ZB_F64 ? 8 : 4;
-    return align256(e * Bsz * (size_t)admm_ws_elems(N, n, m)) + 256;  // >= the gains buffer of the unconstrained path
+    const size_t Bpad = ((size_t)Bsz + 31) / 32 * 32;  // the (12,4) kernel stores gains per 32-problem group
+    return align256(e * Bpad * (size_t)admm_ws_elems(N, n, m)) + 256;  // >= the gains buffer of the unconstrained path
 }
 
 int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t n, int32_t m,
                          const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, const zb_arr* Qf,
                          const zb_arr* x_lb, const zb_arr* x_ub, const zb_arr* u_lb, const zb_arr* u_ub,
-                         int32_t bounded, const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj,
+                         int32_t flags, const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj,
                          void* uTraj, int8_t* status_out, int32_t* iters_out, void* workspace,
                          size_t workspace_bytes) {
     int32_t rc = check_dims(dtype, Bsz, n, m);
@@ -588,7 +602,7 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
     ZB_ARG(workspace && workspace_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
     DeviceGuard g(device);
     ZB_CUDA(g.err);
-    if (bounded) {
+    if (flags & ZB_MPC_BOUNDED) {
         ZB_ARG(x_lb && x_ub && u_lb && u_ub && x_lb->ptr && x_ub->ptr && u_lb->ptr && u_ub->ptr, "bounds are NULL");
         AdmmP P{};
         P.Bsz = Bsz; P.N = N; P.n = n; P.m = m;
@@ -621,7 +635,7 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
         F.uTraj = reinterpret_cast<float*>(uTraj);
         F.status = status_out;
         F.iters = iters_out;
-        return riccati_fast_launch<true>(F, (cudaStream_t)stream);
+        return riccati_t1_launch<true>(F, (cudaStream_t)stream, (flags & ZB_COST_DIAGONAL) != 0);
     }
     ZB_DISPATCH(dtype, k_mpc_riccati, gen_grid(Bsz), GEN_THREADS, stream, P);
     return 0;

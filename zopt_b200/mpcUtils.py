@@ -31,6 +31,20 @@ def _isinf_all(t, sign):
     return bool(torch.all(torch.isinf(t) & ((t > 0) if sign > 0 else (t < 0))))
 
 
+_DIAG_CACHE = {}
+
+
+def _is_diagonal(t):
+    key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version)
+    hit = _DIAG_CACHE.get(key)
+    if hit is None:
+        if len(_DIAG_CACHE) > 256:
+            _DIAG_CACHE.clear()
+        hit = bool((t - torch.diag_embed(torch.diagonal(t, dim1=-2, dim2=-1))).abs().max() == 0)
+        _DIAG_CACHE[key] = hit
+    return hit
+
+
 class lqrMpc():
 
     def __init__(self, A, B, Q, R, N, x_lb, x_ub, u_lb, u_ub, Qf=None):
@@ -60,6 +74,10 @@ class lqrMpc():
         self.views = [View(t, nd, False, t.ndim == nd + 1) for t, nd in zip(self.ops, core)]
         self.bounded = not (_isinf_all(x_lb, -1) and _isinf_all(x_ub, +1) and _isinf_all(u_lb, -1) and
                             _isinf_all(u_ub, +1))
+        # diagonal costs: lets the fp32 (12,4) kernel keep less cost data on chip.  The check needs a device->host
+        # read, so it is cached per tensor (storage, shape, in-place version): re-building the problem every MPC step
+        # around the same Q, R, Qf (demos/lqrMpc.py:31 builds once; a re-linearising loop rebuilds) costs nothing.
+        self.cost_diagonal = all(_is_diagonal(t) for t in (self.ops[2], self.ops[3], self.ops[4]))
         self.iters = None
 
     def solve(self, x0, **kwargs):
@@ -94,7 +112,7 @@ class lqrMpc():
                           float(kwargs.get("eps_abs", 1e-3)), float(kwargs.get("eps_rel", 1e-3)),
                           float(kwargs.get("eps_prim_inf", 1e-4)))
         check(lib.zb_mpc_lqr_solve(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, n, m, *[v.ref() for v in self.views],
-                                   int(self.bounded), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
+                                   (1 if self.bounded else 0) | (2 if self.cost_diagonal else 0), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
                                    ptr(iters), ptr(ws), wsb))
         self.iters = iters
         if not batched:
