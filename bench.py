@@ -180,13 +180,14 @@ def run_ours(args):
     Q = torch.diag_embed(torch.as_tensor(d["qdiag"], dtype=f32, device=dev))
     R = torch.diag_embed(torch.as_tensor(d["rdiag"], dtype=f32, device=dev))
     Qf = 10 * Q
-    inf_n, inf_m = torch.full((NX,), float("inf")), torch.full((NU,), float("inf"))
+    inf_n, inf_m = torch.full((NX,), float("inf"), device=dev), torch.full((NU,), float("inf"), device=dev)
+    ninf_n, ninf_m = -inf_n, -inf_m
     ac = Quadcopter()
     N, dt = d["N"], d["dt"]
 
     def step(x0_dev):
         A, B = ac.linearizeInertial(xbar, ubar, dt)
-        prob = lqrMpc(A, B, Q, R, N, -inf_n, inf_n, -inf_m, inf_m, Qf=Qf)
+        prob = lqrMpc(A, B, Q, R, N, ninf_n, inf_n, ninf_m, inf_m, Qf=Qf)
         return prob.solve(x0_dev)
 
     def barrier():
@@ -214,7 +215,7 @@ def run_ours(args):
 
     # --- dominant kernel alone (the Riccati sweep + rollout launch), events on the launching stream
     A, B = ac.linearizeInertial(xbar, ubar, dt)
-    prob = lqrMpc(A, B, Q, R, N, -inf_n, inf_n, -inf_m, inf_m, Qf=Qf)
+    prob = lqrMpc(A, B, Q, R, N, ninf_n, inf_n, ninf_m, inf_m, Qf=Qf)
     kms = []
     for _ in range(max(3, min(args.steps, 20))):
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -226,24 +227,93 @@ def run_ours(args):
     k_ms = float(np.mean(kms))
 
     # --- end to end through the public API with host buffers -----------------------------------
-    host_out = None
+    # every step: x0 pinned host -> device, linearise + solve, then the call's whole return value (u, plan, status)
+    # device -> pinned host.  The D2H of step i runs on a copy stream while step i+1 computes (two host buffer sets).
+    def host_bufs():
+        return [torch.empty((Bsz, NU), dtype=f32).pin_memory(), torch.empty((Bsz, N + 1, NX), dtype=f32).pin_memory(),
+                torch.empty((Bsz, N, NU), dtype=f32).pin_memory(), torch.empty((Bsz,), dtype=torch.int8).pin_memory()]
+
+    hb = [host_bufs(), host_bufs()]
+    copy_stream = torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+
+    def e2e_loop(steps, full):
+        for i in range(steps):
+            x0d = x0_host.to(dev, non_blocking=True)
+            u, traj, status = step(x0d)
+            outs = (u, traj.xTraj, traj.uTraj, status) if full else (u, status)
+            dst = hb[i % 2] if full else [hb[i % 2][0], hb[i % 2][3]]
+            ready = torch.cuda.Event()
+            ready.record(main)
+            copy_stream.wait_event(ready)
+            with torch.cuda.stream(copy_stream):
+                for h, t in zip(dst, outs):
+                    t.record_stream(copy_stream)
+                    h.copy_(t, non_blocking=True)
+        copy_stream.synchronize()
+
+    e2e_loop(2, True)
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
-        x0d = x0_host.to(dev, non_blocking=True)
-        u, traj, status = step(x0d)
-        host_out = (u.cpu(), traj.xTraj.cpu(), traj.uTraj.cpu(), status.cpu())
+    e2e_loop(args.steps, True)
+    main.wait_stream(copy_stream)
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)
     h2d = x0_host.numel() * 4
-    d2h = sum(t.numel() * t.element_size() for t in host_out)
+    d2h = sum(t.numel() * t.element_size() for t in hb[0])
+    t2, t3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t2.record()
+    e2e_loop(args.steps, False)
+    main.wait_stream(copy_stream)
+    t3.record()
+    barrier()
+    e2e_u_ms = t2.elapsed_time(t3)
 
-    times = torch.tensor([ms, e2e_ms, k_ms], dtype=torch.float64, device=dev)
+    # --- secondary workloads of BASELINE.json (reported under "extra"; the headline stays cfg 2) -------------------
+    # cfg 3: closed-loop LQR-MPC, N=50 horizon x 200 sim steps, 16,384 problems in total SHARDED over the ranks (strong)
+    # cfg 4: iLQR, N=200, 10 forced iterations with the 16-way line search, 16,384 problems in total, fp64
+    from zopt_b200 import configs, ilqrUtils
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    from zopt_b200.mpcUtils import quadcopterClosedLoopMpc
+    from zopt_b200.sharding import shard_range
+    extra_ms = [0.0, 0.0]
+    if not args.no_extras:
+        lo, hi = shard_range(16384, rank, world)
+        d3 = configs.cfg3(Bsz=16384)
+        x3 = torch.as_tensor(d3["xbar"][lo:hi], dtype=f32, device=dev)
+        x3[:, 9:12] *= 0.2
+        Q3 = torch.diag_embed(torch.as_tensor(d3["qdiag"][lo:hi], dtype=f32, device=dev))
+        R3 = torch.diag_embed(torch.as_tensor(d3["rdiag"][lo:hi], dtype=f32, device=dev))
+        Qf3 = 10 * Q3
+        quadcopterClosedLoopMpc(x3, Q3, R3, 50, 200, dt=0.1, Qf=Qf3)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            quadcopterClosedLoopMpc(x3, Q3, R3, 50, 200, dt=0.1, Qf=Qf3)
+        c1.record()
+        barrier()
+        extra_ms[0] = c0.elapsed_time(c1) / 3
+        d4 = configs.cfg4(Bsz=16384)
+        x4 = torch.as_tensor(d4["x0"][lo:hi], dtype=torch.float64, device=dev)
+        uG = torch.as_tensor(d4["uGuess"], dtype=torch.float64, device=dev)
+        margs = (QuadcopterEuler(d4["dt"]), QuadraticCost(d4["Q"], d4["R"]), QuadraticTerminalCost(d4["Qf"]))
+        ilqrUtils.iterativeLqr(*margs, x4, uG, maxIter=10, tol=-1.0)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(2):
+            ilqrUtils.iterativeLqr(*margs, x4, uG, maxIter=10, tol=-1.0)
+        c1.record()
+        barrier()
+        extra_ms[1] = c0.elapsed_time(c1) / 2
+
+    times = torch.tensor([ms, e2e_ms, k_ms, e2e_u_ms] + extra_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, k_ms = (float(v) for v in times.cpu())
+    ms, e2e_ms, k_ms, e2e_u_ms, cl_ms, il_ms = (float(v) for v in times.cpu())
 
     if rank == 0:
         total = Bsz * world
@@ -273,8 +343,19 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(Bsz), "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "returns": "u (Bsz,4), plan xTraj (Bsz,51,12) + uTraj (Bsz,50,4), status -- PCIe-bound",
+                    "control_only": {"value": total * args.steps / (e2e_u_ms * 1e-3), "unit": UNIT,
+                                     "d2h_bytes_per_step": Bsz * (NU * 4 + 1), "returns": "u and status only"}},
             "gpu_launches": 2 * args.steps, "roofline": roof,
+            "extra": None if args.no_extras else {
+                "cfg3_closed_loop_mpc": {"value": 16384 * 200 / (cl_ms * 1e-3), "unit": "MPC solves/s", "ms": cl_ms,
+                                         "workload": "16,384 problems total (sharded over ranks), 200 sim steps, horizon 50, fp32, "
+                                                     "re-linearised every step, bounds inactive, one fused kernel",
+                                         "scaling": "strong"},
+                "cfg4_ilqr": {"value": 16384 * 10 / (il_ms * 1e-3), "unit": "problem-iterations/s", "ms": il_ms,
+                              "workload": "16,384 problems total (sharded over ranks), N=200, 10 iterations, 16-way line search, fp64",
+                              "scaling": "strong", "algorithmic_flop_per_problem_iteration": 4.66e6}},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{args.cpu_sample} problems of the same workload, 1 step ({cpu_sec:.1f} s), torch-CPU fp64 oracle port"},
         }
@@ -291,6 +372,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
     ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary cfg3/cfg4 measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

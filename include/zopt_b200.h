@@ -175,6 +175,15 @@ ZB_API int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int
                          void* uTraj, int8_t* status_out, int32_t* iters_out, void* workspace,
                          size_t workspace_bytes);
 
+/* ---- closed-loop LQR-MPC of the quadcopter (BASELINE cfg 3; the receding-horizon loop of demos/lqrMpc.py:42-47 with a
+ * nonlinear plant), fp32, bounds inactive.  Per simulation step t: A_t = I + dt dF/dx(x_t,u_trim), B = dt dF/du, a full
+ * Riccati sweep of horizon N from Qf (zopt/mpcUtils.py:47-59 with infinite bounds), u_t = first move of the plan,
+ * x_{t+1} = x_t + dt F(x_t, u_trim + u_t) (zopt/quadcopter.py:116-144).  One fused kernel; only the trajectory is written:
+ * xSim_out (Bsz,Tsim+1,12), uSim_out (Bsz,Tsim,4) (deviation from u_trim).  Q,R,Qf: (12,12),(4,4),(12,12) blocks (symmetric). */
+ZB_API int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t Tsim, double dt,
+                                const double* u_trim /* host, 4 */, const zb_arr* Q, const zb_arr* R, const zb_arr* Qf,
+                                int32_t flags /* ZB_COST_DIAGONAL */, const void* x0, void* xSim_out, void* uSim_out);
+
 /* ---- roofline denominators: dependent-FMA throughput probe; returns achieved FLOP/s ------------ */
 ZB_API int32_t zb_peak_fma(int32_t dtype, int32_t device, double* flops_per_s_out, double* sm_clock_mhz_out);
 

@@ -561,3 +561,57 @@ def test_fast_paths_fp32_time_invariant(dense_cost):
         xr, ur = ompc.riccati_plan(A[b], B[b], Q[b], R[b], N, d["xbar"][b], Qf=10 * Q[b])
         assert relerr(traj.uTraj[b], ur) < 2e-5 and relerr(traj.xTraj[b], xr) < 2e-5
     assert (status == 0).all() and relerr(u, traj.uTraj[:, 0]) == 0
+
+
+@pytest.mark.parametrize("dense_cost", [False, True])
+def test_closed_loop_mpc_fused_vs_composed(dense_cost):
+    """BASELINE cfg 3 path: the fused fp32 closed-loop kernel against the same loop composed step by step in fp64 from
+    the individually verified entry points (linearizeInertial -> lqrMpc.solve -> inertialDynamics), and against the
+    oracle (autodiff linearisation + Riccati plan + oracle plant) for one problem."""
+    from oracle import mpc as ompc
+    from zopt_b200.mpcUtils import lqrMpc, quadcopterClosedLoopMpc
+    from zopt_b200.quadcopter import Quadcopter
+    Bsz, N, Tsim, dt = 40, 20, 25, 0.1
+    d = configs.cfg3(Bsz=Bsz)
+    Q, R = configs.diag_embed(d["qdiag"]), configs.diag_embed(d["rdiag"])
+    if dense_cost:
+        rng = np.random.default_rng(8)
+        Mq, Mr = rng.normal(size=(Bsz, 12, 12)) * 0.2, rng.normal(size=(Bsz, 4, 4)) * 0.2
+        Q, R = Q + Mq @ np.swapaxes(Mq, 1, 2), R + Mr @ np.swapaxes(Mr, 1, 2)
+    x0 = d["xbar"].copy()
+    x0[:, 9:12] *= 0.2  # +-2 m offsets: the linearised controller keeps the nonlinear plant well inside |theta| < pi/2
+    traj = quadcopterClosedLoopMpc(cuda(x0, torch.float32), cuda(Q, torch.float32), cuda(R, torch.float32), N, Tsim, dt=dt,
+                                   Qf=cuda(10 * Q, torch.float32))
+    assert traj.xTraj.shape == (Bsz, Tsim + 1, 12) and traj.uTraj.shape == (Bsz, Tsim, 4)
+    # composed fp64 loop through the public API
+    ac = Quadcopter()
+    inf12, inf4 = np.full(12, np.inf), np.full(4, np.inf)
+    x = cuda(x0)
+    ut = cuda(np.tile(configs.U_TRIM, (Bsz, 1)))
+    Qd, Rd = cuda(Q), cuda(R)
+    xs, us = [x], []
+    for t in range(Tsim):
+        A, B = ac.linearizeInertial(x, ut, dt)
+        u, _, status = lqrMpc(A, B, Qd, Rd, N, -inf12, inf12, -inf4, inf4, Qf=10 * Qd).solve(x)
+        x = x + dt * ac.inertialDynamics(x, ut + u)
+        xs.append(x)
+        us.append(u)
+    xref, uref = torch.stack(xs, 1), torch.stack(us, 1)
+    finite = torch.isfinite(xref).all(dim=2).all(dim=1).cpu().numpy()
+    assert finite.sum() >= Bsz - 2, f"{Bsz - finite.sum()} reference closed loops left the model's domain"
+    # a loop that diverges (tan(theta) blows up) must do so in both; NaN/inf is data, not an error
+    assert not torch.isfinite(traj.xTraj[torch.as_tensor(~finite)]).all() or finite.all()
+    fi = np.nonzero(finite)[0]
+    assert per_problem_relerr(traj.xTraj[fi], xref.cpu().numpy()[fi]).max() < 2e-4
+    assert per_problem_relerr(traj.uTraj[fi], uref.cpu().numpy()[fi]).max() < 2e-4
+    # oracle for problem 0
+    oac = OQuadcopter()
+    f = oac.eulerStep(dt)
+    xo = torch.as_tensor(x0[0])
+    uto = torch.as_tensor(configs.U_TRIM)
+    for t in range(Tsim):
+        Ao, Bo = torch.func.jacrev(f, argnums=(0, 1))(xo, uto)
+        _, up = ompc.riccati_plan(Ao.numpy(), Bo.numpy(), Q[0], R[0], N, xo.numpy(), Qf=10 * Q[0])
+        assert relerr(uref[0, t], up[0]) < 1e-9
+        xo = f(xo, uto + torch.as_tensor(up[0]))
+    assert relerr(xref[0, -1], xo) < 1e-9

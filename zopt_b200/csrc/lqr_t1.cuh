@@ -50,6 +50,139 @@ __device__ __forceinline__ void load_sym_lower(const float* g, float* v) {
         }
 }
 
+// One backward Riccati step for the problem owned by this thread: v (lower triangle of V) is updated in place and the
+// gain L = (R + B'VB)^-1 B'VA is returned in registers.  S = this lane's column of the shared-memory slab.
+template <bool QDIAG>
+__device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&L)[4][12]) {
+    // ---- 1. [W | VB] = V [A | B] in four 12x4 panels.  ROLLED loop: one ~600-instruction body re-used four
+    //         times keeps the step's code inside the instruction cache (the fully unrolled first version
+    //         stalled 0.8 cycle/instruction on instruction fetch with one warp per scheduler).
+    float G[10];
+    float4 xfirst = S[(X4 + 0) * 32];  // row 0 of the next panel, fetched before the previous panel's epilogue
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+        float acc[12][4];
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 12; ++kk) {
+            const float4 x4 = (kk == 0) ? xfirst : S[(X4 + kk * 4 + p) * 32];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const float vik = v[tri(i, kk)];
+                acc[i][0] = fmaf(vik, x4.x, acc[i][0]);
+                acc[i][1] = fmaf(vik, x4.y, acc[i][1]);
+                acc[i][2] = fmaf(vik, x4.z, acc[i][2]);
+                acc[i][3] = fmaf(vik, x4.w, acc[i][3]);
+            }
+        }
+        xfirst = S[(X4 + ((p < 3) ? p + 1 : 0)) * 32];
+        if (p < 3) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) S[(W4 + i * 3 + p) * 32] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        } else {  // acc = V B: G = R + B^T (V B), lower triangle
+            if (QDIAG) {
+                const float4 rd = S[(Q4 + 3) * 32];
+                G[0] = rd.x; G[1] = 0.f; G[2] = rd.y; G[3] = 0.f; G[4] = 0.f; G[5] = rd.z; G[6] = 0.f; G[7] = 0.f; G[8] = 0.f; G[9] = rd.w;
+            } else {
+                const float4 r0 = S[(R4 + 0) * 32], r1 = S[(R4 + 1) * 32], r2 = S[(R4 + 2) * 32];
+                G[0] = r0.x; G[1] = r0.y; G[2] = r0.z; G[3] = r0.w; G[4] = r1.x;
+                G[5] = r1.y; G[6] = r1.z; G[7] = r1.w; G[8] = r2.x; G[9] = r2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const float4 b4 = S[(X4 + i * 4 + 3) * 32];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c <= a; ++c) G[tri(a, c)] = fmaf(ZB_F4(b4, a), acc[i][c], G[tri(a, c)]);
+            }
+        }
+    }
+    // ---- 2. Cholesky G = C C^T (G already holds G0 + R) ------------------------------------------------
+    const float d0 = rsqrtf(G[0]);
+    const float c10 = G[1] * d0, c20 = G[3] * d0, c30 = G[6] * d0;
+    const float d1 = rsqrtf(fmaf(-c10, c10, G[2]));
+    const float c21 = fmaf(-c20, c10, G[4]) * d1, c31 = fmaf(-c30, c10, G[7]) * d1;
+    const float d2 = rsqrtf(fmaf(-c21, c21, fmaf(-c20, c20, G[5])));
+    const float c32 = fmaf(-c31, c21, fmaf(-c30, c20, G[8])) * d2;
+    const float d3 = rsqrtf(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
+    // ---- 3a. V' (lower) = Q + A^T W and M = B^T W in one pass over the rows of A, W, B ------------------
+    // (independent of the Cholesky chain above, so the scheduler can hide its latency behind these FMAs)
+    if (QDIAG) {
+        const float4 q0 = S[(Q4 + 0) * 32], q1 = S[(Q4 + 1) * 32], q2 = S[(Q4 + 2) * 32];
+        const float qd[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) v[tri(i, j)] = (i == j) ? qd[i] : 0.f;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int c = 0; c <= i / 4; ++c) {
+                const float4 q = S[(Q4 + qoff(i) + c) * 32];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (4 * c + e <= i) v[tri(i, 4 * c + e)] = ZB_F4(q, e);
+            }
+    }
+    float M[4][12];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 12; ++j) M[a][j] = 0.f;
+    {
+        float4 ra[3], rw[3], rb;  // rows kk of A, W, B; next rows are fetched while the current ones are consumed
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + c) * 32]; rw[c] = S[(W4 + c) * 32]; }
+        rb = S[(X4 + 3) * 32];
+#pragma unroll 1
+        for (int kk = 0; kk < 12; ++kk) {
+            const float a[12] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w, ra[1].x, ra[1].y, ra[1].z, ra[1].w, ra[2].x, ra[2].y, ra[2].z, ra[2].w};
+            const float w[12] = {rw[0].x, rw[0].y, rw[0].z, rw[0].w, rw[1].x, rw[1].y, rw[1].z, rw[1].w, rw[2].x, rw[2].y, rw[2].z, rw[2].w};
+            const float4 b4 = rb;
+            const int kn = (kk < 11) ? kk + 1 : 11;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + kn * 4 + c) * 32]; rw[c] = S[(W4 + kn * 3 + c) * 32]; }
+            rb = S[(X4 + kn * 4 + 3) * 32];
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) v[tri(i, j)] = fmaf(a[i], w[j], v[tri(i, j)]);
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                M[0][j] = fmaf(b4.x, w[j], M[0][j]);
+                M[1][j] = fmaf(b4.y, w[j], M[1][j]);
+                M[2][j] = fmaf(b4.z, w[j], M[2][j]);
+                M[3][j] = fmaf(b4.w, w[j], M[3][j]);
+            }
+        }
+    }
+    // ---- 2b. L = G^-1 M (12 right-hand sides) ------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        const float y0 = M[0][j] * d0;
+        const float y1 = fmaf(-c10, y0, M[1][j]) * d1;
+        const float y2 = fmaf(-c21, y1, fmaf(-c20, y0, M[2][j])) * d2;
+        const float y3 = fmaf(-c32, y2, fmaf(-c31, y1, fmaf(-c30, y0, M[3][j]))) * d3;
+        const float x3 = y3 * d3;
+        const float x2 = fmaf(-c32, x3, y2) * d2;
+        const float x1 = fmaf(-c31, x3, fmaf(-c21, x2, y1)) * d1;
+        const float x0 = fmaf(-c30, x3, fmaf(-c20, x2, fmaf(-c10, x1, y0))) * d0;
+        L[0][j] = x0; L[1][j] = x1; L[2][j] = x2; L[3][j] = x3;
+    }
+    // ---- 3b. V' -= M^T L (lower) --------------------------------------------------------------------
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) v[tri(i, j)] = fmaf(-M[a][i], L[a][j], v[tri(i, j)]);
+}
+
 // QDIAG: the caller asserts Q, R, Qf diagonal (ZB_COST_DIAGONAL): 4 float4 of cost data instead of 27, so FIVE
 // CTAs fit an SM (88 float4 = 1,408 B per problem) and 65,536 problems take 3 rounds of CTAs instead of 4.
 template <bool MPC, bool QDIAG>
@@ -108,134 +241,8 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
     float* gpub = P.gains + (long long)blockIdx.x * 32 * (long long)P.N * 48;
 
     for (int k = P.N - 1; k >= 0; --k) {
-        // ---- 1. [W | VB] = V [A | B] in four 12x4 panels.  ROLLED loop: one ~600-instruction body re-used four
-        //         times keeps the step's code inside the instruction cache (the fully unrolled first version
-        //         stalled 0.8 cycle/instruction on instruction fetch with one warp per scheduler).
-        float G[10];
-        float4 xfirst = S[(X4 + 0) * 32];  // row 0 of the next panel, fetched before the previous panel's epilogue
-#pragma unroll 1
-        for (int p = 0; p < 4; ++p) {
-            float acc[12][4];
-#pragma unroll
-            for (int i = 0; i < 12; ++i)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
-#pragma unroll
-            for (int kk = 0; kk < 12; ++kk) {
-                const float4 x4 = (kk == 0) ? xfirst : S[(X4 + kk * 4 + p) * 32];
-#pragma unroll
-                for (int i = 0; i < 12; ++i) {
-                    const float vik = v[tri(i, kk)];
-                    acc[i][0] = fmaf(vik, x4.x, acc[i][0]);
-                    acc[i][1] = fmaf(vik, x4.y, acc[i][1]);
-                    acc[i][2] = fmaf(vik, x4.z, acc[i][2]);
-                    acc[i][3] = fmaf(vik, x4.w, acc[i][3]);
-                }
-            }
-            xfirst = S[(X4 + ((p < 3) ? p + 1 : 0)) * 32];
-            if (p < 3) {
-#pragma unroll
-                for (int i = 0; i < 12; ++i) S[(W4 + i * 3 + p) * 32] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            } else {  // acc = V B: G = R + B^T (V B), lower triangle
-                if (QDIAG) {
-                    const float4 rd = S[(Q4 + 3) * 32];
-                    G[0] = rd.x; G[1] = 0.f; G[2] = rd.y; G[3] = 0.f; G[4] = 0.f; G[5] = rd.z; G[6] = 0.f; G[7] = 0.f; G[8] = 0.f; G[9] = rd.w;
-                } else {
-                    const float4 r0 = S[(R4 + 0) * 32], r1 = S[(R4 + 1) * 32], r2 = S[(R4 + 2) * 32];
-                    G[0] = r0.x; G[1] = r0.y; G[2] = r0.z; G[3] = r0.w; G[4] = r1.x;
-                    G[5] = r1.y; G[6] = r1.z; G[7] = r1.w; G[8] = r2.x; G[9] = r2.y;
-                }
-#pragma unroll
-                for (int i = 0; i < 12; ++i) {
-                    const float4 b4 = S[(X4 + i * 4 + 3) * 32];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int c = 0; c <= a; ++c) G[tri(a, c)] = fmaf(ZB_F4(b4, a), acc[i][c], G[tri(a, c)]);
-                }
-            }
-        }
-        // ---- 2. Cholesky G = C C^T (G already holds G0 + R) ------------------------------------------------
-        const float d0 = rsqrtf(G[0]);
-        const float c10 = G[1] * d0, c20 = G[3] * d0, c30 = G[6] * d0;
-        const float d1 = rsqrtf(fmaf(-c10, c10, G[2]));
-        const float c21 = fmaf(-c20, c10, G[4]) * d1, c31 = fmaf(-c30, c10, G[7]) * d1;
-        const float d2 = rsqrtf(fmaf(-c21, c21, fmaf(-c20, c20, G[5])));
-        const float c32 = fmaf(-c31, c21, fmaf(-c30, c20, G[8])) * d2;
-        const float d3 = rsqrtf(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
-        // ---- 3a. V' (lower) = Q + A^T W and M = B^T W in one pass over the rows of A, W, B ------------------
-        // (independent of the Cholesky chain above, so the scheduler can hide its latency behind these FMAs)
-        if (QDIAG) {
-            const float4 q0 = S[(Q4 + 0) * 32], q1 = S[(Q4 + 1) * 32], q2 = S[(Q4 + 2) * 32];
-            const float qd[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-#pragma unroll
-            for (int i = 0; i < 12; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) v[tri(i, j)] = (i == j) ? qd[i] : 0.f;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 12; ++i)
-#pragma unroll
-                for (int c = 0; c <= i / 4; ++c) {
-                    const float4 q = S[(Q4 + qoff(i) + c) * 32];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (4 * c + e <= i) v[tri(i, 4 * c + e)] = ZB_F4(q, e);
-                }
-        }
-        float M[4][12];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int j = 0; j < 12; ++j) M[a][j] = 0.f;
-        {
-            float4 ra[3], rw[3], rb;  // rows kk of A, W, B; next rows are fetched while the current ones are consumed
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + c) * 32]; rw[c] = S[(W4 + c) * 32]; }
-            rb = S[(X4 + 3) * 32];
-#pragma unroll 1
-            for (int kk = 0; kk < 12; ++kk) {
-                const float a[12] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w, ra[1].x, ra[1].y, ra[1].z, ra[1].w, ra[2].x, ra[2].y, ra[2].z, ra[2].w};
-                const float w[12] = {rw[0].x, rw[0].y, rw[0].z, rw[0].w, rw[1].x, rw[1].y, rw[1].z, rw[1].w, rw[2].x, rw[2].y, rw[2].z, rw[2].w};
-                const float4 b4 = rb;
-                const int kn = (kk < 11) ? kk + 1 : 11;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + kn * 4 + c) * 32]; rw[c] = S[(W4 + kn * 3 + c) * 32]; }
-                rb = S[(X4 + kn * 4 + 3) * 32];
-#pragma unroll
-                for (int i = 0; i < 12; ++i)
-#pragma unroll
-                    for (int j = 0; j <= i; ++j) v[tri(i, j)] = fmaf(a[i], w[j], v[tri(i, j)]);
-#pragma unroll
-                for (int j = 0; j < 12; ++j) {
-                    M[0][j] = fmaf(b4.x, w[j], M[0][j]);
-                    M[1][j] = fmaf(b4.y, w[j], M[1][j]);
-                    M[2][j] = fmaf(b4.z, w[j], M[2][j]);
-                    M[3][j] = fmaf(b4.w, w[j], M[3][j]);
-                }
-            }
-        }
-        // ---- 2b. L = G^-1 M (12 right-hand sides) ------------------------------------------------------
         float L[4][12];
-#pragma unroll
-        for (int j = 0; j < 12; ++j) {
-            const float y0 = M[0][j] * d0;
-            const float y1 = fmaf(-c10, y0, M[1][j]) * d1;
-            const float y2 = fmaf(-c21, y1, fmaf(-c20, y0, M[2][j])) * d2;
-            const float y3 = fmaf(-c32, y2, fmaf(-c31, y1, fmaf(-c30, y0, M[3][j]))) * d3;
-            const float x3 = y3 * d3;
-            const float x2 = fmaf(-c32, x3, y2) * d2;
-            const float x1 = fmaf(-c31, x3, fmaf(-c21, x2, y1)) * d1;
-            const float x0 = fmaf(-c30, x3, fmaf(-c20, x2, fmaf(-c10, x1, y0))) * d0;
-            L[0][j] = x0; L[1][j] = x1; L[2][j] = x2; L[3][j] = x3;
-        }
-        // ---- 3b. V' -= M^T L (lower) --------------------------------------------------------------------
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int i = 0; i < 12; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) v[tri(i, j)] = fmaf(-M[a][i], L[a][j], v[tri(i, j)]);
+        riccati_step<QDIAG>(S, v, L);
         // ---- 4. gains out ------------------------------------------------------------------------------
         if (MPC) {
             float4* g = gws + (long long)k * 12 * 32;
@@ -344,6 +351,129 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------
+// Closed-loop LQR-MPC for the quadcopter (BASELINE cfg 3; the loop of demos/lqrMpc.py:42-47 with a nonlinear plant):
+// for every simulation step t:  A_t = I + dt dF/dx(x_t, u_trim), B = dt dF/du  (linearised IN the kernel),
+// full Riccati sweep of horizon N from Qf (nothing cached between steps), u_t = -L_0 x_t  (the first move of the
+// unconstrained lqrMpc plan, mpcUtils.py:47-59 with infinite bounds), plant step x_{t+1} = x_t + dt F(x_t, u_trim + u_t).
+// Only the simulated trajectory leaves the chip: no gains, no plans, no A/B in HBM.
+struct ClosedLoopP {
+    long long Bsz;
+    int N, Tsim;
+    float dt;
+    float utrim[4];
+    Arr Q, R, Qf;
+    const float* x0;  // (Bsz,12)
+    float* xSim;      // (Bsz,Tsim+1,12)
+    float* uSim;      // (Bsz,Tsim,4)  applied deviation u_t (the control sent to the plant is u_trim + u_t)
+};
+
+template <bool QDIAG>
+__global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_mpc_closed_loop_quad(ClosedLoopP P) {
+    extern __shared__ float4 sm[];
+    const int lane = threadIdx.x;
+    const long long b_raw = (long long)blockIdx.x * 32 + lane;
+    const bool active = b_raw < P.Bsz;
+    const long long b = active ? b_raw : P.Bsz - 1;
+    float4* S = sm + lane;
+    const float dt = P.dt;
+    // constant operands: B rows (chunk 3 of every X row), cost
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+        S[(X4 + k * 4 + 3) * 32] = make_float4(k == 2 ? -dt : 0.f, k == 3 ? dt : 0.f, k == 4 ? dt : 0.f, k == 5 ? dt : 0.f);
+    if (QDIAG) {
+        const float* q = P.Q.at<float>(b);
+        const float* r = P.R.at<float>(b);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            S[(Q4 + c) * 32] = make_float4(__ldg(q + (4 * c) * 13), __ldg(q + (4 * c + 1) * 13), __ldg(q + (4 * c + 2) * 13), __ldg(q + (4 * c + 3) * 13));
+        S[(Q4 + 3) * 32] = make_float4(__ldg(r), __ldg(r + 5), __ldg(r + 10), __ldg(r + 15));
+    } else {
+        const float4* gQ = reinterpret_cast<const float4*>(P.Q.at<float>(b));
+        const float4* gR = reinterpret_cast<const float4*>(P.R.at<float>(b));
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+#pragma unroll
+            for (int c = 0; c <= k / 4; ++c) S[(Q4 + qoff(k) + c) * 32] = __ldg(gQ + k * 3 + c);
+        const float4 r0 = __ldg(gR), r1 = __ldg(gR + 1), r2 = __ldg(gR + 2), r3 = __ldg(gR + 3);
+        S[(R4 + 0) * 32] = make_float4(r0.x, r1.x, r1.y, r2.x);
+        S[(R4 + 1) * 32] = make_float4(r2.y, r2.z, r3.x, r3.y);
+        S[(R4 + 2) * 32] = make_float4(r3.z, r3.w, 0.f, 0.f);
+    }
+    float x[12];
+    {
+        const float4* gx = reinterpret_cast<const float4*>(P.x0 + b * 12);
+        const float4 x0 = __ldg(gx), x1 = __ldg(gx + 1), x2 = __ldg(gx + 2);
+        x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+        x[8] = x2.x; x[9] = x2.y; x[10] = x2.z; x[11] = x2.w;
+    }
+    float4* xS = reinterpret_cast<float4*>(P.xSim + b * (long long)(P.Tsim + 1) * 12);
+    float4* uS = reinterpret_cast<float4*>(P.uSim + b * (long long)P.Tsim * 4);
+    const float ut[4] = {P.utrim[0], P.utrim[1], P.utrim[2], P.utrim[3]};
+#pragma unroll 1
+    for (int t = 0; t < P.Tsim; ++t) {
+        if (active) {
+            xS[(long long)t * 3 + 0] = make_float4(x[0], x[1], x[2], x[3]);
+            xS[(long long)t * 3 + 1] = make_float4(x[4], x[5], x[6], x[7]);
+            xS[(long long)t * 3 + 2] = make_float4(x[8], x[9], x[10], x[11]);
+        }
+        // ---- linearise at (x_t, u_trim): A = I + dt * dF/dx  -> rows of X (chunks 0..2) ----
+        {
+            float J[144];
+            QuadTrig<float> tr = quad_trig(x);
+            quad_jac_x(tr, x, ut, J);
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    S[(X4 + i * 4 + c) * 32] = make_float4(fmaf(dt, J[i * 12 + 4 * c + 0], (i == 4 * c + 0) ? 1.f : 0.f),
+                                                          fmaf(dt, J[i * 12 + 4 * c + 1], (i == 4 * c + 1) ? 1.f : 0.f),
+                                                          fmaf(dt, J[i * 12 + 4 * c + 2], (i == 4 * c + 2) ? 1.f : 0.f),
+                                                          fmaf(dt, J[i * 12 + 4 * c + 3], (i == 4 * c + 3) ? 1.f : 0.f));
+        }
+        // ---- Riccati sweep from Qf; only the last gain (k = 0) is needed ----
+        float v[78];
+        {
+            const float* qf = P.Qf.at<float>(b);
+            if (QDIAG) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) v[tri(i, j)] = (i == j) ? __ldg(qf + i * 13) : 0.f;
+            } else {
+                load_sym_lower(qf, v);
+            }
+        }
+        float L[4][12];
+#pragma unroll 1
+        for (int k = P.N - 1; k >= 0; --k) riccati_step<QDIAG>(S, v, L);
+        // ---- u_t = -L_0 x_t ; plant: x <- x + dt F(x, u_trim + u_t) ----
+        float u[4], ua[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) s = fmaf(L[a][j], x[j], s);
+            u[a] = -s;
+            ua[a] = ut[a] + u[a];
+        }
+        if (active) uS[t] = make_float4(u[0], u[1], u[2], u[3]);
+        {
+            float xd[12];
+            QuadTrig<float> tr = quad_trig(x);
+            quad_xdot(tr, x, ua, xd);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) x[i] = fmaf(dt, xd[i], x[i]);
+        }
+    }
+    if (active) {
+        xS[(long long)P.Tsim * 3 + 0] = make_float4(x[0], x[1], x[2], x[3]);
+        xS[(long long)P.Tsim * 3 + 1] = make_float4(x[4], x[5], x[6], x[7]);
+        xS[(long long)P.Tsim * 3 + 2] = make_float4(x[8], x[9], x[10], x[11]);
+    }
+}
+
 }  // namespace t1
 
 // eligibility on top of the 4-thread kernel's: Q time-invariant and symmetric handling (lower triangle is used)
@@ -360,6 +490,22 @@ inline int32_t riccati_t1_launch_impl(const FastP& F, cudaStream_t stream) {
 template <bool MPC>
 inline int32_t riccati_t1_launch(const FastP& F, cudaStream_t stream, bool cost_diagonal = false) {
     return cost_diagonal ? riccati_t1_launch_impl<MPC, true>(F, stream) : riccati_t1_launch_impl<MPC, false>(F, stream);
+}
+
+
+inline int32_t mpc_closed_loop_launch(const t1::ClosedLoopP& P, cudaStream_t stream, bool cost_diagonal) {
+    const unsigned grid = (unsigned)((P.Bsz + 31) / 32);
+    if (cost_diagonal) {
+        const size_t smem = (size_t)t1::NF4_DIAG * 32 * sizeof(float4);
+        ZB_CUDA(cudaFuncSetAttribute(t1::k_mpc_closed_loop_quad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        t1::k_mpc_closed_loop_quad<true><<<grid, 32, smem, stream>>>(P);
+    } else {
+        const size_t smem = (size_t)t1::NF4 * 32 * sizeof(float4);
+        ZB_CUDA(cudaFuncSetAttribute(t1::k_mpc_closed_loop_quad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        t1::k_mpc_closed_loop_quad<false><<<grid, 32, smem, stream>>>(P);
+    }
+    ZB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace zb

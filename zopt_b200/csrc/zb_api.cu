@@ -1,5 +1,7 @@
 // C ABI entry points (include/zopt_b200.h) and the generic one-thread-per-problem kernels.
 // The (n,m)=(12,4) fast kernels live in lqr_fast.cuh / ilqr_fast.cuh and are dispatched from here.
+#include <type_traits>
+
 #include "zb_common.cuh"
 #include "lqr_fast.cuh"
 #include "ilqr_fast.cuh"
@@ -45,15 +47,42 @@ template <typename T>
 __global__ void k_quad_linearize(QuadP P) {
     long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (b >= P.Bsz) return;
-    T x[12], u[4], fx[144], fu[48], w[3] = {T(P.wind[0]), T(P.wind[1]), T(P.wind[2])};
+    T x[12], u[4], fx[144], w[3] = {T(P.wind[0]), T(P.wind[1]), T(P.wind[2])};
+#pragma unroll
     for (int i = 0; i < 12; ++i) x[i] = reinterpret_cast<const T*>(P.x)[b * 12 + i];
+#pragma unroll
     for (int i = 0; i < 4; ++i) u[i] = reinterpret_cast<const T*>(P.u)[b * 4 + i];
-    quad_lin<T>(x, u, w, P.has_wind != 0, T(P.dt), fx, fu);
-    T* A = reinterpret_cast<T*>(P.o1) + b * 144;
-    for (int i = 0; i < 144; ++i) A[i] = fx[i];
+    QuadTrig<T> tr = quad_trig(x);
+    if (P.has_wind) quad_jac_x_wind(tr, x, u, w, fx);
+    else quad_jac_x(tr, x, u, fx);
+    const T s = (P.dt != 0.0) ? T(P.dt) : T(1), one = (P.dt != 0.0) ? T(1) : T(0);
+    // 16-byte vector stores of the row-major blocks (A: 12x12, B: 12x4; both 16-byte aligned per problem)
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    constexpr int PER = 16 / sizeof(T);
+    V* A = reinterpret_cast<V*>(reinterpret_cast<T*>(P.o1) + b * 144);
+#pragma unroll
+    for (int q = 0; q < 144 / PER; ++q) {
+        T e[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int idx = q * PER + j;
+            e[j] = s * fx[idx] + ((idx / 12 == idx % 12) ? one : T(0));
+        }
+        if (sizeof(T) == 4) A[q] = *reinterpret_cast<V*>(e);
+        else A[q] = *reinterpret_cast<V*>(e);
+    }
     if (P.o2) {
-        T* B = reinterpret_cast<T*>(P.o2) + b * 48;
-        for (int i = 0; i < 48; ++i) B[i] = fu[i];
+        V* B = reinterpret_cast<V*>(reinterpret_cast<T*>(P.o2) + b * 48);
+#pragma unroll
+        for (int q = 0; q < 48 / PER; ++q) {
+            T e[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int idx = q * PER + j;  // f_u: [2,0] = -s, [3,1] = [4,2] = [5,3] = +s
+                e[j] = (idx == 8) ? -s : ((idx == 13 || idx == 18 || idx == 23) ? s : T(0));
+            }
+            B[q] = *reinterpret_cast<V*>(e);
+        }
     }
 }
 
@@ -639,6 +668,27 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
     }
     ZB_DISPATCH(dtype, k_mpc_riccati, gen_grid(Bsz), GEN_THREADS, stream, P);
     return 0;
+}
+
+int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t Tsim, double dt,
+                                const double* u_trim, const zb_arr* Q, const zb_arr* R, const zb_arr* Qf, int32_t flags,
+                                const void* x0, void* xSim_out, void* uSim_out) {
+    ZB_ARG(dtype == ZB_F32, "zb_mpc_closed_loop_quad: fp32 only (compose linearize + zb_mpc_lqr_solve + dynamics for fp64)");
+    ZB_ARG(Bsz >= 0 && N >= 1 && Tsim >= 0, "bad sizes");
+    if (Bsz == 0) return 0;
+    ZB_ARG(Q && R && Qf && Q->ptr && R->ptr && Qf->ptr && x0 && xSim_out && (uSim_out || Tsim == 0) && u_trim, "NULL operand");
+    ZB_ARG(aligned16(x0) && aligned16(xSim_out) && aligned16(uSim_out), "x0 / outputs must be 16-byte aligned");
+    ZB_ARG((flags & ZB_COST_DIAGONAL) || (arr_ok(to_arr(Q)) && arr_ok(to_arr(R)) && arr_ok(to_arr(Qf))), "cost blocks must be 16-byte aligned");
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    t1::ClosedLoopP P{};
+    P.Bsz = Bsz; P.N = N; P.Tsim = Tsim; P.dt = (float)dt;
+    for (int i = 0; i < 4; ++i) P.utrim[i] = (float)u_trim[i];
+    P.Q = to_arr(Q); P.R = to_arr(R); P.Qf = to_arr(Qf);
+    P.x0 = reinterpret_cast<const float*>(x0);
+    P.xSim = reinterpret_cast<float*>(xSim_out);
+    P.uSim = reinterpret_cast<float*>(uSim_out);
+    return mpc_closed_loop_launch(P, (cudaStream_t)stream, (flags & ZB_COST_DIAGONAL) != 0);
 }
 
 int32_t zb_peak_fma(int32_t dtype, int32_t device, double* flops_per_s_out, double* sm_clock_mhz_out) {

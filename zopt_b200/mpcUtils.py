@@ -16,6 +16,7 @@ Returns `(u, Trajectory(xTraj, uTraj), status)`; un-batched calls return cvxpy's
 batched calls an int8 tensor of codes (`STATUS[code]` gives the string).
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -26,8 +27,22 @@ from .pytrees import Trajectory
 STATUS = ("optimal", "optimal_inaccurate", "infeasible")
 
 
+_INF_CACHE = {}
+
+
 def _isinf_all(t, sign):
-    t = torch.as_tensor(np.asarray(t)) if not isinstance(t, torch.Tensor) else t
+    """every entry is +inf (sign > 0) / -inf; device tensors are cached by object identity (one sync per tensor)"""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t))
+    elif t.is_cuda:
+        ent = _INF_CACHE.get((id(t), sign))
+        if ent is not None and ent[0]() is t and ent[1] == t._version:
+            return ent[2]
+        if len(_INF_CACHE) > 256:
+            _INF_CACHE.clear()
+        res = bool(torch.all(torch.isinf(t) & ((t > 0) if sign > 0 else (t < 0))))
+        _INF_CACHE[(id(t), sign)] = (weakref.ref(t), t._version, res)
+        return res
     return bool(torch.all(torch.isinf(t) & ((t > 0) if sign > 0 else (t < 0))))
 
 
@@ -35,14 +50,16 @@ _DIAG_CACHE = {}
 
 
 def _is_diagonal(t):
-    key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version)
-    hit = _DIAG_CACHE.get(key)
-    if hit is None:
-        if len(_DIAG_CACHE) > 256:
-            _DIAG_CACHE.clear()
-        hit = bool((t - torch.diag_embed(torch.diagonal(t, dim1=-2, dim2=-1))).abs().max() == 0)
-        _DIAG_CACHE[key] = hit
-    return hit
+    """Exact diagonality of a batch of square matrices; cached by tensor OBJECT identity (weak reference) and in-place
+    version counter, never by address, so a recycled allocation can not produce a stale answer."""
+    ent = _DIAG_CACHE.get(id(t))
+    if ent is not None and ent[0]() is t and ent[1] == t._version:
+        return ent[2]
+    if len(_DIAG_CACHE) > 256:
+        _DIAG_CACHE.clear()
+    res = bool((t - torch.diag_embed(torch.diagonal(t, dim1=-2, dim2=-1))).abs().max() == 0)
+    _DIAG_CACHE[id(t)] = (weakref.ref(t), t._version, res)
+    return res
 
 
 class lqrMpc():
@@ -122,3 +139,34 @@ class lqrMpc():
     @staticmethod
     def status_str(status, i=0):
         return STATUS[int(status[i])]
+
+
+def quadcopterClosedLoopMpc(x0, Q, R, N, Tsim, dt=0.1, Qf=None, uTrim=(9.807, 0.0, 0.0, 0.0)):
+    """
+    Receding-horizon LQR-MPC of the quadcopter in closed loop with the nonlinear plant (BASELINE cfg 3) -- the loop of
+    demos/lqrMpc.py:42-47, batched and fused into one kernel: every simulation step re-linearises the Euler quadcopter at
+    the current state (`A = I + dt dF/dx(x_t, uTrim)`, `B = dt dF/du`, zopt/quadcopter.py:116-144), solves the
+    unconstrained `lqrMpc(A, B, Q, R, N, Qf=Qf)` problem from `x_t` (a full Riccati sweep, nothing cached), applies the
+    first move (`uTrim + u_t`) to the plant `x + dt * inertialDynamics(x, u)`.  fp32, bounds inactive.
+
+    x0 (Bsz,12) or (12,); Q (12,12), R (4,4), Qf (12,12, default Q) optionally batched.
+    Returns Trajectory(xTraj (Bsz,Tsim+1,12), uTraj (Bsz,Tsim,4)) with uTraj the deviation from uTrim.
+    With finite bounds or in fp64, compose `Quadcopter.linearizeInertial`, `lqrMpc(...).solve` and
+    `Quadcopter.inertialDynamics` step by step instead.
+    """
+    if Qf is None:
+        Qf = Q
+    device = pick_device(x0, Q, R, Qf)
+    f32 = torch.float32
+    x0, Q, R, Qf = (to_dev(t, f32, device) for t in (x0, Q, R, Qf))
+    batched = x0.ndim == 2
+    x0 = (x0 if batched else x0[None]).contiguous()
+    Bsz = x0.shape[0]
+    views = [View(t, 2, False, t.ndim == 3) for t in (Q, R, Qf)]
+    diag = all(_is_diagonal(t) for t in (Q, R, Qf))
+    xS = torch.empty((Bsz, Tsim + 1, 12), dtype=f32, device=device)
+    uS = torch.empty((Bsz, Tsim, 4), dtype=f32, device=device)
+    ut = (C.c_double * 4)(*[float(v) for v in uTrim])
+    check(lib.zb_mpc_closed_loop_quad(0, device.index, stream_ptr(device), Bsz, int(N), int(Tsim), float(dt), ut,
+                                      *[v.ref() for v in views], 2 if diag else 0, ptr(x0), ptr(xS), ptr(uS)))
+    return Trajectory(xS, uS) if batched else Trajectory(xS[0], uS[0])
