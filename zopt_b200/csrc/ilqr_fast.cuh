@@ -136,12 +136,19 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     const int cstride = (t < 3) ? 12 : 4;
     const int tcol = (t < 3) ? 4 * t : 0;
 
+    // trajectory rows are prefetched one step ahead (the L2 round trip of x_{k-1}, u_{k-1} overlaps step k)
+    Vec4<T> px0 = ldv4(xT + (long long)(N - 1) * 12), px1 = ldv4(xT + (long long)(N - 1) * 12 + 4), px2 = ldv4(xT + (long long)(N - 1) * 12 + 8);
+    Vec4<T> pu0 = ldv4(uT + (long long)(N - 1) * 4);
     for (int k = N - 1; k >= 0; --k) {
         // ---- 0. linearise at (x_k, u_k): every thread evaluates dF/dx (no divergence), stores 3 rows ----
         {
             T x[12], u[4], J[144];
-            const Vec4<T> x0 = ldv4(xT + (long long)k * 12), x1 = ldv4(xT + (long long)k * 12 + 4), x2 = ldv4(xT + (long long)k * 12 + 8);
-            const Vec4<T> u0 = ldv4(uT + (long long)k * 4);
+            const Vec4<T> x0 = px0, x1 = px1, x2 = px2, u0 = pu0;
+            {
+                const int kp = (k > 0) ? k - 1 : 0;
+                px0 = ldv4(xT + (long long)kp * 12); px1 = ldv4(xT + (long long)kp * 12 + 4); px2 = ldv4(xT + (long long)kp * 12 + 8);
+                pu0 = ldv4(uT + (long long)kp * 4);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) { x[i] = x0.v[i]; x[4 + i] = x1.v[i]; x[8 + i] = x2.v[i]; u[i] = u0.v[i]; }
             QuadTrig<T> tr = quad_trig(x);

@@ -294,56 +294,57 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
         if (active) {
             xT[0] = make_float4(x[0], x[1], x[2], x[3]); xT[1] = make_float4(x[4], x[5], x[6], x[7]); xT[2] = make_float4(x[8], x[9], x[10], x[11]);
         }
-        // gains of steps k, k+1, k+2 are in flight in three register buffers (L2 latency ~ two steps of the chain)
-        float4 gbuf[3][12];
+        // gains stream back through a 3-stage cp.async ring in the (now free) W region: the copies of steps k+1, k+2
+        // are in flight while step k's dependent chain runs; every lane reads only the slots it filled (no barrier).
+        auto stage_ptr = [&](int st, int j) -> float4* { return &S[(W4 + st * 12 + j) * 32]; };
+        auto issue = [&](int kk) {
+            const int ks = (kk < P.N) ? kk : P.N - 1;
+            const float4* src = gws + (long long)ks * 12 * 32;
+            const int st = kk % 3;
 #pragma unroll
-        for (int s3 = 0; s3 < 3; ++s3) {
-            const int ks = (s3 < P.N) ? s3 : P.N - 1;
-#pragma unroll
-            for (int j = 0; j < 12; ++j) gbuf[s3][j] = __ldcg(gws + ((long long)ks * 12 + j) * 32);
-        }
+            for (int j = 0; j < 12; ++j) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_ptr(st, j));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + j * 32) : "memory");
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        };
+        issue(0);
+        issue(1);
 #pragma unroll 1
-        for (int k0 = 0; k0 < P.N; k0 += 3) {
+        for (int k = 0; k < P.N; ++k) {
+            issue(k + 2);
+            asm volatile("cp.async.wait_group 2;\n" ::: "memory");
+            const int st = k % 3;
+            float u[4];
 #pragma unroll
-            for (int s3 = 0; s3 < 3; ++s3) {
-                const int k = k0 + s3;
-                if (k < P.N) {
-                    float u[4];
+            for (int a = 0; a < 4; ++a) {
+                const float4 l0 = *stage_ptr(st, a * 3), l1 = *stage_ptr(st, a * 3 + 1), l2 = *stage_ptr(st, a * 3 + 2);
+                float s0 = l0.x * x[0], s1 = l1.x * x[4], s2 = l2.x * x[8];
+                s0 = fmaf(l0.y, x[1], s0); s1 = fmaf(l1.y, x[5], s1); s2 = fmaf(l2.y, x[9], s2);
+                s0 = fmaf(l0.z, x[2], s0); s1 = fmaf(l1.z, x[6], s1); s2 = fmaf(l2.z, x[10], s2);
+                s0 = fmaf(l0.w, x[3], s0); s1 = fmaf(l1.w, x[7], s1); s2 = fmaf(l2.w, x[11], s2);
+                u[a] = -((s0 + s1) + s2);
+            }
+            float xn[12];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const float4 l0 = gbuf[s3][a * 3], l1 = gbuf[s3][a * 3 + 1], l2 = gbuf[s3][a * 3 + 2];
-                        float s0 = l0.x * x[0], s1 = l1.x * x[4], s2 = l2.x * x[8];
-                        s0 = fmaf(l0.y, x[1], s0); s1 = fmaf(l1.y, x[5], s1); s2 = fmaf(l2.y, x[9], s2);
-                        s0 = fmaf(l0.z, x[2], s0); s1 = fmaf(l1.z, x[6], s1); s2 = fmaf(l2.z, x[10], s2);
-                        s0 = fmaf(l0.w, x[3], s0); s1 = fmaf(l1.w, x[7], s1); s2 = fmaf(l2.w, x[11], s2);
-                        u[a] = -((s0 + s1) + s2);
-                    }
-                    {
-                        const int kp = (k + 3 < P.N) ? k + 3 : P.N - 1;
+            for (int i = 0; i < 12; ++i) {
+                const float4 a0 = S[(X4 + i * 4 + 0) * 32], a1 = S[(X4 + i * 4 + 1) * 32], a2 = S[(X4 + i * 4 + 2) * 32], b4 = S[(X4 + i * 4 + 3) * 32];
+                float s0 = a0.x * x[0], s1 = a1.x * x[4], s2 = a2.x * x[8], s3f = b4.x * u[0];
+                s0 = fmaf(a0.y, x[1], s0); s1 = fmaf(a1.y, x[5], s1); s2 = fmaf(a2.y, x[9], s2); s3f = fmaf(b4.y, u[1], s3f);
+                s0 = fmaf(a0.z, x[2], s0); s1 = fmaf(a1.z, x[6], s1); s2 = fmaf(a2.z, x[10], s2); s3f = fmaf(b4.z, u[2], s3f);
+                s0 = fmaf(a0.w, x[3], s0); s1 = fmaf(a1.w, x[7], s1); s2 = fmaf(a2.w, x[11], s2); s3f = fmaf(b4.w, u[3], s3f);
+                xn[i] = (s0 + s1) + (s2 + s3f);
+            }
 #pragma unroll
-                        for (int j = 0; j < 12; ++j) gbuf[s3][j] = __ldcg(gws + ((long long)kp * 12 + j) * 32);
-                    }
-                    float xn[12];
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) {
-                        const float4 a0 = S[(X4 + i * 4 + 0) * 32], a1 = S[(X4 + i * 4 + 1) * 32], a2 = S[(X4 + i * 4 + 2) * 32], b4 = S[(X4 + i * 4 + 3) * 32];
-                        float s0 = a0.x * x[0], s1 = a1.x * x[4], s2 = a2.x * x[8], s3f = b4.x * u[0];
-                        s0 = fmaf(a0.y, x[1], s0); s1 = fmaf(a1.y, x[5], s1); s2 = fmaf(a2.y, x[9], s2); s3f = fmaf(b4.y, u[1], s3f);
-                        s0 = fmaf(a0.z, x[2], s0); s1 = fmaf(a1.z, x[6], s1); s2 = fmaf(a2.z, x[10], s2); s3f = fmaf(b4.z, u[2], s3f);
-                        s0 = fmaf(a0.w, x[3], s0); s1 = fmaf(a1.w, x[7], s1); s2 = fmaf(a2.w, x[11], s2); s3f = fmaf(b4.w, u[3], s3f);
-                        xn[i] = (s0 + s1) + (s2 + s3f);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) x[i] = xn[i];
-                    if (active) {
-                        uT[k] = make_float4(u[0], u[1], u[2], u[3]);
-                        float4* xr = xT + (long long)(k + 1) * 3;
-                        xr[0] = make_float4(x[0], x[1], x[2], x[3]); xr[1] = make_float4(x[4], x[5], x[6], x[7]); xr[2] = make_float4(x[8], x[9], x[10], x[11]);
-                        if (k == 0) *reinterpret_cast<float4*>(P.u0 + b * 4) = make_float4(u[0], u[1], u[2], u[3]);
-                    }
-                }
+            for (int i = 0; i < 12; ++i) x[i] = xn[i];
+            if (active) {
+                uT[k] = make_float4(u[0], u[1], u[2], u[3]);
+                float4* xr = xT + (long long)(k + 1) * 3;
+                xr[0] = make_float4(x[0], x[1], x[2], x[3]); xr[1] = make_float4(x[4], x[5], x[6], x[7]); xr[2] = make_float4(x[8], x[9], x[10], x[11]);
+                if (k == 0) *reinterpret_cast<float4*>(P.u0 + b * 4) = make_float4(u[0], u[1], u[2], u[3]);
             }
         }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         if (active) {
             P.status[b] = 0;
             if (P.iters) P.iters[b] = 0;

@@ -398,23 +398,28 @@ ZB_HD void solve_backward_problem(const SolveBackP& P, long long b) {
         }
         T c = quad_form<T>(Q, x, n) + quad_form<T>(R, u, m);
         if (P.second_order) {
-            // conditionQuadraticDynamics (ilqrUtils.py:237-251); f_ux = f_uu = 0 for both registered models
+            // conditionQuadraticDynamics (ilqrUtils.py:237-251); f_ux = f_uu = 0 for both registered models, and for
+            // the quadcopter v_x.f_xx only touches states 0..8, so the (n+m)x(n+m) block is blockdiag(H9, 0): its
+            // eigen-clamp is blockdiag(clampPD(H9), eps*I) exactly (block-diagonal matrices have block eigenvectors;
+            // the result is a spectral function, independent of the basis chosen inside the null space).
+            for (int i = 0; i < n * n; ++i) vf_xx[i] = T(0);
+            for (int i = 0; i < m * n; ++i) vf_ux[i] = T(0);
+            for (int i = 0; i < m * m; ++i) vf_uu[i] = T(0);
+            int q = 0;  // size of the non-trivial leading block
             T Z[ZB_PD_MAX * ZB_PD_MAX], W[ZB_PD_MAX * ZB_PD_MAX];
-            for (int i = 0; i < p * p; ++i) Z[i] = T(0);
             if (P.M.kind == 1) {
                 T w[3] = {T(P.M.wind[0]), T(P.M.wind[1]), T(P.M.wind[2])};
                 T H[144];
                 quad_hess<T>(x, u, w, P.M.has_wind != 0, T(P.M.dt), v_x, H);
-                for (int i = 0; i < n; ++i)
-                    for (int j = 0; j < n; ++j) Z[i * p + j] = H[i * n + j];
+                q = 9;
+                for (int i = 0; i < q; ++i)
+                    for (int j = 0; j < q; ++j) Z[i * q + j] = H[i * n + j];
+                pd_clamp<T>(Z, W, q, T(P.eps));
+                for (int i = 0; i < q; ++i)
+                    for (int j = 0; j < q; ++j) vf_xx[i * n + j] = Z[i * q + j];
             }
-            pd_clamp<T>(Z, W, p, T(P.eps));
-            for (int i = 0; i < n; ++i)
-                for (int j = 0; j < n; ++j) vf_xx[i * n + j] = Z[i * p + j];
-            for (int i = 0; i < m; ++i) {
-                for (int j = 0; j < n; ++j) vf_ux[i * n + j] = Z[(n + i) * p + j];
-                for (int j = 0; j < m; ++j) vf_uu[i * m + j] = Z[(n + i) * p + n + j];
-            }
+            for (int i = q; i < n; ++i) vf_xx[i * n + i] = T(P.eps);
+            for (int i = 0; i < m; ++i) vf_uu[i * m + i] = T(P.eps);
         }
         ilqr_step<T>(n, m, fx, fu, c, c_x, c_u, c_xx, c_ux, c_uu, P.second_order ? vf_xx : nullptr, vf_ux, vf_uu, v,
                      v_x, v_xx, l, L);
