@@ -140,9 +140,11 @@ ZB_API int32_t zb_pd_clamp(int32_t dtype, int32_t device, void* stream, int64_t 
  * x0 (Bsz,n), uGuess (Bsz,N,m).  Outputs xTraj (Bsz,N+1,n), uTraj (Bsz,N,m), L_out (Bsz,N,m,n),
  * J_out (Bsz), converged_out (Bsz) uint8, iters_out (Bsz) int32,
  * alpha_log (Bsz,maxIter) int32 optional (-1 = iteration not run), J_log (Bsz,maxIter+1) optional.
+ * flags: ZB_SECOND_ORDER = DDP (ilqrUtils.py:330-397) instead of iLQR; ZB_COST_DIAGONAL = the caller asserts Q, R, Qf diagonal
+ * (the quadcopter backward kernel then keeps twice as many problems per SM).
  * workspace: device scratch of zb_ilqr_workspace_bytes(...) bytes. */
 ZB_API size_t zb_ilqr_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m);
-ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t second_order,
+ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t flags,
                       const zb_model* model, const zb_cost* cost, const void* x0, const void* uGuess,
                       int32_t maxIter, double tol, void* xTraj, void* uTraj, void* L_out, void* J_out,
                       uint8_t* converged_out, int32_t* iters_out, int32_t* alpha_log, void* J_log,
@@ -157,8 +159,9 @@ ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_
  * and Qf are diagonal (the fp32 (12,4) kernel then keeps 4 instead of 27 float4 of cost data per problem on chip).
  * status_out (Bsz) int8: 0 optimal, 1 optimal_inaccurate (max_iter hit), 2 infeasible.
  * iters_out (Bsz) int32 ADMM iterations (0 on the unconstrained path). */
-#define ZB_MPC_BOUNDED 1
-#define ZB_COST_DIAGONAL 2
+#define ZB_MPC_BOUNDED 1   /* zb_mpc_lqr_solve */
+#define ZB_SECOND_ORDER 1  /* zb_ilqr_solve */
+#define ZB_COST_DIAGONAL 2 /* both */
 
 typedef struct zb_admm_opts {
     int32_t max_iter;   /* default 4000 */

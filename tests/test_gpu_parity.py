@@ -393,13 +393,20 @@ def test_solvers_linear_known_answer(second_order):  # reference tests/test_ilqr
         solver(lambda x, u: x + u, QuadraticCost(I, I), QuadraticTerminalCost(I), x0, uGuess)
 
 
-@pytest.mark.parametrize("second_order,R_scale,spread", [(False, 1.0, 10.0), (True, 0.2, 5.0)])
-def test_solvers_quadcopter_vs_oracle_fp64(second_order, R_scale, spread):
-    """iLQR / DDP on the quadcopter, N=30, 3 forced iterations: step-size sequence first, then x, u, L, J at 1e-10"""
+@pytest.mark.parametrize("second_order,R_scale,spread,dense_cost", [(False, 1.0, 10.0, False), (True, 0.2, 5.0, False),
+                                                                   (False, 1.0, 10.0, True), (True, 0.2, 5.0, True)])
+def test_solvers_quadcopter_vs_oracle_fp64(second_order, R_scale, spread, dense_cost):
+    """iLQR / DDP on the quadcopter, N=30, 3 forced iterations: step-size sequence first, then x, u, L, J at 1e-10.
+    Diagonal costs take the diagonal-cost kernel variant, dense (SPD, non-diagonal) costs the general one."""
     from zopt_b200 import ilqrUtils
     from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
     N, Bsz, iters = 30, 4, 3
     x0, uG, Q, R, Qf = _quad_problem(N, Bsz, 21 + int(second_order), R_scale, spread)
+    if dense_cost:
+        rng = np.random.default_rng(99)
+        Mq, Mr = rng.normal(size=(12, 12)) * 0.2, rng.normal(size=(4, 4)) * 0.2
+        Q, R = Q + Mq @ Mq.T, R + Mr @ Mr.T
+        Qf = 10 * Q
     solver = ilqrUtils.differentialDynamicProgramming if second_order else ilqrUtils.iterativeLqr
     traj, L, J, conv, log = solver(QuadcopterEuler(0.1), QuadraticCost(Q, R), QuadraticTerminalCost(Qf), cuda(x0), uG,
                                    maxIter=iters, tol=-1.0, return_log=True)

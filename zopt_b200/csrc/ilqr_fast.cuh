@@ -48,6 +48,12 @@ constexpr int IQ_XK = 784;     // x_k 12, u_k 4
 constexpr int IQ_QU = 800;     // Q_u 4
 constexpr int IQ_PS_F32 = 812;  // 812/4 = 203 odd
 constexpr int IQ_PS_F64 = 806;  // 806*8/16 = 403 odd (16-byte units)
+// diagonal-cost variant (Q, R, Qf diagonal => conditioned Hessians diagonal, c_ux = 0) with f_u's known sparsity:
+// no B, c_xx, Q+Q', c_ux, c_uu, R+R' matrices in the slab -> 420 words, twice as many problems (warps) per SM
+constexpr int ID_V = 0, ID_A = 144, ID_M = 288, ID_G = 336, ID_CXX = 352, ID_QS = 364, ID_CUU = 376, ID_RS = 380;
+constexpr int ID_VX = 384, ID_XK = 400, ID_QU = 416;
+constexpr int ID_PS_F32 = 420;  // 420/4 = 105 odd
+constexpr int ID_PS_F64 = 422;  // 422*8/16 = 211 odd
 
 template <typename T>
 struct Vec4 {
@@ -71,10 +77,10 @@ __device__ __forceinline__ void stv4(double* p, double a, double b, double c, do
 __device__ __forceinline__ float rsq(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double rsq(double x) { return 1.0 / sqrt(x); }
 
-template <typename T>
+template <typename T, bool CDIAG>
 __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int PS = sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64;
+    constexpr int PS = CDIAG ? (sizeof(T) == 4 ? ID_PS_F32 : ID_PS_F64) : (sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64);
     T* smem = reinterpret_cast<T*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & 3, quad = lane >> 2;
@@ -85,8 +91,10 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     // a warp whose 8 problems are all frozen / out of range has nothing to do
     if (__ballot_sync(0xffffffffu, active) == 0u) return;
     T* S = smem + (warp * 8 + quad) * PS;
-    T *Vs = S + IQ_V, *As = S + IQ_A, *Bs = S + IQ_B, *Cxx = S + IQ_CXX, *Qs = S + IQ_QS, *Ms = S + IQ_M, *Cux = S + IQ_CUX;
-    T *Gs = S + IQ_G, *Cuu = S + IQ_CUU, *Rs = S + IQ_RS, *vx = S + IQ_VX, *xk = S + IQ_XK, *Qu = S + IQ_QU;
+    T *Vs = S + (CDIAG ? ID_V : IQ_V), *As = S + (CDIAG ? ID_A : IQ_A), *Bs = S + IQ_B, *Cxx = S + (CDIAG ? ID_CXX : IQ_CXX);
+    T *Qs = S + (CDIAG ? ID_QS : IQ_QS), *Ms = S + (CDIAG ? ID_M : IQ_M), *Cux = S + IQ_CUX, *Gs = S + (CDIAG ? ID_G : IQ_G);
+    T *Cuu = S + (CDIAG ? ID_CUU : IQ_CUU), *Rs = S + (CDIAG ? ID_RS : IQ_RS), *vx = S + (CDIAG ? ID_VX : IQ_VX);
+    T *xk = S + (CDIAG ? ID_XK : IQ_XK), *Qu = S + (CDIAG ? ID_QU : IQ_QU);  // Bs, Cux unused when CDIAG
     const int N = P.N;
     const T dt = T(P.dt);
     const T* xT = reinterpret_cast<const T*>(P.xTraj) + b * (long long)(N + 1) * 12;
@@ -101,26 +109,33 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
         const T* Q = P.C.Q.at<T>(b);
         const T* R = P.C.R.at<T>(b);
         const T* Qf = P.C.Qf.at<T>(b);
-        for (int e = t; e < 144; e += 4) {
-            const int i = e / 12, j = e % 12;
-            Cxx[e] = Czz[i * 16 + j];
-            Qs[e] = Q[i * 12 + j] + Q[j * 12 + i];
-            Vs[e] = Vf[e];
-            As[e] = T(0);
-        }
-        for (int e = t; e < 48; e += 4) {
-            const int a = e / 12, j = e % 12;
-            Cux[e] = Czz[(12 + a) * 16 + j];
-            Bs[e] = T(0);
-        }
-        for (int e = t; e < 16; e += 4) {
-            const int a = e / 4, c = e % 4;
-            Cuu[e] = Czz[(12 + a) * 16 + 12 + c];
-            Rs[e] = R[a * 4 + c] + R[c * 4 + a];
-        }
-        __syncwarp();
-        if (t == 0) {  // f_u = dt * dF/du: [2,0] = -dt, [3,1] = [4,2] = [5,3] = +dt (quad_model_gen.cuh)
-            Bs[2 * 4 + 0] = -dt; Bs[3 * 4 + 1] = dt; Bs[4 * 4 + 2] = dt; Bs[5 * 4 + 3] = dt;
+        if (CDIAG) {
+            for (int e = t; e < 144; e += 4) { Vs[e] = Vf[e]; As[e] = T(0); }
+            for (int i = t; i < 12; i += 4) { Cxx[i] = Czz[i * 17]; Qs[i] = T(2) * Q[i * 13]; }
+            Cuu[t] = Czz[(12 + t) * 17];
+            Rs[t] = T(2) * R[t * 5];
+        } else {
+            for (int e = t; e < 144; e += 4) {
+                const int i = e / 12, j = e % 12;
+                Cxx[e] = Czz[i * 16 + j];
+                Qs[e] = Q[i * 12 + j] + Q[j * 12 + i];
+                Vs[e] = Vf[e];
+                As[e] = T(0);
+            }
+            for (int e = t; e < 48; e += 4) {
+                const int a = e / 12, j = e % 12;
+                Cux[e] = Czz[(12 + a) * 16 + j];
+                Bs[e] = T(0);
+            }
+            for (int e = t; e < 16; e += 4) {
+                const int a = e / 4, c = e % 4;
+                Cuu[e] = Czz[(12 + a) * 16 + 12 + c];
+                Rs[e] = R[a * 4 + c] + R[c * 4 + a];
+            }
+            __syncwarp();
+            if (t == 0) {  // f_u = dt * dF/du: [2,0] = -dt, [3,1] = [4,2] = [5,3] = +dt (quad_model_gen.cuh)
+                Bs[2 * 4 + 0] = -dt; Bs[3 * 4 + 1] = dt; Bs[4 * 4 + 2] = dt; Bs[5 * 4 + 3] = dt;
+            }
         }
         // v_x(N) = (Qf + Qf') x_N
         const T* xN = xT + (long long)N * 12;
@@ -132,8 +147,8 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     }
     __syncwarp();
 
-    const T* Ct = (t < 3) ? (As + 4 * t) : Bs;
-    const int cstride = (t < 3) ? 12 : 4;
+    const T* Ct = (t < 3) ? (As + 4 * t) : (CDIAG ? As : Bs);  // CDIAG: thread 3's rows of f_u are formed arithmetically
+    const int cstride = (t < 3) ? 12 : (CDIAG ? 12 : 4);
     const int tcol = (t < 3) ? 4 * t : 0;
 
     // trajectory rows are prefetched one step ahead (the L2 round trip of x_{k-1}, u_{k-1} overlaps step k)
@@ -185,7 +200,9 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
             for (int c = 0; c < 4; ++c) W[i][c] = T(0);
 #pragma unroll
         for (int kk = 0; kk < 12; ++kk) {
-            const Vec4<T> c4 = ldv4(Ct + kk * cstride);
+            Vec4<T> c4 = ldv4(Ct + kk * cstride);
+            if (CDIAG && t == 3)  // row kk of f_u = dt*dF/du: (-dt at [2,0]; +dt at [3,1], [4,2], [5,3])
+                c4 = Vec4<T>{{kk == 2 ? -dt : T(0), kk == 3 ? dt : T(0), kk == 4 ? dt : T(0), kk == 5 ? dt : T(0)}};
             const Vec4<T> v0 = ldv4(Vs + kk * 12), v1 = ldv4(Vs + kk * 12 + 4), v2 = ldv4(Vs + kk * 12 + 8);
             const T vxk = vx[kk];
 #pragma unroll
@@ -200,7 +217,12 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                 }
         }
         // c_x tile = (Q+Q')[4t..4t+3, :] x_k   /   c_u = (R+R') u_k  (thread 3)
-        if (t < 3) {
+        if (CDIAG) {
+            const Vec4<T> xq = ldv4(xk + 4 * t);                 // x_k[4t..4t+3]  (thread 3: u_k)
+            const Vec4<T> dq = (t < 3) ? ldv4(Qs + 4 * t) : ldv4(Rs);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) qv[c] = fma(dq.v[c], xq.v[c], qv[c]);
+        } else if (t < 3) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const T* qrow = Qs + (4 * t + c) * 12;
@@ -224,32 +246,43 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
         }
         // ---- 2. [M | G0] tile = f_u' * [W | VB] tile ------------------------------------------
         T M[4][4];
+        if (CDIAG) {  // f_u' X = rows 2..5 of X scaled by (-dt, dt, dt, dt): no loads, no FMAs
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) M[a][c] = T(0);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            const Vec4<T> b4 = ldv4(Bs + i * 4);
+            for (int c = 0; c < 4; ++c) { M[0][c] = -dt * W[2][c]; M[1][c] = dt * W[3][c]; M[2][c] = dt * W[4][c]; M[3][c] = dt * W[5][c]; }
+        } else {
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) M[a][c] = fma(b4.v[a], W[i][c], M[a][c]);
+                for (int c = 0; c < 4; ++c) M[a][c] = T(0);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const Vec4<T> b4 = ldv4(Bs + i * 4);
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) M[a][c] = fma(b4.v[a], W[i][c], M[a][c]);
+            }
         }
         // ---- 3. Q_uu = c_uu + G0 (thread 3), Q_ux tile = c_ux tile + M (threads 0..2); share through smem
         if (t == 3) {
 #pragma unroll
+            const Vec4<T> cd = ldv4(Cuu);  // CDIAG: the diagonal of c_uu
+#pragma unroll
             for (int a = 0; a < 4; ++a) {
-                const Vec4<T> c4 = ldv4(Cuu + a * 4);
+                Vec4<T> c4;
+                if (CDIAG) c4 = Vec4<T>{{a == 0 ? cd.v[0] : T(0), a == 1 ? cd.v[1] : T(0), a == 2 ? cd.v[2] : T(0), a == 3 ? cd.v[3] : T(0)}};
+                else c4 = ldv4(Cuu + a * 4);
                 stv4(Gs + a * 4, M[a][0] + c4.v[0], M[a][1] + c4.v[1], M[a][2] + c4.v[2], M[a][3] + c4.v[3]);
             }
             stv4(Qu, qv[0], qv[1], qv[2], qv[3]);
         } else {
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                const Vec4<T> c4 = ldv4(Cux + a * 12 + 4 * t);
+                if (!CDIAG) {
+                    const Vec4<T> c4 = ldv4(Cux + a * 12 + 4 * t);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) M[a][c] += c4.v[c];
+                    for (int c = 0; c < 4; ++c) M[a][c] += c4.v[c];
+                }
                 stv4(Ms + a * 12 + 4 * t, M[a][0], M[a][1], M[a][2], M[a][3]);
             }
         }
@@ -300,9 +333,15 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
             T acc[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const Vec4<T> q4 = ldv4(Cxx + (4 * sblk + i) * 12 + tcol);
+                if (CDIAG) {  // c_xx diagonal: only the diagonal block (sblk == t) carries it
+                    const Vec4<T> cd4 = ldv4(Cxx + tcol);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[i][c] = q4.v[c];
+                    for (int c = 0; c < 4; ++c) acc[i][c] = (sblk == t && i == c) ? cd4.v[c] : T(0);
+                } else {
+                    const Vec4<T> q4 = ldv4(Cxx + (4 * sblk + i) * 12 + tcol);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[i][c] = q4.v[c];
+                }
             }
 #pragma unroll
             for (int kk = 0; kk < 12; ++kk) {
@@ -342,28 +381,27 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     }
 }
 
-inline size_t ilqr_fast_smem(int32_t dtype, int warps) {
-    return (size_t)warps * 8 * (dtype == ZB_F32 ? IQ_PS_F32 * 4 : IQ_PS_F64 * 8);
-}
-
-// launch the cooperative backward pass; returns false if the configuration is not eligible
+// launch the cooperative backward pass
 inline bool ilqr_fast_eligible(const Model& M, int second_order) {
     return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && !second_order;
 }
 
-inline int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream) {
-    const int warps = (dtype == ZB_F32) ? 4 : 2;  // problems per CTA: 32 (fp32) / 16 (fp64)
-    const size_t smem = ilqr_fast_smem(dtype, warps);
+template <typename T, bool CDIAG>
+inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
+    constexpr int PS = CDIAG ? (sizeof(T) == 4 ? ID_PS_F32 : ID_PS_F64) : (sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64);
+    // problems per CTA: fp32 32 (4 warps); fp64 16 (2 warps) so several CTAs share an SM's shared memory
+    const int warps = (sizeof(T) == 4) ? 4 : 2;
+    const size_t smem = (size_t)warps * 8 * PS * sizeof(T);
     const unsigned grid = (unsigned)((P.Bsz + warps * 8 - 1) / (warps * 8));
-    if (dtype == ZB_F32) {
-        ZB_CUDA(cudaFuncSetAttribute(k_ilqr_backward_quad<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ilqr_backward_quad<float><<<grid, warps * 32, smem, stream>>>(P);
-    } else {
-        ZB_CUDA(cudaFuncSetAttribute(k_ilqr_backward_quad<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ilqr_backward_quad<double><<<grid, warps * 32, smem, stream>>>(P);
-    }
+    ZB_CUDA(cudaFuncSetAttribute(k_ilqr_backward_quad<T, CDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ilqr_backward_quad<T, CDIAG><<<grid, warps * 32, smem, stream>>>(P);
     ZB_CUDA(cudaGetLastError());
     return 0;
+}
+
+inline int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream, bool cost_diagonal) {
+    if (dtype == ZB_F32) return cost_diagonal ? ilqr_fast_launch_impl<float, true>(P, stream) : ilqr_fast_launch_impl<float, false>(P, stream);
+    return cost_diagonal ? ilqr_fast_launch_impl<double, true>(P, stream) : ilqr_fast_launch_impl<double, false>(P, stream);
 }
 
 }  // namespace zb

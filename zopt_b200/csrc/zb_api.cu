@@ -563,11 +563,13 @@ size_t zb_ilqr_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n,
     return align256(e * Bsz * N * m) + align256(e * Bsz * 16) + align256(e * Bsz * p * p) + align256(e * Bsz * n * n) + 256;
 }
 
-int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t second_order,
+int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t flags,
                       const zb_model* model, const zb_cost* cost, const void* x0, const void* uGuess,
                       int32_t maxIter, double tol, void* xTraj, void* uTraj, void* L_out, void* J_out,
                       uint8_t* converged_out, int32_t* iters_out, int32_t* alpha_log, void* J_log,
                       void* workspace, size_t workspace_bytes) {
+    const int32_t second_order = flags & ZB_SECOND_ORDER;
+    const bool cost_diagonal = (flags & ZB_COST_DIAGONAL) != 0;
     RollP P;
     int32_t rc = roll_common(dtype, Bsz, N, model, cost, true, P);
     if (rc) return rc;
@@ -598,7 +600,7 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out};
     for (int it = 0; it < maxIter; ++it) {
         if (fast_bwd) {
-            rc = ilqr_fast_launch(dtype, Fb, s);
+            rc = ilqr_fast_launch(dtype, Fb, s, cost_diagonal);
             if (rc) return rc;
         } else
             ZB_DISPATCH(dtype, k_solve_backward, gen_grid(Bsz), GEN_THREADS, stream, Bk);

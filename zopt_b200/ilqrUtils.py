@@ -237,7 +237,10 @@ def _solve(dynamics, runningCost, terminalCost, x0, uGuess, maxIter, tol, second
     Jlog = torch.empty((Bsz, maxIter + 1), dtype=dtype, device=device) if return_log else None
     wsb = lib.zb_ilqr_workspace_bytes(dcode(dtype), Bsz, N, n, m)
     ws = torch.empty((wsb,), dtype=torch.uint8, device=device)
-    check(lib.zb_ilqr_solve(dcode(dtype), device.index, stream_ptr(device), Bsz, N, int(second_order), C.byref(mspec),
+    from .mpcUtils import _is_diagonal
+    Qd, Rd, Qfd = (vw.t for vw in ckeep)
+    flags = (1 if second_order else 0) | (2 if all(_is_diagonal(t) for t in (Qd, Rd, Qfd)) else 0)
+    check(lib.zb_ilqr_solve(dcode(dtype), device.index, stream_ptr(device), Bsz, N, flags, C.byref(mspec),
                             C.byref(cspec), ptr(x0), ptr(uGuess), maxIter, float(tol), ptr(xTraj), ptr(uTraj), ptr(L),
                             ptr(J), ptr(conv), ptr(iters), ptr(alog), ptr(Jlog), ptr(ws), wsb))
     conv = conv.bool()
