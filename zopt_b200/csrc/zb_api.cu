@@ -107,9 +107,12 @@ __global__ void __launch_bounds__(GEN_THREADS) k_rollout(RollP P, double alpha) 
     if (P.J) reinterpret_cast<T*>(P.J)[b] = J;
 }
 
-// forwardPass2 phase 1: 16 threads per problem, one step size each, cost only (ilqrUtils.py:139-146)
+// forwardPass2 phase 1: 16 threads per problem, one step size each (ilqrUtils.py:139-146).  All lanes compute the cost;
+// the lanes of the two largest step sizes (alpha = 1, 1/2: the usual winners) also store their trajectories into the
+// speculative buffers `spec` ((2,Bsz,(N+1)n + Nm)) so that the commit can copy the winner instead of re-running it.
+constexpr int SPEC_N = 2;
 template <typename T>
-__global__ void __launch_bounds__(GEN_THREADS) k_forward_costs(RollP P, void* Jall, const uint8_t* done) {
+__global__ void __launch_bounds__(GEN_THREADS) k_forward_costs(RollP P, void* Jall, const uint8_t* done, void* spec) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long b = t >> 4;
     int j = (int)(t & 15);
@@ -117,7 +120,16 @@ __global__ void __launch_bounds__(GEN_THREADS) k_forward_costs(RollP P, void* Ja
     if (done && done[b]) return;
     T alpha = T(1);
     for (int i = 0; i < j; ++i) alpha *= T(0.5);  // 0.5**j exactly (ilqrUtils.py:145)
-    T J = rollout_any<T>(P, b, alpha, false);
+    // one call for all 16 lanes (no divergence): the stores are predicated on `write`
+    const bool write = spec != nullptr && j < SPEC_N;
+    RollP Q = P;  // same inputs; outputs redirected so that problem b lands at spec[j][b]
+    if (write) {
+        const long long per = (long long)(P.N + 1) * P.M.n + (long long)P.N * P.M.m;
+        T* base = reinterpret_cast<T*>(spec) + (long long)j * P.Bsz * per;
+        Q.xTraj = base;
+        Q.uTraj = base + P.Bsz * (long long)(P.N + 1) * P.M.n;
+    }
+    const T J = rollout_any<T>(Q, b, alpha, write);
     reinterpret_cast<T*>(Jall)[b * 16 + j] = J;
 }
 
@@ -135,16 +147,33 @@ struct CommitP {
     int32_t* idx_out;    // bare entry point: (Bsz) or null
 };
 
+// 16 lanes per problem: if the winner's trajectory was stored speculatively the lanes copy it (coalesced), otherwise
+// lane 0 re-runs the winning rollout in place (identical arithmetic, so identical values).
 template <typename T>
-__global__ void __launch_bounds__(GEN_THREADS) k_forward_commit(RollP P, const void* Jall, CommitP S) {
-    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(GEN_THREADS) k_forward_commit(RollP P, const void* Jall, CommitP S, const void* spec) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long b = t >> 4;
+    const int lane16 = (int)(t & 15);
     if (b >= P.Bsz) return;
     if (S.converged && S.J && S.converged[b]) return;
     const T* Ja = reinterpret_cast<const T*>(Jall) + b * 16;
-    int idx = argmin16<T>(Ja);
-    T alpha = T(1);
-    for (int i = 0; i < idx; ++i) alpha *= T(0.5);
-    rollout_any<T>(P, b, alpha, true);
+    const int idx = argmin16<T>(Ja);
+    const int n = P.M.n, m = P.M.m, N = P.N;
+    if (spec && idx < SPEC_N) {
+        const long long per = (long long)(N + 1) * n + (long long)N * m;
+        const T* base = reinterpret_cast<const T*>(spec) + (long long)idx * P.Bsz * per;
+        const T* sx = base + b * (long long)(N + 1) * n;
+        const T* su = base + P.Bsz * (long long)(N + 1) * n + b * (long long)N * m;
+        T* dx = reinterpret_cast<T*>(P.xTraj) + b * (long long)(N + 1) * n;
+        T* du = reinterpret_cast<T*>(P.uTraj) + b * (long long)N * m;
+        for (int i = lane16; i < (N + 1) * n; i += 16) dx[i] = sx[i];
+        for (int i = lane16; i < N * m; i += 16) du[i] = su[i];
+    } else if (lane16 == 0) {
+        T alpha = T(1);
+        for (int i = 0; i < idx; ++i) alpha *= T(0.5);
+        rollout_any<T>(P, b, alpha, true);
+    }
+    if (lane16 != 0) return;
     T Jn = Ja[idx];
     if (S.J) {
         T* J = reinterpret_cast<T*>(S.J);
@@ -512,11 +541,11 @@ int32_t zb_ilqr_forward_pass(int32_t dtype, int32_t device, void* stream, int64_
     ZB_CUDA(g.err);
     P.x0 = x0; P.l = l; P.L = L; P.xPrev = xPrev; P.uPrev = uPrev;
     P.xTraj = xTraj; P.uTraj = uTraj; P.J = nullptr;
-    ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall_out, (const uint8_t*)nullptr);
+    ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall_out, (const uint8_t*)nullptr, (void*)nullptr);
     CommitP S{};
     S.J_out = J_out;
     S.idx_out = alpha_idx_out;
-    ZB_DISPATCH(dtype, k_forward_commit, gen_grid(Bsz), GEN_THREADS, stream, P, (const void*)Jall_out, S);
+    ZB_DISPATCH(dtype, k_forward_commit, gen_grid(Bsz * 16), GEN_THREADS, stream, P, (const void*)Jall_out, S, (const void*)nullptr);
     return 0;
 }
 
@@ -560,7 +589,9 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t zb_ilqr_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m) {
     size_t e = dtype == ZB_F64 ? 8 : 4;
     size_t p = (size_t)(n + m);
-    return align256(e * Bsz * N * m) + align256(e * Bsz * 16) + align256(e * Bsz * p * p) + align256(e * Bsz * n * n) + 256;
+    const size_t per = (size_t)(N + 1) * n + (size_t)N * m;  // one trajectory
+    return align256(e * Bsz * N * m) + align256(e * Bsz * 16) + align256(e * Bsz * p * p) + align256(e * Bsz * n * n) +
+           align256(e * SPEC_N * Bsz * per) + 256;
 }
 
 int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t flags,
@@ -586,7 +617,8 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     void* l_ws = w;  w += align256(e * Bsz * N * m);
     void* Jall = w;  w += align256(e * Bsz * 16);
     void* Czz = w;   w += align256(e * Bsz * p * p);
-    void* Vfxx = w;
+    void* Vfxx = w;  w += align256(e * Bsz * n * n);
+    void* spec = w;  // speculative trajectories of the two largest step sizes
     cudaStream_t s = (cudaStream_t)stream;
     // policy.L = 0 before the first iteration (ilqrUtils.py:293)
     ZB_CUDA(cudaMemsetAsync(L_out, 0, e * Bsz * N * m * n, s));
@@ -604,9 +636,9 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
             if (rc) return rc;
         } else
             ZB_DISPATCH(dtype, k_solve_backward, gen_grid(Bsz), GEN_THREADS, stream, Bk);
-        ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall, (const uint8_t*)converged_out);
+        ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall, (const uint8_t*)converged_out, spec);
         CommitP S{J_out, converged_out, iters_out, alpha_log, J_log, it, (int)maxIter, tol, nullptr, nullptr};
-        ZB_DISPATCH(dtype, k_forward_commit, gen_grid(Bsz), GEN_THREADS, stream, P, (const void*)Jall, S);
+        ZB_DISPATCH(dtype, k_forward_commit, gen_grid(Bsz * 16), GEN_THREADS, stream, P, (const void*)Jall, S, (const void*)spec);
     }
     return 0;
 }
