@@ -278,7 +278,7 @@ def run_ours(args):
     from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
     from zopt_b200.mpcUtils import quadcopterClosedLoopMpc
     from zopt_b200.sharding import shard_range
-    extra_ms = [0.0, 0.0]
+    extra_ms = [0.0]
     if not args.no_extras:
         lo, hi = shard_range(16384, rank, world)
         d3 = configs.cfg3(Bsz=16384)
@@ -296,6 +296,25 @@ def run_ours(args):
         c1.record()
         barrier()
         extra_ms[0] = c0.elapsed_time(c1) / 3
+        # the same with 16,384 problems PER GPU (weak scaling): 2,048 problems leave most SMs of a B200 idle
+        if world > 1:
+            d3w = configs.cfg3(Bsz=16384, seed=1234 + 3 + 1000 * rank)
+            x3w = torch.as_tensor(d3w["xbar"], dtype=f32, device=dev)
+            x3w[:, 9:12] *= 0.2
+            Q3w = torch.diag_embed(torch.as_tensor(d3w["qdiag"], dtype=f32, device=dev))
+            R3w = torch.diag_embed(torch.as_tensor(d3w["rdiag"], dtype=f32, device=dev))
+            Qf3w = 10 * Q3w
+            quadcopterClosedLoopMpc(x3w, Q3w, R3w, 50, 200, dt=0.1, Qf=Qf3w)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                quadcopterClosedLoopMpc(x3w, Q3w, R3w, 50, 200, dt=0.1, Qf=Qf3w)
+            c1.record()
+            barrier()
+            extra_ms.append(c0.elapsed_time(c1) / 3)
+        else:
+            extra_ms.append(extra_ms[0])
         d4 = configs.cfg4(Bsz=16384)
         x4 = torch.as_tensor(d4["x0"][lo:hi], dtype=torch.float64, device=dev)
         uG = torch.as_tensor(d4["uGuess"], dtype=torch.float64, device=dev)
@@ -308,12 +327,14 @@ def run_ours(args):
             ilqrUtils.iterativeLqr(*margs, x4, uG, maxIter=10, tol=-1.0)
         c1.record()
         barrier()
-        extra_ms[1] = c0.elapsed_time(c1) / 2
+        extra_ms.append(c0.elapsed_time(c1) / 2)
+    while len(extra_ms) < 3:
+        extra_ms.append(0.0)
 
     times = torch.tensor([ms, e2e_ms, k_ms, e2e_u_ms] + extra_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, k_ms, e2e_u_ms, cl_ms, il_ms = (float(v) for v in times.cpu())
+    ms, e2e_ms, k_ms, e2e_u_ms, cl_ms, clw_ms, il_ms = (float(v) for v in times.cpu())
 
     if rank == 0:
         total = Bsz * world
@@ -330,15 +351,22 @@ def run_ours(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = (1456 + 9600 * 2 + 3248) * Bsz  # in: A,B,Q,R,Qf,x0; gains written + re-read; plan written (fp32)
+        traffic = None
+        try:  # DRAM bytes of the dominant kernel from the committed ncu capture (same kernel, same batch)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("batch") == Bsz and tj.get("N") == N:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         roof = {"bound": "fp32_fma", "achieved": ach_tf, "peak": peak32.value / 1e12, "unit": "TFLOP/s",
-                "frac": ach_tf / (peak32.value / 1e12), "traffic": None,
+                "frac": ach_tf / (peak32.value / 1e12), "traffic": traffic, "algorithmic_bytes": alg_bytes,
                 "peak_source": "zb_peak_fma dependent-FMA probe measured in this run (MEASURED_PEAKS.json has no FP32 CUDA-core figure)",
                 "kernel": "lqrMpc.solve launch (Riccati sweep + rollout)", "kernel_ms": k_ms,
                 "algorithmic_flop_per_solve": FLOP_PER_SOLVE,
                 "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
-        cpu_val, cpu_sec, threads = time_cpu(args.cpu_sample, 1, 1)
+        cpu_val, cpu_sec, threads = time_cpu(args.cpu_sample, 3, 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -353,11 +381,13 @@ def run_ours(args):
                                          "workload": "16,384 problems total (sharded over ranks), 200 sim steps, horizon 50, fp32, "
                                                      "re-linearised every step, bounds inactive, one fused kernel",
                                          "scaling": "strong"},
+                "cfg3_closed_loop_mpc_weak": {"value": 16384 * world * 200 / (clw_ms * 1e-3), "unit": "MPC solves/s", "ms": clw_ms,
+                                              "workload": "as cfg3 but 16,384 problems PER GPU", "scaling": "weak"},
                 "cfg4_ilqr": {"value": 16384 * 10 / (il_ms * 1e-3), "unit": "problem-iterations/s", "ms": il_ms,
                               "workload": "16,384 problems total (sharded over ranks), N=200, 10 iterations, 16-way line search, fp64",
                               "scaling": "strong", "algorithmic_flop_per_problem_iteration": 4.66e6}},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{args.cpu_sample} problems of the same workload, 1 step ({cpu_sec:.1f} s), torch-CPU fp64 oracle port"},
+                             "sample": f"{args.cpu_sample} problems of the same workload per step, 3 steps of {cpu_sec:.2f} s after 1 warm-up, torch-CPU fp64 oracle port (JAX not installed)"},
         }
         print(json.dumps(line))
     if world > 1:
@@ -371,7 +401,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary cfg3/cfg4 measurements")
     args = ap.parse_args()
     if args.impl == "reference":

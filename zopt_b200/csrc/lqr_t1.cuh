@@ -36,6 +36,22 @@ __host__ __device__ constexpr int qoff(int i) { return i < 4 ? i : (i < 8 ? 4 + 
 
 #define ZB_F4(v, e) ((e) == 0 ? (v).x : (e) == 1 ? (v).y : (e) == 2 ? (v).z : (v).w)
 
+// (d0, d1) += a * (b0, b1) as ONE packed FP32x2 FMA (Blackwell `fma.rn.f32x2`, SASS FFMA2): the step is bound by
+// issue slots / dispatch with one warp per scheduler, and the packed form halves the FMA instruction count.
+#ifndef ZB_USE_FFMA2
+#define ZB_USE_FFMA2 1
+#endif
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a, float b0, float b1) {
+#if ZB_USE_FFMA2
+    const float2 r = __ffma2_rn(make_float2(a, a), make_float2(b0, b1), make_float2(d0, d1));
+    d0 = r.x;
+    d1 = r.y;
+#else
+    d0 = fmaf(a, b0, d0);
+    d1 = fmaf(a, b1, d1);
+#endif
+}
+
 // load the lower triangle of a symmetric 12x12 (row-major, global) into v[78]
 __device__ __forceinline__ void load_sym_lower(const float* g, float* v) {
     const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -151,13 +167,16 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
 #pragma unroll
             for (int i = 0; i < 12; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j) v[tri(i, j)] = fmaf(a[i], w[j], v[tri(i, j)]);
+                for (int j = 0; j <= i; j += 2) {
+                    if (j + 1 <= i) fma2(v[tri(i, j)], v[tri(i, j + 1)], a[i], w[j], w[j + 1]);
+                    else v[tri(i, j)] = fmaf(a[i], w[j], v[tri(i, j)]);
+                }
 #pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                M[0][j] = fmaf(b4.x, w[j], M[0][j]);
-                M[1][j] = fmaf(b4.y, w[j], M[1][j]);
-                M[2][j] = fmaf(b4.z, w[j], M[2][j]);
-                M[3][j] = fmaf(b4.w, w[j], M[3][j]);
+            for (int j = 0; j < 12; j += 2) {
+                fma2(M[0][j], M[0][j + 1], b4.x, w[j], w[j + 1]);
+                fma2(M[1][j], M[1][j + 1], b4.y, w[j], w[j + 1]);
+                fma2(M[2][j], M[2][j + 1], b4.z, w[j], w[j + 1]);
+                fma2(M[3][j], M[3][j + 1], b4.w, w[j], w[j + 1]);
             }
         }
     }
@@ -180,7 +199,10 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
 #pragma unroll
         for (int i = 0; i < 12; ++i)
 #pragma unroll
-            for (int j = 0; j <= i; ++j) v[tri(i, j)] = fmaf(-M[a][i], L[a][j], v[tri(i, j)]);
+            for (int j = 0; j <= i; j += 2) {
+                if (j + 1 <= i) fma2(v[tri(i, j)], v[tri(i, j + 1)], -M[a][i], L[a][j], L[a][j + 1]);
+                else v[tri(i, j)] = fmaf(-M[a][i], L[a][j], v[tri(i, j)]);
+            }
 }
 
 // QDIAG: the caller asserts Q, R, Qf diagonal (ZB_COST_DIAGONAL): 4 float4 of cost data instead of 27, so FIVE
