@@ -30,6 +30,7 @@ struct IlqrFastP {
     const void* Vfxx;  // (Bsz,12,12)
     const uint8_t* done;
     void *l, *L;
+    double eps;  // ensurePositiveDefinite threshold (1e-3)
 };
 
 // slab layout in elements of T
@@ -54,6 +55,10 @@ constexpr int ID_V = 0, ID_A = 144, ID_M = 288, ID_G = 336, ID_CXX = 352, ID_QS 
 constexpr int ID_VX = 384, ID_XK = 400, ID_QU = 416;
 constexpr int ID_PS_F32 = 420;  // 420/4 = 105 odd
 constexpr int ID_PS_F64 = 422;  // 422*8/16 = 211 odd
+// DDP (diagonal-cost variant only): + 81 words eigenvector exchange + 81 words clamped block  (+ pad)
+constexpr int ID_WS = 420, ID_PC = 504;   // 84-word regions (81 used)
+constexpr int IDD_PS_F32 = 588;  // 588/4 = 147 odd
+constexpr int IDD_PS_F64 = 590;  // 590/2 = 295 odd
 
 template <typename T>
 struct Vec4 {
@@ -77,10 +82,61 @@ __device__ __forceinline__ void stv4(double* p, double a, double b, double c, do
 __device__ __forceinline__ float rsq(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double rsq(double x) { return 1.0 / sqrt(x); }
 
-template <typename T, bool CDIAG>
+// ---- cooperative 9x9 symmetric eigen-clamp for the DDP step (ilqrUtils.py:217-219 on the v_x . f_xx block) ----------
+// Cyclic Jacobi with COMPILE-TIME rotation indices: the packed lower triangle A[45] is replicated in the registers of the
+// four threads of a quad (every thread applies the same rotations, so no exchange is needed for A), the eigenvector
+// matrix is distributed by rows (thread t holds rows t, t+4, t+8; row 8 only in thread 0).
+__host__ __device__ constexpr int tri9(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+template <typename T>
+__device__ __noinline__ void jacobi_cs(T app, T aqq, T apq, T& c, T& s, T& t) {
+    const T tau = (aqq - app) / (T(2) * apq);
+    t = (tau >= T(0) ? T(1) : T(-1)) / (fabs(tau) + sqrt(T(1) + tau * tau));
+    c = T(1) / sqrt(T(1) + t * t);
+    s = t * c;
+}
+
+template <typename T, int PP, int QQ>
+__device__ __forceinline__ void jacobi_rot(T (&A)[45], T (&Wr)[3][9]) {
+    const T apq = A[tri9(QQ, PP)];
+    if (apq != T(0)) {
+        T c, s, t;
+        jacobi_cs<T>(A[tri9(PP, PP)], A[tri9(QQ, QQ)], apq, c, s, t);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (k != PP && k != QQ) {
+                const T akp = A[tri9(k, PP)], akq = A[tri9(k, QQ)];
+                A[tri9(k, PP)] = c * akp - s * akq;
+                A[tri9(k, QQ)] = s * akp + c * akq;
+            }
+        }
+        A[tri9(PP, PP)] -= t * apq;
+        A[tri9(QQ, QQ)] += t * apq;
+        A[tri9(QQ, PP)] = T(0);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const T wp = Wr[r][PP], wq = Wr[r][QQ];
+            Wr[r][PP] = c * wp - s * wq;
+            Wr[r][QQ] = s * wp + c * wq;
+        }
+    }
+}
+
+template <typename T, int PP, int QQ>
+struct JacobiSweep {
+    static __device__ __forceinline__ void run(T (&A)[45], T (&Wr)[3][9]) {
+        jacobi_rot<T, PP, QQ>(A, Wr);
+        if constexpr (QQ < 8) JacobiSweep<T, PP, QQ + 1>::run(A, Wr);
+        else if constexpr (PP < 7) JacobiSweep<T, PP + 1, PP + 2>::run(A, Wr);
+    }
+};
+
+template <typename T, bool CDIAG, bool DDP>
 __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int PS = CDIAG ? (sizeof(T) == 4 ? ID_PS_F32 : ID_PS_F64) : (sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64);
+    static_assert(!DDP || CDIAG, "the DDP fast path exists for diagonal costs only");
+    constexpr int PS = DDP ? (sizeof(T) == 4 ? IDD_PS_F32 : IDD_PS_F64)
+                           : CDIAG ? (sizeof(T) == 4 ? ID_PS_F32 : ID_PS_F64) : (sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64);
     T* smem = reinterpret_cast<T*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & 3, quad = lane >> 2;
@@ -189,6 +245,70 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                 const Vec4<T> mine = (t == 0) ? x0 : (t == 1) ? x1 : (t == 2) ? x2 : u0;  // x_k quarter / u_k
                 stv4(xk + 4 * t, mine.v[0], mine.v[1], mine.v[2], mine.v[3]);
             }
+            if (DDP) {
+                // conditionQuadraticDynamics (ilqrUtils.py:237-251): H = dt * sum_i v_x[i] d2F_i/dx2 touches states 0..8 only,
+                // f_ux = f_uu = 0, so clampPD(blockdiag(H9, 0)) = blockdiag(clampPD(H9), eps I) exactly.
+                T* Wsm = S + ID_WS;
+                T* Pc = S + ID_PC;
+                T lam[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) lam[i] = vx[i];
+                T A9[45], Wr[3][9];
+                {
+                    T h9[81];
+                    quad_hess_contract(tr, x, u, lam, h9);  // lower triangle of the 9x9
+#pragma unroll
+                    for (int i = 0; i < 9; ++i)
+#pragma unroll
+                        for (int j = 0; j <= i; ++j) A9[tri9(i, j)] = dt * h9[i * 9 + j];
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) Wr[r][c] = (c == t + 4 * r) ? T(1) : T(0);  // rows t, t+4, t+8 of I
+                for (int sweep = 0; sweep < 30; ++sweep) {
+                    T off = T(0), dg = T(0);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) {
+                        dg = fma(A9[tri9(i, i)], A9[tri9(i, i)], dg);
+#pragma unroll
+                        for (int j = 0; j < i; ++j) off = fma(A9[tri9(i, j)], A9[tri9(i, j)], off);
+                    }
+                    const T thr = (sizeof(T) == 8) ? T(1e-32) : T(1e-15), tiny = (sizeof(T) == 8) ? T(1e-300) : T(1e-37);
+                    if (off <= thr * dg || off < tiny) break;
+                    JacobiSweep<T, 0, 1>::run(A9, Wr);
+                }
+                // exchange eigenvector rows, then P9 = W max(Lambda, eps) W^T, rows t, t+4, t+8 per thread
+                const T eps = T(P.eps);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int row = t + 4 * r;
+                    if (row < 9) {
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) Wsm[row * 9 + c] = Wr[r][c];
+                    }
+                }
+                __syncwarp();
+                T lamc[9];
+#pragma unroll
+                for (int k2 = 0; k2 < 9; ++k2) lamc[k2] = A9[tri9(k2, k2)] > eps ? A9[tri9(k2, k2)] : eps;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int row = t + 4 * r;
+                    if (row < 9) {
+                        T wl[9];
+#pragma unroll
+                        for (int k2 = 0; k2 < 9; ++k2) wl[k2] = Wr[r][k2] * lamc[k2];
+                        for (int j = 0; j < 9; ++j) {
+                            T acc9 = T(0);
+#pragma unroll
+                            for (int k2 = 0; k2 < 9; ++k2) acc9 = fma(wl[k2], Wsm[j * 9 + k2], acc9);
+                            Pc[row * 9 + j] = acc9;
+                        }
+                    }
+                }
+                // visibility of Pc for step 5 is ensured by the __syncwarp() calls that follow
+            }
         }
         __syncwarp();
         // ---- 1. [W | VB] tile = v_xx * tile ;  [Q_x | Q_u] tile = tile' v_x + c_x / c_u -------------
@@ -272,6 +392,7 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                 Vec4<T> c4;
                 if (CDIAG) c4 = Vec4<T>{{a == 0 ? cd.v[0] : T(0), a == 1 ? cd.v[1] : T(0), a == 2 ? cd.v[2] : T(0), a == 3 ? cd.v[3] : T(0)}};
                 else c4 = ldv4(Cuu + a * 4);
+                if (DDP) c4.v[a] += T(P.eps);  // vf_uu = eps I (ilqrUtils.py:197)
                 stv4(Gs + a * 4, M[a][0] + c4.v[0], M[a][1] + c4.v[1], M[a][2] + c4.v[2], M[a][3] + c4.v[3]);
             }
             stv4(Qu, qv[0], qv[1], qv[2], qv[3]);
@@ -337,6 +458,18 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                     const Vec4<T> cd4 = ldv4(Cxx + tcol);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) acc[i][c] = (sblk == t && i == c) ? cd4.v[c] : T(0);
+                    if (DDP) {  // + vf_xx = blockdiag(clampPD(H9), eps I3), symmetric: use the lower value for both halves
+                        const int gi = 4 * sblk + i;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int gj = tcol + c;
+                            const int hi_ = gi > gj ? gi : gj, lo_ = gi > gj ? gj : gi;
+                            T add = T(0);
+                            if (hi_ < 9) add = (S + ID_PC)[hi_ * 9 + lo_];
+                            else if (gi == gj) add = T(P.eps);
+                            acc[i][c] += add;
+                        }
+                    }
                 } else {
                     const Vec4<T> q4 = ldv4(Cxx + (4 * sblk + i) * 12 + tcol);
 #pragma unroll
@@ -382,24 +515,27 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
 }
 
 // launch the cooperative backward pass
-inline bool ilqr_fast_eligible(const Model& M, int second_order) {
-    return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && !second_order;
+inline bool ilqr_fast_eligible(const Model& M, int second_order, bool cost_diagonal) {
+    return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && (!second_order || cost_diagonal);
 }
 
-template <typename T, bool CDIAG>
+template <typename T, bool CDIAG, bool DDP = false>
 inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
-    constexpr int PS = CDIAG ? (sizeof(T) == 4 ? ID_PS_F32 : ID_PS_F64) : (sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64);
+    constexpr int PS = DDP ? (sizeof(T) == 4 ? IDD_PS_F32 : IDD_PS_F64)
+                           : CDIAG ? (sizeof(T) == 4 ? ID_PS_F32 : ID_PS_F64) : (sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64);
     // problems per CTA: fp32 32 (4 warps); fp64 16 (2 warps) so several CTAs share an SM's shared memory
     const int warps = (sizeof(T) == 4) ? 4 : 2;
     const size_t smem = (size_t)warps * 8 * PS * sizeof(T);
     const unsigned grid = (unsigned)((P.Bsz + warps * 8 - 1) / (warps * 8));
-    ZB_CUDA(cudaFuncSetAttribute(k_ilqr_backward_quad<T, CDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_ilqr_backward_quad<T, CDIAG><<<grid, warps * 32, smem, stream>>>(P);
+    ZB_CUDA(cudaFuncSetAttribute(k_ilqr_backward_quad<T, CDIAG, DDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ilqr_backward_quad<T, CDIAG, DDP><<<grid, warps * 32, smem, stream>>>(P);
     ZB_CUDA(cudaGetLastError());
     return 0;
 }
 
-inline int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream, bool cost_diagonal) {
+inline int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream, bool cost_diagonal, bool second_order) {
+    if (second_order)  // eligibility (diagonal costs) is checked by the caller
+        return dtype == ZB_F32 ? ilqr_fast_launch_impl<float, true, true>(P, stream) : ilqr_fast_launch_impl<double, true, true>(P, stream);
     if (dtype == ZB_F32) return cost_diagonal ? ilqr_fast_launch_impl<float, true>(P, stream) : ilqr_fast_launch_impl<float, false>(P, stream);
     return cost_diagonal ? ilqr_fast_launch_impl<double, true>(P, stream) : ilqr_fast_launch_impl<double, false>(P, stream);
 }

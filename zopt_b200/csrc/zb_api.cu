@@ -628,11 +628,11 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     ZB_DISPATCH(dtype, k_solve_init, gen_grid(Bsz), GEN_THREADS, stream, P, uGuess, J_out, converged_out, iters_out,
                 alpha_log, J_log, (int)maxIter);
     SolveBackP Bk{Bsz, N, second_order, P.M, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
-    const bool fast_bwd = ilqr_fast_eligible(P.M, second_order) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out);
-    IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out};
+    const bool fast_bwd = ilqr_fast_eligible(P.M, second_order, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out);
+    IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
     for (int it = 0; it < maxIter; ++it) {
         if (fast_bwd) {
-            rc = ilqr_fast_launch(dtype, Fb, s, cost_diagonal);
+            rc = ilqr_fast_launch(dtype, Fb, s, cost_diagonal, second_order != 0);
             if (rc) return rc;
         } else
             ZB_DISPATCH(dtype, k_solve_backward, gen_grid(Bsz), GEN_THREADS, stream, Bk);
