@@ -328,13 +328,26 @@ def run_ours(args):
         c1.record()
         barrier()
         extra_ms.append(c0.elapsed_time(c1) / 2)
-    while len(extra_ms) < 3:
+        # cfg 5: DDP (second-order dynamics terms), N=100, 10 forced iterations, 16,384 problems in total, fp64
+        d5 = configs.cfg5(Bsz=16384, N=100)
+        x5 = torch.as_tensor(d5["x0"][lo:hi], dtype=torch.float64, device=dev)
+        uG5 = torch.as_tensor(d5["uGuess"], dtype=torch.float64, device=dev)
+        m5 = (QuadcopterEuler(d5["dt"]), QuadraticCost(d5["Q"], d5["R"]), QuadraticTerminalCost(d5["Qf"]))
+        ilqrUtils.differentialDynamicProgramming(*m5, x5, uG5, maxIter=10, tol=-1.0)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        ilqrUtils.differentialDynamicProgramming(*m5, x5, uG5, maxIter=10, tol=-1.0)
+        c1.record()
+        barrier()
+        extra_ms.append(c0.elapsed_time(c1))
+    while len(extra_ms) < 4:
         extra_ms.append(0.0)
 
     times = torch.tensor([ms, e2e_ms, k_ms, e2e_u_ms] + extra_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, k_ms, e2e_u_ms, cl_ms, clw_ms, il_ms = (float(v) for v in times.cpu())
+    ms, e2e_ms, k_ms, e2e_u_ms, cl_ms, clw_ms, il_ms, ddp_ms = (float(v) for v in times.cpu())
 
     if rank == 0:
         total = Bsz * world
@@ -385,7 +398,10 @@ def run_ours(args):
                                               "workload": "as cfg3 but 16,384 problems PER GPU", "scaling": "weak"},
                 "cfg4_ilqr": {"value": 16384 * 10 / (il_ms * 1e-3), "unit": "problem-iterations/s", "ms": il_ms,
                               "workload": "16,384 problems total (sharded over ranks), N=200, 10 iterations, 16-way line search, fp64",
-                              "scaling": "strong", "algorithmic_flop_per_problem_iteration": 4.66e6}},
+                              "scaling": "strong", "algorithmic_flop_per_problem_iteration": 4.66e6},
+                "cfg5_ddp": {"value": 16384 * 10 / (ddp_ms * 1e-3), "unit": "problem-iterations/s", "ms": ddp_ms,
+                             "workload": "16,384 problems total (sharded over ranks), N=100, 10 iterations, eigen-clamped second-order "
+                                         "terms every step, fp64", "scaling": "strong"}},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{args.cpu_sample} problems of the same workload per step, 3 steps of {cpu_sec:.2f} s after 1 warm-up, torch-CPU fp64 oracle port (JAX not installed)"},
         }
