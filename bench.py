@@ -134,13 +134,55 @@ def time_cpu(sample, steps, warmup, rank=0):
     return sample * steps / el, el / steps, threads
 
 
+def try_real_reference(sample, steps, warmup):
+    """The reference's own JAX-CPU path, if `jax` and the reference package are importable (they are not in this image:
+    DESIGN.md "Reference install").  jax.jit(jax.vmap(...)) over zopt.lqrUtils.discreteFiniteHorizonLqr + the plan rollout."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        os.environ.setdefault("JAX_PLATFORMS", "cpu")
+        import jax
+        import jax.numpy as jnp
+        from zopt.lqrUtils import discreteFiniteHorizonLqr
+        from zopt.quadcopter import Quadcopter
+    except Exception:
+        return None
+    d = make_problem(sample, 0)
+    ac, N, dt = Quadcopter(), d["N"], d["dt"]
+
+    def one(xbar, ubar, qd, rd):
+        Aw, Bw = jax.jacobian(ac.inertialDynamics, argnums=(0, 1))(xbar, ubar)
+        A, B = jnp.eye(12) + dt * Aw, dt * Bw
+        Q, R = jnp.diag(qd), jnp.diag(rd)
+        Qk = jnp.concatenate([jnp.repeat(Q[None], N, 0), 10 * Q[None]], 0)
+        L = discreteFiniteHorizonLqr(jnp.repeat(A[None], N, 0), jnp.repeat(B[None], N, 0), Qk, jnp.repeat(R[None], N, 0), N)
+
+        def stepf(x, Lk):
+            u = -Lk @ x
+            return A @ x + B @ u, (x, u)
+
+        _, (xs, us) = jax.lax.scan(stepf, xbar, L)
+        return xs, us
+
+    f = jax.jit(jax.vmap(one))
+    args_ = tuple(jnp.asarray(d[k]) for k in ("xbar", "ubar", "qdiag", "rdiag"))
+    for _ in range(max(warmup, 1)):
+        jax.block_until_ready(f(*args_))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        jax.block_until_ready(f(*args_))
+    el = time.perf_counter() - t0
+    return sample * steps / el, el / steps, os.cpu_count() or 1
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
     sample = args.cpu_sample
-    val, sec, threads = time_cpu(sample, args.steps, min(args.warmup, 1))
-    cb = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+    real = try_real_reference(sample, args.steps, min(args.warmup, 1))
+    kind = "reference" if real else "port"
+    val, sec, threads = real if real else time_cpu(sample, args.steps, min(args.warmup, 1))
+    cb = {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
           "sample": f"{sample} problems of the same cfg-2 workload per step (torch-CPU fp64 oracle port; JAX is not installed)"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
