@@ -622,3 +622,53 @@ def test_closed_loop_mpc_fused_vs_composed(dense_cost):
         assert relerr(uref[0, t], up[0]) < 1e-9
         xo = f(xo, uto + torch.as_tensor(up[0]))
     assert relerr(xref[0, -1], xo) < 1e-9
+
+
+def test_pytree_constructors_and_building_block_pipeline():
+    """The reference's building blocks composed by hand exactly as ilqrUtils.py:308-316 does (expansion pytrees from the
+    registered model/cost -> conditioning -> backward pass -> forwardPass2), against the oracle doing the same with autodiff."""
+    from zopt_b200 import ilqrUtils, pytrees
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    N = 12
+    rng = np.random.default_rng(17)
+    x0 = np.zeros(12)
+    x0[9:12] = [3.0, -2.0, 1.0]
+    Q, R, Qf = np.diag(rng.uniform(0.5, 2, 12)), np.diag(rng.uniform(0.5, 2, 4)), 10 * np.eye(12)
+    dyn, rc, tc = _oracle_fns(Q, R, Qf)
+    T = torch.as_tensor
+    # a trajectory to expand about: oracle rollout of the hover guess plus a perturbation
+    uG = np.tile(configs.U_TRIM, (N, 1)) + 0.3 * rng.normal(size=(N, 4))
+    otraj = oilqr.trajectoryRollout(T(x0), dyn, opt.AffinePolicy(T(uG), torch.zeros((N, 4, 12), dtype=torch.float64)),
+                                    opt.Trajectory(torch.zeros((N + 1, 12), dtype=torch.float64), torch.zeros((N, 4), dtype=torch.float64)))
+    model, cost = QuadcopterEuler(0.1), pytrees.CostFunction(QuadraticCost(Q, R), QuadraticTerminalCost(Qf))
+    traj = pytrees.Trajectory(cuda(otraj.xTraj.numpy()), cuda(otraj.uTraj.numpy()))
+    # expansions (pytrees.py:138-153, 179-194, 99-115, 71-81)
+    ad = pytrees.AffineDynamics.from_trajectory(model, traj)
+    qd = pytrees.QuadraticDynamics.from_trajectory(model, traj)
+    qc = pytrees.QuadraticCostFunction.from_trajectory(cost, traj)
+    Vf = pytrees.QuadraticValueFunction.fromTerminalCostFunction(cost, traj.xTraj[-1])
+    oad = opt.AffineDynamics.from_trajectory(dyn, otraj)
+    oqd = opt.QuadraticDynamics.from_trajectory(dyn, otraj)
+    ocost = opt.CostFunction(rc, tc)
+    oqc = opt.QuadraticCostFunction.from_trajectory(ocost, otraj)
+    oVf = opt.QuadraticValueFunction.fromTerminalCostFunction(ocost, otraj.xTraj[-1])
+    for got, ref in list(zip(ad, oad)) + list(zip(qd, oqd)) + list(zip(qc, oqc)) + list(zip(Vf, oVf)):
+        assert got.shape == ref.shape and relerr(got, ref) < 1e-11
+    assert abs(float(cost(traj)) - float(ocost(otraj))) < 1e-10 * float(ocost(otraj))   # CostFunction.__call__ (pytrees.py:40-55)
+    assert relerr(ad[3].f_x, oad[3].f_x) < 1e-11                                          # __getitem__ slices every leaf
+    # conditioning + backward pass + forward pass, iLQR and DDP
+    qcc, Vfc = ilqrUtils.conditionQuadraticCost(qc), ilqrUtils.conditionValueFunction(Vf)
+    oqcc, oVfc = oilqr.conditionQuadraticCost(oqc), oilqr.conditionValueFunction(oVf)
+    assert relerr(qcc.c_xx, oqcc.c_xx) < 1e-11 and relerr(Vfc.v_xx, oVfc.v_xx) < 1e-11
+    for second_order in (False, True):
+        if second_order:
+            pol, opol = ilqrUtils.backwardPass_ddp(qd, qcc, Vfc), oilqr.backwardPass_ddp(oqd, oqcc, oVfc)
+        else:
+            pol, opol = ilqrUtils.backwardPass_ilqr(ad, qcc, Vfc), oilqr.backwardPass_ilqr(oad, oqcc, oVfc)
+        assert relerr(pol.l, opol.l) < 1e-9 and relerr(pol.L, opol.L) < 1e-9
+        tn, Jn, idx, _ = ilqrUtils.forwardPass2(cuda(x0), model, cost, pol, traj, return_index=True)
+        otn, oJn, oidx, _ = oilqr.forwardPass2(T(x0), dyn, ocost, opol, otraj, return_all=True)
+        assert int(idx) == oidx and relerr(tn.xTraj, otn.xTraj) < 1e-9 and abs(float(Jn) - float(oJn)) < 1e-9 * float(oJn)
+    # unregistered callables are refused by the constructors too
+    with pytest.raises(TypeError):
+        pytrees.AffineDynamics.from_trajectory(lambda x, u: x + u, traj)
