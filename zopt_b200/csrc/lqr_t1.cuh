@@ -68,13 +68,15 @@ __device__ __forceinline__ void load_sym_lower(const float* g, float* v) {
 
 // One backward Riccati step for the problem owned by this thread: v (lower triangle of V) is updated in place and the
 // gain L = (R + B'VB)^-1 B'VA is returned in registers.  S = this lane's column of the shared-memory slab.
-template <bool QDIAG>
+// RS = row stride of the slab in float4 (32 lanes; 33 in the time-varying kernel, whose cooperative loads need the pad);
+// RFULL = R stored as four full rows (slots R4..R4+3) instead of the packed lower triangle.
+template <bool QDIAG, int RS = 32, bool RFULL = false>
 __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&L)[4][12]) {
     // ---- 1. [W | VB] = V [A | B] in four 12x4 panels.  ROLLED loop: one ~600-instruction body re-used four
     //         times keeps the step's code inside the instruction cache (the fully unrolled first version
     //         stalled 0.8 cycle/instruction on instruction fetch with one warp per scheduler).
     float G[10];
-    float4 xfirst = S[(X4 + 0) * 32];  // row 0 of the next panel, fetched before the previous panel's epilogue
+    float4 xfirst = S[(X4 + 0) * RS];  // row 0 of the next panel, fetched before the previous panel's epilogue
 #pragma unroll 1
     for (int p = 0; p < 4; ++p) {
         float acc[12][4];
@@ -84,7 +86,7 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
             for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
 #pragma unroll
         for (int kk = 0; kk < 12; ++kk) {
-            const float4 x4 = (kk == 0) ? xfirst : S[(X4 + kk * 4 + p) * 32];
+            const float4 x4 = (kk == 0) ? xfirst : S[(X4 + kk * 4 + p) * RS];
 #pragma unroll
             for (int i = 0; i < 12; ++i) {
                 const float vik = v[tri(i, kk)];
@@ -94,22 +96,28 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
                 acc[i][3] = fmaf(vik, x4.w, acc[i][3]);
             }
         }
-        xfirst = S[(X4 + ((p < 3) ? p + 1 : 0)) * 32];
+        xfirst = S[(X4 + ((p < 3) ? p + 1 : 0)) * RS];
         if (p < 3) {
 #pragma unroll
-            for (int i = 0; i < 12; ++i) S[(W4 + i * 3 + p) * 32] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            for (int i = 0; i < 12; ++i) S[(W4 + i * 3 + p) * RS] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         } else {  // acc = V B: G = R + B^T (V B), lower triangle
             if (QDIAG) {
-                const float4 rd = S[(Q4 + 3) * 32];
+                const float4 rd = S[(Q4 + 3) * RS];
                 G[0] = rd.x; G[1] = 0.f; G[2] = rd.y; G[3] = 0.f; G[4] = 0.f; G[5] = rd.z; G[6] = 0.f; G[7] = 0.f; G[8] = 0.f; G[9] = rd.w;
             } else {
-                const float4 r0 = S[(R4 + 0) * 32], r1 = S[(R4 + 1) * 32], r2 = S[(R4 + 2) * 32];
-                G[0] = r0.x; G[1] = r0.y; G[2] = r0.z; G[3] = r0.w; G[4] = r1.x;
-                G[5] = r1.y; G[6] = r1.z; G[7] = r1.w; G[8] = r2.x; G[9] = r2.y;
+                if (RFULL) {  // R as four full rows
+                    const float4 r0 = S[(R4 + 0) * RS], r1 = S[(R4 + 1) * RS], r2 = S[(R4 + 2) * RS], r3 = S[(R4 + 3) * RS];
+                    G[0] = r0.x; G[1] = r1.x; G[2] = r1.y; G[3] = r2.x; G[4] = r2.y;
+                    G[5] = r2.z; G[6] = r3.x; G[7] = r3.y; G[8] = r3.z; G[9] = r3.w;
+                } else {  // packed lower triangle
+                    const float4 r0 = S[(R4 + 0) * RS], r1 = S[(R4 + 1) * RS], r2 = S[(R4 + 2) * RS];
+                    G[0] = r0.x; G[1] = r0.y; G[2] = r0.z; G[3] = r0.w; G[4] = r1.x;
+                    G[5] = r1.y; G[6] = r1.z; G[7] = r1.w; G[8] = r2.x; G[9] = r2.y;
+                }
             }
 #pragma unroll
             for (int i = 0; i < 12; ++i) {
-                const float4 b4 = S[(X4 + i * 4 + 3) * 32];
+                const float4 b4 = S[(X4 + i * 4 + 3) * RS];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -128,7 +136,7 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
     // ---- 3a. V' (lower) = Q + A^T W and M = B^T W in one pass over the rows of A, W, B ------------------
     // (independent of the Cholesky chain above, so the scheduler can hide its latency behind these FMAs)
     if (QDIAG) {
-        const float4 q0 = S[(Q4 + 0) * 32], q1 = S[(Q4 + 1) * 32], q2 = S[(Q4 + 2) * 32];
+        const float4 q0 = S[(Q4 + 0) * RS], q1 = S[(Q4 + 1) * RS], q2 = S[(Q4 + 2) * RS];
         const float qd[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
         for (int i = 0; i < 12; ++i)
@@ -139,7 +147,7 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
         for (int i = 0; i < 12; ++i)
 #pragma unroll
             for (int c = 0; c <= i / 4; ++c) {
-                const float4 q = S[(Q4 + qoff(i) + c) * 32];
+                const float4 q = S[(Q4 + qoff(i) + c) * RS];
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                     if (4 * c + e <= i) v[tri(i, 4 * c + e)] = ZB_F4(q, e);
@@ -153,8 +161,8 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
     {
         float4 ra[3], rw[3], rb;  // rows kk of A, W, B; next rows are fetched while the current ones are consumed
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + c) * 32]; rw[c] = S[(W4 + c) * 32]; }
-        rb = S[(X4 + 3) * 32];
+        for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + c) * RS]; rw[c] = S[(W4 + c) * RS]; }
+        rb = S[(X4 + 3) * RS];
 #pragma unroll 1
         for (int kk = 0; kk < 12; ++kk) {
             const float a[12] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w, ra[1].x, ra[1].y, ra[1].z, ra[1].w, ra[2].x, ra[2].y, ra[2].z, ra[2].w};
@@ -162,8 +170,8 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
             const float4 b4 = rb;
             const int kn = (kk < 11) ? kk + 1 : 11;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + kn * 4 + c) * 32]; rw[c] = S[(W4 + kn * 3 + c) * 32]; }
-            rb = S[(X4 + kn * 4 + 3) * 32];
+            for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + kn * 4 + c) * RS]; rw[c] = S[(W4 + kn * 3 + c) * RS]; }
+            rb = S[(X4 + kn * 4 + 3) * RS];
 #pragma unroll
             for (int i = 0; i < 12; ++i)
 #pragma unroll
@@ -276,6 +284,7 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
         } else {
             // public layout (Bsz,N,4,12): transpose through smem (the W region is free now) for coalesced stores
             float4* stg = sm + W4 * 32;
+            __syncwarp();  // every lane is done reading its W slots before the region is reused for staging
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -374,6 +383,91 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------
+// Time-varying discreteFiniteHorizonLqr (zopt/lqrUtils.py:144-173 with genuinely different A[k], B[k], Q[k], R[k]), fp32,
+// (12,4).  Same per-thread step; the step's operands are STREAMED from HBM: the warp copies the 32 problems' blocks with
+// coalesced 128-bit loads (consecutive lanes = consecutive 16 B of one problem's block) into the lane-interleaved slab,
+// whose rows are padded to 33 float4 so that both the transposing store (stride 33) and the per-thread reads (stride 1)
+// are bank-conflict free.  1,408 B per problem-step: this path is HBM / LSU bound, not FMA bound.
+constexpr int RS_TV = 33;
+constexpr int NF4_TV = 112;  // X 48 + W 36 + Q 24 + R 4 (full rows)
+
+__device__ __forceinline__ void cp_async16(float4* dst_smem, const float4* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
+
+// all 88 float4 per problem of step k are put in flight with cp.async (no registers, one HBM latency per step instead of
+// one per dependent load batch), transposed on the fly into the padded lane-interleaved slab
+__device__ __forceinline__ void tv_load_step(float4* sm, const FastP& P, long long b0, int k, int lane) {
+    // A: 36 float4 per problem -> slots X4 + r*4 + c ; B: 12 -> X4 + r*4 + 3 ; Q: 36 (upper chunks skipped) ; R: 4
+#pragma unroll 4
+    for (int it = 0; it < 36; ++it) {
+        const int i = it * 32 + lane, p = i / 36, j = i - p * 36, r = j / 3, c = j - r * 3;
+        long long pb = b0 + p;
+        if (pb >= P.Bsz) pb = P.Bsz - 1;
+        cp_async16(&sm[(X4 + r * 4 + c) * RS_TV + p], reinterpret_cast<const float4*>(P.A.at<float>(pb, k)) + j);
+        if (c <= r / 4) cp_async16(&sm[(Q4 + qoff(r) + c) * RS_TV + p], reinterpret_cast<const float4*>(P.Q.at<float>(pb, k)) + j);
+    }
+#pragma unroll 4
+    for (int it = 0; it < 12; ++it) {
+        const int i = it * 32 + lane, p = i / 12, j = i - p * 12;
+        long long pb = b0 + p;
+        if (pb >= P.Bsz) pb = P.Bsz - 1;
+        cp_async16(&sm[(X4 + j * 4 + 3) * RS_TV + p], reinterpret_cast<const float4*>(P.B.at<float>(pb, k)) + j);
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int i = it * 32 + lane, p = i / 4, j = i - p * 4;
+        long long pb = b0 + p;
+        if (pb >= P.Bsz) pb = P.Bsz - 1;
+        cp_async16(&sm[(R4 + j) * RS_TV + p], reinterpret_cast<const float4*>(P.R.at<float>(pb, k)) + j);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+__global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P) {
+    extern __shared__ float4 sm[];
+    const int lane = threadIdx.x;
+    const long long b0 = (long long)blockIdx.x * 32;
+    const long long b_raw = b0 + lane;
+    const bool active = b_raw < P.Bsz;
+    const long long b = active ? b_raw : P.Bsz - 1;
+    float4* S = sm + lane;
+    float v[78];
+    load_sym_lower(P.Q.at<float>(b, P.T - 1), v);  // lqrUtils.py:172: terminal value is Q[-1]
+    float* gpub = P.gains + b0 * (long long)P.N * 48;
+    for (int k = P.N - 1; k >= 0; --k) {
+        __syncwarp();  // everybody is done with the previous step's operands (and the staging area)
+        tv_load_step(sm, P, b0, k, lane);
+        __syncwarp();
+        float L[4][12];
+        riccati_step<false, RS_TV, true>(S, v, L);
+        float4* stg = sm + W4 * RS_TV;  // W region is free now: transpose the gains for coalesced stores
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                stg[lane * STG + a * 3 + c] = make_float4(L[a][4 * c], L[a][4 * c + 1], L[a][4 * c + 2], L[a][4 * c + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 12; ++r) {
+            const int idx = r * 32 + lane, pr = idx / 12, j4 = idx - pr * 12;
+            const float4 val = stg[pr * STG + j4];
+            if (b0 + pr < P.Bsz) *reinterpret_cast<float4*>(gpub + ((long long)pr * P.N + k) * 48 + j4 * 4) = val;
+        }
+    }
+    if (P.V0 && active) {
+        float* o = P.V0 + b * 144;
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int j = 0; j < 12; ++j) o[i * 12 + j] = v[tri(i, j)];
+    }
+}
 
 // -------------------------------------------------------------------------------------------------------------
 // Closed-loop LQR-MPC for the quadcopter (BASELINE cfg 3; the loop of demos/lqrMpc.py:42-47 with a nonlinear plant):
@@ -515,6 +609,15 @@ inline int32_t riccati_t1_launch(const FastP& F, cudaStream_t stream, bool cost_
     return cost_diagonal ? riccati_t1_launch_impl<MPC, true>(F, stream) : riccati_t1_launch_impl<MPC, false>(F, stream);
 }
 
+
+inline int32_t riccati_t1_tv_launch(const FastP& F, cudaStream_t stream) {
+    const size_t smem = (size_t)t1::NF4_TV * t1::RS_TV * sizeof(float4);
+    ZB_CUDA(cudaFuncSetAttribute(t1::k_riccati_t1_tv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((F.Bsz + 31) / 32);
+    t1::k_riccati_t1_tv<<<grid, 32, smem, stream>>>(F);
+    ZB_CUDA(cudaGetLastError());
+    return 0;
+}
 
 inline int32_t mpc_closed_loop_launch(const t1::ClosedLoopP& P, cudaStream_t stream, bool cost_diagonal) {
     const unsigned grid = (unsigned)((P.Bsz + 31) / 32);

@@ -396,6 +396,16 @@ int32_t zb_lqr_dfh(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int
     DeviceGuard g(device);
     ZB_CUDA(g.err);
     LqrP P{Bsz, N, T, n, m, to_arr(A), to_arr(B), to_arr(Q), to_arr(R), L_out, V0_out};
+    // genuinely time-varying (12,4) fp32 problems: streamed thread-per-problem kernel (lqr_t1.cuh)
+    if (dtype == ZB_F32 && n == 12 && m == 4 && N >= 2 && !lqr_fast_eligible(dtype, P) && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) &&
+        arr_ok(P.R) && aligned16(P.L) && (!P.V0 || aligned16(P.V0))) {
+        FastP F{};
+        F.Bsz = P.Bsz; F.N = P.N; F.T = P.T;
+        F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R;
+        F.gains = reinterpret_cast<float*>(P.L);
+        F.V0 = reinterpret_cast<float*>(P.V0);
+        return riccati_t1_tv_launch(F, (cudaStream_t)stream);
+    }
     if (lqr_fast_eligible(dtype, P)) {
         if (P.Q.st == 0 || P.N == 1) {  // fully time-invariant: thread-per-problem kernel (lqr_t1.cuh)
             FastP F{};
