@@ -1,0 +1,121 @@
+"""
+Out-of-bounds write check without compute-sanitizer (closed on this pool): every output and workspace buffer of the
+fast kernels is carved out of a larger allocation whose head and tail guard zones are filled with a sentinel; after
+the call through the raw C ABI the guards must be untouched.  Ragged batch sizes exercise the partial last CTA / warp.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from zopt_b200 import _lib, configs  # noqa: E402
+from zopt_b200._lib import View, ZbAdmmOpts, check, lib, ptr, stream_ptr  # noqa: E402
+
+GUARD = 4096  # elements
+SENT = 12345.0
+
+
+class Guarded:
+    def __init__(self, shape, dtype, dev):
+        n = int(np.prod(shape))
+        self.raw = torch.full((n + 2 * GUARD,), SENT, dtype=torch.float64, device=dev).to(dtype) if dtype != torch.uint8 \
+            else torch.full((n + 2 * GUARD,), 77, dtype=torch.uint8, device=dev)
+        self.sent = self.raw[0].clone()
+        self.t = self.raw[GUARD:GUARD + n].view(shape)
+
+    def ok(self):
+        return bool((self.raw[:GUARD] == self.sent).all()) and bool((self.raw[-GUARD:] == self.sent).all())
+
+
+def _cfg(Bsz, dev, dt=torch.float32):
+    from zopt_b200.quadcopter import Quadcopter
+    d = configs.cfg2(Bsz=Bsz)
+    xbar = torch.as_tensor(d["xbar"], dtype=dt, device=dev)
+    ubar = torch.as_tensor(d["ubar"], dtype=dt, device=dev)
+    A, B = Quadcopter().linearizeInertial(xbar, ubar, 0.1)
+    Q = torch.diag_embed(torch.as_tensor(d["qdiag"], dtype=dt, device=dev))
+    R = torch.diag_embed(torch.as_tensor(d["rdiag"], dtype=dt, device=dev))
+    return d, xbar, A, B, Q, R
+
+
+@pytest.mark.parametrize("Bsz", [1, 33, 77])
+@pytest.mark.parametrize("diag", [True, False])
+def test_mpc_and_closed_loop_guards(Bsz, diag):
+    dev = torch.device("cuda", 0)
+    f32 = torch.float32
+    d, xbar, A, B, Q, R = _cfg(Bsz, dev)
+    if not diag:
+        Q = Q + 0.01
+        R = R + 0.01
+    N = 17
+    Qf = (10 * Q).contiguous()
+    views = [View(t, 2, False, True) for t in (A, B, Q, R, Qf)]
+    inf = [View(torch.full((k,), s * float("inf"), dtype=f32, device=dev), 1, False, False) for k, s in ((12, -1), (12, 1), (4, -1), (4, 1))]
+    u0, xT, uT = Guarded((Bsz, 4), f32, dev), Guarded((Bsz, N + 1, 12), f32, dev), Guarded((Bsz, N, 4), f32, dev)
+    st, it = Guarded((Bsz,), torch.uint8, dev), Guarded((Bsz,), f32, dev)
+    wsb = lib.zb_mpc_workspace_bytes(0, Bsz, N, 12, 4)
+    ws = Guarded((wsb,), torch.uint8, dev)
+    opts = ZbAdmmOpts(4000, 25, 0.1, 1e-6, 1.6, 1e-3, 1e-3, 1e-4)
+    check(lib.zb_mpc_lqr_solve(0, 0, stream_ptr(dev), Bsz, N, 12, 4, *[v.ref() for v in views], *[v.ref() for v in inf],
+                               2 if diag else 0, ptr(xbar), C.byref(opts), ptr(u0.t), ptr(xT.t), ptr(uT.t), ptr(st.t), ptr(it.t),
+                               ptr(ws.t), wsb))
+    torch.cuda.synchronize()
+    assert all(g.ok() for g in (u0, xT, uT, st, it, ws))
+    assert torch.isfinite(xT.t).all() and torch.isfinite(uT.t).all() and (st.t == 0).all()
+    # closed loop
+    Ts = 5
+    xS, uS = Guarded((Bsz, Ts + 1, 12), f32, dev), Guarded((Bsz, Ts, 4), f32, dev)
+    ut = (C.c_double * 4)(*configs.U_TRIM)
+    x0 = xbar.clone()
+    x0[:, 9:12] *= 0.2
+    check(lib.zb_mpc_closed_loop_quad(0, 0, stream_ptr(dev), Bsz, N, Ts, 0.1, ut, views[2].ref(), views[3].ref(), views[4].ref(),
+                                      2 if diag else 0, ptr(x0), ptr(xS.t), ptr(uS.t)))
+    torch.cuda.synchronize()
+    assert xS.ok() and uS.ok() and torch.isfinite(xS.t).all()
+
+
+@pytest.mark.parametrize("Bsz", [1, 45])
+@pytest.mark.parametrize("mode", ["views", "q_series", "materialised"])
+def test_lqr_dfh_guards(Bsz, mode):
+    dev = torch.device("cuda", 0)
+    f32 = torch.float32
+    d, xbar, A, B, Q, R = _cfg(Bsz, dev)
+    N = 9
+    ex = lambda t: t[:, None].expand(-1, N, -1, -1)
+    Ak, Bk, Qk, Rk = ex(A), ex(B), ex(Q), ex(R)
+    if mode != "views":
+        Qk = Qk.contiguous()
+    if mode == "materialised":
+        Ak, Bk, Rk = Ak.contiguous(), Bk.contiguous(), Rk.contiguous()
+    views = [View(t, 2, True, True) for t in (Ak, Bk, Qk, Rk)]
+    L, V0 = Guarded((Bsz, N, 4, 12), f32, dev), Guarded((Bsz, 12, 12), f32, dev)
+    check(lib.zb_lqr_dfh(0, 0, stream_ptr(dev), Bsz, N, N, 12, 4, *[v.ref() for v in views], ptr(L.t), ptr(V0.t)))
+    torch.cuda.synchronize()
+    assert L.ok() and V0.ok() and torch.isfinite(L.t).all() and torch.isfinite(V0.t).all()
+
+
+@pytest.mark.parametrize("second_order", [0, 1])
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_ilqr_solve_guards(second_order, dt):
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost, cost_spec
+    dev = torch.device("cuda", 0)
+    Bsz, N, maxIter = 21, 11, 2
+    d = configs.cfg4(Bsz=Bsz, N=N)
+    x0 = torch.as_tensor(d["x0"], dtype=dt, device=dev)
+    uG = torch.as_tensor(d["uGuess"], dtype=dt, device=dev)[None].expand(Bsz, N, 4).contiguous()
+    mspec, _ = QuadcopterEuler(0.1).spec(dt, dev)
+    cspec, keep = cost_spec(QuadraticCost(d["Q"], d["R"]), QuadraticTerminalCost(d["Qf"]), dt, dev)
+    xT, uT, L = Guarded((Bsz, N + 1, 12), dt, dev), Guarded((Bsz, N, 4), dt, dev), Guarded((Bsz, N, 4, 12), dt, dev)
+    J, conv = Guarded((Bsz,), dt, dev), Guarded((Bsz,), torch.uint8, dev)
+    iters = torch.zeros((Bsz,), dtype=torch.int32, device=dev)
+    code = 0 if dt == torch.float32 else 1
+    wsb = lib.zb_ilqr_workspace_bytes(code, Bsz, N, 12, 4)
+    ws = Guarded((wsb,), torch.uint8, dev)
+    check(lib.zb_ilqr_solve(code, 0, stream_ptr(dev), Bsz, N, second_order | 2, C.byref(mspec), C.byref(cspec), ptr(x0), ptr(uG),
+                            maxIter, -1.0, ptr(xT.t), ptr(uT.t), ptr(L.t), ptr(J.t), ptr(conv.t), ptr(iters), None, None, ptr(ws.t), wsb))
+    torch.cuda.synchronize()
+    assert all(g.ok() for g in (xT, uT, L, J, conv, ws))
+    assert torch.isfinite(xT.t).all() and torch.isfinite(L.t).all() and (iters == maxIter).all()
