@@ -162,6 +162,8 @@ ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_
 #define ZB_MPC_BOUNDED 1   /* zb_mpc_lqr_solve */
 #define ZB_SECOND_ORDER 1  /* zb_ilqr_solve */
 #define ZB_COST_DIAGONAL 2 /* both */
+#define ZB_VARIANT_THREAD 4 /* zb_mpc_closed_loop_quad: force the thread-per-problem kernel */
+#define ZB_VARIANT_QUAD 8   /* zb_mpc_closed_loop_quad: force the 4-threads-per-problem kernel (default for small batches) */
 
 typedef struct zb_admm_opts {
     int32_t max_iter;   /* default 4000 */
@@ -185,7 +187,7 @@ ZB_API int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int
  * xSim_out (Bsz,Tsim+1,12), uSim_out (Bsz,Tsim,4) (deviation from u_trim).  Q,R,Qf: (12,12),(4,4),(12,12) blocks (symmetric). */
 ZB_API int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t Tsim, double dt,
                                 const double* u_trim /* host, 4 */, const zb_arr* Q, const zb_arr* R, const zb_arr* Qf,
-                                int32_t flags /* ZB_COST_DIAGONAL */, const void* x0, void* xSim_out, void* uSim_out);
+                                int32_t flags /* ZB_COST_DIAGONAL | ZB_VARIANT_* */, const void* x0, void* xSim_out, void* uSim_out);
 
 /* ---- roofline denominators: dependent-FMA throughput probe; returns achieved FLOP/s ------------ */
 ZB_API int32_t zb_peak_fma(int32_t dtype, int32_t device, double* flops_per_s_out, double* sm_clock_mhz_out);

@@ -71,10 +71,11 @@ def test_mpc_and_closed_loop_guards(Bsz, diag):
     ut = (C.c_double * 4)(*configs.U_TRIM)
     x0 = xbar.clone()
     x0[:, 9:12] *= 0.2
-    check(lib.zb_mpc_closed_loop_quad(0, 0, stream_ptr(dev), Bsz, N, Ts, 0.1, ut, views[2].ref(), views[3].ref(), views[4].ref(),
-                                      2 if diag else 0, ptr(x0), ptr(xS.t), ptr(uS.t)))
-    torch.cuda.synchronize()
-    assert xS.ok() and uS.ok() and torch.isfinite(xS.t).all()
+    for variant in (4, 8):  # thread-per-problem, quad
+        check(lib.zb_mpc_closed_loop_quad(0, 0, stream_ptr(dev), Bsz, N, Ts, 0.1, ut, views[2].ref(), views[3].ref(), views[4].ref(),
+                                          (2 if diag else 0) | variant, ptr(x0), ptr(xS.t), ptr(uS.t)))
+        torch.cuda.synchronize()
+        assert xS.ok() and uS.ok() and torch.isfinite(xS.t).all()
 
 
 @pytest.mark.parametrize("Bsz", [1, 45])

@@ -570,8 +570,9 @@ def test_fast_paths_fp32_time_invariant(dense_cost):
     assert (status == 0).all() and relerr(u, traj.uTraj[:, 0]) == 0
 
 
+@pytest.mark.parametrize("variant", ["thread", "quad"])
 @pytest.mark.parametrize("dense_cost", [False, True])
-def test_closed_loop_mpc_fused_vs_composed(dense_cost):
+def test_closed_loop_mpc_fused_vs_composed(dense_cost, variant):
     """BASELINE cfg 3 path: the fused fp32 closed-loop kernel against the same loop composed step by step in fp64 from
     the individually verified entry points (linearizeInertial -> lqrMpc.solve -> inertialDynamics), and against the
     oracle (autodiff linearisation + Riccati plan + oracle plant) for one problem."""
@@ -588,7 +589,7 @@ def test_closed_loop_mpc_fused_vs_composed(dense_cost):
     x0 = d["xbar"].copy()
     x0[:, 9:12] *= 0.2  # +-2 m offsets: the linearised controller keeps the nonlinear plant well inside |theta| < pi/2
     traj = quadcopterClosedLoopMpc(cuda(x0, torch.float32), cuda(Q, torch.float32), cuda(R, torch.float32), N, Tsim, dt=dt,
-                                   Qf=cuda(10 * Q, torch.float32))
+                                   Qf=cuda(10 * Q, torch.float32), variant=variant)
     assert traj.xTraj.shape == (Bsz, Tsim + 1, 12) and traj.uTraj.shape == (Bsz, Tsim, 4)
     # composed fp64 loop through the public API
     ac = Quadcopter()

@@ -6,6 +6,7 @@
 #include "lqr_fast.cuh"
 #include "ilqr_fast.cuh"
 #include "lqr_t1.cuh"
+#include "mpc_coop.cuh"
 
 using namespace zb;
 
@@ -732,6 +733,12 @@ int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int
     P.x0 = reinterpret_cast<const float*>(x0);
     P.xSim = reinterpret_cast<float*>(xSim_out);
     P.uSim = reinterpret_cast<float*>(uSim_out);
+    // small batches: the cooperative (4 threads per problem) variant shortens the sequential chain and fills more SMs
+    cudaDeviceProp prop;
+    ZB_CUDA(cudaGetDeviceProperties(&prop, device));
+    const bool dense_ok = arr_ok(to_arr(Q)) && arr_ok(to_arr(R)) && arr_ok(to_arr(Qf));
+    const bool want_quad = (flags & ZB_VARIANT_QUAD) || (!(flags & ZB_VARIANT_THREAD) && Bsz <= (int64_t)prop.multiProcessorCount * 56);  // measured crossover on B200: ~8-10 K problems
+    if (dense_ok && want_quad) return mpc_closed_loop_coop_launch(P, (cudaStream_t)stream);
     return mpc_closed_loop_launch(P, (cudaStream_t)stream, (flags & ZB_COST_DIAGONAL) != 0);
 }
 

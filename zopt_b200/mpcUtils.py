@@ -141,7 +141,7 @@ class lqrMpc():
         return STATUS[int(status[i])]
 
 
-def quadcopterClosedLoopMpc(x0, Q, R, N, Tsim, dt=0.1, Qf=None, uTrim=(9.807, 0.0, 0.0, 0.0)):
+def quadcopterClosedLoopMpc(x0, Q, R, N, Tsim, dt=0.1, Qf=None, uTrim=(9.807, 0.0, 0.0, 0.0), variant="auto"):
     """
     Receding-horizon LQR-MPC of the quadcopter in closed loop with the nonlinear plant (BASELINE cfg 3) -- the loop of
     demos/lqrMpc.py:42-47, batched and fused into one kernel: every simulation step re-linearises the Euler quadcopter at
@@ -151,6 +151,7 @@ def quadcopterClosedLoopMpc(x0, Q, R, N, Tsim, dt=0.1, Qf=None, uTrim=(9.807, 0.
 
     x0 (Bsz,12) or (12,); Q (12,12), R (4,4), Qf (12,12, default Q) optionally batched.
     Returns Trajectory(xTraj (Bsz,Tsim+1,12), uTraj (Bsz,Tsim,4)) with uTraj the deviation from uTrim.
+    `variant`: "auto" (4 threads per problem for small batches, one thread per problem otherwise), "thread", "quad".
     With finite bounds or in fp64, compose `Quadcopter.linearizeInertial`, `lqrMpc(...).solve` and
     `Quadcopter.inertialDynamics` step by step instead.
     """
@@ -168,5 +169,6 @@ def quadcopterClosedLoopMpc(x0, Q, R, N, Tsim, dt=0.1, Qf=None, uTrim=(9.807, 0.
     uS = torch.empty((Bsz, Tsim, 4), dtype=f32, device=device)
     ut = (C.c_double * 4)(*[float(v) for v in uTrim])
     check(lib.zb_mpc_closed_loop_quad(0, device.index, stream_ptr(device), Bsz, int(N), int(Tsim), float(dt), ut,
-                                      *[v.ref() for v in views], 2 if diag else 0, ptr(x0), ptr(xS), ptr(uS)))
+                                      *[v.ref() for v in views],
+                                      (2 if diag else 0) | {"auto": 0, "thread": 4, "quad": 8}[variant], ptr(x0), ptr(xS), ptr(uS)))
     return Trajectory(xS, uS) if batched else Trajectory(xS[0], uS[0])
