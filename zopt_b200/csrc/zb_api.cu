@@ -734,10 +734,10 @@ int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int
     P.xSim = reinterpret_cast<float*>(xSim_out);
     P.uSim = reinterpret_cast<float*>(uSim_out);
     // small batches: the cooperative (4 threads per problem) variant shortens the sequential chain and fills more SMs
-    cudaDeviceProp prop;
-    ZB_CUDA(cudaGetDeviceProperties(&prop, device));
+    int sm_count = 0;  // cudaDeviceGetAttribute is cheap; cudaGetDeviceProperties costs milliseconds per call
+    ZB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     const bool dense_ok = arr_ok(to_arr(Q)) && arr_ok(to_arr(R)) && arr_ok(to_arr(Qf));
-    const bool want_quad = (flags & ZB_VARIANT_QUAD) || (!(flags & ZB_VARIANT_THREAD) && Bsz <= (int64_t)prop.multiProcessorCount * 56);  // measured crossover on B200: ~8-10 K problems
+    const bool want_quad = (flags & ZB_VARIANT_QUAD) || (!(flags & ZB_VARIANT_THREAD) && Bsz <= (int64_t)sm_count * 56);  // measured crossover on B200: ~8-10 K problems
     if (dense_ok && want_quad) return mpc_closed_loop_coop_launch(P, (cudaStream_t)stream);
     return mpc_closed_loop_launch(P, (cudaStream_t)stream, (flags & ZB_COST_DIAGONAL) != 0);
 }
