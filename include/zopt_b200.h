@@ -180,6 +180,25 @@ ZB_API int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int
                          void* uTraj, int8_t* status_out, int32_t* iters_out, void* workspace,
                          size_t workspace_bytes);
 
+/* ---- lqrMpc with finite bounds, ONE problem definition for the whole batch, (n,m) = (12,4) ---------------------------
+ * The reference object `lqrMpc(A,B,Q,R,N,x_lb,x_ub,u_lb,u_ub,Qf)` builds the QP once (zopt/mpcUtils.py:14-59) and
+ * `solve(x0)` re-solves it per initial state (mpcUtils.py:61-81; receding-horizon loop demos/lqrMpc.py:42-47).  Here the
+ * problem definition is passed on the HOST (row-major fp64, converted to `dtype`; bounds may be +-inf) and travels to the
+ * kernel by value; only x0 and the outputs are device buffers (Bsz leading).  Same ADMM as zb_mpc_lqr_solve's bounded path
+ * with rho kept on the grid rho0 * 2^j, j = -12..12, whose LQ gains are tabulated once per problem definition:
+ *   zb_mpc_box_build_tables -> `tables` (device, zb_mpc_box_tables_bytes), valid for (A,B,Q,R,Qf,N,rho0,dtype);
+ *   zb_mpc_box_solve        -> any number of solves against them; opts->rho must equal the rho0 the tables were built with.
+ * Outputs and status codes as zb_mpc_lqr_solve. */
+ZB_API size_t zb_mpc_box_tables_bytes(int32_t dtype, int32_t N);
+ZB_API size_t zb_mpc_box_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N);
+ZB_API int32_t zb_mpc_box_build_tables(int32_t dtype, int32_t device, void* stream, int32_t N, const double* A /* host 12x12 */,
+                                const double* B /* host 12x4 */, const double* Q, const double* R, const double* Qf,
+                                double rho0, void* tables, size_t tables_bytes);
+ZB_API int32_t zb_mpc_box_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, const double* A, const double* B,
+                         const double* x_lb, const double* x_ub, const double* u_lb, const double* u_ub /* host */,
+                         const void* tables, const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj, void* uTraj,
+                         int8_t* status_out, int32_t* iters_out, void* workspace, size_t workspace_bytes);
+
 /* ---- closed-loop LQR-MPC of the quadcopter (BASELINE cfg 3; the receding-horizon loop of demos/lqrMpc.py:42-47 with a
  * nonlinear plant), fp32, bounds inactive.  Per simulation step t: A_t = I + dt dF/dx(x_t,u_trim), B = dt dF/du, a full
  * Riccati sweep of horizon N from Qf (zopt/mpcUtils.py:47-59 with infinite bounds), u_t = first move of the plan,

@@ -11,8 +11,11 @@ using std::sqrt;
 using std::sin;
 using std::cos;
 using std::fmax;
+using std::log2;
+using std::ldexp;
 #include "../../include/zopt_b200.h"
 #include "../../zopt_b200/csrc/zb_problems.cuh"
+#include "../../zopt_b200/csrc/mpc_box.cuh"
 
 using namespace zb;
 
@@ -222,5 +225,39 @@ EXPORT int hs_mpc_admm(int dtype, int64_t Bsz, int N, int n, int m, const zb_arr
     P.max_iter = max_iter; P.check_every = check_every; P.rho = rho; P.alpha = alpha;
     P.eps_abs = eps_abs; P.eps_rel = eps_rel; P.eps_inf = eps_inf;
     for (int64_t b = 0; b < Bsz; ++b) dtype ? admm_problem<double>(P, b) : admm_problem<float>(P, b);
+    return 0;
+}
+
+// host run of the shared-definition box-constrained lqrMpc kernel body (zopt_b200/csrc/mpc_box.cuh): tables + per-problem ADMM
+template <typename T>
+static void box_run(int64_t Bsz, int N, const double* A, const double* B, const double* Q, const double* R, const double* Qf,
+                    const double* xlb, const double* xub, const double* ulb, const double* uub, const void* x0, int max_iter,
+                    int check_every, double rho, double alpha, double eps_abs, double eps_rel, double eps_inf, void* u0,
+                    void* xTraj, void* uTraj, int8_t* status, int32_t* iters) {
+    box::Ops<T> O;
+    box::Costs<T> C;
+    for (int i = 0; i < 144; ++i) { O.A[i] = (T)A[i]; C.Q[i] = (T)Q[i]; C.Qf[i] = (T)Qf[i]; }
+    for (int i = 0; i < 48; ++i) O.B[i] = (T)B[i];
+    for (int i = 0; i < 16; ++i) C.R[i] = (T)R[i];
+    for (int i = 0; i < 12; ++i) { O.xlb[i] = (T)xlb[i]; O.xub[i] = (T)xub[i]; }
+    for (int i = 0; i < 4; ++i) { O.ulb[i] = (T)ulb[i]; O.uub[i] = (T)uub[i]; }
+    std::vector<T> tab(box::tab_elems(N)), ws(box::ws_elems(N, Bsz)), sm(592);
+    for (int lv = 0; lv < box::LEVELS; ++lv)
+        box::table_level<T>(O, C, N, (T)std::ldexp(rho, lv - box::LEVEL0), tab.data() + (long long)lv * N * box::TW, sm.data(), 0, 1, [] {});
+    box::Params<T> P{};
+    P.Bsz = Bsz; P.N = N;
+    P.x0 = (const T*)x0; P.u0 = (T*)u0; P.xTraj = (T*)xTraj; P.uTraj = (T*)uTraj; P.status = status; P.iters = iters;
+    P.ws = ws.data(); P.tab = tab.data();
+    P.max_iter = max_iter; P.check_every = check_every;
+    P.rho0 = (T)rho; P.alpha = (T)alpha; P.eps_abs = (T)eps_abs; P.eps_rel = (T)eps_rel; P.eps_inf = (T)eps_inf;
+    for (int64_t b = 0; b < Bsz; ++b) box::problem<T>(O, P, b);
+}
+
+EXPORT int hs_mpc_box(int dtype, int64_t Bsz, int N, const double* A, const double* B, const double* Q, const double* R,
+                      const double* Qf, const double* xlb, const double* xub, const double* ulb, const double* uub,
+                      const void* x0, int max_iter, int check_every, double rho, double alpha, double eps_abs, double eps_rel,
+                      double eps_inf, void* u0, void* xTraj, void* uTraj, int8_t* status, int32_t* iters) {
+    if (dtype) box_run<double>(Bsz, N, A, B, Q, R, Qf, xlb, xub, ulb, uub, x0, max_iter, check_every, rho, alpha, eps_abs, eps_rel, eps_inf, u0, xTraj, uTraj, status, iters);
+    else box_run<float>(Bsz, N, A, B, Q, R, Qf, xlb, xub, ulb, uub, x0, max_iter, check_every, rho, alpha, eps_abs, eps_rel, eps_inf, u0, xTraj, uTraj, status, iters);
     return 0;
 }

@@ -7,6 +7,7 @@
 #include "ilqr_fast.cuh"
 #include "lqr_t1.cuh"
 #include "mpc_coop.cuh"
+#include "mpc_box.cuh"
 
 using namespace zb;
 
@@ -714,6 +715,105 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
     ZB_DISPATCH(dtype, k_mpc_riccati, gen_grid(Bsz), GEN_THREADS, stream, P);
     return 0;
 }
+
+}  // extern "C"
+
+// ---- lqrMpc with finite bounds, one problem definition shared by the batch (mpc_box.cuh) ----------------------------
+template <typename T>
+static void box_fill_ops(box::Ops<T>& O, const double* A, const double* B, const double* xlb, const double* xub,
+                         const double* ulb, const double* uub) {
+    for (int i = 0; i < 144; ++i) O.A[i] = (T)A[i];
+    for (int i = 0; i < 48; ++i) O.B[i] = (T)B[i];
+    for (int i = 0; i < 12; ++i) { O.xlb[i] = xlb ? (T)xlb[i] : T(0); O.xub[i] = xub ? (T)xub[i] : T(0); }
+    for (int i = 0; i < 4; ++i) { O.ulb[i] = ulb ? (T)ulb[i] : T(0); O.uub[i] = uub ? (T)uub[i] : T(0); }
+}
+
+template <typename T>
+static int32_t box_build_tables(cudaStream_t s, int N, const double* A, const double* B, const double* Q, const double* R,
+                                const double* Qf, double rho0, void* tables) {
+    box::Ops<T> O;
+    box::Costs<T> C;
+    box_fill_ops<T>(O, A, B, nullptr, nullptr, nullptr, nullptr);
+    for (int i = 0; i < 144; ++i) { C.Q[i] = (T)Q[i]; C.Qf[i] = (T)Qf[i]; }
+    for (int i = 0; i < 16; ++i) C.R[i] = (T)R[i];
+    box::k_box_tables<T><<<box::LEVELS, 32, 0, s>>>(O, C, N, (T)rho0, reinterpret_cast<T*>(tables));
+    ZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int32_t box_solve(cudaStream_t s, int64_t Bsz, int N, const double* A, const double* B, const double* xlb,
+                         const double* xub, const double* ulb, const double* uub, const void* tables, const void* x0,
+                         const zb_admm_opts* opts, void* u0, void* xTraj, void* uTraj, int8_t* status, int32_t* iters,
+                         void* workspace) {
+    box::Ops<T> O;
+    box_fill_ops<T>(O, A, B, xlb, xub, ulb, uub);
+    box::Params<T> P{};
+    P.Bsz = Bsz; P.N = N;
+    P.x0 = reinterpret_cast<const T*>(x0);
+    P.u0 = reinterpret_cast<T*>(u0); P.xTraj = reinterpret_cast<T*>(xTraj); P.uTraj = reinterpret_cast<T*>(uTraj);
+    P.status = status; P.iters = iters;
+    P.ws = reinterpret_cast<T*>(workspace); P.tab = reinterpret_cast<const T*>(tables);
+    P.max_iter = opts && opts->max_iter > 0 ? opts->max_iter : 4000;
+    P.check_every = opts && opts->check_every > 0 ? opts->check_every : 25;
+    P.rho0 = (T)(opts && opts->rho > 0 ? opts->rho : 0.1);
+    P.alpha = (T)(opts && opts->alpha > 0 ? opts->alpha : 1.6);
+    P.eps_abs = (T)(opts && opts->eps_abs > 0 ? opts->eps_abs : 1e-3);
+    P.eps_rel = (T)(opts && opts->eps_rel > 0 ? opts->eps_rel : 1e-3);
+    P.eps_inf = (T)(opts && opts->eps_prim_inf > 0 ? opts->eps_prim_inf : 1e-4);
+    box::k_mpc_box<T><<<(unsigned)((Bsz + 31) / 32), 32, 0, s>>>(O, P);
+    ZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+size_t zb_mpc_box_tables_bytes(int32_t dtype, int32_t N) {
+    return align256((dtype == ZB_F64 ? 8 : 4) * (size_t)box::tab_elems(N));
+}
+
+size_t zb_mpc_box_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N) {
+    return align256((dtype == ZB_F64 ? 8 : 4) * (size_t)box::ws_elems(N, Bsz)) + 256;
+}
+
+int32_t zb_mpc_box_build_tables(int32_t dtype, int32_t device, void* stream, int32_t N, const double* A, const double* B,
+                                const double* Q, const double* R, const double* Qf, double rho0, void* tables,
+                                size_t tables_bytes) {
+    ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "dtype must be ZB_F32 or ZB_F64 (got %d)", dtype);
+    ZB_ARG(N >= 1, "N must be >= 1");
+    ZB_ARG(A && B && Q && R && Qf && tables, "NULL operand");
+    ZB_ARG(rho0 > 0, "rho0 must be positive");
+    ZB_ARG(tables_bytes >= zb_mpc_box_tables_bytes(dtype, N), "tables buffer too small: need %zu bytes, got %zu",
+           zb_mpc_box_tables_bytes(dtype, N), tables_bytes);
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    return dtype == ZB_F32 ? box_build_tables<float>((cudaStream_t)stream, N, A, B, Q, R, Qf, rho0, tables)
+                           : box_build_tables<double>((cudaStream_t)stream, N, A, B, Q, R, Qf, rho0, tables);
+}
+
+int32_t zb_mpc_box_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, const double* A, const double* B,
+                         const double* x_lb, const double* x_ub, const double* u_lb, const double* u_ub, const void* tables,
+                         const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj, void* uTraj, int8_t* status_out,
+                         int32_t* iters_out, void* workspace, size_t workspace_bytes) {
+    ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "dtype must be ZB_F32 or ZB_F64 (got %d)", dtype);
+    ZB_ARG(Bsz >= 0, "negative batch size");
+    if (Bsz == 0) return 0;
+    ZB_ARG(N >= 1, "N must be >= 1");
+    ZB_ARG(A && B && x_lb && x_ub && u_lb && u_ub && tables, "NULL operand");
+    ZB_ARG(x0 && u0_out && xTraj && uTraj && status_out, "NULL operand");
+    size_t need = zb_mpc_box_workspace_bytes(dtype, Bsz, N);
+    ZB_ARG(workspace && workspace_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    return dtype == ZB_F32 ? box_solve<float>((cudaStream_t)stream, Bsz, N, A, B, x_lb, x_ub, u_lb, u_ub, tables, x0, opts, u0_out,
+                                              xTraj, uTraj, status_out, iters_out, workspace)
+                           : box_solve<double>((cudaStream_t)stream, Bsz, N, A, B, x_lb, x_ub, u_lb, u_ub, tables, x0, opts, u0_out,
+                                               xTraj, uTraj, status_out, iters_out, workspace);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t Tsim, double dt,
                                 const double* u_trim, const zb_arr* Q, const zb_arr* R, const zb_arr* Qf, int32_t flags,

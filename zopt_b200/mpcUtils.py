@@ -96,11 +96,20 @@ class lqrMpc():
         # around the same Q, R, Qf (demos/lqrMpc.py:31 builds once; a re-linearising loop rebuilds) costs nothing.
         self.cost_diagonal = all(_is_diagonal(t) for t in (self.ops[2], self.ops[3], self.ops[4]))
         self.iters = None
+        # Finite bounds, (n,m) = (12,4), one problem definition for every x0 (the reference's usage: the QP is built once,
+        # mpcUtils.py:14-59, and re-solved per x0): the definition is kept on the host and handed to the kernel by value,
+        # the rho-grid gain tables are built at the first solve and reused (zb_mpc_box_*).
+        self._box = None
+        if self.bounded and (self.n, self.m) == (12, 4) and all(t.ndim == nd or t.shape[0] == 1 for t, nd in zip(self.ops, core)):
+            host = [np.ascontiguousarray(t.detach().to("cpu", torch.float64).numpy().reshape(t.shape[-nd:]))
+                    for t, nd in zip(self.ops, core)]
+            self._box = {"host": host, "tables": None, "rho0": None}
 
     def solve(self, x0, **kwargs):
         """
         Solve the MPC step at state x0 (zopt/mpcUtils.py:61-81).  Keyword arguments follow OSQP's names as passed through
         cvxpy in the reference demo (`eps_abs`, `eps_rel`, `max_iter`, `rho`, `sigma`, `alpha`); others are ignored.
+        `kernel="generic"` forces the one-thread-per-problem ADMM kernel where the shared-definition (12,4) kernel would run.
 
         Returns
         -------
@@ -122,12 +131,18 @@ class lqrMpc():
         uTraj = torch.empty((Bsz, N, m), dtype=dt, device=dev)
         status = torch.empty((Bsz,), dtype=torch.int8, device=dev)
         iters = torch.empty((Bsz,), dtype=torch.int32, device=dev)
-        wsb = lib.zb_mpc_workspace_bytes(dcode(dt), Bsz, N, n, m)
-        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         opts = ZbAdmmOpts(int(kwargs.get("max_iter", 4000)), int(kwargs.get("check_termination", 25)),
                           float(kwargs.get("rho", 0.1)), float(kwargs.get("sigma", 1e-6)), float(kwargs.get("alpha", 1.6)),
                           float(kwargs.get("eps_abs", 1e-3)), float(kwargs.get("eps_rel", 1e-3)),
                           float(kwargs.get("eps_prim_inf", 1e-4)))
+        if self._box is not None and kwargs.get("kernel", "auto") != "generic":
+            self._solve_box(x0, Bsz, opts, u0, xTraj, uTraj, status, iters)
+            self.iters = iters
+            if not batched:
+                return u0[0], Trajectory(xTraj[0], uTraj[0]), STATUS[int(status[0])]
+            return u0, Trajectory(xTraj, uTraj), status
+        wsb = lib.zb_mpc_workspace_bytes(dcode(dt), Bsz, N, n, m)
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         check(lib.zb_mpc_lqr_solve(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, n, m, *[v.ref() for v in self.views],
                                    (1 if self.bounded else 0) | (2 if self.cost_diagonal else 0), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
                                    ptr(iters), ptr(ws), wsb))
@@ -135,6 +150,23 @@ class lqrMpc():
         if not batched:
             return u0[0], Trajectory(xTraj[0], uTraj[0]), STATUS[int(status[0])]
         return u0, Trajectory(xTraj, uTraj), status
+
+    def _solve_box(self, x0, Bsz, opts, u0, xTraj, uTraj, status, iters):
+        """bounded (12,4) problem shared by the batch -> zb_mpc_box_solve (csrc/mpc_box.cuh)"""
+        dt, dev, N, box = self.dtype, self.device, self.N, self._box
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        A, B, Q, R, Qf, xlb, xub, ulb, uub = box["host"]
+        if box["tables"] is None or box["rho0"] != opts.rho:
+            tb = lib.zb_mpc_box_tables_bytes(dcode(dt), N)
+            tables = torch.empty((tb,), dtype=torch.uint8, device=dev)
+            check(lib.zb_mpc_box_build_tables(dcode(dt), dev.index, stream_ptr(dev), N, dp(A), dp(B), dp(Q), dp(R), dp(Qf),
+                                              opts.rho, ptr(tables), tb))
+            box["tables"], box["rho0"] = tables, opts.rho
+        wsb = lib.zb_mpc_box_workspace_bytes(dcode(dt), Bsz, N)
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+        check(lib.zb_mpc_box_solve(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, dp(A), dp(B), dp(xlb), dp(xub), dp(ulb), dp(uub),
+                                   ptr(box["tables"]), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
+                                   ptr(iters), ptr(ws), wsb))
 
     @staticmethod
     def status_str(status, i=0):
