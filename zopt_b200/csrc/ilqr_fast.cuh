@@ -88,48 +88,135 @@ __device__ __forceinline__ double rsq(double x) { return 1.0 / sqrt(x); }
 // matrix is distributed by rows (thread t holds rows t, t+4, t+8; row 8 only in thread 0).
 __host__ __device__ constexpr int tri9(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-template <typename T>
-__device__ __noinline__ void jacobi_cs(T app, T aqq, T apq, T& c, T& s, T& t) {
-    const T tau = (aqq - app) / (T(2) * apq);
-    t = (tau >= T(0) ? T(1) : T(-1)) / (fabs(tau) + sqrt(T(1) + tau * tau));
-    c = T(1) / sqrt(T(1) + t * t);
+// Rotation (c, s) that annihilates a_pq.  Only the ORTHOGONALITY of the rotation has to be exact to working precision
+// (A stays similar to the input whatever the angle); the angle itself only steers convergence.  So tan(theta) is formed
+// in fp32 from operands scaled by a power of two (no overflow / underflow whatever the magnitudes), with approximate
+// sqrt / reciprocal, and c = rsqrt(1 + t^2), s = t c are then computed at full precision.  An fp64 rotation costs ~35
+// instructions this way instead of the ~110 of three IEEE divisions and two square roots.
+__device__ __forceinline__ float approx_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float approx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+__device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, double& c, double& s) {
+    const double d = aqq - app, a2 = apq + apq;
+    const double mx = fmax(fabs(d), fabs(a2));
+    const int ex = __double2hiint(mx) & 0x7ff00000;
+    const double sc = __hiloint2double(0x7fe00000 - ex, 0);  // 2^(1023 - exponent(mx)): the larger operand lands in [1, 2)
+    const float df = (float)(d * sc), af = (float)(a2 * sc);
+    float tf = af * approx_rcp(fabsf(df) + approx_sqrt(fmaf(df, df, af * af)));  // = sgn(tau) / (|tau| + sqrt(1 + tau^2)), tau = d / a2
+    if (d < 0.0) tf = -tf;
+    const double t = (apq != 0.0) ? (double)tf : 0.0;
+    c = rsqrt(fma(t, t, 1.0));
+    s = t * c;
+}
+__device__ __forceinline__ void jacobi_cs(float app, float aqq, float apq, float& c, float& s) {
+    const float d = aqq - app, a2 = apq + apq;
+    const float mx = fmaxf(fabsf(d), fabsf(a2));
+    const int ex = __float_as_int(mx) & 0x7f800000;
+    const float sc = __int_as_float(0x7e800000 - ex);  // 2^(126 - exponent(mx))
+    const float df = d * sc, af = a2 * sc;
+    float tf = af * approx_rcp(fabsf(df) + approx_sqrt(fmaf(df, df, af * af)));
+    if (d < 0.0f) tf = -tf;
+    const float t = (apq != 0.0f) ? tf : 0.0f;
+    c = 1.0f / sqrtf(fmaf(t, t, 1.0f));
     s = t * c;
 }
 
+// apply the (PP,QQ) rotation [[c, s], [-s, c]] (columns p' = c p - s q, q' = s p + c q) to the replicated packed matrix and
+// to this thread's eigenvector rows.  The 2x2 block uses the general formulas: a_pq does not vanish exactly because tan
+// was approximate -- it shrinks by ~1e-7 per visit, and quadratically once small, like the exact rotation.
 template <typename T, int PP, int QQ>
-__device__ __forceinline__ void jacobi_rot(T (&A)[45], T (&Wr)[3][9]) {
-    const T apq = A[tri9(QQ, PP)];
-    if (apq != T(0)) {
-        T c, s, t;
-        jacobi_cs<T>(A[tri9(PP, PP)], A[tri9(QQ, QQ)], apq, c, s, t);
+__device__ __forceinline__ void jacobi_apply(T (&A)[45], T (&Wr)[3][9], T c, T s) {
+    const T app = A[tri9(PP, PP)], aqq = A[tri9(QQ, QQ)], apq = A[tri9(QQ, PP)];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (k != PP && k != QQ) {
-                const T akp = A[tri9(k, PP)], akq = A[tri9(k, QQ)];
-                A[tri9(k, PP)] = c * akp - s * akq;
-                A[tri9(k, QQ)] = s * akp + c * akq;
-            }
+    for (int k = 0; k < 9; ++k) {
+        if (k != PP && k != QQ) {
+            const T akp = A[tri9(k, PP)], akq = A[tri9(k, QQ)];
+            A[tri9(k, PP)] = c * akp - s * akq;
+            A[tri9(k, QQ)] = s * akp + c * akq;
         }
-        A[tri9(PP, PP)] -= t * apq;
-        A[tri9(QQ, QQ)] += t * apq;
-        A[tri9(QQ, PP)] = T(0);
+    }
+    const T cc = c * c, ss = s * s, cs = c * s;
+    const T x2 = (cs + cs) * apq;
+    const T npp = fma(cc, app, fma(ss, aqq, -x2)), nqq = fma(ss, app, fma(cc, aqq, x2));
+    const T npq = fma(cs, app - aqq, (cc - ss) * apq);
+    A[tri9(PP, PP)] = npp;
+    A[tri9(QQ, QQ)] = nqq;
+    // rounding noise of the annihilated entry is dropped (a perturbation below one ulp of the diagonal), so a converged
+    // matrix has exact zeros and the sweep loop terminates on its off-diagonal test
+    const T tiny = (sizeof(T) == 8 ? T(8.9e-16) : T(4.8e-7)) * (fabs(npp) + fabs(nqq));
+    A[tri9(QQ, PP)] = fabs(npq) <= tiny ? T(0) : npq;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const T wp = Wr[r][PP], wq = Wr[r][QQ];
-            Wr[r][PP] = c * wp - s * wq;
-            Wr[r][QQ] = s * wp + c * wq;
-        }
+    for (int r = 0; r < 3; ++r) {
+        const T wp = Wr[r][PP], wq = Wr[r][QQ];
+        Wr[r][PP] = c * wp - s * wq;
+        Wr[r][QQ] = s * wp + c * wq;
     }
 }
 
-template <typename T, int PP, int QQ>
-struct JacobiSweep {
-    static __device__ __forceinline__ void run(T (&A)[45], T (&Wr)[3][9]) {
-        jacobi_rot<T, PP, QQ>(A, Wr);
-        if constexpr (QQ < 8) JacobiSweep<T, PP, QQ + 1>::run(A, Wr);
-        else if constexpr (PP < 7) JacobiSweep<T, PP + 1, PP + 2>::run(A, Wr);
-    }
-};
+// Round-robin (tournament) ordering of the 36 pairs of a 9x9 sweep: 9 rounds of 4 DISJOINT pairs.  Disjoint rotations
+// commute in their (c, s): each of the quad's four threads computes ONE of them from the replicated matrix, the four
+// (c, s) go through shared memory, then every thread applies all four.
+// Brent-Luk form: the rotated pairs always sit at POSITIONS (0,1), (2,3), (4,5), (6,7) (position 8 idles) and the indices
+// move one step around the ring 0>2>4>6>8>7>5>3>1>0 after every round, so ONE block of code serves all rounds.  Three
+// rounds are unrolled (the two intermediate moves are compile-time renamings), then the registers are permuted once:
+// the loop body is ~1,100 instructions (fits the 32 KB instruction cache) instead of ~2,900 for a fully unrolled sweep,
+// which spent 42 % of its stall samples waiting for instruction fetch.  V max(L,eps) V' does not depend on the order of
+// the eigenpairs, so the accumulated permutation never has to be undone.
+__host__ __device__ constexpr int rr_src(int p) {  // content of position p after a move = content of position rr_src(p) before
+    constexpr int src[9] = {1, 3, 0, 5, 2, 7, 4, 8, 6};
+    return src[p];
+}
+__host__ __device__ constexpr int rr_slot(int j, int p) {  // register slot that holds logical position p after j moves
+    for (int i = 0; i < j; ++i) p = rr_src(p);
+    return p;
+}
+__device__ __forceinline__ void st_cs(double* p, double c, double s) { *reinterpret_cast<double2*>(p) = make_double2(c, s); }
+__device__ __forceinline__ void st_cs(float* p, float c, float s) { *reinterpret_cast<float2*>(p) = make_float2(c, s); }
+__device__ __forceinline__ void ld_cs(const double* p, double& c, double& s) { const double2 v = *reinterpret_cast<const double2*>(p); c = v.x; s = v.y; }
+__device__ __forceinline__ void ld_cs(const float* p, float& c, float& s) { const float2 v = *reinterpret_cast<const float2*>(p); c = v.x; s = v.y; }
+
+template <typename T, int J>
+__device__ __forceinline__ void jacobi_round(T (&A)[45], T (&Wr)[3][9], T* buf /* 8 words, this quad, this round parity */, int t, unsigned qmask) {
+    constexpr int p1 = rr_slot(J, 0), q1 = rr_slot(J, 1), p2 = rr_slot(J, 2), q2 = rr_slot(J, 3);
+    constexpr int p3 = rr_slot(J, 4), q3 = rr_slot(J, 5), p4 = rr_slot(J, 6), q4 = rr_slot(J, 7);
+    const T app = t == 0 ? A[tri9(p1, p1)] : t == 1 ? A[tri9(p2, p2)] : t == 2 ? A[tri9(p3, p3)] : A[tri9(p4, p4)];
+    const T aqq = t == 0 ? A[tri9(q1, q1)] : t == 1 ? A[tri9(q2, q2)] : t == 2 ? A[tri9(q3, q3)] : A[tri9(q4, q4)];
+    const T apq = t == 0 ? A[tri9(q1, p1)] : t == 1 ? A[tri9(q2, p2)] : t == 2 ? A[tri9(q3, p3)] : A[tri9(q4, p4)];
+    T c, s;
+    jacobi_cs(app, aqq, apq, c, s);
+    st_cs(buf + 2 * t, c, s);
+    __syncwarp(qmask);
+    T c1, s1, c2, s2, c3, s3, c4, s4;
+    ld_cs(buf, c1, s1); ld_cs(buf + 2, c2, s2); ld_cs(buf + 4, c3, s3); ld_cs(buf + 6, c4, s4);
+    jacobi_apply<T, p1, q1>(A, Wr, c1, s1);
+    jacobi_apply<T, p2, q2>(A, Wr, c2, s2);
+    jacobi_apply<T, p3, q3>(A, Wr, c3, s3);
+    jacobi_apply<T, p4, q4>(A, Wr, c4, s4);
+}
+
+// three rounds + the register permutation that brings the positions back to slots 0..8
+template <typename T>
+__device__ __forceinline__ void jacobi_group(T (&A)[45], T (&Wr)[3][9], T* csbuf, int& par, int t, unsigned qmask) {
+    jacobi_round<T, 0>(A, Wr, csbuf + par * 8, t, qmask);
+    jacobi_round<T, 1>(A, Wr, csbuf + (par ^ 1) * 8, t, qmask);  // alternate buffers: a round's stores never race the previous round's loads
+    jacobi_round<T, 2>(A, Wr, csbuf + par * 8, t, qmask);
+    par ^= 1;
+    T B[45], Wn[3][9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) B[tri9(i, j)] = A[tri9(rr_slot(3, i), rr_slot(3, j))];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) Wn[r][j] = Wr[r][rr_slot(3, j)];
+#pragma unroll
+    for (int e = 0; e < 45; ++e) A[e] = B[e];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) Wr[r][j] = Wn[r][j];
+}
 
 template <typename T, bool CDIAG, bool DDP>
 __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
@@ -266,6 +353,9 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                 for (int r = 0; r < 3; ++r)
 #pragma unroll
                     for (int c = 0; c < 9; ++c) Wr[r][c] = (c == t + 4 * r) ? T(1) : T(0);  // rows t, t+4, t+8 of I
+                T* csbuf = Pc;  // 16 words of the (not yet rewritten) clamped-block region carry the rotations of a round
+                const unsigned qmask = 0xFu << (lane & 28);
+                int par = 0;
                 for (int sweep = 0; sweep < 30; ++sweep) {
                     T off = T(0), dg = T(0);
 #pragma unroll
@@ -276,7 +366,8 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                     }
                     const T thr = (sizeof(T) == 8) ? T(1e-32) : T(1e-15), tiny = (sizeof(T) == 8) ? T(1e-300) : T(1e-37);
                     if (off <= thr * dg || off < tiny) break;
-                    JacobiSweep<T, 0, 1>::run(A9, Wr);
+#pragma unroll 1
+                    for (int g = 0; g < 3; ++g) jacobi_group<T>(A9, Wr, csbuf, par, t, qmask);
                 }
                 // exchange eigenvector rows, then P9 = W max(Lambda, eps) W^T, rows t, t+4, t+8 per thread
                 const T eps = T(P.eps);
