@@ -199,6 +199,18 @@ ZB_API int32_t zb_mpc_box_solve(int32_t dtype, int32_t device, void* stream, int
                          const void* tables, const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj, void* uTraj,
                          int8_t* status_out, int32_t* iters_out, void* workspace, size_t workspace_bytes);
 
+/* The receding-horizon loop of demos/lqrMpc.py:42-47 around that problem, fused into one kernel: every simulation step clips
+ * the state into [x_lb + clip_margin, x_ub - clip_margin] (demo: 1e-6; the QP constrains x_0 too), solves from it warm-started
+ * with the previous step's ADMM state (cvxpy re-solves warm), applies the first move and continues from the plan's own next
+ * state ("assume perfect tracking").  xSim_out (Bsz,Tsim+1,12): the states the solves started from + the final state;
+ * uSim_out (Bsz,Tsim,4); status_out (Bsz): worst status over the steps (an infeasible step ends that problem's loop, NaN
+ * afterwards); iters_out (Bsz): total ADMM iterations. */
+ZB_API size_t zb_mpc_box_closed_loop_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N);
+ZB_API int32_t zb_mpc_box_closed_loop(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t Tsim, const double* A,
+                               const double* B, const double* x_lb, const double* x_ub, const double* u_lb, const double* u_ub,
+                               const void* tables, const void* x0, const zb_admm_opts* opts, double clip_margin, void* xSim_out,
+                               void* uSim_out, int8_t* status_out, int32_t* iters_out, void* workspace, size_t workspace_bytes);
+
 /* ---- closed-loop LQR-MPC of the quadcopter (BASELINE cfg 3; the receding-horizon loop of demos/lqrMpc.py:42-47 with a
  * nonlinear plant), fp32, bounds inactive.  Per simulation step t: A_t = I + dt dF/dx(x_t,u_trim), B = dt dF/du, a full
  * Riccati sweep of horizon N from Qf (zopt/mpcUtils.py:47-59 with infinite bounds), u_t = first move of the plan,

@@ -233,7 +233,8 @@ template <typename T>
 static void box_run(int64_t Bsz, int N, const double* A, const double* B, const double* Q, const double* R, const double* Qf,
                     const double* xlb, const double* xub, const double* ulb, const double* uub, const void* x0, int max_iter,
                     int check_every, double rho, double alpha, double eps_abs, double eps_rel, double eps_inf, void* u0,
-                    void* xTraj, void* uTraj, int8_t* status, int32_t* iters) {
+                    void* xTraj, void* uTraj, int8_t* status, int32_t* iters, int Tsim = -1, void* xSim = nullptr,
+                    void* uSim = nullptr, double clip = 0) {
     box::Ops<T> O;
     box::Costs<T> C;
     for (int i = 0; i < 144; ++i) { O.A[i] = (T)A[i]; C.Q[i] = (T)Q[i]; C.Qf[i] = (T)Qf[i]; }
@@ -250,7 +251,12 @@ static void box_run(int64_t Bsz, int N, const double* A, const double* B, const 
     P.ws = ws.data(); P.tab = tab.data();
     P.max_iter = max_iter; P.check_every = check_every;
     P.rho0 = (T)rho; P.alpha = (T)alpha; P.eps_abs = (T)eps_abs; P.eps_rel = (T)eps_rel; P.eps_inf = (T)eps_inf;
-    for (int64_t b = 0; b < Bsz; ++b) box::problem<T>(O, P, b);
+    if (Tsim >= 0) {
+        P.Tsim = Tsim; P.xSim = (T*)xSim; P.uSim = (T*)uSim; P.clip_margin = (T)clip;
+        for (int64_t b = 0; b < Bsz; ++b) box::closed_loop_problem<T>(O, P, b);
+    } else {
+        for (int64_t b = 0; b < Bsz; ++b) box::problem<T>(O, P, b);
+    }
 }
 
 EXPORT int hs_mpc_box(int dtype, int64_t Bsz, int N, const double* A, const double* B, const double* Q, const double* R,
@@ -259,5 +265,20 @@ EXPORT int hs_mpc_box(int dtype, int64_t Bsz, int N, const double* A, const doub
                       double eps_inf, void* u0, void* xTraj, void* uTraj, int8_t* status, int32_t* iters) {
     if (dtype) box_run<double>(Bsz, N, A, B, Q, R, Qf, xlb, xub, ulb, uub, x0, max_iter, check_every, rho, alpha, eps_abs, eps_rel, eps_inf, u0, xTraj, uTraj, status, iters);
     else box_run<float>(Bsz, N, A, B, Q, R, Qf, xlb, xub, ulb, uub, x0, max_iter, check_every, rho, alpha, eps_abs, eps_rel, eps_inf, u0, xTraj, uTraj, status, iters);
+    return 0;
+}
+
+EXPORT int hs_mpc_box_closed_loop(int dtype, int64_t Bsz, int N, int Tsim, const double* A, const double* B, const double* Q,
+                                  const double* R, const double* Qf, const double* xlb, const double* xub, const double* ulb,
+                                  const double* uub, const void* x0, int max_iter, int check_every, double rho, double alpha,
+                                  double eps_abs, double eps_rel, double eps_inf, double clip, void* xSim, void* uSim,
+                                  int8_t* status, int32_t* iters) {
+    if (dtype) {
+        std::vector<double> px((size_t)Bsz * (N + 1) * 12), pu((size_t)Bsz * N * 4);
+        box_run<double>(Bsz, N, A, B, Q, R, Qf, xlb, xub, ulb, uub, x0, max_iter, check_every, rho, alpha, eps_abs, eps_rel, eps_inf, nullptr, px.data(), pu.data(), status, iters, Tsim, xSim, uSim, clip);
+    } else {
+        std::vector<float> px((size_t)Bsz * (N + 1) * 12), pu((size_t)Bsz * N * 4);
+        box_run<float>(Bsz, N, A, B, Q, R, Qf, xlb, xub, ulb, uub, x0, max_iter, check_every, rho, alpha, eps_abs, eps_rel, eps_inf, nullptr, px.data(), pu.data(), status, iters, Tsim, xSim, uSim, clip);
+    }
     return 0;
 }

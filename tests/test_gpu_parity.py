@@ -582,6 +582,38 @@ def test_lqrMpc_box_kernel_vs_generic_and_oracle(dt):
     assert (status3 == 0).all() and relerr(traj3.uTraj, traj.uTraj[ok]) < tol
 
 
+def test_lqrMpc_box_closed_loop_vs_composed():
+    """fused receding-horizon loop (demos/lqrMpc.py:42-47, zb_mpc_box_closed_loop, shifted warm starts) against the same loop
+    composed from solve() calls (cold starts) and against the host build of the same kernel body"""
+    from tests.test_mpc_oracle_and_hostsim import run_box_closed_loop
+    from zopt_b200.mpcUtils import lqrMpc
+    A, B, Q, R, N, xlb, xub, ulb, uub = _mpc_demo()
+    rng = np.random.default_rng(5)
+    Bsz, Tsim = 37, 8
+    x0 = np.zeros((Bsz, 12))
+    x0[:, 9:12] = rng.uniform(-10, 10, (Bsz, 3))
+    prob = lqrMpc(A, B, Q, R, N, xlb, xub, ulb, uub)
+    kw = dict(eps_abs=1e-5, eps_rel=1e-5, max_iter=20000)
+    traj, status = prob.closedLoop(cuda(x0), Tsim, **kw)
+    assert (status == 0).all() and traj.xTraj.shape == (Bsz, Tsim + 1, 12) and traj.uTraj.shape == (Bsz, Tsim, 4)
+    lo, hi = cuda(xlb + 1e-6), cuda(xub - 1e-6)
+    x = cuda(x0)
+    for t in range(Tsim):
+        x = torch.minimum(torch.maximum(x, lo), hi)
+        assert relerr(traj.xTraj[:, t], x) < 2e-4
+        u, plan, st = prob.solve(x, **kw)
+        assert (st == 0).all()
+        assert float((traj.uTraj[:, t] - u).abs().max()) < 5e-3 * max(1.0, float(u.abs().max()))
+        x = plan.xTraj[:, 1]
+    # same arithmetic on the host (identical iterates up to rounding: the iteration counts agree)
+    xS, uS, st_h, it_h = run_box_closed_loop(A, B, Q, R, N, xlb, xub, ulb, uub, x0[:5], Tsim, **kw)
+    assert relerr(traj.uTraj[:5], uS) < 1e-6 and np.array_equal(prob.iters[:5].cpu().numpy(), it_h)
+    # fp32 at the demo's tolerance, un-batched call
+    p32 = lqrMpc(*(cuda(t, torch.float32) for t in (A, B, Q, R)), N, xlb, xub, ulb, uub)
+    tr32, st32 = p32.closedLoop(cuda(x0[0], torch.float32), 20, eps_abs=1e-2, eps_rel=1e-2)
+    assert st32 == "optimal" and tr32.xTraj.shape == (21, 12) and bool(torch.isfinite(tr32.uTraj).all())
+
+
 @pytest.mark.parametrize("dense_cost", [False, True])
 def test_fast_paths_fp32_time_invariant(dense_cost):
     """fp32 (12,4) thread-per-problem kernel (lqr_t1.cuh): diagonal-cost and dense-cost variants, through

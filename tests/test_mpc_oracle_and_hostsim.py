@@ -218,3 +218,49 @@ def test_box_body_fp32_and_certificate():
     u0, xT, uT, status, iters = run_box(A, B, Q, R, N, xlb2, xub2, ulb2, uub2, x0c)
     ug, xg, uug, sg, ig = run_admm(A, B, Q, R, N, xlb2, xub2, ulb2, uub2, x0c)
     assert st_or == "infeasible" and sg[0] == 2 and status[0] == 2 and np.isnan(uT).all()
+
+
+def run_box_closed_loop(A, B, Q, R, N, xlb, xub, ulb, uub, x0, Tsim, clip=1e-6, dt=np.float64, **kw):
+    x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=dt)))
+    Bsz = x0.shape[0]
+    host = [np.ascontiguousarray(a, dtype=np.float64) for a in (A, B, Q, R, Q, xlb, xub, ulb, uub)]
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    xS, uS = np.zeros((Bsz, Tsim + 1, 12), dtype=dt), np.zeros((Bsz, Tsim, 4), dtype=dt)
+    status, iters = np.zeros(Bsz, dtype=np.int8), np.zeros(Bsz, dtype=np.int32)
+    H.hs.hs_mpc_box_closed_loop(int(dt == np.float64), C.c_int64(Bsz), N, Tsim, *[dp(a) for a in host], H.P(x0),
+                                int(kw.get("max_iter", 4000)), int(kw.get("check_every", 25)), C.c_double(kw.get("rho", 0.1)),
+                                C.c_double(kw.get("alpha", 1.6)), C.c_double(kw.get("eps_abs", 1e-3)),
+                                C.c_double(kw.get("eps_rel", 1e-3)), C.c_double(kw.get("eps_inf", 1e-4)), C.c_double(clip),
+                                H.P(xS), H.P(uS), H.P(status), H.P(iters))
+    return xS, uS, status, iters
+
+
+def test_box_closed_loop_body_vs_oracle_loop():
+    """demos/lqrMpc.py:42-47 (clip, solve, x = traj.xTraj[1]) with the oracle QP solver at every step vs the fused warm-started
+    loop of the kernel body; the shifted warm start must also cut the ADMM iteration count well below cold re-solves"""
+    A, B, Q, R, N, xlb, xub, ulb, uub = demo_problem()
+    x0 = np.zeros((2, 12))
+    x0[0, 9:12] = [10, 10, 10]  # the demo's initial state
+    x0[1, 9:12] = [-4, 6, -2]
+    Tsim = 6
+    # ADMM converges sub-linearly on this degenerate problem (the velocity bound is active with the state clipped onto it),
+    # so the comparison runs at eps 1e-5 with matching gates
+    xS, uS, status, iters = run_box_closed_loop(A, B, Q, R, N, xlb, xub, ulb, uub, x0, Tsim, eps_abs=1e-5, eps_rel=1e-5, max_iter=20000)
+    assert (status == 0).all()
+    for b in range(2):
+        x = x0[b].copy()
+        for t in range(Tsim):
+            x = np.clip(x, xlb + 1e-6, xub - 1e-6)
+            assert np.max(np.abs(xS[b, t] - x)) < 2e-3
+            u0, xr, ur, st, info = ompc.solve_qp(A, B, Q, R, N, xlb, xub, ulb, uub, x)
+            assert st == "optimal"
+            assert np.max(np.abs(uS[b, t] - u0)) < 5e-3 * max(1.0, np.max(np.abs(u0)))
+            x = xr[1]
+        assert np.max(np.abs(xS[b, Tsim] - x)) < 2e-3
+    # the simulated states satisfy the (linear, perfectly tracked) plant up to the clip margin
+    assert np.max(np.abs(xS[:, 1:] - (xS[:, :-1] @ A.T + uS @ B.T))) < 5e-5  # the plan may overshoot a bound by ~eps before the clip
+    # OSQP-default tolerance: a warm-started step needs a fraction of a cold solve's iterations
+    Tsim = 12
+    xS, uS, status, iters = run_box_closed_loop(A, B, Q, R, N, xlb, xub, ulb, uub, x0, Tsim)
+    cold = run_box(A, B, Q, R, N, xlb, xub, ulb, uub, x0)[4]
+    assert (status == 0).all() and (iters < 0.5 * Tsim * cold).all(), (iters, cold)

@@ -50,6 +50,10 @@ struct Params {
     const T* tab;  // LEVELS * N * TW
     int max_iter, check_every;
     T rho0, alpha, eps_abs, eps_rel, eps_inf;
+    // closed loop only
+    int Tsim;
+    T *xSim, *uSim;
+    T clip_margin;
 };
 
 ZB_HD long long ws_elems(int N, long long Bsz) { return (Bsz + 31) / 32 * (long long)(N + 1) * SW * 32; }
@@ -195,6 +199,127 @@ ZB_HD void forward(const Ops<T>& O, T* ws, int N, const T* tab, const T (&x0)[12
     }
 }
 
+// ADMM iterations from the state (w, lambda) found in `ws` (zeros = cold start; the previous solve's = warm start), rho level
+// carried in/out.  On return the plan z of the last iteration is in zx (N+1,12) / zu (N,4).  Returns 0 optimal, 1 max_iter
+// reached, 2 infeasible (certificate); `it` = iterations run.
+template <typename T>
+ZB_HD int admm_solve(const Ops<T>& O, const Params<T>& P, T* ws, const T (&x0)[12], T* zx, T* zu, int& level, int& it) {
+    const int N = P.N;
+    int status = 1;
+    T rho = ldexp(P.rho0, level - LEVEL0), inv_rho = T(1) / rho;
+    int rho_gap = P.check_every, rho_next = 0;  // back-off: every rho move doubles the wait before the next one (no limit cycles)
+    for (it = 1; it <= P.max_iter; ++it) {
+        const T* tab = P.tab + (long long)level * N * TW;
+        // ---- z-update, part 1: backward vector sweep with linear terms lam - rho*w ----
+        T p[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) p[i] = ZB_LD(N, O_LX + i) - rho * ZB_LD(N, O_WX + i);
+        T sl[16], sw[16];  // lambda / w of the step being processed, loaded one step ahead of their use
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { sw[j] = ZB_LD(N - 1, O_WX + j); sl[j] = ZB_LD(N - 1, O_LX + j); }
+        for (int k = N - 1; k >= 0; --k) {
+            const T* Kk = tab + (long long)k * TW;
+            T Kr[64];  // K_k (48) and G_k^-1 (16): issued first, consumed after the 192 multiply-adds with A and B
+            ldrow<T, 64>(Kk, Kr);
+            T g[16];  // lam - rho*w: [0,12) state part, [12,16) control part
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = sl[j] - rho * sw[j];
+            if (k > 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { sw[j] = ZB_LD(k - 1, O_WX + j); sl[j] = ZB_LD(k - 1, O_LX + j); }
+            }
+            T h[4], pn[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                T s = g[i];
+#pragma unroll
+                for (int j = 0; j < 12; ++j) s += O.A[j * 12 + i] * p[j];
+                pn[i] = s;
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                T s = g[12 + a];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) s += O.B[i * 4 + a] * p[i];
+                h[a] = s;
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                T s = T(0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) s += Kr[48 + a * 4 + c] * h[c];
+                ZB_ST(k, O_KFF + a, s);
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) pn[i] -= Kr[a * 12 + i] * h[a];
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) p[i] = pn[i];
+        }
+        // ---- z-update, part 2 + projection (forward<>) ----
+        const bool chk = (it % P.check_every == 0) || it == P.max_iter;
+        Res<T> r{T(0), T(0), T(0), T(0), T(0), T(0), T(0), true};
+        if (chk) forward<T, true>(O, ws, N, tab, x0, rho, inv_rho, P.alpha, zx, zu, r);
+        else forward<T, false>(O, ws, N, tab, x0, rho, inv_rho, P.alpha, zx, zu, r);
+        if (chk) {
+            if (r.rp <= P.eps_abs + P.eps_rel * fmax(r.nz, r.nw) && r.rd <= P.eps_abs + P.eps_rel * r.nl) {
+                status = 0;
+                break;
+            }
+            // primal infeasibility certificate: delta-lambda separates the box from the dynamics' affine set
+            if (r.cert_ok && r.ndl > P.eps_inf && r.S < -P.eps_inf * r.ndl) {
+                T mu[12], g = T(0);
+#pragma unroll
+                for (int i = 0; i < 12; ++i) mu[i] = ZB_LD(N, O_DX + i);
+                for (int k = N - 1; k >= 0; --k) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        T s = ZB_LD(k, O_DU + a);
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) s += O.B[i * 4 + a] * mu[i];
+                        g = fmax(g, fabs(s));
+                    }
+                    T mn[12];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        T s = ZB_LD(k, O_DX + i);
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) s += O.A[j * 12 + i] * mu[j];
+                        mn[i] = s;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) mu[i] = mn[i];
+                }
+                if (g <= P.eps_inf * r.ndl) {
+                    status = 2;
+                    break;
+                }
+            }
+            // residual balancing as OSQP, on the rho grid: move by round(log2(ratio)) levels when the residuals are 5x apart
+            if (it < P.max_iter && it >= rho_next) {
+                const T rpn = r.rp / fmax(fmax(r.nz, r.nw), T(1e-10)), rdn = r.rd / fmax(r.nl, T(1e-10));
+                const T ratio = sqrt(rpn / fmax(rdn, T(1e-30)));
+                if ((ratio > T(5) || ratio < T(0.2)) && rdn > T(0)) {
+                    const T lg = log2(ratio);
+                    int nl = level + (int)(lg >= T(0) ? lg + T(0.5) : lg - T(0.5));
+                    nl = nl < 0 ? 0 : (nl > LEVELS - 1 ? LEVELS - 1 : nl);
+                    if (nl != level) {
+                        rho_gap *= 2;
+                        rho_next = it + rho_gap;
+                        level = nl;
+                        rho = ldexp(P.rho0, level - LEVEL0);
+                        inv_rho = T(1) / rho;
+                    }
+                }
+            }
+        }
+    }
+    if (it > P.max_iter) it = P.max_iter;
+    return status;
+}
+
 template <typename T>
 ZB_HD void problem(const Ops<T>& O, const Params<T>& P, long long b) {
     const int N = P.N;
@@ -212,122 +337,13 @@ ZB_HD void problem(const Ops<T>& O, const Params<T>& P, long long b) {
     bool x0_bad = false;
 #pragma unroll
     for (int i = 0; i < 12; ++i) x0_bad |= !(x0[i] >= O.xlb[i] - P.eps_abs && x0[i] <= O.xub[i] + P.eps_abs);
-    int status = 1, it = 0;
-    if (x0_bad) {
-        status = 2;
-    } else {
+    int status = 2, it = 0;
+    if (!x0_bad) {
         int level = LEVEL0;
-        T rho = P.rho0, inv_rho = T(1) / rho;
         for (int k = 0; k <= N; ++k)
 #pragma unroll
             for (int j = 0; j < 32; ++j) ZB_ST(k, j, T(0));
-        for (it = 1; it <= P.max_iter; ++it) {
-            const T* tab = P.tab + (long long)level * N * TW;
-            // ---- z-update, part 1: backward vector sweep with linear terms lam - rho*w ----
-            T p[12];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) p[i] = ZB_LD(N, O_LX + i) - rho * ZB_LD(N, O_WX + i);
-            T sl[16], sw[16];  // lambda / w of the step being processed, loaded one step ahead of their use
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { sw[j] = ZB_LD(N - 1, O_WX + j); sl[j] = ZB_LD(N - 1, O_LX + j); }
-            for (int k = N - 1; k >= 0; --k) {
-                const T* Kk = tab + (long long)k * TW;
-                T Kr[64];  // K_k (48) and G_k^-1 (16): issued first, consumed after the 192 multiply-adds with A and B
-                ldrow<T, 64>(Kk, Kr);
-                T g[16];  // lam - rho*w: [0,12) state part, [12,16) control part
-#pragma unroll
-                for (int j = 0; j < 16; ++j) g[j] = sl[j] - rho * sw[j];
-                if (k > 0) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) { sw[j] = ZB_LD(k - 1, O_WX + j); sl[j] = ZB_LD(k - 1, O_LX + j); }
-                }
-                T h[4], pn[12];
-#pragma unroll
-                for (int i = 0; i < 12; ++i) {
-                    T s = g[i];
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) s += O.A[j * 12 + i] * p[j];
-                    pn[i] = s;
-                }
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    T s = g[12 + a];
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) s += O.B[i * 4 + a] * p[i];
-                    h[a] = s;
-                }
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    T s = T(0);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) s += Kr[48 + a * 4 + c] * h[c];
-                    ZB_ST(k, O_KFF + a, s);
-                }
-#pragma unroll
-                for (int i = 0; i < 12; ++i) {
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) pn[i] -= Kr[a * 12 + i] * h[a];
-                }
-#pragma unroll
-                for (int i = 0; i < 12; ++i) p[i] = pn[i];
-            }
-            // ---- z-update, part 2 + projection (forward<>) ----
-            const bool chk = (it % P.check_every == 0) || it == P.max_iter;
-            Res<T> r{T(0), T(0), T(0), T(0), T(0), T(0), T(0), true};
-            if (chk) forward<T, true>(O, ws, N, tab, x0, rho, inv_rho, P.alpha, zx, zu, r);
-            else forward<T, false>(O, ws, N, tab, x0, rho, inv_rho, P.alpha, zx, zu, r);
-            if (chk) {
-                if (r.rp <= P.eps_abs + P.eps_rel * fmax(r.nz, r.nw) && r.rd <= P.eps_abs + P.eps_rel * r.nl) {
-                    status = 0;
-                    break;
-                }
-                // primal infeasibility certificate: delta-lambda separates the box from the dynamics' affine set
-                if (r.cert_ok && r.ndl > P.eps_inf && r.S < -P.eps_inf * r.ndl) {
-                    T mu[12], g = T(0);
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) mu[i] = ZB_LD(N, O_DX + i);
-                    for (int k = N - 1; k >= 0; --k) {
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            T s = ZB_LD(k, O_DU + a);
-#pragma unroll
-                            for (int i = 0; i < 12; ++i) s += O.B[i * 4 + a] * mu[i];
-                            g = fmax(g, fabs(s));
-                        }
-                        T mn[12];
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) {
-                            T s = ZB_LD(k, O_DX + i);
-#pragma unroll
-                            for (int j = 0; j < 12; ++j) s += O.A[j * 12 + i] * mu[j];
-                            mn[i] = s;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) mu[i] = mn[i];
-                    }
-                    if (g <= P.eps_inf * r.ndl) {
-                        status = 2;
-                        break;
-                    }
-                }
-                // residual balancing as OSQP, on the rho grid: move by round(log2(ratio)) levels when the residuals are 5x apart
-                if (it < P.max_iter) {
-                    const T rpn = r.rp / fmax(fmax(r.nz, r.nw), T(1e-10)), rdn = r.rd / fmax(r.nl, T(1e-10));
-                    const T ratio = sqrt(rpn / fmax(rdn, T(1e-30)));
-                    if ((ratio > T(5) || ratio < T(0.2)) && rdn > T(0)) {
-                        const T lg = log2(ratio);
-                        int nl = level + (int)(lg >= T(0) ? lg + T(0.5) : lg - T(0.5));
-                        nl = nl < 0 ? 0 : (nl > LEVELS - 1 ? LEVELS - 1 : nl);
-                        if (nl != level) {
-                            level = nl;
-                            rho = ldexp(P.rho0, level - LEVEL0);
-                            inv_rho = T(1) / rho;
-                        }
-                    }
-                }
-            }
-        }
-        if (it > P.max_iter) it = P.max_iter;
+        status = admm_solve<T>(O, P, ws, x0, zx, zu, level, it);
     }
     if (status == 2) {
         const T nan = INF - INF;
@@ -338,10 +354,73 @@ ZB_HD void problem(const Ops<T>& O, const Params<T>& P, long long b) {
     for (int a = 0; a < 4; ++a) u0[a] = zu[a];
     P.status[b] = (int8_t)status;
     if (P.iters) P.iters[b] = it;
+}
+
+// Receding-horizon loop of demos/lqrMpc.py:42-47 for one problem: every simulation step clips the state into the box
+// (x_lb + margin, x_ub - margin: the QP also constrains x_0), solves the MPC problem from it WARM-STARTED with the previous
+// step's (w, lambda) and rho level (cvxpy re-solves with warm_start=True by default), applies the first move and takes the
+// plan's own next state as the new state ("assume perfect tracking", demos/lqrMpc.py:47).  xSim (Tsim+1,12) holds the
+// clipped states the solves started from (+ the final one), uSim (Tsim,4) the applied moves; status = worst over the steps,
+// iters = total ADMM iterations; a step that is infeasible ends the loop with NaNs from there on.
+template <typename T>
+ZB_HD void closed_loop_problem(const Ops<T>& O, const Params<T>& P, long long b) {
+    const int N = P.N;
+    T* ws = P.ws + (b >> 5) * ((long long)(N + 1) * SW * 32) + (b & 31);
+    T* zx = P.xTraj + b * (long long)(N + 1) * 12;  // scratch: the current plan
+    T* zu = P.uTraj + b * (long long)N * 4;
+    T* xs = P.xSim + b * (long long)(P.Tsim + 1) * 12;
+    T* us = P.uSim + b * (long long)P.Tsim * 4;
+    const T INF = T(1) / T(0);
+    T x[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) x[i] = P.x0[b * 12 + i];
+    for (int k = 0; k <= N; ++k)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ZB_ST(k, j, T(0));
+    int level = LEVEL0, worst = 0;
+    long long total = 0;
+    int ts = 0;
+    for (; ts < P.Tsim; ++ts) {
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            x[i] = clampv<T>(x[i], O.xlb[i] + P.clip_margin, O.xub[i] - P.clip_margin);
+            bad |= !(x[i] == x[i]);
+            xs[(long long)ts * 12 + i] = x[i];
+        }
+        int it = 0;
+        const int st = bad ? 2 : admm_solve<T>(O, P, ws, x, zx, zu, level, it);
+        total += it;
+        worst = st > worst ? st : worst;
+        if (st == 2) break;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) us[(long long)ts * 4 + a] = zu[a];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) x[i] = zx[12 + i];
+        // receding horizon: the next problem's step k is this one's step k+1 -- shift (w, lambda) one step down (the last
+        // control keeps its own values, the terminal state its own)
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const bool upart = (j & 15) >= 12;
+                if (!(upart && k == N - 1)) ZB_ST(k, j, ZB_LD(k + 1, j));
+            }
+        }
+    }
+    if (ts < P.Tsim) {  // infeasible step: NaN from here on
+        const T nan = INF - INF;
+        for (long long i = (long long)(ts + 1) * 12; i < (long long)(P.Tsim + 1) * 12; ++i) xs[i] = nan;
+        for (long long i = (long long)ts * 4; i < (long long)P.Tsim * 4; ++i) us[i] = nan;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) xs[(long long)P.Tsim * 12 + i] = x[i];
+    }
+    P.status[b] = (int8_t)worst;
+    if (P.iters) P.iters[b] = (int32_t)(total > 2147483647LL ? 2147483647LL : total);
+}
 #undef ZB_WS
 #undef ZB_LD
 #undef ZB_ST
-}
 
 // One level of the table: gains K_k = G^-1 B'PA and G_k^-1 of the Hessian-form LQ problem with weights
 // (2Q + rho I, 2R + rho I, 2Qf + rho I) -- admm_factor (zb_problems.cuh) for rho = rho0 * 2^(level - LEVEL0).
@@ -422,6 +501,12 @@ template <typename T>
 __global__ void __launch_bounds__(32) k_mpc_box(const __grid_constant__ Ops<T> O, const __grid_constant__ Params<T> P) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b < P.Bsz) problem<T>(O, P, b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32) k_mpc_box_closed_loop(const __grid_constant__ Ops<T> O, const __grid_constant__ Params<T> P) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < P.Bsz) closed_loop_problem<T>(O, P, b);
 }
 
 template <typename T>

@@ -745,7 +745,7 @@ template <typename T>
 static int32_t box_solve(cudaStream_t s, int64_t Bsz, int N, const double* A, const double* B, const double* xlb,
                          const double* xub, const double* ulb, const double* uub, const void* tables, const void* x0,
                          const zb_admm_opts* opts, void* u0, void* xTraj, void* uTraj, int8_t* status, int32_t* iters,
-                         void* workspace) {
+                         void* workspace, int Tsim = -1, void* xSim = nullptr, void* uSim = nullptr, double clip_margin = 0) {
     box::Ops<T> O;
     box_fill_ops<T>(O, A, B, xlb, xub, ulb, uub);
     box::Params<T> P{};
@@ -761,7 +761,12 @@ static int32_t box_solve(cudaStream_t s, int64_t Bsz, int N, const double* A, co
     P.eps_abs = (T)(opts && opts->eps_abs > 0 ? opts->eps_abs : 1e-3);
     P.eps_rel = (T)(opts && opts->eps_rel > 0 ? opts->eps_rel : 1e-3);
     P.eps_inf = (T)(opts && opts->eps_prim_inf > 0 ? opts->eps_prim_inf : 1e-4);
-    box::k_mpc_box<T><<<(unsigned)((Bsz + 31) / 32), 32, 0, s>>>(O, P);
+    if (Tsim >= 0) {
+        P.Tsim = Tsim; P.xSim = reinterpret_cast<T*>(xSim); P.uSim = reinterpret_cast<T*>(uSim); P.clip_margin = (T)clip_margin;
+        box::k_mpc_box_closed_loop<T><<<(unsigned)((Bsz + 31) / 32), 32, 0, s>>>(O, P);
+    } else {
+        box::k_mpc_box<T><<<(unsigned)((Bsz + 31) / 32), 32, 0, s>>>(O, P);
+    }
     ZB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -774,6 +779,35 @@ size_t zb_mpc_box_tables_bytes(int32_t dtype, int32_t N) {
 
 size_t zb_mpc_box_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N) {
     return align256((dtype == ZB_F64 ? 8 : 4) * (size_t)box::ws_elems(N, Bsz)) + 256;
+}
+
+size_t zb_mpc_box_closed_loop_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N) {  // ADMM state + one plan per problem
+    const size_t e = dtype == ZB_F64 ? 8 : 4;
+    return align256(e * (size_t)box::ws_elems(N, Bsz)) + align256(e * (size_t)Bsz * (N + 1) * 12) + align256(e * (size_t)Bsz * N * 4) + 256;
+}
+
+int32_t zb_mpc_box_closed_loop(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t Tsim, const double* A,
+                               const double* B, const double* x_lb, const double* x_ub, const double* u_lb, const double* u_ub,
+                               const void* tables, const void* x0, const zb_admm_opts* opts, double clip_margin, void* xSim_out,
+                               void* uSim_out, int8_t* status_out, int32_t* iters_out, void* workspace, size_t workspace_bytes) {
+    ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "dtype must be ZB_F32 or ZB_F64 (got %d)", dtype);
+    ZB_ARG(Bsz >= 0 && N >= 1 && Tsim >= 0, "bad sizes");
+    if (Bsz == 0) return 0;
+    ZB_ARG(A && B && x_lb && x_ub && u_lb && u_ub && tables, "NULL operand");
+    ZB_ARG(x0 && xSim_out && (uSim_out || Tsim == 0) && status_out, "NULL operand");
+    size_t need = zb_mpc_box_closed_loop_workspace_bytes(dtype, Bsz, N);
+    ZB_ARG(workspace && workspace_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    const size_t e = dtype == ZB_F64 ? 8 : 4;
+    char* w = reinterpret_cast<char*>(workspace);
+    void* state = w; w += align256(e * (size_t)box::ws_elems(N, Bsz));
+    void* planx = w; w += align256(e * (size_t)Bsz * (N + 1) * 12);
+    void* planu = w;
+    return dtype == ZB_F32 ? box_solve<float>((cudaStream_t)stream, Bsz, N, A, B, x_lb, x_ub, u_lb, u_ub, tables, x0, opts, nullptr, planx, planu,
+                                              status_out, iters_out, state, Tsim, xSim_out, uSim_out, clip_margin)
+                           : box_solve<double>((cudaStream_t)stream, Bsz, N, A, B, x_lb, x_ub, u_lb, u_ub, tables, x0, opts, nullptr, planx, planu,
+                                               status_out, iters_out, state, Tsim, xSim_out, uSim_out, clip_margin);
 }
 
 int32_t zb_mpc_box_build_tables(int32_t dtype, int32_t device, void* stream, int32_t N, const double* A, const double* B,

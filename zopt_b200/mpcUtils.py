@@ -151,22 +151,69 @@ class lqrMpc():
             return u0[0], Trajectory(xTraj[0], uTraj[0]), STATUS[int(status[0])]
         return u0, Trajectory(xTraj, uTraj), status
 
-    def _solve_box(self, x0, Bsz, opts, u0, xTraj, uTraj, status, iters):
-        """bounded (12,4) problem shared by the batch -> zb_mpc_box_solve (csrc/mpc_box.cuh)"""
+    def _box_tables(self, opts):
+        """rho-grid gain tables of the shared problem definition, built once per (object, rho0)"""
         dt, dev, N, box = self.dtype, self.device, self.N, self._box
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-        A, B, Q, R, Qf, xlb, xub, ulb, uub = box["host"]
+        A, B, Q, R, Qf = box["host"][:5]
         if box["tables"] is None or box["rho0"] != opts.rho:
             tb = lib.zb_mpc_box_tables_bytes(dcode(dt), N)
             tables = torch.empty((tb,), dtype=torch.uint8, device=dev)
             check(lib.zb_mpc_box_build_tables(dcode(dt), dev.index, stream_ptr(dev), N, dp(A), dp(B), dp(Q), dp(R), dp(Qf),
                                               opts.rho, ptr(tables), tb))
             box["tables"], box["rho0"] = tables, opts.rho
+        return box["tables"]
+
+    def _solve_box(self, x0, Bsz, opts, u0, xTraj, uTraj, status, iters):
+        """bounded (12,4) problem shared by the batch -> zb_mpc_box_solve (csrc/mpc_box.cuh)"""
+        dt, dev, N, box = self.dtype, self.device, self.N, self._box
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        A, B, Q, R, Qf, xlb, xub, ulb, uub = box["host"]
+        self._box_tables(opts)
         wsb = lib.zb_mpc_box_workspace_bytes(dcode(dt), Bsz, N)
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         check(lib.zb_mpc_box_solve(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, dp(A), dp(B), dp(xlb), dp(xub), dp(ulb), dp(uub),
                                    ptr(box["tables"]), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
                                    ptr(iters), ptr(ws), wsb))
+
+    def closedLoop(self, x0, Tsim, clip=1e-6, **kwargs):
+        """
+        The receding-horizon loop of demos/lqrMpc.py:42-47 for a batch of initial states, fused into one kernel
+        (zb_mpc_box_closed_loop): per simulation step `x = clip(x, x_lb + clip, x_ub - clip)`, `solve(x)` warm-started from
+        the previous step, `x = traj.xTraj[1]` ("assume perfect tracking").  Needs the shared-definition (12,4) bounded
+        problem (one A, B, Q, R, bounds for the batch); otherwise loop over `solve` as the demo does.
+
+        Returns (Trajectory(xTraj (Bsz,Tsim+1,12), uTraj (Bsz,Tsim,4)), status (Bsz,) int8 worst over the steps); total ADMM
+        iterations per problem in `self.iters`.
+        """
+        if self._box is None:
+            raise NotImplementedError("closedLoop needs finite bounds, (n,m) = (12,4) and one problem definition for the batch; "
+                                      "compose solve() step by step otherwise")
+        dt, dev, N, box = self.dtype, self.device, self.N, self._box
+        x0 = to_dev(x0, dt, dev)
+        batched = x0.ndim == 2
+        x0 = (x0 if batched else x0[None]).contiguous()
+        Bsz, Tsim = x0.shape[0], int(Tsim)
+        opts = ZbAdmmOpts(int(kwargs.get("max_iter", 4000)), int(kwargs.get("check_termination", 25)),
+                          float(kwargs.get("rho", 0.1)), float(kwargs.get("sigma", 1e-6)), float(kwargs.get("alpha", 1.6)),
+                          float(kwargs.get("eps_abs", 1e-3)), float(kwargs.get("eps_rel", 1e-3)),
+                          float(kwargs.get("eps_prim_inf", 1e-4)))
+        tables = self._box_tables(opts)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        A, B, Q, R, Qf, xlb, xub, ulb, uub = box["host"]
+        xS = torch.empty((Bsz, Tsim + 1, 12), dtype=dt, device=dev)
+        uS = torch.empty((Bsz, Tsim, 4), dtype=dt, device=dev)
+        status = torch.empty((Bsz,), dtype=torch.int8, device=dev)
+        iters = torch.empty((Bsz,), dtype=torch.int32, device=dev)
+        wsb = lib.zb_mpc_box_closed_loop_workspace_bytes(dcode(dt), Bsz, N)
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+        check(lib.zb_mpc_box_closed_loop(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, Tsim, dp(A), dp(B), dp(xlb), dp(xub),
+                                         dp(ulb), dp(uub), ptr(tables), ptr(x0), C.byref(opts), float(clip), ptr(xS), ptr(uS),
+                                         ptr(status), ptr(iters), ptr(ws), wsb))
+        self.iters = iters
+        if not batched:
+            return Trajectory(xS[0], uS[0]), STATUS[int(status[0])]
+        return Trajectory(xS, uS), status
 
     @staticmethod
     def status_str(status, i=0):
