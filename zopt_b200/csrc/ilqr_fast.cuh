@@ -540,8 +540,15 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
             for (int c = 0; c < 4; ++c) nv[c] = qv[c] + (M[0][c] * L[0][4] + M[1][c] * L[1][4] + M[2][c] * L[2][4] + M[3][c] * L[3][4]);
             stv4(vx + 4 * t, nv[0], nv[1], nv[2], nv[3]);
         }
+        // v_xx' is symmetric: of the 9 4x4 blocks only 6 are distinct.  Thread t computes (t, t) and ((t+1)%3, t) -- for t = 2
+        // that is the UPPER block (0, 2), stored together with its transpose (2, 0) -- so every thread does 2 blocks, not 3.
+        // (The DDP instantiation keeps the 3-block loop with a compile-time row block: its clamped-block lookups and register
+        // budget are tuned around it -- measured 153 vs 197 ms on cfg 5.)
+        constexpr int NBLK = DDP ? 3 : 2;
 #pragma unroll
-        for (int sblk = 0; sblk < 3; ++sblk) {  // rows 4*sblk .. 4*sblk+3 of the tile = block (sblk, t)
+        for (int bi = 0; bi < NBLK; ++bi) {
+            const int tb = t < 3 ? t : 0;  // thread 3 (the f_u tile) owns no block: it shadows thread 0 and stores nothing
+            const int sblk = DDP ? bi : ((bi == 0) ? tb : (tb == 2 ? 0 : tb + 1));  // rows 4*sblk .. 4*sblk+3 of the tile = block (sblk, t)
             T acc[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -585,13 +592,13 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
             }
             // write back, lower triangle wins: strictly-lower blocks are stored with their transpose,
             // diagonal blocks are mirrored, upper blocks are dropped (their transposes are authoritative)
-            if (sblk > t) {
+            if (DDP ? (sblk > t) : (t < 3 && sblk != t)) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     stv4(Vs + (4 * sblk + r) * 12 + 4 * t, acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
                     stv4(Vs + (4 * t + r) * 12 + 4 * sblk, acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
                 }
-            } else if (sblk == t) {
+            } else if (DDP ? (sblk == t) : (t < 3)) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     T e[4];
