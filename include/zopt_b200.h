@@ -162,8 +162,9 @@ ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_
 #define ZB_MPC_BOUNDED 1   /* zb_mpc_lqr_solve */
 #define ZB_SECOND_ORDER 1  /* zb_ilqr_solve */
 #define ZB_COST_DIAGONAL 2 /* both */
-#define ZB_VARIANT_THREAD 4 /* zb_mpc_closed_loop_quad: force the thread-per-problem kernel */
-#define ZB_VARIANT_QUAD 8   /* zb_mpc_closed_loop_quad: force the 4-threads-per-problem kernel (default for small batches) */
+#define ZB_VARIANT_THREAD 4 /* zb_mpc_closed_loop_quad, zb_mpc_box_*: force the thread-per-problem kernel */
+#define ZB_VARIANT_QUAD 8   /* ... force the 4-threads-per-problem kernel (default for small batches) */
+#define ZB_BOX_STATE_GLOBAL 16 /* zb_mpc_box_*: keep the 4-threads-per-problem kernel's ADMM state in the global workspace even when it would fit on chip */
 
 typedef struct zb_admm_opts {
     int32_t max_iter;   /* default 4000 */
@@ -196,8 +197,9 @@ ZB_API int32_t zb_mpc_box_build_tables(int32_t dtype, int32_t device, void* stre
                                 double rho0, void* tables, size_t tables_bytes);
 ZB_API int32_t zb_mpc_box_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, const double* A, const double* B,
                          const double* x_lb, const double* x_ub, const double* u_lb, const double* u_ub /* host */,
-                         const void* tables, const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj, void* uTraj,
-                         int8_t* status_out, int32_t* iters_out, void* workspace, size_t workspace_bytes);
+                         const void* tables, const void* x0, const zb_admm_opts* opts,
+                         int32_t flags /* 0 = pick by batch size | ZB_VARIANT_THREAD | ZB_VARIANT_QUAD (fp32 only) */, void* u0_out,
+                         void* xTraj, void* uTraj, int8_t* status_out, int32_t* iters_out, void* workspace, size_t workspace_bytes);
 
 /* The receding-horizon loop of demos/lqrMpc.py:42-47 around that problem, fused into one kernel: every simulation step clips
  * the state into [x_lb + clip_margin, x_ub - clip_margin] (demo: 1e-6; the QP constrains x_0 too), solves from it warm-started
@@ -208,8 +210,9 @@ ZB_API int32_t zb_mpc_box_solve(int32_t dtype, int32_t device, void* stream, int
 ZB_API size_t zb_mpc_box_closed_loop_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N);
 ZB_API int32_t zb_mpc_box_closed_loop(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t Tsim, const double* A,
                                const double* B, const double* x_lb, const double* x_ub, const double* u_lb, const double* u_ub,
-                               const void* tables, const void* x0, const zb_admm_opts* opts, double clip_margin, void* xSim_out,
-                               void* uSim_out, int8_t* status_out, int32_t* iters_out, void* workspace, size_t workspace_bytes);
+                               const void* tables, const void* x0, const zb_admm_opts* opts, int32_t flags /* as zb_mpc_box_solve */,
+                               double clip_margin, void* xSim_out, void* uSim_out, int8_t* status_out, int32_t* iters_out,
+                               void* workspace, size_t workspace_bytes);
 
 /* ---- closed-loop LQR-MPC of the quadcopter (BASELINE cfg 3; the receding-horizon loop of demos/lqrMpc.py:42-47 with a
  * nonlinear plant), fp32, bounds inactive.  Per simulation step t: A_t = I + dt dF/dx(x_t,u_trim), B = dt dF/du, a full

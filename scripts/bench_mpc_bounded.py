@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Box-constrained lqrMpc (ADMM tier) throughput probe: demos/lqrMpc.py problem, batched initial states.
-usage: bench_mpc_bounded.py [Bsz] [f64|f32] [eps] [auto|generic] [N]"""
+usage: bench_mpc_bounded.py [Bsz] [f64|f32] [eps] [auto|generic|thread|quad|quad_global] [N]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

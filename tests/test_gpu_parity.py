@@ -575,6 +575,16 @@ def test_lqrMpc_box_kernel_vs_generic_and_oracle(dt):
         ur0, xr, ur, st, info = ompc.solve_qp(A, B, Qd, R, N, xlb, xub, ulb, uub, x0[b], Qf=Qf)
         assert st == "optimal"
         assert np.max(np.abs(uT[b] - ur)) < (2e-3 if dt == torch.float64 else 5e-2) * max(1.0, np.max(np.abs(ur)))
+    if dt == torch.float32:  # one thread per problem vs four threads per problem (csrc/mpc_box_quad.cuh): same iterates up to rounding
+        uq, trajq, statusq = prob.solve(cuda(x0, dt), kernel="quad", **kw)
+        it_q = prob.iters.clone()
+        ug2, trajg2, statusg2 = prob.solve(cuda(x0, dt), kernel="quad_global", **kw)  # same kernel, state in the global workspace
+        assert torch.equal(statusq, statusg2) and torch.equal(trajq.uTraj[ok], trajg2.uTraj[ok]) and torch.equal(it_q, prob.iters)
+        ut, trajt, statust = prob.solve(cuda(x0, dt), kernel="thread", **kw)
+        assert torch.equal(statusq, statust) and torch.isnan(trajq.uTraj[bad]).all() and torch.isnan(trajq.xTraj[bad]).all()
+        assert relerr(trajq.uTraj[ok], trajt.uTraj[ok]) < 2e-3 and relerr(trajq.xTraj[ok], trajt.xTraj[ok]) < 2e-3
+        assert float((it_q[ok] - prob.iters[ok]).abs().float().mean()) < 0.1 * float(it_q[ok].float().mean())
+        assert torch.equal(uq[ok], trajq.uTraj[ok, 0])
     # second solve on the same object reuses the tables; a different rho rebuilds them
     u2, traj2, status2 = prob.solve(cuda(x0[ok], dt), **kw)
     assert torch.equal(traj2.uTraj, traj.uTraj[ok])
@@ -613,6 +623,17 @@ def test_lqrMpc_box_closed_loop_vs_composed():
     p32 = lqrMpc(*(cuda(t, torch.float32) for t in (A, B, Q, R)), N, xlb, xub, ulb, uub)
     tr32, st32 = p32.closedLoop(cuda(x0[0], torch.float32), 20, eps_abs=1e-2, eps_rel=1e-2)
     assert st32 == "optimal" and tr32.xTraj.shape == (21, 12) and bool(torch.isfinite(tr32.uTraj).all())
+    # fp32, tight tolerance: the 4-threads-per-problem and the thread-per-problem loop kernels agree, ragged batch
+    kw32 = dict(eps_abs=1e-4, eps_rel=1e-4, max_iter=20000)
+    trq, stq = p32.closedLoop(cuda(x0, torch.float32), Tsim, kernel="quad", **kw32)
+    itq = p32.iters.clone()
+    trg, stg = p32.closedLoop(cuda(x0, torch.float32), Tsim, kernel="quad_global", **kw32)
+    assert torch.equal(trg.uTraj, trq.uTraj) and torch.equal(trg.xTraj, trq.xTraj) and torch.equal(p32.iters, itq)
+    trt, stt = p32.closedLoop(cuda(x0, torch.float32), Tsim, kernel="thread", **kw32)
+    assert (stq == 0).all() and (stt == 0).all()
+    assert relerr(trq.xTraj, trt.xTraj) < 2e-3 and float((trq.uTraj - trt.uTraj).abs().max()) < 3e-2
+    assert relerr(trq.xTraj, traj.xTraj) < 5e-3   # and both follow the fp64 loop
+    assert abs(float(itq.float().mean()) / float(p32.iters.float().mean()) - 1) < 0.2
 
 
 @pytest.mark.parametrize("dense_cost", [False, True])

@@ -67,11 +67,11 @@ SIGNATURES = {
     "zb_mpc_box_tables_bytes": (_sz, [_i32, _i32]),
     "zb_mpc_box_workspace_bytes": (_sz, [_i32, _i64, _i32]),
     "zb_mpc_box_build_tables": (_i32, [_i32, _i32, _P, _i32] + [C.POINTER(_f64)] * 5 + [_f64, _P, _sz]),
-    "zb_mpc_box_solve": (_i32, [_i32, _i32, _P, _i64, _i32] + [C.POINTER(_f64)] * 6 + [_P, _P, C.POINTER(ZbAdmmOpts),
+    "zb_mpc_box_solve": (_i32, [_i32, _i32, _P, _i64, _i32] + [C.POINTER(_f64)] * 6 + [_P, _P, C.POINTER(ZbAdmmOpts), _i32,
                                 _P, _P, _P, _P, _P, _P, _sz]),
     "zb_mpc_box_closed_loop_workspace_bytes": (_sz, [_i32, _i64, _i32]),
     "zb_mpc_box_closed_loop": (_i32, [_i32, _i32, _P, _i64, _i32, _i32] + [C.POINTER(_f64)] * 6 + [_P, _P, C.POINTER(ZbAdmmOpts),
-                                      _f64, _P, _P, _P, _P, _P, _sz]),
+                                      _i32, _f64, _P, _P, _P, _P, _P, _sz]),
     "zb_mpc_closed_loop_quad": (_i32, [_i32, _i32, _P, _i64, _i32, _i32, _f64, C.POINTER(_f64), _AP, _AP, _AP, _i32, _P, _P, _P]),
     "zb_peak_fma": (_i32, [_i32, _i32, C.POINTER(_f64), C.POINTER(_f64)]),
 }

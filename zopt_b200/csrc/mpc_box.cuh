@@ -27,7 +27,7 @@ namespace box {
 constexpr int LEVELS = 25, LEVEL0 = 12;  // rho_j = rho0 * 2^(j - LEVEL0)
 constexpr int SW = 52;                   // state words per horizon step: w_x 12, w_u 4, lam_x 12, lam_u 4, kff 4, dlam_x 12, dlam_u 4
 constexpr int O_WX = 0, O_WU = 12, O_LX = 16, O_LU = 28, O_KFF = 32, O_DX = 36, O_DU = 48;
-constexpr int TW = 64;                   // table words per (level, step): K 4x12, G^-1 4x4
+constexpr int TW = 112;                  // table words per (level, step): K 4x12, G^-1 4x4, K' 12x4 (for the 4-threads-per-problem kernel)
 
 template <typename T>
 struct Ops {  // the problem definition, shared by the batch (kernel parameter -> constant bank)
@@ -465,6 +465,7 @@ ZB_HD void table_level(const Ops<T>& O, const Costs<T>& C, int N, T rho, T* tabl
             for (int c = 0; c < 4; ++c) s += G[a * 4 + c] * M4[c * 12 + j];
             Kk[e] = s;
             out[e] = s;
+            out[64 + j * 4 + a] = s;  // transposed copy
         }
         sync();
         for (int e = lane; e < 144; e += nlanes) {  // Acl = A - B K

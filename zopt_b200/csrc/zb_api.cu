@@ -8,6 +8,7 @@
 #include "lqr_t1.cuh"
 #include "mpc_coop.cuh"
 #include "mpc_box.cuh"
+#include "mpc_box_quad.cuh"
 
 using namespace zb;
 
@@ -745,7 +746,8 @@ template <typename T>
 static int32_t box_solve(cudaStream_t s, int64_t Bsz, int N, const double* A, const double* B, const double* xlb,
                          const double* xub, const double* ulb, const double* uub, const void* tables, const void* x0,
                          const zb_admm_opts* opts, void* u0, void* xTraj, void* uTraj, int8_t* status, int32_t* iters,
-                         void* workspace, int Tsim = -1, void* xSim = nullptr, void* uSim = nullptr, double clip_margin = 0) {
+                         void* workspace, int32_t flags, int device, int Tsim = -1, void* xSim = nullptr, void* uSim = nullptr,
+                         double clip_margin = 0) {
     box::Ops<T> O;
     box_fill_ops<T>(O, A, B, xlb, xub, ulb, uub);
     box::Params<T> P{};
@@ -761,8 +763,40 @@ static int32_t box_solve(cudaStream_t s, int64_t Bsz, int N, const double* A, co
     P.eps_abs = (T)(opts && opts->eps_abs > 0 ? opts->eps_abs : 1e-3);
     P.eps_rel = (T)(opts && opts->eps_rel > 0 ? opts->eps_rel : 1e-3);
     P.eps_inf = (T)(opts && opts->eps_prim_inf > 0 ? opts->eps_prim_inf : 1e-4);
+    if (Tsim >= 0) { P.Tsim = Tsim; P.xSim = reinterpret_cast<T*>(xSim); P.uSim = reinterpret_cast<T*>(uSim); P.clip_margin = (T)clip_margin; }
+    if constexpr (sizeof(T) == 4) {
+        int sm_count = 0;
+        ZB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+        // One-warp CTAs (8 problems) with the ADMM state in shared memory, as many per SM as fit; larger batches run as
+        // successive waves of such CTAs.  Measured on B200 (N = 25, eps 1e-3): 4.6-5.3 ms per wave of <= 5,920 problems
+        // against 15-20 ms for the same problems with the state in L2, and still ahead of the thread-per-problem kernel
+        // (all problems resident, state streamed from L2/HBM) at 65,536 problems (49 vs 53-70 ms).  So: whenever the
+        // horizon's state fits in shared memory.
+        const size_t smem = (size_t)(N + 1) * box::QW * 32 * sizeof(float);
+        const bool fits = smem + 1024 <= 227u * 1024;
+        (void)sm_count;
+        const bool quad = (flags & ZB_VARIANT_QUAD) || (!(flags & ZB_VARIANT_THREAD) && fits);
+        if (quad) {
+            const bool on_chip = !(flags & ZB_BOX_STATE_GLOBAL) && fits;
+            if (on_chip) {
+                const unsigned grid = (unsigned)((Bsz + 7) / 8);
+                if (Tsim >= 0) {
+                    ZB_CUDA(cudaFuncSetAttribute(box::k_mpc_box_quad<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    box::k_mpc_box_quad<true, true><<<grid, 32, smem, s>>>(O, P);
+                } else {
+                    ZB_CUDA(cudaFuncSetAttribute(box::k_mpc_box_quad<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    box::k_mpc_box_quad<false, true><<<grid, 32, smem, s>>>(O, P);
+                }
+            } else {
+                const unsigned grid = (unsigned)((Bsz + 15) / 16);
+                if (Tsim >= 0) box::k_mpc_box_quad<true, false><<<grid, 64, 0, s>>>(O, P);
+                else box::k_mpc_box_quad<false, false><<<grid, 64, 0, s>>>(O, P);
+            }
+            ZB_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     if (Tsim >= 0) {
-        P.Tsim = Tsim; P.xSim = reinterpret_cast<T*>(xSim); P.uSim = reinterpret_cast<T*>(uSim); P.clip_margin = (T)clip_margin;
         box::k_mpc_box_closed_loop<T><<<(unsigned)((Bsz + 31) / 32), 32, 0, s>>>(O, P);
     } else {
         box::k_mpc_box<T><<<(unsigned)((Bsz + 31) / 32), 32, 0, s>>>(O, P);
@@ -788,8 +822,9 @@ size_t zb_mpc_box_closed_loop_workspace_bytes(int32_t dtype, int64_t Bsz, int32_
 
 int32_t zb_mpc_box_closed_loop(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t Tsim, const double* A,
                                const double* B, const double* x_lb, const double* x_ub, const double* u_lb, const double* u_ub,
-                               const void* tables, const void* x0, const zb_admm_opts* opts, double clip_margin, void* xSim_out,
-                               void* uSim_out, int8_t* status_out, int32_t* iters_out, void* workspace, size_t workspace_bytes) {
+                               const void* tables, const void* x0, const zb_admm_opts* opts, int32_t flags, double clip_margin,
+                               void* xSim_out, void* uSim_out, int8_t* status_out, int32_t* iters_out, void* workspace,
+                               size_t workspace_bytes) {
     ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "dtype must be ZB_F32 or ZB_F64 (got %d)", dtype);
     ZB_ARG(Bsz >= 0 && N >= 1 && Tsim >= 0, "bad sizes");
     if (Bsz == 0) return 0;
@@ -805,9 +840,9 @@ int32_t zb_mpc_box_closed_loop(int32_t dtype, int32_t device, void* stream, int6
     void* planx = w; w += align256(e * (size_t)Bsz * (N + 1) * 12);
     void* planu = w;
     return dtype == ZB_F32 ? box_solve<float>((cudaStream_t)stream, Bsz, N, A, B, x_lb, x_ub, u_lb, u_ub, tables, x0, opts, nullptr, planx, planu,
-                                              status_out, iters_out, state, Tsim, xSim_out, uSim_out, clip_margin)
+                                              status_out, iters_out, state, flags, device, Tsim, xSim_out, uSim_out, clip_margin)
                            : box_solve<double>((cudaStream_t)stream, Bsz, N, A, B, x_lb, x_ub, u_lb, u_ub, tables, x0, opts, nullptr, planx, planu,
-                                               status_out, iters_out, state, Tsim, xSim_out, uSim_out, clip_margin);
+                                               status_out, iters_out, state, flags, device, Tsim, xSim_out, uSim_out, clip_margin);
 }
 
 int32_t zb_mpc_box_build_tables(int32_t dtype, int32_t device, void* stream, int32_t N, const double* A, const double* B,
@@ -827,8 +862,8 @@ int32_t zb_mpc_box_build_tables(int32_t dtype, int32_t device, void* stream, int
 
 int32_t zb_mpc_box_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, const double* A, const double* B,
                          const double* x_lb, const double* x_ub, const double* u_lb, const double* u_ub, const void* tables,
-                         const void* x0, const zb_admm_opts* opts, void* u0_out, void* xTraj, void* uTraj, int8_t* status_out,
-                         int32_t* iters_out, void* workspace, size_t workspace_bytes) {
+                         const void* x0, const zb_admm_opts* opts, int32_t flags, void* u0_out, void* xTraj, void* uTraj,
+                         int8_t* status_out, int32_t* iters_out, void* workspace, size_t workspace_bytes) {
     ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "dtype must be ZB_F32 or ZB_F64 (got %d)", dtype);
     ZB_ARG(Bsz >= 0, "negative batch size");
     if (Bsz == 0) return 0;
@@ -840,9 +875,9 @@ int32_t zb_mpc_box_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
     DeviceGuard g(device);
     ZB_CUDA(g.err);
     return dtype == ZB_F32 ? box_solve<float>((cudaStream_t)stream, Bsz, N, A, B, x_lb, x_ub, u_lb, u_ub, tables, x0, opts, u0_out,
-                                              xTraj, uTraj, status_out, iters_out, workspace)
+                                              xTraj, uTraj, status_out, iters_out, workspace, flags, device)
                            : box_solve<double>((cudaStream_t)stream, Bsz, N, A, B, x_lb, x_ub, u_lb, u_ub, tables, x0, opts, u0_out,
-                                               xTraj, uTraj, status_out, iters_out, workspace);
+                                               xTraj, uTraj, status_out, iters_out, workspace, flags, device);
 }
 
 }  // extern "C"

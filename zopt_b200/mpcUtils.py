@@ -109,7 +109,8 @@ class lqrMpc():
         """
         Solve the MPC step at state x0 (zopt/mpcUtils.py:61-81).  Keyword arguments follow OSQP's names as passed through
         cvxpy in the reference demo (`eps_abs`, `eps_rel`, `max_iter`, `rho`, `sigma`, `alpha`); others are ignored.
-        `kernel="generic"` forces the one-thread-per-problem ADMM kernel where the shared-definition (12,4) kernel would run.
+        `kernel="generic"` forces the generic one-thread-per-problem ADMM kernel where the shared-definition (12,4) kernels would
+        run; `"thread"` / `"quad"` pick the shared-definition kernel with one / four threads per problem (default: by batch size).
 
         Returns
         -------
@@ -136,7 +137,7 @@ class lqrMpc():
                           float(kwargs.get("eps_abs", 1e-3)), float(kwargs.get("eps_rel", 1e-3)),
                           float(kwargs.get("eps_prim_inf", 1e-4)))
         if self._box is not None and kwargs.get("kernel", "auto") != "generic":
-            self._solve_box(x0, Bsz, opts, u0, xTraj, uTraj, status, iters)
+            self._solve_box(x0, Bsz, opts, u0, xTraj, uTraj, status, iters, {"auto": 0, "thread": 4, "quad": 8, "quad_global": 24}[kwargs.get("kernel", "auto")])
             self.iters = iters
             if not batched:
                 return u0[0], Trajectory(xTraj[0], uTraj[0]), STATUS[int(status[0])]
@@ -164,7 +165,7 @@ class lqrMpc():
             box["tables"], box["rho0"] = tables, opts.rho
         return box["tables"]
 
-    def _solve_box(self, x0, Bsz, opts, u0, xTraj, uTraj, status, iters):
+    def _solve_box(self, x0, Bsz, opts, u0, xTraj, uTraj, status, iters, variant=0):
         """bounded (12,4) problem shared by the batch -> zb_mpc_box_solve (csrc/mpc_box.cuh)"""
         dt, dev, N, box = self.dtype, self.device, self.N, self._box
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
@@ -173,7 +174,7 @@ class lqrMpc():
         wsb = lib.zb_mpc_box_workspace_bytes(dcode(dt), Bsz, N)
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         check(lib.zb_mpc_box_solve(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, dp(A), dp(B), dp(xlb), dp(xub), dp(ulb), dp(uub),
-                                   ptr(box["tables"]), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
+                                   ptr(box["tables"]), ptr(x0), C.byref(opts), variant, ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
                                    ptr(iters), ptr(ws), wsb))
 
     def closedLoop(self, x0, Tsim, clip=1e-6, **kwargs):
@@ -208,7 +209,8 @@ class lqrMpc():
         wsb = lib.zb_mpc_box_closed_loop_workspace_bytes(dcode(dt), Bsz, N)
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         check(lib.zb_mpc_box_closed_loop(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, Tsim, dp(A), dp(B), dp(xlb), dp(xub),
-                                         dp(ulb), dp(uub), ptr(tables), ptr(x0), C.byref(opts), float(clip), ptr(xS), ptr(uS),
+                                         dp(ulb), dp(uub), ptr(tables), ptr(x0), C.byref(opts),
+                                         {"auto": 0, "thread": 4, "quad": 8, "quad_global": 24}[kwargs.get("kernel", "auto")], float(clip), ptr(xS), ptr(uS),
                                          ptr(status), ptr(iters), ptr(ws), wsb))
         self.iters = iters
         if not batched:
