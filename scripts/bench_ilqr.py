@@ -23,8 +23,10 @@ uG = torch.as_tensor(d["uGuess"], dtype=dt, device=dev)
 solver = ilqrUtils.iterativeLqr if kind == "ilqr" else ilqrUtils.differentialDynamicProgramming
 args = (QuadcopterEuler(d["dt"]), QuadraticCost(d["Q"], d["R"]), QuadraticTerminalCost(d["Qf"]))
 reps = int(os.environ.get("REPS", 2))
-out = solver(*args, x0, uG, maxIter=iters, tol=-1.0)
-torch.cuda.synchronize()
+t_warm = time.time()
+while time.time() - t_warm < float(os.environ.get("WARM_S", 1.0)):  # let the clocks ramp up: a fresh process starts at idle clocks
+    out = solver(*args, x0, uG, maxIter=iters, tol=-1.0)
+    torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):

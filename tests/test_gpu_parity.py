@@ -423,6 +423,40 @@ def test_solvers_quadcopter_vs_oracle_fp64(second_order, R_scale, spread, dense_
         assert not bool(conv[b]) and int(log["iters"][b]) == iters
 
 
+@pytest.mark.parametrize("second_order", [False, True])
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_fused_forward_equals_two_kernel_forward(second_order, dt):
+    """The fused line-search kernel (csrc/ilqr_forward.cuh: cp.async-staged operands, in-warp argmin, copy / re-run commit)
+    performs the arithmetic of k_forward_costs + k_forward_commit in the same order: identical step sizes and bit-identical
+    trajectories, gains and costs, including problems whose winner is not one of the two speculatively stored step sizes,
+    ragged batch sizes (not a multiple of the 4 problems per CTA) and frozen (converged) problems."""
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    N, Bsz, iters = 37, 27, 4
+    x0, uG, Q, R, Qf = _quad_problem(N, Bsz, 77 + int(second_order), 0.2 if second_order else 1.0, 25.0)
+    uG = uG + np.random.default_rng(5).normal(size=uG.shape) * 2.0  # a poor guess: small step sizes win in early iterations
+    solver = ilqrUtils.differentialDynamicProgramming if second_order else ilqrUtils.iterativeLqr
+    args = (QuadcopterEuler(0.1), QuadraticCost(Q, R), QuadraticTerminalCost(Qf), cuda(x0, dt), cuda(uG, dt))
+    outs = []
+    for generic in (False, True):
+        ilqrUtils._GENERIC_FORWARD = generic
+        try:
+            outs.append(solver(*args, maxIter=iters, tol=-1.0, return_log=True))
+            outs.append(solver(*args, maxIter=iters, tol=50.0, return_log=True))  # some problems freeze early
+        finally:
+            ilqrUtils._GENERIC_FORWARD = False
+    def same(u, v):  # bit-identical, NaNs (diverged rollouts: a NaN cost wins the argmin, as jnp.argmin) in the same places
+        return torch.equal(torch.isnan(u), torch.isnan(v)) and torch.equal(u.nan_to_num(0.0), v.nan_to_num(0.0))
+
+    for a, b in ((outs[0], outs[2]), (outs[1], outs[3])):
+        assert torch.equal(a[4]["alpha_idx"], b[4]["alpha_idx"]) and torch.equal(a[4]["iters"], b[4]["iters"])
+        assert same(a[0].xTraj, b[0].xTraj) and same(a[0].uTraj, b[0].uTraj)
+        assert same(a[1], b[1]) and same(a[2], b[2]) and torch.equal(a[3], b[3]) and same(a[4]["J"], b[4]["J"])
+    assert int(torch.isnan(outs[0][2]).sum()) < Bsz // 2, "too many diverged problems for a meaningful comparison"
+    assert int((outs[0][4]["alpha_idx"] >= 2).sum()) > 0, "test problem never exercises the re-run path"
+    assert 0 < int(outs[1][3].sum()) , "test problem never exercises the frozen-problem path"
+
+
 def test_solver_fp32_and_convergence_flags():
     """fp32 run against the fp64 oracle: step-size sequences compared first, mismatches counted (never dropped);
     matching problems gated at x,u 2e-5 and L 1e-4.  Also per-problem convergence freeze."""

@@ -1,0 +1,275 @@
+// Fused 16-way line search of the iLQR / DDP solvers for the registered quadcopter model (n=12, m=4), fp32 and fp64.
+//
+// One launch = forwardPass2 (zopt/ilqrUtils.py:116-150) + the solver's bookkeeping (ilqrUtils.py:318-321) for every
+// active problem: 16 lanes of a half-warp roll out the 16 step sizes alpha = 0.5^j (ilqrUtils.py:139-146) with the state,
+// the control and the diagonal cost weights in registers, the costs are exchanged with shuffles, argmin (first minimum,
+// a NaN wins -- jnp.argmin) picks the winner and the same 16 lanes commit its trajectory:
+//   * the lanes of alpha = 1 and 1/2 (the usual winners) store their rollouts speculatively; if one of them won the
+//     half-warp copies it over the current trajectory with 128-bit accesses while it is still in L2;
+//   * otherwise the half-warp re-runs the winning step size (identical arithmetic) and lane 0 stores it in place.
+// The per-step operands every lane of a problem needs -- L_k (4x12), l_k, xPrev_k, uPrev_k: 68 words -- are the only
+// data the rollout reads.  They are streamed with cp.async into a 4-stage per-problem ring in shared memory (issued
+// three steps ahead, no registers held) and read back with 128-bit broadcast loads; the generic kernel's dependent
+// global loads of L_k were 64 % of its stall samples (profiles/r1s3_ilqr_forward_*).
+// Arithmetic order equals rollout_quad (zb_problems.cuh), so parity with the oracle is unchanged.
+#pragma once
+#include "zb_common.cuh"
+
+namespace zb {
+
+// solver bookkeeping shared by the generic commit kernel and the fused kernel
+struct CommitP {
+    void* J;             // (Bsz) current cost, updated in place (null for the bare forwardPass2 entry point)
+    uint8_t* converged;  // (Bsz)
+    int32_t* iters;      // (Bsz)
+    int32_t* alpha_log;  // (Bsz,maxIter) or null
+    void* J_log;         // (Bsz,maxIter+1) or null
+    int it, maxIter;
+    double tol;
+    void* J_out;         // bare entry point: (Bsz)
+    int32_t* idx_out;    // bare entry point: (Bsz) or null
+};
+
+struct FwdQuadP {
+    long long Bsz;
+    int N;
+    double dt;
+    Cost C;
+    const void *x0, *l, *L;
+    void *xTraj, *uTraj;  // current trajectory (xPrev, uPrev), replaced in place by the winner
+    void* spec;           // (2, Bsz, (N+1)*12 + N*4): speculative rollouts of alpha = 1, 1/2
+    void* Jall;           // (Bsz,16) or null
+    CommitP S;
+};
+
+__device__ __forceinline__ void fwd_cp16(void* dst_smem, const void* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void fwd_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void fwd_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory"); }
+
+__device__ __forceinline__ void st4(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void st4(double* p, const double* v) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+__device__ __forceinline__ void ld4(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double* v) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+constexpr int FWD_DEPTH = 4;   // ring stages (steps in flight: 3)
+constexpr int FWD_STAGE = 68;  // words per step: L 48 | l 4 | xPrev 12 | uPrev 4
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_forward_quad(FwdQuadP P) {
+    constexpr int n = 12, m = 4, D = FWD_DEPTH, ST = FWD_STAGE;
+    constexpr int EPC = 16 / (int)sizeof(T);  // words per 16-byte chunk
+    constexpr int NCH = ST / EPC;             // chunks per step: 34 (fp64) / 17 (fp32)
+    constexpr int C_L = 48 / EPC, C_l = 4 / EPC, C_X = 12 / EPC;
+    __shared__ __align__(16) T ring[4][D][ST];
+    const int tid = threadIdx.x, hw = tid >> 4, j = tid & 15;
+    const long long b = (long long)blockIdx.x * 4 + hw;
+    if (b >= P.Bsz) return;
+    if (P.S.converged && P.S.J && P.S.converged[b]) return;  // frozen problem (half-warp uniform)
+    const unsigned hmask = 0xFFFFu << (tid & 16);
+    const int N = P.N;
+    const T dt = T(P.dt);
+    const T* x0 = reinterpret_cast<const T*>(P.x0) + b * n;
+    T* xCur = reinterpret_cast<T*>(P.xTraj) + b * (long long)(N + 1) * n;
+    T* uCur = reinterpret_cast<T*>(P.uTraj) + b * (long long)N * m;
+    const long long per = (long long)(N + 1) * n + (long long)N * m;
+
+    // this lane's (up to three) 16-byte chunks of a step: source pointer at k = 0, words per step, offset in the stage
+    const T* csrc[3];
+    int cstr[3], coff[3];
+    bool cval[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int c = j + 16 * r;
+        cval[r] = c < NCH;
+        coff[r] = c * EPC;
+        if (c < C_L) {
+            csrc[r] = reinterpret_cast<const T*>(P.L) + b * (long long)N * 48 + c * EPC;
+            cstr[r] = 48;
+        } else if (c < C_L + C_l) {
+            csrc[r] = reinterpret_cast<const T*>(P.l) + b * (long long)N * 4 + (c - C_L) * EPC;
+            cstr[r] = 4;
+        } else if (c < C_L + C_l + C_X) {
+            csrc[r] = xCur + (c - C_L - C_l) * EPC;
+            cstr[r] = 12;
+        } else {
+            csrc[r] = uCur + (c - C_L - C_l - C_X) * EPC;
+            cstr[r] = 4;
+        }
+    }
+    T(*rg)[ST] = ring[hw];
+    auto issue = [&](int k) {
+        T* dst = rg[k % D];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            if (cval[r]) fwd_cp16(dst + coff[r], csrc[r] + (long long)k * cstr[r]);
+    };
+
+    // diagonal running-cost weights (the caller asserted ZB_COST_DIAGONAL)
+    T qd[n], rd[m];
+    {
+        const T* Q = P.C.Q.at<T>(b);
+        const T* R = P.C.R.at<T>(b);
+#pragma unroll
+        for (int i = 0; i < n; ++i) qd[i] = Q[i * 13];
+#pragma unroll
+        for (int i = 0; i < m; ++i) rd[i] = R[i * 5];
+    }
+    T alpha = T(1);
+    for (int i = 0; i < j; ++i) alpha *= T(0.5);  // 0.5**j exactly (ilqrUtils.py:145)
+    bool write = false;
+    T *wx = nullptr, *wu = nullptr;
+    if (P.spec != nullptr && j < 2) {
+        T* base = reinterpret_cast<T*>(P.spec) + (long long)j * P.Bsz * per;
+        wx = base + b * (long long)(N + 1) * n;
+        wu = base + P.Bsz * (long long)(N + 1) * n + b * (long long)N * m;
+        write = true;
+    }
+    int idx = 0;
+    T Jn = T(0);
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int s = 0; s < D - 1; ++s) {
+            if (s < N) issue(s);
+            fwd_commit();
+        }
+        T x[n], u[m], xd[n];
+        T J = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) x[i] = x0[i];
+        for (int k = 0; k < N; ++k) {
+            fwd_wait<D - 2>();
+            __syncwarp(hmask);  // step k's operands have landed for every lane; stage (k-1)%D is free again
+            if (k + D - 1 < N) issue(k + D - 1);
+            fwd_commit();
+            const T* st = rg[k % D];
+            T dx[n];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                T xp[4];
+                ld4(st + 52 + 4 * q, xp);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dx[4 * q + c] = x[4 * q + c] - xp[c];
+            }
+            T lk[4], up[4];
+            ld4(st + 48, lk);
+            ld4(st + 64, up);
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+                T s = T(0);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    T Lr[4];
+                    ld4(st + i * 12 + 4 * q, Lr);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s += Lr[c] * dx[4 * q + c];
+                }
+                u[i] = (alpha * lk[i] + s) + up[i];
+            }
+            if (write) {
+                st4(wx + (long long)k * n, x);
+                st4(wx + (long long)k * n + 4, x + 4);
+                st4(wx + (long long)k * n + 8, x + 8);
+                st4(wu + (long long)k * m, u);
+            }
+            {
+                T a = T(0), c = T(0);
+#pragma unroll
+                for (int i = 0; i < n; ++i) a += x[i] * (qd[i] * x[i]);
+#pragma unroll
+                for (int i = 0; i < m; ++i) c += u[i] * (rd[i] * u[i]);
+                J += a + c;
+            }
+            QuadTrig<T> tr = quad_trig(x);
+            quad_xdot(tr, x, u, xd);
+#pragma unroll
+            for (int i = 0; i < n; ++i) x[i] = x[i] + dt * xd[i];
+        }
+        if (write) {
+            st4(wx + (long long)N * n, x);
+            st4(wx + (long long)N * n + 4, x + 4);
+            st4(wx + (long long)N * n + 8, x + 8);
+        }
+        J += quad_form<T>(P.C.Qf.at<T>(b), x, n);
+        fwd_wait<0>();
+        __syncwarp(hmask);  // speculative stores visible to the half-warp; ring idle
+        if (pass == 1) break;
+        // ---- argmin over the 16 step sizes (ilqrUtils.py:147) ----
+        if (P.Jall) reinterpret_cast<T*>(P.Jall)[b * 16 + j] = J;
+        T Ja[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) Ja[q] = __shfl_sync(hmask, J, q, 16);
+        idx = argmin16<T>(Ja);
+        Jn = Ja[0];
+#pragma unroll
+        for (int q = 1; q < 16; ++q) Jn = (idx == q) ? Ja[q] : Jn;
+        if (P.spec != nullptr && idx < 2) {
+            // the winner was stored speculatively: copy it over the current trajectory, 16 bytes per lane
+            const T* base = reinterpret_cast<const T*>(P.spec) + (long long)idx * P.Bsz * per;
+            const int4* sx = reinterpret_cast<const int4*>(base + b * (long long)(N + 1) * n);
+            const int4* su = reinterpret_cast<const int4*>(base + P.Bsz * (long long)(N + 1) * n + b * (long long)N * m);
+            int4* dxp = reinterpret_cast<int4*>(xCur);
+            int4* dup = reinterpret_cast<int4*>(uCur);
+            const int nx4 = (N + 1) * n / EPC, nu4 = N * m / EPC;
+            int i = j;
+            for (; i + 48 < nx4; i += 64) {
+                const int4 a0 = sx[i], a1 = sx[i + 16], a2 = sx[i + 32], a3 = sx[i + 48];
+                dxp[i] = a0; dxp[i + 16] = a1; dxp[i + 32] = a2; dxp[i + 48] = a3;
+            }
+            for (; i < nx4; i += 16) dxp[i] = sx[i];
+            i = j;
+            for (; i + 48 < nu4; i += 64) {
+                const int4 a0 = su[i], a1 = su[i + 16], a2 = su[i + 32], a3 = su[i + 48];
+                dup[i] = a0; dup[i + 16] = a1; dup[i + 32] = a2; dup[i + 48] = a3;
+            }
+            for (; i < nu4; i += 16) dup[i] = su[i];
+            break;
+        }
+        // another step size won: every lane re-runs it (same arithmetic), lane 0 stores in place.  Row k of the current
+        // trajectory is overwritten only after its copy has landed in the ring.
+        alpha = T(1);
+        for (int i = 0; i < idx; ++i) alpha *= T(0.5);
+        write = (j == 0);
+        wx = xCur;
+        wu = uCur;
+    }
+    if (j != 0) return;
+    if (P.S.J) {
+        T* Jc = reinterpret_cast<T*>(P.S.J);
+        const T dJ = Jc[b] - Jn;
+        P.S.converged[b] = (fabs(dJ) <= T(P.S.tol)) ? 1 : 0;  // NaN compares false, as in the reference
+        Jc[b] = Jn;
+        P.S.iters[b] = P.S.it + 1;
+        if (P.S.alpha_log) P.S.alpha_log[b * (long long)P.S.maxIter + P.S.it] = idx;
+        if (P.S.J_log) reinterpret_cast<T*>(P.S.J_log)[b * (long long)(P.S.maxIter + 1) + P.S.it + 1] = Jn;
+    } else {
+        reinterpret_cast<T*>(P.S.J_out)[b] = Jn;
+        if (P.S.idx_out) P.S.idx_out[b] = idx;
+    }
+}
+
+inline bool fwd_quad_eligible(const Model& M, bool cost_diagonal) {
+    return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && cost_diagonal;
+}
+
+inline int32_t fwd_quad_launch(int32_t dtype, const FwdQuadP& P, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((P.Bsz + 3) / 4);
+    if (dtype == ZB_F32) k_forward_quad<float><<<grid, 64, 0, stream>>>(P);
+    else k_forward_quad<double><<<grid, 64, 0, stream>>>(P);
+    ZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace zb

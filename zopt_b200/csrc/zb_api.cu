@@ -9,6 +9,7 @@
 #include "mpc_coop.cuh"
 #include "mpc_box.cuh"
 #include "mpc_box_quad.cuh"
+#include "ilqr_forward.cuh"
 
 using namespace zb;
 
@@ -137,18 +138,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_forward_costs(RollP P, void* Ja
 }
 
 // forwardPass2 phase 2: argmin over the 16 costs, re-run the winning rollout and store it
-// (ilqrUtils.py:147-150), plus the solver's bookkeeping (ilqrUtils.py:318-321) when `S.J` is set.
-struct CommitP {
-    void* J;             // (Bsz) current cost, updated in place (null for the bare forwardPass2 entry point)
-    uint8_t* converged;  // (Bsz)
-    int32_t* iters;      // (Bsz)
-    int32_t* alpha_log;  // (Bsz,maxIter) or null
-    void* J_log;         // (Bsz,maxIter+1) or null
-    int it, maxIter;
-    double tol;
-    void* J_out;         // bare entry point: (Bsz)
-    int32_t* idx_out;    // bare entry point: (Bsz) or null
-};
+// (ilqrUtils.py:147-150), plus the solver's bookkeeping (ilqrUtils.py:318-321) when `S.J` is set (CommitP: ilqr_forward.cuh).
 
 // 16 lanes per problem: if the winner's trajectory was stored speculatively the lanes copy it (coalesced), otherwise
 // lane 0 re-runs the winning rollout in place (identical arithmetic, so identical values).
@@ -642,6 +632,7 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
                 alpha_log, J_log, (int)maxIter);
     SolveBackP Bk{Bsz, N, second_order, P.M, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
     const bool fast_bwd = ilqr_fast_eligible(P.M, second_order, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out);
+    const bool fast_fwd = !(flags & ZB_GENERIC_FORWARD) && fwd_quad_eligible(P.M, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out) && aligned16(x0);
     IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
     for (int it = 0; it < maxIter; ++it) {
         if (fast_bwd) {
@@ -649,8 +640,14 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
             if (rc) return rc;
         } else
             ZB_DISPATCH(dtype, k_solve_backward, gen_grid(Bsz), GEN_THREADS, stream, Bk);
-        ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall, (const uint8_t*)converged_out, spec);
         CommitP S{J_out, converged_out, iters_out, alpha_log, J_log, it, (int)maxIter, tol, nullptr, nullptr};
+        if (fast_fwd) {  // line search + commit + bookkeeping in one launch (ilqr_forward.cuh)
+            FwdQuadP Fw{Bsz, N, P.M.dt, P.C, x0, l_ws, L_out, xTraj, uTraj, spec, nullptr, S};
+            rc = fwd_quad_launch(dtype, Fw, s);
+            if (rc) return rc;
+            continue;
+        }
+        ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall, (const uint8_t*)converged_out, spec);
         ZB_DISPATCH(dtype, k_forward_commit, gen_grid(Bsz * 16), GEN_THREADS, stream, P, (const void*)Jall, S, (const void*)spec);
     }
     return 0;

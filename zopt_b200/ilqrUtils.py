@@ -211,6 +211,10 @@ def conditionValueFunction(Vf):
 
 
 # ------------------------------------------------------------------------------------------------ solvers
+# test hook: force the two-kernel line search (k_forward_costs + k_forward_commit) instead of the fused quadcopter kernel
+_GENERIC_FORWARD = False
+
+
 def _solve(dynamics, runningCost, terminalCost, x0, uGuess, maxIter, tol, second_order, return_log):
     model = require_model(dynamics)
     rc, tc = require_cost(runningCost, terminalCost)
@@ -240,6 +244,8 @@ def _solve(dynamics, runningCost, terminalCost, x0, uGuess, maxIter, tol, second
     from .mpcUtils import _is_diagonal
     Qd, Rd, Qfd = (vw.t for vw in ckeep)
     flags = (1 if second_order else 0) | (2 if all(_is_diagonal(t) for t in (Qd, Rd, Qfd)) else 0)
+    if _GENERIC_FORWARD:
+        flags |= 32  # ZB_GENERIC_FORWARD
     check(lib.zb_ilqr_solve(dcode(dtype), device.index, stream_ptr(device), Bsz, N, flags, C.byref(mspec),
                             C.byref(cspec), ptr(x0), ptr(uGuess), maxIter, float(tol), ptr(xTraj), ptr(uTraj), ptr(L),
                             ptr(J), ptr(conv), ptr(iters), ptr(alog), ptr(Jlog), ptr(ws), wsb))
