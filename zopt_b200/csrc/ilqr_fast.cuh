@@ -16,22 +16,10 @@
 //       written back "lower triangle wins" so v_xx stays exactly symmetric.
 // The algebra equals the reference's as-written expressions; parity with the oracle is gated at 1e-10 (fp64).
 #pragma once
-#include "zb_common.cuh"
+#include "ilqr_params.cuh"
 
 namespace zb {
 
-struct IlqrFastP {
-    long long Bsz;
-    int N;
-    double dt;
-    Cost C;
-    const void *xTraj, *uTraj;
-    const void* Czz;   // (Bsz,16,16)
-    const void* Vfxx;  // (Bsz,12,12)
-    const uint8_t* done;
-    void *l, *L;
-    double eps;  // ensurePositiveDefinite threshold (1e-3)
-};
 
 // slab layout in elements of T
 constexpr int IQ_V = 0;        // v_xx 12x12
@@ -47,18 +35,33 @@ constexpr int IQ_RS = 752;     // R+R' 4x4
 constexpr int IQ_VX = 768;     // v_x 12 (+4 pad)
 constexpr int IQ_XK = 784;     // x_k 12, u_k 4
 constexpr int IQ_QU = 800;     // Q_u 4
-constexpr int IQ_PS_F32 = 812;  // 812/4 = 203 odd
-constexpr int IQ_PS_F64 = 806;  // 806*8/16 = 403 odd (16-byte units)
+constexpr int IQ_XK2 = 804;    // second (x_k, u_k) buffer: the rows of step k-1 land here (cp.async) while step k computes
+constexpr int IQ_PS_F32 = 820;  // 820/4 = 205 odd
+constexpr int IQ_PS_F64 = 822;  // 822*8/16 = 411 odd (16-byte units)
 // diagonal-cost variant (Q, R, Qf diagonal => conditioned Hessians diagonal, c_ux = 0) with f_u's known sparsity:
 // no B, c_xx, Q+Q', c_ux, c_uu, R+R' matrices in the slab -> 420 words, twice as many problems (warps) per SM
 constexpr int ID_V = 0, ID_A = 144, ID_M = 288, ID_G = 336, ID_CXX = 352, ID_QS = 364, ID_CUU = 376, ID_RS = 380;
 constexpr int ID_VX = 384, ID_XK = 400, ID_QU = 416;
-constexpr int ID_PS_F32 = 420;  // 420/4 = 105 odd
-constexpr int ID_PS_F64 = 422;  // 422*8/16 = 211 odd
-// DDP (diagonal-cost variant only): + 81 words eigenvector exchange + 81 words clamped block  (+ pad)
+constexpr int ID_XK2 = 420;
+constexpr int ID_PS_F32 = 436;  // 436/4 = 109 odd
+constexpr int ID_PS_F64 = 438;  // 438*8/16 = 219 odd
+// DDP (diagonal-cost variant only): + 81 words eigenvector exchange + 81 words clamped block  (+ pad); no second (x_k, u_k)
+// buffer (it would cost the fp64 kernel its third CTA per SM): the trajectory rows are prefetched through registers
 constexpr int ID_WS = 420, ID_PC = 504;   // 84-word regions (81 used)
 constexpr int IDD_PS_F32 = 588;  // 588/4 = 147 odd
 constexpr int IDD_PS_F64 = 590;  // 590/2 = 295 odd
+
+// Structure of the quadcopter's dF/dx as generated in quad_model_gen.cuh::quad_jac_x: '0' structurally zero, '1' state-
+// independent constant, '2' depends on (x, u).  tests/test_abi_and_host_logic.py checks this table against the generated
+// source.  Only 17 of the 36 four-column chunks of f_x = I + dt dF/dx change along a trajectory; the others are stored once.
+__host__ __device__ constexpr int quad_jx_kind(int i, int j) {
+    constexpr char K[12][13] = {"222022020000", "222202220000", "222220220000", "000100000000", "000010000000", "000001000000",
+                                "000122220000", "000022200000", "000022220000", "222000222000", "222000222000", "222000220000"};
+    return K[i][j] - '0';
+}
+__host__ __device__ constexpr bool quad_jx_chunk_varies(int i, int q) {
+    return quad_jx_kind(i, 4 * q) == 2 || quad_jx_kind(i, 4 * q + 1) == 2 || quad_jx_kind(i, 4 * q + 2) == 2 || quad_jx_kind(i, 4 * q + 3) == 2;
+}
 
 template <typename T>
 struct Vec4 {
@@ -80,7 +83,7 @@ __device__ __forceinline__ void stv4(double* p, double a, double b, double c, do
     *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
 }
 __device__ __forceinline__ float rsq(float x) { return rsqrtf(x); }
-__device__ __forceinline__ double rsq(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ double rsq(double x) { return rsqrt(x); }  // MUFU.RSQ64H + Newton steps (~1 ulp) instead of DSQRT + DDIV
 
 // ---- cooperative 9x9 symmetric eigen-clamp for the DDP step (ilqrUtils.py:217-219 on the v_x . f_xx block) ----------
 // Cyclic Jacobi with COMPILE-TIME rotation indices: the packed lower triangle A[45] is replicated in the registers of the
@@ -218,6 +221,40 @@ __device__ __forceinline__ void jacobi_group(T (&A)[45], T (&Wr)[3][9], T* csbuf
         for (int j = 0; j < 9; ++j) Wr[r][j] = Wn[r][j];
 }
 
+// f_x = I + dt dF/dx into the slab: row i is written by thread i / 3 of the quad (divergent on purpose: each entry of dF/dx is
+// then evaluated once per quad by the thread that stores it, instead of by all four followed by a four-way select).
+// ALL = every chunk (once, before the sweep: the state-independent entries), otherwise only the chunks that vary.
+template <typename T, bool ALL>
+__device__ __forceinline__ void store_fx(T* As, const T* J, T dt, int t) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        if (t == i / 3) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if (ALL || quad_jx_chunk_varies(i, q)) {
+                    T e[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) e[c] = dt * J[i * 12 + 4 * q + c] + ((4 * q + c == i) ? T(1) : T(0));
+                    stv4(As + i * 12 + 4 * q, e[0], e[1], e[2], e[3]);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void bw_cp16(void* dst_smem, const void* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
+// this thread's quarter (4 words) of (x_k | u_k): x_k[4t..4t+3] for t < 3, u_k for t = 3
+template <typename T>
+__device__ __forceinline__ void stage_xu(T* dst16, const T* xT, const T* uT, int k, int t) {
+    const T* src = (t < 3) ? xT + (long long)k * 12 + 4 * t : uT + (long long)k * 4;
+    bw_cp16(dst16 + 4 * t, src);
+    if (sizeof(T) == 8) bw_cp16(dst16 + 4 * t + 2, src + 2);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
 template <typename T, bool CDIAG, bool DDP>
 __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -237,7 +274,9 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     T *Vs = S + (CDIAG ? ID_V : IQ_V), *As = S + (CDIAG ? ID_A : IQ_A), *Bs = S + IQ_B, *Cxx = S + (CDIAG ? ID_CXX : IQ_CXX);
     T *Qs = S + (CDIAG ? ID_QS : IQ_QS), *Ms = S + (CDIAG ? ID_M : IQ_M), *Cux = S + IQ_CUX, *Gs = S + (CDIAG ? ID_G : IQ_G);
     T *Cuu = S + (CDIAG ? ID_CUU : IQ_CUU), *Rs = S + (CDIAG ? ID_RS : IQ_RS), *vx = S + (CDIAG ? ID_VX : IQ_VX);
-    T *xk = S + (CDIAG ? ID_XK : IQ_XK), *Qu = S + (CDIAG ? ID_QU : IQ_QU);  // Bs, Cux unused when CDIAG
+    T *xk0 = S + (CDIAG ? ID_XK : IQ_XK), *Qu = S + (CDIAG ? ID_QU : IQ_QU);  // Bs, Cux unused when CDIAG
+    constexpr bool STAGE = !DDP;  // (x_k, u_k) through a two-slot cp.async buffer; the DDP slab has no room for the second slot
+    constexpr int XK2 = CDIAG ? (ID_XK2 - ID_XK) : (IQ_XK2 - IQ_XK);
     const int N = P.N;
     const T dt = T(P.dt);
     const T* xT = reinterpret_cast<const T*>(P.xTraj) + b * (long long)(N + 1) * 12;
@@ -253,7 +292,7 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
         const T* R = P.C.R.at<T>(b);
         const T* Qf = P.C.Qf.at<T>(b);
         if (CDIAG) {
-            for (int e = t; e < 144; e += 4) { Vs[e] = Vf[e]; As[e] = T(0); }
+            for (int e = t; e < 144; e += 4) Vs[e] = Vf[e];
             for (int i = t; i < 12; i += 4) { Cxx[i] = Czz[i * 17]; Qs[i] = T(2) * Q[i * 13]; }
             Cuu[t] = Czz[(12 + t) * 17];
             Rs[t] = T(2) * R[t * 5];
@@ -263,7 +302,6 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                 Cxx[e] = Czz[i * 16 + j];
                 Qs[e] = Q[i * 12 + j] + Q[j * 12 + i];
                 Vs[e] = Vf[e];
-                As[e] = T(0);
             }
             for (int e = t; e < 48; e += 4) {
                 const int a = e / 12, j = e % 12;
@@ -280,6 +318,14 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                 Bs[2 * 4 + 0] = -dt; Bs[3 * 4 + 1] = dt; Bs[4 * 4 + 2] = dt; Bs[5 * 4 + 3] = dt;
             }
         }
+        {   // the state-independent entries of f_x (zeros, 1 + dt * constants): dF/dx at the origin, folded at compile time
+            const T z12[12] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)}, z4[4] = {T(0), T(0), T(0), T(0)};
+            QuadTrig<T> tr0;
+            tr0.sph = T(0); tr0.cph = T(1); tr0.sth = T(0); tr0.cth = T(1); tr0.sps = T(0); tr0.cps = T(1); tr0.tth = T(0); tr0.sec = T(1);
+            T J0[144];
+            quad_jac_x(tr0, z12, z4, J0);
+            store_fx<T, true>(As, J0, dt, t);
+        }
         // v_x(N) = (Qf + Qf') x_N
         const T* xN = xT + (long long)N * 12;
         for (int i = t; i < 12; i += 4) {
@@ -294,44 +340,54 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     const int cstride = (t < 3) ? 12 : (CDIAG ? 12 : 4);
     const int tcol = (t < 3) ? 4 * t : 0;
 
-    // trajectory rows are prefetched one step ahead (the L2 round trip of x_{k-1}, u_{k-1} overlaps step k)
-    Vec4<T> px0 = ldv4(xT + (long long)(N - 1) * 12), px1 = ldv4(xT + (long long)(N - 1) * 12 + 4), px2 = ldv4(xT + (long long)(N - 1) * 12 + 8);
-    Vec4<T> pu0 = ldv4(uT + (long long)(N - 1) * 4);
+    // trajectory rows are fetched one step ahead: cp.async into the other (x_k, u_k) slot (iLQR), or through registers (DDP)
+    Vec4<T> px0, px1, px2, pu0;
+    if (STAGE) {
+        stage_xu(xk0 + ((N - 1) & 1) * XK2, xT, uT, N - 1, t);
+    } else {
+        px0 = ldv4(xT + (long long)(N - 1) * 12); px1 = ldv4(xT + (long long)(N - 1) * 12 + 4); px2 = ldv4(xT + (long long)(N - 1) * 12 + 8);
+        pu0 = ldv4(uT + (long long)(N - 1) * 4);
+    }
+    const int qbase = lane & 28;
     for (int k = N - 1; k >= 0; --k) {
-        // ---- 0. linearise at (x_k, u_k): every thread evaluates dF/dx (no divergence), stores 3 rows ----
+        T* xk = STAGE ? xk0 + (k & 1) * XK2 : xk0;
+        // ---- 0. linearise at (x_k, u_k) ----
         {
             T x[12], u[4], J[144];
-            const Vec4<T> x0 = px0, x1 = px1, x2 = px2, u0 = pu0;
-            {
-                const int kp = (k > 0) ? k - 1 : 0;
-                px0 = ldv4(xT + (long long)kp * 12); px1 = ldv4(xT + (long long)kp * 12 + 4); px2 = ldv4(xT + (long long)kp * 12 + 8);
-                pu0 = ldv4(uT + (long long)kp * 4);
-            }
+            if (STAGE) {
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+                __syncwarp();  // row k has landed for the whole quad; the other slot (read during step k+1) is free
+                stage_xu(xk0 + ((k - 1) & 1) * XK2, xT, uT, k > 0 ? k - 1 : 0, t);
+                const Vec4<T> x0 = ldv4(xk), x1 = ldv4(xk + 4), x2 = ldv4(xk + 8), u0 = ldv4(xk + 12);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { x[i] = x0.v[i]; x[4 + i] = x1.v[i]; x[8 + i] = x2.v[i]; u[i] = u0.v[i]; }
-            QuadTrig<T> tr = quad_trig(x);
-            quad_jac_x(tr, x, u, J);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                T row[12];
-#pragma unroll
-                for (int c = 0; c < 12; ++c) {
-                    const T j0 = J[r * 12 + c], j1 = J[(3 + r) * 12 + c], j2 = J[(6 + r) * 12 + c], j3 = J[(9 + r) * 12 + c];
-                    const T jv = (t == 0) ? j0 : (t == 1) ? j1 : (t == 2) ? j2 : j3;
-                    row[c] = dt * jv;
+                for (int i = 0; i < 4; ++i) { x[i] = x0.v[i]; x[4 + i] = x1.v[i]; x[8 + i] = x2.v[i]; u[i] = u0.v[i]; }
+            } else {
+                const Vec4<T> x0 = px0, x1 = px1, x2 = px2, u0 = pu0;
+                {
+                    const int kp = (k > 0) ? k - 1 : 0;
+                    px0 = ldv4(xT + (long long)kp * 12); px1 = ldv4(xT + (long long)kp * 12 + 4); px2 = ldv4(xT + (long long)kp * 12 + 8);
+                    pu0 = ldv4(uT + (long long)kp * 4);
                 }
-                // + identity: row index 3t+r, so column 3t+r gets +1
 #pragma unroll
-                for (int c = 0; c < 12; ++c) row[c] += (c == 3 * t + r) ? T(1) : T(0);
-                T* dst = As + (3 * t + r) * 12;
-                stv4(dst, row[0], row[1], row[2], row[3]);
-                stv4(dst + 4, row[4], row[5], row[6], row[7]);
-                stv4(dst + 8, row[8], row[9], row[10], row[11]);
-            }
-            {
+                for (int i = 0; i < 4; ++i) { x[i] = x0.v[i]; x[4 + i] = x1.v[i]; x[8 + i] = x2.v[i]; u[i] = u0.v[i]; }
                 const Vec4<T> mine = (t == 0) ? x0 : (t == 1) ? x1 : (t == 2) ? x2 : u0;  // x_k quarter / u_k
                 stv4(xk + 4 * t, mine.v[0], mine.v[1], mine.v[2], mine.v[3]);
             }
+            // sin / cos of the three Euler angles: one angle per thread of the quad (thread 3 idles along with psi), exchanged
+            // with shuffles -- the same sincos() result whichever thread evaluates it
+            QuadTrig<T> tr;
+            {
+                const T ang = (t == 0) ? x[6] : (t == 1) ? x[7] : x[8];
+                T sv, cv;
+                sincos(ang, &sv, &cv);
+                tr.sph = __shfl_sync(0xffffffffu, sv, qbase); tr.cph = __shfl_sync(0xffffffffu, cv, qbase);
+                tr.sth = __shfl_sync(0xffffffffu, sv, qbase + 1); tr.cth = __shfl_sync(0xffffffffu, cv, qbase + 1);
+                tr.sps = __shfl_sync(0xffffffffu, sv, qbase + 2); tr.cps = __shfl_sync(0xffffffffu, cv, qbase + 2);
+                tr.sec = T(1) / tr.cth;
+                tr.tth = tr.sth * tr.sec;
+            }
+            quad_jac_x(tr, x, u, J);
+            store_fx<T, false>(As, J, dt, t);
             if (DDP) {
                 // conditionQuadraticDynamics (ilqrUtils.py:237-251): H = dt * sum_i v_x[i] d2F_i/dx2 touches states 0..8 only,
                 // f_ux = f_uu = 0, so clampPD(blockdiag(H9, 0)) = blockdiag(clampPD(H9), eps I) exactly.
@@ -613,10 +669,6 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
 }
 
 // launch the cooperative backward pass
-inline bool ilqr_fast_eligible(const Model& M, int second_order, bool cost_diagonal) {
-    return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && (!second_order || cost_diagonal);
-}
-
 template <typename T, bool CDIAG, bool DDP = false>
 inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
     constexpr int PS = DDP ? (sizeof(T) == 4 ? IDD_PS_F32 : IDD_PS_F64)
@@ -631,7 +683,7 @@ inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
     return 0;
 }
 
-inline int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream, bool cost_diagonal, bool second_order) {
+int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream, bool cost_diagonal, bool second_order) {
     if (second_order)  // eligibility (diagonal costs) is checked by the caller
         return dtype == ZB_F32 ? ilqr_fast_launch_impl<float, true, true>(P, stream) : ilqr_fast_launch_impl<double, true, true>(P, stream);
     if (dtype == ZB_F32) return cost_diagonal ? ilqr_fast_launch_impl<float, true>(P, stream) : ilqr_fast_launch_impl<float, false>(P, stream);

@@ -13,34 +13,9 @@
 // global loads of L_k were 64 % of its stall samples (profiles/r1s3_ilqr_forward_*).
 // Arithmetic order equals rollout_quad (zb_problems.cuh), so parity with the oracle is unchanged.
 #pragma once
-#include "zb_common.cuh"
+#include "ilqr_params.cuh"
 
 namespace zb {
-
-// solver bookkeeping shared by the generic commit kernel and the fused kernel
-struct CommitP {
-    void* J;             // (Bsz) current cost, updated in place (null for the bare forwardPass2 entry point)
-    uint8_t* converged;  // (Bsz)
-    int32_t* iters;      // (Bsz)
-    int32_t* alpha_log;  // (Bsz,maxIter) or null
-    void* J_log;         // (Bsz,maxIter+1) or null
-    int it, maxIter;
-    double tol;
-    void* J_out;         // bare entry point: (Bsz)
-    int32_t* idx_out;    // bare entry point: (Bsz) or null
-};
-
-struct FwdQuadP {
-    long long Bsz;
-    int N;
-    double dt;
-    Cost C;
-    const void *x0, *l, *L;
-    void *xTraj, *uTraj;  // current trajectory (xPrev, uPrev), replaced in place by the winner
-    void* spec;           // (2, Bsz, (N+1)*12 + N*4): speculative rollouts of alpha = 1, 1/2
-    void* Jall;           // (Bsz,16) or null
-    CommitP S;
-};
 
 __device__ __forceinline__ void fwd_cp16(void* dst_smem, const void* src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -260,11 +235,94 @@ __global__ void __launch_bounds__(64) k_forward_quad(FwdQuadP P) {
     }
 }
 
-inline bool fwd_quad_eligible(const Model& M, bool cost_diagonal) {
-    return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && cost_diagonal;
+// Once per solve, quadcopter + diagonal costs: (i) conditionQuadraticCost / conditionValueFunction (ilqrUtils.py:222-234,
+// 254-257) of a diagonal Hessian -- its eigenvectors are the identity, so V max(L, eps) V' = diag(max(2 q_i, eps)) exactly,
+// which is also what the generic Jacobi routine returns (no rotation is ever applied); (ii) the initial rollout
+// u_k = uGuess_k (ilqrUtils.py:292-298) with the state in registers; (iii) the solver state.  Same arithmetic as
+// k_solve_prep + k_solve_init (zb_api.cu), 10x faster than their run-time-sized local-memory bodies.
+template <typename T>
+__global__ void __launch_bounds__(64) k_solve_setup_quad(SetupQuadP P) {
+    constexpr int n = 12, m = 4;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= P.Bsz) return;
+    const int N = P.N;
+    const T eps = T(P.eps), dt = T(P.dt);
+    const T* Q = P.C.Q.at<T>(b);
+    const T* R = P.C.R.at<T>(b);
+    const T* Qf = P.C.Qf.at<T>(b);
+    T qd[n], rd[m];
+#pragma unroll
+    for (int i = 0; i < n; ++i) qd[i] = Q[i * 13];
+#pragma unroll
+    for (int i = 0; i < m; ++i) rd[i] = R[i * 5];
+    {
+        T* cz = reinterpret_cast<T*>(P.Czz) + b * 256;
+        for (int e = 0; e < 256; ++e) cz[e] = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) { const T h = qd[i] + qd[i]; cz[i * 17] = h > eps ? h : eps; }
+#pragma unroll
+        for (int i = 0; i < m; ++i) { const T h = rd[i] + rd[i]; cz[(n + i) * 17] = h > eps ? h : eps; }
+        T* vf = reinterpret_cast<T*>(P.Vfxx) + b * 144;
+        for (int e = 0; e < 144; ++e) vf[e] = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) { const T h = Qf[i * 13] + Qf[i * 13]; vf[i * 13] = h > eps ? h : eps; }
+    }
+    const T* x0 = reinterpret_cast<const T*>(P.x0) + b * n;
+    const T* ug = reinterpret_cast<const T*>(P.uGuess) + b * (long long)N * m;
+    T* xT = reinterpret_cast<T*>(P.xTraj) + b * (long long)(N + 1) * n;
+    T* uT = reinterpret_cast<T*>(P.uTraj) + b * (long long)N * m;
+    T x[n], u[m], xd[n];
+    T Jc = T(0);
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = x0[i];
+    T un[m];
+    if (N > 0) ld4(ug, un);
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int i = 0; i < m; ++i) u[i] = un[i];
+        if (k + 1 < N) ld4(ug + (long long)(k + 1) * m, un);
+        st4(xT + (long long)k * n, x);
+        st4(xT + (long long)k * n + 4, x + 4);
+        st4(xT + (long long)k * n + 8, x + 8);
+        st4(uT + (long long)k * m, u);
+        {   // quad_form(Q, x) + quad_form(R, u) of diagonal Q, R: the off-diagonal terms of the dense form add exact zeros
+            T a = T(0), c = T(0);
+#pragma unroll
+            for (int i = 0; i < n; ++i) a += x[i] * (qd[i] * x[i]);
+#pragma unroll
+            for (int i = 0; i < m; ++i) c += u[i] * (rd[i] * u[i]);
+            Jc += a + c;
+        }
+        QuadTrig<T> tr = quad_trig(x);
+        quad_xdot(tr, x, u, xd);
+#pragma unroll
+        for (int i = 0; i < n; ++i) x[i] = x[i] + dt * xd[i];
+    }
+    st4(xT + (long long)N * n, x);
+    st4(xT + (long long)N * n + 4, x + 4);
+    st4(xT + (long long)N * n + 8, x + 8);
+    Jc += quad_form<T>(Qf, x, n);
+    reinterpret_cast<T*>(P.J)[b] = Jc;
+    P.converged[b] = 0;
+    P.iters[b] = 0;
+    if (P.alpha_log)
+        for (int i = 0; i < P.maxIter; ++i) P.alpha_log[b * (long long)P.maxIter + i] = -1;
+    if (P.J_log) {
+        T* jl = reinterpret_cast<T*>(P.J_log) + b * (long long)(P.maxIter + 1);
+        jl[0] = Jc;
+        for (int i = 1; i <= P.maxIter; ++i) jl[i] = Jc * T(0) + T(NAN);
+    }
 }
 
-inline int32_t fwd_quad_launch(int32_t dtype, const FwdQuadP& P, cudaStream_t stream) {
+int32_t solve_setup_quad_launch(int32_t dtype, const SetupQuadP& P, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((P.Bsz + 63) / 64);
+    if (dtype == ZB_F32) k_solve_setup_quad<float><<<grid, 64, 0, stream>>>(P);
+    else k_solve_setup_quad<double><<<grid, 64, 0, stream>>>(P);
+    ZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int32_t fwd_quad_launch(int32_t dtype, const FwdQuadP& P, cudaStream_t stream) {
     const unsigned grid = (unsigned)((P.Bsz + 3) / 4);
     if (dtype == ZB_F32) k_forward_quad<float><<<grid, 64, 0, stream>>>(P);
     else k_forward_quad<double><<<grid, 64, 0, stream>>>(P);

@@ -1,0 +1,72 @@
+// Parameter blocks and host launchers of the quadcopter iLQR / DDP kernels (ilqr_fast.cuh, ilqr_forward.cuh).
+// The kernels are compiled in their own translation unit (zb_ilqr_kernels.cu); zb_api.cu only sees this header.
+#pragma once
+#include "zb_common.cuh"
+
+namespace zb {
+
+struct IlqrFastP {
+    long long Bsz;
+    int N;
+    double dt;
+    Cost C;
+    const void *xTraj, *uTraj;
+    const void* Czz;   // (Bsz,16,16)
+    const void* Vfxx;  // (Bsz,12,12)
+    const uint8_t* done;
+    void *l, *L;
+    double eps;  // ensurePositiveDefinite threshold (1e-3)
+};
+
+// solver bookkeeping shared by the generic commit kernel and the fused kernel
+struct CommitP {
+    void* J;             // (Bsz) current cost, updated in place (null for the bare forwardPass2 entry point)
+    uint8_t* converged;  // (Bsz)
+    int32_t* iters;      // (Bsz)
+    int32_t* alpha_log;  // (Bsz,maxIter) or null
+    void* J_log;         // (Bsz,maxIter+1) or null
+    int it, maxIter;
+    double tol;
+    void* J_out;         // bare entry point: (Bsz)
+    int32_t* idx_out;    // bare entry point: (Bsz) or null
+};
+
+struct FwdQuadP {
+    long long Bsz;
+    int N;
+    double dt;
+    Cost C;
+    const void *x0, *l, *L;
+    void *xTraj, *uTraj;  // current trajectory (xPrev, uPrev), replaced in place by the winner
+    void* spec;           // (2, Bsz, (N+1)*12 + N*4): speculative rollouts of alpha = 1, 1/2
+    void* Jall;           // (Bsz,16) or null
+    CommitP S;
+};
+
+// once per solve: conditioned cost blocks of a DIAGONAL quadratic cost + the initial rollout u_k = uGuess_k
+struct SetupQuadP {
+    long long Bsz;
+    int N, maxIter;
+    double dt, eps;
+    Cost C;
+    const void *x0, *uGuess;
+    void *xTraj, *uTraj, *J;
+    uint8_t* converged;
+    int32_t* iters;
+    int32_t* alpha_log;  // (Bsz,maxIter) or null
+    void* J_log;         // (Bsz,maxIter+1) or null
+    void *Czz, *Vfxx;    // (Bsz,16,16), (Bsz,12,12)
+};
+
+inline bool ilqr_fast_eligible(const Model& M, int second_order, bool cost_diagonal) {
+    return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && (!second_order || cost_diagonal);
+}
+inline bool fwd_quad_eligible(const Model& M, bool cost_diagonal) {
+    return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && cost_diagonal;
+}
+// backward pass (ilqr_fast.cuh) and fused line search (ilqr_forward.cuh); defined in zb_ilqr_kernels.cu
+int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream, bool cost_diagonal, bool second_order);
+int32_t fwd_quad_launch(int32_t dtype, const FwdQuadP& P, cudaStream_t stream);
+int32_t solve_setup_quad_launch(int32_t dtype, const SetupQuadP& P, cudaStream_t stream);
+
+}  // namespace zb

@@ -4,12 +4,11 @@
 
 #include "zb_common.cuh"
 #include "lqr_fast.cuh"
-#include "ilqr_fast.cuh"
+#include "ilqr_params.cuh"
 #include "lqr_t1.cuh"
 #include "mpc_coop.cuh"
 #include "mpc_box.cuh"
 #include "mpc_box_quad.cuh"
-#include "ilqr_forward.cuh"
 
 using namespace zb;
 
@@ -627,12 +626,18 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     ZB_CUDA(cudaMemsetAsync(L_out, 0, e * Bsz * N * m * n, s));
     P.x0 = x0; P.l = l_ws; P.L = L_out; P.xPrev = xTraj; P.uPrev = uTraj;
     P.xTraj = xTraj; P.uTraj = uTraj; P.J = nullptr;
-    ZB_DISPATCH(dtype, k_solve_prep, gen_grid(Bsz), GEN_THREADS, stream, (long long)Bsz, n, m, P.C, 1e-3, Czz, Vfxx);
-    ZB_DISPATCH(dtype, k_solve_init, gen_grid(Bsz), GEN_THREADS, stream, P, uGuess, J_out, converged_out, iters_out,
-                alpha_log, J_log, (int)maxIter);
+    const bool fast_fwd = !(flags & ZB_GENERIC_FORWARD) && fwd_quad_eligible(P.M, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out) && aligned16(x0);
+    if (fast_fwd && aligned16(uGuess)) {  // diagonal costs + quadcopter: closed-form conditioning and a register-resident initial rollout
+        SetupQuadP Sp{Bsz, N, (int)maxIter, P.M.dt, 1e-3, P.C, x0, uGuess, xTraj, uTraj, J_out, converged_out, iters_out, alpha_log, J_log, Czz, Vfxx};
+        rc = solve_setup_quad_launch(dtype, Sp, s);
+        if (rc) return rc;
+    } else {
+        ZB_DISPATCH(dtype, k_solve_prep, gen_grid(Bsz), GEN_THREADS, stream, (long long)Bsz, n, m, P.C, 1e-3, Czz, Vfxx);
+        ZB_DISPATCH(dtype, k_solve_init, gen_grid(Bsz), GEN_THREADS, stream, P, uGuess, J_out, converged_out, iters_out,
+                    alpha_log, J_log, (int)maxIter);
+    }
     SolveBackP Bk{Bsz, N, second_order, P.M, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
     const bool fast_bwd = ilqr_fast_eligible(P.M, second_order, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out);
-    const bool fast_fwd = !(flags & ZB_GENERIC_FORWARD) && fwd_quad_eligible(P.M, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out) && aligned16(x0);
     IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
     for (int it = 0; it < maxIter; ++it) {
         if (fast_bwd) {
