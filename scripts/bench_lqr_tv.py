@@ -15,7 +15,10 @@ A, B = Quadcopter().linearizeInertial(xbar, ubar, 0.1)
 Q = torch.diag_embed(torch.as_tensor(d["qdiag"], dtype=f32, device=dev)); R = torch.diag_embed(torch.as_tensor(d["rdiag"], dtype=f32, device=dev))
 ex = lambda t: t[:, None].expand(-1, N, -1, -1)
 def timeit(name, args):
-    discreteFiniteHorizonLqr(*args, N); torch.cuda.synchronize()
+    import time
+    t0 = time.time()
+    while time.time() - t0 < 0.5:  # clock ramp-up
+        L = discreteFiniteHorizonLqr(*args, N); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5): L = discreteFiniteHorizonLqr(*args, N)

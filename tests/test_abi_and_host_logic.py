@@ -106,3 +106,25 @@ def test_pytree_semantics():  # container half of reference tests/test_pytrees.p
             tree(*args)
     dJ = pytrees.QuadraticDeltaCost(1, 2)
     assert dJ(1) == 3 and dJ(0.5) == 1
+
+
+def test_quadcopter_jacobian_structure_table_matches_generated_model():
+    """csrc/ilqr_fast.cuh::quad_jx_kind (which entries of dF/dx are zero / constant / state-dependent: the backward kernel
+    rewrites only the chunks of f_x that vary) must agree with the sympy-generated csrc/quad_model_gen.cuh::quad_jac_x."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gen = open(os.path.join(root, "zopt_b200", "csrc", "quad_model_gen.cuh")).read()
+    a = gen.index("ZB_HD void quad_jac_x(const QuadTrig<T>& tr")
+    body = gen[a:gen.index("\n}\n", a)]
+    kind = {}
+    for m in re.finditer(r"J\[(\d+)\] = (.*);", body):
+        rhs = m.group(2).strip()
+        kind[int(m.group(1))] = 0 if rhs == "T(0)" else (2 if re.search(r"\b(t\d+|x\[|u\[|tr\.)", rhs) else 1)
+    assert sorted(kind) == list(range(144))
+    fast = open(os.path.join(root, "zopt_b200", "csrc", "ilqr_fast.cuh")).read()
+    a = fast.index("constexpr char K[12][13] = {")
+    rows = re.findall(r'"([012]{12})"', fast[a:fast.index("};", a)])
+    assert len(rows) == 12
+    assert [int(c) for r in rows for c in r] == [kind[i] for i in range(144)]
+    # 17 of the 36 four-column chunks vary along a trajectory (the count the kernel's comments and DESIGN.md quote)
+    assert sum(any(kind[i * 12 + 4 * q + c] == 2 for c in range(4)) for i in range(12) for q in range(3)) == 17

@@ -41,9 +41,10 @@ __device__ __forceinline__ void ld4(const double* p, double* v) {
 
 constexpr int FWD_DEPTH = 4;   // ring stages (steps in flight: 3)
 constexpr int FWD_STAGE = 68;  // words per step: L 48 | l 4 | xPrev 12 | uPrev 4
+// resident 64-thread CTAs per SM asked of the compiler: fp64 8 (16 warps, caps the kernel at 128 registers), fp32 12
 
 template <typename T>
-__global__ void __launch_bounds__(64) k_forward_quad(FwdQuadP P) {
+__global__ void __launch_bounds__(64, sizeof(T) == 8 ? 8 : 12) k_forward_quad(FwdQuadP P) {
     constexpr int n = 12, m = 4, D = FWD_DEPTH, ST = FWD_STAGE;
     constexpr int EPC = 16 / (int)sizeof(T);  // words per 16-byte chunk
     constexpr int NCH = ST / EPC;             // chunks per step: 34 (fp64) / 17 (fp32)

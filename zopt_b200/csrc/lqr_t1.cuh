@@ -386,46 +386,58 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
 
 // -------------------------------------------------------------------------------------------------------------
 // Time-varying discreteFiniteHorizonLqr (zopt/lqrUtils.py:144-173 with genuinely different A[k], B[k], Q[k], R[k]), fp32,
-// (12,4).  Same per-thread step; the step's operands are STREAMED from HBM: the warp copies the 32 problems' blocks with
-// coalesced 128-bit loads (consecutive lanes = consecutive 16 B of one problem's block) into the lane-interleaved slab,
-// whose rows are padded to 33 float4 so that both the transposing store (stride 33) and the per-thread reads (stride 1)
-// are bank-conflict free.  1,408 B per problem-step: this path is HBM / LSU bound, not FMA bound.
-constexpr int RS_TV = 33;
+// (12,4).  Same per-thread step; the step's operands are STREAMED from HBM with cp.async, each lane copying ITS OWN
+// problem's blocks (76 x 16 B: A 36, B 12, the lower-triangle chunks of Q 24, R 4 -- 1,216 B per problem-step) straight
+// into its column of the lane-interleaved slab: consecutive lanes write consecutive 16 B (conflict-free without padding,
+// so the slab is 112 x 32 float4 = 56 KB and FOUR one-warp CTAs fit an SM), source and destination offsets are
+// instruction immediates (2 instructions per copy), and a lane's reads walk its problem's contiguous blocks, so every
+// fetched 32-byte sector is used in full.  The blocks of step k-1 are prefetched into L2 while step k computes, and their
+// copies are issued as soon as the lane's own step is done (the slots are private), overlapping the gain stores.
+// History (ncu: profiles/r1s3_lqr_tv_*), 65,536 solves x N=50: v1 issued coalesced copies with a per-copy transposing
+// (problem, chunk) index into a padded slab (7,300 instructions per step, 3 CTAs per SM): 2.76 ms; v2 (this one,
+// 4,900 instructions per step, 4 CTAs per SM): 1.88 ms; v3 made the copies coalesced again with a fixed per-lane
+// schedule (four problems x eight consecutive chunks per instruction, 8-way bank conflicts on the shared-memory side):
+// 2.17 ms, 2.32 ms with the L2 prefetch -- slower than the scattered but conflict-free copies, so it was dropped.
+// Bound: the load/store unit (operand copies + the step's own 128-bit shared-memory reads: lg_throttle 21 %,
+// short_scoreboard 30 % of the stall samples), not the FMA pipe and not yet HBM (2.5 TB/s of 6.5).
+constexpr int RS_TV = 32;
 constexpr int NF4_TV = 112;  // X 48 + W 36 + Q 24 + R 4 (full rows)
 
 __device__ __forceinline__ void cp_async16(float4* dst_smem, const float4* src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
-// all 88 float4 per problem of step k are put in flight with cp.async (no registers, one HBM latency per step instead of
-// one per dependent load batch), transposed on the fly into the padded lane-interleaved slab
-__device__ __forceinline__ void tv_load_step(float4* sm, const FastP& P, long long b0, int k, int lane) {
-    // A: 36 float4 per problem -> slots X4 + r*4 + c ; B: 12 -> X4 + r*4 + 3 ; Q: 36 (upper chunks skipped) ; R: 4
-#pragma unroll 4
-    for (int it = 0; it < 36; ++it) {
-        const int i = it * 32 + lane, p = i / 36, j = i - p * 36, r = j / 3, c = j - r * 3;
-        long long pb = b0 + p;
-        if (pb >= P.Bsz) pb = P.Bsz - 1;
-        cp_async16(&sm[(X4 + r * 4 + c) * RS_TV + p], reinterpret_cast<const float4*>(P.A.at<float>(pb, k)) + j);
-        if (c <= r / 4) cp_async16(&sm[(Q4 + qoff(r) + c) * RS_TV + p], reinterpret_cast<const float4*>(P.Q.at<float>(pb, k)) + j);
-    }
-#pragma unroll 4
-    for (int it = 0; it < 12; ++it) {
-        const int i = it * 32 + lane, p = i / 12, j = i - p * 12;
-        long long pb = b0 + p;
-        if (pb >= P.Bsz) pb = P.Bsz - 1;
-        cp_async16(&sm[(X4 + j * 4 + 3) * RS_TV + p], reinterpret_cast<const float4*>(P.B.at<float>(pb, k)) + j);
+__device__ __forceinline__ void tv_load_step(float4* S, const FastP& P, long long b, int k) {
+    const float4* gA = reinterpret_cast<const float4*>(P.A.at<float>(b, k));
+    const float4* gB = reinterpret_cast<const float4*>(P.B.at<float>(b, k));
+    const float4* gQ = reinterpret_cast<const float4*>(P.Q.at<float>(b, k));
+    const float4* gR = reinterpret_cast<const float4*>(P.R.at<float>(b, k));
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cp_async16(&S[(X4 + r * 4 + c) * RS_TV], gA + r * 3 + c);
+        cp_async16(&S[(X4 + r * 4 + 3) * RS_TV], gB + r);
     }
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int i = it * 32 + lane, p = i / 4, j = i - p * 4;
-        long long pb = b0 + p;
-        if (pb >= P.Bsz) pb = P.Bsz - 1;
-        cp_async16(&sm[(R4 + j) * RS_TV + p], reinterpret_cast<const float4*>(P.R.at<float>(pb, k)) + j);
-    }
+    for (int r = 0; r < 12; ++r)
+#pragma unroll
+        for (int c = 0; c <= r / 4; ++c) cp_async16(&S[(Q4 + qoff(r) + c) * RS_TV], gQ + r * 3 + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cp_async16(&S[(R4 + j) * RS_TV], gR + j);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+// pull the blocks of step k into L2: one request per 128-byte line a 16-byte-aligned block can touch
+__device__ __forceinline__ void tv_prefetch_step(const FastP& P, long long b, int k) {
+    const char* gA = reinterpret_cast<const char*>(P.A.at<float>(b, k));
+    const char* gB = reinterpret_cast<const char*>(P.B.at<float>(b, k));
+    const char* gQ = reinterpret_cast<const char*>(P.Q.at<float>(b, k));
+    const char* gR = reinterpret_cast<const char*>(P.R.at<float>(b, k));
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { prefetch_l2(gA + (i < 5 ? i * 128 : 560)); prefetch_l2(gQ + (i < 5 ? i * 128 : 560)); }
+    prefetch_l2(gB); prefetch_l2(gB + 128); prefetch_l2(gB + 176);
+    prefetch_l2(gR); prefetch_l2(gR + 48);
 }
 
 __global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P) {
@@ -439,12 +451,16 @@ __global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P) {
     float v[78];
     load_sym_lower(P.Q.at<float>(b, P.T - 1), v);  // lqrUtils.py:172: terminal value is Q[-1]
     float* gpub = P.gains + b0 * (long long)P.N * 48;
+    tv_load_step(S, P, b, P.N - 1);
     for (int k = P.N - 1; k >= 0; --k) {
-        __syncwarp();  // everybody is done with the previous step's operands (and the staging area)
-        tv_load_step(sm, P, b0, k, lane);
-        __syncwarp();
+        if (k > 0) tv_prefetch_step(P, b, k - 1);  // HBM -> L2 while this step computes
+        __syncwarp();  // everybody is done with the staging area (the W region) of the previous step
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");  // each lane reads only what it copied itself
         float L[4][12];
         riccati_step<false, RS_TV, true>(S, v, L);
+        // the operand slots are private to the lane and free from here on: the copies of step k-1 (L2 hits) overlap the
+        // gain transposition and stores below
+        if (k > 0) tv_load_step(S, P, b, k - 1);
         float4* stg = sm + W4 * RS_TV;  // W region is free now: transpose the gains for coalesced stores
         __syncwarp();
 #pragma unroll
