@@ -207,6 +207,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner / INFO lines must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     from zopt_b200 import _lib
     from zopt_b200.mpcUtils import lqrMpc

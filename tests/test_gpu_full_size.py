@@ -1,0 +1,220 @@
+"""
+GPU tests (-m gpu) at BASELINE.json's FULL sizes (cfg 2: 65,536 problems; cfg 3/4/5: 16,384 problems), where the oracle
+cannot run the whole batch in seconds.  Parity is carried by
+  * the oracle on a random subset of the benchmark batch ("checked on a random subset of every benchmark
+    batch"), with the tolerances of tests/test_gpu_parity.py, and
+  * size-independent properties of the whole batch: batch-split invariance (problem b solved inside the full batch ==
+    the same problem solved in a small batch, BIT FOR BIT: no cross-problem contamination, no dependence on the CTA /
+    wave a problem lands in), permutation equivariance, the plan obeying the dynamics it was computed for, the
+    Riccati identity J(plan) = x0' V0 x0, monotone line-search costs.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ilqr as oilqr  # noqa: E402
+from oracle import lqr as olqr  # noqa: E402
+from oracle.quadcopter import Quadcopter as OQuadcopter  # noqa: E402
+from zopt_b200 import configs  # noqa: E402
+
+DEV = "cuda"
+
+
+def _t(a, dt):
+    return torch.as_tensor(np.asarray(a), dtype=dt, device=DEV)
+
+
+def _same(u, v):
+    return torch.equal(torch.isnan(u), torch.isnan(v)) and torch.equal(u.nan_to_num(0.0), v.nan_to_num(0.0))
+
+
+def _relerr(a, b):
+    a = a.detach().cpu().numpy().astype(np.float64) if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().numpy().astype(np.float64) if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+    ax = tuple(range(1, a.ndim))
+    return np.max(np.abs(a - b), axis=ax) / np.max(np.abs(b), axis=ax)
+
+
+# =================================================================================================== cfg 2
+def test_cfg2_full_batch_lqr_mpc_fp32():
+    """65,536 quadcopter problems, n=12 m=4 N=50, fp32: the bench's own step (linearise + lqrMpc.solve)."""
+    from zopt_b200.mpcUtils import lqrMpc
+    from zopt_b200.quadcopter import Quadcopter
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    Bsz, f32 = 65536, torch.float32
+    d = configs.cfg2(Bsz=Bsz)
+    N, dt = d["N"], d["dt"]
+    xbar, ubar = _t(d["xbar"], f32), _t(d["ubar"], f32)
+    Q, R = torch.diag_embed(_t(d["qdiag"], f32)), torch.diag_embed(_t(d["rdiag"], f32))
+    inf_n, inf_m = torch.full((12,), float("inf")), torch.full((4,), float("inf"))
+    A, B = Quadcopter().linearizeInertial(xbar, ubar, dt)
+
+    def solve(idx=None):
+        sl = (lambda t: t) if idx is None else (lambda t: t[idx].contiguous())
+        u, traj, status = lqrMpc(sl(A), sl(B), sl(Q), sl(R), N, -inf_n, inf_n, -inf_m, inf_m, Qf=10 * sl(Q)).solve(sl(xbar))
+        return u, traj.xTraj, traj.uTraj, status
+
+    u, xT, uT, status = solve()
+    assert int(status.max()) == 0 and bool(torch.isfinite(xT).all()) and bool(torch.isfinite(uT).all())
+    # (i) batch-split invariance and permutation equivariance, bit for bit: a ragged slice from the middle of the batch
+    # (different CTA, different lane, different wave) and a random permutation of 4,097 problems
+    rng = np.random.default_rng(7)
+    for idx in (torch.arange(30001, 30001 + 333, device=DEV), _t(rng.permutation(Bsz)[:4097], torch.int64)):
+        us, xs, uss, _ = solve(idx)
+        assert torch.equal(us, u[idx]) and torch.equal(xs, xT[idx]) and torch.equal(uss, uT[idx])
+    # (ii) the plan obeys the linearised dynamics it was computed for, and its first move is the returned control
+    xn = torch.einsum("bij,bkj->bki", A, xT[:, :-1]) + torch.einsum("bij,bkj->bki", B, uT)
+    scale = xT.abs().amax(dim=(1, 2), keepdim=True)
+    assert float(((xn - xT[:, 1:]).abs() / scale).max()) < 2e-5
+    assert torch.equal(u, uT[:, 0]) and torch.equal(xT[:, 0], xbar)
+    # (iii) Riccati identity: the cost of the optimal plan equals x0' V0 x0 (V0 from discreteFiniteHorizonLqr)
+    ex = lambda t: t[:, None].expand(-1, N, -1, -1)
+    Qk = torch.cat([ex(Q), (10 * Q)[:, None]], dim=1)
+    L, V0 = discreteFiniteHorizonLqr(ex(A), ex(B), Qk, ex(R), N, return_value=True)
+    xd, ud, Qd, Rd = xT.double(), uT.double(), Q.double(), R.double()
+    Jplan = (torch.einsum("bki,bij,bkj->b", xd[:, :-1], Qd, xd[:, :-1]) + torch.einsum("bki,bij,bkj->b", ud, Rd, ud)
+             + 10 * torch.einsum("bi,bij,bj->b", xd[:, -1], Qd, xd[:, -1]))
+    Jv = torch.einsum("bi,bij,bj->b", xd[:, 0], V0.double(), xd[:, 0])
+    assert float(((Jplan - Jv).abs() / Jv).max()) < 5e-4  # fp32 plan: the cost is second-order flat around the optimum
+    # the plan's controls are the gains applied to the plan's states
+    assert float(((uT + torch.einsum("bkij,bkj->bki", L, xT[:, :-1])).abs() / uT.abs().amax(dim=(1, 2), keepdim=True)).max()) < 2e-5
+    # (iv) the oracle (autodiff linearisation + fp64 Riccati + rollout) on a random 1,024-problem subset
+    sub = np.sort(rng.choice(Bsz, 1024, replace=False))
+    f = OQuadcopter().eulerStep(dt)
+    Ao, Bo = torch.func.vmap(torch.func.jacrev(f, argnums=(0, 1)))(torch.as_tensor(d["xbar"][sub]), torch.as_tensor(d["ubar"][sub]))
+    Ao, Bo = Ao.numpy(), Bo.numpy()
+    Qo, Ro = configs.diag_embed(d["qdiag"][sub]), configs.diag_embed(d["rdiag"][sub])
+    Qko = np.repeat(Qo[:, None], N + 1, axis=1)
+    Qko[:, N] *= 10
+    Lo = olqr.discreteFiniteHorizonLqr_batched(np.repeat(Ao[:, None], N, 1), np.repeat(Bo[:, None], N, 1), Qko,
+                                               np.repeat(Ro[:, None], N, 1), N)
+    x = d["xbar"][sub].copy()
+    us = []
+    for k in range(N):
+        uk = -np.einsum("bij,bj->bi", Lo[:, k], x)
+        x = np.einsum("bij,bj->bi", Ao, x) + np.einsum("bij,bj->bi", Bo, uk)
+        us.append(uk)
+    sub_t = _t(sub, torch.int64)
+    assert _relerr(L[sub_t], Lo).max() < 1e-5
+    assert _relerr(uT[sub_t], np.stack(us, 1)).max() < 2e-5
+
+
+def test_cfg2_full_batch_time_varying_lqr_fp32():
+    """65,536 problems with A[k], B[k], Q[k], R[k] materialised per step (the streamed kernel): equal to the time-invariant
+    kernel on time-invariant data to fp32 rounding, bit-identical under batch splitting, and correct on operands that
+    really vary along the horizon (oracle on a subset)."""
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    from zopt_b200.quadcopter import Quadcopter
+    Bsz, f32 = 65536, torch.float32
+    d = configs.cfg2(Bsz=Bsz)
+    N, dt = d["N"], d["dt"]
+    A, B = Quadcopter().linearizeInertial(_t(d["xbar"], f32), _t(d["ubar"], f32), dt)
+    Q, R = torch.diag_embed(_t(d["qdiag"], f32)), torch.diag_embed(_t(d["rdiag"], f32))
+    rng = np.random.default_rng(11)
+    # per-step modulation so that every operand genuinely depends on k
+    sA = _t(1 + 0.02 * rng.standard_normal((1, N, 1, 1)), f32)
+    sQ = _t(10.0 ** rng.uniform(-0.3, 0.3, (1, N, 1, 1)), f32)
+    Ak, Bk = (A[:, None] * sA).contiguous(), (B[:, None] * (2 - sA)).contiguous()
+    Qk, Rk = (Q[:, None] * sQ).contiguous(), (R[:, None] / sQ).contiguous()
+    L = discreteFiniteHorizonLqr(Ak, Bk, Qk, Rk, N)
+    assert L.shape == (Bsz, N, 4, 12) and bool(torch.isfinite(L).all())
+    idx = torch.arange(41007, 41007 + 517, device=DEV)
+    Ls = discreteFiniteHorizonLqr(Ak[idx].contiguous(), Bk[idx].contiguous(), Qk[idx].contiguous(), Rk[idx].contiguous(), N)
+    assert torch.equal(Ls, L[idx])
+    sub = np.sort(rng.choice(Bsz, 256, replace=False))
+    st = _t(sub, torch.int64)
+    Lo = olqr.discreteFiniteHorizonLqr_batched(*(t[st].double().cpu().numpy() for t in (Ak, Bk, Qk, Rk)), N)
+    assert _relerr(L[st], Lo).max() < 1e-5
+    # time-invariant data through the streamed kernel vs the register-resident time-invariant kernel
+    ex = lambda t: t[:, None].expand(-1, N, -1, -1)
+    L1 = discreteFiniteHorizonLqr(ex(A), ex(B), ex(Q), ex(R), N)
+    L2 = discreteFiniteHorizonLqr(ex(A).contiguous(), ex(B).contiguous(), ex(Q).contiguous(), ex(R).contiguous(), N)
+    assert float(((L1 - L2).abs().amax(dim=(1, 2, 3)) / L1.abs().amax(dim=(1, 2, 3))).max()) < 1e-5
+
+
+# =================================================================================================== cfg 3
+@pytest.mark.parametrize("variant", ["thread", "quad"])
+def test_cfg3_full_batch_closed_loop(variant):
+    """16,384 closed loops x 200 steps (horizon 50, re-linearised every step): batch-split invariance bit for bit, and the
+    composed per-step path (linearise -> lqrMpc.solve -> plant step) on a small subset."""
+    from zopt_b200.mpcUtils import lqrMpc, quadcopterClosedLoopMpc
+    from zopt_b200.quadcopter import Quadcopter
+    Bsz, f32, steps = 16384, torch.float32, 200
+    d = configs.cfg3(Bsz=Bsz)
+    x0 = _t(d["xbar"], f32)
+    x0[:, 9:12] *= 0.2
+    Q, R = torch.diag_embed(_t(d["qdiag"], f32)), torch.diag_embed(_t(d["rdiag"], f32))
+    xs, us = quadcopterClosedLoopMpc(x0, Q, R, 50, steps, dt=0.1, Qf=10 * Q, variant=variant)
+    assert xs.shape == (Bsz, steps + 1, 12) and us.shape == (Bsz, steps, 4)
+    # the linear feedback does not stabilise the nonlinear plant from every random 0.5 rad / 0.3 rad/s initial attitude:
+    # diverged loops (inf / NaN, as the reference's own loop would produce) are counted, not hidden
+    good = torch.isfinite(xs).all(dim=2).all(dim=1)
+    assert float(good.float().mean()) > 0.98, f"{int((~good).sum())} of {Bsz} closed loops diverged"
+    idx = torch.arange(9001, 9001 + 77, device=DEV)
+    xs2, us2 = quadcopterClosedLoopMpc(x0[idx].contiguous(), Q[idx].contiguous(), R[idx].contiguous(), 50, steps, dt=0.1,
+                                       Qf=10 * Q[idx].contiguous(), variant=variant)
+    assert _same(xs2, xs[idx]) and _same(us2, us[idx])
+    # the regulator regulates: every loop ends closer to the origin (weighted by its own Q) than it started
+    c0 = torch.einsum("bi,bij,bj->b", xs[good, 0], Q[good], xs[good, 0])
+    cT = torch.einsum("bi,bij,bj->b", xs[good, -1], Q[good], xs[good, -1])
+    assert float((cT / c0).median()) < 0.05 and float(((cT / c0) < 1.0).float().mean()) > 0.99
+    # composed path for the first 20 steps of 8 problems (fp32 closed loops separate slowly: 1e-3 after 20 steps)
+    ac = Quadcopter()
+    sub = idx[good[idx]][:8]
+    x = x0[sub].clone()
+    inf_n, inf_m = torch.full((12,), float("inf")), torch.full((4,), float("inf"))
+    utrim = _t(np.tile(configs.U_TRIM, (8, 1)), f32)
+    for k in range(20):
+        A, B = ac.linearizeInertial(x, utrim, 0.1)
+        u, _, _ = lqrMpc(A, B, Q[sub], R[sub], 50, -inf_n, inf_n, -inf_m, inf_m, Qf=10 * Q[sub]).solve(x)
+        assert float((u - us[sub, k]).abs().max() / us[sub, k].abs().max()) < 2e-3
+        x = xs[sub, k + 1]  # follow the fused loop's state so that the comparison stays a one-step comparison
+
+
+# =================================================================================================== cfg 4 / 5
+@pytest.mark.parametrize("kind", ["ilqr", "ddp"])
+def test_cfg45_full_batch_solvers_fp64(kind):
+    """cfg 4: iLQR 16,384 x N=200 x 10 iterations; cfg 5: DDP 16,384 x N=100 x 10 iterations, fp64."""
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    f64, Bsz, iters = torch.float64, 16384, 10
+    d = configs.cfg4(Bsz=Bsz) if kind == "ilqr" else configs.cfg5(Bsz=Bsz, N=100)
+    solver = ilqrUtils.iterativeLqr if kind == "ilqr" else ilqrUtils.differentialDynamicProgramming
+    margs = (QuadcopterEuler(d["dt"]), QuadraticCost(d["Q"], d["R"]), QuadraticTerminalCost(d["Qf"]))
+    x0, uG = _t(d["x0"], f64), _t(d["uGuess"], f64)
+    traj, L, J, conv, log = solver(*margs, x0, uG, maxIter=iters, tol=-1.0, return_log=True)
+    assert bool(torch.isfinite(traj.xTraj).all()) and bool(torch.isfinite(L).all())
+    assert int(log["iters"].min()) == iters and not bool(conv.any())
+    # the line search never accepts a worse trajectory than alpha -> 0 would give: costs fall monotonically (to rounding)
+    Jl = log["J"]
+    assert float(((Jl[:, 1:] - Jl[:, :-1]) / Jl[:, :-1]).max()) < 1e-9
+    assert float((Jl[:, -1] / Jl[:, 0]).max()) < 1.0
+    # batch-split invariance, bit for bit (ragged slice: 4 problems per line-search CTA, 16 per backward CTA)
+    idx = torch.arange(5003, 5003 + 131, device=DEV)
+    t2, L2, J2, _, log2 = solver(*margs, x0[idx].contiguous(), uG, maxIter=iters, tol=-1.0, return_log=True)
+    assert torch.equal(log2["alpha_idx"], log["alpha_idx"][idx])
+    assert _same(t2.xTraj, traj.xTraj[idx]) and _same(t2.uTraj, traj.uTraj[idx]) and _same(L2, L[idx]) and _same(J2, J[idx])
+    # the two-kernel line search gives the same bits on a slice
+    ilqrUtils._GENERIC_FORWARD = True
+    try:
+        t3, L3, J3, _, log3 = solver(*margs, x0[idx].contiguous(), uG, maxIter=iters, tol=-1.0, return_log=True)
+    finally:
+        ilqrUtils._GENERIC_FORWARD = False
+    assert torch.equal(log3["alpha_idx"], log2["alpha_idx"]) and _same(t3.xTraj, t2.xTraj) and _same(L3, L2)
+    # the oracle on two problems of the batch, 3 iterations (the fp64 oracle needs ~1 s per problem-iteration at N=200)
+    ac = OQuadcopter()
+    Qt, Rt, Qft = (torch.as_tensor(d[k]) for k in ("Q", "R", "Qf"))
+    dyn, rc, tc = ac.eulerStep(d["dt"]), (lambda x, u: x @ Qt @ x + u @ Rt @ u), (lambda x: x @ Qft @ x)
+    osolver = oilqr.iterativeLqr if kind == "ilqr" else oilqr.differentialDynamicProgramming
+    sub = torch.tensor([17, 12345], device=DEV)
+    ts, Ls, Js, _, logs = solver(*margs, x0[sub].contiguous(), uG, maxIter=3, tol=-1.0, return_log=True)
+    for i, b in enumerate(sub.tolist()):
+        olog = []
+        tr, Lr, Jr, _ = osolver(dyn, rc, tc, torch.as_tensor(d["x0"][b]), torch.as_tensor(d["uGuess"]), maxIter=3, tol=-1.0, log=olog)
+        assert [e["alpha_idx"] for e in olog[1:]] == logs["alpha_idx"][i].tolist()
+        assert [e["alpha_idx"] for e in olog[1:]] == log["alpha_idx"][b, :3].tolist()  # ... and inside the full batch
+        assert _relerr(ts.xTraj[i][None], np.asarray(tr.xTraj)[None]).max() < 1e-10
+        assert _relerr(Ls[i][None], np.asarray(Lr)[None]).max() < 1e-10
+        assert abs(float(Js[i]) - float(Jr)) < 1e-10 * abs(float(Jr))
