@@ -404,6 +404,26 @@ def run_ours(args):
         barrier()
         extra_ms.append(c0.elapsed_time(c1) / 5)
         del Atv, Btv, Qtv, Rtv, Ltv
+        # the headline workload in the reference's own precision (fp64): cooperative four-threads-per-problem Riccati kernel
+        f64 = torch.float64
+        xb64, ub64 = xbar.to(f64), ubar.to(f64)
+        Q64, R64 = Q.to(f64), R.to(f64)
+        Qf64 = 10 * Q64
+
+        def step64():
+            A64, B64 = ac.linearizeInertial(xb64, ub64, dt)
+            return lqrMpc(A64, B64, Q64, R64, N, ninf_n, inf_n, ninf_m, inf_m, Qf=Qf64).solve(xb64)
+
+        step64()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            step64()
+        c1.record()
+        barrier()
+        extra_ms.append(c0.elapsed_time(c1) / 5)
+        del xb64, ub64, Q64, R64, Qf64
         # cfg 3 tier B: the reference demo's box-constrained lqrMpc (demos/lqrMpc.py:11-32: hover linearisation, N=25, bounds
         # |uvw|<=1, |pq|<=0.3, |r|<=0.1, |phi,theta|<=0.5, |u|<=3, OSQP eps 1e-2), one solve per initial state, bounds bind
         from zopt_b200.quadcopter import Quadcopter as _Q
@@ -448,13 +468,13 @@ def run_ours(args):
         extra_ms.append(c0.elapsed_time(c1))
         boxcl5_iters = float(pb.iters.float().mean()) / 200
         boxcl5_opt = float((stc5 == 0).float().mean())
-    while len(extra_ms) < 8:
+    while len(extra_ms) < 9:
         extra_ms.append(0.0)
 
     times = torch.tensor([ms, e2e_ms, k_ms, e2e_u_ms] + extra_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, k_ms, e2e_u_ms, cl_ms, clw_ms, il_ms, ddp_ms, tv_ms, box_ms, boxcl_ms, boxcl5_ms = (float(v) for v in times.cpu())
+    ms, e2e_ms, k_ms, e2e_u_ms, cl_ms, clw_ms, il_ms, ddp_ms, tv_ms, f64_ms, box_ms, boxcl_ms, boxcl5_ms = (float(v) for v in times.cpu())
 
     if rank == 0:
         total = Bsz * world
@@ -519,6 +539,12 @@ def run_ours(args):
                              "roofline": {"bound": "fp64_fma", "achieved": 16384 * 10 * 7.33e6 / (ddp_ms * 1e-3) / 1e12,
                                           "peak": peak64.value / 1e12, "unit": "TFLOP/s",
                                           "frac": 16384 * 10 * 7.33e6 / (ddp_ms * 1e-3) / peak64.value}},
+                "cfg2_fp64": {"value": Bsz * world / (f64_ms * 1e-3), "unit": "solves/s", "ms": f64_ms,
+                              "workload": f"the headline step (linearise + lqrMpc.solve, N={N}) in fp64, the reference's own precision, "
+                                          f"{Bsz} problems per GPU", "scaling": "weak",
+                              "roofline": {"bound": "fp64_fma", "achieved": FLOP_PER_SOLVE * Bsz / (f64_ms * 1e-3) / 1e12,
+                                           "peak": peak64.value / 1e12, "unit": "TFLOP/s",
+                                           "frac": FLOP_PER_SOLVE * Bsz / (f64_ms * 1e-3) / peak64.value}},
                 "lqr_time_varying": {"value": Bsz * world / (tv_ms * 1e-3), "unit": "solves/s", "ms": tv_ms,
                                      "workload": f"discreteFiniteHorizonLqr with A[k], B[k], Q[k], R[k] materialised per step "
                                                  f"(streamed from HBM), {Bsz} problems per GPU, N={N}, fp32", "scaling": "weak",

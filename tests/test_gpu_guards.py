@@ -43,10 +43,11 @@ def _cfg(Bsz, dev, dt=torch.float32):
 
 @pytest.mark.parametrize("Bsz", [1, 33, 77])
 @pytest.mark.parametrize("diag", [True, False])
-def test_mpc_and_closed_loop_guards(Bsz, diag):
+@pytest.mark.parametrize("f32", [torch.float32, torch.float64])  # fp64: cooperative Riccati + quad plan rollout (csrc/lqr_quad64.cuh)
+def test_mpc_and_closed_loop_guards(Bsz, diag, f32):
     dev = torch.device("cuda", 0)
-    f32 = torch.float32
-    d, xbar, A, B, Q, R = _cfg(Bsz, dev)
+    code = 0 if f32 == torch.float32 else 1
+    d, xbar, A, B, Q, R = _cfg(Bsz, dev, f32)
     if not diag:
         Q = Q + 0.01
         R = R + 0.01
@@ -55,16 +56,18 @@ def test_mpc_and_closed_loop_guards(Bsz, diag):
     views = [View(t, 2, False, True) for t in (A, B, Q, R, Qf)]
     inf = [View(torch.full((k,), s * float("inf"), dtype=f32, device=dev), 1, False, False) for k, s in ((12, -1), (12, 1), (4, -1), (4, 1))]
     u0, xT, uT = Guarded((Bsz, 4), f32, dev), Guarded((Bsz, N + 1, 12), f32, dev), Guarded((Bsz, N, 4), f32, dev)
-    st, it = Guarded((Bsz,), torch.uint8, dev), Guarded((Bsz,), f32, dev)
-    wsb = lib.zb_mpc_workspace_bytes(0, Bsz, N, 12, 4)
+    st, it = Guarded((Bsz,), torch.uint8, dev), Guarded((Bsz,), torch.float32, dev)
+    wsb = lib.zb_mpc_workspace_bytes(code, Bsz, N, 12, 4)
     ws = Guarded((wsb,), torch.uint8, dev)
     opts = ZbAdmmOpts(4000, 25, 0.1, 1e-6, 1.6, 1e-3, 1e-3, 1e-4)
-    check(lib.zb_mpc_lqr_solve(0, 0, stream_ptr(dev), Bsz, N, 12, 4, *[v.ref() for v in views], *[v.ref() for v in inf],
+    check(lib.zb_mpc_lqr_solve(code, 0, stream_ptr(dev), Bsz, N, 12, 4, *[v.ref() for v in views], *[v.ref() for v in inf],
                                2 if diag else 0, ptr(xbar), C.byref(opts), ptr(u0.t), ptr(xT.t), ptr(uT.t), ptr(st.t), ptr(it.t),
                                ptr(ws.t), wsb))
     torch.cuda.synchronize()
     assert all(g.ok() for g in (u0, xT, uT, st, it, ws))
     assert torch.isfinite(xT.t).all() and torch.isfinite(uT.t).all() and (st.t == 0).all()
+    if code == 1:
+        return  # the fused closed loop is an fp32 kernel
     # closed loop
     Ts = 5
     xS, uS = Guarded((Bsz, Ts + 1, 12), f32, dev), Guarded((Bsz, Ts, 4), f32, dev)
@@ -80,10 +83,10 @@ def test_mpc_and_closed_loop_guards(Bsz, diag):
 
 @pytest.mark.parametrize("Bsz", [1, 45])
 @pytest.mark.parametrize("mode", ["views", "q_series", "materialised"])
-def test_lqr_dfh_guards(Bsz, mode):
+@pytest.mark.parametrize("f32", [torch.float32, torch.float64])  # fp64: the cooperative kernel of csrc/lqr_quad64.cuh
+def test_lqr_dfh_guards(Bsz, mode, f32):
     dev = torch.device("cuda", 0)
-    f32 = torch.float32
-    d, xbar, A, B, Q, R = _cfg(Bsz, dev)
+    d, xbar, A, B, Q, R = _cfg(Bsz, dev, f32)
     N = 9
     ex = lambda t: t[:, None].expand(-1, N, -1, -1)
     Ak, Bk, Qk, Rk = ex(A), ex(B), ex(Q), ex(R)
@@ -93,7 +96,7 @@ def test_lqr_dfh_guards(Bsz, mode):
         Ak, Bk, Rk = Ak.contiguous(), Bk.contiguous(), Rk.contiguous()
     views = [View(t, 2, True, True) for t in (Ak, Bk, Qk, Rk)]
     L, V0 = Guarded((Bsz, N, 4, 12), f32, dev), Guarded((Bsz, 12, 12), f32, dev)
-    check(lib.zb_lqr_dfh(0, 0, stream_ptr(dev), Bsz, N, N, 12, 4, *[v.ref() for v in views], ptr(L.t), ptr(V0.t)))
+    check(lib.zb_lqr_dfh(0 if f32 == torch.float32 else 1, 0, stream_ptr(dev), Bsz, N, N, 12, 4, *[v.ref() for v in views], ptr(L.t), ptr(V0.t)))
     torch.cuda.synchronize()
     assert L.ok() and V0.ok() and torch.isfinite(L.t).all() and torch.isfinite(V0.t).all()
 

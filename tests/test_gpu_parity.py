@@ -132,6 +132,27 @@ def test_lqr_time_varying_random(dt):
         assert per_problem_relerr(L, Lref).max() < TOL[dt], (n, m)
 
 
+def test_lqr_fp64_cooperative_kernel_operand_patterns():
+    """(12,4) fp64 goes to the four-threads-per-problem kernel (csrc/lqr_quad64.cuh): every operand pattern of the C ABI --
+    stride-0 views, a Q series with a distinct terminal row (T = N + 1), everything time-varying, N = 1, ragged batches --
+    against the fp64 oracle at 1e-10, gains and the value matrix V0."""
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    rng = np.random.default_rng(42)
+    spd = lambda k: (lambda M: M @ M.T / k + np.eye(k))(rng.normal(size=(k, k)))
+    for Bsz, N, T, tvAB, tvQ in ((1, 1, 1, False, False), (17, 6, 7, False, True), (33, 9, 9, True, True), (5, 4, 6, True, False)):
+        A = rng.normal(size=(Bsz, T if tvAB else 1, 12, 12)) * 0.5 / np.sqrt(12)
+        B = rng.normal(size=(Bsz, T if tvAB else 1, 12, 4))
+        Q = np.stack([[spd(12) for _ in range(T if tvQ else 1)] for _ in range(Bsz)])
+        R = np.stack([[spd(4) for _ in range(T if tvQ else 1)] for _ in range(Bsz)])
+        full = lambda M: np.repeat(M, T, axis=1) if M.shape[1] == 1 else M
+        Lref, Vref = olqr.discreteFiniteHorizonLqr_batched(full(A), full(B), full(Q), full(R), N, return_value=True)
+        dev = lambda M: cuda(M).expand(-1, T, -1, -1) if M.shape[1] == 1 else cuda(M)
+        L, V0 = discreteFiniteHorizonLqr(dev(A), dev(B), dev(Q), dev(R), N, return_value=True)
+        assert L.shape == (Bsz, N, 4, 12) and L.dtype == torch.float64
+        assert per_problem_relerr(L, Lref).max() < 1e-10 and per_problem_relerr(V0, Vref).max() < 1e-10
+        assert torch.equal(V0, V0.transpose(1, 2))  # "lower triangle wins": exactly symmetric
+
+
 def test_lqr_edge_cases():
     from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
     I = np.repeat(np.eye(2)[None], 3, axis=0)

@@ -58,6 +58,19 @@ struct SetupQuadP {
     void *Czz, *Vfxx;    // (Bsz,16,16), (Bsz,12,12)
 };
 
+// cooperative (12,4) Riccati recursion, fp64 (lqr_quad64.cuh): discreteFiniteHorizonLqr, and lqrMpc.solve when x0 is set
+struct LqrQuadP {
+    long long Bsz;
+    int N, T;
+    Arr A, B, Q, R, Qf;  // Qf.p == nullptr: terminal value Q[T-1] (lqrUtils.py:172)
+    void* L;             // (Bsz,N,4,12) gains (the workspace for lqrMpc.solve)
+    void* V0;            // (Bsz,12,12) or null
+    const void* x0;      // null: gains only
+    void *u0, *xTraj, *uTraj;
+    int8_t* status;
+    int32_t* iters;
+};
+
 inline bool ilqr_fast_eligible(const Model& M, int second_order, bool cost_diagonal) {
     return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && (!second_order || cost_diagonal);
 }
@@ -68,5 +81,6 @@ inline bool fwd_quad_eligible(const Model& M, bool cost_diagonal) {
 int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream, bool cost_diagonal, bool second_order);
 int32_t fwd_quad_launch(int32_t dtype, const FwdQuadP& P, cudaStream_t stream);
 int32_t solve_setup_quad_launch(int32_t dtype, const SetupQuadP& P, cudaStream_t stream);
+int32_t riccati_quad_launch(int32_t dtype, const LqrQuadP& P, cudaStream_t stream);
 
 }  // namespace zb

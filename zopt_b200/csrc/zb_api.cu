@@ -411,6 +411,15 @@ int32_t zb_lqr_dfh(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int
         }
         return lqr_fast_launch(dtype, P, (cudaStream_t)stream);
     }
+    // fp64 (12,4): cooperative four-threads-per-problem kernel (lqr_quad64.cuh)
+    if (dtype == ZB_F64 && n == 12 && m == 4 && N >= 1 && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) && arr_ok(P.R) && aligned16(P.L) &&
+        (!P.V0 || aligned16(P.V0))) {
+        LqrQuadP F{};
+        F.Bsz = Bsz; F.N = N; F.T = T;
+        F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R;
+        F.L = L_out; F.V0 = V0_out;
+        return riccati_quad_launch(dtype, F, (cudaStream_t)stream);
+    }
     ZB_DISPATCH(dtype, k_lqr_generic, gen_grid(Bsz), GEN_THREADS, stream, P);
     return 0;
 }
@@ -626,7 +635,7 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     ZB_CUDA(cudaMemsetAsync(L_out, 0, e * Bsz * N * m * n, s));
     P.x0 = x0; P.l = l_ws; P.L = L_out; P.xPrev = xTraj; P.uPrev = uTraj;
     P.xTraj = xTraj; P.uTraj = uTraj; P.J = nullptr;
-    const bool fast_fwd = !(flags & ZB_GENERIC_FORWARD) && fwd_quad_eligible(P.M, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out) && aligned16(x0);
+    const bool fast_fwd = N >= 1 && !(flags & ZB_GENERIC_FORWARD) && fwd_quad_eligible(P.M, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out) && aligned16(x0);
     if (fast_fwd && aligned16(uGuess)) {  // diagonal costs + quadcopter: closed-form conditioning and a register-resident initial rollout
         SetupQuadP Sp{Bsz, N, (int)maxIter, P.M.dt, 1e-3, P.C, x0, uGuess, xTraj, uTraj, J_out, converged_out, iters_out, alpha_log, J_log, Czz, Vfxx};
         rc = solve_setup_quad_launch(dtype, Sp, s);
@@ -637,7 +646,7 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
                     alpha_log, J_log, (int)maxIter);
     }
     SolveBackP Bk{Bsz, N, second_order, P.M, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
-    const bool fast_bwd = ilqr_fast_eligible(P.M, second_order, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out);
+    const bool fast_bwd = N >= 1 && ilqr_fast_eligible(P.M, second_order, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out);
     IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
     for (int it = 0; it < maxIter; ++it) {
         if (fast_bwd) {
@@ -714,6 +723,16 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
         F.status = status_out;
         F.iters = iters_out;
         return riccati_t1_launch<true>(F, (cudaStream_t)stream, (flags & ZB_COST_DIAGONAL) != 0);
+    }
+    if (dtype == ZB_F64 && n == 12 && m == 4 && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) && arr_ok(P.R) && arr_ok(P.Qf) &&
+        aligned16(x0) && aligned16(u0_out) && aligned16(xTraj) && aligned16(uTraj) && aligned16(workspace)) {
+        LqrQuadP F{};  // fp64: cooperative Riccati sweep (gains to the workspace) + quad plan rollout (lqr_quad64.cuh)
+        F.Bsz = Bsz; F.N = N; F.T = 1;
+        F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R; F.Qf = P.Qf;
+        F.A.st = F.B.st = F.Q.st = F.R.st = 0;
+        F.L = workspace; F.x0 = x0; F.u0 = u0_out; F.xTraj = xTraj; F.uTraj = uTraj;
+        F.status = status_out; F.iters = iters_out;
+        return riccati_quad_launch(dtype, F, (cudaStream_t)stream);
     }
     ZB_DISPATCH(dtype, k_mpc_riccati, gen_grid(Bsz), GEN_THREADS, stream, P);
     return 0;
