@@ -1,0 +1,113 @@
+"""
+User-defined symbolic dynamics (zopt_b200/plugin.py): sympy -> CUDA code generation and the nvcc build of the
+solver plug-in (CPU, no GPU needed: nvcc cross-compiles), then on a GPU the generated code against torch autodiff of the
+same expressions and iLQR / DDP / trajectoryRollout against the oracle, which differentiates the model's own callable the
+way the reference does with JAX (zopt/pytrees.py:138-194).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import plugin_models
+
+
+@pytest.mark.parametrize("name", ["pendulum", "car"])
+def test_codegen_and_build(name):
+    mdl = plugin_models.build(name)
+    f, n, m = plugin_models.MODELS[name]
+    assert (mdl.n, mdl.m) == (n, m)
+    for fn in ("user_step", "user_lin", "user_hess"):
+        assert f"ZB_HD void {fn}(" in mdl.source
+    assert os.path.exists(mdl.so_path)
+    lib = C.CDLL(mdl.so_path)
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "zopt_b200_plugin.h")).read()
+    declared = re.findall(r"^ZB_API\s+\w+\s+(zb_\w+)\(", hdr, flags=re.M)
+    assert len(declared) == 6
+    for sym in declared:  # every symbol include/zopt_b200_plugin.h declares is exported by the built plug-in
+        assert hasattr(lib, sym), sym
+    # the object is callable like the lambda it replaces, and differentiable (this is what the oracle uses)
+    x, u = torch.linspace(0.1, 0.4, n, dtype=torch.float64), torch.linspace(-0.3, 0.2, m, dtype=torch.float64)
+    xn = mdl(x, u)
+    assert xn.shape == (n,) and xn.dtype == torch.float64
+    fx = torch.func.jacrev(mdl, argnums=0)(x, u)
+    assert fx.shape == (n, n) and torch.isfinite(fx).all()
+    xb = x[None].repeat(3, 1)
+    assert torch.allclose(mdl(xb, u[None].repeat(3, 1))[1], xn)
+    # a model that is not a function of (x, u) only, or too large, is refused up front
+    import sympy as sp
+    from zopt_b200.plugin import SymbolicDynamics
+    with pytest.raises(ValueError):
+        SymbolicDynamics(lambda x, u: [x[0] + sp.Symbol("k")], 1, 1, build=False)
+    with pytest.raises(ValueError):
+        SymbolicDynamics(lambda x, u: list(x), 17, 1, build=False)
+    # no CPU fallback: solving without a CUDA device raises
+    if not torch.cuda.is_available():
+        from zopt_b200 import ilqrUtils
+        from zopt_b200.models import QuadraticCost, QuadraticTerminalCost
+        with pytest.raises(RuntimeError):
+            ilqrUtils.iterativeLqr(mdl, QuadraticCost(np.eye(n), np.eye(m)), QuadraticTerminalCost(np.eye(n)), np.zeros(n), np.zeros((5, m)))
+
+
+def _relerr(a, b):
+    a = a.detach().cpu().numpy().astype(np.float64) if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().numpy().astype(np.float64) if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["pendulum", "car"])
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_generated_model_vs_autodiff(name, dt):
+    mdl = plugin_models.build(name)
+    rng = np.random.default_rng(3)
+    x, u = rng.normal(size=(37, mdl.n)), rng.normal(size=(37, mdl.m))
+    xn, fx, fu = mdl.step(torch.as_tensor(x, dtype=dt, device="cuda"), torch.as_tensor(u, dtype=dt, device="cuda"), linearize=True)
+    xt, ut = torch.as_tensor(x), torch.as_tensor(u)
+    ref = mdl(xt, ut)
+    Jx, Ju = torch.func.vmap(torch.func.jacrev(mdl, argnums=(0, 1)))(xt, ut)
+    tol = 1e-12 if dt == torch.float64 else 2e-6
+    assert _relerr(xn, ref) < tol and _relerr(fx, Jx) < tol and _relerr(fu, Ju) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["pendulum", "car"])
+@pytest.mark.parametrize("second_order", [False, True])
+def test_solvers_with_symbolic_model_vs_oracle(name, second_order):
+    """iLQR / DDP on a user-defined model, fp64: step-size sequence first, then x, u, L, J at 1e-10 against the oracle, whose
+    derivatives come from torch autodiff of the same callable (DDP exercises the full (n+m)^2 second-order block)."""
+    from oracle import ilqr as oilqr
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadraticCost, QuadraticTerminalCost
+    mdl = plugin_models.build(name)
+    n, m, N, Bsz, iters = mdl.n, mdl.m, 25, 5, 3
+    rng = np.random.default_rng(11 + int(second_order))
+    x0 = rng.uniform(-1, 1, (Bsz, n))
+    uG = 0.1 * rng.normal(size=(N, m))
+    Q, R, Qf = np.eye(n), 0.5 * np.eye(m), 10 * np.eye(n)
+    solver = ilqrUtils.differentialDynamicProgramming if second_order else ilqrUtils.iterativeLqr
+    traj, L, J, conv, log = solver(mdl, QuadraticCost(Q, R), QuadraticTerminalCost(Qf), torch.as_tensor(x0, device="cuda"), uG,
+                                   maxIter=iters, tol=-1.0, return_log=True)
+    assert traj.xTraj.shape == (Bsz, N + 1, n) and L.shape == (Bsz, N, m, n)
+    Qt, Rt, Qft = torch.as_tensor(Q), torch.as_tensor(R), torch.as_tensor(Qf)
+    rc, tc = (lambda x, u: x @ Qt @ x + u @ Rt @ u), (lambda x: x @ Qft @ x)
+    osolver = oilqr.differentialDynamicProgramming if second_order else oilqr.iterativeLqr
+    for b in range(Bsz):
+        olog = []
+        tr, Lr, Jr, _ = osolver(mdl, rc, tc, torch.as_tensor(x0[b]), torch.as_tensor(uG), maxIter=iters, tol=-1.0, log=olog)
+        assert [e["alpha_idx"] for e in olog[1:]] == log["alpha_idx"][b].tolist()
+        assert _relerr(traj.xTraj[b], tr.xTraj) < 1e-10 and _relerr(traj.uTraj[b], tr.uTraj) < 1e-10
+        assert _relerr(L[b], Lr) < 1e-10 and abs(float(J[b]) - float(Jr)) < 1e-10 * abs(float(Jr))
+    # un-batched call: reference shapes; trajectoryRollout with the same model reproduces the solver's trajectory
+    t1, L1, J1, c1 = solver(mdl, QuadraticCost(Q, R), QuadraticTerminalCost(Qf), torch.as_tensor(x0[0], device="cuda"), uG, maxIter=iters, tol=-1.0)
+    assert t1.xTraj.shape == (N + 1, n) and torch.equal(t1.xTraj, traj.xTraj[0])
+    from zopt_b200.pytrees import AffinePolicy, Trajectory
+    zero = torch.zeros((N, m), dtype=torch.float64, device="cuda")
+    t2 = ilqrUtils.trajectoryRollout(torch.as_tensor(x0[0], device="cuda"), mdl, AffinePolicy(zero, L1), Trajectory(t1.xTraj, t1.uTraj), alpha=1)
+    assert _relerr(t2.xTraj, t1.xTraj) < 1e-12 and _relerr(t2.uTraj, t1.uTraj) < 1e-12
+    with pytest.raises(TypeError):
+        solver(lambda x, u: x, QuadraticCost(Q, R), QuadraticTerminalCost(Qf), x0[0], uG)

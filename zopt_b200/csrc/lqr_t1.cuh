@@ -41,6 +41,9 @@ __host__ __device__ constexpr int qoff(int i) { return i < 4 ? i : (i < 8 ? 4 + 
 #ifndef ZB_USE_FFMA2
 #define ZB_USE_FFMA2 1
 #endif
+#ifndef ZB_T1_PANEL_FFMA2
+#define ZB_T1_PANEL_FFMA2 1  // packed FMAs in the V [A | B] panel product too
+#endif
 __device__ __forceinline__ void fma2(float& d0, float& d1, float a, float b0, float b1) {
 #if ZB_USE_FFMA2
     const float2 r = __ffma2_rn(make_float2(a, a), make_float2(b0, b1), make_float2(d0, d1));
@@ -90,10 +93,15 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
 #pragma unroll
             for (int i = 0; i < 12; ++i) {
                 const float vik = v[tri(i, kk)];
+#if ZB_T1_PANEL_FFMA2
+                fma2(acc[i][0], acc[i][1], vik, x4.x, x4.y);
+                fma2(acc[i][2], acc[i][3], vik, x4.z, x4.w);
+#else
                 acc[i][0] = fmaf(vik, x4.x, acc[i][0]);
                 acc[i][1] = fmaf(vik, x4.y, acc[i][1]);
                 acc[i][2] = fmaf(vik, x4.z, acc[i][2]);
                 acc[i][3] = fmaf(vik, x4.w, acc[i][3]);
+#endif
             }
         }
         xfirst = S[(X4 + ((p < 3) ? p + 1 : 0)) * RS];

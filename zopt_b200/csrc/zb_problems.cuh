@@ -85,8 +85,18 @@ struct Cost {
     Arr Q, R, Qf;
 };
 
+// ZB_USER_MODEL: this translation unit is a plug-in compiled around a user-defined model (kind 2, csrc/zb_user_model.cu):
+// user_step / user_lin / user_hess come from the generated header (zopt_b200/plugin.py: sympy -> CUDA).
 template <typename T>
 ZB_HD void model_step(const Model& M, long long b, const T* x, const T* u, T* xn) {
+#ifdef ZB_USER_MODEL
+    if (M.kind == 2) {
+        T t[NX];
+        user_step<T>(x, u, t);  // xn may alias x
+        for (int i = 0; i < M.n; ++i) xn[i] = t[i];
+        return;
+    }
+#endif
     if (M.kind == 1) {
         T w[3] = {T(M.wind[0]), T(M.wind[1]), T(M.wind[2])};
         quad_euler<T>(x, u, w, M.has_wind != 0, T(M.dt), xn);
@@ -107,6 +117,12 @@ ZB_HD void model_step(const Model& M, long long b, const T* x, const T* u, T* xn
 // f_x (n x n), f_u (n x m) at (x,u)
 template <typename T>
 ZB_HD void model_lin(const Model& M, long long b, const T* x, const T* u, T* fx, T* fu) {
+#ifdef ZB_USER_MODEL
+    if (M.kind == 2) {
+        user_lin<T>(x, u, fx, fu);
+        return;
+    }
+#endif
     if (M.kind == 1) {
         T w[3] = {T(M.wind[0]), T(M.wind[1]), T(M.wind[2])};
         quad_lin<T>(x, u, w, M.has_wind != 0, T(M.dt), fx, fu);
@@ -407,6 +423,20 @@ ZB_HD void solve_backward_problem(const SolveBackP& P, long long b) {
             for (int i = 0; i < m * m; ++i) vf_uu[i] = T(0);
             int q = 0;  // size of the non-trivial leading block
             T Z[ZB_PD_MAX * ZB_PD_MAX], W[ZB_PD_MAX * ZB_PD_MAX];
+#ifdef ZB_USER_MODEL
+            if (P.M.kind == 2) {
+                // general model: the full (n+m) x (n+m) block [[v_x.f_xx, (v_x.f_ux)'], [v_x.f_ux, v_x.f_uu]] (ilqrUtils.py:244-249)
+                user_hess<T>(x, u, v_x, Z);
+                pd_clamp<T>(Z, W, p, T(P.eps));
+                for (int i = 0; i < n; ++i)
+                    for (int j = 0; j < n; ++j) vf_xx[i * n + j] = Z[i * p + j];
+                for (int i = 0; i < m; ++i) {
+                    for (int j = 0; j < n; ++j) vf_ux[i * n + j] = Z[(n + i) * p + j];
+                    for (int j = 0; j < m; ++j) vf_uu[i * m + j] = Z[(n + i) * p + n + j];
+                }
+                q = -1;  // all blocks are set
+            }
+#endif
             if (P.M.kind == 1) {
                 T w[3] = {T(P.M.wind[0]), T(P.M.wind[1]), T(P.M.wind[2])};
                 T H[144];
@@ -418,8 +448,10 @@ ZB_HD void solve_backward_problem(const SolveBackP& P, long long b) {
                 for (int i = 0; i < q; ++i)
                     for (int j = 0; j < q; ++j) vf_xx[i * n + j] = Z[i * q + j];
             }
-            for (int i = q; i < n; ++i) vf_xx[i * n + i] = T(P.eps);
-            for (int i = 0; i < m; ++i) vf_uu[i * m + i] = T(P.eps);
+            if (q >= 0) {
+                for (int i = q; i < n; ++i) vf_xx[i * n + i] = T(P.eps);
+                for (int i = 0; i < m; ++i) vf_uu[i * m + i] = T(P.eps);
+            }
         }
         ilqr_step<T>(n, m, fx, fu, c, c_x, c_u, c_xx, c_ux, c_uu, P.second_order ? vf_xx : nullptr, vf_ux, vf_uu, v,
                      v_x, v_xx, l, L);

@@ -4,8 +4,9 @@ Iterative LQR / differential dynamic programming -- mirror of zopt/ilqrUtils.py.
 Same function names, argument order and return pytrees as the reference.  Differences forced by
 the GPU:
   * `dynamics` / `dynFun` must be a registered model (zopt_b200.models.LinearDynamics or
-    QuadcopterEuler) and costs `QuadraticCost` / `QuadraticTerminalCost`; an arbitrary callable
-    raises TypeError (no CPU fallback).
+    QuadcopterEuler) or a symbolic definition compiled into a plug-in (zopt_b200.plugin.SymbolicDynamics),
+    and costs `QuadraticCost` / `QuadraticTerminalCost`; an arbitrary callable raises TypeError
+    (no CPU fallback).
   * every array may carry one leading batch axis; `J` and `converged` then have shape (Bsz,).
   * the legacy `forwardPass` (ilqrUtils.py:69-113) is not provided: neither solver calls it, and its
     loop never terminates once alpha <= alphaMin.
@@ -62,7 +63,7 @@ def _rollout_args(x0, dynFun, policy, trajPrev, costFun):
     n = x0.shape[1]
     if (n, m) != (model.n, model.m):
         raise ValueError(f"policy/state dimensions ({n},{m}) do not match the model ({model.n},{model.m})")
-    mspec, mkeep = model.spec(dtype, device)
+    mspec, mkeep = (model, None) if getattr(model, "is_plugin", False) else model.spec(dtype, device)
     return device, dtype, Bsz, any_b, N, n, m, x0, l, L, xPrev, uPrev, mspec, mkeep, cspec, ckeep
 
 
@@ -75,8 +76,13 @@ def trajectoryRollout(x0, dynFun, policy, trajPrev, alpha=1):
         _rollout_args(x0, dynFun, policy, trajPrev, None)
     xTraj = torch.empty((Bsz, N + 1, n), dtype=dtype, device=device)
     uTraj = torch.empty((Bsz, N, m), dtype=dtype, device=device)
-    check(lib.zb_ilqr_rollout(dcode(dtype), device.index, stream_ptr(device), Bsz, N, C.byref(mspec), None, ptr(x0), ptr(l),
-                              ptr(L), ptr(xPrev), ptr(uPrev), float(alpha), ptr(xTraj), ptr(uTraj), None))
+    if getattr(mspec, "is_plugin", False):  # user-defined symbolic model (plugin.py)
+        mspec._need()
+        mspec._check(mspec._lib.zb_user_rollout(dcode(dtype), device.index, stream_ptr(device), Bsz, N, None, ptr(x0), ptr(l), ptr(L),
+                                                ptr(xPrev), ptr(uPrev), float(alpha), ptr(xTraj), ptr(uTraj), None))
+    else:
+        check(lib.zb_ilqr_rollout(dcode(dtype), device.index, stream_ptr(device), Bsz, N, C.byref(mspec), None, ptr(x0), ptr(l),
+                                  ptr(L), ptr(xPrev), ptr(uPrev), float(alpha), ptr(xTraj), ptr(uTraj), None))
     return Trajectory(xTraj, uTraj) if any_b else Trajectory(xTraj[0], uTraj[0])
 
 
@@ -87,6 +93,9 @@ def forwardPass2(x0, dynFun, costFun, policy, trajPrev, return_index=False):
     """
     (device, dtype, Bsz, any_b, N, n, m, x0, l, L, xPrev, uPrev, mspec, mkeep, cspec, ckeep) = \
         _rollout_args(x0, dynFun, policy, trajPrev, costFun)
+    if getattr(mspec, "is_plugin", False):
+        raise TypeError("forwardPass2 as a stand-alone building block is available for the registered models; a "
+                        "SymbolicDynamics model runs it inside iterativeLqr / differentialDynamicProgramming")
     xTraj = torch.empty((Bsz, N + 1, n), dtype=dtype, device=device)
     uTraj = torch.empty((Bsz, N, m), dtype=dtype, device=device)
     J = torch.empty((Bsz,), dtype=dtype, device=device)
@@ -229,8 +238,12 @@ def _solve(dynamics, runningCost, terminalCost, x0, uGuess, maxIter, tol, second
     if (n, m) != (model.n, model.m):
         raise ValueError(f"x0/uGuess dimensions ({n},{m}) do not match the model ({model.n},{model.m})")
     maxIter = int(maxIter)
-    mspec, mkeep = model.spec(dtype, device)
     cspec, ckeep = cost_spec(rc, tc, dtype, device)
+    if getattr(model, "is_plugin", False):  # user-defined symbolic model: its own compiled solver library (plugin.py)
+        xTraj, uTraj, L, J, conv, iters, alog, Jlog = model.solve(cspec, dtype, device, Bsz, N, x0, uGuess, maxIter, tol,
+                                                                  second_order, return_log)
+        return _pack_solution(xTraj, uTraj, L, J, conv, iters, alog, Jlog, any_b, return_log, maxIter)
+    mspec, mkeep = model.spec(dtype, device)
     xTraj = torch.empty((Bsz, N + 1, n), dtype=dtype, device=device)
     uTraj = torch.empty((Bsz, N, m), dtype=dtype, device=device)
     L = torch.empty((Bsz, N, m, n), dtype=dtype, device=device)
@@ -249,6 +262,10 @@ def _solve(dynamics, runningCost, terminalCost, x0, uGuess, maxIter, tol, second
     check(lib.zb_ilqr_solve(dcode(dtype), device.index, stream_ptr(device), Bsz, N, flags, C.byref(mspec),
                             C.byref(cspec), ptr(x0), ptr(uGuess), maxIter, float(tol), ptr(xTraj), ptr(uTraj), ptr(L),
                             ptr(J), ptr(conv), ptr(iters), ptr(alog), ptr(Jlog), ptr(ws), wsb))
+    return _pack_solution(xTraj, uTraj, L, J, conv, iters, alog, Jlog, any_b, return_log, maxIter)
+
+
+def _pack_solution(xTraj, uTraj, L, J, conv, iters, alog, Jlog, any_b, return_log, maxIter):
     conv = conv.bool()
     if not any_b:
         xTraj, uTraj, L, J, conv, iters = xTraj[0], uTraj[0], L[0], J[0], conv[0], iters[0]

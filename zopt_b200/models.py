@@ -9,6 +9,7 @@ and each carries the spec the kernels need.  Anything else raises TypeError -- t
 fallback.
 
     LinearDynamics(A, B)              x+ = A x + B u                 (tests/test_ilqrUtils.py:167-196)
+    plugin.SymbolicDynamics(f, n, m)  x+ = f(x, u) given in sympy, compiled into a solver plug-in (zopt_b200/plugin.py)
     QuadcopterEuler(dt, wind_ned)     x+ = x + dt*inertialDynamics   (demos/iterativeLqr.py:35, zopt/quadcopter.py:116-144)
     QuadraticCost(Q, R)               c(x,u) = x'Qx + u'Ru           (demos/iterativeLqr.py:12-13)
     QuadraticTerminalCost(Qf)         cf(x) = x'Qf x                 (demos/iterativeLqr.py:37)
@@ -98,12 +99,12 @@ class QuadraticTerminalCost:
 
 
 def require_model(dynFun):
-    if isinstance(dynFun, (LinearDynamics, QuadcopterEuler)):
+    if isinstance(dynFun, (LinearDynamics, QuadcopterEuler)) or getattr(dynFun, "is_plugin", False):
         return dynFun
     raise TypeError(
         "zopt_b200 cannot differentiate or roll out an arbitrary Python callable on the GPU (the reference traces it "
-        "with JAX). Pass a registered model: zopt_b200.models.LinearDynamics(A, B) or QuadcopterEuler(dt, wind_ned). "
-        "There is no CPU fallback.")
+        "with JAX). Pass a registered model: zopt_b200.models.LinearDynamics(A, B) or QuadcopterEuler(dt, wind_ned), or "
+        "define the dynamics symbolically: zopt_b200.plugin.SymbolicDynamics(f, n, m). There is no CPU fallback.")
 
 
 def require_cost(runningCost, terminalCost):

@@ -1,0 +1,236 @@
+"""
+User-defined dynamics for the iLQR / DDP solvers and trajectoryRollout.
+
+The reference's solvers take an arbitrary Python callable `dynamics(x, u)` and differentiate it with JAX
+(zopt/ilqrUtils.py:260-268, zopt/pytrees.py:138-194).  A CUDA kernel cannot trace a lambda, so a model outside the
+registered ones (zopt_b200.models) is defined SYMBOLICALLY:
+
+    import sympy as sp
+    from zopt_b200.plugin import SymbolicDynamics
+    pend = SymbolicDynamics(lambda x, u: [x[0] + 0.1 * x[1], x[1] + 0.1 * (u[0] - sp.sin(x[0]))], n=2, m=1)
+    traj, L, J, converged = iterativeLqr(pend, QuadraticCost(Q, R), QuadraticTerminalCost(Qf), x0, uGuess)
+
+`f` is called once with lists of sympy symbols and returns the n expressions of x+.  sympy differentiates them (Jacobians
+f_x, f_u and the costate-contracted Hessian sum_i lam_i d2f_i/dz2, z = [x; u], with common subexpressions shared), the
+result is printed as CUDA into a header, and `csrc/zb_user_model.cu` -- the library's generic solver kernels compiled
+around that header -- is built with nvcc for sm_100a into its own shared library (cached by content hash under
+`zopt_b200/_plugin_cache/`, in-tree so that a library built on a machine without a GPU travels with the repo).
+The object stays callable like the lambda it replaces (`dyn(x, u)` on torch tensors, differentiable with torch.func: that
+is what the test oracle does), and there is no CPU fallback: solving needs the compiled plug-in and a CUDA device.
+Limits of the generic kernels: n <= 16, m <= 8, one thread per problem (16 per problem in the line search).
+"""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+from ._lib import ZbCost, check as _check_main, dcode, pick_device, ptr, stream_ptr, to_dev
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+CACHE_DIR = os.path.join(_HERE, "_plugin_cache")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+MAX_N, MAX_M = 16, 8
+
+
+def _cuda_printer():
+    from sympy.printing.c import C99CodePrinter
+
+    class Printer(C99CodePrinter):
+        """C with every literal typed T(...) (the kernels are templates over float / double) and small integer powers
+        written as products."""
+
+        def _print_Float(self, e):
+            return "T(%s)" % repr(float(e))
+
+        def _print_Integer(self, e):
+            return "T(%d)" % int(e)
+
+        def _print_Rational(self, e):
+            return "(T(%d)/T(%d))" % (int(e.p), int(e.q))
+
+        def _print_Pow(self, e):
+            b, ex = e.base, e.exp
+            if ex.is_Integer and 2 <= int(ex) <= 4:
+                return "(" + "*".join(["(%s)" % self._print(b)] * int(ex)) + ")"
+            if ex.is_Integer and -4 <= int(ex) <= -1:
+                return "(T(1)/(" + "*".join(["(%s)" % self._print(b)] * (-int(ex))) + "))"
+            if ex == 0.5 or (ex.is_Rational and ex.p == 1 and ex.q == 2):
+                return "sqrt(%s)" % self._print(b)
+            return "pow((T)(%s), (T)(%s))" % (self._print(b), self._print(ex))
+
+    return Printer()
+
+
+def _emit(name, args, outputs, sizes):
+    """One templated ZB_HD function `name(args...)` writing the flat output arrays in `outputs` ({array name: [exprs]})."""
+    import sympy as sp
+    pr = _cuda_printer()
+    flat = [e for k in outputs for e in outputs[k]]
+    repl, red = sp.cse(flat, symbols=sp.numbered_symbols("t_"), optimizations="basic")
+    lines = ["template <typename T>", "ZB_HD void %s(%s) {" % (name, args)]
+    for s, e in repl:
+        lines.append("    const T %s = %s;" % (s, pr.doprint(e)))
+    i = 0
+    for k in outputs:
+        for j in range(len(outputs[k])):
+            lines.append("    %s[%d] = %s;" % (k, j, pr.doprint(red[i])))
+            i += 1
+    lines.append("}")
+    return "\n".join(lines)
+
+
+class SymbolicDynamics:
+    """x+ = f(x, u) given as sympy expressions; compiled into a solver plug-in (see the module docstring)."""
+    is_plugin = True
+
+    def __init__(self, f, n, m, build=True):
+        import sympy as sp
+        n, m = int(n), int(m)
+        if not (1 <= n <= MAX_N and 1 <= m <= MAX_M):
+            raise ValueError(f"user models are limited to n <= {MAX_N}, m <= {MAX_M} (got {n}, {m})")
+        self.n, self.m = n, m
+        xs, us = list(sp.symbols(f"x0:{n}", real=True)), list(sp.symbols(f"u0:{m}", real=True))
+        exprs = [sp.sympify(e) for e in f(xs, us)]
+        if len(exprs) != n:
+            raise ValueError(f"f must return {n} expressions (got {len(exprs)})")
+        free = set().union(*[e.free_symbols for e in exprs]) - set(xs) - set(us)
+        if free:
+            raise ValueError(f"f may only depend on its arguments; free symbols: {sorted(map(str, free))}")
+        self._xs, self._us, self._exprs = xs, us, exprs
+        z = xs + us
+        lam = list(sp.symbols(f"lam0:{n}", real=True))
+        F = sp.Matrix(exprs)
+        Jx, Ju = F.jacobian(xs), F.jacobian(us)
+        contracted = sum((lam[i] * exprs[i] for i in range(n)), sp.Integer(0))
+        H = sp.hessian(contracted, z)
+        # symbols -> array accesses
+        sub = {xs[i]: sp.Symbol(f"x[{i}]") for i in range(n)}
+        sub.update({us[i]: sp.Symbol(f"u[{i}]") for i in range(m)})
+        sub.update({lam[i]: sp.Symbol(f"lam[{i}]") for i in range(n)})
+        S = lambda e: sp.sympify(e).xreplace(sub)
+        p = n + m
+        parts = ["// GENERATED by zopt_b200/plugin.py -- do not edit.  x+ = f(x, u), n = %d, m = %d" % (n, m), "#pragma once",
+                 "#define ZB_USER_N %d" % n, "#define ZB_USER_M %d" % m,
+                 _emit("user_step", "const T* __restrict__ x, const T* __restrict__ u, T* __restrict__ xn", {"xn": [S(e) for e in exprs]}, None),
+                 _emit("user_lin", "const T* __restrict__ x, const T* __restrict__ u, T* __restrict__ fx, T* __restrict__ fu",
+                       {"fx": [S(Jx[i, j]) for i in range(n) for j in range(n)], "fu": [S(Ju[i, j]) for i in range(n) for j in range(m)]}, None),
+                 _emit("user_hess", "const T* __restrict__ x, const T* __restrict__ u, const T* __restrict__ lam, T* __restrict__ H",
+                       {"H": [S(H[i, j]) for i in range(p) for j in range(p)]}, None)]
+        self.source = "\n\n".join(parts) + "\n"
+        self._torch_fn = None
+        self._lib = None
+        if build:
+            self.build()
+
+    # ------------------------------------------------------------------------------------------ callable like the lambda
+    def __call__(self, x, u):
+        """Evaluate x+ = f(x, u) on torch tensors (leading batch axes allowed); differentiable with torch autograd."""
+        import sympy as sp
+        if self._torch_fn is None:
+            tm = {k: getattr(torch, k) for k in ("sin", "cos", "tan", "exp", "log", "sqrt", "tanh", "sinh", "cosh", "atan", "asin", "acos")}
+            tm["Abs"] = torch.abs
+            self._torch_fn = sp.lambdify(self._xs + self._us, self._exprs, modules=[tm])
+        x, u = torch.as_tensor(x), torch.as_tensor(u)
+        out = self._torch_fn(*x.unbind(-1), *u.unbind(-1))
+        zero = x[..., 0] * 0
+        return torch.stack([zero + o for o in out], dim=-1)
+
+    def batch(self):
+        return 1
+
+    # ------------------------------------------------------------------------------------------ build / load
+    def _key(self):
+        h = hashlib.sha1(self.source.encode())
+        for fn in ("zb_user_model.cu", "ilqr_generic.cuh", "zb_problems.cuh", "zb_steps.cuh", "zb_math.cuh", "zb_common.cuh", "ilqr_params.cuh"):
+            with open(os.path.join(_CSRC, fn), "rb") as fh:
+                h.update(fh.read())
+        return h.hexdigest()[:16]
+
+    def build(self):
+        """Generate the model header and compile the plug-in for sm_100a (nvcc cross-compiles without a GPU); cached."""
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        key = self._key()
+        hdr, so = os.path.join(CACHE_DIR, f"model_{key}.cuh"), os.path.join(CACHE_DIR, f"libzb_model_{key}.so")
+        if not os.path.exists(so):
+            with open(hdr, "w") as fh:
+                fh.write(self.source)
+            cmd = [NVCC, "-cudart", "static", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+                   "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
+                   f'-DZB_USER_MODEL_HEADER="{hdr}"', "-I", _CSRC, "-shared", "-o", so + ".tmp", os.path.join(_CSRC, "zb_user_model.cu")]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed for the user model:\n" + r.stderr[-4000:])
+            os.replace(so + ".tmp", so)
+        self.so_path = so
+        L = C.CDLL(so)
+        L.zb_user_ilqr_workspace_bytes.restype = C.c_size_t
+        L.zb_user_ilqr_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32]
+        for name in ("zb_user_dims", "zb_user_last_error", "zb_user_step", "zb_user_rollout", "zb_user_ilqr_solve"):
+            getattr(L, name).restype = C.c_int32
+        L.zb_user_step.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64] + [C.c_void_p] * 5
+        L.zb_user_rollout.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(ZbCost)] + [C.c_void_p] * 5 + \
+            [C.c_double] + [C.c_void_p] * 3
+        L.zb_user_ilqr_solve.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(ZbCost),
+                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_double] + [C.c_void_p] * 9 + [C.c_size_t]
+        nn, mm = C.c_int32(0), C.c_int32(0)
+        L.zb_user_dims(C.byref(nn), C.byref(mm))
+        assert (nn.value, mm.value) == (self.n, self.m)
+        self._lib = L
+        return self
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        buf = C.create_string_buffer(512)
+        self._lib.zb_user_last_error(buf, 512)
+        msg = buf.value.decode(errors="replace")
+        if rc < 0:
+            raise ValueError(msg)
+        raise RuntimeError(f"CUDA error {rc}: {msg}")
+
+    def _need(self):
+        if self._lib is None:
+            raise RuntimeError("the model's plug-in library is not built (SymbolicDynamics(..., build=False)); call .build()")
+        if not torch.cuda.is_available():
+            raise RuntimeError("zopt_b200 needs a CUDA device; there is no CPU fallback")
+
+    # ------------------------------------------------------------------------------------------ device entry points
+    def step(self, x, u, linearize=False):
+        """x+ (and optionally f_x, f_u) at a batch of points, evaluated by the generated CUDA code."""
+        self._need()
+        device = pick_device(x, u)
+        dtype = x.dtype if isinstance(x, torch.Tensor) and x.dtype in (torch.float32, torch.float64) else torch.float64
+        x, u = to_dev(x, dtype, device), to_dev(u, dtype, device)
+        batched = x.ndim == 2
+        x, u = (x if batched else x[None]).contiguous(), (u if batched else u[None]).contiguous()
+        Bsz = x.shape[0]
+        xn = torch.empty_like(x)
+        fx = torch.empty((Bsz, self.n, self.n), dtype=dtype, device=device) if linearize else None
+        fu = torch.empty((Bsz, self.n, self.m), dtype=dtype, device=device) if linearize else None
+        self._check(self._lib.zb_user_step(dcode(dtype), device.index, stream_ptr(device), Bsz, ptr(x), ptr(u), ptr(xn), ptr(fx), ptr(fu)))
+        if not batched:
+            xn, fx, fu = xn[0], (fx[0] if linearize else None), (fu[0] if linearize else None)
+        return (xn, fx, fu) if linearize else xn
+
+    def solve(self, cspec, dtype, device, Bsz, N, x0, uGuess, maxIter, tol, second_order, return_log):
+        """iterativeLqr / differentialDynamicProgramming for this model (called by zopt_b200.ilqrUtils._solve)."""
+        self._need()
+        n, m = self.n, self.m
+        xTraj = torch.empty((Bsz, N + 1, n), dtype=dtype, device=device)
+        uTraj = torch.empty((Bsz, N, m), dtype=dtype, device=device)
+        L = torch.empty((Bsz, N, m, n), dtype=dtype, device=device)
+        J = torch.empty((Bsz,), dtype=dtype, device=device)
+        conv = torch.empty((Bsz,), dtype=torch.uint8, device=device)
+        iters = torch.empty((Bsz,), dtype=torch.int32, device=device)
+        alog = torch.empty((Bsz, max(maxIter, 1)), dtype=torch.int32, device=device) if return_log else None
+        Jlog = torch.empty((Bsz, maxIter + 1), dtype=dtype, device=device) if return_log else None
+        wsb = self._lib.zb_user_ilqr_workspace_bytes(dcode(dtype), Bsz, N)
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=device)
+        self._check(self._lib.zb_user_ilqr_solve(dcode(dtype), device.index, stream_ptr(device), Bsz, N, 1 if second_order else 0,
+                                                 C.byref(cspec), ptr(x0), ptr(uGuess), maxIter, float(tol), ptr(xTraj), ptr(uTraj),
+                                                 ptr(L), ptr(J), ptr(conv), ptr(iters), ptr(alog), ptr(Jlog), ptr(ws), wsb))
+        return xTraj, uTraj, L, J, conv, iters, alog, Jlog
