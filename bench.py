@@ -178,7 +178,8 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    sample = args.cpu_sample
+    # bounded sample of the workload per step, scaled so that the whole run is ~20 full samples of CPU work whatever K is
+    sample = max(256, min(args.cpu_sample, args.cpu_sample * 20 // max(args.steps, 1)))
     real = try_real_reference(sample, args.steps, min(args.warmup, 1))
     kind = "reference" if real else "port"
     val, sec, threads = real if real else time_cpu(sample, args.steps, min(args.warmup, 1))
@@ -187,7 +188,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(sample), "cpu_baseline": cb,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args.batch), "cpu_baseline": cb,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
