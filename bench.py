@@ -363,6 +363,18 @@ def run_ours(args):
             extra_ms.append(c0.elapsed_time(c1) / 3)
         else:
             extra_ms.append(extra_ms[0])
+        # cfg 3 in fp64, the reference's own precision: fused cooperative kernel (csrc/lqr_quad64.cuh)
+        x3d, Q3d, R3d = x3.double(), Q3.double(), R3.double()
+        quadcopterClosedLoopMpc(x3d, Q3d, R3d, 50, 200, dt=0.1, Qf=10 * Q3d)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(2):
+            quadcopterClosedLoopMpc(x3d, Q3d, R3d, 50, 200, dt=0.1, Qf=10 * Q3d)
+        c1.record()
+        barrier()
+        cl64_ms = c0.elapsed_time(c1) / 2
+        del x3d, Q3d, R3d
         d4 = configs.cfg4(Bsz=16384)
         x4 = torch.as_tensor(d4["x0"][lo:hi], dtype=torch.float64, device=dev)
         uG = torch.as_tensor(d4["uGuess"], dtype=torch.float64, device=dev)
@@ -471,11 +483,12 @@ def run_ours(args):
         boxcl5_opt = float((stc5 == 0).float().mean())
     while len(extra_ms) < 9:
         extra_ms.append(0.0)
+    extra_ms.append(0.0 if args.no_extras else cl64_ms)
 
     times = torch.tensor([ms, e2e_ms, k_ms, e2e_u_ms] + extra_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, k_ms, e2e_u_ms, cl_ms, clw_ms, il_ms, ddp_ms, tv_ms, f64_ms, box_ms, boxcl_ms, boxcl5_ms = (float(v) for v in times.cpu())
+    ms, e2e_ms, k_ms, e2e_u_ms, cl_ms, clw_ms, il_ms, ddp_ms, tv_ms, f64_ms, box_ms, boxcl_ms, boxcl5_ms, cl64_ms = (float(v) for v in times.cpu())
 
     if rank == 0:
         total = Bsz * world
@@ -526,6 +539,12 @@ def run_ours(args):
                                          "scaling": "strong"},
                 "cfg3_closed_loop_mpc_weak": {"value": 16384 * world * 200 / (clw_ms * 1e-3), "unit": "MPC solves/s", "ms": clw_ms,
                                               "workload": "as cfg3 but 16,384 problems PER GPU", "scaling": "weak"},
+                "cfg3_closed_loop_mpc_fp64": {"value": 16384 * 200 / (cl64_ms * 1e-3), "unit": "MPC solves/s", "ms": cl64_ms,
+                                              "workload": "cfg3 (16,384 problems total, sharded over ranks) in fp64, the reference's own precision: "
+                                                          "one fused cooperative kernel", "scaling": "strong",
+                                              "roofline": {"bound": "fp64_fma", "achieved": 16384 * 200 * FLOP_PER_SOLVE / (cl64_ms * 1e-3) / 1e12,
+                                                           "peak": peak64.value / 1e12, "unit": "TFLOP/s",
+                                                           "frac": 16384 * 200 * FLOP_PER_SOLVE / (cl64_ms * 1e-3) / peak64.value}},
                 "cfg4_ilqr": {"value": 16384 * 10 / (il_ms * 1e-3), "unit": "problem-iterations/s", "ms": il_ms,
                               "workload": "16,384 problems total (sharded over ranks), N=200, 10 iterations, 16-way line search, fp64",
                               "scaling": "strong", "algorithmic_flop_per_problem_iteration": 4.66e6,

@@ -217,7 +217,8 @@ ZB_API int32_t zb_mpc_box_closed_loop(int32_t dtype, int32_t device, void* strea
                                void* workspace, size_t workspace_bytes);
 
 /* ---- closed-loop LQR-MPC of the quadcopter (BASELINE cfg 3; the receding-horizon loop of demos/lqrMpc.py:42-47 with a
- * nonlinear plant), fp32, bounds inactive.  Per simulation step t: A_t = I + dt dF/dx(x_t,u_trim), B = dt dF/du, a full
+ * nonlinear plant), fp32 or fp64 (the fp64 kernel is the cooperative one of csrc/lqr_quad64.cuh; the ZB_VARIANT_* flags select
+ * between the two fp32 kernels), bounds inactive.  Per simulation step t: A_t = I + dt dF/dx(x_t,u_trim), B = dt dF/du, a full
  * Riccati sweep of horizon N from Qf (zopt/mpcUtils.py:47-59 with infinite bounds), u_t = first move of the plan,
  * x_{t+1} = x_t + dt F(x_t, u_trim + u_t) (zopt/quadcopter.py:116-144).  One fused kernel; only the trajectory is written:
  * xSim_out (Bsz,Tsim+1,12), uSim_out (Bsz,Tsim,4) (deviation from u_trim).  Q,R,Qf: (12,12),(4,4),(12,12) blocks (symmetric). */

@@ -66,16 +66,14 @@ def test_mpc_and_closed_loop_guards(Bsz, diag, f32):
     torch.cuda.synchronize()
     assert all(g.ok() for g in (u0, xT, uT, st, it, ws))
     assert torch.isfinite(xT.t).all() and torch.isfinite(uT.t).all() and (st.t == 0).all()
-    if code == 1:
-        return  # the fused closed loop is an fp32 kernel
     # closed loop
     Ts = 5
     xS, uS = Guarded((Bsz, Ts + 1, 12), f32, dev), Guarded((Bsz, Ts, 4), f32, dev)
     ut = (C.c_double * 4)(*configs.U_TRIM)
     x0 = xbar.clone()
     x0[:, 9:12] *= 0.2
-    for variant in (4, 8):  # thread-per-problem, quad
-        check(lib.zb_mpc_closed_loop_quad(0, 0, stream_ptr(dev), Bsz, N, Ts, 0.1, ut, views[2].ref(), views[3].ref(), views[4].ref(),
+    for variant in ((4, 8) if code == 0 else (0,)):  # fp32: thread-per-problem, quad; fp64: the cooperative kernel
+        check(lib.zb_mpc_closed_loop_quad(code, 0, stream_ptr(dev), Bsz, N, Ts, 0.1, ut, views[2].ref(), views[3].ref(), views[4].ref(),
                                           (2 if diag else 0) | variant, ptr(x0), ptr(xS.t), ptr(uS.t)))
         torch.cuda.synchronize()
         assert xS.ok() and uS.ok() and torch.isfinite(xS.t).all()

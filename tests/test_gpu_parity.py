@@ -780,6 +780,14 @@ def test_closed_loop_mpc_fused_vs_composed(dense_cost, variant):
         assert relerr(uref[0, t], up[0]) < 1e-9
         xo = f(xo, uto + torch.as_tensor(up[0]))
     assert relerr(xref[0, -1], xo) < 1e-9
+    # the fused fp64 kernel (csrc/lqr_quad64.cuh: cooperative sweep, in-kernel linearisation) against the composed fp64 loop
+    # and, through it, the oracle: closed loops amplify rounding differences, hence 1e-8 over 25 steps
+    if variant == "thread":
+        t64 = quadcopterClosedLoopMpc(cuda(x0), Qd, Rd, N, Tsim, dt=dt, Qf=10 * Qd)
+        assert t64.xTraj.dtype == torch.float64
+        assert per_problem_relerr(t64.xTraj[fi], xref.cpu().numpy()[fi]).max() < 1e-8
+        assert per_problem_relerr(t64.uTraj[fi], uref.cpu().numpy()[fi]).max() < 1e-8
+        assert relerr(t64.uTraj[0, 0], uref[0, 0]) < 1e-11  # first step: no accumulated history
 
 
 def test_pytree_constructors_and_building_block_pipeline():

@@ -71,6 +71,18 @@ struct LqrQuadP {
     int32_t* iters;
 };
 
+// fused fp64 closed-loop LQR-MPC of the quadcopter (lqr_quad64.cuh)
+struct ClosedLoopQuadP {
+    long long Bsz;
+    int N, Tsim;
+    double dt;
+    double utrim[4];
+    Arr Q, R, Qf;
+    const void* x0;  // (Bsz,12)
+    void* xSim;      // (Bsz,Tsim+1,12)
+    void* uSim;      // (Bsz,Tsim,4)  applied deviation u_t (the control sent to the plant is u_trim + u_t)
+};
+
 inline bool ilqr_fast_eligible(const Model& M, int second_order, bool cost_diagonal) {
     return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && (!second_order || cost_diagonal);
 }
@@ -82,5 +94,6 @@ int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream,
 int32_t fwd_quad_launch(int32_t dtype, const FwdQuadP& P, cudaStream_t stream);
 int32_t solve_setup_quad_launch(int32_t dtype, const SetupQuadP& P, cudaStream_t stream);
 int32_t riccati_quad_launch(int32_t dtype, const LqrQuadP& P, cudaStream_t stream);
+int32_t mpc_closed_loop_quad64_launch(const ClosedLoopQuadP& P, cudaStream_t stream);
 
 }  // namespace zb

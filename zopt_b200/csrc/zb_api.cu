@@ -762,7 +762,7 @@ extern "C" {
 int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t Tsim, double dt,
                                 const double* u_trim, const zb_arr* Q, const zb_arr* R, const zb_arr* Qf, int32_t flags,
                                 const void* x0, void* xSim_out, void* uSim_out) {
-    ZB_ARG(dtype == ZB_F32, "zb_mpc_closed_loop_quad: fp32 only (compose linearize + zb_mpc_lqr_solve + dynamics for fp64)");
+    ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "bad dtype %d", dtype);
     ZB_ARG(Bsz >= 0 && N >= 1 && Tsim >= 0, "bad sizes");
     if (Bsz == 0) return 0;
     ZB_ARG(Q && R && Qf && Q->ptr && R->ptr && Qf->ptr && x0 && xSim_out && (uSim_out || Tsim == 0) && u_trim, "NULL operand");
@@ -770,6 +770,15 @@ int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int
     ZB_ARG((flags & ZB_COST_DIAGONAL) || (arr_ok(to_arr(Q)) && arr_ok(to_arr(R)) && arr_ok(to_arr(Qf))), "cost blocks must be 16-byte aligned");
     DeviceGuard g(device);
     ZB_CUDA(g.err);
+    if (dtype == ZB_F64) {  // the reference's own precision: cooperative four-threads-per-problem kernel (lqr_quad64.cuh)
+        ZB_ARG(arr_ok(to_arr(Q)) && arr_ok(to_arr(R)) && arr_ok(to_arr(Qf)), "cost blocks must be 16-byte aligned");
+        ClosedLoopQuadP P64{};
+        P64.Bsz = Bsz; P64.N = N; P64.Tsim = Tsim; P64.dt = dt;
+        for (int i = 0; i < 4; ++i) P64.utrim[i] = u_trim[i];
+        P64.Q = to_arr(Q); P64.R = to_arr(R); P64.Qf = to_arr(Qf);
+        P64.x0 = x0; P64.xSim = xSim_out; P64.uSim = uSim_out;
+        return mpc_closed_loop_quad64_launch(P64, (cudaStream_t)stream);
+    }
     t1::ClosedLoopP P{};
     P.Bsz = Bsz; P.N = N; P.Tsim = Tsim; P.dt = (float)dt;
     for (int i = 0; i < 4; ++i) P.utrim[i] = (float)u_trim[i];

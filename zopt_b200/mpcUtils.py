@@ -228,18 +228,20 @@ def quadcopterClosedLoopMpc(x0, Q, R, N, Tsim, dt=0.1, Qf=None, uTrim=(9.807, 0.
     demos/lqrMpc.py:42-47, batched and fused into one kernel: every simulation step re-linearises the Euler quadcopter at
     the current state (`A = I + dt dF/dx(x_t, uTrim)`, `B = dt dF/du`, zopt/quadcopter.py:116-144), solves the
     unconstrained `lqrMpc(A, B, Q, R, N, Qf=Qf)` problem from `x_t` (a full Riccati sweep, nothing cached), applies the
-    first move (`uTrim + u_t`) to the plant `x + dt * inertialDynamics(x, u)`.  fp32, bounds inactive.
+    first move (`uTrim + u_t`) to the plant `x + dt * inertialDynamics(x, u)`.  Bounds inactive; fp32, or fp64 when `x0` is an
+    fp64 tensor.
 
     x0 (Bsz,12) or (12,); Q (12,12), R (4,4), Qf (12,12, default Q) optionally batched.
     Returns Trajectory(xTraj (Bsz,Tsim+1,12), uTraj (Bsz,Tsim,4)) with uTraj the deviation from uTrim.
     `variant`: "auto" (4 threads per problem for small batches, one thread per problem otherwise), "thread", "quad".
-    With finite bounds or in fp64, compose `Quadcopter.linearizeInertial`, `lqrMpc(...).solve` and
+    With finite bounds, compose `Quadcopter.linearizeInertial`, `lqrMpc(...).solve` and
     `Quadcopter.inertialDynamics` step by step instead.
     """
     if Qf is None:
         Qf = Q
     device = pick_device(x0, Q, R, Qf)
-    f32 = torch.float32
+    # fp64 when the caller's state is fp64 (the reference's precision: cooperative kernel of csrc/lqr_quad64.cuh), else fp32
+    f32 = torch.float64 if (isinstance(x0, torch.Tensor) and x0.dtype == torch.float64) else torch.float32
     x0, Q, R, Qf = (to_dev(t, f32, device) for t in (x0, Q, R, Qf))
     batched = x0.ndim == 2
     x0 = (x0 if batched else x0[None]).contiguous()
@@ -249,7 +251,7 @@ def quadcopterClosedLoopMpc(x0, Q, R, N, Tsim, dt=0.1, Qf=None, uTrim=(9.807, 0.
     xS = torch.empty((Bsz, Tsim + 1, 12), dtype=f32, device=device)
     uS = torch.empty((Bsz, Tsim, 4), dtype=f32, device=device)
     ut = (C.c_double * 4)(*[float(v) for v in uTrim])
-    check(lib.zb_mpc_closed_loop_quad(0, device.index, stream_ptr(device), Bsz, int(N), int(Tsim), float(dt), ut,
+    check(lib.zb_mpc_closed_loop_quad(0 if f32 == torch.float32 else 1, device.index, stream_ptr(device), Bsz, int(N), int(Tsim), float(dt), ut,
                                       *[v.ref() for v in views],
                                       (2 if diag else 0) | {"auto": 0, "thread": 4, "quad": 8}[variant], ptr(x0), ptr(xS), ptr(uS)))
     return Trajectory(xS, uS) if batched else Trajectory(xS[0], uS[0])
