@@ -69,6 +69,7 @@ struct LqrQuadP {
     void *u0, *xTraj, *uTraj;
     int8_t* status;
     int32_t* iters;
+    int cost_diagonal;   // the caller asserted diagonal Q, R (ZB_COST_DIAGONAL)
 };
 
 // fused fp64 closed-loop LQR-MPC of the quadcopter (lqr_quad64.cuh)
@@ -81,6 +82,7 @@ struct ClosedLoopQuadP {
     const void* x0;  // (Bsz,12)
     void* xSim;      // (Bsz,Tsim+1,12)
     void* uSim;      // (Bsz,Tsim,4)  applied deviation u_t (the control sent to the plant is u_trim + u_t)
+    int cost_diagonal;
 };
 
 inline bool ilqr_fast_eligible(const Model& M, int second_order, bool cost_diagonal) {

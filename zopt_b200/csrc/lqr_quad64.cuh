@@ -12,7 +12,7 @@
 //   5.  V' = Q + A'W - M'L, two 4x4 blocks per thread, written back "lower triangle wins" (V stays exactly symmetric)
 // V' = Q + A'VA - M'G^-1 M is the reference's Joseph form (lqrUtils.py:169) in exact arithmetic; parity with the fp64
 // oracle is gated at 1e-10.  Q_k and R_k are read from global memory where they are needed (once per step, L1-resident
-// when time-invariant), so the slab is 402 words and 8 warps fit an SM in fp64.  A_k, B_k that really vary along the
+// when time-invariant; with ZB_COST_DIAGONAL their diagonals sit in the slab), so the slab is 418 words and 8 warps fit an SM in fp64.  A_k, B_k that really vary along the
 // horizon are re-staged every step (synchronously: the streamed fp32 kernel of lqr_t1.cuh is the tuned path for that).
 #pragma once
 #include "ilqr_fast.cuh"
@@ -20,12 +20,16 @@
 namespace zb {
 
 constexpr int LQ_V = 0, LQ_A = 144, LQ_B = 288, LQ_M = 336, LQ_G = 384;
-constexpr int LQ_PS_F32 = 404;  // 404/4 = 101 odd (16-byte units)
-constexpr int LQ_PS_F64 = 402;  // 402/2 = 201 odd
+constexpr int LQ_QD = 400;      // diagonal-cost variants: diag(Q) 12 words, diag(R) 4 words
+constexpr int LQ_PS_F32 = 420;  // 420/4 = 105 odd (16-byte units)
+constexpr int LQ_PS_F64 = 418;  // 418/2 = 209 odd
 
 // One backward Riccati step of the quad that owns the slab (Vs, As, Bs, Ms, Gs): V <- Q_k + A'VA - M'G^-1 M in place, and
 // this thread's 4x4 tile of L_k = G^-1 B'VA (columns 4t..4t+3; thread 3's tile is not a gain).  Ends with a __syncwarp().
-template <typename T>
+// QDIAG: the caller asserted diagonal Q, R (ZB_COST_DIAGONAL): Qk / Rk then point at their DIAGONALS (12 + 4 words, kept in
+// the slab) -- reading dense Q_k blocks from global memory every step was 25 % of the stall samples (L1 is mostly carved
+// out as shared memory, so they came from L2).
+template <typename T, bool QDIAG = false>
 __device__ __forceinline__ void riccati_quad_step(T* Vs, const T* As, const T* Bs, T* Ms, T* Gs, const T* Qk, const T* Rk, int t,
                                                   T (&L)[4][4]) {
     const T* Ct = (t < 3) ? (As + 4 * t) : Bs;
@@ -66,8 +70,12 @@ __device__ __forceinline__ void riccati_quad_step(T* Vs, const T* As, const T* B
     // ---- 3. G = R_k + G0 (thread 3), M tile (threads 0..2) -> shared ----
     if (t == 3) {
 #pragma unroll
+        const Vec4<T> rd = QDIAG ? ldv4(Rk) : Vec4<T>{{T(0), T(0), T(0), T(0)}};
+#pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const Vec4<T> r4 = ldv4(Rk + a * 4);
+            Vec4<T> r4;
+            if (QDIAG) r4 = Vec4<T>{{a == 0 ? rd.v[0] : T(0), a == 1 ? rd.v[1] : T(0), a == 2 ? rd.v[2] : T(0), a == 3 ? rd.v[3] : T(0)}};
+            else r4 = ldv4(Rk + a * 4);
             stv4(Gs + a * 4, M[a][0] + r4.v[0], M[a][1] + r4.v[1], M[a][2] + r4.v[2], M[a][3] + r4.v[3]);
         }
     } else {
@@ -102,11 +110,19 @@ __device__ __forceinline__ void riccati_quad_step(T* Vs, const T* As, const T* B
         const int sblk = (bi == 0) ? tb : (tb == 2 ? 0 : tb + 1);
         const int tcol = 4 * tb;
         T acc[4][4];
+        if (QDIAG) {
+            const Vec4<T> qd = ldv4(Qk + tcol);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const Vec4<T> q4 = ldv4(Qk + (4 * sblk + i) * 12 + tcol);
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[i][c] = q4.v[c];
+                for (int c = 0; c < 4; ++c) acc[i][c] = (sblk == tb && i == c) ? qd.v[c] : T(0);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const Vec4<T> q4 = ldv4(Qk + (4 * sblk + i) * 12 + tcol);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = q4.v[c];
+            }
         }
 #pragma unroll
         for (int kk = 0; kk < 12; ++kk) {
@@ -144,7 +160,7 @@ __device__ __forceinline__ void riccati_quad_step(T* Vs, const T* As, const T* B
     __syncwarp();
 }
 
-template <typename T>
+template <typename T, bool QDIAG>
 __global__ void __launch_bounds__(128) k_riccati_quad(LqrQuadP P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PS = sizeof(T) == 4 ? LQ_PS_F32 : LQ_PS_F64;
@@ -165,6 +181,12 @@ __global__ void __launch_bounds__(128) k_riccati_quad(LqrQuadP P) {
         const T* B = P.B.at<T>(b, N - 1);
         for (int e = t; e < 144; e += 4) { Vs[e] = Vf[e]; As[e] = A[e]; }
         for (int e = t; e < 48; e += 4) Bs[e] = B[e];
+        if (QDIAG) {  // time-invariant diagonal costs (lqrMpc.solve): diagonals into the slab
+            const T* Q = P.Q.at<T>(b);
+            const T* R = P.R.at<T>(b);
+            for (int i = t; i < 12; i += 4) S[LQ_QD + i] = Q[i * 13];
+            S[LQ_QD + 12 + t] = R[t * 5];
+        }
     }
     __syncwarp();
     T* Lo = reinterpret_cast<T*>(P.L) + b * (long long)N * 48;
@@ -177,7 +199,8 @@ __global__ void __launch_bounds__(128) k_riccati_quad(LqrQuadP P) {
             __syncwarp();
         }
         T L[4][4];
-        riccati_quad_step<T>(Vs, As, Bs, Ms, Gs, P.Q.at<T>(b, k), P.R.at<T>(b, k), t, L);
+        if (QDIAG) riccati_quad_step<T, true>(Vs, As, Bs, Ms, Gs, S + LQ_QD, S + LQ_QD + 12, t, L);
+        else riccati_quad_step<T, false>(Vs, As, Bs, Ms, Gs, P.Q.at<T>(b, k), P.R.at<T>(b, k), t, L);
         if (active && t < 3) {  // gains -> global
             T* g = Lo + (long long)k * 48 + 4 * t;
 #pragma unroll
@@ -196,7 +219,7 @@ __global__ void __launch_bounds__(128) k_riccati_quad(LqrQuadP P) {
 // N-step Riccati sweep from Qf keeping only L_0, applies u_t = -L_0 x_t and steps the nonlinear plant.  Only the simulated
 // trajectory goes to HBM.  The state is replicated in the four threads of the quad (every thread steps the plant with the
 // same inputs, hence the same bits).
-template <typename T>
+template <typename T, bool QDIAG>
 __global__ void __launch_bounds__(128) k_mpc_closed_loop_quad64(ClosedLoopQuadP P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PS = sizeof(T) == 4 ? LQ_PS_F32 : LQ_PS_F64;
@@ -228,6 +251,10 @@ __global__ void __launch_bounds__(128) k_mpc_closed_loop_quad64(ClosedLoopQuadP 
         for (int e = t; e < 48; e += 4) Bs[e] = T(0);
         __syncwarp();
         if (t == 0) { Bs[2 * 4 + 0] = -dt; Bs[3 * 4 + 1] = dt; Bs[4 * 4 + 2] = dt; Bs[5 * 4 + 3] = dt; }
+        if (QDIAG) {
+            for (int i = t; i < 12; i += 4) S[LQ_QD + i] = Q[i * 13];
+            S[LQ_QD + 12 + t] = R[t * 5];
+        }
     }
     T* xS = reinterpret_cast<T*>(P.xSim) + b * (long long)(P.Tsim + 1) * 12;
     T* uS = reinterpret_cast<T*>(P.uSim) + b * (long long)P.Tsim * 4;
@@ -255,7 +282,10 @@ __global__ void __launch_bounds__(128) k_mpc_closed_loop_quad64(ClosedLoopQuadP 
         __syncwarp();
         // ---- full Riccati sweep; only the first gain is used (nothing cached across simulation steps) ----
         T L[4][4];
-        for (int k = P.N - 1; k >= 0; --k) riccati_quad_step<T>(Vs, As, Bs, Ms, Gs, Q, R, t, L);
+        for (int k = P.N - 1; k >= 0; --k) {
+            if (QDIAG) riccati_quad_step<T, true>(Vs, As, Bs, Ms, Gs, S + LQ_QD, S + LQ_QD + 12, t, L);
+            else riccati_quad_step<T, false>(Vs, As, Bs, Ms, Gs, Q, R, t, L);
+        }
         // ---- u_t = -L_0 x_t: partial products of the three A tiles, summed in a fixed order ----
         T part[4];
 #pragma unroll
@@ -371,8 +401,13 @@ int32_t riccati_quad_launch(int32_t dtype, const LqrQuadP& P, cudaStream_t strea
     const int warps = 2;  // 16 problems per CTA, so four CTAs share an SM's shared memory
     const size_t smem = (size_t)warps * 8 * LQ_PS_F64 * sizeof(double);
     const unsigned grid = (unsigned)((P.Bsz + warps * 8 - 1) / (warps * 8));
-    ZB_CUDA(cudaFuncSetAttribute(k_riccati_quad<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_riccati_quad<double><<<grid, warps * 32, smem, stream>>>(P);
+    if (P.cost_diagonal && P.Q.st == 0 && P.R.st == 0) {
+        ZB_CUDA(cudaFuncSetAttribute(k_riccati_quad<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_riccati_quad<double, true><<<grid, warps * 32, smem, stream>>>(P);
+    } else {
+        ZB_CUDA(cudaFuncSetAttribute(k_riccati_quad<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_riccati_quad<double, false><<<grid, warps * 32, smem, stream>>>(P);
+    }
     ZB_CUDA(cudaGetLastError());
     if (P.x0) {  // lqrMpc.solve: plan rollout against the gains just written
         const unsigned g2 = (unsigned)((P.Bsz * 4 + 127) / 128);
@@ -386,8 +421,13 @@ int32_t mpc_closed_loop_quad64_launch(const ClosedLoopQuadP& P, cudaStream_t str
     const int warps = 2;
     const size_t smem = (size_t)warps * 8 * LQ_PS_F64 * sizeof(double);
     const unsigned grid = (unsigned)((P.Bsz + warps * 8 - 1) / (warps * 8));
-    ZB_CUDA(cudaFuncSetAttribute(k_mpc_closed_loop_quad64<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_mpc_closed_loop_quad64<double><<<grid, warps * 32, smem, stream>>>(P);
+    if (P.cost_diagonal) {
+        ZB_CUDA(cudaFuncSetAttribute(k_mpc_closed_loop_quad64<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_mpc_closed_loop_quad64<double, true><<<grid, warps * 32, smem, stream>>>(P);
+    } else {
+        ZB_CUDA(cudaFuncSetAttribute(k_mpc_closed_loop_quad64<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_mpc_closed_loop_quad64<double, false><<<grid, warps * 32, smem, stream>>>(P);
+    }
     ZB_CUDA(cudaGetLastError());
     return 0;
 }

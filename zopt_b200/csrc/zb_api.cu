@@ -586,6 +586,7 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
         F.A.st = F.B.st = F.Q.st = F.R.st = 0;
         F.L = workspace; F.x0 = x0; F.u0 = u0_out; F.xTraj = xTraj; F.uTraj = uTraj;
         F.status = status_out; F.iters = iters_out;
+        F.cost_diagonal = (flags & ZB_COST_DIAGONAL) ? 1 : 0;
         return riccati_quad_launch(dtype, F, (cudaStream_t)stream);
     }
     ZB_DISPATCH(dtype, k_mpc_riccati, gen_grid(Bsz), GEN_THREADS, stream, P);
@@ -777,6 +778,7 @@ int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int
         for (int i = 0; i < 4; ++i) P64.utrim[i] = u_trim[i];
         P64.Q = to_arr(Q); P64.R = to_arr(R); P64.Qf = to_arr(Qf);
         P64.x0 = x0; P64.xSim = xSim_out; P64.uSim = uSim_out;
+        P64.cost_diagonal = (flags & ZB_COST_DIAGONAL) ? 1 : 0;
         return mpc_closed_loop_quad64_launch(P64, (cudaStream_t)stream);
     }
     t1::ClosedLoopP P{};
