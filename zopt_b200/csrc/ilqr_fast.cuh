@@ -45,11 +45,20 @@ constexpr int ID_VX = 384, ID_XK = 400, ID_QU = 416;
 constexpr int ID_XK2 = 420;
 constexpr int ID_PS_F32 = 436;  // 436/4 = 109 odd
 constexpr int ID_PS_F64 = 438;  // 438*8/16 = 219 odd
-// DDP (diagonal-cost variant only): + 81 words eigenvector exchange + 81 words clamped block  (+ pad); no second (x_k, u_k)
-// buffer (it would cost the fp64 kernel its third CTA per SM): the trajectory rows are prefetched through registers
+// DDP (diagonal-cost variant only): + 81 words eigenvector exchange + 81 words clamped block (+ pad); no second (x_k, u_k)
+// buffer: the trajectory rows are prefetched through registers.
 constexpr int ID_WS = 420, ID_PC = 504;   // 84-word regions (81 used)
 constexpr int IDD_PS_F32 = 588;  // 588/4 = 147 odd
-constexpr int IDD_PS_F64 = 590;  // 590/2 = 295 odd
+// fp64 DDP ("PACK"): the slab is packed so that FOUR 16-problem CTAs fit an SM instead of three (the eigen-clamp is bound by
+// the latency of its rotation chain, so warps per SM is what counts): the eigenvector exchange lives in the f_x region,
+// which is dead during the eigen-solve (f_x is written after it), the clamped block is a packed lower triangle (45 words),
+// (x_k, u_k) share the G region (read in steps 0-1, G is written in step 3), Q_u moves into the pad of v_x.
+// (In fp32 the kernel is register-limited to two 4-warp CTAs either way, and the packed variant measured 5 % slower.)
+constexpr int IDD_XK = ID_G;     // (x_k | u_k), 16 words
+constexpr int IDD_QU = 396;      // Q_u 4
+constexpr int IDD_PC = 400;      // packed lower triangle of the clamped 9x9 block (45 words); its first 16 words carry the
+                                 // rotations of a Jacobi round while the block is not yet rewritten
+constexpr int IDD_PS_F64 = 446;  // 446/2 = 223 odd
 
 // Structure of the quadcopter's dF/dx as generated in quad_model_gen.cuh::quad_jac_x: '0' structurally zero, '1' state-
 // independent constant, '2' depends on (x, u).  tests/test_abi_and_host_logic.py checks this table against the generated
@@ -274,7 +283,8 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     T *Vs = S + (CDIAG ? ID_V : IQ_V), *As = S + (CDIAG ? ID_A : IQ_A), *Bs = S + IQ_B, *Cxx = S + (CDIAG ? ID_CXX : IQ_CXX);
     T *Qs = S + (CDIAG ? ID_QS : IQ_QS), *Ms = S + (CDIAG ? ID_M : IQ_M), *Cux = S + IQ_CUX, *Gs = S + (CDIAG ? ID_G : IQ_G);
     T *Cuu = S + (CDIAG ? ID_CUU : IQ_CUU), *Rs = S + (CDIAG ? ID_RS : IQ_RS), *vx = S + (CDIAG ? ID_VX : IQ_VX);
-    T *xk0 = S + (CDIAG ? ID_XK : IQ_XK), *Qu = S + (CDIAG ? ID_QU : IQ_QU);  // Bs, Cux unused when CDIAG
+    constexpr bool PACK = DDP && sizeof(T) == 8;  // packed DDP slab (see IDD_*)
+    T *xk0 = S + (PACK ? IDD_XK : CDIAG ? ID_XK : IQ_XK), *Qu = S + (PACK ? IDD_QU : CDIAG ? ID_QU : IQ_QU);  // Bs, Cux unused when CDIAG
     constexpr bool STAGE = !DDP;  // (x_k, u_k) through a two-slot cp.async buffer; the DDP slab has no room for the second slot
     constexpr int XK2 = CDIAG ? (ID_XK2 - ID_XK) : (IQ_XK2 - IQ_XK);
     const int N = P.N;
@@ -386,13 +396,15 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                 tr.sec = T(1) / tr.cth;
                 tr.tth = tr.sth * tr.sec;
             }
-            quad_jac_x(tr, x, u, J);
-            store_fx<T, false>(As, J, dt, t);
+            if (!PACK) {
+                quad_jac_x(tr, x, u, J);
+                store_fx<T, false>(As, J, dt, t);
+            }
             if (DDP) {
                 // conditionQuadraticDynamics (ilqrUtils.py:237-251): H = dt * sum_i v_x[i] d2F_i/dx2 touches states 0..8 only,
                 // f_ux = f_uu = 0, so clampPD(blockdiag(H9, 0)) = blockdiag(clampPD(H9), eps I) exactly.
-                T* Wsm = S + ID_WS;
-                T* Pc = S + ID_PC;
+                T* Wsm = PACK ? As : S + ID_WS;  // PACK: the f_x region is dead until the eigen-solve is over
+                T* Pc = S + (PACK ? IDD_PC : ID_PC);
                 T lam[12];
 #pragma unroll
                 for (int i = 0; i < 12; ++i) lam[i] = vx[i];
@@ -446,15 +458,25 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                         T wl[9];
 #pragma unroll
                         for (int k2 = 0; k2 < 9; ++k2) wl[k2] = Wr[r][k2] * lamc[k2];
-                        for (int j = 0; j < 9; ++j) {
+                        for (int j = 0; j <= row; ++j) {  // lower triangle only (the block is symmetric)
                             T acc9 = T(0);
 #pragma unroll
                             for (int k2 = 0; k2 < 9; ++k2) acc9 = fma(wl[k2], Wsm[j * 9 + k2], acc9);
-                            Pc[row * 9 + j] = acc9;
+                            Pc[PACK ? row * (row + 1) / 2 + j : row * 9 + j] = acc9;
                         }
                     }
                 }
-                // visibility of Pc for step 5 is ensured by the __syncwarp() calls that follow
+                if (PACK) {
+                    __syncwarp();  // every thread is done reading the eigenvectors: the f_x region can be rewritten
+                    // f_x = I + dt dF/dx at (x_k, u_k), every chunk (the exchange overwrote the state-independent ones); the state
+                    // is re-read from the slab rather than kept in registers across the eigen-solve
+                    const Vec4<T> x0 = ldv4(xk), x1 = ldv4(xk + 4), x2 = ldv4(xk + 8), u0 = ldv4(xk + 12);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { x[i] = x0.v[i]; x[4 + i] = x1.v[i]; x[8 + i] = x2.v[i]; u[i] = u0.v[i]; }
+                    quad_jac_x(tr, x, u, J);
+                    store_fx<T, true>(As, J, dt, t);
+                }
+                // visibility of Pc and f_x for the steps below is ensured by the __syncwarp() that follows
             }
         }
         __syncwarp();
@@ -531,6 +553,7 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
             }
         }
         // ---- 3. Q_uu = c_uu + G0 (thread 3), Q_ux tile = c_ux tile + M (threads 0..2); share through smem
+        if (PACK) __syncwarp();  // (x_k, u_k) share the G region: every thread of the quad has read them (steps 0-1)
         if (t == 3) {
 #pragma unroll
             const Vec4<T> cd = ldv4(Cuu);  // CDIAG: the diagonal of c_uu
@@ -619,7 +642,7 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                             const int gj = tcol + c;
                             const int hi_ = gi > gj ? gi : gj, lo_ = gi > gj ? gj : gi;
                             T add = T(0);
-                            if (hi_ < 9) add = (S + ID_PC)[hi_ * 9 + lo_];
+                            if (hi_ < 9) add = PACK ? (S + IDD_PC)[hi_ * (hi_ + 1) / 2 + lo_] : (S + ID_PC)[hi_ * 9 + lo_];
                             else if (gi == gj) add = T(P.eps);
                             acc[i][c] += add;
                         }
@@ -675,7 +698,10 @@ inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
                            : CDIAG ? (sizeof(T) == 4 ? ID_PS_F32 : ID_PS_F64) : (sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64);
     // problems per CTA: fp32 32 (4 warps); fp64 16 (2 warps) so several CTAs share an SM's shared memory
     const int warps = (sizeof(T) == 4) ? 4 : 2;
-    const size_t smem = (size_t)warps * 8 * PS * sizeof(T);
+    size_t smem = (size_t)warps * 8 * PS * sizeof(T);
+    // fp32 DDP: two 4-warp CTAs per SM run faster than three (measured 65 vs 79 ms on cfg 5: the ~1,100-instruction Jacobi loop
+    // of three CTAs in different phases thrashes the instruction cache), so the request is padded past a third of the SM
+    if (DDP && sizeof(T) == 4 && smem < 80 * 1024) smem = 80 * 1024;
     const unsigned grid = (unsigned)((P.Bsz + warps * 8 - 1) / (warps * 8));
     ZB_CUDA(cudaFuncSetAttribute(k_ilqr_backward_quad<T, CDIAG, DDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_ilqr_backward_quad<T, CDIAG, DDP><<<grid, warps * 32, smem, stream>>>(P);
