@@ -482,6 +482,36 @@ def test_fused_forward_equals_two_kernel_forward(second_order, dt):
     assert 0 < frozen < Bsz, "test problem never exercises the frozen-problem path"
 
 
+@pytest.mark.parametrize("N", [1, 2, 3, 5])
+@pytest.mark.parametrize("second_order", [False, True])
+def test_quadcopter_fast_kernels_short_horizons(N, second_order):
+    """Horizons shorter than the line search's 4-stage operand ring and the backward pass's two-slot staging (N = 1, 2, 3):
+    fused == two-kernel line search bit for bit, and both match the oracle at 1e-10."""
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    Bsz, iters = 9, 2
+    x0, uG, Q, R, Qf = _quad_problem(N, Bsz, 5 + N, 0.2 if second_order else 1.0, 3.0)
+    solver = ilqrUtils.differentialDynamicProgramming if second_order else ilqrUtils.iterativeLqr
+    args = (QuadcopterEuler(0.1), QuadraticCost(Q, R), QuadraticTerminalCost(Qf), cuda(x0), uG)
+    a = solver(*args, maxIter=iters, tol=-1.0, return_log=True)
+    ilqrUtils._GENERIC_FORWARD = True
+    try:
+        b = solver(*args, maxIter=iters, tol=-1.0, return_log=True)
+    finally:
+        ilqrUtils._GENERIC_FORWARD = False
+    assert torch.equal(a[4]["alpha_idx"], b[4]["alpha_idx"]) and torch.equal(a[0].xTraj, b[0].xTraj) and torch.equal(a[1], b[1])
+    dyn, rc, tc = _oracle_fns(Q, R, Qf)
+    osolver = oilqr.differentialDynamicProgramming if second_order else oilqr.iterativeLqr
+    # one iteration against the oracle (a second iteration of so short a problem starts at the optimum, where the costs of
+    # the 16 step sizes tie to rounding and the argmin is not a meaningful comparison)
+    c = solver(*args, maxIter=1, tol=-1.0, return_log=True)
+    for i in range(2):
+        olog = []
+        tr, Lr, Jr, _ = osolver(dyn, rc, tc, torch.as_tensor(x0[i]), torch.as_tensor(uG), maxIter=1, tol=-1.0, log=olog)
+        assert [e["alpha_idx"] for e in olog[1:]] == c[4]["alpha_idx"][i].tolist()
+        assert relerr(c[0].xTraj[i], tr.xTraj) < 1e-10 and relerr(c[1][i], Lr) < 1e-10
+
+
 def test_solver_fp32_and_convergence_flags():
     """fp32 run against the fp64 oracle: step-size sequences compared first, mismatches counted (never dropped);
     matching problems gated at x,u 2e-5 and L 1e-4.  Also per-problem convergence freeze."""
