@@ -28,6 +28,11 @@ ZB_API int32_t zb_user_last_error(char* buf, size_t len);
 ZB_API int32_t zb_user_step(int32_t dtype, int32_t device, void* stream, int64_t Bsz, const void* x, const void* u, void* xn,
                             void* fx, void* fu);
 
+/* Z (Bsz,n+m,n+m) = sum_i lam_i d2 f_i / dz2 at (x, u), z = [x; u]: the costate contraction of QuadraticDynamics' f_xx, f_ux,
+ * f_uu (pytrees.py:179-194; with lam = e_i it returns the slices themselves).  x (Bsz,n), u (Bsz,m), lam (Bsz,n). */
+ZB_API int32_t zb_user_hess(int32_t dtype, int32_t device, void* stream, int64_t Bsz, const void* x, const void* u, const void* lam,
+                            void* Z);
+
 /* zopt/ilqrUtils.py:33-66 trajectoryRollout with the user model (arguments as zb_ilqr_rollout) */
 ZB_API int32_t zb_user_rollout(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, const zb_cost* cost,
                                const void* x0, const void* l, const void* L, const void* xPrev, const void* uPrev, double alpha,

@@ -58,7 +58,31 @@ __global__ void k_user_step(long long Bsz, const void* x, const void* u, void* x
     }
 }
 
+// Z (Bsz,p,p), p = n+m: sum_i lam_i d2 f_i / dz2 at (x, u), z = [x; u]  (the contraction of QuadraticDynamics' f_xx, f_ux, f_uu)
+template <typename T>
+__global__ void k_user_hess(long long Bsz, const void* x, const void* u, const void* lam, void* Z) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= Bsz) return;
+    constexpr int n = ZB_USER_N, m = ZB_USER_M, p = n + m;
+    T xl[NX], ul[NU], ll[NX], H[(NX + NU) * (NX + NU)];
+    for (int i = 0; i < n; ++i) { xl[i] = reinterpret_cast<const T*>(x)[b * n + i]; ll[i] = reinterpret_cast<const T*>(lam)[b * n + i]; }
+    for (int i = 0; i < m; ++i) ul[i] = reinterpret_cast<const T*>(u)[b * m + i];
+    user_hess<T>(xl, ul, ll, H);
+    for (int i = 0; i < p * p; ++i) reinterpret_cast<T*>(Z)[b * p * p + i] = H[i];
+}
+
 extern "C" {
+
+__attribute__((visibility("default"))) int32_t zb_user_hess(int32_t dtype, int32_t device, void* stream, int64_t Bsz, const void* x,
+                                                            const void* u, const void* lam, void* Z) {
+    ZB_ARG(dtype == ZB_F32 || dtype == ZB_F64, "bad dtype %d", dtype);
+    ZB_ARG(Bsz >= 0 && (Bsz == 0 || (x && u && lam && Z)), "bad operand");
+    if (Bsz == 0) return 0;
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    ZB_DISPATCH(dtype, k_user_hess, gen_grid(Bsz), GEN_THREADS, stream, (long long)Bsz, x, u, lam, Z);
+    return 0;
+}
 
 __attribute__((visibility("default"))) int32_t zb_user_dims(int32_t* n, int32_t* m) {
     *n = ZB_USER_N;

@@ -145,7 +145,12 @@ def expand_dynamics(dynFun, x, u, second_order):
     xf, lead = _flat(x, n)
     uf, _ = _flat(u, m)
     P = xf.shape[0]
-    if isinstance(model, QuadcopterEuler):
+    if getattr(model, "is_plugin", False):  # user-defined symbolic model: the generated CUDA code (plugin.py)
+        xf, uf = xf.contiguous(), uf.contiguous()
+        f, f_x, f_u = model.step(xf, uf, linearize=True)
+        if second_order:
+            f_xx, f_ux, f_uu = model.second_order(xf, uf)
+    elif isinstance(model, QuadcopterEuler):
         from .quadcopter import quad_linearize, quad_xdot, quad_hess_contract
         f = xf + model.dt * quad_xdot(xf, uf, model.wind)
         f_x, f_u = quad_linearize(xf, uf, model.wind, model.dt)

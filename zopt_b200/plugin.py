@@ -169,9 +169,10 @@ class SymbolicDynamics:
         L = C.CDLL(so)
         L.zb_user_ilqr_workspace_bytes.restype = C.c_size_t
         L.zb_user_ilqr_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32]
-        for name in ("zb_user_dims", "zb_user_last_error", "zb_user_step", "zb_user_rollout", "zb_user_ilqr_solve"):
+        for name in ("zb_user_dims", "zb_user_last_error", "zb_user_step", "zb_user_hess", "zb_user_rollout", "zb_user_ilqr_solve"):
             getattr(L, name).restype = C.c_int32
         L.zb_user_step.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64] + [C.c_void_p] * 5
+        L.zb_user_hess.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64] + [C.c_void_p] * 4
         L.zb_user_rollout.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(ZbCost)] + [C.c_void_p] * 5 + \
             [C.c_double] + [C.c_void_p] * 3
         L.zb_user_ilqr_solve.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(ZbCost),
@@ -215,6 +216,20 @@ class SymbolicDynamics:
         if not batched:
             xn, fx, fu = xn[0], (fx[0] if linearize else None), (fu[0] if linearize else None)
         return (xn, fx, fu) if linearize else xn
+
+    def second_order(self, x, u):
+        """f_xx (P,n,n,n), f_ux (P,n,m,n), f_uu (P,n,m,m) at P points (QuadraticDynamics, pytrees.py:179-194): the generated
+        contracted Hessian evaluated with lam = e_i."""
+        self._need()
+        n, m, p = self.n, self.m, self.n + self.m
+        P = x.shape[0]
+        eye = torch.eye(n, dtype=x.dtype, device=x.device)
+        Z = torch.empty((n, P, p, p), dtype=x.dtype, device=x.device)
+        for i in range(n):
+            lam = eye[i].expand(P, n).contiguous()
+            self._check(self._lib.zb_user_hess(dcode(x.dtype), x.device.index, stream_ptr(x.device), P, ptr(x), ptr(u), ptr(lam), ptr(Z[i])))
+        Z = Z.permute(1, 0, 2, 3)
+        return Z[:, :, :n, :n].contiguous(), Z[:, :, n:, :n].contiguous(), Z[:, :, n:, n:].contiguous()
 
     def solve(self, cspec, dtype, device, Bsz, N, x0, uGuess, maxIter, tol, second_order, return_log):
         """iterativeLqr / differentialDynamicProgramming for this model (called by zopt_b200.ilqrUtils._solve)."""
