@@ -1,6 +1,7 @@
-// Cooperative (n,m) = (12,4) Riccati recursion in fp64 (and fp32 for operand patterns the thread-per-problem fp32 kernels
-// do not cover): discreteFiniteHorizonLqr (zopt/lqrUtils.py:144-173) and the unconstrained lqrMpc.solve
-// (zopt/mpcUtils.py:47-81) -- the reference itself computes in fp64.
+// Cooperative (n,m) = (12,4) Riccati recursion in fp64 -- the reference itself computes in fp64; fp32 has the thread-per-
+// problem kernels of lqr_t1.cuh (the templates below are written over T, only <double> is instantiated):
+// discreteFiniteHorizonLqr (zopt/lqrUtils.py:144-173), the unconstrained lqrMpc.solve (zopt/mpcUtils.py:47-81) and the
+// closed-loop LQR-MPC of BASELINE cfg 3 (demos/lqrMpc.py:42-47 on the nonlinear, re-linearised quadcopter).
 //
 // Same mapping as the iLQR backward kernel (ilqr_fast.cuh): FOUR threads per problem, [A | B] split into four 12x4 column
 // tiles, V / A / B in a per-problem shared-memory slab read with 128-bit broadcast loads (an fp64 value matrix does not
