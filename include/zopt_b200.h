@@ -141,8 +141,9 @@ ZB_API int32_t zb_pd_clamp(int32_t dtype, int32_t device, void* stream, int64_t 
  * J_out (Bsz), converged_out (Bsz) uint8, iters_out (Bsz) int32,
  * alpha_log (Bsz,maxIter) int32 optional (-1 = iteration not run), J_log (Bsz,maxIter+1) optional.
  * flags: ZB_SECOND_ORDER = DDP (ilqrUtils.py:330-397) instead of iLQR; ZB_COST_DIAGONAL = the caller asserts Q, R, Qf diagonal
- * (the quadcopter backward kernel then keeps twice as many problems per SM, and the 16-way line search + commit of a
- * quadcopter solve runs as ONE fused launch, csrc/ilqr_forward.cuh; ZB_GENERIC_FORWARD forces the two-kernel path).
+ * (the quadcopter backward kernel then keeps twice as many problems per SM and the per-solve setup is closed-form).  The 16-way
+ * line search + commit of a quadcopter solve runs as ONE fused launch (csrc/ilqr_forward.cuh); ZB_GENERIC_FORWARD forces the
+ * two-kernel path.
  * workspace: device scratch of zb_ilqr_workspace_bytes(...) bytes. */
 ZB_API size_t zb_ilqr_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m);
 ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t flags,

@@ -445,7 +445,7 @@ def test_solvers_quadcopter_vs_oracle_fp64(second_order, R_scale, spread, dense_
 
 
 @pytest.mark.parametrize("second_order", [False, True])
-@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32, "f64-dense-cost"])
 def test_fused_forward_equals_two_kernel_forward(second_order, dt):
     """The fused line-search kernel (csrc/ilqr_forward.cuh: cp.async-staged operands, in-warp argmin, copy / re-run commit)
     performs the arithmetic of k_forward_costs + k_forward_commit in the same order: identical step sizes and bit-identical
@@ -455,6 +455,12 @@ def test_fused_forward_equals_two_kernel_forward(second_order, dt):
     from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
     N, Bsz, iters = 37, 27, 4
     x0, uG, Q, R, Qf = _quad_problem(N, Bsz, 77 + int(second_order), 0.2 if second_order else 1.0, 25.0)
+    if dt == "f64-dense-cost":  # non-diagonal SPD costs: the fused kernel evaluates the dense quadratic forms as the generic one does
+        dt = torch.float64
+        rng = np.random.default_rng(99)
+        Mq, Mr = rng.normal(size=(12, 12)) * 0.2, rng.normal(size=(4, 4)) * 0.2
+        Q, R = Q + Mq @ Mq.T, R + Mr @ Mr.T
+        Qf = 10 * Q
     uG = uG + np.random.default_rng(5).normal(size=uG.shape) * 2.0  # a poor guess: small step sizes win in early iterations
     solver = ilqrUtils.differentialDynamicProgramming if second_order else ilqrUtils.iterativeLqr
     args = (QuadcopterEuler(0.1), QuadraticCost(Q, R), QuadraticTerminalCost(Qf), cuda(x0, dt), cuda(uG, dt))

@@ -43,7 +43,9 @@ constexpr int FWD_DEPTH = 4;   // ring stages (steps in flight: 3)
 constexpr int FWD_STAGE = 68;  // words per step: L 48 | l 4 | xPrev 12 | uPrev 4
 // resident 64-thread CTAs per SM asked of the compiler: fp64 8 (16 warps, caps the kernel at 128 registers), fp32 12
 
-template <typename T>
+// QDIAG: the caller asserted diagonal Q, R (weights in registers); otherwise the dense quadratic forms are evaluated row by
+// row from global memory, exactly as the generic rollout does.
+template <typename T, bool QDIAG>
 __global__ void __launch_bounds__(64, sizeof(T) == 8 ? 8 : 12) k_forward_quad(FwdQuadP P) {
     constexpr int n = 12, m = 4, D = FWD_DEPTH, ST = FWD_STAGE;
     constexpr int EPC = 16 / (int)sizeof(T);  // words per 16-byte chunk
@@ -93,15 +95,15 @@ __global__ void __launch_bounds__(64, sizeof(T) == 8 ? 8 : 12) k_forward_quad(Fw
             if (cval[r]) fwd_cp16(dst + coff[r], csrc[r] + (long long)k * cstr[r]);
     };
 
-    // diagonal running-cost weights (the caller asserted ZB_COST_DIAGONAL)
+    // running-cost weights: diagonals in registers (the caller asserted ZB_COST_DIAGONAL), else dense blocks through L1
     T qd[n], rd[m];
-    {
-        const T* Q = P.C.Q.at<T>(b);
-        const T* R = P.C.R.at<T>(b);
+    const T* Qg = P.C.Q.at<T>(b);
+    const T* Rg = P.C.R.at<T>(b);
+    if (QDIAG) {
 #pragma unroll
-        for (int i = 0; i < n; ++i) qd[i] = Q[i * 13];
+        for (int i = 0; i < n; ++i) qd[i] = Qg[i * 13];
 #pragma unroll
-        for (int i = 0; i < m; ++i) rd[i] = R[i * 5];
+        for (int i = 0; i < m; ++i) rd[i] = Rg[i * 5];
     }
     T alpha = T(1);
     for (int i = 0; i < j; ++i) alpha *= T(0.5);  // 0.5**j exactly (ilqrUtils.py:145)
@@ -160,13 +162,15 @@ __global__ void __launch_bounds__(64, sizeof(T) == 8 ? 8 : 12) k_forward_quad(Fw
                 st4(wx + (long long)k * n + 8, x + 8);
                 st4(wu + (long long)k * m, u);
             }
-            {
+            if (QDIAG) {
                 T a = T(0), c = T(0);
 #pragma unroll
                 for (int i = 0; i < n; ++i) a += x[i] * (qd[i] * x[i]);
 #pragma unroll
                 for (int i = 0; i < m; ++i) c += u[i] * (rd[i] * u[i]);
                 J += a + c;
+            } else {
+                J += quad_form<T>(Qg, x, n) + quad_form<T>(Rg, u, m);
             }
             QuadTrig<T> tr = quad_trig(x);
             quad_xdot(tr, x, u, xd);
@@ -325,8 +329,13 @@ int32_t solve_setup_quad_launch(int32_t dtype, const SetupQuadP& P, cudaStream_t
 
 int32_t fwd_quad_launch(int32_t dtype, const FwdQuadP& P, cudaStream_t stream) {
     const unsigned grid = (unsigned)((P.Bsz + 3) / 4);
-    if (dtype == ZB_F32) k_forward_quad<float><<<grid, 64, 0, stream>>>(P);
-    else k_forward_quad<double><<<grid, 64, 0, stream>>>(P);
+    if (P.cost_diagonal) {
+        if (dtype == ZB_F32) k_forward_quad<float, true><<<grid, 64, 0, stream>>>(P);
+        else k_forward_quad<double, true><<<grid, 64, 0, stream>>>(P);
+    } else {
+        if (dtype == ZB_F32) k_forward_quad<float, false><<<grid, 64, 0, stream>>>(P);
+        else k_forward_quad<double, false><<<grid, 64, 0, stream>>>(P);
+    }
     ZB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -41,6 +41,7 @@ struct FwdQuadP {
     void* spec;           // (2, Bsz, (N+1)*12 + N*4): speculative rollouts of alpha = 1, 1/2
     void* Jall;           // (Bsz,16) or null
     CommitP S;
+    int cost_diagonal;    // the caller asserted diagonal Q, R (ZB_COST_DIAGONAL)
 };
 
 // once per solve: conditioned cost blocks of a DIAGONAL quadratic cost + the initial rollout u_k = uGuess_k
@@ -88,9 +89,7 @@ struct ClosedLoopQuadP {
 inline bool ilqr_fast_eligible(const Model& M, int second_order, bool cost_diagonal) {
     return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && (!second_order || cost_diagonal);
 }
-inline bool fwd_quad_eligible(const Model& M, bool cost_diagonal) {
-    return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind && cost_diagonal;
-}
+inline bool fwd_quad_eligible(const Model& M) { return M.kind == ZB_MODEL_QUADCOPTER && !M.has_wind; }
 // backward pass (ilqr_fast.cuh) and fused line search (ilqr_forward.cuh); defined in zb_ilqr_kernels.cu
 int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream, bool cost_diagonal, bool second_order);
 int32_t fwd_quad_launch(int32_t dtype, const FwdQuadP& P, cudaStream_t stream);

@@ -489,8 +489,8 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     ZB_CUDA(cudaMemsetAsync(L_out, 0, e * Bsz * N * m * n, s));
     P.x0 = x0; P.l = l_ws; P.L = L_out; P.xPrev = xTraj; P.uPrev = uTraj;
     P.xTraj = xTraj; P.uTraj = uTraj; P.J = nullptr;
-    const bool fast_fwd = N >= 1 && !(flags & ZB_GENERIC_FORWARD) && fwd_quad_eligible(P.M, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out) && aligned16(x0);
-    if (fast_fwd && aligned16(uGuess)) {  // diagonal costs + quadcopter: closed-form conditioning and a register-resident initial rollout
+    const bool fast_fwd = N >= 1 && !(flags & ZB_GENERIC_FORWARD) && fwd_quad_eligible(P.M) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out) && aligned16(x0);
+    if (fast_fwd && cost_diagonal && aligned16(uGuess)) {  // diagonal costs + quadcopter: closed-form conditioning and a register-resident initial rollout
         SetupQuadP Sp{Bsz, N, (int)maxIter, P.M.dt, 1e-3, P.C, x0, uGuess, xTraj, uTraj, J_out, converged_out, iters_out, alpha_log, J_log, Czz, Vfxx};
         rc = solve_setup_quad_launch(dtype, Sp, s);
         if (rc) return rc;
@@ -510,7 +510,7 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
             ZB_DISPATCH(dtype, k_solve_backward, gen_grid(Bsz), GEN_THREADS, stream, Bk);
         CommitP S{J_out, converged_out, iters_out, alpha_log, J_log, it, (int)maxIter, tol, nullptr, nullptr};
         if (fast_fwd) {  // line search + commit + bookkeeping in one launch (ilqr_forward.cuh)
-            FwdQuadP Fw{Bsz, N, P.M.dt, P.C, x0, l_ws, L_out, xTraj, uTraj, spec, nullptr, S};
+            FwdQuadP Fw{Bsz, N, P.M.dt, P.C, x0, l_ws, L_out, xTraj, uTraj, spec, nullptr, S, cost_diagonal ? 1 : 0};
             rc = fwd_quad_launch(dtype, Fw, s);
             if (rc) return rc;
             continue;
