@@ -399,21 +399,32 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
 // into its column of the lane-interleaved slab: consecutive lanes write consecutive 16 B (conflict-free without padding,
 // so the slab is 112 x 32 float4 = 56 KB and FOUR one-warp CTAs fit an SM), source and destination offsets are
 // instruction immediates (2 instructions per copy), and a lane's reads walk its problem's contiguous blocks, so every
-// fetched 32-byte sector is used in full.  The blocks of step k-1 are prefetched into L2 while step k computes, and their
-// copies are issued as soon as the lane's own step is done (the slots are private), overlapping the gain stores.
+// fetched 32-byte sector is used in full.  The copies of step k-1 are issued as soon as the lane's own step k is done (the
+// slots are private), overlapping the gain stores.  (An L2 prefetch of the next step's blocks and cp.async.ca were both
+// measured slower -- the kernel is bound by the load/store unit -- and are compiled out: ZB_TV_L2_PREFETCH, ZB_TV_CP_CA.)
 // History (ncu: profiles/r1s3_lqr_tv_*), 65,536 solves x N=50: v1 issued coalesced copies with a per-copy transposing
 // (problem, chunk) index into a padded slab (7,300 instructions per step, 3 CTAs per SM): 2.76 ms; v2 (this one,
-// 4,900 instructions per step, 4 CTAs per SM): 1.88 ms; v3 made the copies coalesced again with a fixed per-lane
+// 4,900 instructions per step, 4 CTAs per SM): 1.88 ms with the L2 prefetch, 1.74 ms without; v3 made the copies coalesced again with a fixed per-lane
 // schedule (four problems x eight consecutive chunks per instruction, 8-way bank conflicts on the shared-memory side):
 // 2.17 ms, 2.32 ms with the L2 prefetch -- slower than the scattered but conflict-free copies, so it was dropped.
 // Bound: the load/store unit (operand copies + the step's own 128-bit shared-memory reads: lg_throttle 21 %,
 // short_scoreboard 30 % of the stall samples), not the FMA pipe and not yet HBM (2.5 TB/s of 6.5).
+#ifndef ZB_TV_CP_CA
+#define ZB_TV_CP_CA 0  // .ca (allocate in L1) measured 2.21 ms against 1.74 ms with .cg
+#endif
+#ifndef ZB_TV_L2_PREFETCH
+#define ZB_TV_L2_PREFETCH 0  // prefetch.global.L2 of the next step's blocks measured 1.87 ms against 1.74 ms without: the kernel is LSU-bound
+#endif
 constexpr int RS_TV = 32;
 constexpr int NF4_TV = 112;  // X 48 + W 36 + Q 24 + R 4 (full rows)
 
 __device__ __forceinline__ void cp_async16(float4* dst_smem, const float4* src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+#if ZB_TV_CP_CA
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
@@ -461,7 +472,9 @@ __global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P) {
     float* gpub = P.gains + b0 * (long long)P.N * 48;
     tv_load_step(S, P, b, P.N - 1);
     for (int k = P.N - 1; k >= 0; --k) {
+#if ZB_TV_L2_PREFETCH
         if (k > 0) tv_prefetch_step(P, b, k - 1);  // HBM -> L2 while this step computes
+#endif
         __syncwarp();  // everybody is done with the staging area (the W region) of the previous step
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");  // each lane reads only what it copied itself
         float L[4][12];
