@@ -84,10 +84,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_configs():
+    """zopt_b200/configs.py (NumPy-only problem generators) loaded BY PATH: importing the package would map
+    libzopt_b200.so into the process, and the reference arm must not touch the product's native code."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_zb_configs", os.path.join(ROOT, "zopt_b200", "configs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_problem(Bsz, rank):
-    from zopt_b200 import configs
-    d = configs.cfg2(Bsz=Bsz, seed=1234 + 2 + 1000 * rank)
-    return d
+    return load_configs().cfg2(Bsz=Bsz, seed=1234 + 2 + 1000 * rank)
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
@@ -213,13 +221,16 @@ def run_ours(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
-    from zopt_b200 import _lib
+    from zopt_b200 import _lib, hostbind
     from zopt_b200.mpcUtils import lqrMpc
     from zopt_b200.quadcopter import Quadcopter
 
+    # pin this rank to the CPUs of its GPU's NUMA node BEFORE any pinned allocation (the end-to-end loop is PCIe/host bound)
+    binding = hostbind.bind_to_gpu(local_rank, enable=os.environ.get("BENCH_NO_BIND", "0") != "1")
+
     Bsz = args.batch
     d = make_problem(Bsz, rank)
-    f32 = torch.float32
+    f32, f64 = torch.float32, torch.float64
     # host (pinned) inputs of one step: the states to solve from
     x0_host = torch.as_tensor(d["xbar"], dtype=f32).pin_memory()
     xbar = torch.as_tensor(d["xbar"], dtype=f32, device=dev)
@@ -232,15 +243,30 @@ def run_ours(args):
     ac = Quadcopter()
     N, dt = d["N"], d["dt"]
 
-    def step(x0_dev):
-        A, B = ac.linearizeInertial(xbar, ubar, dt)
-        prob = lqrMpc(A, B, Q, R, N, ninf_n, inf_n, ninf_m, inf_m, Qf=Qf)
-        return prob.solve(x0_dev)
+    def make_step(xb, ub, Qm, Rm, Qfm):
+        def step(x0_dev):
+            A, B = ac.linearizeInertial(xb, ub, dt)
+            prob = lqrMpc(A, B, Qm, Rm, N, ninf_n, inf_n, ninf_m, inf_m, Qf=Qfm)
+            return prob.solve(x0_dev)
+        return step
+
+    step = make_step(xbar, ubar, Q, R, Qf)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def timed(fn, reps):
+        """barrier + sync, `reps` back-to-back calls between ONE event pair on the launching stream, barrier + sync"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / reps
 
     for _ in range(max(args.warmup, 3)):
         out = step(xbar)
@@ -250,27 +276,23 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = step(xbar)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed(lambda: step(xbar), args.steps) * args.steps
 
-    # --- dominant kernel alone (the Riccati sweep + rollout launch), events on the launching stream
+    # --- dominant kernel alone (the Riccati sweep + rollout launch): back-to-back launches between one event pair,
+    #     no synchronisation in between, so launch latency is hidden behind the previous launch
     A, B = ac.linearizeInertial(xbar, ubar, dt)
     prob = lqrMpc(A, B, Q, R, N, ninf_n, inf_n, ninf_m, inf_m, Qf=Qf)
-    kms = []
-    for _ in range(max(3, min(args.steps, 20))):
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        prob.solve(xbar)
-        k1.record()
-        torch.cuda.synchronize(dev)
-        kms.append(k0.elapsed_time(k1))
-    k_ms = float(np.mean(kms))
+    prob.solve(xbar)
+    k_reps = max(10, min(args.steps, 100))
+    k_ms = timed(lambda: prob.solve(xbar), k_reps)
+    # the same launch WITHOUT the diagonal-cost variant (dense symmetric Q, R, Qf: 27 instead of 4 float4 of cost data on chip)
+    off = 1e-3 * torch.ones((NX, NX), device=dev, dtype=f32)
+    Qd = Q + off * (1 - torch.eye(NX, device=dev))
+    Rd = R + 1e-3 * (1 - torch.eye(NU, device=dev))
+    prob_dense = lqrMpc(A, B, Qd, Rd, N, ninf_n, inf_n, ninf_m, inf_m, Qf=10 * Qd)
+    prob_dense.solve(xbar)
+    kd_ms = timed(lambda: prob_dense.solve(xbar), max(5, k_reps // 2))
+    del prob_dense, Qd, Rd
 
     if os.environ.get("BENCH_SAMPLE_E2E", "0") != "1":
         clocks = sampler.stop() if rank == 0 else None  # sampled every 100 ms over the device-timed loops above
@@ -278,18 +300,17 @@ def run_ours(args):
     # --- end to end through the public API with host buffers -----------------------------------
     # every step: x0 pinned host -> device, linearise + solve, then the call's whole return value (u, plan, status)
     # device -> pinned host.  The D2H of step i runs on a copy stream while step i+1 computes (two host buffer sets).
-    def host_bufs():
-        return [torch.empty((Bsz, NU), dtype=f32).pin_memory(), torch.empty((Bsz, N + 1, NX), dtype=f32).pin_memory(),
-                torch.empty((Bsz, N, NU), dtype=f32).pin_memory(), torch.empty((Bsz,), dtype=torch.int8).pin_memory()]
+    def host_bufs(dtype):
+        return [torch.empty((Bsz, NU), dtype=dtype).pin_memory(), torch.empty((Bsz, N + 1, NX), dtype=dtype).pin_memory(),
+                torch.empty((Bsz, N, NU), dtype=dtype).pin_memory(), torch.empty((Bsz,), dtype=torch.int8).pin_memory()]
 
-    hb = [host_bufs(), host_bufs()]
     copy_stream = torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
 
-    def e2e_loop(steps, full):
+    def e2e_loop(steps, full, stepf, x0h, hb):
         for i in range(steps):
-            x0d = x0_host.to(dev, non_blocking=True)
-            u, traj, status = step(x0d)
+            x0d = x0h.to(dev, non_blocking=True)
+            u, traj, status = stepf(x0d)
             outs = (u, traj.xTraj, traj.uTraj, status) if full else (u, status)
             dst = hb[i % 2] if full else [hb[i % 2][0], hb[i % 2][3]]
             ready = torch.cuda.Event()
@@ -301,26 +322,63 @@ def run_ours(args):
                     h.copy_(t, non_blocking=True)
         copy_stream.synchronize()
 
-    e2e_loop(2, True)
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    e2e_loop(args.steps, True)
-    main.wait_stream(copy_stream)
-    t1.record()
-    barrier()
-    e2e_ms = t0.elapsed_time(t1)
+    def e2e_time(steps, full, stepf, x0h, hb):
+        e2e_loop(2, full, stepf, x0h, hb)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        e2e_loop(steps, full, stepf, x0h, hb)
+        main.wait_stream(copy_stream)
+        t1.record()
+        barrier()
+        return t0.elapsed_time(t1)
+
+    hb = [host_bufs(f32), host_bufs(f32)]
+    e2e_ms = e2e_time(args.steps, True, step, x0_host, hb)
     h2d = x0_host.numel() * 4
     d2h = sum(t.numel() * t.element_size() for t in hb[0])
-    t2, t3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t2.record()
-    e2e_loop(args.steps, False)
-    main.wait_stream(copy_stream)
-    t3.record()
-    barrier()
-    e2e_u_ms = t2.elapsed_time(t3)
+    e2e_u_ms = e2e_time(args.steps, False, step, x0_host, hb)
+
+    # --- copy roof: the step's D2H payload alone, pinned, every rank at the same time (what PCIe + host memory allow) ---
+    def copy_roof(hbufs, reps):
+        srcs = [torch.empty(h.shape, dtype=h.dtype, device=dev) for h in hbufs[0]]
+        for h, s in zip(hbufs[0], srcs):
+            h.copy_(s, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(reps):
+            for h, s in zip(hbufs[i % 2], srcs):
+                h.copy_(s, non_blocking=True)
+        c1.record()
+        barrier()
+        return c0.elapsed_time(c1) / reps
+
+    roof_ms = copy_roof(hb, max(5, min(args.steps, 20)))
+    del hb
+
+    # --- the same end-to-end loop in fp64, the reference's own precision (cooperative fp64 kernels) ------------------
+    e2e64_ms, d2h64, h2d64 = 0.0, 0, 0
+    if not args.no_extras:
+        xb64, ub64, Q64, R64 = xbar.to(f64), ubar.to(f64), Q.to(f64), R.to(f64)
+        step64 = make_step(xb64, ub64, Q64, R64, 10 * Q64)
+        x0_host64 = torch.as_tensor(d["xbar"], dtype=f64).pin_memory()
+        hb64 = [host_bufs(f64), host_bufs(f64)]
+        n64 = max(3, min(args.steps, 20))
+        e2e64_ms = e2e_time(n64, True, step64, x0_host64, hb64) / n64
+        d2h64 = sum(t.numel() * t.element_size() for t in hb64[0])
+        h2d64 = x0_host64.numel() * 8
+        del hb64, x0_host64
     if os.environ.get("BENCH_SAMPLE_E2E", "0") == "1":
         clocks = sampler.stop() if rank == 0 else None
+
+    # --- final gather of the step's costs-sized result over NCCL (the only collective, off the hot path) --
+    gather_ms = 0.0
+    if world > 1:
+        from zopt_b200.sharding import gather
+        u_last, traj_last, _ = out
+        gather(u_last, Bsz * world)
+        gather_ms = timed(lambda: (gather(u_last, Bsz * world), gather(traj_last.xTraj, Bsz * world), gather(traj_last.uTraj, Bsz * world)), 3)
 
     # --- secondary workloads of BASELINE.json (reported under "extra"; the headline stays cfg 2) -------------------
     # cfg 3: closed-loop LQR-MPC, N=50 horizon x 200 sim steps, 16,384 problems in total SHARDED over the ranks (strong)
@@ -329,7 +387,8 @@ def run_ours(args):
     from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
     from zopt_b200.mpcUtils import quadcopterClosedLoopMpc
     from zopt_b200.sharding import shard_range
-    extra_ms = [0.0]
+    X = {}  # name -> ms (max over ranks below)
+    info = {}
     if not args.no_extras:
         lo, hi = shard_range(16384, rank, world)
         d3 = configs.cfg3(Bsz=16384)
@@ -339,15 +398,8 @@ def run_ours(args):
         R3 = torch.diag_embed(torch.as_tensor(d3["rdiag"][lo:hi], dtype=f32, device=dev))
         Qf3 = 10 * Q3
         quadcopterClosedLoopMpc(x3, Q3, R3, 50, 200, dt=0.1, Qf=Qf3)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(3):
-            quadcopterClosedLoopMpc(x3, Q3, R3, 50, 200, dt=0.1, Qf=Qf3)
-        c1.record()
-        barrier()
-        extra_ms[0] = c0.elapsed_time(c1) / 3
-        # the same with 16,384 problems PER GPU (weak scaling): 2,048 problems leave most SMs of a B200 idle
+        X["cl"] = timed(lambda: quadcopterClosedLoopMpc(x3, Q3, R3, 50, 200, dt=0.1, Qf=Qf3), 3)
+        # the same with 16,384 problems PER GPU (weak scaling)
         if world > 1:
             d3w = configs.cfg3(Bsz=16384, seed=1234 + 3 + 1000 * rank)
             x3w = torch.as_tensor(d3w["xbar"], dtype=f32, device=dev)
@@ -356,94 +408,56 @@ def run_ours(args):
             R3w = torch.diag_embed(torch.as_tensor(d3w["rdiag"], dtype=f32, device=dev))
             Qf3w = 10 * Q3w
             quadcopterClosedLoopMpc(x3w, Q3w, R3w, 50, 200, dt=0.1, Qf=Qf3w)
-            barrier()
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
-            for _ in range(3):
-                quadcopterClosedLoopMpc(x3w, Q3w, R3w, 50, 200, dt=0.1, Qf=Qf3w)
-            c1.record()
-            barrier()
-            extra_ms.append(c0.elapsed_time(c1) / 3)
+            X["clw"] = timed(lambda: quadcopterClosedLoopMpc(x3w, Q3w, R3w, 50, 200, dt=0.1, Qf=Qf3w), 3)
+            del x3w, Q3w, R3w, Qf3w
         else:
-            extra_ms.append(extra_ms[0])
+            X["clw"] = X["cl"]
         # cfg 3 in fp64, the reference's own precision: fused cooperative kernel (csrc/lqr_quad64.cuh)
         x3d, Q3d, R3d = x3.double(), Q3.double(), R3.double()
         quadcopterClosedLoopMpc(x3d, Q3d, R3d, 50, 200, dt=0.1, Qf=10 * Q3d)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(2):
-            quadcopterClosedLoopMpc(x3d, Q3d, R3d, 50, 200, dt=0.1, Qf=10 * Q3d)
-        c1.record()
-        barrier()
-        cl64_ms = c0.elapsed_time(c1) / 2
+        X["cl64"] = timed(lambda: quadcopterClosedLoopMpc(x3d, Q3d, R3d, 50, 200, dt=0.1, Qf=10 * Q3d), 2)
         del x3d, Q3d, R3d
         d4 = configs.cfg4(Bsz=16384)
-        x4 = torch.as_tensor(d4["x0"][lo:hi], dtype=torch.float64, device=dev)
-        uG = torch.as_tensor(d4["uGuess"], dtype=torch.float64, device=dev)
+        x4 = torch.as_tensor(d4["x0"][lo:hi], dtype=f64, device=dev)
+        uG = torch.as_tensor(d4["uGuess"], dtype=f64, device=dev)
         margs = (QuadcopterEuler(d4["dt"]), QuadraticCost(d4["Q"], d4["R"]), QuadraticTerminalCost(d4["Qf"]))
         ilqrUtils.iterativeLqr(*margs, x4, uG, maxIter=10, tol=-1.0)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(2):
-            ilqrUtils.iterativeLqr(*margs, x4, uG, maxIter=10, tol=-1.0)
-        c1.record()
-        barrier()
-        extra_ms.append(c0.elapsed_time(c1) / 2)
+        X["il"] = timed(lambda: ilqrUtils.iterativeLqr(*margs, x4, uG, maxIter=10, tol=-1.0), 2)
+        # the reference's defaults (maxIter=100, tol=1e-3, ilqrUtils.py:267-268): cost must follow the iterations actually taken
+        _, _, _, conv_d, log_d = ilqrUtils.iterativeLqr(*margs, x4, uG, return_log=True)
+        X["il_default"] = timed(lambda: ilqrUtils.iterativeLqr(*margs, x4, uG), 1)
+        info["il_default_iters_mean"] = float(log_d["iters"].float().mean())
+        info["il_default_iters_max"] = int(log_d["iters"].max())
+        info["il_default_converged"] = float(conv_d.float().mean())
+        # fp32 vs fp64 step-size sequences on a 1,024-problem subset (mismatches counted and reported)
+        xs = x4[:min(1024, x4.shape[0])]
+        _, _, _, _, lg64 = ilqrUtils.iterativeLqr(*margs, xs, uG, maxIter=10, tol=-1.0, return_log=True)
+        _, _, _, _, lg32 = ilqrUtils.iterativeLqr(*margs, xs.float(), uG.float(), maxIter=10, tol=-1.0, return_log=True)
+        info["ilqr_fp32_alpha_mismatch"] = int((lg64["alpha_idx"] != lg32["alpha_idx"]).any(dim=1).sum())
+        info["ilqr_fp32_alpha_subset"] = int(xs.shape[0])
         # cfg 5: DDP (second-order dynamics terms), N=100, 10 forced iterations, 16,384 problems in total, fp64
         d5 = configs.cfg5(Bsz=16384, N=100)
-        x5 = torch.as_tensor(d5["x0"][lo:hi], dtype=torch.float64, device=dev)
-        uG5 = torch.as_tensor(d5["uGuess"], dtype=torch.float64, device=dev)
+        x5 = torch.as_tensor(d5["x0"][lo:hi], dtype=f64, device=dev)
+        uG5 = torch.as_tensor(d5["uGuess"], dtype=f64, device=dev)
         m5 = (QuadcopterEuler(d5["dt"]), QuadraticCost(d5["Q"], d5["R"]), QuadraticTerminalCost(d5["Qf"]))
         ilqrUtils.differentialDynamicProgramming(*m5, x5, uG5, maxIter=10, tol=-1.0)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        ilqrUtils.differentialDynamicProgramming(*m5, x5, uG5, maxIter=10, tol=-1.0)
-        c1.record()
-        barrier()
-        extra_ms.append(c0.elapsed_time(c1))
+        X["ddp"] = timed(lambda: ilqrUtils.differentialDynamicProgramming(*m5, x5, uG5, maxIter=10, tol=-1.0), 1)
         # a1 with genuinely time-varying operands: A[k], B[k], Q[k], R[k] materialised per step and streamed from HBM
         from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
         Atv = A[:, None].expand(-1, N, -1, -1).contiguous()
         Btv = B[:, None].expand(-1, N, -1, -1).contiguous()
         Qtv = Q[:, None].expand(-1, N, -1, -1).contiguous()
         Rtv = R[:, None].expand(-1, N, -1, -1).contiguous()
-        Ltv = discreteFiniteHorizonLqr(Atv, Btv, Qtv, Rtv, N)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(5):
-            Ltv = discreteFiniteHorizonLqr(Atv, Btv, Qtv, Rtv, N)
-        c1.record()
-        barrier()
-        extra_ms.append(c0.elapsed_time(c1) / 5)
-        del Atv, Btv, Qtv, Rtv, Ltv
+        discreteFiniteHorizonLqr(Atv, Btv, Qtv, Rtv, N)
+        X["tv"] = timed(lambda: discreteFiniteHorizonLqr(Atv, Btv, Qtv, Rtv, N), 5)
+        del Atv, Btv, Qtv, Rtv
         # the headline workload in the reference's own precision (fp64): cooperative four-threads-per-problem Riccati kernel
-        f64 = torch.float64
-        xb64, ub64 = xbar.to(f64), ubar.to(f64)
-        Q64, R64 = Q.to(f64), R.to(f64)
-        Qf64 = 10 * Q64
-
-        def step64():
-            A64, B64 = ac.linearizeInertial(xb64, ub64, dt)
-            return lqrMpc(A64, B64, Q64, R64, N, ninf_n, inf_n, ninf_m, inf_m, Qf=Qf64).solve(xb64)
-
-        step64()
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(5):
-            step64()
-        c1.record()
-        barrier()
-        extra_ms.append(c0.elapsed_time(c1) / 5)
-        del xb64, ub64, Q64, R64, Qf64
+        step64(xb64)
+        X["f64"] = timed(lambda: step64(xb64), 5)
+        del xb64, ub64, Q64, R64
         # cfg 3 tier B: the reference demo's box-constrained lqrMpc (demos/lqrMpc.py:11-32: hover linearisation, N=25, bounds
         # |uvw|<=1, |pq|<=0.3, |r|<=0.1, |phi,theta|<=0.5, |u|<=3, OSQP eps 1e-2), one solve per initial state, bounds bind
-        from zopt_b200.quadcopter import Quadcopter as _Q
-        Ab, Bb = _Q().linearizeInertial(np.zeros(12), configs.U_TRIM, 0.1)
+        Ab, Bb = Quadcopter().linearizeInertial(np.zeros(12), configs.U_TRIM, 0.1)
         x_ub = np.array([1, 1, 1, 0.3, 0.3, 0.1, 0.5, 0.5, np.inf, np.inf, np.inf, np.inf])
         u_ub = np.full(4, 3.0)
         xb = np.zeros((16384, 12))
@@ -451,47 +465,29 @@ def run_ours(args):
         xb = torch.as_tensor(xb[lo:hi], dtype=f32, device=dev)
         pb = lqrMpc(Ab.to(f32), Bb.to(f32), torch.eye(12, dtype=f32, device=dev), torch.eye(4, dtype=f32, device=dev), 25,
                     -x_ub, x_ub, -u_ub, u_ub)
-        pb.solve(xb, eps_abs=1e-2, eps_rel=1e-2)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(3):
-            _, _, stb = pb.solve(xb, eps_abs=1e-2, eps_rel=1e-2)
-        c1.record()
-        barrier()
-        extra_ms.append(c0.elapsed_time(c1) / 3)
-        box_iters = float(pb.iters.float().mean())
-        box_opt = float((stb == 0).float().mean())
+        _, _, stb = pb.solve(xb, eps_abs=1e-2, eps_rel=1e-2)
+        X["box"] = timed(lambda: pb.solve(xb, eps_abs=1e-2, eps_rel=1e-2), 3)
+        info["box_iters"] = float(pb.iters.float().mean())
+        info["box_opt"] = float((stb == 0).float().mean())
         # ... and the demo's receding-horizon loop around it (demos/lqrMpc.py:42-47): 200 steps, warm-started, one fused kernel
-        pb.closedLoop(xb, 200, eps_abs=1e-2, eps_rel=1e-2)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
         _, stc = pb.closedLoop(xb, 200, eps_abs=1e-2, eps_rel=1e-2)
-        c1.record()
-        barrier()
-        extra_ms.append(c0.elapsed_time(c1))
-        boxcl_iters = float(pb.iters.float().mean()) / 200
-        boxcl_opt = float((stc == 0).float().mean())
+        X["boxcl"] = timed(lambda: pb.closedLoop(xb, 200, eps_abs=1e-2, eps_rel=1e-2), 1)
+        info["boxcl_iters"] = float(pb.iters.float().mean()) / 200
+        info["boxcl_opt"] = float((stc == 0).float().mean())
         # same loop, termination checked every 5 ADMM iterations instead of OSQP's default 25 (a warm-started solve converges in ~5)
-        pb.closedLoop(xb, 200, eps_abs=1e-2, eps_rel=1e-2, check_termination=5)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
         _, stc5 = pb.closedLoop(xb, 200, eps_abs=1e-2, eps_rel=1e-2, check_termination=5)
-        c1.record()
-        barrier()
-        extra_ms.append(c0.elapsed_time(c1))
-        boxcl5_iters = float(pb.iters.float().mean()) / 200
-        boxcl5_opt = float((stc5 == 0).float().mean())
-    while len(extra_ms) < 9:
-        extra_ms.append(0.0)
-    extra_ms.append(0.0 if args.no_extras else cl64_ms)
+        X["boxcl5"] = timed(lambda: pb.closedLoop(xb, 200, eps_abs=1e-2, eps_rel=1e-2, check_termination=5), 1)
+        info["boxcl5_iters"] = float(pb.iters.float().mean()) / 200
+        info["boxcl5_opt"] = float((stc5 == 0).float().mean())
 
-    times = torch.tensor([ms, e2e_ms, k_ms, e2e_u_ms] + extra_ms, dtype=torch.float64, device=dev)
+    names = sorted(X)
+    base = [ms, e2e_ms, k_ms, e2e_u_ms, kd_ms, roof_ms, e2e64_ms, gather_ms]
+    times = torch.tensor(base + [X[k] for k in names], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, k_ms, e2e_u_ms, cl_ms, clw_ms, il_ms, ddp_ms, tv_ms, f64_ms, box_ms, boxcl_ms, boxcl5_ms, cl64_ms = (float(v) for v in times.cpu())
+    vals = [float(v) for v in times.cpu()]
+    ms, e2e_ms, k_ms, e2e_u_ms, kd_ms, roof_ms, e2e64_ms, gather_ms = vals[:len(base)]
+    X = dict(zip(names, vals[len(base):]))
 
     if rank == 0:
         total = Bsz * world
@@ -502,6 +498,7 @@ def run_ours(args):
         _lib.check(_lib.lib.zb_peak_fma(0, local_rank, C.byref(peak32), C.byref(clk)))
         peak64 = C.c_double(0)
         _lib.check(_lib.lib.zb_peak_fma(1, local_rank, C.byref(peak64), C.byref(clk)))
+        p32, p64 = peak32.value / 1e12, peak64.value / 1e12  # per GPU
         ach_tf = FLOP_PER_SOLVE * Bsz / (k_ms * 1e-3) / 1e12
         peaks = {}
         try:
@@ -510,88 +507,108 @@ def run_ours(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = (1456 + 9600 * 2 + 3248) * Bsz  # in: A,B,Q,R,Qf,x0; gains written + re-read; plan written (fp32)
-        traffic = None
-        try:  # DRAM bytes of the dominant kernel from the committed ncu capture (same kernel, same batch)
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes of the dominant kernel from the committed ncu capture (same kernel, same batch); not measured in this run
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             if tj.get("batch") == Bsz and tj.get("N") == N:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_src = "profiles/traffic.json (ncu --set full capture of this kernel at this batch; not re-measured in this run)"
         except Exception:
             pass
-        roof = {"bound": "fp32_fma", "achieved": ach_tf, "peak": peak32.value / 1e12, "unit": "TFLOP/s",
-                "frac": ach_tf / (peak32.value / 1e12), "traffic": traffic, "algorithmic_bytes": alg_bytes,
+        roof = {"bound": "fp32_fma", "achieved": ach_tf, "peak": p32, "unit": "TFLOP/s",
+                "frac": ach_tf / p32, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
                 "peak_source": "zb_peak_fma dependent-FMA probe measured in this run (MEASURED_PEAKS.json has no FP32 CUDA-core figure)",
-                "kernel": "lqrMpc.solve launch (Riccati sweep + rollout)", "kernel_ms": k_ms,
+                "kernel": "k_riccati_t1<MPC,QDIAG>: lqrMpc.solve launch (Riccati sweep + rollout)", "kernel_ms": k_ms,
+                "kernel_timing": f"{k_reps} back-to-back launches between one CUDA-event pair on the launching stream",
                 "algorithmic_flop_per_solve": FLOP_PER_SOLVE,
-                "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
+                "dense_cost_kernel_ms": kd_ms, "dense_cost_frac": FLOP_PER_SOLVE * Bsz / (kd_ms * 1e-3) / 1e12 / p32,
+                "hbm_achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
+                "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
         cpu_val, cpu_sec, threads = time_cpu(args.cpu_sample, 3, 1)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(Bsz), "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "returns": "u (Bsz,4), plan xTraj (Bsz,51,12) + uTraj (Bsz,50,4), status -- PCIe-bound",
-                    "control_only": {"value": total * args.steps / (e2e_u_ms * 1e-3), "unit": UNIT,
-                                     "d2h_bytes_per_step": Bsz * (NU * 4 + 1), "returns": "u and status only"}},
-            "gpu_launches": 2 * args.steps, "roofline": roof,
-            "extra": None if args.no_extras else {
-                "cfg3_closed_loop_mpc": {"value": 16384 * 200 / (cl_ms * 1e-3), "unit": "MPC solves/s", "ms": cl_ms,
+        # copy roof: all ranks moving the step's D2H payload at once; e2e as a fraction of it
+        roof_gbs = d2h * world / (roof_ms * 1e-3) / 1e9
+        e2e_gbs = e2e_val * (d2h / Bsz) / 1e9
+        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "returns": "u (Bsz,4), plan xTraj (Bsz,51,12) + uTraj (Bsz,50,4), status -- PCIe-bound",
+               "d2h_gbs": e2e_gbs, "pcie_roof_gbs": roof_gbs, "frac_of_pcie_roof": e2e_gbs / roof_gbs,
+               "pcie_roof_how": "the step's D2H payload alone (pinned, same buffers), every rank at once, CUDA events, max over ranks; aggregate GB/s",
+               "control_only_value": total * args.steps / (e2e_u_ms * 1e-3), "control_only_d2h_bytes_per_step": Bsz * (NU * 4 + 1),
+               "fp64_value": (total / (e2e64_ms * 1e-3)) if e2e64_ms else None, "fp64_d2h_bytes_per_step": d2h64, "fp64_h2d_bytes_per_step": h2d64,
+               "gather_ms": gather_ms, "gather_bytes": (Bsz * world * (NU + (N + 1) * NX + N * NU) * 4) if world > 1 else 0,
+               "cpu_binding": binding["how"], "cpu_binding_numa_node": binding["numa_node"], "cpus_bound": binding["cpus"]}
+        extra = None
+        tail = ""
+        if not args.no_extras:
+            def fl(units, flop, t_ms, peak):  # strong-scaled extras: the job's flops against `world` GPUs' peak
+                a = units * flop / (t_ms * 1e-3) / 1e12
+                return {"achieved": a, "peak": peak * world, "unit": "TFLOP/s", "frac": a / (peak * world), "n_gpus": world}
+            cl, clw, cl64, il, ild, ddp, tv, f64t = X["cl"], X["clw"], X["cl64"], X["il"], X["il_default"], X["ddp"], X["tv"], X["f64"]
+            extra = {
+                "cfg3_closed_loop_mpc": {"value": 16384 * 200 / (cl * 1e-3), "unit": "MPC solves/s", "ms": cl,
                                          "workload": "16,384 problems total (sharded over ranks), 200 sim steps, horizon 50, fp32, "
                                                      "re-linearised every step, bounds inactive, one fused kernel",
-                                         "scaling": "strong"},
-                "cfg3_closed_loop_mpc_weak": {"value": 16384 * world * 200 / (clw_ms * 1e-3), "unit": "MPC solves/s", "ms": clw_ms,
+                                         "scaling": "strong", "roofline": dict(bound="fp32_fma", **fl(16384 * 200, FLOP_PER_SOLVE, cl, p32))},
+                "cfg3_closed_loop_mpc_weak": {"value": 16384 * world * 200 / (clw * 1e-3), "unit": "MPC solves/s", "ms": clw,
                                               "workload": "as cfg3 but 16,384 problems PER GPU", "scaling": "weak"},
-                "cfg3_closed_loop_mpc_fp64": {"value": 16384 * 200 / (cl64_ms * 1e-3), "unit": "MPC solves/s", "ms": cl64_ms,
+                "cfg3_closed_loop_mpc_fp64": {"value": 16384 * 200 / (cl64 * 1e-3), "unit": "MPC solves/s", "ms": cl64,
                                               "workload": "cfg3 (16,384 problems total, sharded over ranks) in fp64, the reference's own precision: "
                                                           "one fused cooperative kernel", "scaling": "strong",
-                                              "roofline": {"bound": "fp64_fma", "achieved": 16384 * 200 * FLOP_PER_SOLVE / (cl64_ms * 1e-3) / 1e12,
-                                                           "peak": peak64.value / 1e12, "unit": "TFLOP/s",
-                                                           "frac": 16384 * 200 * FLOP_PER_SOLVE / (cl64_ms * 1e-3) / peak64.value}},
-                "cfg4_ilqr": {"value": 16384 * 10 / (il_ms * 1e-3), "unit": "problem-iterations/s", "ms": il_ms,
+                                              "roofline": dict(bound="fp64_fma", **fl(16384 * 200, FLOP_PER_SOLVE, cl64, p64))},
+                "cfg4_ilqr": {"value": 16384 * 10 / (il * 1e-3), "unit": "problem-iterations/s", "ms": il,
                               "workload": "16,384 problems total (sharded over ranks), N=200, 10 iterations, 16-way line search, fp64",
                               "scaling": "strong", "algorithmic_flop_per_problem_iteration": 4.66e6,
-                              "roofline": {"bound": "fp64_fma", "achieved": 16384 * 10 * 4.66e6 / (il_ms * 1e-3) / 1e12,
-                                           "peak": peak64.value / 1e12, "unit": "TFLOP/s",
-                                           "frac": 16384 * 10 * 4.66e6 / (il_ms * 1e-3) / peak64.value,
-                                           "peak_source": "zb_peak_fma(f64) dependent-FMA probe measured in this run"}},
-                "cfg5_ddp": {"value": 16384 * 10 / (ddp_ms * 1e-3), "unit": "problem-iterations/s", "ms": ddp_ms,
+                              "fp32_alpha_sequence_mismatches": info["ilqr_fp32_alpha_mismatch"], "fp32_alpha_subset": info["ilqr_fp32_alpha_subset"],
+                              "roofline": dict(bound="fp64_fma", **fl(16384 * 10, 4.66e6, il, p64))},
+                "cfg4_ilqr_reference_defaults": {"ms": ild, "iterations_mean_rank0": info["il_default_iters_mean"],
+                                                 "iterations_max_rank0": info["il_default_iters_max"], "converged_fraction_rank0": info["il_default_converged"],
+                                                 "value": 16384 * info["il_default_iters_mean"] / (ild * 1e-3), "unit": "problem-iterations/s",
+                                                 "workload": "cfg4 problems with the reference's defaults maxIter=100, tol=1e-3 (ilqrUtils.py:267-268): "
+                                                             "early exit on the device, cost follows the iterations taken", "scaling": "strong"},
+                "cfg5_ddp": {"value": 16384 * 10 / (ddp * 1e-3), "unit": "problem-iterations/s", "ms": ddp,
                              "workload": "16,384 problems total (sharded over ranks), N=100, 10 iterations, eigen-clamped second-order "
                                          "terms every step, fp64", "scaling": "strong",
                              "algorithmic_flop_per_problem_iteration": 7.33e6,
-                             "roofline": {"bound": "fp64_fma", "achieved": 16384 * 10 * 7.33e6 / (ddp_ms * 1e-3) / 1e12,
-                                          "peak": peak64.value / 1e12, "unit": "TFLOP/s",
-                                          "frac": 16384 * 10 * 7.33e6 / (ddp_ms * 1e-3) / peak64.value}},
-                "cfg2_fp64": {"value": Bsz * world / (f64_ms * 1e-3), "unit": "solves/s", "ms": f64_ms,
+                             "roofline": dict(bound="fp64_fma", **fl(16384 * 10, 7.33e6, ddp, p64))},
+                "cfg2_fp64": {"value": Bsz * world / (f64t * 1e-3), "unit": "solves/s", "ms": f64t,
                               "workload": f"the headline step (linearise + lqrMpc.solve, N={N}) in fp64, the reference's own precision, "
                                           f"{Bsz} problems per GPU", "scaling": "weak",
-                              "roofline": {"bound": "fp64_fma", "achieved": FLOP_PER_SOLVE * Bsz / (f64_ms * 1e-3) / 1e12,
-                                           "peak": peak64.value / 1e12, "unit": "TFLOP/s",
-                                           "frac": FLOP_PER_SOLVE * Bsz / (f64_ms * 1e-3) / peak64.value}},
-                "lqr_time_varying": {"value": Bsz * world / (tv_ms * 1e-3), "unit": "solves/s", "ms": tv_ms,
+                              "roofline": {"bound": "fp64_fma", "achieved": FLOP_PER_SOLVE * Bsz / (f64t * 1e-3) / 1e12,
+                                           "peak": p64, "unit": "TFLOP/s", "frac": FLOP_PER_SOLVE * Bsz / (f64t * 1e-3) / 1e12 / p64}},
+                "lqr_time_varying": {"value": Bsz * world / (tv * 1e-3), "unit": "solves/s", "ms": tv,
                                      "workload": f"discreteFiniteHorizonLqr with A[k], B[k], Q[k], R[k] materialised per step "
                                                  f"(streamed from HBM), {Bsz} problems per GPU, N={N}, fp32", "scaling": "weak",
-                                     "roofline": {"bound": "hbm", "achieved": Bsz * N * 1600 / (tv_ms * 1e-3) / 1e9,
+                                     "roofline": {"bound": "hbm", "achieved": Bsz * N * 1600 / (tv * 1e-3) / 1e9,
                                                   "peak": hbm_peak, "unit": "GB/s",
-                                                  "frac": Bsz * N * 1600 / (tv_ms * 1e-3) / 1e9 / hbm_peak,
+                                                  "frac": Bsz * N * 1600 / (tv * 1e-3) / 1e9 / hbm_peak,
                                                   "algorithmic_bytes_per_problem_step": 1600,
                                                   "note": "SURVEY 8d: A 576 + B 192 + Q 576 + R 64 in, gains 192 out (fp32); the kernel "
                                                           "fetches only the lower-triangle chunks of Q (384 B)"}},
-                "cfg3_box_constrained_mpc": {"value": 16384 / (box_ms * 1e-3), "unit": "solves/s", "ms": box_ms,
-                                             "admm_iterations_mean_rank0": box_iters, "optimal_fraction_rank0": box_opt,
+                "cfg3_box_constrained_mpc": {"value": 16384 / (X["box"] * 1e-3), "unit": "solves/s", "ms": X["box"],
+                                             "admm_iterations_mean_rank0": info["box_iters"], "optimal_fraction_rank0": info["box_opt"],
                                              "workload": "16,384 initial states total (sharded over ranks), the reference demo's box-constrained "
                                                          "lqrMpc (hover linearisation, N=25, demo bounds, eps 1e-2 as demos/lqrMpc.py:32), fp32, "
                                                          "bounds bind (10 m offsets, |v| <= 1)", "scaling": "strong"},
-                "cfg3_box_constrained_mpc_closed_loop": {"value": 16384 * 200 / (boxcl_ms * 1e-3), "unit": "MPC solves/s", "ms": boxcl_ms,
-                                                         "admm_iterations_per_solve_rank0": boxcl_iters, "optimal_fraction_rank0": boxcl_opt,
+                "cfg3_box_constrained_mpc_closed_loop": {"value": 16384 * 200 / (X["boxcl"] * 1e-3), "unit": "MPC solves/s", "ms": X["boxcl"],
+                                                         "admm_iterations_per_solve_rank0": info["boxcl_iters"], "optimal_fraction_rank0": info["boxcl_opt"],
                                                          "workload": "the same problem in the demo's receding-horizon loop (demos/lqrMpc.py:42-47): "
                                                                      "16,384 initial states total, 200 steps, clip + warm-started solve + perfect "
                                                                      "tracking, one fused kernel, fp32, eps 1e-2", "scaling": "strong"},
-                "cfg3_box_constrained_mpc_closed_loop_check5": {"value": 16384 * 200 / (boxcl5_ms * 1e-3), "unit": "MPC solves/s", "ms": boxcl5_ms,
-                                                                "admm_iterations_per_solve_rank0": boxcl5_iters, "optimal_fraction_rank0": boxcl5_opt,
-                                                                "workload": "as above with check_termination=5 (OSQP default is 25)", "scaling": "strong"}},
+                "cfg3_box_constrained_mpc_closed_loop_check5": {"value": 16384 * 200 / (X["boxcl5"] * 1e-3), "unit": "MPC solves/s", "ms": X["boxcl5"],
+                                                                "admm_iterations_per_solve_rank0": info["boxcl5_iters"], "optimal_fraction_rank0": info["boxcl5_opt"],
+                                                                "workload": "as above with check_termination=5 (OSQP default is 25)", "scaling": "strong"}}
+            # compact digest as the LAST key of the line: the driver's record keeps the tail of stdout
+            tail = (f"N={world} e2e {e2e_val / 1e6:.1f}M/s ({e2e_gbs:.0f} of {roof_gbs:.0f} GB/s copy roof) | cfg3 strong 16384x200: {cl:.2f} ms "
+                    f"{16384 * 200 / cl / 1e3:.1f}M MPC/s; weak {clw:.2f} ms; fp64 {cl64:.1f} ms | cfg4 iLQR f64 {il:.1f} ms {16384 * 10 / il / 1e3:.2f}M it/s; "
+                    f"defaults {ild:.1f} ms @{info['il_default_iters_mean']:.1f} it | cfg5 DDP {ddp:.1f} ms | tv {tv:.2f} ms | f64 {f64t:.2f} ms")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(Bsz), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": 2 * args.steps, "roofline": roof, "extra": extra,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{args.cpu_sample} problems of the same workload per step, 3 steps of {cpu_sec:.2f} s after 1 warm-up, torch-CPU fp64 oracle port (JAX not installed)"},
+            "host": hostbind.host_topology(), "digest": tail,
         }
         print(json.dumps(line))
     if world > 1:

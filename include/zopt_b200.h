@@ -166,6 +166,7 @@ ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_
 #define ZB_COST_DIAGONAL 2 /* both */
 #define ZB_VARIANT_THREAD 4 /* zb_mpc_closed_loop_quad, zb_mpc_box_*: force the thread-per-problem kernel */
 #define ZB_VARIANT_QUAD 8   /* ... force the 4-threads-per-problem kernel (default for small batches) */
+#define ZB_VARIANT_WARP 64  /* zb_mpc_closed_loop_quad (fp32): force the nine-lanes-per-problem register-tiled kernel (default for the smallest batches) */
 #define ZB_GENERIC_FORWARD 32 /* zb_ilqr_solve: force the two-kernel line search (k_forward_costs + k_forward_commit) instead of the fused quadcopter kernel */
 #define ZB_BOX_STATE_GLOBAL 16 /* zb_mpc_box_*: keep the 4-threads-per-problem kernel's ADMM state in the global workspace even when it would fit on chip */
 

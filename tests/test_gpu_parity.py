@@ -763,7 +763,7 @@ def test_fast_paths_fp32_time_invariant(dense_cost):
     assert (status == 0).all() and relerr(u, traj.uTraj[:, 0]) == 0
 
 
-@pytest.mark.parametrize("variant", ["thread", "quad"])
+@pytest.mark.parametrize("variant", ["thread", "quad", "warp"])
 @pytest.mark.parametrize("dense_cost", [False, True])
 def test_closed_loop_mpc_fused_vs_composed(dense_cost, variant):
     """BASELINE cfg 3 path: the fused fp32 closed-loop kernel against the same loop composed step by step in fp64 from
@@ -824,6 +824,32 @@ def test_closed_loop_mpc_fused_vs_composed(dense_cost, variant):
         assert per_problem_relerr(t64.xTraj[fi], xref.cpu().numpy()[fi]).max() < 1e-8
         assert per_problem_relerr(t64.uTraj[fi], uref.cpu().numpy()[fi]).max() < 1e-8
         assert relerr(t64.uTraj[0, 0], uref[0, 0]) < 1e-11  # first step: no accumulated history
+
+
+@pytest.mark.parametrize("dense_cost", [False, True])
+def test_closed_loop_mpc_warp_variant_equals_thread_variant(dense_cost):
+    """The nine-lanes-per-problem kernel (csrc/mpc_warp.cuh, small per-GPU batches: cfg 3 sharded over 8 GPUs) performs the
+    thread-per-problem kernel's operations in the same order, so the two agree BIT FOR BIT -- ragged batch (not a multiple of
+    the 3 problems a warp holds), full cfg-3 horizon, 40 closed-loop steps."""
+    from zopt_b200.mpcUtils import quadcopterClosedLoopMpc
+    Bsz, N, Tsim = 100, 50, 40
+    d = configs.cfg3(Bsz=Bsz)
+    Q, R = configs.diag_embed(d["qdiag"]), configs.diag_embed(d["rdiag"])
+    if dense_cost:
+        rng = np.random.default_rng(9)
+        Mq, Mr = rng.normal(size=(Bsz, 12, 12)) * 0.2, rng.normal(size=(Bsz, 4, 4)) * 0.2
+        Q, R = Q + Mq @ np.swapaxes(Mq, 1, 2), R + Mr @ np.swapaxes(Mr, 1, 2)
+    x0 = d["xbar"].copy()
+    x0[:, 9:12] *= 0.2
+    args = (cuda(x0, torch.float32), cuda(Q, torch.float32), cuda(R, torch.float32), N, Tsim)
+    tt = quadcopterClosedLoopMpc(*args, dt=0.1, Qf=cuda(10 * Q, torch.float32), variant="thread")
+    tw = quadcopterClosedLoopMpc(*args, dt=0.1, Qf=cuda(10 * Q, torch.float32), variant="warp")
+    fin = torch.isfinite(tt.xTraj).all(dim=2).all(dim=1)
+    assert int(fin.sum()) >= Bsz - 2
+    assert torch.equal(tt.xTraj[fin], tw.xTraj[fin]) and torch.equal(tt.uTraj[fin], tw.uTraj[fin])
+    # small batches pick the kernel by themselves
+    ta = quadcopterClosedLoopMpc(*args, dt=0.1, Qf=cuda(10 * Q, torch.float32))
+    assert torch.equal(ta.xTraj[fin], tw.xTraj[fin])
 
 
 def test_pytree_constructors_and_building_block_pipeline():

@@ -13,6 +13,14 @@
 
 using namespace zb;
 
+namespace zb {
+int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream);  // zb_small_batch.cu
+}
+
+#ifndef ZB_W9_MAX_PER_SM
+#define ZB_W9_MAX_PER_SM 28  // problems per SM up to which the nine-lanes-per-problem closed-loop kernel is selected
+#endif
+
 // =================================================================================================
 // generic kernels: one thread per problem
 // =================================================================================================
@@ -792,7 +800,11 @@ int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int
     int sm_count = 0;  // cudaDeviceGetAttribute is cheap; cudaGetDeviceProperties costs milliseconds per call
     ZB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     const bool dense_ok = arr_ok(to_arr(Q)) && arr_ok(to_arr(R)) && arr_ok(to_arr(Qf));
-    const bool want_quad = (flags & ZB_VARIANT_QUAD) || (!(flags & ZB_VARIANT_THREAD) && Bsz <= (int64_t)sm_count * 56);  // measured crossover on B200: ~8-10 K problems
+    // smallest batches (cfg 3 sharded over 8 GPUs: ~14 problems per SM): nine lanes per problem, operands in registers (mpc_warp.cuh)
+    const bool forced = (flags & (ZB_VARIANT_THREAD | ZB_VARIANT_QUAD | ZB_VARIANT_WARP)) != 0;
+    const bool want_warp = (flags & ZB_VARIANT_WARP) || (!forced && Bsz <= (int64_t)sm_count * ZB_W9_MAX_PER_SM);
+    if (want_warp) return mpc_closed_loop_w9_launch(P, (cudaStream_t)stream);
+    const bool want_quad = (flags & ZB_VARIANT_QUAD) || (!forced && Bsz <= (int64_t)sm_count * 56);  // measured crossover on B200: ~8-10 K problems
     if (dense_ok && want_quad) return mpc_closed_loop_coop_launch(P, (cudaStream_t)stream);
     return mpc_closed_loop_launch(P, (cudaStream_t)stream, (flags & ZB_COST_DIAGONAL) != 0);
 }

@@ -233,7 +233,8 @@ def quadcopterClosedLoopMpc(x0, Q, R, N, Tsim, dt=0.1, Qf=None, uTrim=(9.807, 0.
 
     x0 (Bsz,12) or (12,); Q (12,12), R (4,4), Qf (12,12, default Q) optionally batched.
     Returns Trajectory(xTraj (Bsz,Tsim+1,12), uTraj (Bsz,Tsim,4)) with uTraj the deviation from uTrim.
-    `variant`: "auto" (4 threads per problem for small batches, one thread per problem otherwise), "thread", "quad".
+    `variant`: "auto" (by batch size: nine lanes per problem for the smallest batches, four threads per problem for small
+    ones, one thread per problem otherwise), "thread", "quad", "warp" (fp32 only).
     With finite bounds, compose `Quadcopter.linearizeInertial`, `lqrMpc(...).solve` and
     `Quadcopter.inertialDynamics` step by step instead.
     """
@@ -253,5 +254,5 @@ def quadcopterClosedLoopMpc(x0, Q, R, N, Tsim, dt=0.1, Qf=None, uTrim=(9.807, 0.
     ut = (C.c_double * 4)(*[float(v) for v in uTrim])
     check(lib.zb_mpc_closed_loop_quad(0 if f32 == torch.float32 else 1, device.index, stream_ptr(device), Bsz, int(N), int(Tsim), float(dt), ut,
                                       *[v.ref() for v in views],
-                                      (2 if diag else 0) | {"auto": 0, "thread": 4, "quad": 8}[variant], ptr(x0), ptr(xS), ptr(uS)))
+                                      (2 if diag else 0) | {"auto": 0, "thread": 4, "quad": 8, "warp": 64}[variant], ptr(x0), ptr(xS), ptr(uS)))
     return Trajectory(xS, uS) if batched else Trajectory(xS[0], uS[0])
