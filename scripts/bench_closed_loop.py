@@ -16,7 +16,9 @@ for Bsz in (512, 2048, 4096, 8192, 16384, 65536):
         if variant == "warp" and Bsz > 16384:
             continue
         quadcopterClosedLoopMpc(x, Q, R, 50, 20, Qf=Qf, variant=variant); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); quadcopterClosedLoopMpc(x, Q, R, 50, 200, Qf=Qf, variant=variant); e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = 1e9
+        for _ in range(3):  # best of three
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); quadcopterClosedLoopMpc(x, Q, R, 50, 200, Qf=Qf, variant=variant); e1.record(); torch.cuda.synchronize()
+            ms = min(ms, e0.elapsed_time(e1))
         print(f"Bsz={Bsz:6d} {variant:6s}: {ms:8.2f} ms  {Bsz * 200 / ms * 1e3:.3e} MPC solves/s")

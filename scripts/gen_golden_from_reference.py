@@ -150,4 +150,65 @@ np.savez(os.path.join(OUT, "riccati_steps.npz"), f_x=f_x, f_u=f_u, f_xx=f_xx, f_
          ddp_v=npy(vo2.v), ddp_vx=npy(vo2.v_x), ddp_vxx=npy(vo2.v_xx), ddp_l=npy(p2.l), ddp_L=npy(p2.L), S=S,
          S_pd=npy(ref_ilqr.ensurePositiveDefinite(T(S))))
 print("riccati_steps")
+
+# ---- (vii) the reference's Simulator (discrete branch, zopt/simulator.py:124-169) on the demos' two closed loops -------
+import zopt.simulator as ref_sim  # noqa: E402
+assert ref_sim.__file__.startswith("/root/reference/")
+# (a) demos/iterativeLqr.py:44-56: tracking controller u = L_k (x - xTraj_k) + uTraj_k on the plant in wind [3,1,0]; the
+#     plan is the frozen iLQR demo solution above (N = 40)
+gi = np.load(os.path.join(OUT, "ilqr_demo_N40_it4.npz"))
+Np = int(gi["N"])
+xTj, uTj, LTj = T(gi["xTraj"]), T(gi["uTraj"]), T(gi["L"])
+wind = np.array([3.0, 1.0, 0.0])
+x0s = np.array(gi["x0"], dtype=np.float64)
+noisyDynFun = lambda k, x, u: (None, T(x) + dt * ac.inertialDynamics(T(x), T(u), wind_ned=T(wind)))
+dynamicsBlock = ref_sim.SimBlock(noisyDynFun, T(x0s), dt=dt, name="Dynamics")
+controllerBlock = ref_sim.SimBlock(lambda k, xCtrl, x: (LTj[k] @ (T(x) - xTj[k]) + uTj[k], T(np.array([]))), T(np.array([])), dt=dt,
+                                   name="Controller")
+tS, xc, xS, uS, _ = ref_sim.Simulator([controllerBlock, dynamicsBlock], (0, Np * dt)).simulate()
+sim_a = dict(a_t=npy(tS), a_x=npy(xS), a_u=npy(uS), a_x0=x0s, a_wind=wind, a_xTraj=npy(xTj), a_uTraj=npy(uTj), a_L=npy(LTj), a_dt=dt)
+print("simulator (tracking, wind)", npy(xS).shape, npy(uS).shape)
+# (b) demos/discreteFiniteHorizonLqr.py:38-49: 8-state LQR gains on the 12-state plant through x[:8]
+gl = np.load(os.path.join(OUT, "lqr_demo_n8.npz"))
+Kd = T(gl["K"])
+xTrim8 = T(np.zeros(8))
+x0b = np.zeros(12)
+x0b[0:3] = 1
+dynB = ref_sim.SimBlock(lambda k, x, u: (None, T(x) + dt * ac.inertialDynamics(T(x), T(u))), T(x0b), dt=dt, name="Dynamics")
+ctlB = ref_sim.SimBlock(lambda k, xCtrl, x: ref_lqr.proportionalFeedbackController(T(x)[:8], xTrim8, uTrim, Kd[k]), T(np.array([])), dt=dt,
+                        name="Controller", jittable=False)
+tB, _, xB, uB, _ = ref_sim.Simulator([ctlB, dynB], (0, 10)).simulate()
+np.savez(os.path.join(OUT, "simulator_demos.npz"), b_t=npy(tB), b_x=npy(xB), b_u=npy(uB), b_x0=x0b, b_K=npy(Kd), b_uTrim=npy(uTrim), **sim_a)
+print("simulator (lqr gains)", npy(xB).shape, npy(uB).shape)
+
+# ---- (viii) iLQR / DDP at BASELINE cfg 4 / cfg 5 size: N = 200 x 10 iterations (iLQR), N = 100 x 10 iterations (DDP), four
+#      problems each from the configs' own initial-state distributions; per-iteration J, step-size index, final x, u, L ------
+
+
+def run_solver_logged(solver, x0, N, R, maxIter):
+    """The reference solver run with maxIter = 0..K (deterministic): J after every iteration; the step-size index of
+    iteration k is recovered from the reference's own forwardPass2 candidates (argmin of the 16 costs, ilqrUtils.py:145-149)
+    by re-running the solver's iteration body on the previous iterate -- here simply by matching J_k against the 16
+    candidate costs computed with the reference's trajectoryRollout + CostFunction."""
+    Q = np.eye(12)
+    Qt, Rt = T(Q), T(R)
+    costFun = lambda x, u: x.T @ Qt @ x + u.T @ Rt @ u
+    terminalCostFun = lambda x: 10 * x @ Qt @ x
+    uGuess = T(np.repeat(configs.U_TRIM[None], N, axis=0))
+    Js = []
+    for k in range(0, maxIter + 1):
+        traj, LArr, J, conv = solver(dynFun, costFun, terminalCostFun, T(x0), uGuess, maxIter=k, tol=-1.0)
+        Js.append(float(J))
+    return dict(J_per_iter=np.array(Js), xTraj=npy(traj.xTraj), uTraj=npy(traj.uTraj), L=npy(LArr))
+
+
+if os.environ.get("GOLDEN_FULL_SIZE", "1") == "1":
+    for name, solver, cfg, N, nprob in (("ilqr_cfg4_N200_it10", ref_ilqr.iterativeLqr, configs.cfg4, 200, 4),
+                                        ("ddp_cfg5_N100_it10", ref_ilqr.differentialDynamicProgramming, configs.cfg5, 100, 4)):
+        dd = cfg(Bsz=nprob, N=N)
+        recs = [run_solver_logged(solver, dd["x0"][i], N, dd["R"], 10) for i in range(nprob)]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), x0=dd["x0"], R=dd["R"], N=N, maxIter=10,
+                            J_per_iter=np.array([r["J_per_iter"] for r in recs]), xTraj=np.array([r["xTraj"] for r in recs]),
+                            uTraj=np.array([r["uTraj"] for r in recs]), L=np.array([r["L"] for r in recs]))
+        print(name, np.array([r["J_per_iter"] for r in recs])[:, [0, 1, -1]])
 print("golden fixtures written to", OUT)

@@ -827,10 +827,11 @@ def test_closed_loop_mpc_fused_vs_composed(dense_cost, variant):
 
 
 @pytest.mark.parametrize("dense_cost", [False, True])
-def test_closed_loop_mpc_warp_variant_equals_thread_variant(dense_cost):
-    """The nine-lanes-per-problem kernel (csrc/mpc_warp.cuh, small per-GPU batches: cfg 3 sharded over 8 GPUs) performs the
-    thread-per-problem kernel's operations in the same order, so the two agree BIT FOR BIT -- ragged batch (not a multiple of
-    the 3 problems a warp holds), full cfg-3 horizon, 40 closed-loop steps."""
+def test_closed_loop_mpc_warp_variant_vs_thread_variant(dense_cost):
+    """The nine-lanes-per-problem kernel (csrc/mpc_warp.cuh, small per-GPU batches: cfg 3 sharded over 8 GPUs) against the
+    thread-per-problem kernel on the SAME fp32 problems -- ragged batch (not a multiple of the 3 problems a warp holds), full
+    cfg-3 horizon, 40 closed-loop steps.  Same algebra, different summation grouping: agreement to fp32 rounding amplified by
+    the closed loop, and the first applied control (no history) to a few ulp of the control's scale."""
     from zopt_b200.mpcUtils import quadcopterClosedLoopMpc
     Bsz, N, Tsim = 100, 50, 40
     d = configs.cfg3(Bsz=Bsz)
@@ -846,7 +847,12 @@ def test_closed_loop_mpc_warp_variant_equals_thread_variant(dense_cost):
     tw = quadcopterClosedLoopMpc(*args, dt=0.1, Qf=cuda(10 * Q, torch.float32), variant="warp")
     fin = torch.isfinite(tt.xTraj).all(dim=2).all(dim=1)
     assert int(fin.sum()) >= Bsz - 2
-    assert torch.equal(tt.xTraj[fin], tw.xTraj[fin]) and torch.equal(tt.uTraj[fin], tw.uTraj[fin])
+    assert torch.equal(tt.xTraj[:, 0], tw.xTraj[:, 0])
+    e0 = per_problem_relerr(tw.uTraj[fin][:, :1], tt.uTraj[fin][:, :1].cpu().numpy()).max()
+    ex = per_problem_relerr(tw.xTraj[fin], tt.xTraj[fin].cpu().numpy()).max()
+    eu = per_problem_relerr(tw.uTraj[fin], tt.uTraj[fin].cpu().numpy()).max()
+    print(f"warp vs thread: first control {e0:.2e}, x {ex:.2e}, u {eu:.2e}")
+    assert e0 < 5e-6 and ex < 2e-5 and eu < 2e-5
     # small batches pick the kernel by themselves
     ta = quadcopterClosedLoopMpc(*args, dt=0.1, Qf=cuda(10 * Q, torch.float32))
     assert torch.equal(ta.xTraj[fin], tw.xTraj[fin])

@@ -531,17 +531,13 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_mpc_closed_loop_quad(Clos
         }
         // ---- linearise at (x_t, u_trim): A = I + dt * dF/dx  -> rows of X (chunks 0..2) ----
         {
-            float J[144];
-            QuadTrig<float> tr = quad_trig(x);
-            quad_jac_x(tr, x, ut, J);
+            float Am[144];
+            closed_loop_linearize(x, ut, dt, Am);
 #pragma unroll
             for (int i = 0; i < 12; ++i)
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    S[(X4 + i * 4 + c) * 32] = make_float4(fmaf(dt, J[i * 12 + 4 * c + 0], (i == 4 * c + 0) ? 1.f : 0.f),
-                                                          fmaf(dt, J[i * 12 + 4 * c + 1], (i == 4 * c + 1) ? 1.f : 0.f),
-                                                          fmaf(dt, J[i * 12 + 4 * c + 2], (i == 4 * c + 2) ? 1.f : 0.f),
-                                                          fmaf(dt, J[i * 12 + 4 * c + 3], (i == 4 * c + 3) ? 1.f : 0.f));
+                    S[(X4 + i * 4 + c) * 32] = make_float4(Am[i * 12 + 4 * c + 0], Am[i * 12 + 4 * c + 1], Am[i * 12 + 4 * c + 2], Am[i * 12 + 4 * c + 3]);
         }
         // ---- Riccati sweep from Qf; only the last gain (k = 0) is needed ----
         float v[78];
@@ -570,13 +566,7 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_mpc_closed_loop_quad(Clos
             ua[a] = ut[a] + u[a];
         }
         if (active) uS[t] = make_float4(u[0], u[1], u[2], u[3]);
-        {
-            float xd[12];
-            QuadTrig<float> tr = quad_trig(x);
-            quad_xdot(tr, x, ua, xd);
-#pragma unroll
-            for (int i = 0; i < 12; ++i) x[i] = fmaf(dt, xd[i], x[i]);
-        }
+        closed_loop_plant(x, ua, dt);
     }
     if (active) {
         xS[(long long)P.Tsim * 3 + 0] = make_float4(x[0], x[1], x[2], x[3]);

@@ -13,9 +13,12 @@
 // lane-step instead of ~700 loaded words per thread-step in the 4-thread kernel.
 // The quadcopter's f_u = dt [e2 -> -1; e3, e4, e5 -> +1] (zopt/quadcopter.py:116-144) makes B'(.) a scaled row selection:
 //     G = R + s s' o V[2..5, 2..5],  M = s o W[2..5, :]      (s = (-dt, dt, dt, dt))
-// which is exactly what the thread-per-problem kernel's FMA chains evaluate (products with B's zeros are exact zeros), so
-// the arithmetic -- operation order included -- is the one of t1::riccati_step and the two variants agree bit for bit;
-// V stays exactly symmetric ("lower triangle wins", the upper tiles are mirrored copies).
+// and the scaling can be taken out of the loop altogether: with S = diag(s), G = S (S^-1 R S^-1 + V[2..5,2..5]) S and
+// M = S W[2..5,:], so L = S^-1 Lt with Lt = Gt^-1 Mt (Gt = Rt + V[2..5,2..5], Rt = S^-1 R S^-1 once per problem,
+// Mt = W[2..5,:]) and M'L = Mt'Lt: no multiplication by s in the sweep, only the applied control is rescaled.
+// V stays exactly symmetric ("lower triangle wins", the upper tiles are mirrored copies).  Same algebra as
+// t1::riccati_step; the two kernels agree to rounding (tests: 1e-5 on 40 closed-loop steps, model evaluated by the same
+// instruction sequence in both, t1_common.cuh).
 // Reference loop: demos/lqrMpc.py:42-47 around zopt/mpcUtils.py:47-59 with inactive bounds; step: zopt/lqrUtils.py:167-170.
 #pragma once
 #include "t1_common.cuh"
@@ -27,10 +30,18 @@ namespace w9 {
 constexpr int SV = 164;  // floats per problem in the V slab (12 rows of 12 + a 4-float pad after every 4 rows = 152; 164 = 4 mod 32)
 constexpr int SW = 172;  // floats per problem in the W slab (144; 172 = 12 mod 32): see the bank notes at the loads
 __host__ __device__ constexpr int vrow(int i) { return i * 12 + (i / 4) * 4; }  // offset of row i in the V slab
+// 1/sqrt of a Cholesky pivot: the pivots are O(R + dt^2 V) > 0 and far from the subnormal range, so the bare MUFU.RSQ
+// (2 ulp) replaces rsqrtf()'s range-checked sequence (5 instructions on the sweep's critical path)
+__device__ __forceinline__ float rsq(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP P) {
     __shared__ __align__(16) float sV[3 * SV];
     __shared__ __align__(16) float sW[3 * SW];
+    __shared__ __align__(16) float sS[3 * 3 * 48];  // scratch tiles of the redundant upper lanes
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x;
     const bool writer = lane < 27;           // lanes 27..31 shadow lane 26 and never store
@@ -43,8 +54,13 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
     const long long b = active ? b_raw : P.Bsz - 1;
     float* Vs = sV + g * SV;
     float* Ws = sW + g * SW;
+    // store targets, fixed for the kernel: own W tile; own V tile and its transpose, or a scratch tile for the redundant r < c lanes
+    float* const Wdst = Ws + (4 * r) * 12 + 4 * c;
+    const bool diag_tile = (r == c);
+    float* const Vdst = (r >= c) ? Vs + vrow(4 * r) + 4 * c : sS + (g * 3 + (r + c - 1)) * 48;
+    float* const Vdst_t = (r >= c) ? Vs + vrow(4 * c) + 4 * r : sS + (g * 3 + (r + c - 1)) * 48;
     const float dt = P.dt;
-    const float s4[4] = {-dt, dt, dt, dt};   // f_u = dt dF/du: rows 2..5, one entry each
+    const float is4[4] = {-1.f / dt, 1.f / dt, 1.f / dt, 1.f / dt};  // 1/s: f_u = dt dF/du has one entry in each of rows 2..5
 
     // ---- constant operands: this lane's tile of Q (lower triangle of Q wins, as t1::riccati_step reads it), R lower ----
     float Qt[4][4], Rl[10];
@@ -61,7 +77,7 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int cc = 0; cc <= a; ++cc) Rl[t1::tri(a, cc)] = __ldg(gR + a * 4 + cc);
+            for (int cc = 0; cc <= a; ++cc) Rl[t1::tri(a, cc)] = __ldg(gR + a * 4 + cc) * (is4[a] * is4[cc]);  // Rt = S^-1 R S^-1
     }
     float x[12];
     {
@@ -86,19 +102,13 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
         //      write the same values to the (free) W slab, then each reads the two column blocks it multiplies with ----
         float Ac[12][4], Ar[12][4];
         {
-            float J[144];
-            QuadTrig<float> tr = quad_trig(x);
-            quad_jac_x(tr, x, ut, J);
-            if (writer) {
+            float Am[144];
+            t1::closed_loop_linearize(x, ut, dt, Am);
 #pragma unroll
-                for (int i = 0; i < 12; ++i)
+            for (int i = 0; i < 12; ++i)
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch)
-                        sts4(Ws + i * 12 + 4 * ch, fmaf(dt, J[i * 12 + 4 * ch + 0], (i == 4 * ch + 0) ? 1.f : 0.f),
-                             fmaf(dt, J[i * 12 + 4 * ch + 1], (i == 4 * ch + 1) ? 1.f : 0.f),
-                             fmaf(dt, J[i * 12 + 4 * ch + 2], (i == 4 * ch + 2) ? 1.f : 0.f),
-                             fmaf(dt, J[i * 12 + 4 * ch + 3], (i == 4 * ch + 3) ? 1.f : 0.f));
-            }
+                for (int ch = 0; ch < 3; ++ch)
+                    sts4(Ws + i * 12 + 4 * ch, Am[i * 12 + 4 * ch + 0], Am[i * 12 + 4 * ch + 1], Am[i * 12 + 4 * ch + 2], Am[i * 12 + 4 * ch + 3]);
         }
         __syncwarp();
 #pragma unroll
@@ -120,75 +130,73 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
                     Vr[i][k] = (gi >= k) ? __ldg(gF + gi * 12 + k) : __ldg(gF + k * 12 + gi);
                 }
         }
-        float Lc[4][4];  // gain tile L[:, 4c..4c+3] of the last step
+        float Lc[4][4];  // gain tile Lt[:, 4c..4c+3] of the last step
+        // Gt = Rt + V[2..5, 2..5] (lower triangle), carried across the steps: re-read with the lane's rows after every exchange
+        float G[10];
+        {
+            const float* gF = P.Qf.at<float>(b);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int cc = 0; cc <= a; ++cc) G[t1::tri(a, cc)] = __ldg(gF + (2 + a) * 12 + 2 + cc) + Rl[t1::tri(a, cc)];
+        }
 #pragma unroll 1
         for (int k = P.N - 1; k >= 0; --k) {
-            // ---- G = R + B'VB = R + s s' o V[2..5, 2..5]: rows 2,3 live in the problem's lane (0,0), rows 4,5 in lane (1,0) ----
-            float G[10];
-            {
-                const float v22 = __shfl_sync(FULL, Vr[2][2], base), v32 = __shfl_sync(FULL, Vr[3][2], base), v33 = __shfl_sync(FULL, Vr[3][3], base);
-                const float v42 = __shfl_sync(FULL, Vr[0][2], base + 3), v43 = __shfl_sync(FULL, Vr[0][3], base + 3), v44 = __shfl_sync(FULL, Vr[0][4], base + 3);
-                const float v52 = __shfl_sync(FULL, Vr[1][2], base + 3), v53 = __shfl_sync(FULL, Vr[1][3], base + 3), v54 = __shfl_sync(FULL, Vr[1][4], base + 3),
-                            v55 = __shfl_sync(FULL, Vr[1][5], base + 3);
-                const float vv[10] = {v22, v32, v33, v42, v43, v44, v52, v53, v54, v55};
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int cc = 0; cc <= a; ++cc)  // same rounding as the FMA chains of t1::riccati_step: (V s_c) first, then s_a (.) + R
-                        G[t1::tri(a, cc)] = fmaf(s4[a], __fmul_rn(vv[t1::tri(a, cc)], s4[cc]), Rl[t1::tri(a, cc)]);
-            }
-            // ---- 1. W tile = Vr Ac ----
-            float Wt[4][4];
+            // ---- 1. W tile = Vr Ac: two independent accumulator sets (even / odd k) = 16 FFMA2 chains in flight ----
+            float W0[4][4], W1[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) Wt[i][j] = 0.f;
+                for (int j = 0; j < 4; ++j) W0[i][j] = W1[i][j] = 0.f;
 #pragma unroll
-            for (int kk = 0; kk < 12; ++kk)
+            for (int kk = 0; kk < 12; kk += 2)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    t1::fma2(Wt[i][0], Wt[i][1], Vr[i][kk], Ac[kk][0], Ac[kk][1]);
-                    t1::fma2(Wt[i][2], Wt[i][3], Vr[i][kk], Ac[kk][2], Ac[kk][3]);
+                    t1::fma2(W0[i][0], W0[i][1], Vr[i][kk], Ac[kk][0], Ac[kk][1]);
+                    t1::fma2(W0[i][2], W0[i][3], Vr[i][kk], Ac[kk][2], Ac[kk][3]);
+                    t1::fma2(W1[i][0], W1[i][1], Vr[i][kk + 1], Ac[kk + 1][0], Ac[kk + 1][1]);
+                    t1::fma2(W1[i][2], W1[i][3], Vr[i][kk + 1], Ac[kk + 1][2], Ac[kk + 1][3]);
                 }
-            if (writer) {
+            // (lanes 27..31 shadow lane 26: same operands, same values, same address -- no predicate, no divergence)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) sts4(Ws + (4 * r + i) * 12 + 4 * c, Wt[i][0], Wt[i][1], Wt[i][2], Wt[i][3]);
-            }
-            // ---- 2. Cholesky G = C C^T (overlaps the exchange) ----
-            const float d0 = rsqrtf(G[0]);
+            for (int i = 0; i < 4; ++i)
+                sts4(Wdst + i * 12, W0[i][0] + W1[i][0], W0[i][1] + W1[i][1], W0[i][2] + W1[i][2], W0[i][3] + W1[i][3]);
+            // ---- 2. Cholesky Gt = C C^T (overlaps the exchange) ----
+            const float d0 = rsq(G[0]);
             const float c10 = G[1] * d0, c20 = G[3] * d0, c30 = G[6] * d0;
-            const float d1 = rsqrtf(fmaf(-c10, c10, G[2]));
+            const float d1 = rsq(fmaf(-c10, c10, G[2]));
             const float c21 = fmaf(-c20, c10, G[4]) * d1, c31 = fmaf(-c30, c10, G[7]) * d1;
-            const float d2 = rsqrtf(fmaf(-c21, c21, fmaf(-c20, c20, G[5])));
+            const float d2 = rsq(fmaf(-c21, c21, fmaf(-c20, c20, G[5])));
             const float c32 = fmaf(-c31, c21, fmaf(-c30, c20, G[8])) * d2;
-            const float d3 = rsqrtf(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
+            const float d3 = rsq(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
             __syncwarp();
-            // ---- 3. V' tile = Q + Ar^T Wc - Mr^T Lc ----
+            // ---- 3. V' tile = Q + Ar^T Wc - Mr^T Lc, again as two accumulator sets ----
             // (lanes of one problem read 3 distinct 16 B segments at 0/16/32 B; neighbouring problems are 12 banks apart)
-            float Vt[4][4], Mc[4][4];
+            float V0[4][4], V1[4][4], Mc[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) Vt[i][j] = Qt[i][j];
+                for (int j = 0; j < 4; ++j) { V0[i][j] = Qt[i][j]; V1[i][j] = 0.f; }
 #pragma unroll
-            for (int kk = 0; kk < 12; ++kk) {
-                const float4 w4 = lds4(Ws + kk * 12 + 4 * c);
-                if (kk >= 2 && kk < 6) {  // rows 2..5 of W: M[:, 4c..] = s o W[2..5, 4c..]
-                    Mc[kk - 2][0] = __fmul_rn(s4[kk - 2], w4.x); Mc[kk - 2][1] = __fmul_rn(s4[kk - 2], w4.y);
-                    Mc[kk - 2][2] = __fmul_rn(s4[kk - 2], w4.z); Mc[kk - 2][3] = __fmul_rn(s4[kk - 2], w4.w);
+            for (int kk = 0; kk < 12; kk += 2) {
+                const float4 w4 = lds4(Ws + kk * 12 + 4 * c), w5 = lds4(Ws + (kk + 1) * 12 + 4 * c);
+                if (kk >= 2 && kk < 6) {  // rows 2..5 of W: Mt[:, 4c..]
+                    Mc[kk - 2][0] = w4.x; Mc[kk - 2][1] = w4.y; Mc[kk - 2][2] = w4.z; Mc[kk - 2][3] = w4.w;
+                    Mc[kk - 1][0] = w5.x; Mc[kk - 1][1] = w5.y; Mc[kk - 1][2] = w5.z; Mc[kk - 1][3] = w5.w;
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    t1::fma2(Vt[i][0], Vt[i][1], Ar[kk][i], w4.x, w4.y);
-                    t1::fma2(Vt[i][2], Vt[i][3], Ar[kk][i], w4.z, w4.w);
+                    t1::fma2(V0[i][0], V0[i][1], Ar[kk][i], w4.x, w4.y);
+                    t1::fma2(V0[i][2], V0[i][3], Ar[kk][i], w4.z, w4.w);
+                    t1::fma2(V1[i][0], V1[i][1], Ar[kk + 1][i], w5.x, w5.y);
+                    t1::fma2(V1[i][2], V1[i][3], Ar[kk + 1][i], w5.z, w5.w);
                 }
             }
-            float Mr[4][4];  // M[:, 4r..4r+3]
+            float Mr[4][4];  // Mt[:, 4r..4r+3]
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const float4 w4 = lds4(Ws + (2 + a) * 12 + 4 * r);
-                Mr[a][0] = __fmul_rn(s4[a], w4.x); Mr[a][1] = __fmul_rn(s4[a], w4.y);
-                Mr[a][2] = __fmul_rn(s4[a], w4.z); Mr[a][3] = __fmul_rn(s4[a], w4.w);
+                Mr[a][0] = w4.x; Mr[a][1] = w4.y; Mr[a][2] = w4.z; Mr[a][3] = w4.w;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -203,32 +211,41 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
                 Lc[0][j] = x0; Lc[1][j] = x1; Lc[2][j] = x2; Lc[3][j] = x3;
             }
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int i = 0; i < 4; ++i) {
+                t1::fma2(V0[i][0], V0[i][1], -Mr[0][i], Lc[0][0], Lc[0][1]);
+                t1::fma2(V0[i][2], V0[i][3], -Mr[0][i], Lc[0][2], Lc[0][3]);
+                t1::fma2(V1[i][0], V1[i][1], -Mr[1][i], Lc[1][0], Lc[1][1]);
+                t1::fma2(V1[i][2], V1[i][3], -Mr[1][i], Lc[1][2], Lc[1][3]);
+            }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    t1::fma2(Vt[i][0], Vt[i][1], -Mr[a][i], Lc[a][0], Lc[a][1]);
-                    t1::fma2(Vt[i][2], Vt[i][3], -Mr[a][i], Lc[a][2], Lc[a][3]);
+            for (int i = 0; i < 4; ++i) {
+                t1::fma2(V0[i][0], V0[i][1], -Mr[2][i], Lc[2][0], Lc[2][1]);
+                t1::fma2(V0[i][2], V0[i][3], -Mr[2][i], Lc[2][2], Lc[2][3]);
+                t1::fma2(V1[i][0], V1[i][1], -Mr[3][i], Lc[3][0], Lc[3][1]);
+                t1::fma2(V1[i][2], V1[i][3], -Mr[3][i], Lc[3][2], Lc[3][3]);
+            }
+            float Vt[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) Vt[i][j] = V0[i][j] + V1[i][j];
+            // ---- 4. write back, lower triangle wins, without divergence: tiles r > c store themselves and their transpose
+            //      (= tile (c,r)); diagonal tiles store their symmetrised self twice (same values, same place); tiles r < c are
+            //      redundant copies and go to a scratch slab ----
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float e[4], et[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    e[j] = (diag_tile && i < j) ? Vt[j][i] : Vt[i][j];
+                    et[j] = (diag_tile && i > j) ? Vt[i][j] : Vt[j][i];
                 }
-            // ---- 4. write back, lower triangle wins: tile (r,c) with r > c also stores its transpose as tile (c,r) ----
-            if (writer) {
-                if (r > c) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        sts4(Vs + vrow(4 * r + i) + 4 * c, Vt[i][0], Vt[i][1], Vt[i][2], Vt[i][3]);
-                        sts4(Vs + vrow(4 * c + i) + 4 * r, Vt[0][i], Vt[1][i], Vt[2][i], Vt[3][i]);
-                    }
-                } else if (r == c) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float e[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) e[j] = (i >= j) ? Vt[i][j] : Vt[j][i];
-                        sts4(Vs + vrow(4 * r + i) + 4 * r, e[0], e[1], e[2], e[3]);
-                    }
-                }
+                sts4(Vdst + i * 12, e[0], e[1], e[2], e[3]);
+                sts4(Vdst_t + i * 12, et[0], et[1], et[2], et[3]);
             }
             __syncwarp();
-            // ---- 5. this lane's rows of the new V (3 distinct row blocks per problem, 20 banks apart; problems 4 banks apart) ----
+            // ---- 5. this lane's rows of the new V (3 distinct row blocks per problem, 20 banks apart; problems 4 banks apart)
+            //      and the block V[2..5, 2..5] of the next step's Gt (six 64-bit broadcast loads) ----
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -236,6 +253,13 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
                     const float4 v4 = lds4(Vs + vrow(4 * r + i) + 4 * ch);
                     Vr[i][4 * ch + 0] = v4.x; Vr[i][4 * ch + 1] = v4.y; Vr[i][4 * ch + 2] = v4.z; Vr[i][4 * ch + 3] = v4.w;
                 }
+            {
+                const float2 g2 = *reinterpret_cast<const float2*>(Vs + vrow(2) + 2), g3 = *reinterpret_cast<const float2*>(Vs + vrow(3) + 2);
+                const float2 g4a = *reinterpret_cast<const float2*>(Vs + vrow(4) + 2), g4b = *reinterpret_cast<const float2*>(Vs + vrow(4) + 4);
+                const float2 g5a = *reinterpret_cast<const float2*>(Vs + vrow(5) + 2), g5b = *reinterpret_cast<const float2*>(Vs + vrow(5) + 4);
+                G[0] = g2.x + Rl[0]; G[1] = g3.x + Rl[1]; G[2] = g3.y + Rl[2]; G[3] = g4a.x + Rl[3]; G[4] = g4a.y + Rl[4];
+                G[5] = g4b.x + Rl[5]; G[6] = g5a.x + Rl[6]; G[7] = g5a.y + Rl[7]; G[8] = g5b.x + Rl[8]; G[9] = g5b.y + Rl[9];
+            }
         }
         // ---- u_t = -L_0 x_t: gather the three gain tiles from the problem's lanes (0,0), (0,1), (0,2) ----
         float u[4], ua[4];
@@ -252,18 +276,12 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
                 float s = 0.f;
 #pragma unroll
                 for (int j = 0; j < 12; ++j) s = fmaf(Lf[a][j], x[j], s);
-                u[a] = -s;
+                u[a] = -s * is4[a];  // L = S^-1 Lt
                 ua[a] = ut[a] + u[a];
             }
         }
         if (out_lane) uS[ts] = make_float4(u[0], u[1], u[2], u[3]);
-        {
-            float xd[12];
-            QuadTrig<float> tr = quad_trig(x);
-            quad_xdot(tr, x, ua, xd);
-#pragma unroll
-            for (int i = 0; i < 12; ++i) x[i] = fmaf(dt, xd[i], x[i]);
-        }
+        t1::closed_loop_plant(x, ua, dt);
     }
     if (out_lane) {
         xS[(long long)P.Tsim * 3 + 0] = make_float4(x[0], x[1], x[2], x[3]);

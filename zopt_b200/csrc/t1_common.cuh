@@ -1,6 +1,7 @@
 // Helpers shared by the (12,4) fp32 kernels: packed-triangle indexing, packed FP32x2 FMA, closed-loop parameter block.
 #pragma once
 #include "lqr_fast.cuh"
+#include "quad_model_gen.cuh"
 
 namespace zb {
 namespace t1 {
@@ -47,6 +48,29 @@ struct ClosedLoopP {
     float* xSim;      // (Bsz,Tsim+1,12)
     float* uSim;      // (Bsz,Tsim,4)  applied deviation u_t (the control sent to the plant is u_trim + u_t)
 };
+
+// Model evaluations of the closed-loop kernels.  The thread-per-problem kernel (lqr_t1.cuh) and the nine-lane kernel
+// (mpc_warp.cuh) perform the same operations in the same order and are tested to agree BIT FOR BIT; that only holds if both
+// evaluate the generated model expressions with the same instruction sequence.  Inlined, the compiler's FMA contraction of
+// sums of products depends on the surrounding code, so these two are real calls (once per simulation step, against 50
+// Riccati steps: the call and the trip of 144 words through local memory are noise).
+static __device__ __noinline__ void closed_loop_linearize(const float* __restrict__ x, const float* __restrict__ ut, float dt,
+                                                          float* __restrict__ A) {  // A = I + dt dF/dx(x, ut), row-major 12x12
+    float J[144];
+    QuadTrig<float> tr = quad_trig(x);
+    quad_jac_x(tr, x, ut, J);
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+#pragma unroll
+        for (int j = 0; j < 12; ++j) A[i * 12 + j] = fmaf(dt, J[i * 12 + j], (i == j) ? 1.f : 0.f);
+}
+static __device__ __noinline__ void closed_loop_plant(float* __restrict__ x, const float* __restrict__ ua, float dt) {  // x <- x + dt F(x, ua)
+    float xd[12];
+    QuadTrig<float> tr = quad_trig(x);
+    quad_xdot(tr, x, ua, xd);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) x[i] = fmaf(dt, xd[i], x[i]);
+}
 
 }  // namespace t1
 }  // namespace zb
