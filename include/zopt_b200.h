@@ -80,6 +80,13 @@ ZB_API int32_t zb_lqr_dfh(int32_t dtype, int32_t device, void* stream, int64_t B
                    int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, void* L_out,
                    void* V0_out);
 
+/* Same with flags: ZB_FORCE_GENERIC = take the generic kernel, which uses Q and R exactly as given (the (12,4) kernels read
+ * only the lower triangle of the symmetric weights; the Python mirror passes this flag when a weight is not symmetric, so
+ * that results equal the reference's for any input, lqrUtils.py:168-169). */
+ZB_API int32_t zb_lqr_dfh_flags(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
+                         int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, int32_t flags,
+                         void* L_out, void* V0_out);
+
 /* ---- zopt/lqrUtils.py:207-262  bilinearAffineLqr(A,B,d,Q,R,H,q,r,q0,N) -> (L,l) ------------------
  * L_out (Bsz,N,m,n), l_out (Bsz,N,m). */
 ZB_API int32_t zb_lqr_bilinear(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
@@ -167,6 +174,7 @@ ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_
 #define ZB_VARIANT_THREAD 4 /* zb_mpc_closed_loop_quad, zb_mpc_box_*: force the thread-per-problem kernel */
 #define ZB_VARIANT_QUAD 8   /* ... force the 4-threads-per-problem kernel (default for small batches) */
 #define ZB_VARIANT_WARP 64  /* zb_mpc_closed_loop_quad (fp32): force the nine-lanes-per-problem register-tiled kernel (default for the smallest batches) */
+#define ZB_FORCE_GENERIC 128 /* zb_lqr_dfh_flags, zb_mpc_lqr_solve: use the generic kernels (weights taken as given, not assumed symmetric) */
 #define ZB_GENERIC_FORWARD 32 /* zb_ilqr_solve: force the two-kernel line search (k_forward_costs + k_forward_commit) instead of the fused quadcopter kernel */
 #define ZB_BOX_STATE_GLOBAL 16 /* zb_mpc_box_*: keep the 4-threads-per-problem kernel's ADMM state in the global workspace even when it would fit on chip */
 

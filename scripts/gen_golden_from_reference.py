@@ -207,7 +207,21 @@ if os.environ.get("GOLDEN_FULL_SIZE", "1") == "1":
                                         ("ddp_cfg5_N100_it10", ref_ilqr.differentialDynamicProgramming, configs.cfg5, 100, 4)):
         dd = cfg(Bsz=nprob, N=N)
         recs = [run_solver_logged(solver, dd["x0"][i], N, dd["R"], 10) for i in range(nprob)]
-        np.savez_compressed(os.path.join(OUT, name + ".npz"), x0=dd["x0"], R=dd["R"], N=N, maxIter=10,
+        # step-size indices: the reference does not return them; they are taken from the oracle restatement AFTER checking that
+        # its cost after every iteration equals the reference's (so every argmin of ilqrUtils.py:147-149 fell on the same index)
+        from oracle import ilqr as oilqr
+        from oracle.quadcopter import Quadcopter as OQ
+        Qt_, Rt_ = T(np.eye(12)), T(dd["R"])
+        osolver = oilqr.differentialDynamicProgramming if "ddp" in name else oilqr.iterativeLqr
+        alphas = []
+        for i in range(nprob):
+            olog = []
+            osolver(OQ().eulerStep(dt), lambda x, u: x @ Qt_ @ x + u @ Rt_ @ u, lambda x: 10 * x @ Qt_ @ x, T(dd["x0"][i]),
+                    T(np.repeat(configs.U_TRIM[None], N, axis=0)), maxIter=10, tol=-1.0, log=olog)
+            Jo = np.array([e["J"] for e in olog])
+            assert np.max(np.abs(Jo - recs[i]["J_per_iter"]) / recs[i]["J_per_iter"]) < 1e-11, (name, i)
+            alphas.append([e["alpha_idx"] for e in olog[1:]])
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), x0=dd["x0"], R=dd["R"], N=N, maxIter=10, alpha_idx=np.array(alphas),
                             J_per_iter=np.array([r["J_per_iter"] for r in recs]), xTraj=np.array([r["xTraj"] for r in recs]),
                             uTraj=np.array([r["uTraj"] for r in recs]), L=np.array([r["L"] for r in recs]))
         print(name, np.array([r["J_per_iter"] for r in recs])[:, [0, 1, -1]])

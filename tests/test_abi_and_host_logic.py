@@ -128,3 +128,35 @@ def test_quadcopter_jacobian_structure_table_matches_generated_model():
     assert [int(c) for r in rows for c in r] == [kind[i] for i in range(144)]
     # 17 of the 36 four-column chunks vary along a trajectory (the count the kernel's comments and DESIGN.md quote)
     assert sum(any(kind[i * 12 + 4 * q + c] == 2 for c in range(4)) for i in range(12) for q in range(3)) == 17
+
+
+def test_batch_and_shape_validation_host_side():
+    """every batched operand is shared (1) or carries exactly Bsz problems, and block shapes are checked against
+    (n, m), before a raw pointer can reach a kernel (pure host logic, no device needed)."""
+    from zopt_b200.models import LinearDynamics, QuadraticCost, QuadraticTerminalCost, cost_batch, reconcile_batch
+    assert reconcile_batch(1, 8, 1, 8) == 8 and reconcile_batch(1, 1) == 1
+    with pytest.raises(ValueError):
+        reconcile_batch(8, 4)
+    rc, tc = QuadraticCost(np.zeros((4, 12, 12)), np.zeros((4, 4))), QuadraticTerminalCost(np.zeros((12, 12)))
+    assert cost_batch(rc, tc, 12, 4) == 4
+    with pytest.raises(ValueError):  # Q batched by 4, Qf by 8
+        cost_batch(rc, QuadraticTerminalCost(np.zeros((8, 12, 12))), 12, 4)
+    with pytest.raises(ValueError):  # R is not (m, m)
+        cost_batch(QuadraticCost(np.zeros((12, 12)), np.zeros((3, 3))), tc, 12, 4)
+    with pytest.raises(ValueError):  # Q is not (n, n) for the model
+        cost_batch(QuadraticCost(np.zeros((8, 8)), np.zeros((4, 4))), QuadraticTerminalCost(np.zeros((8, 8))), 12, 4)
+    assert LinearDynamics(np.zeros((5, 2, 2)), np.zeros((2, 1))).batch() == 5
+    with pytest.raises(ValueError):
+        LinearDynamics(np.zeros((5, 2, 2)), np.zeros((3, 2, 1)))
+    with pytest.raises(ValueError):
+        LinearDynamics(np.zeros((2, 3)), np.zeros((2, 1)))
+
+
+def test_hostbind_helpers_without_gpu():
+    """zopt_b200.hostbind: cpulist parsing and the topology record of the bench (pure host logic)"""
+    from zopt_b200 import hostbind
+    assert hostbind._parse_cpulist("0-3,8,10-11") == {0, 1, 2, 3, 8, 10, 11} and hostbind._parse_cpulist("") == set()
+    topo = hostbind.host_topology()
+    assert topo["cpus_allowed"] >= 1 and topo["cpu_count"] >= topo["cpus_allowed"]
+    info = hostbind.bind_to_gpu(0, enable=False)
+    assert info["bound"] is False and info["how"] == "unbound"

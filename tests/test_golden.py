@@ -83,6 +83,46 @@ def test_oracle_solver_goldens(name):
     assert relerr(traj.xTraj, g["xTraj"]) < 1e-10 and relerr(traj.uTraj, g["uTraj"]) < 1e-10 and relerr(L, g["L"]) < 1e-10
 
 
+
+def _sim_blocks_a(g, mod, conv=lambda a: a):
+    """demos/iterativeLqr.py:44-56: tracking controller on the plant in wind [3,1,0]; blocks as plain callables"""
+    oac = OQuadcopter()
+    dt, wind = float(g["a_dt"]), g["a_wind"]
+    L, xT, uT = g["a_L"], g["a_xTraj"], g["a_uTraj"]
+    dyn = mod.SimBlock(lambda k, x, u: (None, x + dt * oac.inertialDynamics(T(x), T(u), T(wind)).numpy()), g["a_x0"], dt=dt)
+    ctrl = mod.SimBlock(lambda k, xc, x: (L[k] @ (x - xT[k]) + uT[k], np.array([])), np.array([]), dt=dt)
+    return [ctrl, dyn], (0, L.shape[0] * dt)
+
+
+def test_oracle_simulator_goldens():
+    """oracle/simulator.py against the reference's own Simulator (zopt/simulator.py:124-169, run unmodified on the shim) on
+    the two closed loops of the demos (demos/iterativeLqr.py:44-56, demos/discreteFiniteHorizonLqr.py:38-49)."""
+    from oracle import simulator as osim
+    g = load("simulator_demos.npz")
+    blocks, span = _sim_blocks_a(g, osim)
+    t, x0A, xA, uA, _ = osim.Simulator(blocks, span).simulate()
+    assert np.allclose(t, g["a_t"]) and relerr(xA, g["a_x"]) < 1e-12 and relerr(uA, g["a_u"]) < 1e-12 and x0A.shape == (len(t), 0)
+    oac = OQuadcopter()
+    K, uTrim, dt = g["b_K"], g["b_uTrim"], 0.1
+    dyn = osim.SimBlock(lambda k, x, u: (None, x + dt * oac.inertialDynamics(T(x), T(u)).numpy()), g["b_x0"], dt=dt)
+    ctrl = osim.SimBlock(lambda k, xc, x: (-K[k] @ (x[:8] - np.zeros(8)) + uTrim, np.array([])), np.array([]), dt=dt)
+    t, _, xB, uB, _ = osim.Simulator([ctrl, dyn], (0, 10)).simulate()
+    assert np.allclose(t, g["b_t"]) and relerr(xB, g["b_x"]) < 1e-12 and relerr(uB, g["b_u"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["ilqr_cfg4_N200_it10.npz", "ddp_cfg5_N100_it10.npz"])
+def test_oracle_solver_goldens_bench_size(name):
+    """BASELINE cfg 4 / cfg 5 size (N = 200 / 100, 10 iterations): the oracle against the reference run on problem 0 --
+    cost after EVERY iteration, final trajectory and gains."""
+    g, ddp, dyn, rc, tc, N = _solver_golden(name)
+    log = []
+    solver = oilqr.differentialDynamicProgramming if ddp else oilqr.iterativeLqr
+    traj, L, J, conv = solver(dyn, rc, tc, T(g["x0"][0]), T(rep(configs.U_TRIM, N)), maxIter=10, tol=-1.0, log=log)
+    assert relerr(np.array([e["J"] for e in log]), g["J_per_iter"][0]) < 1e-11
+    assert [e["alpha_idx"] for e in log[1:]] == g["alpha_idx"][0].tolist()
+    assert relerr(traj.xTraj, g["xTraj"][0]) < 1e-9 and relerr(traj.uTraj, g["uTraj"][0]) < 1e-9 and relerr(L, g["L"][0]) < 1e-9
+
+
 def test_oracle_riccati_step_goldens():
     g = load("riccati_steps.npz")
     n = 5
@@ -168,3 +208,42 @@ def test_gpu_riccati_step_goldens():
     vo, p = ilqrUtils.riccatiStep_ddp(pytrees.QuadraticDynamics(np.zeros(n), g["f_x"], g["f_u"], g["f_xx"], g["f_ux"], g["f_uu"]), cost, val)
     assert relerr(vo.v_xx, g["ddp_vxx"]) < 1e-10 and relerr(p.L, g["ddp_L"]) < 1e-10 and relerr(p.l, g["ddp_l"]) < 1e-10
     assert relerr(ilqrUtils.ensurePositiveDefinite(g["S"]), g["S_pd"]) < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ilqr_cfg4_N200_it10.npz", "ddp_cfg5_N100_it10.npz"])
+def test_gpu_solver_goldens_bench_size(name):
+    """BASELINE cfg 4 / cfg 5 size (N = 200 / 100, 10 iterations, four problems of the configs' own distributions, one batched
+    call): cost after every iteration, the step-size index of every iteration, final x, u, L against the reference run."""
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    g, ddp, _, _, _, N = _solver_golden(name)
+    solver = ilqrUtils.differentialDynamicProgramming if ddp else ilqrUtils.iterativeLqr
+    traj, L, J, conv, log = solver(QuadcopterEuler(0.1), QuadraticCost(np.eye(12), g["R"]), QuadraticTerminalCost(10 * np.eye(12)),
+                                   g["x0"], rep(configs.U_TRIM, N), maxIter=10, tol=-1.0, return_log=True)
+    assert log["alpha_idx"].cpu().numpy().tolist() == g["alpha_idx"].tolist()
+    for b in range(g["x0"].shape[0]):
+        assert relerr(log["J"][b], g["J_per_iter"][b]) < 1e-10
+        assert relerr(traj.xTraj[b], g["xTraj"][b]) < 1e-9 and relerr(traj.uTraj[b], g["uTraj"][b]) < 1e-9 and relerr(L[b], g["L"][b]) < 1e-9
+        assert abs(float(J[b]) - g["J_per_iter"][b][-1]) < 1e-10 * g["J_per_iter"][b][-1]
+
+
+@pytest.mark.gpu
+def test_gpu_simulator_goldens():
+    """zopt_b200.simulator (one launch of the rollout kernel) against the reference's Simulator run unmodified on the shim:
+    the tracking controller in wind (demos/iterativeLqr.py:44-56) and the 8-state LQR gains on the 12-state plant
+    (demos/discreteFiniteHorizonLqr.py:38-49); reference shapes, fp64 1e-10."""
+    from zopt_b200.models import QuadcopterEuler
+    from zopt_b200.simulator import ProportionalFeedbackController, SimBlock, Simulator, TrackingController
+    g = load("simulator_demos.npz")
+    dt = float(g["a_dt"])
+    N = g["a_L"].shape[0]
+    sim = Simulator([SimBlock(TrackingController(g["a_xTraj"], g["a_uTraj"], g["a_L"]), np.array([]), dt=dt, name="Controller"),
+                     SimBlock(QuadcopterEuler(dt, g["a_wind"]), g["a_x0"], dt=dt, name="Dynamics")], (0, N * dt))
+    tS, x0A, xS, uS, _ = sim.simulate()
+    assert np.allclose(tS.cpu().numpy(), g["a_t"]) and xS.shape == g["a_x"].shape and uS.shape == g["a_u"].shape
+    assert relerr(xS, g["a_x"]) < 1e-10 and relerr(uS, g["a_u"]) < 1e-10
+    sim = Simulator([SimBlock(ProportionalFeedbackController(np.zeros(8), g["b_uTrim"], g["b_K"], ns=8), np.array([]), dt=0.1),
+                     SimBlock(QuadcopterEuler(0.1), g["b_x0"], dt=0.1)], (0, 10))
+    tS, _, xS, uS, _ = sim.simulate()
+    assert np.allclose(tS.cpu().numpy(), g["b_t"]) and relerr(xS, g["b_x"]) < 1e-10 and relerr(uS, g["b_u"]) < 1e-10

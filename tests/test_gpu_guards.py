@@ -121,3 +121,69 @@ def test_ilqr_solve_guards(second_order, dt):
     torch.cuda.synchronize()
     assert all(g.ok() for g in (xT, uT, L, J, conv, ws))
     assert torch.isfinite(xT.t).all() and torch.isfinite(L.t).all() and (iters == maxIter).all()
+
+
+def test_python_mirror_rejects_inconsistent_batches_and_shapes():
+    """operands whose batch size is neither 1 nor Bsz, short time axes and wrong block shapes raise ValueError in
+    the Python mirror instead of reaching a kernel as an out-of-bounds read."""
+    import numpy as np
+    import torch
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.lqrUtils import bilinearAffineLqr
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    from zopt_b200.mpcUtils import lqrMpc, quadcopterClosedLoopMpc
+    x0 = torch.zeros((8, 12), dtype=torch.float64, device="cuda")
+    uG = np.tile(np.array([9.807, 0, 0, 0]), (5, 1))
+    with pytest.raises(ValueError):  # x0 batch 8, Q batch 4
+        ilqrUtils.iterativeLqr(QuadcopterEuler(0.1), QuadraticCost(np.tile(np.eye(12), (4, 1, 1)), np.eye(4)), QuadraticTerminalCost(np.eye(12)),
+                               x0, uG, maxIter=1)
+    with pytest.raises(ValueError):  # R is 3x3
+        ilqrUtils.iterativeLqr(QuadcopterEuler(0.1), QuadraticCost(np.eye(12), np.eye(3)), QuadraticTerminalCost(np.eye(12)), x0, uG, maxIter=1)
+    n, m, N = 3, 2, 6
+    ops = dict(A=np.zeros((N, n, n)), B=np.zeros((N, n, m)), d=np.zeros((N, n)), Q=np.tile(np.eye(n), (N, 1, 1)), R=np.tile(np.eye(m), (N, 1, 1)),
+               H=np.zeros((N, m, n)), q=np.zeros((N, n)), r=np.zeros((N, m)), q0=np.zeros(N))
+    bilinearAffineLqr(*ops.values(), N)
+    for bad in ("A", "B", "d", "R", "H", "r"):  # time axis shorter than the horizon
+        o = dict(ops)
+        o[bad] = o[bad][:N - 2]
+        with pytest.raises(ValueError):
+            bilinearAffineLqr(*o.values(), N)
+    o = dict(ops)
+    o["H"] = np.zeros((N, n, m))  # transposed block
+    with pytest.raises(ValueError):
+        bilinearAffineLqr(*o.values(), N)
+    with pytest.raises(ValueError):  # x0 is not a 12-state
+        quadcopterClosedLoopMpc(torch.zeros((4, 8), device="cuda"), np.eye(12), np.eye(4), 5, 2)
+    with pytest.raises(ValueError):  # Q batch 3, x0 batch 4
+        quadcopterClosedLoopMpc(torch.zeros((4, 12), device="cuda"), np.tile(np.eye(12), (3, 1, 1)), np.eye(4), 5, 2)
+    tr = quadcopterClosedLoopMpc(np.zeros((2, 12)), np.eye(12), np.eye(4), 5, 2)  # NumPy float64 input -> fp64, like everywhere else
+    assert tr.xTraj.dtype == torch.float64
+    inf12, inf4 = np.full(12, np.inf), np.full(4, np.inf)
+    with pytest.raises(ValueError):
+        lqrMpc(np.eye(12), np.zeros((12, 4)), np.eye(12), np.eye(3), 5, -inf12, inf12, -inf4, inf4)
+    with pytest.raises(ValueError):
+        lqrMpc(np.eye(12), np.zeros((12, 4)), np.eye(12), np.eye(4), 5, -inf12, inf12, -inf4, inf4).solve(np.zeros(8))
+
+
+def test_non_symmetric_weights_take_the_generic_kernels():
+    """the (12,4) fast kernels read the lower triangle of Q, R; the reference uses the weights as given
+    (lqrUtils.py:168-169).  With a non-symmetric Q the Python mirror must select the generic kernel: gains equal the oracle's
+    as-written recursion, and differ from what the lower triangle alone would give."""
+    import numpy as np
+    import torch
+    from oracle import lqr as olqr
+    from oracle.quadcopter import Quadcopter as OQ
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    rng = np.random.default_rng(5)
+    N = 12
+    A, B = (t.numpy() for t in OQ().linearizeInertial(np.zeros(12), np.array([9.807, 0, 0, 0]), 0.1))
+    Q = np.eye(12) + 0.3 * np.triu(rng.normal(size=(12, 12)), 1)  # upper triangle only: invisible to a lower-triangle reader
+    R = np.eye(4)
+    rep = lambda M: np.tile(M[None], (N, 1, 1))
+    Lref = olqr.discreteFiniteHorizonLqr(rep(A), rep(B), rep(Q), rep(R), N)
+    Llow = olqr.discreteFiniteHorizonLqr(rep(A), rep(B), rep(np.tril(Q) + np.tril(Q, -1).T), rep(R), N)
+    assert np.max(np.abs(Lref - Llow)) > 1e-3
+    for dt, tol in ((torch.float64, 1e-10), (torch.float32, 2e-5)):
+        c = lambda M: torch.as_tensor(rep(M), dtype=dt, device="cuda")
+        L = discreteFiniteHorizonLqr(c(A), c(B), c(Q), c(R), N)
+        assert np.max(np.abs(L.double().cpu().numpy() - Lref)) < tol * np.max(np.abs(Lref))

@@ -48,6 +48,7 @@ SIGNATURES = {
     "zb_last_error": (_i32, [C.c_char_p, _sz]),
     "zb_device_info": (_i32, [_i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_sz)]),
     "zb_lqr_dfh": (_i32, [_i32, _i32, _P, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _AP, _AP, _P, _P]),
+    "zb_lqr_dfh_flags": (_i32, [_i32, _i32, _P, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _AP, _AP, _i32, _P, _P]),
     "zb_lqr_bilinear": (_i32, [_i32, _i32, _P, _i64, _i32, _i32, _i32, _i32] + [_AP] * 9 + [_P, _P]),
     "zb_quad_dynamics": (_i32, [_i32, _i32, _P, _i64, _P, _P, C.POINTER(_f64), _P]),
     "zb_quad_linearize": (_i32, [_i32, _i32, _P, _i64, _P, _P, C.POINTER(_f64), _f64, _P, _P]),
@@ -192,6 +193,29 @@ class View:
 
     def ref(self):
         return C.byref(self.arr)
+
+
+_FLAG_CACHE = {}
+
+
+def cached_matrix_flag(t, name, fn):
+    """A boolean property of a batch of matrices that needs a device->host read (exact diagonality, symmetry), cached by
+    tensor OBJECT identity (weak reference) and in-place version counter -- never by address, so a recycled allocation can
+    not produce a stale answer.  Re-building a problem around the same weights every MPC step costs nothing."""
+    import weakref
+    ent = _FLAG_CACHE.get((id(t), name))
+    if ent is not None and ent[0]() is t and ent[1] == t._version:
+        return ent[2]
+    if len(_FLAG_CACHE) > 512:
+        _FLAG_CACHE.clear()
+    res = bool(fn(t))
+    _FLAG_CACHE[(id(t), name)] = (weakref.ref(t), t._version, res)
+    return res
+
+
+def is_symmetric(t):
+    """exact symmetry of the trailing two axes (the (12,4) fast kernels read the lower triangle of the weights only)"""
+    return cached_matrix_flag(t, "sym", lambda a: bool((a - a.transpose(-1, -2)).abs().max() == 0) if a.numel() else True)
 
 
 def null_arr():

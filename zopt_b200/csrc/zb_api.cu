@@ -240,6 +240,12 @@ int32_t zb_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int
 int32_t zb_lqr_dfh(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
                    int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, void* L_out,
                    void* V0_out) {
+    return zb_lqr_dfh_flags(dtype, device, stream, Bsz, N, T, n, m, A, B, Q, R, 0, L_out, V0_out);
+}
+
+int32_t zb_lqr_dfh_flags(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
+                         int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, int32_t flags,
+                         void* L_out, void* V0_out) {
     int32_t rc = check_dims(dtype, Bsz, n, m);
     if (rc) return rc;
     if (Bsz == 0) return 0;  // empty batch: nothing to read or write (pointers may be NULL)
@@ -250,6 +256,10 @@ int32_t zb_lqr_dfh(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int
     DeviceGuard g(device);
     ZB_CUDA(g.err);
     LqrP P{Bsz, N, T, n, m, to_arr(A), to_arr(B), to_arr(Q), to_arr(R), L_out, V0_out};
+    if (flags & ZB_FORCE_GENERIC) {  // e.g. non-symmetric weights: the (12,4) kernels read the lower triangle only
+        ZB_DISPATCH(dtype, k_lqr_generic, gen_grid(Bsz), GEN_THREADS, stream, P);
+        return 0;
+    }
     // genuinely time-varying (12,4) fp32 problems: streamed thread-per-problem kernel (lqr_t1.cuh)
     if (dtype == ZB_F32 && n == 12 && m == 4 && N >= 2 && !lqr_fast_eligible(dtype, P) && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) &&
         arr_ok(P.R) && aligned16(P.L) && (!P.V0 || aligned16(P.V0))) {
@@ -571,7 +581,8 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
     }
     MpcP P{Bsz, N, n, m, to_arr(A), to_arr(B), to_arr(Q), to_arr(R), to_arr(Qf), x0, u0_out, xTraj, uTraj, workspace,
            status_out, iters_out};
-    if (dtype == ZB_F32 && n == 12 && m == 4 && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) && arr_ok(P.R) && arr_ok(P.Qf) &&
+    const bool fast_ok = !(flags & ZB_FORCE_GENERIC);
+    if (fast_ok && dtype == ZB_F32 && n == 12 && m == 4 && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) && arr_ok(P.R) && arr_ok(P.Qf) &&
         aligned16(x0) && aligned16(u0_out) && aligned16(xTraj) && aligned16(uTraj) && aligned16(workspace)) {
         FastP F{};
         F.Bsz = Bsz; F.N = N; F.T = 1;
@@ -586,7 +597,7 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
         F.iters = iters_out;
         return riccati_t1_launch<true>(F, (cudaStream_t)stream, (flags & ZB_COST_DIAGONAL) != 0);
     }
-    if (dtype == ZB_F64 && n == 12 && m == 4 && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) && arr_ok(P.R) && arr_ok(P.Qf) &&
+    if (fast_ok && dtype == ZB_F64 && n == 12 && m == 4 && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) && arr_ok(P.R) && arr_ok(P.Qf) &&
         aligned16(x0) && aligned16(u0_out) && aligned16(xTraj) && aligned16(uTraj) && aligned16(workspace)) {
         LqrQuadP F{};  // fp64: cooperative Riccati sweep (gains to the workspace) + quad plan rollout (lqr_quad64.cuh)
         F.Bsz = Bsz; F.N = N; F.T = 1;

@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import View, ZbArr, check, dcode, lib, null_arr, pick_device, pick_dtype, ptr, stream_ptr, to_dev
-from .models import cost_batch, cost_spec, require_cost, require_model
+from .models import cost_batch, cost_spec, reconcile_batch, require_cost, require_model
 from .pytrees import (AffineDynamics, AffinePolicy, CostFunction, QuadraticCostFunction, QuadraticDynamics,
                       QuadraticValueFunction, Trajectory)
 
@@ -51,12 +51,12 @@ def _rollout_args(x0, dynFun, policy, trajPrev, costFun):
     dtype = pick_dtype(x0, l, L, xPrev, uPrev)
     x0, l, L, xPrev, uPrev = (to_dev(t, dtype, device) for t in (x0, l, L, xPrev, uPrev))
     Bsz, any_b = _batch_of([x0, l, L, xPrev, uPrev], [1, 2, 3, 2, 2])
-    Bsz = max(Bsz, model.batch())
+    Bsz = reconcile_batch(Bsz, model.batch())  # every operand: shared, or exactly Bsz problems
     cspec, ckeep = None, None
     if costFun is not None:
         rc, tc = require_cost(*costFun)
-        Bsz = max(Bsz, cost_batch(rc, tc))
-        cspec, ckeep = cost_spec(rc, tc, dtype, device)
+        Bsz = reconcile_batch(Bsz, cost_batch(rc, tc, model.n, model.m))
+        cspec, ckeep = cost_spec(rc, tc, dtype, device, model.n, model.m)
     any_b = any_b or Bsz > 1
     x0, l, L, xPrev, uPrev = (_full(t, nd, Bsz) for t, nd in zip((x0, l, L, xPrev, uPrev), (1, 2, 3, 2, 2)))
     N, m = l.shape[1], l.shape[2]
@@ -231,14 +231,14 @@ def _solve(dynamics, runningCost, terminalCost, x0, uGuess, maxIter, tol, second
     dtype = pick_dtype(x0, uGuess)
     x0, uGuess = to_dev(x0, dtype, device), to_dev(uGuess, dtype, device)
     Bsz, any_b = _batch_of([x0, uGuess], [1, 2])
-    Bsz = max(Bsz, model.batch(), cost_batch(rc, tc))
+    Bsz = reconcile_batch(Bsz, model.batch(), cost_batch(rc, tc, model.n, model.m))  # shared (1) or exactly Bsz, nothing else
     any_b = any_b or Bsz > 1
     x0, uGuess = _full(x0, 1, Bsz), _full(uGuess, 2, Bsz)
     n, (N, m) = x0.shape[1], uGuess.shape[1:]
     if (n, m) != (model.n, model.m):
         raise ValueError(f"x0/uGuess dimensions ({n},{m}) do not match the model ({model.n},{model.m})")
     maxIter = int(maxIter)
-    cspec, ckeep = cost_spec(rc, tc, dtype, device)
+    cspec, ckeep = cost_spec(rc, tc, dtype, device, model.n, model.m)
     if getattr(model, "is_plugin", False):  # user-defined symbolic model: its own compiled solver library (plugin.py)
         xTraj, uTraj, L, J, conv, iters, alog, Jlog = model.solve(cspec, dtype, device, Bsz, N, x0, uGuess, maxIter, tol,
                                                                   second_order, return_log)

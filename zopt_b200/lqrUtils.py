@@ -7,7 +7,7 @@ Returns torch CUDA tensors; dtype follows the inputs (fp32 only when every input
 """
 import torch
 
-from ._lib import View, check, dcode, lib, pick_device, pick_dtype, ptr, stream_ptr, to_dev
+from ._lib import View, check, dcode, is_symmetric, lib, pick_device, pick_dtype, ptr, stream_ptr, to_dev
 
 
 def _prep(arrs, core_ndims):
@@ -42,7 +42,8 @@ def discreteFiniteHorizonLqr(A, B, Q, R, N, return_value=False):
         A : (T,n,n) or (Bsz,T,n,n), time along the axis before the matrix: `A[k]`
         B : (T,n,m) or (Bsz,T,n,m)
         Q : (T,n,n) or (Bsz,T,n,n); the terminal value is `Q[-1]` (lqrUtils.py:172)
-        R : (T,m,m) or (Bsz,T,m,m)
+        R : (T,m,m) or (Bsz,T,m,m); Q, R are used as given -- symmetric weights (the normal case) run on the fast
+            (12,4) kernels, non-symmetric ones on the generic kernel, with the reference's result either way
         N : horizon (T >= N)
 
     Returns
@@ -61,8 +62,11 @@ def discreteFiniteHorizonLqr(A, B, Q, R, N, return_value=False):
     vA, vB, vQ, vR = (View(t, 2, True, b) for t, b in zip((A, B, Q, R), batched))
     L = torch.empty((Bsz, N, m, n), dtype=dtype, device=device)
     V0 = torch.empty((Bsz, n, n), dtype=dtype, device=device) if return_value else None
-    check(lib.zb_lqr_dfh(dcode(dtype), device.index, stream_ptr(device), Bsz, N, T, n, m, vA.ref(), vB.ref(), vQ.ref(),
-                         vR.ref(), ptr(L), ptr(V0)))
+    # The (12,4) fast kernels keep the symmetric value matrix as a lower triangle and read the lower triangle of Q, R.  The
+    # reference uses the weights exactly as given (lqrUtils.py:168-169), so non-symmetric ones take the generic kernel.
+    flags = 0 if ((n, m) != (12, 4) or (is_symmetric(Q) and is_symmetric(R))) else 128  # ZB_FORCE_GENERIC
+    check(lib.zb_lqr_dfh_flags(dcode(dtype), device.index, stream_ptr(device), Bsz, N, T, n, m, vA.ref(), vB.ref(), vQ.ref(),
+                               vR.ref(), flags, ptr(L), ptr(V0)))
     if not any_b:
         L = L[0]
         V0 = V0[0] if return_value else None
@@ -87,6 +91,17 @@ def bilinearAffineLqr(A, B, d, Q, R, H, q, r, q0, N):
     T = Q.shape[-3]
     if q.shape[-2] != T or q0.shape[-1] != T:
         raise ValueError("Q, q and q0 must have the same time length (the initial carry is their last row)")
+    # every operand is indexed up to step N-1 by the kernel: time axes and block shapes are checked here, as for
+    # discreteFiniteHorizonLqr (the C entry point only sees T from Q)
+    want = {"A": (A, (n, n)), "B": (B, (n, m)), "d": (d, (n,)), "Q": (Q, (n, n)), "R": (R, (m, m)), "H": (H, (m, n)),
+            "q": (q, (n,)), "r": (r, (m,))}
+    for name, (t, blk) in want.items():
+        if tuple(t.shape[t.ndim - len(blk):]) != blk:
+            raise ValueError(f"{name}: expected blocks of shape {blk}, got {tuple(t.shape)}")
+        if t.shape[t.ndim - len(blk) - 1] < N:
+            raise ValueError(f"{name}: time axis ({t.shape[t.ndim - len(blk) - 1]}) shorter than the horizon N={N}")
+    if T < max(N, 1):
+        raise ValueError(f"time axis shorter than the horizon N={N}")
     blocks = [2, 2, 1, 2, 2, 2, 1, 1, 0]
     views = [View(t, k, True, b) for t, k, b in zip(ts, blocks, batched)]
     L = torch.empty((Bsz, N, m, n), dtype=dtype, device=device)

@@ -30,12 +30,38 @@ def _mat(x):
     return torch.as_tensor(np.asarray(x, dtype=np.float64))
 
 
+def _block_batch(t, shape, name):
+    """Batch size of an operand holding `shape` blocks: `shape` itself (shared by the batch -> 1) or one leading batch axis.
+    Anything else is rejected here, before a raw pointer reaches a kernel."""
+    shape = tuple(shape)
+    if tuple(t.shape) == shape:
+        return 1
+    if t.ndim == len(shape) + 1 and tuple(t.shape[1:]) == shape:
+        return int(t.shape[0])
+    raise ValueError(f"{name} must have shape {shape} or (Bsz,) + {shape}, got {tuple(t.shape)}")
+
+
+def reconcile_batch(*sizes):
+    """One batch size for a call: every operand is either shared (1) or carries exactly that many problems."""
+    Bsz = 1
+    for b in sizes:
+        b = int(b)
+        if b != 1:
+            if Bsz != 1 and Bsz != b:
+                raise ValueError(f"inconsistent batch sizes {Bsz} and {b}")
+            Bsz = b
+    return Bsz
+
+
 class LinearDynamics:
     """x+ = A x + B u; A (n,n) or (Bsz,n,n), B (n,m) or (Bsz,n,m)."""
 
     def __init__(self, A, B):
         self.A, self.B = _mat(A), _mat(B)
+        if self.B.ndim not in (2, 3) or self.A.ndim not in (2, 3):
+            raise ValueError(f"A must be (n,n) or (Bsz,n,n) and B (n,m) or (Bsz,n,m), got {tuple(self.A.shape)}, {tuple(self.B.shape)}")
         self.n, self.m = self.B.shape[-2], self.B.shape[-1]
+        self.batch()  # shapes and batch sizes are checked once, here
 
     def __call__(self, x, u):
         A, B = self.A.to(x), self.B.to(x)
@@ -50,7 +76,7 @@ class LinearDynamics:
         return M, (vA, vB)
 
     def batch(self):
-        return max(self.A.shape[0] if self.A.ndim == 3 else 1, self.B.shape[0] if self.B.ndim == 3 else 1)
+        return reconcile_batch(_block_batch(self.A, (self.n, self.n), "A"), _block_batch(self.B, (self.n, self.m), "B"))
 
 
 class QuadcopterEuler:
@@ -115,8 +141,9 @@ def require_cost(runningCost, terminalCost):
     return runningCost, terminalCost
 
 
-def cost_spec(runningCost, terminalCost, dtype, device):
+def cost_spec(runningCost, terminalCost, dtype, device, n=None, m=None):
     runningCost, terminalCost = require_cost(runningCost, terminalCost)
+    cost_batch(runningCost, terminalCost, n, m)
     Q, R, Qf = (to_dev(t, dtype, device) for t in (runningCost.Q, runningCost.R, terminalCost.Qf))
     views = [View(t, 2, False, t.ndim == 3) for t in (Q, R, Qf)]
     c = ZbCost()
@@ -124,8 +151,13 @@ def cost_spec(runningCost, terminalCost, dtype, device):
     return c, views
 
 
-def cost_batch(runningCost, terminalCost):
-    return max(t.shape[0] if t.ndim == 3 else 1 for t in (runningCost.Q, runningCost.R, terminalCost.Qf))
+def cost_batch(runningCost, terminalCost, n=None, m=None):
+    """Batch size of the cost operands; Q, Qf must be (n,n) blocks and R (m,m) (n, m from the model when given), each shared
+    or batched, all batched ones with the same batch size."""
+    Q, R, Qf = runningCost.Q, runningCost.R, terminalCost.Qf
+    n = int(Q.shape[-1]) if n is None else int(n)
+    m = int(R.shape[-1]) if m is None else int(m)
+    return reconcile_batch(_block_batch(Q, (n, n), "Q"), _block_batch(R, (m, m), "R"), _block_batch(Qf, (n, n), "Qf"))
 
 
 # ------------------------------------------------------------------------------------------------

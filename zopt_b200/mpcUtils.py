@@ -21,7 +21,8 @@ import weakref
 import numpy as np
 import torch
 
-from ._lib import View, ZbAdmmOpts, check, dcode, lib, null_arr, pick_device, pick_dtype, ptr, stream_ptr, to_dev
+from ._lib import (View, ZbAdmmOpts, cached_matrix_flag, check, dcode, is_symmetric, lib, null_arr, pick_device, pick_dtype, ptr,
+                   stream_ptr, to_dev)
 from .pytrees import Trajectory
 
 STATUS = ("optimal", "optimal_inaccurate", "infeasible")
@@ -46,20 +47,9 @@ def _isinf_all(t, sign):
     return bool(torch.all(torch.isinf(t) & ((t > 0) if sign > 0 else (t < 0))))
 
 
-_DIAG_CACHE = {}
-
-
 def _is_diagonal(t):
-    """Exact diagonality of a batch of square matrices; cached by tensor OBJECT identity (weak reference) and in-place
-    version counter, never by address, so a recycled allocation can not produce a stale answer."""
-    ent = _DIAG_CACHE.get(id(t))
-    if ent is not None and ent[0]() is t and ent[1] == t._version:
-        return ent[2]
-    if len(_DIAG_CACHE) > 256:
-        _DIAG_CACHE.clear()
-    res = bool((t - torch.diag_embed(torch.diagonal(t, dim1=-2, dim2=-1))).abs().max() == 0)
-    _DIAG_CACHE[id(t)] = (weakref.ref(t), t._version, res)
-    return res
+    """Exact diagonality of a batch of square matrices (cached per tensor object, see _lib.cached_matrix_flag)."""
+    return cached_matrix_flag(t, "diag", lambda a: bool((a - torch.diag_embed(torch.diagonal(a, dim1=-2, dim2=-1))).abs().max() == 0))
 
 
 class lqrMpc():
@@ -95,6 +85,13 @@ class lqrMpc():
         # read, so it is cached per tensor (storage, shape, in-place version): re-building the problem every MPC step
         # around the same Q, R, Qf (demos/lqrMpc.py:31 builds once; a re-linearising loop rebuilds) costs nothing.
         self.cost_diagonal = all(_is_diagonal(t) for t in (self.ops[2], self.ops[3], self.ops[4]))
+        # the (12,4) Riccati kernels read the lower triangle of the (symmetric) weights; non-symmetric weights are legal input
+        # for the reference's cvxpy quad_form only up to symmetrisation, so they take the generic kernels, weights as given
+        self.cost_symmetric = self.cost_diagonal or all(is_symmetric(t) for t in (self.ops[2], self.ops[3], self.ops[4]))
+        shapes = [(self.n, self.n), (self.n, self.m), (self.n, self.n), (self.m, self.m), (self.n, self.n), (self.n,), (self.n,), (self.m,), (self.m,)]
+        for name, t, nd, shp in zip(("A", "B", "Q", "R", "Qf", "x_lb", "x_ub", "u_lb", "u_ub"), self.ops, core, shapes):
+            if tuple(t.shape[-nd:]) != shp:
+                raise ValueError(f"{name}: expected trailing shape {shp}, got {tuple(t.shape)}")
         self.iters = None
         # Finite bounds, (n,m) = (12,4), one problem definition for every x0 (the reference's usage: the QP is built once,
         # mpcUtils.py:14-59, and re-solved per x0): the definition is kept on the host and handed to the kernel by value,
@@ -108,7 +105,9 @@ class lqrMpc():
     def solve(self, x0, **kwargs):
         """
         Solve the MPC step at state x0 (zopt/mpcUtils.py:61-81).  Keyword arguments follow OSQP's names as passed through
-        cvxpy in the reference demo (`eps_abs`, `eps_rel`, `max_iter`, `rho`, `sigma`, `alpha`); others are ignored.
+        cvxpy in the reference demo; honoured: `eps_abs`, `eps_rel`, `max_iter`, `rho` (initial, then residual-balanced),
+        `alpha` (over-relaxation), `check_termination`, `eps_prim_inf`.  Others are accepted and ignored -- in particular
+        `sigma`: OSQP regularises its KKT system with it, the Riccati-structured solve here needs no regularisation.
         `kernel="generic"` forces the generic one-thread-per-problem ADMM kernel where the shared-definition (12,4) kernels would
         run; `"thread"` / `"quad"` pick the shared-definition kernel with one / four threads per problem (default: by batch size).
 
@@ -119,6 +118,8 @@ class lqrMpc():
             status : "optimal" / "optimal_inaccurate" / "infeasible" (int8 codes when batched)
         """
         x0 = to_dev(x0, self.dtype, self.device)
+        if x0.ndim not in (1, 2) or x0.shape[-1] != self.n:
+            raise ValueError(f"x0 must be ({self.n},) or (Bsz,{self.n}), got {tuple(x0.shape)}")
         batched = self.batched or x0.ndim == 2
         Bsz = self.Bsz
         if x0.ndim == 2 and x0.shape[0] != 1:
@@ -145,7 +146,7 @@ class lqrMpc():
         wsb = lib.zb_mpc_workspace_bytes(dcode(dt), Bsz, N, n, m)
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         check(lib.zb_mpc_lqr_solve(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, n, m, *[v.ref() for v in self.views],
-                                   (1 if self.bounded else 0) | (2 if self.cost_diagonal else 0), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
+                                   (1 if self.bounded else 0) | (2 if self.cost_diagonal else 0) | (0 if self.cost_symmetric else 128), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
                                    ptr(iters), ptr(ws), wsb))
         self.iters = iters
         if not batched:
@@ -192,6 +193,8 @@ class lqrMpc():
                                       "compose solve() step by step otherwise")
         dt, dev, N, box = self.dtype, self.device, self.N, self._box
         x0 = to_dev(x0, dt, dev)
+        if x0.ndim not in (1, 2) or x0.shape[-1] != 12:
+            raise ValueError(f"x0 must be (12,) or (Bsz,12), got {tuple(x0.shape)}")
         batched = x0.ndim == 2
         x0 = (x0 if batched else x0[None]).contiguous()
         Bsz, Tsim = x0.shape[0], int(Tsim)
@@ -241,14 +244,23 @@ def quadcopterClosedLoopMpc(x0, Q, R, N, Tsim, dt=0.1, Qf=None, uTrim=(9.807, 0.
     if Qf is None:
         Qf = Q
     device = pick_device(x0, Q, R, Qf)
-    # fp64 when the caller's state is fp64 (the reference's precision: cooperative kernel of csrc/lqr_quad64.cuh), else fp32
-    f32 = torch.float64 if (isinstance(x0, torch.Tensor) and x0.dtype == torch.float64) else torch.float32
+    # dtype as everywhere else (pick_dtype): fp32 only when every floating input is fp32; NumPy / Python numbers are fp64, the
+    # reference's precision (cooperative fp64 kernel of csrc/lqr_quad64.cuh)
+    f32 = pick_dtype(x0, Q, R, Qf)
     x0, Q, R, Qf = (to_dev(t, f32, device) for t in (x0, Q, R, Qf))
+    if x0.ndim not in (1, 2) or x0.shape[-1] != 12:
+        raise ValueError(f"x0 must be (12,) or (Bsz,12), got {tuple(x0.shape)}")
     batched = x0.ndim == 2
     x0 = (x0 if batched else x0[None]).contiguous()
     Bsz = x0.shape[0]
+    for name, t, blk in (("Q", Q, (12, 12)), ("R", R, (4, 4)), ("Qf", Qf, (12, 12))):
+        if tuple(t.shape[-2:]) != blk or t.ndim not in (2, 3) or (t.ndim == 3 and t.shape[0] not in (1, Bsz)):
+            raise ValueError(f"{name} must be {blk} or (Bsz,) + {blk} with Bsz = {Bsz}, got {tuple(t.shape)}")
     views = [View(t, 2, False, t.ndim == 3) for t in (Q, R, Qf)]
     diag = all(_is_diagonal(t) for t in (Q, R, Qf))
+    if not diag and not all(is_symmetric(t) for t in (Q, R, Qf)):
+        raise ValueError("Q, R, Qf must be symmetric (the fused kernels read their lower triangle; cvxpy's quad_form in the "
+                         "reference, zopt/mpcUtils.py:52-54, rejects non-symmetric weights as well)")
     xS = torch.empty((Bsz, Tsim + 1, 12), dtype=f32, device=device)
     uS = torch.empty((Bsz, Tsim, 4), dtype=f32, device=device)
     ut = (C.c_double * 4)(*[float(v) for v in uTrim])

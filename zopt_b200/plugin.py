@@ -143,28 +143,50 @@ class SymbolicDynamics:
         return 1
 
     # ------------------------------------------------------------------------------------------ build / load
+    _NVCC_FLAGS = ["-cudart", "static", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+                   "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+
     def _key(self):
+        """Content hash of everything the plug-in is compiled from: the generated model, EVERY header of csrc/ (the solver
+        kernels include them transitively), the public headers and the compiler command line."""
         h = hashlib.sha1(self.source.encode())
-        for fn in ("zb_user_model.cu", "ilqr_generic.cuh", "zb_problems.cuh", "zb_steps.cuh", "zb_math.cuh", "zb_common.cuh", "ilqr_params.cuh"):
-            with open(os.path.join(_CSRC, fn), "rb") as fh:
+        files = [os.path.join(_CSRC, "zb_user_model.cu")] + sorted(
+            os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh"))
+        inc = os.path.join(os.path.dirname(os.path.dirname(_CSRC)), "include")
+        files += sorted(os.path.join(inc, f) for f in os.listdir(inc) if f.endswith(".h"))
+        for fn in files:
+            with open(fn, "rb") as fh:
+                h.update(os.path.basename(fn).encode())
                 h.update(fh.read())
+        h.update(" ".join([NVCC] + self._NVCC_FLAGS).encode())
         return h.hexdigest()[:16]
 
     def build(self):
-        """Generate the model header and compile the plug-in for sm_100a (nvcc cross-compiles without a GPU); cached."""
+        """Generate the model header and compile the plug-in for sm_100a (nvcc cross-compiles without a GPU); cached.
+        Safe when several ranks build the same model at once: each compiles to its own temporary name and publishes the
+        library with an atomic rename (the losers of the race replace it with identical bytes)."""
         os.makedirs(CACHE_DIR, exist_ok=True)
         key = self._key()
         hdr, so = os.path.join(CACHE_DIR, f"model_{key}.cuh"), os.path.join(CACHE_DIR, f"libzb_model_{key}.so")
         if not os.path.exists(so):
-            with open(hdr, "w") as fh:
+            import tempfile
+            fd, tmp_hdr = tempfile.mkstemp(prefix=f"model_{key}.", suffix=".cuh", dir=CACHE_DIR)
+            with os.fdopen(fd, "w") as fh:
                 fh.write(self.source)
-            cmd = [NVCC, "-cudart", "static", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-                   "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-                   f'-DZB_USER_MODEL_HEADER="{hdr}"', "-I", _CSRC, "-shared", "-o", so + ".tmp", os.path.join(_CSRC, "zb_user_model.cu")]
-            r = subprocess.run(cmd, capture_output=True, text=True)
-            if r.returncode != 0:
-                raise RuntimeError("nvcc failed for the user model:\n" + r.stderr[-4000:])
-            os.replace(so + ".tmp", so)
+            fd, tmp_so = tempfile.mkstemp(prefix=f"libzb_model_{key}.", suffix=".so.tmp", dir=CACHE_DIR)
+            os.close(fd)
+            try:
+                cmd = [NVCC] + self._NVCC_FLAGS + [f'-DZB_USER_MODEL_HEADER="{tmp_hdr}"', "-I", _CSRC, "-shared", "-o", tmp_so,
+                                                   os.path.join(_CSRC, "zb_user_model.cu")]
+                r = subprocess.run(cmd, capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise RuntimeError("nvcc failed for the user model:\n" + r.stderr[-4000:])
+                os.replace(tmp_hdr, hdr)
+                os.replace(tmp_so, so)
+            finally:
+                for t in (tmp_hdr, tmp_so):
+                    if os.path.exists(t):
+                        os.unlink(t)
         self.so_path = so
         L = C.CDLL(so)
         L.zb_user_ilqr_workspace_bytes.restype = C.c_size_t
