@@ -34,6 +34,10 @@ def per_problem_relerr(a, b):
     return np.max(np.abs(a - b), axis=ax) / np.max(np.abs(b), axis=ax)
 
 
+def rep_np(a, N):
+    return np.repeat(np.asarray(a)[None], N, axis=0)
+
+
 TOL = {torch.float64: 1e-10, torch.float32: 1e-5}
 DT = [torch.float64, torch.float32]
 cuda = lambda a, dt=torch.float64: torch.as_tensor(np.asarray(a), dtype=dt, device="cuda")
@@ -856,6 +860,38 @@ def test_closed_loop_mpc_warp_variant_vs_thread_variant(dense_cost):
     # small batches pick the kernel by themselves
     ta = quadcopterClosedLoopMpc(*args, dt=0.1, Qf=cuda(10 * Q, torch.float32))
     assert torch.equal(ta.xTraj[fin], tw.xTraj[fin])
+
+
+@pytest.mark.parametrize("ddp", [False, True])
+def test_solver_early_exit_and_active_list_compaction(ddp):
+    """iterativeLqr / differentialDynamicProgramming with the reference's defaults (maxIter=100, tol=1e-3, ilqrUtils.py:267-268):
+    problems converge at different iterations, the still-iterating ones are re-listed after every forward pass and the host
+    stops enqueuing when the list is empty.  The mapping of problems to thread groups must not change any result: every
+    problem solved ALONE (batch of one) gives bit-identical iterates, iteration counts and step-size logs; converged problems
+    stay frozen; and the iteration counts really differ inside the batch."""
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    N, Bsz = 30, 37
+    rng = np.random.default_rng(23)
+    x0 = np.zeros((Bsz, 12))
+    x0[:, 9:12] = rng.uniform(-6, 6, (Bsz, 3)) * rng.uniform(0.02, 1.0, (Bsz, 1))  # near and far starts: early and late convergence
+    x0[5] = 0.0  # already optimal at hover: converges in the first iteration
+    uG = rep_np(configs.U_TRIM, N)
+    solver = ilqrUtils.differentialDynamicProgramming if ddp else ilqrUtils.iterativeLqr
+    args = (QuadcopterEuler(0.1), QuadraticCost(np.eye(12), (0.2 if ddp else 1.0) * np.eye(4)), QuadraticTerminalCost(10 * np.eye(12)))
+    traj, L, J, conv, log = solver(*args, cuda(x0), uG, maxIter=60, tol=1e-3, return_log=True)
+    iters = log["iters"].cpu().numpy()
+    assert conv.all() and iters.min() < iters.max() and iters.max() < 60, iters
+    for b in list(range(0, Bsz, 6)) + [5, int(np.argmax(iters)), int(np.argmin(iters))]:
+        t1, L1, J1, c1, lg1 = solver(*args, cuda(x0[b]), uG, maxIter=60, tol=1e-3, return_log=True)
+        assert int(lg1["iters"]) == iters[b] and bool(c1)
+        assert torch.equal(t1.xTraj, traj.xTraj[b]) and torch.equal(t1.uTraj, traj.uTraj[b]) and torch.equal(L1, L[b])
+        assert torch.equal(lg1["alpha_idx"], log["alpha_idx"][b]) and float(J1) == float(J[b])
+        # the log past the last iteration run stays at its "not run" marker
+        assert (log["alpha_idx"][b, iters[b]:] == -1).all()
+    # fp32: same machinery (different kernels' instantiations)
+    t32, L32, J32, c32, lg32 = solver(*args, cuda(x0, torch.float32), torch.as_tensor(uG, dtype=torch.float32), maxIter=60, tol=1e-3, return_log=True)
+    assert c32.all() and per_problem_relerr(t32.xTraj, traj.xTraj.cpu().numpy()).max() < 5e-3
 
 
 def test_pytree_constructors_and_building_block_pipeline():

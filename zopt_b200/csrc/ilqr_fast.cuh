@@ -273,9 +273,9 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     T* smem = reinterpret_cast<T*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & 3, quad = lane >> 2;
-    const long long b_raw = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 8 + quad;
-    const bool in_range = b_raw < P.Bsz;
-    const long long b = in_range ? b_raw : P.Bsz - 1;
+    const long long slot = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 8 + quad;
+    const bool in_range = slot < (P.act.perm ? (long long)*P.act.count : P.Bsz);
+    const long long b = P.act.perm ? (in_range ? (long long)P.act.perm[slot] : 0) : (in_range ? slot : P.Bsz - 1);
     const bool active = in_range && !(P.done && P.done[b]);
     // a warp whose 8 problems are all frozen / out of range has nothing to do
     if (__ballot_sync(0xffffffffu, active) == 0u) return;

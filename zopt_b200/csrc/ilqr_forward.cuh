@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(64, sizeof(T) == 8 ? 8 : 12) k_forward_quad(Fw
     constexpr int C_L = 48 / EPC, C_l = 4 / EPC, C_X = 12 / EPC;
     __shared__ __align__(16) T ring[4][D][ST];
     const int tid = threadIdx.x, hw = tid >> 4, j = tid & 15;
-    const long long b = (long long)blockIdx.x * 4 + hw;
-    if (b >= P.Bsz) return;
+    const long long slot = (long long)blockIdx.x * 4 + hw;
+    if (slot >= (P.act.perm ? (long long)*P.act.count : P.Bsz)) return;
+    const long long b = P.act.perm ? (long long)P.act.perm[slot] : slot;
     if (P.S.converged && P.S.J && P.S.converged[b]) return;  // frozen problem (half-warp uniform)
     const unsigned hmask = 0xFFFFu << (tid & 16);
     const int N = P.N;
@@ -317,6 +318,26 @@ __global__ void __launch_bounds__(64) k_solve_setup_quad(SetupQuadP P) {
         jl[0] = Jc;
         for (int i = 1; i <= P.maxIter; ++i) jl[i] = Jc * T(0) + T(NAN);
     }
+}
+
+__global__ void k_compact_active(long long Bsz, const uint8_t* __restrict__ converged, int32_t* __restrict__ perm, int32_t* __restrict__ count) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool act = b < Bsz && converged[b] == 0;
+    // one atomic per warp: the active lanes take consecutive positions
+    const unsigned m = __ballot_sync(0xffffffffu, act);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (act) perm[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)b;
+}
+
+int32_t compact_active_launch(long long Bsz, const uint8_t* converged, int32_t* perm_out, int32_t* count_out, cudaStream_t stream) {
+    ZB_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int32_t), stream));
+    k_compact_active<<<(unsigned)((Bsz + 255) / 256), 256, 0, stream>>>(Bsz, converged, perm_out, count_out);
+    ZB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int32_t solve_setup_quad_launch(int32_t dtype, const SetupQuadP& P, cudaStream_t stream) {

@@ -5,6 +5,13 @@
 
 namespace zb {
 
+// Compaction of the problems that are still iterating (frozen problems must not keep lanes idle): `perm[0..*count)`
+// lists them; thread groups map slot -> perm[slot] and groups past *count leave at once.  perm == nullptr: identity.
+struct ActiveP {
+    const int32_t* perm;
+    const int32_t* count;
+};
+
 struct IlqrFastP {
     long long Bsz;
     int N;
@@ -16,6 +23,7 @@ struct IlqrFastP {
     const uint8_t* done;
     void *l, *L;
     double eps;  // ensurePositiveDefinite threshold (1e-3)
+    ActiveP act;
 };
 
 // solver bookkeeping shared by the generic commit kernel and the fused kernel
@@ -42,6 +50,7 @@ struct FwdQuadP {
     void* Jall;           // (Bsz,16) or null
     CommitP S;
     int cost_diagonal;    // the caller asserted diagonal Q, R (ZB_COST_DIAGONAL)
+    ActiveP act;
 };
 
 // once per solve: conditioned cost blocks of a DIAGONAL quadratic cost + the initial rollout u_k = uGuess_k
@@ -94,6 +103,8 @@ inline bool fwd_quad_eligible(const Model& M) { return M.kind == ZB_MODEL_QUADCO
 int32_t ilqr_fast_launch(int32_t dtype, const IlqrFastP& P, cudaStream_t stream, bool cost_diagonal, bool second_order);
 int32_t fwd_quad_launch(int32_t dtype, const FwdQuadP& P, cudaStream_t stream);
 int32_t solve_setup_quad_launch(int32_t dtype, const SetupQuadP& P, cudaStream_t stream);
+// perm_out[0..*count_out) <- problems with converged[b] == 0 (count_out zeroed on the stream first); any order
+int32_t compact_active_launch(long long Bsz, const uint8_t* converged, int32_t* perm_out, int32_t* count_out, cudaStream_t stream);
 int32_t riccati_quad_launch(int32_t dtype, const LqrQuadP& P, cudaStream_t stream);
 int32_t mpc_closed_loop_quad64_launch(const ClosedLoopQuadP& P, cudaStream_t stream);
 

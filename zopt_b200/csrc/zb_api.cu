@@ -17,6 +17,9 @@ namespace zb {
 int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream);  // zb_small_batch.cu
 }
 
+#ifndef ZB_EXIT_CHECK
+#define ZB_EXIT_CHECK 4  // zb_ilqr_solve: iterations between two "is anything still iterating" reads
+#endif
 #ifndef ZB_W9_MAX_PER_SM
 #define ZB_W9_MAX_PER_SM 28  // problems per SM up to which the nine-lanes-per-problem closed-loop kernel is selected
 #endif
@@ -474,7 +477,7 @@ size_t zb_ilqr_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n,
     size_t p = (size_t)(n + m);
     const size_t per = (size_t)(N + 1) * n + (size_t)N * m;  // one trajectory
     return align256(e * Bsz * N * m) + align256(e * Bsz * 16) + align256(e * Bsz * p * p) + align256(e * Bsz * n * n) +
-           align256(e * SPEC_N * Bsz * per) + 256;
+           align256(e * SPEC_N * Bsz * per) + 2 * align256(sizeof(int32_t) * (size_t)Bsz) + 512;  // + two active lists, two counters
 }
 
 int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t flags,
@@ -501,8 +504,17 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     void* Jall = w;  w += align256(e * Bsz * 16);
     void* Czz = w;   w += align256(e * Bsz * p * p);
     void* Vfxx = w;  w += align256(e * Bsz * n * n);
-    void* spec = w;  // speculative trajectories of the two largest step sizes
+    void* spec = w;  w += align256(e * SPEC_N * Bsz * ((size_t)(N + 1) * n + (size_t)N * m));  // speculative trajectories of the two largest step sizes
+    int32_t* perm2[2];
+    perm2[0] = reinterpret_cast<int32_t*>(w);  w += align256(sizeof(int32_t) * (size_t)Bsz);
+    perm2[1] = reinterpret_cast<int32_t*>(w);  w += align256(sizeof(int32_t) * (size_t)Bsz);
+    int32_t* count2 = reinterpret_cast<int32_t*>(w);  // two counters, 128 bytes apart
     cudaStream_t s = (cudaStream_t)stream;
+    // With a real tolerance problems freeze at different iterations (ilqrUtils.py:301-303,318): the still-iterating ones are
+    // re-listed after every forward pass so that frozen problems occupy no lane, and the host stops enqueuing once the list is
+    // empty (checked every ZB_EXIT_CHECK iterations: one 4-byte read + stream sync).  tol < 0 (forced iteration count, as the
+    // benchmarks use) never converges: no lists, no check, the call stays fully asynchronous.
+    const bool track = tol >= 0.0 && maxIter > 0;
     // policy.L = 0 before the first iteration (ilqrUtils.py:293)
     ZB_CUDA(cudaMemsetAsync(L_out, 0, e * Bsz * N * m * n, s));
     P.x0 = x0; P.l = l_ws; P.L = L_out; P.xPrev = xTraj; P.uPrev = uTraj;
@@ -519,8 +531,14 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     }
     SolveBackP Bk{Bsz, N, second_order, P.M, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
     const bool fast_bwd = N >= 1 && ilqr_fast_eligible(P.M, second_order, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out);
-    IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
+    IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3, ActiveP{nullptr, nullptr}};
+    if (track) {
+        rc = compact_active_launch(Bsz, converged_out, perm2[0], count2, s);
+        if (rc) return rc;
+    }
     for (int it = 0; it < maxIter; ++it) {
+        const ActiveP act = track ? ActiveP{perm2[it & 1], count2 + 32 * (it & 1)} : ActiveP{nullptr, nullptr};
+        Fb.act = act;
         if (fast_bwd) {
             rc = ilqr_fast_launch(dtype, Fb, s, cost_diagonal, second_order != 0);
             if (rc) return rc;
@@ -528,13 +546,24 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
             ZB_DISPATCH(dtype, k_solve_backward, gen_grid(Bsz), GEN_THREADS, stream, Bk);
         CommitP S{J_out, converged_out, iters_out, alpha_log, J_log, it, (int)maxIter, tol, nullptr, nullptr};
         if (fast_fwd) {  // line search + commit + bookkeeping in one launch (ilqr_forward.cuh)
-            FwdQuadP Fw{Bsz, N, P.M.dt, P.C, x0, l_ws, L_out, xTraj, uTraj, spec, nullptr, S, cost_diagonal ? 1 : 0};
+            FwdQuadP Fw{Bsz, N, P.M.dt, P.C, x0, l_ws, L_out, xTraj, uTraj, spec, nullptr, S, cost_diagonal ? 1 : 0, act};
             rc = fwd_quad_launch(dtype, Fw, s);
             if (rc) return rc;
-            continue;
+        } else {
+            ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall, (const uint8_t*)converged_out, spec);
+            ZB_DISPATCH(dtype, k_forward_commit, gen_grid(Bsz * 16), GEN_THREADS, stream, P, (const void*)Jall, S, (const void*)spec);
         }
-        ZB_DISPATCH(dtype, k_forward_costs, gen_grid(Bsz * 16), GEN_THREADS, stream, P, Jall, (const uint8_t*)converged_out, spec);
-        ZB_DISPATCH(dtype, k_forward_commit, gen_grid(Bsz * 16), GEN_THREADS, stream, P, (const void*)Jall, S, (const void*)spec);
+        if (track && it + 1 < maxIter) {
+            int32_t* cnt_next = count2 + 32 * ((it + 1) & 1);
+            rc = compact_active_launch(Bsz, converged_out, perm2[(it + 1) & 1], cnt_next, s);
+            if (rc) return rc;
+            if ((it % ZB_EXIT_CHECK) == ZB_EXIT_CHECK - 1) {  // anything left to iterate on?
+                int32_t left = 1;
+                ZB_CUDA(cudaMemcpyAsync(&left, cnt_next, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+                ZB_CUDA(cudaStreamSynchronize(s));
+                if (left == 0) break;
+            }
+        }
     }
     return 0;
 }
