@@ -18,6 +18,7 @@
 // access of a warp is one contiguous 512 B row: conflict-free, and no thread ever reads another thread's
 // slots -- the main loop needs no barrier.  One warp per CTA, 4 CTAs per SM (111 float4 = 1,776 B per problem).
 #pragma once
+#include <stdlib.h>
 #include "t1_common.cuh"
 
 namespace zb {
@@ -41,13 +42,18 @@ __device__ __forceinline__ void load_sym_lower(const float* g, float* v) {
 // gain L = (R + B'VB)^-1 B'VA is returned in registers.  S = this lane's column of the shared-memory slab.
 // RS = row stride of the slab in float4 (32 lanes; 33 in the time-varying kernel, whose cooperative loads need the pad);
 // RFULL = R stored as four full rows (slots R4..R4+3) instead of the packed lower triangle.
-template <bool QDIAG, int RS = 32, bool RFULL = false>
+// SPLIT: [A | B] kept as two contiguous blocks (A rows at slots 0..35, B rows at 36..47 -- how bulk copies deliver them)
+// instead of row-interleaved (row k = slots 4k..4k+3, chunk 3 = B row).
+template <bool SPLIT>
+__device__ __forceinline__ int xs(int k, int c) { return SPLIT ? (c < 3 ? k * 3 + c : 36 + k) : X4 + k * 4 + c; }
+
+template <bool QDIAG, int RS = 32, bool RFULL = false, bool SPLIT = false>
 __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&L)[4][12]) {
     // ---- 1. [W | VB] = V [A | B] in four 12x4 panels.  ROLLED loop: one ~600-instruction body re-used four
     //         times keeps the step's code inside the instruction cache (the fully unrolled first version
     //         stalled 0.8 cycle/instruction on instruction fetch with one warp per scheduler).
     float G[10];
-    float4 xfirst = S[(X4 + 0) * RS];  // row 0 of the next panel, fetched before the previous panel's epilogue
+    float4 xfirst = S[xs<SPLIT>(0, 0) * RS];  // row 0 of the next panel, fetched before the previous panel's epilogue
 #pragma unroll 1
     for (int p = 0; p < 4; ++p) {
         float acc[12][4];
@@ -57,7 +63,7 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
             for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
 #pragma unroll
         for (int kk = 0; kk < 12; ++kk) {
-            const float4 x4 = (kk == 0) ? xfirst : S[(X4 + kk * 4 + p) * RS];
+            const float4 x4 = (kk == 0) ? xfirst : S[xs<SPLIT>(kk, p) * RS];
 #pragma unroll
             for (int i = 0; i < 12; ++i) {
                 const float vik = v[tri(i, kk)];
@@ -72,7 +78,7 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
 #endif
             }
         }
-        xfirst = S[(X4 + ((p < 3) ? p + 1 : 0)) * RS];
+        xfirst = S[xs<SPLIT>(0, (p < 3) ? p + 1 : 0) * RS];
         if (p < 3) {
 #pragma unroll
             for (int i = 0; i < 12; ++i) S[(W4 + i * 3 + p) * RS] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -93,7 +99,7 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
             }
 #pragma unroll
             for (int i = 0; i < 12; ++i) {
-                const float4 b4 = S[(X4 + i * 4 + 3) * RS];
+                const float4 b4 = S[xs<SPLIT>(i, 3) * RS];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -137,8 +143,8 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
     {
         float4 ra[3], rw[3], rb;  // rows kk of A, W, B; next rows are fetched while the current ones are consumed
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + c) * RS]; rw[c] = S[(W4 + c) * RS]; }
-        rb = S[(X4 + 3) * RS];
+        for (int c = 0; c < 3; ++c) { ra[c] = S[xs<SPLIT>(0, c) * RS]; rw[c] = S[(W4 + c) * RS]; }
+        rb = S[xs<SPLIT>(0, 3) * RS];
 #pragma unroll 1
         for (int kk = 0; kk < 12; ++kk) {
             const float a[12] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w, ra[1].x, ra[1].y, ra[1].z, ra[1].w, ra[2].x, ra[2].y, ra[2].z, ra[2].w};
@@ -146,8 +152,8 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
             const float4 b4 = rb;
             const int kn = (kk < 11) ? kk + 1 : 11;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { ra[c] = S[(X4 + kn * 4 + c) * RS]; rw[c] = S[(W4 + kn * 3 + c) * RS]; }
-            rb = S[(X4 + kn * 4 + 3) * RS];
+            for (int c = 0; c < 3; ++c) { ra[c] = S[xs<SPLIT>(kn, c) * RS]; rw[c] = S[(W4 + kn * 3 + c) * RS]; }
+            rb = S[xs<SPLIT>(kn, 3) * RS];
 #pragma unroll
             for (int i = 0; i < 12; ++i)
 #pragma unroll
@@ -475,6 +481,129 @@ __global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P) {
 }
 
 // -------------------------------------------------------------------------------------------------------------
+// The same time-varying recursion with the operands delivered by the TMA engine (round 2): `cp.async.bulk` global -> shared
+// with an mbarrier carrying the byte count.  ncu on the cp.async version above: the load/store unit binds (lg_throttle 21 %,
+// short_scoreboard 30 %): every lane issues 76 sixteen-byte copies per step on top of the step's own ~830 shared-memory
+// loads.  Here a lane issues FOUR bulk copies per step (A 576 B, B 192 B, R 64 B, Q rows 8..11 192 B), which run in the copy
+// engine, not the LSU, plus twelve cp.async for the scattered lower-triangle chunks of Q rows 0..7 (the same 1,216 B).
+// A bulk copy lands contiguously, so the slab is PROBLEM-major: problem p owns float4 slots [113 p, 113 p + 112); 113 is
+// 1 mod 8, so the eight lanes of a quarter-warp hit eight different 16-byte bank groups on every 128-bit access
+// (conflict-free without interleaving).  Two-warp CTAs of 64 problems: 64 x 113 x 16 B = 113 KB, two CTAs fill the SM's
+// 228 KB exactly (four warps per SM, as before); the mbarriers live in pad slots.  [A | B] arrive as two blocks
+// (riccati_step<.., SPLIT>).  One mbarrier per WARP: lane 0 arms it with the step's 32 x 1,216 bytes, every lane issues its
+// own problem's copies, the warp waits on the phase; the two warps of a CTA never synchronise.  The slots are private to the lane, so the copies of step k-1 are
+// issued as soon as the lane's step k is done (fence.proxy.async orders its reads before the engine's writes) and overlap
+// the gain transposition and stores.
+// MEASURED (65,536 x N=50, one B200): 1.77 ms against 1.72 ms for the cp.async kernel -- no gain, and the experiments say why.
+// (i) With one warp per scheduler nothing covers a warp's wait: the step is 4.4 us of arithmetic + 4.5 us of waiting for the
+// operands requested at the end of the previous step (the kernel with the arithmetic removed streams in 1.08 ms, the
+// time-invariant kernel computes in 0.88 ms, together 1.96 ms: the two barely overlap).  (ii) De-phasing the warps of an SM
+// changes nothing (each scheduler still idles while ITS warp waits); an L2 prefetch one step ahead makes it slower (1.93 ms),
+// so the wait is not HBM latency but the copy path itself: the engine costs ~6 ns per request per SM (twelve requests per
+// lane-step: 15.3 us per warp-step; four: 8.9 us).  (iii) A second operand buffer (76 slots) would leave two warps per SM.
+// What would lift it: double-buffering A only (148 slots, three warps per SM, est. 1.2-1.3 ms).
+constexpr int PS4_TVB = 113;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// FOUR bulk copies per problem-step (A, B, R, rows 8..11 of Q: 1,024 B) -- the copy engine takes tens of nanoseconds per
+// request whatever its size, so the twelve-request version (Q rows 0..7 as eight 16/32-byte bulk copies) spent 10 us per
+// warp-step in the engine against 4.4 us of arithmetic -- and twelve per-lane cp.async for the lower-triangle-covering
+// chunks of Q rows 0..7 (192 B), which do not form a contiguous block.
+__device__ __forceinline__ void tvb_issue(float4* S, const FastP& P, long long b, int k, unsigned long long* bar) {
+    const float* gA = P.A.at<float>(b, k);
+    const float* gB = P.B.at<float>(b, k);
+    const float* gQ = P.Q.at<float>(b, k);
+    const float* gR = P.R.at<float>(b, k);
+    bulk_g2s(S + 0, gA, 576, bar);
+    bulk_g2s(S + 36, gB, 192, bar);
+    bulk_g2s(S + Q4 + 12, gQ + 96, 192, bar);  // rows 8..11, whole
+    bulk_g2s(S + R4, gR, 64, bar);
+    const float4* q4 = reinterpret_cast<const float4*>(gQ);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c <= r / 4; ++c) cp_async16(S + Q4 + qoff(r) + c, q4 + r * 3 + c);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+__global__ void __launch_bounds__(64, 2) k_riccati_t1_tvb(FastP P) {
+    extern __shared__ float4 sm_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* sm = sm_all + warp * 32 * PS4_TVB;  // this warp's 32 problem slabs
+    unsigned long long& bar = *reinterpret_cast<unsigned long long*>(sm + 112);  // pad slot of the warp's first problem
+    const long long b0 = ((long long)blockIdx.x * 2 + warp) * 32;
+    const long long b_raw = b0 + lane;
+    const bool active = b_raw < P.Bsz;
+    const long long b = active ? b_raw : P.Bsz - 1;  // idle lanes shadow the last problem: the byte count per step is fixed
+    float4* S = sm + lane * PS4_TVB;
+    constexpr unsigned STEP_BYTES = 32u * 1024u;  // per warp-step through the copy engine (the other 192 B per problem: cp.async)
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"(STEP_BYTES) : "memory");
+    }
+    __syncwarp();
+    tvb_issue(S, P, b, P.N - 1, &bar);
+    float v[78];
+    load_sym_lower(P.Q.at<float>(b, P.T - 1), v);  // lqrUtils.py:172: terminal value is Q[-1]
+    float* gpub = P.gains + b0 * (long long)P.N * 48;
+    unsigned phase = 0;
+    for (int k = P.N - 1; k >= 0; --k) {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");  // this lane's own Q chunks
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        float L[4][12];
+        riccati_step<false, 1, true, true>(S, v, L);
+        if (k > 0) {  // this lane is done with its operand slots: hand them back to the copy engine for step k-1
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"(STEP_BYTES) : "memory");
+            __syncwarp();
+            tvb_issue(S, P, b, k - 1, &bar);
+        }
+        // gains: each lane parks its 12 float4 in its own W slots, then the warp stores them transposed (coalesced rows of the
+        // public (Bsz,N,4,12) layout)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) S[W4 + a * 3 + c] = make_float4(L[a][4 * c], L[a][4 * c + 1], L[a][4 * c + 2], L[a][4 * c + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 12; ++r) {
+            const int idx = r * 32 + lane, pr = idx / 12, j4 = idx - pr * 12;
+            const float4 val = sm[pr * PS4_TVB + W4 + j4];
+            if (b0 + pr < P.Bsz) *reinterpret_cast<float4*>(gpub + ((long long)pr * P.N + k) * 48 + j4 * 4) = val;
+        }
+        __syncwarp();  // the W slots are overwritten by the next step
+    }
+    if (P.V0 && active) {
+        float* o = P.V0 + b * 144;
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int j = 0; j < 12; ++j) o[i * 12 + j] = v[tri(i, j)];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
 // Closed-loop LQR-MPC for the quadcopter (BASELINE cfg 3; the loop of demos/lqrMpc.py:42-47 with a nonlinear plant):
 // for every simulation step t:  A_t = I + dt dF/dx(x_t, u_trim), B = dt dF/du  (linearised IN the kernel),
 // full Riccati sweep of horizon N from Qf (nothing cached between steps), u_t = -L_0 x_t  (the first move of the
@@ -594,7 +723,18 @@ inline int32_t riccati_t1_launch(const FastP& F, cudaStream_t stream, bool cost_
 }
 
 
-inline int32_t riccati_t1_tv_launch(const FastP& F, cudaStream_t stream) {
+#ifndef ZB_TV_BULK
+#define ZB_TV_BULK 0  // default kernel: 1 = operands by cp.async.bulk + mbarrier (k_riccati_t1_tvb), 0 = per-lane cp.async (k_riccati_t1_tv).
+#endif                // Measured equal (1.77 vs 1.72 ms per 65,536 x 50): see the kernel's header; the flag ZB_TV_BULK_COPY selects it per call
+inline int32_t riccati_t1_tv_launch(const FastP& F, cudaStream_t stream, bool bulk = ZB_TV_BULK != 0) {
+    if (bulk) {
+        const size_t smem = (size_t)t1::PS4_TVB * 64 * sizeof(float4);
+        ZB_CUDA(cudaFuncSetAttribute(t1::k_riccati_t1_tvb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)((F.Bsz + 63) / 64);
+        t1::k_riccati_t1_tvb<<<grid, 64, smem, stream>>>(F);
+        ZB_CUDA(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = (size_t)t1::NF4_TV * t1::RS_TV * sizeof(float4);
     ZB_CUDA(cudaFuncSetAttribute(t1::k_riccati_t1_tv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((F.Bsz + 31) / 32);

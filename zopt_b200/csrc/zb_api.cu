@@ -271,7 +271,7 @@ int32_t zb_lqr_dfh_flags(int32_t dtype, int32_t device, void* stream, int64_t Bs
         F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R;
         F.gains = reinterpret_cast<float*>(P.L);
         F.V0 = reinterpret_cast<float*>(P.V0);
-        return riccati_t1_tv_launch(F, (cudaStream_t)stream);
+        return riccati_t1_tv_launch(F, (cudaStream_t)stream, (flags & ZB_TV_BULK_COPY) ? true : (ZB_TV_BULK != 0));
     }
     if (lqr_fast_eligible(dtype, P)) {
         if (P.Q.st == 0 || P.N == 1) {  // fully time-invariant: thread-per-problem kernel (lqr_t1.cuh)
