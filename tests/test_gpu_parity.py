@@ -894,6 +894,26 @@ def test_solver_early_exit_and_active_list_compaction(ddp):
     assert c32.all() and per_problem_relerr(t32.xTraj, traj.xTraj.cpu().numpy()).max() < 5e-3
 
 
+def test_time_varying_lqr_bulk_copy_kernel_equals_cp_async_kernel():
+    """k_riccati_t1_tvb (operands through the TMA engine: cp.async.bulk + mbarrier, problem-major slab, [A | B] as two blocks)
+    against k_riccati_t1_tv (per-lane cp.async, lane-interleaved slab): the same per-thread step on the same operands, so the
+    gains agree BIT FOR BIT; ragged batch (partial CTA and an idle second warp), and against the oracle."""
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    rng = np.random.default_rng(31)
+    Bsz, N = 97, 13
+    A = np.eye(12) + 0.1 * rng.normal(size=(Bsz, N, 12, 12))
+    B = 0.3 * rng.normal(size=(Bsz, N, 12, 4))
+    Mq, Mr = rng.normal(size=(Bsz, N + 1, 12, 12)) * 0.3, rng.normal(size=(Bsz, N, 4, 4)) * 0.3
+    Q = np.eye(12) + Mq @ np.swapaxes(Mq, -1, -2)
+    R = np.eye(4) + Mr @ np.swapaxes(Mr, -1, -2)
+    args = [cuda(t, torch.float32) for t in (A, B, Q, R)]
+    L0, V0 = discreteFiniteHorizonLqr(*args, N, return_value=True)
+    L1, V1 = discreteFiniteHorizonLqr(*args, N, return_value=True, kernel_flags=256)
+    assert torch.equal(L0, L1) and torch.equal(V0, V1)
+    for b in (0, 50, Bsz - 1):
+        assert relerr(L1[b], olqr.discreteFiniteHorizonLqr(A[b], B[b], Q[b], R[b], N)) < 1e-5
+
+
 def test_pytree_constructors_and_building_block_pipeline():
     """The reference's building blocks composed by hand exactly as ilqrUtils.py:308-316 does (expansion pytrees from the
     registered model/cost -> conditioning -> backward pass -> forwardPass2), against the oracle doing the same with autodiff."""

@@ -33,7 +33,7 @@ def _prep(arrs, core_ndims):
     return device, dtype, ts, batched, any_batched, Bsz
 
 
-def discreteFiniteHorizonLqr(A, B, Q, R, N, return_value=False):
+def discreteFiniteHorizonLqr(A, B, Q, R, N, return_value=False, kernel_flags=0):
     """
     Finite-horizon LQR gains by the backward Riccati recursion (zopt/lqrUtils.py:144-173).
 
@@ -65,6 +65,7 @@ def discreteFiniteHorizonLqr(A, B, Q, R, N, return_value=False):
     # The (12,4) fast kernels keep the symmetric value matrix as a lower triangle and read the lower triangle of Q, R.  The
     # reference uses the weights exactly as given (lqrUtils.py:168-169), so non-symmetric ones take the generic kernel.
     flags = 0 if ((n, m) != (12, 4) or (is_symmetric(Q) and is_symmetric(R))) else 128  # ZB_FORCE_GENERIC
+    flags |= int(kernel_flags)  # e.g. 256 = ZB_TV_BULK_COPY (tests / experiments)
     check(lib.zb_lqr_dfh_flags(dcode(dtype), device.index, stream_ptr(device), Bsz, N, T, n, m, vA.ref(), vB.ref(), vQ.ref(),
                                vR.ref(), flags, ptr(L), ptr(V0)))
     if not any_b:
