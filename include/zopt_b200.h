@@ -176,6 +176,7 @@ ZB_API int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_
 #define ZB_VARIANT_WARP 64  /* zb_mpc_closed_loop_quad (fp32): force the nine-lanes-per-problem register-tiled kernel (default for the smallest batches) */
 #define ZB_FORCE_GENERIC 128 /* zb_lqr_dfh_flags, zb_mpc_lqr_solve: use the generic kernels (weights taken as given, not assumed symmetric) */
 #define ZB_TV_BULK_COPY 256 /* zb_lqr_dfh_flags, time-varying fp32 (12,4): operands by cp.async.bulk + mbarrier (TMA engine) instead of per-lane cp.async */
+#define ZB_MPC_SPLIT_ROLLOUT 512 /* zb_mpc_lqr_solve, fp32 (12,4), diagonal costs, bounds inactive, multi-wave batches: sweep and plan rollout as two concurrent kernels (rollout on a side stream, following the sweep group by group through flags) instead of the fused kernel; measured equal (0.88 ms per 65,536 solves), kept for experiments */
 #define ZB_GENERIC_FORWARD 32 /* zb_ilqr_solve: force the two-kernel line search (k_forward_costs + k_forward_commit) instead of the fused quadcopter kernel */
 #define ZB_BOX_STATE_GLOBAL 16 /* zb_mpc_box_*: keep the 4-threads-per-problem kernel's ADMM state in the global workspace even when it would fit on chip */
 

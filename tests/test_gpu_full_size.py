@@ -19,6 +19,8 @@ from oracle import lqr as olqr  # noqa: E402
 from oracle.quadcopter import Quadcopter as OQuadcopter  # noqa: E402
 from zopt_b200 import configs  # noqa: E402
 
+cuda = lambda a, dt=torch.float64: torch.as_tensor(np.asarray(a), dtype=dt, device="cuda")
+
 DEV = "cuda"
 
 
@@ -218,3 +220,29 @@ def test_cfg45_full_batch_solvers_fp64(kind):
         assert _relerr(ts.xTraj[i][None], np.asarray(tr.xTraj)[None]).max() < 1e-10
         assert _relerr(Ls[i][None], np.asarray(Lr)[None]).max() < 1e-10
         assert abs(float(Js[i]) - float(Jr)) < 1e-10 * abs(float(Jr))
+
+
+def test_lqrMpc_split_rollout_equals_fused_kernel():
+    """lqrMpc.solve(kernel="split"): the sweep (k_riccati_t1<.., ROLL=false>) on the caller's stream and, concurrently on a side
+    stream, a persistent rollout kernel (k_plan_rollout_q4) that follows it group by group through flags (fork/join with
+    events).  Same operations in the same order as the fused kernel: every output BIT-identical on a ragged multi-wave batch;
+    and usable from a non-default stream."""
+    from zopt_b200.mpcUtils import lqrMpc
+    from zopt_b200.quadcopter import Quadcopter
+    Bsz = 2 * 148 * 5 * 32 + 1234  # > two waves, ragged
+    d = configs.cfg2(Bsz=Bsz)
+    f32 = torch.float32
+    xbar, ubar = cuda(d["xbar"], f32), cuda(d["ubar"], f32)
+    Q, R = torch.diag_embed(cuda(d["qdiag"], f32)), torch.diag_embed(cuda(d["rdiag"], f32))
+    A, B = Quadcopter().linearizeInertial(xbar, ubar, d["dt"])
+    inf_n, inf_m = torch.full((12,), float("inf")), torch.full((4,), float("inf"))
+    prob = lqrMpc(A, B, Q, R, d["N"], -inf_n, inf_n, -inf_m, inf_m, Qf=10 * Q)
+    u0, t0, s0 = prob.solve(xbar)
+    u1, t1, s1 = prob.solve(xbar, kernel="split")
+    assert torch.equal(u0, u1) and torch.equal(t0.xTraj, t1.xTraj) and torch.equal(t0.uTraj, t1.uTraj) and torch.equal(s0, s1)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        u2, t2, s2 = prob.solve(xbar, kernel="split")
+    st.synchronize()
+    assert torch.equal(u0, u2) and torch.equal(t0.xTraj, t2.xTraj)

@@ -197,7 +197,9 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
 
 // QDIAG: the caller asserts Q, R, Qf diagonal (ZB_COST_DIAGONAL): 4 float4 of cost data instead of 27, so FIVE
 // CTAs fit an SM (88 float4 = 1,408 B per problem) and 65,536 problems take 3 rounds of CTAs instead of 4.
-template <bool MPC, bool QDIAG>
+// ROLL = false (with MPC): sweep only -- the gains stay in the workspace and the plan is rolled out by k_plan_rollout_q4,
+// launched on a second stream so that it overlaps the next chunk's sweep (riccati_t1_mpc_split_launch).
+template <bool MPC, bool QDIAG, bool ROLL = true>
 __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
     extern __shared__ float4 sm[];
     const int lane = threadIdx.x;
@@ -292,7 +294,12 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
             for (int j = 0; j < 12; ++j) o[i * 12 + j] = v[tri(i, j)];
     }
 
-    if (MPC) {
+    if (MPC && !ROLL) {  // sweep-only launch: publish "this group's gains are in memory" to the concurrent rollout kernel
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int*>(P.iters + blockIdx.x) = 1;  // (iters: the flag array in this launch)
+    }
+    if (MPC && ROLL) {
         // ---- plan rollout x+ = A x + B u, u = -L_k x (mpcUtils.py:55).  A, B rows from smem; the gains of the
         //      next step are prefetched (L2) while the current step's dependent chain runs ----
         float x[12];
@@ -704,6 +711,114 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_mpc_closed_loop_quad(Clos
     }
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// Plan rollout of lqrMpc.solve (x+ = A x + B u, u = -L_k x, zopt/mpcUtils.py:55) as its OWN kernel, four threads per problem,
+// no shared memory and ~100 registers, so that its CTAs fit beside a full wave of sweep CTAs (which own all of the SM's
+// shared memory but only 60 % of its registers).  In the fused kernel the rollout is 18 % of the launch: every warp of a
+// wave reaches it at the same time, 227 MB of gains are re-read with nothing to overlap them.  Split, the rollout of chunk
+// c runs on a second stream while chunk c+1 sweeps.  Thread t of a quad keeps rows 3t..3t+2 of [A | B] in registers, computes
+// u_t = -L_k[t,:] x and its three rows of x+; x and u are all-gathered with shuffles.  The gains come from the workspace in the
+// sweep's layout [32-problem group][k][12 float4][lane] (a quad reads 4 x 16 B per row, eight neighbouring problems 128 B),
+// fetched one step ahead.  Operation order = the fused kernel's rollout, so both paths give the same bits.
+constexpr int ROLL_D = 4;  // ring depth of the rollout kernel: 3 steps of gains in flight per thread (24 KB per CTA)
+__global__ void __launch_bounds__(128) k_plan_rollout_q4(FastP P, const int* flags) {
+    extern __shared__ float4 ring[];  // [ROLL_D][3][128]
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, t = lane & 3, qbase = lane & ~3;
+    // grid-stride over groups of 32 problems: beside a sweeping chunk the launcher starts only two CTAs per SM (more would take
+    // the registers the sweep CTAs need and serialise the two kernels)
+    for (long long grp = blockIdx.x; grp * 32 < P.Bsz; grp += gridDim.x) {
+    if (flags) {  // the sweep CTA of this group signals when its gains are stored (it runs concurrently on the caller's stream)
+        if (threadIdx.x == 0) {
+            while (*reinterpret_cast<const volatile int*>(flags + grp) == 0) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    const long long b_raw = grp * 32 + (threadIdx.x >> 2);
+    const bool active = b_raw < P.Bsz;
+    const long long b = active ? b_raw : P.Bsz - 1;
+    // rows 3t..3t+2 of [A | B]
+    float a[3][12], bb[3][4];
+    {
+        const float4* gA = reinterpret_cast<const float4*>(P.A.at<float>(b));
+        const float4* gB = reinterpret_cast<const float4*>(P.B.at<float>(b));
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 v = __ldg(gA + (3 * t + r) * 3 + c);
+                a[r][4 * c] = v.x; a[r][4 * c + 1] = v.y; a[r][4 * c + 2] = v.z; a[r][4 * c + 3] = v.w;
+            }
+            const float4 v = __ldg(gB + 3 * t + r);
+            bb[r][0] = v.x; bb[r][1] = v.y; bb[r][2] = v.z; bb[r][3] = v.w;
+        }
+    }
+    float x[12];
+    {
+        const float4* gx = reinterpret_cast<const float4*>(P.x0 + b * 12);
+        const float4 x0 = __ldg(gx), x1 = __ldg(gx + 1), x2 = __ldg(gx + 2);
+        x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+        x[8] = x2.x; x[9] = x2.y; x[10] = x2.z; x[11] = x2.w;
+    }
+    float* xT = P.xTraj + b * (long long)(P.N + 1) * 12;
+    float* uT = P.uTraj + b * (long long)P.N * 4;
+    if (active && t < 3) *reinterpret_cast<float4*>(xT + 4 * t) = make_float4(x[4 * t], x[4 * t + 1], x[4 * t + 2], x[4 * t + 3]);
+    // gain row t of step k: float4 slots t*3 .. t*3+2 of the problem's column in its group's slab, streamed through a
+    // ROLL_D-stage cp.async ring whose slots are private to the thread (it reads what it copied: no barrier)
+    const float4* g = reinterpret_cast<const float4*>(P.gains) + (b >> 5) * (long long)P.N * 12 * 32 + (t * 3) * 32 + (b & 31);
+    float4* my = ring + threadIdx.x;  // stage st, chunk c: my[(st * 3 + c) * 128]
+    auto issue = [&](int kk) {
+        const float4* gn = g + (long long)(kk < P.N ? kk : P.N - 1) * 12 * 32;
+        const int st = kk % ROLL_D;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cp_async16(my + (st * 3 + c) * 128, gn + c * 32);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+#pragma unroll
+    for (int kk = 0; kk < ROLL_D - 1; ++kk) issue(kk);
+#pragma unroll 1
+    for (int k = 0; k < P.N; ++k) {
+        issue(k + ROLL_D - 1);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(ROLL_D - 1) : "memory");
+        const int st = k % ROLL_D;
+        const float4 c0 = my[(st * 3 + 0) * 128], c1 = my[(st * 3 + 1) * 128], c2 = my[(st * 3 + 2) * 128];
+        float s0 = c0.x * x[0], s1 = c1.x * x[4], s2 = c2.x * x[8];
+        s0 = fmaf(c0.y, x[1], s0); s1 = fmaf(c1.y, x[5], s1); s2 = fmaf(c2.y, x[9], s2);
+        s0 = fmaf(c0.z, x[2], s0); s1 = fmaf(c1.z, x[6], s1); s2 = fmaf(c2.z, x[10], s2);
+        s0 = fmaf(c0.w, x[3], s0); s1 = fmaf(c1.w, x[7], s1); s2 = fmaf(c2.w, x[11], s2);
+        const float ut = -((s0 + s1) + s2);
+        float u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[q] = __shfl_sync(FULL, ut, qbase + q);
+        float xn[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float p0 = a[r][0] * x[0], p1 = a[r][4] * x[4], p2 = a[r][8] * x[8], p3 = bb[r][0] * u[0];
+            p0 = fmaf(a[r][1], x[1], p0); p1 = fmaf(a[r][5], x[5], p1); p2 = fmaf(a[r][9], x[9], p2); p3 = fmaf(bb[r][1], u[1], p3);
+            p0 = fmaf(a[r][2], x[2], p0); p1 = fmaf(a[r][6], x[6], p1); p2 = fmaf(a[r][10], x[10], p2); p3 = fmaf(bb[r][2], u[2], p3);
+            p0 = fmaf(a[r][3], x[3], p0); p1 = fmaf(a[r][7], x[7], p1); p2 = fmaf(a[r][11], x[11], p2); p3 = fmaf(bb[r][3], u[3], p3);
+            xn[r] = (p0 + p1) + (p2 + p3);
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) x[i] = __shfl_sync(FULL, xn[i % 3], qbase + i / 3);
+        if (active) {
+            if (t == 3) {
+                *reinterpret_cast<float4*>(uT + (long long)k * 4) = make_float4(u[0], u[1], u[2], u[3]);
+                if (k == 0) *reinterpret_cast<float4*>(P.u0 + b * 4) = make_float4(u[0], u[1], u[2], u[3]);
+            } else {
+                *reinterpret_cast<float4*>(xT + (long long)(k + 1) * 12 + 4 * t) = make_float4(x[4 * t], x[4 * t + 1], x[4 * t + 2], x[4 * t + 3]);
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (active && t == 0) {
+        P.status[b] = 0;
+        if (P.iters) P.iters[b] = 0;
+    }
+    }
+}
+
 }  // namespace t1
 
 // eligibility on top of the 4-thread kernel's: Q time-invariant and symmetric handling (lower triangle is used)
@@ -720,6 +835,61 @@ inline int32_t riccati_t1_launch_impl(const FastP& F, cudaStream_t stream) {
 template <bool MPC>
 inline int32_t riccati_t1_launch(const FastP& F, cudaStream_t stream, bool cost_diagonal = false) {
     return cost_diagonal ? riccati_t1_launch_impl<MPC, true>(F, stream) : riccati_t1_launch_impl<MPC, false>(F, stream);
+}
+
+// lqrMpc.solve for batches of more than one wave: ONE sweep launch over the whole batch on the caller's stream (CTAs scheduled
+// dynamically, no wave barrier) and, concurrently on a side stream, a persistent rollout kernel of two CTAs per SM that
+// follows it group by group: a sweep CTA raises its group's flag once its 32 problems' gains are stored, the rollout CTA
+// that owns the group waits for the flag, then rolls the plans out.  The rollout kernel has no shared memory and ~100
+// registers, so two of its CTAs fit beside five sweep CTAs on every SM.  It is launched AFTER the sweep so that tools that
+// serialise kernels (ncu) still terminate; the caller's stream finally waits for it (fork / join with events, capturable).
+// `flags`: (Bsz+31)/32 ints of the workspace, zeroed on the stream first.
+// MEASURED (65,536 solves, one B200): 0.88 ms, the same as the fused kernel (0.873 ms) -- and so were a chunked version (one
+// wave of sweeps per launch, the previous chunk's rollout beside it: 0.98-1.04 ms, each wave ends on the slowest scheduler)
+// and a register-only rollout kernel at two CTAs per SM.  What the experiments show instead: the sweep alone (gains stored,
+// no rollout) takes 0.727 ms = 4 rounds of 592 one-warp CTAs at ~182 us (65,536 problems are 3.46 rounds: the last one is
+// half empty), and the rollout needs ~45 us per 32-problem group however it is fed, so ~5,000 problems must be in flight
+// to keep up with the sweep -- more than the registers and shared memory left beside it hold.  Opt-in (ZB_MPC_SPLIT_ROLLOUT).
+constexpr size_t ROLL_SMEM = (size_t)t1::ROLL_D * 3 * 128 * sizeof(float4);
+template <bool QDIAG>
+inline int32_t riccati_t1_sweep_only(const FastP& F, cudaStream_t stream) {
+    // FOUR sweep CTAs per SM (one warp per scheduler: the same throughput as five, which only make two warps share a
+    // scheduler) leave room for one rollout CTA and its gain ring: the request is padded so that exactly four fit beside it
+    size_t smem = (size_t)(QDIAG ? t1::NF4_DIAG : t1::NF4) * 32 * sizeof(float4);
+    const size_t pad4 = (233472 - (ROLL_SMEM + 1024)) / 4 - 1024;
+    if (QDIAG && smem < pad4) smem = pad4 & ~(size_t)15;
+    ZB_CUDA(cudaFuncSetAttribute(t1::k_riccati_t1<true, QDIAG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    t1::k_riccati_t1<true, QDIAG, false><<<(unsigned)((F.Bsz + 31) / 32), 32, smem, stream>>>(F);
+    ZB_CUDA(cudaGetLastError());
+    return 0;
+}
+inline int32_t riccati_t1_mpc_split_launch(const FastP& F, cudaStream_t stream, bool cost_diagonal, int device, int sm_count, int* flags) {
+    cudaStream_t side;
+    int32_t rc = side_stream(device, &side);
+    if (rc) return rc;
+    // CTAs of two kernels share an SM only under the same shared-memory carve-out: the rollout kernel (no shared memory of
+    // its own) is told to prefer the sweep kernel's maximum carve-out
+    ZB_CUDA(cudaFuncSetAttribute(t1::k_plan_rollout_q4, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    const long long groups = (F.Bsz + 31) / 32;
+    ZB_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)groups, stream));
+    cudaEvent_t ev;
+    ZB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ZB_CUDA(cudaEventRecord(ev, stream));  // fork: the side stream starts once the flags are cleared
+    ZB_CUDA(cudaStreamWaitEvent(side, ev, 0));
+    ZB_CUDA(cudaEventDestroy(ev));  // released once it has completed
+    FastP S = F;
+    S.iters = flags;  // the sweep-only kernel writes the group flags through this field
+    rc = cost_diagonal ? riccati_t1_sweep_only<true>(S, stream) : riccati_t1_sweep_only<false>(S, stream);
+    if (rc) return rc;
+    const long long grid = groups < (long long)sm_count ? groups : (long long)sm_count;  // one persistent rollout CTA per SM
+    ZB_CUDA(cudaFuncSetAttribute(t1::k_plan_rollout_q4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROLL_SMEM));
+    t1::k_plan_rollout_q4<<<(unsigned)grid, 128, ROLL_SMEM, side>>>(F, flags);
+    ZB_CUDA(cudaGetLastError());
+    ZB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ZB_CUDA(cudaEventRecord(ev, side));  // join
+    ZB_CUDA(cudaStreamWaitEvent(stream, ev, 0));
+    ZB_CUDA(cudaEventDestroy(ev));
+    return 0;
 }
 
 

@@ -571,7 +571,7 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
 size_t zb_mpc_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n, int32_t m) {
     size_t e = dtype == ZB_F64 ? 8 : 4;
     const size_t Bpad = ((size_t)Bsz + 31) / 32 * 32;  // the (12,4) kernel stores gains per 32-problem group
-    return align256(e * Bpad * (size_t)admm_ws_elems(N, n, m)) + 256;  // >= the gains buffer of the unconstrained path
+    return align256(e * Bpad * (size_t)admm_ws_elems(N, n, m)) + align256(sizeof(int) * (Bpad / 32)) + 512;  // >= the gains buffer of the unconstrained path + its group flags
 }
 
 int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t n, int32_t m,
@@ -624,7 +624,17 @@ int32_t zb_mpc_lqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bs
         F.uTraj = reinterpret_cast<float*>(uTraj);
         F.status = status_out;
         F.iters = iters_out;
-        return riccati_t1_launch<true>(F, (cudaStream_t)stream, (flags & ZB_COST_DIAGONAL) != 0);
+        const bool diag = (flags & ZB_COST_DIAGONAL) != 0;
+        int sm_count = 0;
+        ZB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+        // opt-in: sweep and plan rollout as two concurrent kernels (measured equal to the fused kernel, see lqr_t1.cuh)
+        if ((flags & ZB_MPC_SPLIT_ROLLOUT) && diag && Bsz > (int64_t)sm_count * 4 * 32)
+        {   // the group flags live behind the gains in the workspace
+            const size_t gains_bytes = (((size_t)Bsz + 31) / 32) * 32 * (size_t)N * 48 * sizeof(float);
+            int* flags = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + ((gains_bytes + 255) & ~(size_t)255));
+            return riccati_t1_mpc_split_launch(F, (cudaStream_t)stream, diag, device, sm_count, flags);
+        }
+        return riccati_t1_launch<true>(F, (cudaStream_t)stream, diag);
     }
     if (fast_ok && dtype == ZB_F64 && n == 12 && m == 4 && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) && arr_ok(P.R) && arr_ok(P.Qf) &&
         aligned16(x0) && aligned16(u0_out) && aligned16(xTraj) && aligned16(uTraj) && aligned16(workspace)) {

@@ -102,6 +102,23 @@ inline int32_t check_dims(int32_t dtype, int64_t Bsz, int32_t n, int32_t m) {
     return 0;
 }
 
+// One non-blocking side stream per (host thread, device), created on first use and kept: the fork/join overlap of
+// lqrMpc.solve's plan rollout with the next chunk's sweep (lqr_t1.cuh) runs its rollouts there.
+inline int32_t side_stream(int device, cudaStream_t* out) {
+    static thread_local cudaStream_t streams[64] = {nullptr};
+    ZB_ARG(device >= 0 && device < 64, "device index %d out of range", device);
+    if (!streams[device]) {
+        // greatest priority: the block scheduler keeps dispatching the CTAs of the kernel it started first and turns to another
+        // equal-priority kernel only when that grid is exhausted; a higher-priority kernel gets its (few, small) CTAs placed
+        // as soon as they fit
+        int lo = 0, hi = 0;
+        ZB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = greatest priority (numerically lowest)
+        ZB_CUDA(cudaStreamCreateWithPriority(&streams[device], cudaStreamNonBlocking, hi));
+    }
+    *out = streams[device];
+    return 0;
+}
+
 constexpr int GEN_THREADS = 64;  // generic kernels: threads per block (local-memory heavy)
 inline unsigned gen_grid(long long work) { return (unsigned)((work + GEN_THREADS - 1) / GEN_THREADS); }
 

@@ -108,6 +108,8 @@ class lqrMpc():
         cvxpy in the reference demo; honoured: `eps_abs`, `eps_rel`, `max_iter`, `rho` (initial, then residual-balanced),
         `alpha` (over-relaxation), `check_termination`, `eps_prim_inf`.  Others are accepted and ignored -- in particular
         `sigma`: OSQP regularises its KKT system with it, the Riccati-structured solve here needs no regularisation.
+        `kernel="split"` (bounds inactive, fp32 (12,4), diagonal costs, multi-wave batches) runs the sweep and the plan rollout as two
+        concurrent kernels instead of the fused one (an experiment that measured equal; same bits).
         `kernel="generic"` forces the generic one-thread-per-problem ADMM kernel where the shared-definition (12,4) kernels would
         run; `"thread"` / `"quad"` pick the shared-definition kernel with one / four threads per problem (default: by batch size).
 
@@ -146,7 +148,8 @@ class lqrMpc():
         wsb = lib.zb_mpc_workspace_bytes(dcode(dt), Bsz, N, n, m)
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         check(lib.zb_mpc_lqr_solve(dcode(dt), dev.index, stream_ptr(dev), Bsz, N, n, m, *[v.ref() for v in self.views],
-                                   (1 if self.bounded else 0) | (2 if self.cost_diagonal else 0) | (0 if self.cost_symmetric else 128), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
+                                   (1 if self.bounded else 0) | (2 if self.cost_diagonal else 0) | (0 if self.cost_symmetric else 128) |
+                                   (512 if kwargs.get("kernel") == "split" else 0), ptr(x0), C.byref(opts), ptr(u0), ptr(xTraj), ptr(uTraj), ptr(status),
                                    ptr(iters), ptr(ws), wsb))
         self.iters = iters
         if not batched:
