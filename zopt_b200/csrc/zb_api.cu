@@ -17,6 +17,7 @@ namespace zb {
 int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream);  // zb_small_batch.cu
 }
 
+#define ZB_FORCE_RUNTIME_SIZES ZB_FORCE_GENERIC
 #ifndef ZB_EXIT_CHECK
 #define ZB_EXIT_CHECK 4  // zb_ilqr_solve: iterations between two "is anything still iterating" reads
 #endif
@@ -39,6 +40,21 @@ __global__ void __launch_bounds__(GEN_THREADS) k_bilinear_generic(BilinP P) {
     if (b < P.Bsz) bilinear_problem<T>(P, b);
 }
 
+// compile-time (n, m) variants of the two kernels above (zb_steps.cuh): the shapes of the reference's demos and tests
+template <typename T, int N_, int M_>
+__global__ void __launch_bounds__(GEN_THREADS) k_lqr_ct(LqrP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b < P.Bsz) lqr_problem_ct<T, N_, M_>(P, b);
+}
+template <typename T, int N_, int M_>
+__global__ void __launch_bounds__(GEN_THREADS) k_bilinear_ct(BilinP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b < P.Bsz) bilinear_problem_ct<T, N_, M_>(P, b);
+}
+#define ZB_CT_SHAPES(X) X(8, 4) X(2, 1) X(2, 2)
+// fp64 at n = 8 does not fit one thread's registers (V, A - BL and V(A - BL) alone are 384): measured slower than the
+// run-time-size kernel (0.9 vs 1.2 M solves/s), so fp64 keeps the compile-time variant for the tiny shapes only
+#define ZB_CT_F64_OK(N_) ((N_) <= 4)
 struct QuadP {
     long long Bsz;
     const void *x, *u, *lam;
@@ -295,6 +311,15 @@ int32_t zb_lqr_dfh_flags(int32_t dtype, int32_t device, void* stream, int64_t Bs
         F.L = L_out; F.V0 = V0_out;
         return riccati_quad_launch(dtype, F, (cudaStream_t)stream);
     }
+#define ZB_CT_LQR(N_, M_)                                                                                   \
+    if (n == N_ && m == M_ && (dtype == ZB_F32 || ZB_CT_F64_OK(N_)) && !getenv("ZB_FORCE_RUNTIME_SIZES")) {   \
+        if (dtype == ZB_F32) k_lqr_ct<float, N_, M_><<<gen_grid(Bsz), GEN_THREADS, 0, (cudaStream_t)stream>>>(P);   \
+        else k_lqr_ct<double, (ZB_CT_F64_OK(N_) ? N_ : 2), (ZB_CT_F64_OK(N_) ? M_ : 1)><<<gen_grid(Bsz), GEN_THREADS, 0, (cudaStream_t)stream>>>(P); \
+        ZB_CUDA(cudaGetLastError());                                                                        \
+        return 0;                                                                                           \
+    }
+    ZB_CT_SHAPES(ZB_CT_LQR)
+#undef ZB_CT_LQR
     ZB_DISPATCH(dtype, k_lqr_generic, gen_grid(Bsz), GEN_THREADS, stream, P);
     return 0;
 }
@@ -315,6 +340,15 @@ int32_t zb_lqr_bilinear(int32_t dtype, int32_t device, void* stream, int64_t Bsz
     ZB_CUDA(g.err);
     BilinP P{Bsz, N, T, n, m, to_arr(A), to_arr(B), to_arr(d), to_arr(Q), to_arr(R), to_arr(H), to_arr(q), to_arr(r),
              to_arr(q0), L_out, l_out};
+#define ZB_CT_BIL(N_, M_)                                                                                        \
+    if (n == N_ && m == M_ && (dtype == ZB_F32 || ZB_CT_F64_OK(N_)) && !getenv("ZB_FORCE_RUNTIME_SIZES")) {        \
+        if (dtype == ZB_F32) k_bilinear_ct<float, N_, M_><<<gen_grid(Bsz), GEN_THREADS, 0, (cudaStream_t)stream>>>(P);   \
+        else k_bilinear_ct<double, (ZB_CT_F64_OK(N_) ? N_ : 2), (ZB_CT_F64_OK(N_) ? M_ : 1)><<<gen_grid(Bsz), GEN_THREADS, 0, (cudaStream_t)stream>>>(P); \
+        ZB_CUDA(cudaGetLastError());                                                                             \
+        return 0;                                                                                                \
+    }
+    ZB_CT_SHAPES(ZB_CT_BIL)
+#undef ZB_CT_BIL
     ZB_DISPATCH(dtype, k_bilinear_generic, gen_grid(Bsz), GEN_THREADS, stream, P);
     return 0;
 }

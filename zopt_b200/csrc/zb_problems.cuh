@@ -45,6 +45,25 @@ ZB_HD void lqr_problem(const LqrP& P, long long b) {
     }
 }
 
+template <typename T, int N_, int M_>
+ZB_HD void lqr_problem_ct(const LqrP& P, long long b) {  // lqr_problem with compile-time (n, m): operands in registers
+    T V[N_ * N_], L[M_ * N_];
+    const T* Qf = P.Q.at<T>(b, P.T - 1);
+    ZB_UNROLL
+    for (int i = 0; i < N_ * N_; ++i) V[i] = Qf[i];
+    T* Lout = reinterpret_cast<T*>(P.L) + b * (long long)P.N * M_ * N_;
+    for (int k = P.N - 1; k >= 0; --k) {
+        lqr_joseph_step_ct<T, N_, M_>(P.A.at<T>(b, k), P.B.at<T>(b, k), P.Q.at<T>(b, k), P.R.at<T>(b, k), V, L);
+        ZB_UNROLL
+        for (int i = 0; i < M_ * N_; ++i) Lout[(long long)k * M_ * N_ + i] = L[i];
+    }
+    if (P.V0) {
+        T* V0 = reinterpret_cast<T*>(P.V0) + b * N_ * N_;
+        ZB_UNROLL
+        for (int i = 0; i < N_ * N_; ++i) V0[i] = V[i];
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 struct BilinP {
     long long Bsz;
@@ -70,6 +89,27 @@ ZB_HD void bilinear_problem(const BilinP& P, long long b) {
                          P.H.at<T>(b, k), P.q.at<T>(b, k), P.r.at<T>(b, k), *P.q0.at<T>(b, k), V, v, v0, L, l);
         for (int i = 0; i < m * n; ++i) Lout[(long long)k * m * n + i] = L[i];
         for (int i = 0; i < m; ++i) lout[(long long)k * m + i] = l[i];
+    }
+}
+
+template <typename T, int N_, int M_>
+ZB_HD void bilinear_problem_ct(const BilinP& P, long long b) {  // bilinear_problem with compile-time (n, m)
+    T V[N_ * N_], v[N_], L[M_ * N_], l[M_];
+    const T* Qf = P.Q.at<T>(b, P.T - 1);
+    const T* qf = P.q.at<T>(b, P.T - 1);
+    ZB_UNROLL
+    for (int i = 0; i < N_ * N_; ++i) V[i] = Qf[i];
+    ZB_UNROLL
+    for (int i = 0; i < N_; ++i) v[i] = qf[i];
+    T* Lout = reinterpret_cast<T*>(P.L) + b * (long long)P.N * M_ * N_;
+    T* lout = reinterpret_cast<T*>(P.l) + b * (long long)P.N * M_;
+    for (int k = P.N - 1; k >= 0; --k) {
+        bilinear_step_ct<T, N_, M_>(P.A.at<T>(b, k), P.B.at<T>(b, k), P.d.at<T>(b, k), P.Q.at<T>(b, k), P.R.at<T>(b, k),
+                                    P.H.at<T>(b, k), P.q.at<T>(b, k), P.r.at<T>(b, k), V, v, L, l);
+        ZB_UNROLL
+        for (int i = 0; i < M_ * N_; ++i) Lout[(long long)k * M_ * N_ + i] = L[i];
+        ZB_UNROLL
+        for (int i = 0; i < M_; ++i) lout[(long long)k * M_ + i] = l[i];
     }
 }
 

@@ -79,6 +79,141 @@ ZB_HD void bilinear_step(int n, int m, const T* A, const T* B, const T* d, const
     for (int i = 0; i < n * n; ++i) V[i] += Q[i] - W[i];
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// The two LQR steps above with COMPILE-TIME (n, m): every loop unrolls and V, W, A, B ... live in registers instead of
+// local memory (the run-time-sized bodies index per-thread arrays dynamically, so all of their operands sit in local
+// memory: ~1-2 M solves/s).  Used for the shapes of the reference's demos and tests, (8,4) and (2,1)/(2,2)
+// (demos/discreteFiniteHorizonLqr.py:29-35, demos/bilinearLqrControl.py:21-43, tests/test_lqrUtils.py:61-98).
+// Same formulas in the same order; the m x m system is solved by Gaussian elimination WITHOUT pivoting (S_uu = R + B'VB is
+// symmetric positive definite), which differs from LAPACK's pivoted LU at rounding level only.
+#if defined(__CUDACC__)
+#define ZB_UNROLL _Pragma("unroll")
+#else
+#define ZB_UNROLL
+#endif
+
+template <typename T, int M_, int NR>
+ZB_HD void spd_solve_ct(T* G, T* X) {  // G (M_ x M_) SPD, X (M_ x NR) right-hand sides -> G^-1 X
+    ZB_UNROLL
+    for (int c = 0; c < M_; ++c) {
+        const T inv = T(1) / G[c * M_ + c];
+        ZB_UNROLL
+        for (int i = c + 1; i < M_; ++i) {
+            const T f = G[i * M_ + c] * inv;
+            ZB_UNROLL
+            for (int j = c + 1; j < M_; ++j) G[i * M_ + j] -= f * G[c * M_ + j];
+            ZB_UNROLL
+            for (int j = 0; j < NR; ++j) X[i * NR + j] -= f * X[c * NR + j];
+        }
+    }
+    ZB_UNROLL
+    for (int i = M_ - 1; i >= 0; --i) {
+        const T inv = T(1) / G[i * M_ + i];
+        ZB_UNROLL
+        for (int j = 0; j < NR; ++j) {
+            T s = X[i * NR + j];
+            ZB_UNROLL
+            for (int k = i + 1; k < M_; ++k) s -= G[i * M_ + k] * X[k * NR + j];
+            X[i * NR + j] = s * inv;
+        }
+    }
+}
+
+// C (P_ x R_) = A (P_ x Q_) B (Q_ x R_)   /   C = A' B with A stored (Q_ x P_)
+template <typename T, int P_, int Q_, int R_, bool TA>
+ZB_HD void mm_ct(T* C, const T* A, const T* B) {
+    ZB_UNROLL
+    for (int i = 0; i < P_; ++i)
+        ZB_UNROLL
+        for (int j = 0; j < R_; ++j) {
+            T s = T(0);
+            ZB_UNROLL
+            for (int k = 0; k < Q_; ++k) s += (TA ? A[k * P_ + i] : A[i * Q_ + k]) * B[k * R_ + j];
+            C[i * R_ + j] = s;
+        }
+}
+
+// zopt/lqrUtils.py:167-170 (Joseph form, as written).  A, B, Q, R: global pointers (copied to registers here).
+template <typename T, int N_, int M_>
+ZB_HD void lqr_joseph_step_ct(const T* gA, const T* gB, const T* gQ, const T* gR, T* V, T* L) {
+    T A[N_ * N_], B[N_ * M_], R[M_ * M_], BtV[M_ * N_], G[M_ * M_], W[N_ * N_];
+    ZB_UNROLL
+    for (int i = 0; i < N_ * N_; ++i) A[i] = gA[i];
+    ZB_UNROLL
+    for (int i = 0; i < N_ * M_; ++i) B[i] = gB[i];
+    ZB_UNROLL
+    for (int i = 0; i < M_ * M_; ++i) R[i] = gR[i];
+    mm_ct<T, M_, N_, N_, true>(BtV, B, V);   // B'V
+    mm_ct<T, M_, N_, M_, false>(G, BtV, B);  // B'VB
+    ZB_UNROLL
+    for (int i = 0; i < M_ * M_; ++i) G[i] += R[i];
+    mm_ct<T, M_, N_, N_, false>(L, BtV, A);  // B'VA
+    spd_solve_ct<T, M_, N_>(G, L);           // L = (R + B'VB)^-1 B'VA
+    mm_ct<T, N_, M_, N_, false>(W, B, L);    // B L
+    ZB_UNROLL
+    for (int i = 0; i < N_ * N_; ++i) A[i] -= W[i];  // Acl = A - B L
+    mm_ct<T, N_, N_, N_, false>(W, V, A);    // V Acl
+    mm_ct<T, N_, N_, N_, true>(V, A, W);     // Acl' V Acl
+    mm_ct<T, M_, M_, N_, false>(BtV, R, L);  // R L
+    mm_ct<T, N_, M_, N_, true>(W, L, BtV);   // L' R L
+    ZB_UNROLL
+    for (int i = 0; i < N_ * N_; ++i) V[i] += gQ[i] + W[i];
+}
+
+// zopt/lqrUtils.py:242-259 (the scalar carry v0 does not feed (L, l) and is not formed)
+template <typename T, int N_, int M_>
+ZB_HD void bilinear_step_ct(const T* gA, const T* gB, const T* d, const T* gQ, const T* gR, const T* gH, const T* q, const T* r,
+                            T* V, T* v, T* L, T* l) {
+    T A[N_ * N_], B[N_ * M_], vVd[N_], BtV[M_ * N_], Suu[M_ * M_], Sf[M_ * M_], Sux[M_ * N_], rhs[M_ * (N_ + 1)], W[N_ * N_];
+    ZB_UNROLL
+    for (int i = 0; i < N_ * N_; ++i) A[i] = gA[i];
+    ZB_UNROLL
+    for (int i = 0; i < N_ * M_; ++i) B[i] = gB[i];
+    ZB_UNROLL
+    for (int i = 0; i < N_; ++i) {  // v + V d
+        T s = T(0);
+        ZB_UNROLL
+        for (int k = 0; k < N_; ++k) s += V[i * N_ + k] * d[k];
+        vVd[i] = v[i] + s;
+    }
+    mm_ct<T, M_, N_, N_, true>(BtV, B, V);
+    mm_ct<T, M_, N_, M_, false>(Suu, BtV, B);
+    mm_ct<T, M_, N_, N_, false>(Sux, BtV, A);
+    ZB_UNROLL
+    for (int i = 0; i < M_ * M_; ++i) { Suu[i] += gR[i]; Sf[i] = Suu[i]; }
+    ZB_UNROLL
+    for (int i = 0; i < M_; ++i) {  // [Sux | Su], Su = r + B'(v + V d)
+        T s = T(0);
+        ZB_UNROLL
+        for (int k = 0; k < N_; ++k) s += B[k * M_ + i] * vVd[k];
+        ZB_UNROLL
+        for (int j = 0; j < N_; ++j) { Sux[i * N_ + j] += gH[i * N_ + j]; rhs[i * (N_ + 1) + j] = Sux[i * N_ + j]; }
+        rhs[i * (N_ + 1) + N_] = s + r[i];
+    }
+    spd_solve_ct<T, M_, N_ + 1>(Sf, rhs);
+    ZB_UNROLL
+    for (int i = 0; i < M_; ++i) {
+        ZB_UNROLL
+        for (int j = 0; j < N_; ++j) L[i * N_ + j] = rhs[i * (N_ + 1) + j];
+        l[i] = rhs[i * (N_ + 1) + N_];
+    }
+    ZB_UNROLL
+    for (int i = 0; i < N_; ++i) {  // vNew = q + A'(v + V d) - Sux' l
+        T s = q[i];
+        ZB_UNROLL
+        for (int k = 0; k < N_; ++k) s += A[k * N_ + i] * vVd[k];
+        ZB_UNROLL
+        for (int a = 0; a < M_; ++a) s -= Sux[a * N_ + i] * l[a];
+        v[i] = s;
+    }
+    mm_ct<T, N_, N_, N_, false>(W, V, A);    // V A
+    mm_ct<T, N_, N_, N_, true>(V, A, W);     // A' V A
+    mm_ct<T, M_, M_, N_, false>(BtV, Suu, L);  // Suu L
+    mm_ct<T, N_, M_, N_, true>(W, L, BtV);     // L' Suu L
+    ZB_UNROLL
+    for (int i = 0; i < N_ * N_; ++i) V[i] += gQ[i] - W[i];
+}
+
 // ---- zopt/ilqrUtils.py:153-173 riccatiStep_ilqr  /  :184-206 riccatiStep_ddp -----------------------
 // vf_* (optional, may be null): the eigen-clamped v_x.f_zz blocks of the DDP step.
 // value (v, v_x, v_xx) in/out; policy (l (m), L (m x n)) out.
