@@ -87,6 +87,16 @@ ZB_API int32_t zb_lqr_dfh_flags(int32_t dtype, int32_t device, void* stream, int
                          int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, int32_t flags,
                          void* L_out, void* V0_out);
 
+/* ---- zopt/lqrUtils.py:39-98  finiteHorizonLqr (continuous time): the Riccati differential equation of the LQR HJB,
+ *   -dV/dt = Q + V A + A'V - V B R^-1 B'V,  V(T) = Qf,  integrated backward with RK4, `substeps` steps between two of the N
+ * output points t_i = i T/(N-1) (the reference: jax odeint, adaptive Dormand-Prince at 1.4e-8, same output grid).
+ * A (n,n), B (n,m), Q (n,n), Rinv (m,m) are time series SAMPLED at the scheme's stage times: 2 (N-1) substeps + 1 samples,
+ * sample j at time T - j h/2, h = T / ((N-1) substeps); stride_t = 0 for constant coefficients.  Qf (n,n) blocks.
+ * V_out (Bsz,N,n,n): V_out[i] = V(t_i).  The gains K(t) = R^-1(t) B(t)' V(t) are formed by the caller (lqrUtils.py:95-97). */
+ZB_API int32_t zb_lqr_care_rk4(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t substeps, int32_t n, int32_t m,
+                        double T_horizon, const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* Rinv, const zb_arr* Qf,
+                        void* V_out);
+
 /* ---- zopt/lqrUtils.py:207-262  bilinearAffineLqr(A,B,d,Q,R,H,q,r,q0,N) -> (L,l) ------------------
  * L_out (Bsz,N,m,n), l_out (Bsz,N,m). */
 ZB_API int32_t zb_lqr_bilinear(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,

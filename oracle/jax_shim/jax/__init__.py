@@ -40,7 +40,9 @@ def jit(fun=None, static_argnames=None, static_argnums=None, **kw):
 
 
 def vmap(fun, in_axes=0, out_axes=0):
-    return _F.vmap(fun, in_dims=in_axes, out_dims=out_axes)
+    import numpy as _np
+    mapped = _F.vmap(fun, in_dims=in_axes, out_dims=out_axes)
+    return lambda *a, **k: mapped(*[torch.as_tensor(_np.ascontiguousarray(x)) if isinstance(x, _np.ndarray) else x for x in a], **k)
 
 
 def jacobian(fun, argnums=0):

@@ -53,8 +53,17 @@ def arange(*a):
     return torch.arange(*a)
 
 
-def linspace(a, b, n):
-    return torch.linspace(a, b, n, dtype=torch.float64)
+def linspace(a, b, num=50):
+    return torch.linspace(a, b, num, dtype=torch.float64)
+
+
+def interp(x, xp, fp, left=None, right=None, period=None):
+    """np.interp for a scalar query (clipped at the ends), written so that jax.vmap over `fp` rows works"""
+    xp, fp = _t(xp), _t(fp)
+    xq = min(max(float(x), float(xp[0])), float(xp[-1]))
+    i = min(max(int(torch.searchsorted(xp, torch.tensor(xq, dtype=xp.dtype), right=True)) - 1, 0), len(xp) - 2)
+    w = (xq - float(xp[i])) / (float(xp[i + 1]) - float(xp[i]))
+    return fp[i] * (1.0 - w) + fp[i + 1] * w
 
 
 sin, cos, tan = (lambda x: torch.sin(_t(x))), (lambda x: torch.cos(_t(x))), (lambda x: torch.tan(_t(x)))

@@ -120,3 +120,28 @@ def bilinearAffineLqr_batched(A, B, d, Q, R, H, q, r, q0, N):
         LArr[:, k] = L
         lArr[:, k] = l
     return LArr, lArr
+
+
+def finiteHorizonLqr(A, B, Q, R_inv, Qf, T, N=50):
+    """zopt/lqrUtils.py:55-98 (with _lqrHjb :39-52): integrate `dV/ds = Q - V B R^-1 B' V + V A + A' V` in reversed time
+    s = T - t from V = Qf, report on `linspace(0, T, N)`, return `K(t) = R^-1(t) B(t)' interp(V)(t)`.
+    jax's `odeint` is an adaptive Dormand-Prince 5(4) with rtol = atol = 1.4e-8; SciPy's `RK45` is the same pair and is run
+    at the same tolerances (so the two agree to the integrator's tolerance, not bit for bit)."""
+    import scipy.integrate as spi
+    Qf = np.asarray(Qf, dtype=float)
+    n = np.asarray(A(0)).shape[0]
+    t = np.linspace(0, T, num=N)
+
+    def hjb(tq, V):  # lqrUtils.py:49-52
+        V = V.reshape((n, n))
+        At, Bt = np.asarray(A(tq), dtype=float), np.asarray(B(tq), dtype=float)
+        dV = -np.asarray(Q(tq), dtype=float) + V @ Bt @ np.asarray(R_inv(tq), dtype=float) @ Bt.T @ V - V @ At - At.T @ V
+        return dV.reshape(-1)
+
+    sol = spi.solve_ivp(lambda s, V: -hjb(T - s, V), (0, T), Qf.reshape(-1), method="RK45", t_eval=t, rtol=1.4e-8, atol=1.4e-8)
+    out = sol.y.T                      # (N, n*n), out[i] = V(T - t_i)
+    V = out[::-1].T                    # lqrUtils.py:94
+    Vfun = lambda tq: np.array([np.interp(tq, t, row) for row in V])  # interpMapped (jaxUtils.py:7-24)
+    K = lambda tq: np.asarray(R_inv(tq), dtype=float) @ np.asarray(B(tq), dtype=float).T @ Vfun(tq).reshape((n, n))
+    K.V = out[::-1].reshape(N, n, n)
+    return K

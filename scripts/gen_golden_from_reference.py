@@ -181,6 +181,24 @@ tB, _, xB, uB, _ = ref_sim.Simulator([ctlB, dynB], (0, 10)).simulate()
 np.savez(os.path.join(OUT, "simulator_demos.npz"), b_t=npy(tB), b_x=npy(xB), b_u=npy(uB), b_x0=x0b, b_K=npy(Kd), b_uTrim=npy(uTrim), **sim_a)
 print("simulator (lqr gains)", npy(xB).shape, npy(uB).shape)
 
+
+# ---- (ix) continuous-time finiteHorizonLqr (zopt/lqrUtils.py:55-98) on a time-varying problem (jax odeint -> SciPy RK45 at the
+#      same tolerances in the shim): the value matrices on the output grid and the gains at off-grid times -------------------
+rng = np.random.default_rng(1234 + 13)
+nc, mc, Tc, Nc = 4, 2, 1.5, 12
+A0, A1 = 0.5 * rng.normal(size=(nc, nc)), 0.3 * rng.normal(size=(nc, nc))
+B0, B1 = rng.normal(size=(nc, mc)), 0.2 * rng.normal(size=(nc, mc))
+Qc, Ric, Qfc = np.diag(rng.uniform(0.5, 2, nc)), np.diag(1.0 / rng.uniform(0.5, 2, mc)), 2.0 * np.eye(nc)
+Afun = lambda t: T(A0 + np.sin(2.0 * float(t)) * A1)
+Bfun = lambda t: T(B0 + float(t) * B1)
+Qfun = lambda t: T((1.0 + 0.5 * float(t)) * Qc)
+Rifun = lambda t: T(Ric)
+Kc = ref_lqr.finiteHorizonLqr(Afun, Bfun, Qfun, Rifun, T(Qfc), Tc, N=Nc)
+tq = np.array([0.0, 0.1, 0.37, 0.75, 1.2, 1.5, 2.0])
+np.savez(os.path.join(OUT, "care_tv.npz"), A0=A0, A1=A1, B0=B0, B1=B1, Q=Qc, R_inv=Ric, Qf=Qfc, T=Tc, N=Nc, tq=tq,
+         K=np.array([npy(Kc(t)) for t in tq]))
+print("care_tv", np.array([npy(Kc(t)) for t in tq]).shape)
+
 # ---- (viii) iLQR / DDP at BASELINE cfg 4 / cfg 5 size: N = 200 x 10 iterations (iLQR), N = 100 x 10 iterations (DDP), four
 #      problems each from the configs' own initial-state distributions; per-iteration J, step-size index, final x, u, L ------
 

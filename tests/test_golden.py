@@ -123,6 +123,32 @@ def test_oracle_solver_goldens_bench_size(name):
     assert relerr(traj.xTraj, g["xTraj"][0]) < 1e-9 and relerr(traj.uTraj, g["uTraj"][0]) < 1e-9 and relerr(L, g["L"][0]) < 1e-9
 
 
+
+def _care_problem():
+    g = load("care_tv.npz")
+    A = lambda t: g["A0"] + np.sin(2.0 * float(t)) * g["A1"]
+    B = lambda t: g["B0"] + float(t) * g["B1"]
+    Q = lambda t: (1.0 + 0.5 * float(t)) * g["Q"]
+    Ri = lambda t: g["R_inv"]
+    return g, A, B, Q, Ri
+
+
+def test_oracle_continuous_finite_horizon_lqr():
+    """oracle.lqr.finiteHorizonLqr (zopt/lqrUtils.py:39-98) against the reference's own test (tests/test_lqrUtils.py:31-44:
+    K(T) = I exactly, K(0) = the analytic scalar Riccati solution) and against the reference run on the shim for a
+    time-varying problem, at grid and off-grid times (both integrate with a Dormand-Prince pair at 1.4e-8)."""
+    I2 = lambda t: np.eye(2)
+    K = olqr.finiteHorizonLqr(I2, I2, I2, I2, np.eye(2), 1, N=4)
+    assert np.allclose(K(1), np.eye(2), atol=1e-12)
+    s2 = np.sqrt(2)
+    K_exp = lambda t: ((1 + s2) * np.exp(2 * s2) - (s2 - 1) * np.exp(2 * s2 * t)) / (np.exp(2 * s2 * t) + np.exp(2 * s2))
+    assert np.allclose(K(0), K_exp(0) * np.eye(2), rtol=1e-6)
+    g, A, B, Q, Ri = _care_problem()
+    K = olqr.finiteHorizonLqr(A, B, Q, Ri, g["Qf"], float(g["T"]), N=int(g["N"]))
+    for tq, Kr in zip(g["tq"], g["K"]):
+        assert relerr(K(tq), Kr) < 1e-9
+
+
 def test_oracle_riccati_step_goldens():
     g = load("riccati_steps.npz")
     n = 5
@@ -247,3 +273,41 @@ def test_gpu_simulator_goldens():
                      SimBlock(QuadcopterEuler(0.1), g["b_x0"], dt=0.1)], (0, 10))
     tS, _, xS, uS, _ = sim.simulate()
     assert np.allclose(tS.cpu().numpy(), g["b_t"]) and relerr(xS, g["b_x"]) < 1e-10 and relerr(uS, g["b_u"]) < 1e-10
+
+
+@pytest.mark.gpu
+def test_gpu_continuous_finite_horizon_lqr():
+    """zopt_b200.lqrUtils.finiteHorizonLqr (fixed-step RK4 kernel, coefficients sampled at the stage times) against the
+    reference's test values, the reference run on the shim (time-varying coefficients, grid and off-grid times, clipping
+    outside [0, T]) and the oracle; batched call with per-problem Qf; fp64 1e-7 (the reference's integrator runs at 1.4e-8),
+    fp32 1e-4."""
+    from zopt_b200.lqrUtils import finiteHorizonLqr
+    I2 = lambda t: np.eye(2)
+    K = finiteHorizonLqr(I2, I2, I2, I2, np.eye(2), 1, N=4)
+    assert relerr(K(1), np.eye(2)) < 1e-14
+    s2 = np.sqrt(2)
+    K_exp = lambda t: ((1 + s2) * np.exp(2 * s2) - (s2 - 1) * np.exp(2 * s2 * t)) / (np.exp(2 * s2 * t) + np.exp(2 * s2))
+    assert relerr(K(0), K_exp(0) * np.eye(2)) < 1e-8
+    assert relerr(finiteHorizonLqr(np.eye(2), np.eye(2), np.eye(2), np.eye(2), np.eye(2), 1, N=4)(0), K_exp(0) * np.eye(2)) < 1e-8  # constant matrices
+    g, A, B, Q, Ri = _care_problem()
+    T_, N_ = float(g["T"]), int(g["N"])
+    K = finiteHorizonLqr(A, B, Q, Ri, g["Qf"], T_, N=N_)
+    assert K.V.shape == (N_, 4, 4) and K(0.3).shape == (2, 4)
+    for tq, Kr in zip(g["tq"], g["K"]):
+        assert relerr(K(tq), Kr) < 1e-7
+    Ko = olqr.finiteHorizonLqr(A, B, Q, Ri, g["Qf"], T_, N=N_)
+    assert relerr(K.V, Ko.V) < 1e-7
+    # batched: per-problem terminal cost and a batched callable; every problem equals its own un-batched solve
+    rng = np.random.default_rng(2)
+    Qfb = np.stack([s * g["Qf"] for s in (0.5, 1.0, 3.0)])
+    Ab = lambda t: np.stack([A(t), 0.5 * A(t), A(t) + 0.1 * np.eye(4)])
+    Kb = finiteHorizonLqr(Ab, B, Q, Ri, Qfb, T_, N=N_)
+    assert Kb.V.shape == (3, N_, 4, 4) and Kb(0.4).shape == (3, 2, 4)
+    for i, (Ai, s) in enumerate(zip((A, lambda t: 0.5 * A(t), lambda t: A(t) + 0.1 * np.eye(4)), (0.5, 1.0, 3.0))):
+        Ki = olqr.finiteHorizonLqr(Ai, B, Q, Ri, s * g["Qf"], T_, N=N_)
+        assert relerr(Kb(0.4)[i], Ki(0.4)) < 1e-7
+    K32 = finiteHorizonLqr(lambda t: A(t).astype(np.float32), lambda t: B(t).astype(np.float32), lambda t: Q(t).astype(np.float32),
+                           lambda t: Ri(t).astype(np.float32), g["Qf"].astype(np.float32), T_, N=N_)
+    assert K32.V.dtype == torch.float32 and relerr(K32(0.37), g["K"][2]) < 1e-4
+    with pytest.raises(ValueError):
+        finiteHorizonLqr(A, B, Q, Ri, np.eye(3), T_, N=N_)

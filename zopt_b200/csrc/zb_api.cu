@@ -55,6 +55,12 @@ __global__ void __launch_bounds__(GEN_THREADS) k_bilinear_ct(BilinP P) {
 // fp64 at n = 8 does not fit one thread's registers (V, A - BL and V(A - BL) alone are 384): measured slower than the
 // run-time-size kernel (0.9 vs 1.2 M solves/s), so fp64 keeps the compile-time variant for the tiny shapes only
 #define ZB_CT_F64_OK(N_) ((N_) <= 4)
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_care_rk4(CareP P) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b < P.Bsz) care_problem<T>(P, b);
+}
+
 struct QuadP {
     long long Bsz;
     const void *x, *u, *lam;
@@ -350,6 +356,22 @@ int32_t zb_lqr_bilinear(int32_t dtype, int32_t device, void* stream, int64_t Bsz
     ZB_CT_SHAPES(ZB_CT_BIL)
 #undef ZB_CT_BIL
     ZB_DISPATCH(dtype, k_bilinear_generic, gen_grid(Bsz), GEN_THREADS, stream, P);
+    return 0;
+}
+
+int32_t zb_lqr_care_rk4(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t substeps, int32_t n, int32_t m,
+                        double T_horizon, const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* Rinv, const zb_arr* Qf,
+                        void* V_out) {
+    int32_t rc = check_dims(dtype, Bsz, n, m);
+    if (rc) return rc;
+    ZB_ARG(N >= 2 && substeps >= 1, "need N >= 2 output points and substeps >= 1 (got %d, %d)", N, substeps);
+    ZB_ARG(T_horizon > 0, "the horizon T must be positive");
+    if (Bsz == 0) return 0;
+    ZB_ARG(A && B && Q && Rinv && Qf && A->ptr && B->ptr && Q->ptr && Rinv->ptr && Qf->ptr && V_out, "NULL operand");
+    DeviceGuard g(device);
+    ZB_CUDA(g.err);
+    CareP P{Bsz, N, substeps, n, m, T_horizon / ((double)(N - 1) * substeps), to_arr(A), to_arr(B), to_arr(Q), to_arr(Rinv), to_arr(Qf), V_out};
+    ZB_DISPATCH(dtype, k_care_rk4, gen_grid(Bsz), GEN_THREADS, stream, P);
     return 0;
 }
 

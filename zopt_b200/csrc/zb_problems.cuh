@@ -65,6 +65,62 @@ ZB_HD void lqr_problem_ct(const LqrP& P, long long b) {  // lqr_problem with com
 }
 
 // -------------------------------------------------------------------------------------------------
+// Continuous-time finite-horizon LQR (zopt/lqrUtils.py:39-98): the Riccati differential equation of the LQR HJB,
+//   -dV/dt = Q + V A + A' V - V B R^-1 B' V,   V(T) = Qf,
+// integrated backward from T with the classical RK4 scheme on a uniform grid (`sub` steps per output interval; the reference
+// uses jax's adaptive Dormand-Prince at rtol = atol = 1.4e-8 and reports on the same N-point grid).  The coefficient
+// functions A(t), B(t), Q(t), R^-1(t) are arbitrary Python callables in the reference; here they arrive SAMPLED at the
+// scheme's stage times (two samples per step + 1: sample j is time T - j h/2), shared by the batch or per problem.
+struct CareP {
+    long long Bsz;
+    int N, sub, n, m;  // N output points, `sub` RK4 steps between two of them
+    double h;          // step
+    Arr A, B, Q, Rinv; // time series of 2 (N-1) sub + 1 samples (st = 0: constant)
+    Arr Qf;
+    void* V;           // (Bsz, N, n, n): V[i] = V(t_i), t_i = i T/(N-1)  (the reference's `out[::-1]`)
+};
+
+template <typename T>
+ZB_HD void care_rhs(int n, int m, const T* A, const T* B, const T* Q, const T* Ri, const T* V, T* dV) {
+    T VB[NX * NU], VBR[NX * NU], W[NX * NX];
+    mm(VB, V, B, n, n, m);        // V B
+    mm(VBR, VB, Ri, n, m, m);     // V B R^-1
+    mm(W, V, A, n, n, n);         // V A
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            T s = Q[i * n + j] + W[i * n + j];
+            for (int k = 0; k < n; ++k) s += A[k * n + i] * V[k * n + j];          // A' V
+            for (int a = 0; a < m; ++a) s -= VBR[i * m + a] * VB[j * m + a];       // (V B R^-1)(V B)'   (V symmetric)
+            dV[i * n + j] = s;
+        }
+}
+
+template <typename T>
+ZB_HD void care_problem(const CareP& P, long long b) {
+    const int n = P.n, m = P.m, nn = n * n;
+    T V[NX * NX], k1[NX * NX], k2[NX * NX], k3[NX * NX], k4[NX * NX], Vt[NX * NX];
+    const T* Qf = P.Qf.at<T>(b);
+    for (int i = 0; i < nn; ++i) V[i] = Qf[i];
+    T* out = reinterpret_cast<T*>(P.V) + b * (long long)P.N * nn;
+    for (int i = 0; i < nn; ++i) out[(long long)(P.N - 1) * nn + i] = V[i];  // V(T) = Qf
+    const T h = T(P.h);
+    long long j = 0;  // sample index: time T - j h/2
+    for (int o = P.N - 2; o >= 0; --o) {
+        for (int s = 0; s < P.sub; ++s, j += 2) {
+            care_rhs<T>(n, m, P.A.at<T>(b, j), P.B.at<T>(b, j), P.Q.at<T>(b, j), P.Rinv.at<T>(b, j), V, k1);
+            for (int i = 0; i < nn; ++i) Vt[i] = V[i] + T(0.5) * h * k1[i];
+            care_rhs<T>(n, m, P.A.at<T>(b, j + 1), P.B.at<T>(b, j + 1), P.Q.at<T>(b, j + 1), P.Rinv.at<T>(b, j + 1), Vt, k2);
+            for (int i = 0; i < nn; ++i) Vt[i] = V[i] + T(0.5) * h * k2[i];
+            care_rhs<T>(n, m, P.A.at<T>(b, j + 1), P.B.at<T>(b, j + 1), P.Q.at<T>(b, j + 1), P.Rinv.at<T>(b, j + 1), Vt, k3);
+            for (int i = 0; i < nn; ++i) Vt[i] = V[i] + h * k3[i];
+            care_rhs<T>(n, m, P.A.at<T>(b, j + 2), P.B.at<T>(b, j + 2), P.Q.at<T>(b, j + 2), P.Rinv.at<T>(b, j + 2), Vt, k4);
+            for (int i = 0; i < nn; ++i) V[i] += h / T(6) * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
+        }
+        for (int i = 0; i < nn; ++i) out[(long long)o * nn + i] = V[i];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 struct BilinP {
     long long Bsz;
     int N, T, n, m;

@@ -5,6 +5,7 @@ Same names, argument order and return values as the reference.  Batched conventi
 every array may carry one extra leading axis `Bsz`; operands without it are shared by the batch.
 Returns torch CUDA tensors; dtype follows the inputs (fp32 only when every input is fp32).
 """
+import numpy as np
 import torch
 
 from ._lib import View, check, dcode, is_symmetric, lib, pick_device, pick_dtype, ptr, stream_ptr, to_dev
@@ -112,6 +113,83 @@ def bilinearAffineLqr(A, B, d, Q, R, H, q, r, q0, N):
     if not any_b:
         return L[0], l[0]
     return L, l
+
+
+def _sample_coefficient(f, times, dtype, device):
+    """A coefficient of finiteHorizonLqr on the integrator's stage times: `f` is a callable of time returning a matrix
+    ((p,q) or (Bsz,p,q), NumPy or torch) as in the reference, or a constant matrix.  Returns (tensor, has_time, batched)."""
+    if not callable(f):
+        t = to_dev(f, dtype, device)
+        return t, False, t.ndim == 3
+    first = f(float(times[0]))
+    vals = [to_dev(first, dtype, device)] + [to_dev(f(float(tq)), dtype, device) for tq in times[1:]]
+    batched = vals[0].ndim == 3
+    return torch.stack(vals, dim=1 if batched else 0).contiguous(), True, batched
+
+
+def finiteHorizonLqr(A, B, Q, R_inv, Qf, T, N=50, substeps=8):
+    """
+    Finite-horizon LQR gains in continuous time, by integrating the LQR HJB / Riccati differential equation backward from
+    `V(T) = Qf` (zopt/lqrUtils.py:39-98):  `-dV/dt = Q + V A + A'V - V B R^-1 B'V`,  `K(t) = R^-1(t) B(t)' V(t)`.
+
+    Arguments (as the reference; every matrix optionally with one leading batch axis)
+    ---------
+        A, B, Q, R_inv : callables of time `A(t)` ... returning (n,n), (n,m), (n,n), (m,m) matrices -- or constant matrices
+        Qf : terminal state cost (n,n)
+        T : time horizon;  N : number of output time points (`linspace(0, T, N)`, lqrUtils.py:87)
+        substeps : RK4 steps between two output points.  The reference integrates with jax's adaptive Dormand-Prince
+            (rtol = atol = 1.4e-8); a CUDA kernel cannot call back into Python, so the callables are SAMPLED on the host at
+            the fixed-step scheme's stage times (2 (N-1) substeps + 1 calls each) and the kernel integrates with RK4.
+
+    Returns
+    -------
+        K : callable `K(t)` -> (m,n) or (Bsz,m,n) gains, `V` linearly interpolated between the grid points and clipped
+            outside [0, T] exactly as the reference's `interpMapped` (np.interp) does; `K.V` (.., N, n, n), `K.t` (N,) are kept
+    """
+    N, substeps = int(N), int(substeps)
+    if N < 2 or substeps < 1:
+        raise ValueError("need N >= 2 and substeps >= 1")
+    T = float(T)
+    probe = [f(0.0) if callable(f) else f for f in (A, B, Q, R_inv)] + [Qf]
+    device = pick_device(*probe)
+    dtype = pick_dtype(*probe)
+    S = (N - 1) * substeps
+    times = T - np.arange(2 * S + 1) * (T / S / 2)  # sample j <-> time T - j h/2
+    ops = [_sample_coefficient(f, times, dtype, device) for f in (A, B, Q, R_inv)]
+    Qf = to_dev(Qf, dtype, device)
+    n, m = ops[1][0].shape[-2], ops[1][0].shape[-1]
+    for name, (t, _, _), blk in zip(("A", "B", "Q", "R_inv"), ops, ((n, n), (n, m), (n, n), (m, m))):
+        if tuple(t.shape[-2:]) != blk:
+            raise ValueError(f"{name}: expected {blk} matrices, got {tuple(t.shape)}")
+    if tuple(Qf.shape[-2:]) != (n, n) or Qf.ndim not in (2, 3):
+        raise ValueError(f"Qf: expected ({n},{n}), got {tuple(Qf.shape)}")
+    sizes = [t.shape[0] for t, _, b in ops if b] + ([Qf.shape[0]] if Qf.ndim == 3 else [])
+    Bsz = 1
+    for b in sizes:
+        if b != 1:
+            if Bsz not in (1, b):
+                raise ValueError(f"inconsistent batch sizes {Bsz} and {b}")
+            Bsz = b
+    any_b = len(sizes) > 0
+    views = [View(t, 2, ht, b) for t, ht, b in ops] + [View(Qf, 2, False, Qf.ndim == 3)]
+    V = torch.empty((Bsz, N, n, n), dtype=dtype, device=device)
+    check(lib.zb_lqr_care_rk4(dcode(dtype), device.index, stream_ptr(device), Bsz, N, substeps, n, m, T, *[v.ref() for v in views], ptr(V)))
+    tgrid = torch.linspace(0.0, T, N, dtype=dtype, device=device)
+    if not any_b:
+        V = V[0]
+
+    def K(t):
+        tq = min(max(float(t), 0.0), T)  # np.interp clips outside the grid
+        pos = tq / T * (N - 1)
+        i0 = min(int(np.floor(pos)), N - 2)
+        w = pos - i0
+        Vt = (1.0 - w) * V[..., i0, :, :] + w * V[..., i0 + 1, :, :]
+        Rt = to_dev(R_inv(t) if callable(R_inv) else R_inv, dtype, device)
+        Bt = to_dev(B(t) if callable(B) else B, dtype, device)
+        return Rt @ Bt.transpose(-1, -2) @ Vt
+
+    K.V, K.t = V, tgrid
+    return K
 
 
 def proportionalFeedbackController(x, x0, u0, K):
