@@ -127,36 +127,11 @@ def _sample_coefficient(f, times, dtype, device):
     return torch.stack(vals, dim=1 if batched else 0).contiguous(), True, batched
 
 
-def finiteHorizonLqr(A, B, Q, R_inv, Qf, T, N=50, substeps=8):
-    """
-    Finite-horizon LQR gains in continuous time, by integrating the LQR HJB / Riccati differential equation backward from
-    `V(T) = Qf` (zopt/lqrUtils.py:39-98):  `-dV/dt = Q + V A + A'V - V B R^-1 B'V`,  `K(t) = R^-1(t) B(t)' V(t)`.
-
-    Arguments (as the reference; every matrix optionally with one leading batch axis)
-    ---------
-        A, B, Q, R_inv : callables of time `A(t)` ... returning (n,n), (n,m), (n,n), (m,m) matrices -- or constant matrices
-        Qf : terminal state cost (n,n)
-        T : time horizon;  N : number of output time points (`linspace(0, T, N)`, lqrUtils.py:87)
-        substeps : RK4 steps between two output points.  The reference integrates with jax's adaptive Dormand-Prince
-            (rtol = atol = 1.4e-8); a CUDA kernel cannot call back into Python, so the callables are SAMPLED on the host at
-            the fixed-step scheme's stage times (2 (N-1) substeps + 1 calls each) and the kernel integrates with RK4.
-
-    Returns
-    -------
-        K : callable `K(t)` -> (m,n) or (Bsz,m,n) gains, `V` linearly interpolated between the grid points and clipped
-            outside [0, T] exactly as the reference's `interpMapped` (np.interp) does; `K.V` (.., N, n, n), `K.t` (N,) are kept
-    """
-    N, substeps = int(N), int(substeps)
-    if N < 2 or substeps < 1:
-        raise ValueError("need N >= 2 and substeps >= 1")
-    T = float(T)
-    probe = [f(0.0) if callable(f) else f for f in (A, B, Q, R_inv)] + [Qf]
-    device = pick_device(*probe)
-    dtype = pick_dtype(*probe)
+def _care_solve(A, B, Q, R_inv, Qf, T, N, substeps, dtype, device):
+    """one fixed-step integration: sample the coefficients at the RK4 stage times, launch zb_lqr_care_rk4"""
     S = (N - 1) * substeps
     times = T - np.arange(2 * S + 1) * (T / S / 2)  # sample j <-> time T - j h/2
     ops = [_sample_coefficient(f, times, dtype, device) for f in (A, B, Q, R_inv)]
-    Qf = to_dev(Qf, dtype, device)
     n, m = ops[1][0].shape[-2], ops[1][0].shape[-1]
     for name, (t, _, _), blk in zip(("A", "B", "Q", "R_inv"), ops, ((n, n), (n, m), (n, n), (m, m))):
         if tuple(t.shape[-2:]) != blk:
@@ -170,10 +145,55 @@ def finiteHorizonLqr(A, B, Q, R_inv, Qf, T, N=50, substeps=8):
             if Bsz not in (1, b):
                 raise ValueError(f"inconsistent batch sizes {Bsz} and {b}")
             Bsz = b
-    any_b = len(sizes) > 0
     views = [View(t, 2, ht, b) for t, ht, b in ops] + [View(Qf, 2, False, Qf.ndim == 3)]
     V = torch.empty((Bsz, N, n, n), dtype=dtype, device=device)
     check(lib.zb_lqr_care_rk4(dcode(dtype), device.index, stream_ptr(device), Bsz, N, substeps, n, m, T, *[v.ref() for v in views], ptr(V)))
+    return V, len(sizes) > 0
+
+
+def finiteHorizonLqr(A, B, Q, R_inv, Qf, T, N=50, substeps=None, rtol=1.4e-8):
+    """
+    Finite-horizon LQR gains in continuous time, by integrating the LQR HJB / Riccati differential equation backward from
+    `V(T) = Qf` (zopt/lqrUtils.py:39-98):  `-dV/dt = Q + V A + A'V - V B R^-1 B'V`,  `K(t) = R^-1(t) B(t)' V(t)`.
+
+    Arguments (as the reference; every matrix optionally with one leading batch axis)
+    ---------
+        A, B, Q, R_inv : callables of time `A(t)` ... returning (n,n), (n,m), (n,n), (m,m) matrices -- or constant matrices
+        Qf : terminal state cost (n,n)
+        T : time horizon;  N : number of output time points (`linspace(0, T, N)`, lqrUtils.py:87)
+        substeps, rtol : the reference integrates with jax's adaptive Dormand-Prince at rtol = atol = 1.4e-8.  A CUDA kernel
+            cannot call back into Python, so the callables are SAMPLED on the host at the stage times of a fixed-step RK4
+            scheme (`substeps` steps between two output points) and the kernel integrates the whole batch.  With
+            `substeps=None` (default) the step is halved until two successive solutions agree to `rtol` (Richardson estimate,
+            relative to max|V|, fp64; one pass at ~200 steps over the horizon in fp32): the same error control, applied
+            globally.  `K.substeps`, `K.err_estimate` report what was used.
+
+    Returns
+    -------
+        K : callable `K(t)` -> (m,n) or (Bsz,m,n) gains, `V` linearly interpolated between the grid points and clipped
+            outside [0, T] exactly as the reference's `interpMapped` (np.interp) does; `K.V` (.., N, n, n), `K.t` (N,) are kept
+    """
+    N = int(N)
+    if N < 2 or (substeps is not None and int(substeps) < 1):
+        raise ValueError("need N >= 2 and substeps >= 1")
+    T = float(T)
+    probe = [f(0.0) if callable(f) else f for f in (A, B, Q, R_inv)] + [Qf]
+    device = pick_device(*probe)
+    dtype = pick_dtype(*probe)
+    Qf = to_dev(Qf, dtype, device)
+    err = None
+    if substeps is not None:
+        sub = int(substeps)
+        V, any_b = _care_solve(A, B, Q, R_inv, Qf, T, N, sub, dtype, device)
+    else:
+        sub = max(4, -(-100 // (N - 1)))
+        V, any_b = _care_solve(A, B, Q, R_inv, Qf, T, N, sub, dtype, device)
+        while dtype == torch.float64 or err is None:
+            Vf, _ = _care_solve(A, B, Q, R_inv, Qf, T, N, 2 * sub, dtype, device)
+            err = float((Vf - V).abs().max() / Vf.abs().max()) / 15.0  # RK4: the finer solution carries 1/16 of the difference
+            V, sub = Vf, 2 * sub
+            if err <= rtol or sub * (N - 1) >= 1 << 16 or dtype != torch.float64:
+                break
     tgrid = torch.linspace(0.0, T, N, dtype=dtype, device=device)
     if not any_b:
         V = V[0]
@@ -188,7 +208,7 @@ def finiteHorizonLqr(A, B, Q, R_inv, Qf, T, N=50, substeps=8):
         Bt = to_dev(B(t) if callable(B) else B, dtype, device)
         return Rt @ Bt.transpose(-1, -2) @ Vt
 
-    K.V, K.t = V, tgrid
+    K.V, K.t, K.substeps, K.err_estimate = V, tgrid, sub, err
     return K
 
 
