@@ -137,3 +137,61 @@ def test_pytree_constructors_with_symbolic_model(name):
     assert _relerr(qd.f_ux, Hux) < 1e-12 or float(Hux.abs().max()) == 0.0
     ad = AffineDynamics.from_function(mdl, torch.as_tensor(xT[0], device="cuda"), torch.as_tensor(uT[0], device="cuda"))
     assert ad.f_x.shape == (n, n) and _relerr(ad.f_x, Jx[0]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["pendulum", "car"])
+def test_symbolic_cost_codegen_and_build(name):
+    """plugin.SymbolicCost: generated cost code compiled with the model into one plug-in (nvcc, no GPU needed); the cost parts
+    are callable on torch tensors like the reference's lambdas, and mismatched pairs are refused."""
+    from zopt_b200.models import symbolic_cost_of
+    from zopt_b200.plugin import SymbolicCost
+    mdl, bound, cost = plugin_models.build_with_cost(name)
+    assert bound is mdl.with_cost(cost) and os.path.exists(bound.so_path) and bound.so_path != mdl.so_path
+    for fn in ("user_cost", "user_cost_grad", "user_cost_hess", "user_tcost", "user_tcost_grad", "user_tcost_hess"):
+        assert f" {fn}(" in bound.source
+    assert "#define ZB_USER_COST 1" in bound.source and "ZB_USER_COST" not in mdl.source
+    x, u = torch.linspace(0.1, 0.4, mdl.n, dtype=torch.float64), torch.linspace(-0.3, 0.2, mdl.m, dtype=torch.float64)
+    c, cf = cost.running(x, u), cost.terminal(x)
+    assert c.shape == () and cf.shape == () and torch.isfinite(c) and torch.isfinite(cf)
+    g = torch.func.grad(cost.running, argnums=0)(x, u)
+    assert g.shape == (mdl.n,)
+    assert symbolic_cost_of(cost.running, cost.terminal) is cost
+    other = SymbolicCost(lambda x, u: x[0] ** 2 + u[0] ** 2, lambda x: x[0] ** 2, mdl.n, mdl.m)
+    with pytest.raises(TypeError):
+        symbolic_cost_of(cost.running, other.terminal)
+    with pytest.raises(ValueError):
+        mdl.with_cost(SymbolicCost(lambda x, u: x[0] ** 2, lambda x: x[0] ** 2, mdl.n + 1, mdl.m))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["pendulum", "car"])
+@pytest.mark.parametrize("second_order", [False, True])
+def test_solvers_with_symbolic_cost_vs_oracle(name, second_order):
+    """iLQR / DDP with a user-defined NON-quadratic cost (and model), fp64, against the oracle, which differentiates the cost's
+    own callables with torch autodiff the way the reference does with JAX (pytrees.py:99-115, 71-81) and eigen-clamps the
+    stacked cost Hessian at every time step (ilqrUtils.py:222-234): step-size sequence, then x, u, L, J."""
+    from oracle import ilqr as oilqr
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadraticCost, QuadraticTerminalCost
+    mdl, bound, cost = plugin_models.build_with_cost(name)
+    n, m, N, Bsz, iters = mdl.n, mdl.m, 20, 4, 3
+    rng = np.random.default_rng(19 + int(second_order))
+    x0 = rng.uniform(-1, 1, (Bsz, n))
+    uG = 0.1 * rng.normal(size=(N, m))
+    solver = ilqrUtils.differentialDynamicProgramming if second_order else ilqrUtils.iterativeLqr
+    traj, L, J, conv, log = solver(mdl, cost.running, cost.terminal, torch.as_tensor(x0, device="cuda"), uG, maxIter=iters, tol=-1.0,
+                                   return_log=True)
+    osolver = oilqr.differentialDynamicProgramming if second_order else oilqr.iterativeLqr
+    for b in range(Bsz):
+        olog = []
+        tr, Lr, Jr, _ = osolver(mdl, cost.running, cost.terminal, torch.as_tensor(x0[b]), torch.as_tensor(uG), maxIter=iters, tol=-1.0, log=olog)
+        assert [e["alpha_idx"] for e in olog[1:]] == log["alpha_idx"][b].tolist()
+        assert _relerr(log["J"][b], np.array([e["J"] for e in olog])) < 1e-10
+        assert _relerr(traj.xTraj[b], tr.xTraj) < 1e-9 and _relerr(traj.uTraj[b], tr.uTraj) < 1e-9
+        assert _relerr(L[b], Lr) < 1e-8 and abs(float(J[b]) - float(Jr)) < 1e-10 * abs(float(Jr))
+    # a symbolic cost needs a symbolic model (it is compiled together with it)
+    from zopt_b200.models import QuadcopterEuler
+    with pytest.raises(TypeError):
+        solver(QuadcopterEuler(0.1), cost.running, cost.terminal, np.zeros(12), np.zeros((N, 4)))
+    with pytest.raises(TypeError):
+        solver(mdl, cost.running, QuadraticTerminalCost(np.eye(n)), x0[0], uG)

@@ -90,6 +90,9 @@ template <typename T>
 __global__ void __launch_bounds__(GEN_THREADS) k_solve_prep(long long Bsz, int n, int m, Cost C, double eps, void* Czz, void* Vfxx) {
     long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (b >= Bsz) return;
+#ifdef ZB_USER_COST
+    return;  // a user-defined cost is expanded and conditioned per step inside the backward pass
+#endif
     const int p = n + m;
     T S[ZB_PD_MAX * ZB_PD_MAX], W[ZB_PD_MAX * ZB_PD_MAX];
     const T* Q = C.Q.at<T>(b);
@@ -130,11 +133,20 @@ __global__ void __launch_bounds__(GEN_THREADS) k_solve_init(RollP P, const void*
         for (int i = 0; i < m; ++i) u[i] = ug[(long long)k * m + i];
         for (int i = 0; i < n; ++i) xT[(long long)k * n + i] = x[i];
         for (int i = 0; i < m; ++i) uT[(long long)k * m + i] = u[i];
+#ifdef ZB_USER_COST
+        Jc += user_cost<T>(x, u);
+#else
         Jc += quad_form<T>(Q, x, n) + quad_form<T>(R, u, m);
+#endif
         model_step<T>(P.M, b, x, u, x);
     }
     for (int i = 0; i < n; ++i) xT[(long long)N * n + i] = x[i];
+#ifdef ZB_USER_COST
+    Jc += user_tcost<T>(x);
+    (void)Q; (void)R;
+#else
     Jc += quad_form<T>(P.C.Qf.at<T>(b), x, n);
+#endif
     reinterpret_cast<T*>(J)[b] = Jc;
     converged[b] = 0;
     iters[b] = 0;

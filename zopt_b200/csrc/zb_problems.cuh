@@ -271,12 +271,20 @@ ZB_HD T rollout_core(const RollP& P, long long b, T alpha, bool write) {
             for (int i = 0; i < n; ++i) xT[(long long)k * n + i] = x[i];
             for (int i = 0; i < m; ++i) uT[(long long)k * m + i] = u[i];
         }
+#ifdef ZB_USER_COST  // plug-in with a user-defined (symbolic) cost: pytrees.py:40-55 with the generated c(x,u), cf(x)
+        if (P.has_cost) J += user_cost<T>(x, u);
+#else
         if (P.has_cost) J += quad_form<T>(Q, x, n) + quad_form<T>(R, u, m);
+#endif
         model_step<T>(P.M, b, x, u, x);
     }
     if (write)
         for (int i = 0; i < n; ++i) xT[(long long)N * n + i] = x[i];
+#ifdef ZB_USER_COST
+    if (P.has_cost) J += user_tcost<T>(x);
+#else
     if (P.has_cost) J += quad_form<T>(P.C.Qf.at<T>(b), x, n);
+#endif
     return J;
 }
 
@@ -477,13 +485,26 @@ ZB_HD void solve_backward_problem(const SolveBackP& P, long long b) {
     T v, v_x[NX], v_xx[NX * NX], l[NU], L[NU * NX];
     T fx[NX * NX], fu[NX * NU], c_x[NX], c_u[NU], c_xx[NX * NX], c_ux[NU * NX], c_uu[NU * NU];
     T vf_xx[NX * NX], vf_ux[NU * NX], vf_uu[NU * NU];
+#ifndef ZB_USER_COST
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) c_xx[i * n + j] = Czz[i * p + j];
     for (int i = 0; i < m; ++i) {
         for (int j = 0; j < n; ++j) c_ux[i * n + j] = Czz[(n + i) * p + j];
         for (int j = 0; j < m; ++j) c_uu[i * m + j] = Czz[(n + i) * p + n + j];
     }
+#endif
     const T* xN = xT + (long long)N * n;
+#ifdef ZB_USER_COST
+    // user-defined terminal cost: value, gradient and eigen-clamped Hessian at x_N (pytrees.py:71-81, ilqrUtils.py:254-257)
+    {
+        T Wc[ZB_PD_MAX * ZB_PD_MAX];
+        v = user_tcost<T>(xN);
+        user_tcost_grad<T>(xN, v_x);
+        user_tcost_hess<T>(xN, v_xx);
+        pd_clamp<T>(v_xx, Wc, n, T(P.eps));
+    }
+    (void)Qf; (void)Q; (void)R; (void)Czz;
+#else
     v = quad_form<T>(Qf, xN, n);
     for (int i = 0; i < n; ++i) {
         T s = T(0);
@@ -492,12 +513,31 @@ ZB_HD void solve_backward_problem(const SolveBackP& P, long long b) {
     }
     const T* Vf = reinterpret_cast<const T*>(P.Vfxx) + b * (long long)n * n;
     for (int i = 0; i < n * n; ++i) v_xx[i] = Vf[i];
+#endif
     T* lo = reinterpret_cast<T*>(P.l) + b * (long long)N * m;
     T* Lo = reinterpret_cast<T*>(P.L) + b * (long long)N * m * n;
     for (int k = N - 1; k >= 0; --k) {
         const T* x = xT + (long long)k * n;
         const T* u = uT + (long long)k * m;
         model_lin<T>(P.M, b, x, u, fx, fu);
+#ifdef ZB_USER_COST
+        // user-defined running cost: Taylor data at (x_k, u_k) (pytrees.py:99-115) and the per-step eigen-clamp of the stacked
+        // Hessian [[c_xx, c_ux'], [c_ux, c_uu]] (conditionQuadraticCost, ilqrUtils.py:222-234) -- not hoistable for a general cost
+        T c;
+        {
+            T Zc[ZB_PD_MAX * ZB_PD_MAX], Wc[ZB_PD_MAX * ZB_PD_MAX];
+            c = user_cost<T>(x, u);
+            user_cost_grad<T>(x, u, c_x, c_u);
+            user_cost_hess<T>(x, u, Zc);
+            pd_clamp<T>(Zc, Wc, p, T(P.eps));
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) c_xx[i * n + j] = Zc[i * p + j];
+            for (int i = 0; i < m; ++i) {
+                for (int j = 0; j < n; ++j) c_ux[i * n + j] = Zc[(n + i) * p + j];
+                for (int j = 0; j < m; ++j) c_uu[i * m + j] = Zc[(n + i) * p + n + j];
+            }
+        }
+#else
         for (int i = 0; i < n; ++i) {
             T s = T(0);
             for (int j = 0; j < n; ++j) s += (Q[i * n + j] + Q[j * n + i]) * x[j];
@@ -509,6 +549,7 @@ ZB_HD void solve_backward_problem(const SolveBackP& P, long long b) {
             c_u[i] = s;
         }
         T c = quad_form<T>(Q, x, n) + quad_form<T>(R, u, m);
+#endif
         if (P.second_order) {
             // conditionQuadraticDynamics (ilqrUtils.py:237-251); f_ux = f_uu = 0 for both registered models, and for
             // the quadcopter v_x.f_xx only touches states 0..8, so the (n+m)x(n+m) block is blockdiag(H9, 0): its

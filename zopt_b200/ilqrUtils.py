@@ -17,7 +17,8 @@ import torch
 
 from . import _lib
 from ._lib import View, ZbArr, check, dcode, lib, null_arr, pick_device, pick_dtype, ptr, stream_ptr, to_dev
-from .models import cost_batch, cost_spec, reconcile_batch, require_cost, require_model
+from .models import (QuadraticCost, QuadraticTerminalCost, cost_batch, cost_spec, reconcile_batch, require_cost, require_model,
+                     symbolic_cost_of)
 from .pytrees import (AffineDynamics, AffinePolicy, CostFunction, QuadraticCostFunction, QuadraticDynamics,
                       QuadraticValueFunction, Trajectory)
 
@@ -224,8 +225,22 @@ def conditionValueFunction(Vf):
 _GENERIC_FORWARD = False
 
 
+def _bind_symbolic_cost(model, runningCost, terminalCost):
+    """costs given symbolically (plugin.SymbolicCost): compile them together with the symbolic model into one plug-in and hand
+    the kernels placeholder quadratic weights (never read: the plug-in evaluates the generated cost code)"""
+    sc = symbolic_cost_of(runningCost, terminalCost)
+    if sc is None:
+        return model, runningCost, terminalCost
+    if not getattr(model, "is_plugin", False):
+        raise TypeError("symbolic costs are compiled together with a symbolic model: define the dynamics with "
+                        "zopt_b200.plugin.SymbolicDynamics(f, n, m) as well")
+    import numpy as np
+    return model.with_cost(sc), QuadraticCost(np.eye(model.n), np.eye(model.m)), QuadraticTerminalCost(np.eye(model.n))
+
+
 def _solve(dynamics, runningCost, terminalCost, x0, uGuess, maxIter, tol, second_order, return_log):
     model = require_model(dynamics)
+    model, runningCost, terminalCost = _bind_symbolic_cost(model, runningCost, terminalCost)
     rc, tc = require_cost(runningCost, terminalCost)
     device = pick_device(x0, uGuess)
     dtype = pick_dtype(x0, uGuess)

@@ -133,10 +133,21 @@ def require_model(dynFun):
         "define the dynamics symbolically: zopt_b200.plugin.SymbolicDynamics(f, n, m). There is no CPU fallback.")
 
 
+def symbolic_cost_of(runningCost, terminalCost):
+    """the SymbolicCost both callables belong to (plugin.SymbolicCost(...).running / .terminal), else None"""
+    if getattr(runningCost, "is_symbolic_cost", False) or getattr(terminalCost, "is_symbolic_cost", False):
+        ro, to = getattr(runningCost, "owner", None), getattr(terminalCost, "owner", None)
+        if ro is None or ro is not to:
+            raise TypeError("a symbolic running cost goes with the terminal cost of the SAME plugin.SymbolicCost (cost.running, cost.terminal)")
+        return ro
+    return None
+
+
 def require_cost(runningCost, terminalCost):
     if not isinstance(runningCost, QuadraticCost) or not isinstance(terminalCost, QuadraticTerminalCost):
         raise TypeError(
-            "zopt_b200 needs registered costs: zopt_b200.models.QuadraticCost(Q, R) and QuadraticTerminalCost(Qf) "
+            "zopt_b200 needs registered costs: zopt_b200.models.QuadraticCost(Q, R) and QuadraticTerminalCost(Qf), or costs "
+            "defined symbolically together with a symbolic model: plugin.SymbolicCost(c, cf, n, m).running / .terminal "
             "(the reference autodiffs arbitrary callables with JAX; there is no CPU fallback).")
     return runningCost, terminalCost
 

@@ -83,6 +83,96 @@ def _emit(name, args, outputs, sizes):
     return "\n".join(lines)
 
 
+def _emit_scalar(name, args, expr):
+    """templated ZB_HD function returning one scalar expression"""
+    import sympy as sp
+    pr = _cuda_printer()
+    repl, red = sp.cse([expr], symbols=sp.numbered_symbols("t_"), optimizations="basic")
+    lines = ["template <typename T>", "ZB_HD T %s(%s) {" % (name, args)]
+    for sym, e in repl:
+        lines.append("    const T %s = %s;" % (sym, pr.doprint(e)))
+    lines.append("    return %s;" % pr.doprint(red[0]))
+    lines.append("}")
+    return "\n".join(lines)
+
+
+def _torch_modules():
+    tm = {k: getattr(torch, k) for k in ("sin", "cos", "tan", "exp", "log", "sqrt", "tanh", "sinh", "cosh", "atan", "asin", "acos")}
+    tm["Abs"] = torch.abs
+    return tm
+
+
+class SymbolicCost:
+    """
+    User-defined running and terminal costs `c(x, u)`, `cf(x)` given as sympy expressions -- the counterpart, for costs, of
+    SymbolicDynamics: the reference takes arbitrary callables `runningCost(x, u)`, `terminalCost(x)` and differentiates
+    them with JAX (zopt/ilqrUtils.py:260-268, pytrees.py:71-81, 99-115).  `SymbolicCost(c, cf, n, m)` calls `c` and `cf`
+    once with sympy symbols, derives gradient and Hessian, and generates CUDA for `c`, `(c_x, c_u)`, the stacked Hessian
+    `[[c_xx, c_ux'], [c_ux, c_uu]]`, `cf`, `cf_x`, `cf_xx`.  Pass `cost.running` and `cost.terminal` where the reference
+    takes the two callables; both stay callable on torch tensors (that is how the test oracle differentiates them).
+    Used together with a SymbolicDynamics model: the pair is compiled into one solver plug-in; the eigen-clamp of the cost
+    Hessian (ilqrUtils.py:222-234) then runs per time step inside the backward pass, as in the reference.
+    """
+
+    def __init__(self, c, cf, n, m):
+        import sympy as sp
+        n, m = int(n), int(m)
+        self.n, self.m = n, m
+        xs, us = list(sp.symbols(f"x0:{n}", real=True)), list(sp.symbols(f"u0:{m}", real=True))
+        ce, cfe = sp.sympify(c(xs, us)), sp.sympify(cf(xs))
+        for e, allowed, what in ((ce, set(xs) | set(us), "c(x, u)"), (cfe, set(xs), "cf(x)")):
+            free = e.free_symbols - allowed
+            if free:
+                raise ValueError(f"{what} may only depend on its arguments; free symbols: {sorted(map(str, free))}")
+        self._xs, self._us, self._c, self._cf = xs, us, ce, cfe
+        z = xs + us
+        sub = {xs[i]: sp.Symbol(f"x[{i}]") for i in range(n)}
+        sub.update({us[i]: sp.Symbol(f"u[{i}]") for i in range(m)})
+        S = lambda e: sp.sympify(e).xreplace(sub)
+        p = n + m
+        Hc, Hf = sp.hessian(ce, z), sp.hessian(cfe, xs)
+        XU = "const T* __restrict__ x, const T* __restrict__ u"
+        self.source = "\n\n".join([
+            "// user-defined cost (zopt_b200/plugin.py::SymbolicCost)", "#define ZB_USER_COST 1",
+            _emit_scalar("user_cost", XU, S(ce)),
+            _emit("user_cost_grad", XU + ", T* __restrict__ cx, T* __restrict__ cu",
+                  {"cx": [S(sp.diff(ce, v)) for v in xs], "cu": [S(sp.diff(ce, v)) for v in us]}, None),
+            _emit("user_cost_hess", XU + ", T* __restrict__ Z", {"Z": [S(Hc[i, j]) for i in range(p) for j in range(p)]}, None),
+            _emit_scalar("user_tcost", "const T* __restrict__ x", S(cfe)),
+            _emit("user_tcost_grad", "const T* __restrict__ x, T* __restrict__ vx", {"vx": [S(sp.diff(cfe, v)) for v in xs]}, None),
+            _emit("user_tcost_hess", "const T* __restrict__ x, T* __restrict__ Vxx", {"Vxx": [S(Hf[i, j]) for i in range(n) for j in range(n)]}, None),
+        ]) + "\n"
+        self.running, self.terminal = _SymbolicRunningCost(self), _SymbolicTerminalCost(self)
+
+
+class _SymbolicRunningCost:
+    is_symbolic_cost = True
+
+    def __init__(self, owner):
+        self.owner, self._fn = owner, None
+
+    def __call__(self, x, u):
+        import sympy as sp
+        if self._fn is None:
+            self._fn = sp.lambdify(self.owner._xs + self.owner._us, self.owner._c, modules=[_torch_modules()])
+        x, u = torch.as_tensor(x), torch.as_tensor(u)
+        return x[..., 0] * 0 + self._fn(*x.unbind(-1), *u.unbind(-1))
+
+
+class _SymbolicTerminalCost:
+    is_symbolic_cost = True
+
+    def __init__(self, owner):
+        self.owner, self._fn = owner, None
+
+    def __call__(self, x):
+        import sympy as sp
+        if self._fn is None:
+            self._fn = sp.lambdify(self.owner._xs, self.owner._cf, modules=[_torch_modules()])
+        x = torch.as_tensor(x)
+        return x[..., 0] * 0 + self._fn(*x.unbind(-1))
+
+
 class SymbolicDynamics:
     """x+ = f(x, u) given as sympy expressions; compiled into a solver plug-in (see the module docstring)."""
     is_plugin = True
@@ -141,6 +231,21 @@ class SymbolicDynamics:
 
     def batch(self):
         return 1
+
+    def with_cost(self, cost):
+        """The same model compiled together with a SymbolicCost into one solver plug-in (cached on the model)."""
+        if (cost.n, cost.m) != (self.n, self.m):
+            raise ValueError(f"cost dimensions ({cost.n},{cost.m}) do not match the model ({self.n},{self.m})")
+        cache = self.__dict__.setdefault("_with_cost", {})
+        if id(cost) not in cache:
+            import copy
+            bound = copy.copy(self)
+            bound.__dict__.pop("_with_cost", None)
+            bound.source = self.source + "\n" + cost.source
+            bound._lib, bound.cost = None, cost
+            bound.build()
+            cache[id(cost)] = bound
+        return cache[id(cost)]
 
     # ------------------------------------------------------------------------------------------ build / load
     _NVCC_FLAGS = ["-cudart", "static", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
