@@ -22,7 +22,8 @@ int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream)
 #define ZB_EXIT_CHECK 4  // zb_ilqr_solve: iterations between two "is anything still iterating" reads
 #endif
 #ifndef ZB_W9_MAX_PER_SM
-#define ZB_W9_MAX_PER_SM 28  // problems per SM up to which the nine-lanes-per-problem closed-loop kernel is selected
+#define ZB_W9_MAX_PER_SM 68  // problems per SM up to which the nine-lanes-per-problem closed-loop kernel is selected (measured crossover with
+                            // the thread-per-problem kernel on B200: ~10 K problems; it is ahead of the 4-thread kernel at every size)
 #endif
 
 // =================================================================================================
@@ -910,7 +911,7 @@ int32_t zb_mpc_closed_loop_quad(int32_t dtype, int32_t device, void* stream, int
     const bool forced = (flags & (ZB_VARIANT_THREAD | ZB_VARIANT_QUAD | ZB_VARIANT_WARP)) != 0;
     const bool want_warp = (flags & ZB_VARIANT_WARP) || (!forced && Bsz <= (int64_t)sm_count * ZB_W9_MAX_PER_SM);
     if (want_warp) return mpc_closed_loop_w9_launch(P, (cudaStream_t)stream);
-    const bool want_quad = (flags & ZB_VARIANT_QUAD) || (!forced && Bsz <= (int64_t)sm_count * 56);  // measured crossover on B200: ~8-10 K problems
+    const bool want_quad = (flags & ZB_VARIANT_QUAD) != 0;  // kept selectable; no longer picked automatically
     if (dense_ok && want_quad) return mpc_closed_loop_coop_launch(P, (cudaStream_t)stream);
     return mpc_closed_loop_launch(P, (cudaStream_t)stream, (flags & ZB_COST_DIAGONAL) != 0);
 }
