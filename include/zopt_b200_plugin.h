@@ -9,6 +9,11 @@
  * zb_ilqr_rollout / zb_ilqr_solve of zopt_b200.h minus the `zb_model` argument: same pointers, sizes, strides, stream,
  * error convention (0 OK, < 0 argument error, > 0 CUDA error; message through zb_user_last_error), caller-owned buffers,
  * no synchronisation.  Limits: n <= ZB_MAX_N, m <= ZB_MAX_M.
+ *
+ * User-defined COSTS (plugin.SymbolicCost: `runningCost(x, u)`, `terminalCost(x)` of zopt/ilqrUtils.py:260-268, differentiated by
+ * JAX in the reference, pytrees.py:71-81, 99-115): when the generated header also defines ZB_USER_COST (c, (c_x, c_u), the
+ * stacked Hessian, cf, cf_x, cf_xx), the same entry points evaluate THAT cost -- in the rollouts, and expanded and eigen-clamped
+ * per time step in the backward pass (ilqrUtils.py:222-234) -- and the `zb_cost` argument is a placeholder (non-NULL, never read).
  */
 #ifndef ZOPT_B200_PLUGIN_H
 #define ZOPT_B200_PLUGIN_H
