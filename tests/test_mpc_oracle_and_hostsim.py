@@ -77,6 +77,46 @@ def test_oracle_constrained_two_methods():
     assert ompc.solve_qp(A, B, Q, R, N, xlb, xub, ulb, uub, x0b)[3] == "infeasible"
 
 
+def test_oracle_qp_against_scipy_solvers():
+    """The QP of zopt/mpcUtils.py:47-59 with ACTIVE bounds solved by two independent third-party optimisers (SciPy SLSQP and
+    trust-constr on the un-condensed problem: states and controls as variables, dynamics as equality constraints, the box as
+    bounds -- the formulation cvxpy hands to OSQP) against the oracle's condensed interior-point method.  The QP is strictly
+    convex, so every correct solver reaches the same optimum; the reference's own solver (OSQP at eps 1e-2) cannot run here."""
+    import scipy.optimize as so
+    rng = np.random.default_rng(4)
+    n, m, N = 3, 2, 6
+    A = np.eye(n) + 0.2 * rng.normal(size=(n, n))
+    B = rng.normal(size=(n, m))
+    Q, R = np.diag(rng.uniform(0.5, 2, n)), np.diag(rng.uniform(0.5, 2, m))
+    x0 = np.array([0.9, -0.8, 0.7])
+    xlb, xub, ulb, uub = -np.ones(n), np.ones(n), -0.25 * np.ones(m), 0.25 * np.ones(m)
+    u0, x, u, status, info = ompc.solve_qp(A, B, Q, R, N, xlb, xub, ulb, uub, x0)
+    assert status == "optimal" and np.max(np.abs(u)) > 0.2499  # the control bound binds
+    nx, nu = (N + 1) * n, N * m
+
+    def unpack(z):
+        return z[:nx].reshape(N + 1, n), z[nx:].reshape(N, m)
+
+    def cost(z):
+        X, U = unpack(z)
+        return sum(X[k] @ Q @ X[k] + U[k] @ R @ U[k] for k in range(N)) + X[N] @ Q @ X[N]
+
+    def dyn(z):
+        X, U = unpack(z)
+        return np.concatenate([X[0] - x0] + [X[k + 1] - A @ X[k] - B @ U[k] for k in range(N)])
+
+    bounds = [(l, h) for _ in range(N + 1) for l, h in zip(xlb, xub)] + [(l, h) for _ in range(N) for l, h in zip(ulb, uub)]
+    z0 = np.concatenate([x.reshape(-1) * 0, u.reshape(-1) * 0])
+    r1 = so.minimize(cost, z0, method="SLSQP", bounds=bounds, constraints=[{"type": "eq", "fun": dyn}], options={"ftol": 1e-14, "maxiter": 500})
+    assert r1.success
+    X1, U1 = unpack(r1.x)
+    assert np.max(np.abs(U1 - u)) < 1e-6 and np.max(np.abs(X1 - x)) < 1e-6 and abs(r1.fun - info["J"]) < 1e-9 * info["J"]
+    r2 = so.minimize(cost, z0, method="trust-constr", bounds=so.Bounds([b[0] for b in bounds], [b[1] for b in bounds]),
+                     constraints=[so.NonlinearConstraint(dyn, 0, 0)], options={"gtol": 1e-10, "xtol": 1e-12, "maxiter": 2000})
+    X2, U2 = unpack(r2.x)
+    assert np.max(np.abs(U2 - u)) < 1e-4 and abs(r2.fun - info["J"]) < 1e-6 * info["J"]
+
+
 def test_admm_body_reference_test_problem():
     I = np.eye(2)
     one = np.ones(2)
