@@ -89,9 +89,9 @@ def test_oracle_qp_against_scipy_solvers():
     B = rng.normal(size=(n, m))
     Q, R = np.diag(rng.uniform(0.5, 2, n)), np.diag(rng.uniform(0.5, 2, m))
     x0 = np.array([0.9, -0.8, 0.7])
-    xlb, xub, ulb, uub = -np.ones(n), np.ones(n), -0.25 * np.ones(m), 0.25 * np.ones(m)
+    xlb, xub, ulb, uub = -np.ones(n), np.ones(n), -0.2 * np.ones(m), 0.2 * np.ones(m)
     u0, x, u, status, info = ompc.solve_qp(A, B, Q, R, N, xlb, xub, ulb, uub, x0)
-    assert status == "optimal" and np.max(np.abs(u)) > 0.2499  # the control bound binds
+    assert status == "optimal" and np.max(np.abs(u)) > 0.19999 and np.max(np.abs(x)) > 0.99999  # a control bound and a state bound bind
     nx, nu = (N + 1) * n, N * m
 
     def unpack(z):
