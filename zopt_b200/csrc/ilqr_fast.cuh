@@ -115,7 +115,7 @@ __device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, do
     const double sc = __hiloint2double(0x7fe00000 - ex, 0);  // 2^(1023 - exponent(mx)): the larger operand lands in [1, 2)
     const float df = (float)(d * sc), af = (float)(a2 * sc);
     float tf = af * approx_rcp(fabsf(df) + approx_sqrt(fmaf(df, df, af * af)));  // = sgn(tau) / (|tau| + sqrt(1 + tau^2)), tau = d / a2
-    if (d < 0.0) tf = -tf;
+    tf = __int_as_float(__float_as_int(tf) ^ (__double2hiint(d) & 0x80000000));  // * sgn(d), branch-free
     const double t = (apq != 0.0) ? (double)tf : 0.0;
     c = rsqrt(fma(t, t, 1.0));
     s = t * c;
@@ -127,107 +127,195 @@ __device__ __forceinline__ void jacobi_cs(float app, float aqq, float apq, float
     const float sc = __int_as_float(0x7e800000 - ex);  // 2^(126 - exponent(mx))
     const float df = d * sc, af = a2 * sc;
     float tf = af * approx_rcp(fabsf(df) + approx_sqrt(fmaf(df, df, af * af)));
-    if (d < 0.0f) tf = -tf;
+    tf = __int_as_float(__float_as_int(tf) ^ (__float_as_int(d) & 0x80000000));  // * sgn(d), branch-free
     const float t = (apq != 0.0f) ? tf : 0.0f;
     c = 1.0f / sqrtf(fmaf(t, t, 1.0f));
     s = t * c;
 }
 
-// apply the (PP,QQ) rotation [[c, s], [-s, c]] (columns p' = c p - s q, q' = s p + c q) to the replicated packed matrix and
-// to this thread's eigenvector rows.  The 2x2 block uses the general formulas: a_pq does not vanish exactly because tan
-// was approximate -- it shrinks by ~1e-7 per visit, and quadratically once small, like the exact rotation.
+// four-way select by the thread's index in the quad, as two levels of SEL on 32-bit words (the nested ?: on doubles was
+// compiled to divergent branches: 6 % of the stall samples "branch resolving")
+__device__ __forceinline__ float sel4(int t, float a, float b, float c, float d) {
+    const float x = (t & 1) ? b : a, y = (t & 1) ? d : c;
+    return (t & 2) ? y : x;
+}
+__device__ __forceinline__ double sel4(int t, double a, double b, double c, double d) {
+    const int xl = (t & 1) ? __double2loint(b) : __double2loint(a), xh = (t & 1) ? __double2hiint(b) : __double2hiint(a);
+    const int yl = (t & 1) ? __double2loint(d) : __double2loint(c), yh = (t & 1) ? __double2hiint(d) : __double2hiint(c);
+    return __hiloint2double((t & 2) ? yh : xh, (t & 2) ? yl : xl);
+}
+
+// One rotation's share of the exchange buffer: (c, s) and the rotated 2x2 block, six words (the last one pads to 16 bytes).
+template <typename T>
+struct Rot {
+    T c, s, npp, nqq, npq;
+};
+__device__ __forceinline__ void st_rot(double* p, const Rot<double>& r) {
+    *reinterpret_cast<double2*>(p) = make_double2(r.c, r.s);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(r.npp, r.nqq);
+    p[4] = r.npq;
+}
+__device__ __forceinline__ void st_rot(float* p, const Rot<float>& r) {  // 24-byte stride: 8-byte accesses
+    *reinterpret_cast<float2*>(p) = make_float2(r.c, r.s);
+    *reinterpret_cast<float2*>(p + 2) = make_float2(r.npp, r.nqq);
+    p[4] = r.npq;
+}
+__device__ __forceinline__ Rot<double> ld_rot(const double* p) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    return Rot<double>{a.x, a.y, b.x, b.y, p[4]};
+}
+__device__ __forceinline__ Rot<float> ld_rot(const float* p) {
+    const float2 a = *reinterpret_cast<const float2*>(p), b = *reinterpret_cast<const float2*>(p + 2);
+    return Rot<float>{a.x, a.y, b.x, b.y, p[4]};
+}
+
+// The off-diagonal part of rotation (PP,QQ) on the replicated matrix and on this thread's eigenvector rows, FOLLOWED BY THE
+// SWAP of p and q (odd-even ordering, see jacobi_round): column P receives s p + c q, column Q receives c p - s q.  The 2x2
+// block itself arrives ready-made (and already swapped) from the thread that computed the rotation.
 template <typename T, int PP, int QQ>
-__device__ __forceinline__ void jacobi_apply(T (&A)[45], T (&Wr)[3][9], T c, T s) {
-    const T app = A[tri9(PP, PP)], aqq = A[tri9(QQ, QQ)], apq = A[tri9(QQ, PP)];
+__device__ __forceinline__ void jacobi_apply_off(T (&A)[45], T (&Wr)[3][9], const Rot<T>& r) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         if (k != PP && k != QQ) {
             const T akp = A[tri9(k, PP)], akq = A[tri9(k, QQ)];
-            A[tri9(k, PP)] = c * akp - s * akq;
-            A[tri9(k, QQ)] = s * akp + c * akq;
+            A[tri9(k, PP)] = r.s * akp + r.c * akq;
+            A[tri9(k, QQ)] = r.c * akp - r.s * akq;
         }
     }
-    const T cc = c * c, ss = s * s, cs = c * s;
-    const T x2 = (cs + cs) * apq;
-    const T npp = fma(cc, app, fma(ss, aqq, -x2)), nqq = fma(ss, app, fma(cc, aqq, x2));
-    const T npq = fma(cs, app - aqq, (cc - ss) * apq);
-    A[tri9(PP, PP)] = npp;
-    A[tri9(QQ, QQ)] = nqq;
-    // rounding noise of the annihilated entry is dropped (a perturbation below one ulp of the diagonal), so a converged
-    // matrix has exact zeros and the sweep loop terminates on its off-diagonal test
-    const T tiny = (sizeof(T) == 8 ? T(8.9e-16) : T(4.8e-7)) * (fabs(npp) + fabs(nqq));
-    A[tri9(QQ, PP)] = fabs(npq) <= tiny ? T(0) : npq;
+    A[tri9(PP, PP)] = r.npp;
+    A[tri9(QQ, QQ)] = r.nqq;
+    A[tri9(QQ, PP)] = r.npq;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const T wp = Wr[r][PP], wq = Wr[r][QQ];
-        Wr[r][PP] = c * wp - s * wq;
-        Wr[r][QQ] = s * wp + c * wq;
+    for (int w = 0; w < 3; ++w) {
+        const T wp = Wr[w][PP], wq = Wr[w][QQ];
+        Wr[w][PP] = r.s * wp + r.c * wq;
+        Wr[w][QQ] = r.c * wp - r.s * wq;
     }
 }
 
-// Round-robin (tournament) ordering of the 36 pairs of a 9x9 sweep: 9 rounds of 4 DISJOINT pairs.  Disjoint rotations
-// commute in their (c, s): each of the quad's four threads computes ONE of them from the replicated matrix, the four
-// (c, s) go through shared memory, then every thread applies all four.
-// Brent-Luk form: the rotated pairs always sit at POSITIONS (0,1), (2,3), (4,5), (6,7) (position 8 idles) and the indices
-// move one step around the ring 0>2>4>6>8>7>5>3>1>0 after every round, so ONE block of code serves all rounds.  Three
-// rounds are unrolled (the two intermediate moves are compile-time renamings), then the registers are permuted once:
-// the loop body is ~1,100 instructions (fits the 32 KB instruction cache) instead of ~2,900 for a fully unrolled sweep,
-// which spent 42 % of its stall samples waiting for instruction fetch.  V max(L,eps) V' does not depend on the order of
-// the eigenpairs, so the accumulated permutation never has to be undone.
-__host__ __device__ constexpr int rr_src(int p) {  // content of position p after a move = content of position rr_src(p) before
-    constexpr int src[9] = {1, 3, 0, 5, 2, 7, 4, 8, 6};
-    return src[p];
-}
-__host__ __device__ constexpr int rr_slot(int j, int p) {  // register slot that holds logical position p after j moves
-    for (int i = 0; i < j; ++i) p = rr_src(p);
-    return p;
-}
-__device__ __forceinline__ void st_cs(double* p, double c, double s) { *reinterpret_cast<double2*>(p) = make_double2(c, s); }
-__device__ __forceinline__ void st_cs(float* p, float c, float s) { *reinterpret_cast<float2*>(p) = make_float2(c, s); }
-__device__ __forceinline__ void ld_cs(const double* p, double& c, double& s) { const double2 v = *reinterpret_cast<const double2*>(p); c = v.x; s = v.y; }
-__device__ __forceinline__ void ld_cs(const float* p, float& c, float& s) { const float2 v = *reinterpret_cast<const float2*>(p); c = v.x; s = v.y; }
-
-template <typename T, int J>
-__device__ __forceinline__ void jacobi_round(T (&A)[45], T (&Wr)[3][9], T* buf /* 8 words, this quad, this round parity */, int t, unsigned qmask) {
-    constexpr int p1 = rr_slot(J, 0), q1 = rr_slot(J, 1), p2 = rr_slot(J, 2), q2 = rr_slot(J, 3);
-    constexpr int p3 = rr_slot(J, 4), q3 = rr_slot(J, 5), p4 = rr_slot(J, 6), q4 = rr_slot(J, 7);
-    const T app = t == 0 ? A[tri9(p1, p1)] : t == 1 ? A[tri9(p2, p2)] : t == 2 ? A[tri9(p3, p3)] : A[tri9(p4, p4)];
-    const T aqq = t == 0 ? A[tri9(q1, q1)] : t == 1 ? A[tri9(q2, q2)] : t == 2 ? A[tri9(q3, q3)] : A[tri9(q4, q4)];
-    const T apq = t == 0 ? A[tri9(q1, p1)] : t == 1 ? A[tri9(q2, p2)] : t == 2 ? A[tri9(q3, p3)] : A[tri9(q4, p4)];
-    T c, s;
-    jacobi_cs(app, aqq, apq, c, s);
-    st_cs(buf + 2 * t, c, s);
+// One round of four disjoint rotations.  ODD-EVEN ORDERING (Brent-Luk's transposition scheme): even rounds pair the
+// neighbours (0,1)(2,3)(4,5)(6,7), odd rounds (1,2)(3,4)(5,6)(7,8), and every rotation also SWAPS its two indices -- the swap is
+// a relabelling of the outputs, so it costs nothing.  Nine such rounds are an odd-even transposition sort that reverses
+// the order of the nine indices, so every pair meets exactly once: a cyclic sweep with only TWO code blocks and no data
+// movement.  (Round 1 of this kernel used the tournament ring: three unrolled rounds + a 72-register permutation per loop
+// trip, 48 moves per round.  Measured on cfg 5 trajectories both orderings need the same number of rounds: 25.2 vs 25.1.)
+// V max(L, eps) V' does not depend on the order of the eigenpairs, so the accumulated permutation is never undone.
+// Thread t of the quad computes rotation t of the round AND its rotated 2x2 block (general formulas: a_pq does not vanish
+// exactly because tan was approximate -- it shrinks by ~1e-7 per visit, and quadratically once small, like the exact
+// rotation; rounding noise of the annihilated entry is dropped once it is below one ulp of the diagonal, so a converged
+// matrix has exact zeros and the loop terminates on its off-diagonal test).  The four (c, s, block) go through shared
+// memory; every thread then applies the four rotations to the rest of its replica (round 1 computed the four 2x2 blocks in
+// every thread: 68 of ~260 instructions per round, now 17).
+template <typename T, int ODD>
+__device__ __forceinline__ void jacobi_round(T (&A)[45], T (&Wr)[3][9], T* buf /* 24 words, this quad, this round parity */, int t, unsigned qmask) {
+    constexpr int p1 = ODD, q1 = ODD + 1, p2 = ODD + 2, q2 = ODD + 3, p3 = ODD + 4, q3 = ODD + 5, p4 = ODD + 6, q4 = ODD + 7;
+    const T app = sel4(t, A[tri9(p1, p1)], A[tri9(p2, p2)], A[tri9(p3, p3)], A[tri9(p4, p4)]);
+    const T aqq = sel4(t, A[tri9(q1, q1)], A[tri9(q2, q2)], A[tri9(q3, q3)], A[tri9(q4, q4)]);
+    const T apq = sel4(t, A[tri9(q1, p1)], A[tri9(q2, p2)], A[tri9(q3, p3)], A[tri9(q4, p4)]);
+    Rot<T> r;
+    jacobi_cs(app, aqq, apq, r.c, r.s);
+    {
+        const T cc = r.c * r.c, ss = r.s * r.s, cs = r.c * r.s;
+        const T x2 = (cs + cs) * apq;
+        r.nqq = fma(cc, app, fma(ss, aqq, -x2));  // the rotated a_pp lands in slot q (swap) ...
+        r.npp = fma(ss, app, fma(cc, aqq, x2));   // ... and the rotated a_qq in slot p
+        const T npq = fma(cs, app - aqq, (cc - ss) * apq);
+        const T tiny = (sizeof(T) == 8 ? T(8.9e-16) : T(4.8e-7)) * (fabs(r.npp) + fabs(r.nqq));
+        r.npq = fabs(npq) <= tiny ? T(0) : npq;
+    }
+    st_rot(buf + 6 * t, r);
     __syncwarp(qmask);
-    T c1, s1, c2, s2, c3, s3, c4, s4;
-    ld_cs(buf, c1, s1); ld_cs(buf + 2, c2, s2); ld_cs(buf + 4, c3, s3); ld_cs(buf + 6, c4, s4);
-    jacobi_apply<T, p1, q1>(A, Wr, c1, s1);
-    jacobi_apply<T, p2, q2>(A, Wr, c2, s2);
-    jacobi_apply<T, p3, q3>(A, Wr, c3, s3);
-    jacobi_apply<T, p4, q4>(A, Wr, c4, s4);
+    const Rot<T> r1 = ld_rot(buf), r2 = ld_rot(buf + 6), r3 = ld_rot(buf + 12), r4 = ld_rot(buf + 18);
+    jacobi_apply_off<T, p1, q1>(A, Wr, r1);
+    jacobi_apply_off<T, p2, q2>(A, Wr, r2);
+    jacobi_apply_off<T, p3, q3>(A, Wr, r3);
+    jacobi_apply_off<T, p4, q4>(A, Wr, r4);
 }
 
-// three rounds + the register permutation that brings the positions back to slots 0..8
+// Warm start of the eigen-solve (round 2).  Along a trajectory H_k changes little from one step to the next, so the
+// eigenvectors V of step k+1 nearly diagonalise H_k: the sweep starts from A' = V' H V (off-diagonal norm ~1e-3 of the
+// diagonal instead of ~1) and the rotations are accumulated onto V, which halves the number of rounds (measured on cfg 5
+// trajectories: 48 -> 25 per step).  V is exactly orthogonal in working precision (a product of rotations), so A' is
+// similar to H to rounding.  The product is DISTRIBUTED over the quad and exchanged through shared memory:
+//   pass 1  Z = H V      thread t forms rows t, t+4 (t = 0: also row 8) of Z            3 x 81 FMA
+//   pass 2  A' = V' Z    thread t forms rows t, t+4 (and 8) of A'                       3 x 81 FMA
+// then the lower triangle of A' is gathered back into every thread's replica, and the thread's rows of V seed the
+// eigenvector accumulator.  EV: V (9x9, row-major); Z0 (45 words) | Z1 (36 words): rows 0-4 | 5-8 of Z; Ag: 45 words.
 template <typename T>
-__device__ __forceinline__ void jacobi_group(T (&A)[45], T (&Wr)[3][9], T* csbuf, int& par, int t, unsigned qmask) {
-    jacobi_round<T, 0>(A, Wr, csbuf + par * 8, t, qmask);
-    jacobi_round<T, 1>(A, Wr, csbuf + (par ^ 1) * 8, t, qmask);  // alternate buffers: a round's stores never race the previous round's loads
-    jacobi_round<T, 2>(A, Wr, csbuf + par * 8, t, qmask);
-    par ^= 1;
-    T B[45], Wn[3][9];
+__device__ __forceinline__ void jacobi_warm_start(T (&A)[45], T (&Wr)[3][9], const T* EV, T* Z0, T* Z1, T* Ag, int t, unsigned qmask) {
+    const int r0 = t, r1 = t + 4;
+    T acc[3][9];
+    {
+        T h[3][9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) {
+            h[0][j] = sel4(t, A[tri9(0, j)], A[tri9(1, j)], A[tri9(2, j)], A[tri9(3, j)]);
+            h[1][j] = sel4(t, A[tri9(4, j)], A[tri9(5, j)], A[tri9(6, j)], A[tri9(7, j)]);
+            h[2][j] = A[tri9(8, j)];
+        }
 #pragma unroll
-        for (int j = 0; j <= i; ++j) B[tri9(i, j)] = A[tri9(rr_slot(3, i), rr_slot(3, j))];
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int b = 0; b < 9; ++b) acc[r][b] = T(0);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            T v[9];
+#pragma unroll
+            for (int b = 0; b < 9; ++b) v[b] = EV[j * 9 + b];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int b = 0; b < 9; ++b) acc[r][b] = fma(h[r][j], v[b], acc[r][b]);
+        }
+    }
+    {
+        T* z0 = Z0 + 9 * r0;                              // rows 0..3
+        T* z1 = (t == 0) ? Z0 + 36 : Z1 + 9 * (t - 1);    // rows 4..7
+#pragma unroll
+        for (int b = 0; b < 9; ++b) { z0[b] = acc[0][b]; z1[b] = acc[1][b]; }
+        if (t == 0) {
+#pragma unroll
+            for (int b = 0; b < 9; ++b) Z1[27 + b] = acc[2][b];  // row 8
+        }
+    }
+    __syncwarp(qmask);
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int j = 0; j < 9; ++j) Wn[r][j] = Wr[r][rr_slot(3, j)];
+        for (int b = 0; b < 9; ++b) acc[r][b] = T(0);
 #pragma unroll
-    for (int e = 0; e < 45; ++e) A[e] = B[e];
+    for (int i = 0; i < 9; ++i) {
+        const T* zr = (i < 5) ? Z0 + 9 * i : Z1 + 9 * (i - 5);
+        T z[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+        for (int b = 0; b < 9; ++b) z[b] = zr[b];
+        const T v0 = EV[i * 9 + r0], v1 = EV[i * 9 + r1], v2 = EV[i * 9 + 8];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) Wr[r][j] = Wn[r][j];
+        for (int b = 0; b < 9; ++b) {
+            acc[0][b] = fma(v0, z[b], acc[0][b]);
+            acc[1][b] = fma(v1, z[b], acc[1][b]);
+            acc[2][b] = fma(v2, z[b], acc[2][b]);
+        }
+    }
+    {
+        const int o0 = r0 * (r0 + 1) / 2, o1 = r1 * (r1 + 1) / 2;
+#pragma unroll
+        for (int b = 0; b < 9; ++b) {
+            if (b <= r0) Ag[o0 + b] = acc[0][b];
+            if (b <= r1) Ag[o1 + b] = acc[1][b];
+            if (t == 0) Ag[36 + b] = acc[2][b];
+        }
+    }
+    __syncwarp(qmask);
+#pragma unroll
+    for (int e = 0; e < 45; ++e) A[e] = Ag[e];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        Wr[0][c] = EV[r0 * 9 + c];
+        Wr[1][c] = EV[r1 * 9 + c];
+        Wr[2][c] = EV[72 + c];  // row 8 (kept by thread 0 only)
+    }
+    __syncwarp(qmask);  // Ag / EV may be overwritten from here on (rotation exchange, eigenvector exchange)
 }
 
 // f_x = I + dt dF/dx into the slab: row i is written by thread i / 3 of the quad (divergent on purpose: each entry of dF/dx is
@@ -265,7 +353,7 @@ __device__ __forceinline__ void stage_xu(T* dst16, const T* xT, const T* uT, int
 }
 
 template <typename T, bool CDIAG, bool DDP>
-__global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
+__global__ void __launch_bounds__(DDP ? 256 : 128) k_ilqr_backward_quad(IlqrFastP P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     static_assert(!DDP || CDIAG, "the DDP fast path exists for diagonal costs only");
     constexpr int PS = DDP ? (sizeof(T) == 4 ? IDD_PS_F32 : IDD_PS_F64)
@@ -278,7 +366,11 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
     const long long b = P.act.perm ? (in_range ? (long long)P.act.perm[slot] : 0) : (in_range ? slot : P.Bsz - 1);
     const bool active = in_range && !(P.done && P.done[b]);
     // a warp whose 8 problems are all frozen / out of range has nothing to do
-    if (__ballot_sync(0xffffffffu, active) == 0u) return;
+    if (__ballot_sync(0xffffffffu, active) == 0u) {
+        if (DDP && blockDim.x > 32)  // the DDP CTA meets at a barrier every step (see the loop): idle warps keep the count right
+            for (int k = P.N - 1; k >= 0; --k) __syncthreads();
+        return;
+    }
     T* S = smem + (warp * 8 + quad) * PS;
     T *Vs = S + (CDIAG ? ID_V : IQ_V), *As = S + (CDIAG ? ID_A : IQ_A), *Bs = S + IQ_B, *Cxx = S + (CDIAG ? ID_CXX : IQ_CXX);
     T *Qs = S + (CDIAG ? ID_QS : IQ_QS), *Ms = S + (CDIAG ? ID_M : IQ_M), *Cux = S + IQ_CUX, *Gs = S + (CDIAG ? ID_G : IQ_G);
@@ -359,8 +451,24 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
         pu0 = ldv4(uT + (long long)(N - 1) * 4);
     }
     const int qbase = lane & 28;
+    // DDP warm start: fp32 keeps the eigenvectors of the previous step in its slab; the packed fp64 slab sends them through
+    // a per-problem global scratch (648 bytes, L2-resident) and copies them back into the dead f_x region at the top of a step
+    T* evg = (DDP && P.ev) ? reinterpret_cast<T*>(P.ev) + b * 84 : nullptr;
+    const bool warm_ok = DDP && (!PACK || P.ev != nullptr);
     for (int k = N - 1; k >= 0; --k) {
         T* xk = STAGE ? xk0 + (k & 1) * XK2 : xk0;
+        // The DDP step is ~8,000 instructions (128 KB) of mostly straight-line code, far beyond the instruction cache: warps that
+        // drift apart each stream it from L2 on their own (ncu: 50 % of the stall samples "no instruction").  Meeting once per
+        // step keeps the warps of a CTA within one step of each other, so that they share the fetched lines.
+        if (DDP && blockDim.x > 32) __syncthreads();
+        if (PACK && warm_ok && k < N - 1) {  // 81 words = 41 16-byte chunks (the scratch row is 84 words), 10-11 per thread
+#pragma unroll
+            for (int c = 0; c < 11; ++c) {
+                const int ch = t + 4 * c;
+                if (ch < 41) bw_cp16(As + 2 * ch, evg + 2 * ch);
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
         // ---- 0. linearise at (x_k, u_k) ----
         {
             T x[12], u[4], J[144];
@@ -417,25 +525,37 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
 #pragma unroll
                         for (int j = 0; j <= i; ++j) A9[tri9(i, j)] = dt * h9[i * 9 + j];
                 }
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) Wr[r][c] = (c == t + 4 * r) ? T(1) : T(0);  // rows t, t+4, t+8 of I
-                T* csbuf = Pc;  // 16 words of the (not yet rewritten) clamped-block region carry the rotations of a round
                 const unsigned qmask = 0xFu << (lane & 28);
-                int par = 0;
-                for (int sweep = 0; sweep < 30; ++sweep) {
-                    T off = T(0), dg = T(0);
+                // scratch of the eigen-solve, all of it dead at this point of the step: the rotation exchange (48 words) and the
+                // gathered A' share one region; Z = H V lives where Q_ux and the clamped block will be written later
+                T* csbuf = PACK ? As + 84 : Ms;
+                if (k < N - 1 && warm_ok) {  // eigenvectors of step k+1 are in Wsm (PACK: just copied back from global)
+                    if (PACK) {
+                        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+                        __syncwarp(qmask);
+                    }
+                    jacobi_warm_start<T>(A9, Wr, Wsm, PACK ? Ms : Pc, PACK ? Pc : Pc + 45, csbuf, t, qmask);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) Wr[r][c] = (c == t + 4 * r) ? T(1) : T(0);  // rows t, t+4, t+8 of I
+                }
+                // convergence is tested before every pair of rounds (an even and an odd one; a sweep is nine rounds)
+#pragma unroll 1
+                for (int g = 0; g < 135; ++g) {
+                    T o4[4] = {T(0), T(0), T(0), T(0)}, d2[2] = {T(0), T(0)};  // partial sums: the 36-term chain was 70 % "wait"
 #pragma unroll
                     for (int i = 0; i < 9; ++i) {
-                        dg = fma(A9[tri9(i, i)], A9[tri9(i, i)], dg);
+                        d2[i & 1] = fma(A9[tri9(i, i)], A9[tri9(i, i)], d2[i & 1]);
 #pragma unroll
-                        for (int j = 0; j < i; ++j) off = fma(A9[tri9(i, j)], A9[tri9(i, j)], off);
+                        for (int j = 0; j < i; ++j) o4[tri9(i, j) & 3] = fma(A9[tri9(i, j)], A9[tri9(i, j)], o4[tri9(i, j) & 3]);
                     }
+                    const T off = (o4[0] + o4[1]) + (o4[2] + o4[3]), dg = d2[0] + d2[1];
                     const T thr = (sizeof(T) == 8) ? T(1e-32) : T(1e-15), tiny = (sizeof(T) == 8) ? T(1e-300) : T(1e-37);
                     if (off <= thr * dg || off < tiny) break;
-#pragma unroll 1
-                    for (int g = 0; g < 3; ++g) jacobi_group<T>(A9, Wr, csbuf, par, t, qmask);
+                    jacobi_round<T, 0>(A9, Wr, csbuf, t, qmask);
+                    jacobi_round<T, 1>(A9, Wr, csbuf + 24, t, qmask);  // alternate buffers: a round's stores never race the previous round's loads
                 }
                 // exchange eigenvector rows, then P9 = W max(Lambda, eps) W^T, rows t, t+4, t+8 per thread
                 const T eps = T(P.eps);
@@ -445,6 +565,10 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                     if (row < 9) {
 #pragma unroll
                         for (int c = 0; c < 9; ++c) Wsm[row * 9 + c] = Wr[r][c];
+                        if (PACK && warm_ok && active && k > 0) {  // the packed slab has no room to keep them: via global (L2) to step k-1
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) evg[row * 9 + c] = Wr[r][c];
+                        }
                     }
                 }
                 __syncwarp();
@@ -458,11 +582,12 @@ __global__ void __launch_bounds__(128) k_ilqr_backward_quad(IlqrFastP P) {
                         T wl[9];
 #pragma unroll
                         for (int k2 = 0; k2 < 9; ++k2) wl[k2] = Wr[r][k2] * lamc[k2];
-                        for (int j = 0; j <= row; ++j) {  // lower triangle only (the block is symmetric)
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) {  // lower triangle only (the block is symmetric); fixed trip count: nine independent chains
                             T acc9 = T(0);
 #pragma unroll
                             for (int k2 = 0; k2 < 9; ++k2) acc9 = fma(wl[k2], Wsm[j * 9 + k2], acc9);
-                            Pc[PACK ? row * (row + 1) / 2 + j : row * 9 + j] = acc9;
+                            if (j <= row) Pc[PACK ? row * (row + 1) / 2 + j : row * 9 + j] = acc9;
                         }
                     }
                 }
@@ -697,7 +822,8 @@ inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
     constexpr int PS = DDP ? (sizeof(T) == 4 ? IDD_PS_F32 : IDD_PS_F64)
                            : CDIAG ? (sizeof(T) == 4 ? ID_PS_F32 : ID_PS_F64) : (sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64);
     // problems per CTA: fp32 32 (4 warps); fp64 16 (2 warps) so several CTAs share an SM's shared memory
-    const int warps = (sizeof(T) == 4) ? 4 : 2;
+    int warps = (sizeof(T) == 4) ? 4 : 2;
+    if (DDP) { const char* e = getenv("ZB_DDP_WARPS"); warps = e ? atoi(e) : (sizeof(T) == 4 ? 4 : 8); }
     size_t smem = (size_t)warps * 8 * PS * sizeof(T);
     // fp32 DDP: two 4-warp CTAs per SM run faster than three (measured 65 vs 79 ms on cfg 5: the ~1,100-instruction Jacobi loop
     // of three CTAs in different phases thrashes the instruction cache), so the request is padded past a third of the SM

@@ -534,7 +534,8 @@ size_t zb_ilqr_workspace_bytes(int32_t dtype, int64_t Bsz, int32_t N, int32_t n,
     size_t p = (size_t)(n + m);
     const size_t per = (size_t)(N + 1) * n + (size_t)N * m;  // one trajectory
     return align256(e * Bsz * N * m) + align256(e * Bsz * 16) + align256(e * Bsz * p * p) + align256(e * Bsz * n * n) +
-           align256(e * SPEC_N * Bsz * per) + 2 * align256(sizeof(int32_t) * (size_t)Bsz) + 512;  // + two active lists, two counters
+           align256(e * SPEC_N * Bsz * per) + 2 * align256(sizeof(int32_t) * (size_t)Bsz) + 512 +  // + two active lists, two counters
+           align256(e * Bsz * 84);                                                                // + DDP eigenvector carry
 }
 
 int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t flags,
@@ -565,7 +566,8 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     int32_t* perm2[2];
     perm2[0] = reinterpret_cast<int32_t*>(w);  w += align256(sizeof(int32_t) * (size_t)Bsz);
     perm2[1] = reinterpret_cast<int32_t*>(w);  w += align256(sizeof(int32_t) * (size_t)Bsz);
-    int32_t* count2 = reinterpret_cast<int32_t*>(w);  // two counters, 128 bytes apart
+    int32_t* count2 = reinterpret_cast<int32_t*>(w);  w += 512;  // two counters, 128 bytes apart
+    void* ev_ws = w;  // DDP: eigenvectors of the clamped block, carried from step to step (ilqr_fast.cuh)
     cudaStream_t s = (cudaStream_t)stream;
     // With a real tolerance problems freeze at different iterations (ilqrUtils.py:301-303,318): the still-iterating ones are
     // re-listed after every forward pass so that frozen problems occupy no lane, and the host stops enqueuing once the list is
@@ -588,7 +590,7 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     }
     SolveBackP Bk{Bsz, N, second_order, P.M, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
     const bool fast_bwd = N >= 1 && ilqr_fast_eligible(P.M, second_order, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out);
-    IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3, ActiveP{nullptr, nullptr}};
+    IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3, ActiveP{nullptr, nullptr}, ev_ws};
     if (track) {
         rc = compact_active_launch(Bsz, converged_out, perm2[0], count2, s);
         if (rc) return rc;
