@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(DDP ? 256 : 128) k_ilqr_backward_quad(IlqrFast
                         for (int j = 0; j < i; ++j) o4[tri9(i, j) & 3] = fma(A9[tri9(i, j)], A9[tri9(i, j)], o4[tri9(i, j) & 3]);
                     }
                     const T off = (o4[0] + o4[1]) + (o4[2] + o4[3]), dg = d2[0] + d2[1];
-                    const T thr = (sizeof(T) == 8) ? T(1e-32) : T(1e-15), tiny = (sizeof(T) == 8) ? T(1e-300) : T(1e-37);
+                    const T thr = (sizeof(T) == 8) ? T(1e-30) : T(1e-15), tiny = (sizeof(T) == 8) ? T(1e-300) : T(1e-37);
                     if (off <= thr * dg || off < tiny) break;
                     jacobi_round<T, 0>(A9, Wr, csbuf, t, qmask);
                     jacobi_round<T, 1>(A9, Wr, csbuf + 24, t, qmask);  // alternate buffers: a round's stores never race the previous round's loads
@@ -823,7 +823,18 @@ inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
                            : CDIAG ? (sizeof(T) == 4 ? ID_PS_F32 : ID_PS_F64) : (sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64);
     // problems per CTA: fp32 32 (4 warps); fp64 16 (2 warps) so several CTAs share an SM's shared memory
     int warps = (sizeof(T) == 4) ? 4 : 2;
-    if (DDP) { const char* e = getenv("ZB_DDP_WARPS"); warps = e ? atoi(e) : (sizeof(T) == 4 ? 4 : 8); }
+    if (DDP) {
+        // ONE CTA per SM whose warps meet at a barrier every step (see the kernel).  Eight warps fill the SM (registers in fp64,
+        // the 80 KB floor below in fp32); fewer warps per CTA are chosen when that fills the last wave better at the same number of
+        // waves (16,384 problems: 293 CTAs of 7 warps = 1.98 waves instead of 256 CTAs of 8 = 1.73 -> 2).
+        const char* e = getenv("ZB_DDP_WARPS");
+        const long long nsm = 148;
+        auto waves = [&](int w) { const long long ctas = (P.Bsz + 8 * w - 1) / (8 * w); return (ctas + nsm - 1) / nsm; };
+        warps = 8;
+        const int min_w = waves(8) == 1 ? 1 : 4;  // a batch that does not fill the SMs once is spread over as many SMs as possible
+        while (warps > min_w && waves(warps - 1) == waves(8)) --warps;
+        if (e && atoi(e) >= 1 && atoi(e) <= 8) warps = atoi(e);
+    }
     size_t smem = (size_t)warps * 8 * PS * sizeof(T);
     // fp32 DDP: two 4-warp CTAs per SM run faster than three (measured 65 vs 79 ms on cfg 5: the ~1,100-instruction Jacobi loop
     // of three CTAs in different phases thrashes the instruction cache), so the request is padded past a third of the SM
