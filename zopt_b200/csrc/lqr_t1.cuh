@@ -47,8 +47,16 @@ __device__ __forceinline__ void load_sym_lower(const float* g, float* v) {
 template <bool SPLIT>
 __device__ __forceinline__ int xs(int k, int c) { return SPLIT ? (c < 3 ? k * 3 + c : 36 + k) : X4 + k * 4 + c; }
 
-template <bool QDIAG, int RS = 32, bool RFULL = false, bool SPLIT = false>
-__device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&L)[4][12]) {
+// Hook: called when operand slots fall free inside the step, so that a streaming caller can refill them with the NEXT step's
+// operands while this step still computes (k_riccati_t1_tv): cost_free() once Q and R have been read (before pass 3a),
+// row_free(kk) once row kk of [A | B] has been consumed by pass 3a.
+struct NoHook {
+    __device__ __forceinline__ void cost_free() const {}
+    __device__ __forceinline__ void row_free(int) const {}
+};
+
+template <bool QDIAG, int RS = 32, bool RFULL = false, bool SPLIT = false, typename Hook = NoHook>
+__device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&L)[4][12], const Hook hook = Hook()) {
     // ---- 1. [W | VB] = V [A | B] in four 12x4 panels.  ROLLED loop: one ~600-instruction body re-used four
     //         times keeps the step's code inside the instruction cache (the fully unrolled first version
     //         stalled 0.8 cycle/instruction on instruction fetch with one warp per scheduler).
@@ -135,6 +143,7 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
                     if (4 * c + e <= i) v[tri(i, 4 * c + e)] = ZB_F4(q, e);
             }
     }
+    hook.cost_free();
     float M[4][12];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -154,6 +163,7 @@ __device__ __forceinline__ void riccati_step(float4* S, float (&v)[78], float (&
 #pragma unroll
             for (int c = 0; c < 3; ++c) { ra[c] = S[xs<SPLIT>(kn, c) * RS]; rw[c] = S[(W4 + kn * 3 + c) * RS]; }
             rb = S[xs<SPLIT>(kn, 3) * RS];
+            hook.row_free(kk);  // row kk sits in registers (a, b4); row kn has been read just above
 #pragma unroll
             for (int i = 0; i < 12; ++i)
 #pragma unroll
@@ -396,6 +406,9 @@ __global__ void __launch_bounds__(32, QDIAG ? 5 : 4) k_riccati_t1(FastP P) {
 #ifndef ZB_TV_L2_PREFETCH
 #define ZB_TV_L2_PREFETCH 0  // prefetch.global.L2 of the next step's blocks measured 1.87 ms against 1.74 ms without: the kernel is LSU-bound
 #endif
+#ifndef ZB_TV_EARLY_ISSUE
+#define ZB_TV_EARLY_ISSUE 1  // operand copies of step k-1 issued from inside step k as the slots fall free (TvHook)
+#endif
 constexpr int RS_TV = 32;
 constexpr int NF4_TV = 112;  // X 48 + W 36 + Q 24 + R 4 (full rows)
 
@@ -428,6 +441,32 @@ __device__ __forceinline__ void tv_load_step(float4* S, const FastP& P, long lon
     for (int j = 0; j < 4; ++j) cp_async16(&S[(R4 + j) * RS_TV], gR + j);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
+// The same copies issued from INSIDE the step (round 2): the cost blocks as soon as the step has read Q and R, row kk of
+// [A | B] as soon as pass 3a has consumed it -- the transfers of step k-1 then overlap the second half of step k (with one warp
+// per scheduler nothing else can cover them), and the 76 copies no longer reach the load/store unit as one burst.
+// Measured 1.735 -> 1.45 ms per 65,536 x 50 (ncu: lg_throttle 21 % -> 4 % of the stall samples).  Waiting for rows 8..11 only
+// where the first panel of the next step reaches them (two commit groups) changed nothing (1.47 ms) and is not kept.
+struct TvHook {
+    float4* S;
+    const float4 *gA, *gB, *gQ, *gR;
+    bool on;
+    __device__ __forceinline__ void cost_free() const {
+        if (!on) return;
+#pragma unroll
+        for (int r = 0; r < 12; ++r)
+#pragma unroll
+            for (int c = 0; c <= r / 4; ++c) cp_async16(&S[(Q4 + qoff(r) + c) * RS_TV], gQ + r * 3 + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cp_async16(&S[(R4 + j) * RS_TV], gR + j);
+    }
+    __device__ __forceinline__ void row_free(int kk) const {
+        if (!on) return;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cp_async16(&S[(X4 + kk * 4 + c) * RS_TV], gA + kk * 3 + c);
+        cp_async16(&S[(X4 + kk * 4 + 3) * RS_TV], gB + kk);
+    }
+};
+
 // pull the blocks of step k into L2: one request per 128-byte line a 16-byte-aligned block can touch
 __device__ __forceinline__ void tv_prefetch_step(const FastP& P, long long b, int k) {
     const char* gA = reinterpret_cast<const char*>(P.A.at<float>(b, k));
@@ -459,10 +498,20 @@ __global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P) {
         __syncwarp();  // everybody is done with the staging area (the W region) of the previous step
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");  // each lane reads only what it copied itself
         float L[4][12];
+#if ZB_TV_EARLY_ISSUE
+        {
+            const int kn = k > 0 ? k - 1 : 0;
+            const TvHook hook{S, reinterpret_cast<const float4*>(P.A.at<float>(b, kn)), reinterpret_cast<const float4*>(P.B.at<float>(b, kn)),
+                              reinterpret_cast<const float4*>(P.Q.at<float>(b, kn)), reinterpret_cast<const float4*>(P.R.at<float>(b, kn)), k > 0};
+            riccati_step<false, RS_TV, true, false, TvHook>(S, v, L, hook);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+#else
         riccati_step<false, RS_TV, true>(S, v, L);
         // the operand slots are private to the lane and free from here on: the copies of step k-1 (L2 hits) overlap the
         // gain transposition and stores below
         if (k > 0) tv_load_step(S, P, b, k - 1);
+#endif
         float4* stg = sm + W4 * RS_TV;  // W region is free now: transpose the gains for coalesced stores
         __syncwarp();
 #pragma unroll
