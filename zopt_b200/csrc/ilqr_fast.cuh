@@ -16,6 +16,7 @@
 //       written back "lower triangle wins" so v_xx stays exactly symmetric.
 // The algebra equals the reference's as-written expressions; parity with the oracle is gated at 1e-10 (fp64).
 #pragma once
+#include <algorithm>
 #include "ilqr_params.cuh"
 
 namespace zb {
@@ -353,7 +354,7 @@ __device__ __forceinline__ void stage_xu(T* dst16, const T* xT, const T* uT, int
 }
 
 template <typename T, bool CDIAG, bool DDP>
-__global__ void __launch_bounds__(DDP ? 256 : 128) k_ilqr_backward_quad(IlqrFastP P) {
+__global__ void __launch_bounds__(256) k_ilqr_backward_quad(IlqrFastP P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     static_assert(!DDP || CDIAG, "the DDP fast path exists for diagonal costs only");
     constexpr int PS = DDP ? (sizeof(T) == 4 ? IDD_PS_F32 : IDD_PS_F64)
@@ -460,6 +461,8 @@ __global__ void __launch_bounds__(DDP ? 256 : 128) k_ilqr_backward_quad(IlqrFast
         // The DDP step is ~8,000 instructions (128 KB) of mostly straight-line code, far beyond the instruction cache: warps that
         // drift apart each stream it from L2 on their own (ncu: 50 % of the stall samples "no instruction").  Meeting once per
         // step keeps the warps of a CTA within one step of each other, so that they share the fetched lines.
+        // (The iLQR instantiations are a third of the size and run 10-20 % SLOWER with the barrier: lockstep warps contend for the
+        // same pipe at the same time.)
         if (DDP && blockDim.x > 32) __syncthreads();
         if (PACK && warm_ok && k < N - 1) {  // 81 words = 41 16-byte chunks (the scratch row is 84 words), 10-11 per thread
 #pragma unroll
@@ -823,17 +826,23 @@ inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
                            : CDIAG ? (sizeof(T) == 4 ? ID_PS_F32 : ID_PS_F64) : (sizeof(T) == 4 ? IQ_PS_F32 : IQ_PS_F64);
     // problems per CTA: fp32 32 (4 warps); fp64 16 (2 warps) so several CTAs share an SM's shared memory
     int warps = (sizeof(T) == 4) ? 4 : 2;
+    // Wave balance.  A full SM holds maxw warps of this kernel (shared memory; 8 by registers).  When the batch needs more than
+    // one wave of the machine, ONE CTA per SM is launched with the smallest warp count that keeps the number of waves, so that the
+    // last wave is as full as the first (16,384 problems in fp64: 293 CTAs of 7 warps = 1.98 waves instead of 1.73 -> 2; cfg 4
+    // 35.5 -> 33.1 ms, cfg 5 71.8 -> 70.4 ms).  A batch below one wave keeps small CTAs (fp32: 4 warps, fp64: 2) spread over the SMs.
+    const long long nsm = 148;
+    const int maxw = (int)std::min<size_t>(8, (size_t)232448 / ((size_t)8 * PS * sizeof(T)));
+    auto waves = [&](int w) { const long long ctas = (P.Bsz + 8 * w - 1) / (8 * w); return (ctas + nsm - 1) / nsm; };
     if (DDP) {
-        // ONE CTA per SM whose warps meet at a barrier every step (see the kernel).  Eight warps fill the SM (registers in fp64,
-        // the 80 KB floor below in fp32); fewer warps per CTA are chosen when that fills the last wave better at the same number of
-        // waves (16,384 problems: 293 CTAs of 7 warps = 1.98 waves instead of 256 CTAs of 8 = 1.73 -> 2).
+        // DDP: ONE CTA per SM whose warps meet at a barrier every step (see the kernel), also below one wave
+        const int min_w = waves(maxw) == 1 ? 1 : (maxw + 1) / 2;
+        warps = maxw;
+        while (warps > min_w && waves(warps - 1) == waves(maxw)) --warps;
         const char* e = getenv("ZB_DDP_WARPS");
-        const long long nsm = 148;
-        auto waves = [&](int w) { const long long ctas = (P.Bsz + 8 * w - 1) / (8 * w); return (ctas + nsm - 1) / nsm; };
-        warps = 8;
-        const int min_w = waves(8) == 1 ? 1 : 4;  // a batch that does not fill the SMs once is spread over as many SMs as possible
-        while (warps > min_w && waves(warps - 1) == waves(8)) --warps;
-        if (e && atoi(e) >= 1 && atoi(e) <= 8) warps = atoi(e);
+        if (e && atoi(e) >= 1 && atoi(e) <= maxw) warps = atoi(e);
+    } else if (sizeof(T) == 8 && maxw >= 2 && waves(maxw) > 1) {
+        warps = maxw;
+        while (warps > (maxw + 1) / 2 && waves(warps - 1) == waves(maxw)) --warps;
     }
     size_t smem = (size_t)warps * 8 * PS * sizeof(T);
     // fp32 DDP: two 4-warp CTAs per SM run faster than three (measured 65 vs 79 ms on cfg 5: the ~1,100-instruction Jacobi loop
