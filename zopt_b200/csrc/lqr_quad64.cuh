@@ -162,7 +162,7 @@ __device__ __forceinline__ void riccati_quad_step(T* Vs, const T* As, const T* B
 }
 
 template <typename T, bool QDIAG>
-__global__ void __launch_bounds__(128) k_riccati_quad(LqrQuadP P) {
+__global__ void __launch_bounds__(256) k_riccati_quad(LqrQuadP P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PS = sizeof(T) == 4 ? LQ_PS_F32 : LQ_PS_F64;
     T* smem = reinterpret_cast<T*>(smem_raw);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(128) k_riccati_quad(LqrQuadP P) {
 // trajectory goes to HBM.  The state is replicated in the four threads of the quad (every thread steps the plant with the
 // same inputs, hence the same bits).
 template <typename T, bool QDIAG>
-__global__ void __launch_bounds__(128) k_mpc_closed_loop_quad64(ClosedLoopQuadP P) {
+__global__ void __launch_bounds__(256) k_mpc_closed_loop_quad64(ClosedLoopQuadP P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PS = sizeof(T) == 4 ? LQ_PS_F32 : LQ_PS_F64;
     T* smem = reinterpret_cast<T*>(smem_raw);
@@ -397,9 +397,22 @@ __global__ void __launch_bounds__(128) k_plan_rollout_quad(LqrQuadP P) {
     }
 }
 
+// Warps per CTA.  An SM holds eight warps (64 problems) of these kernels.  A batch of more than one wave of the machine is
+// launched as ONE CTA per SM with the smallest warp count that keeps the number of waves, so that the last wave is as full as
+// the first (16,384 problems: 293 CTAs of 7 warps = 1.98 waves instead of 1.73 -> 2); smaller batches keep two-warp CTAs
+// spread over the SMs (four per SM).
+inline int quad64_warps(long long Bsz) {
+    const long long nsm = 148;
+    auto waves = [&](int w) { const long long ctas = (Bsz + 8 * w - 1) / (8 * w); return (ctas + nsm - 1) / nsm; };
+    if (waves(8) == 1) return 2;
+    int w = 8;
+    while (w > 4 && waves(w - 1) == waves(8)) --w;
+    return w;
+}
+
 int32_t riccati_quad_launch(int32_t dtype, const LqrQuadP& P, cudaStream_t stream) {
     ZB_ARG(dtype == ZB_F64, "the cooperative (12,4) Riccati kernel is instantiated for fp64 (fp32 has its own kernels, lqr_t1.cuh)");
-    const int warps = 2;  // 16 problems per CTA, so four CTAs share an SM's shared memory
+    const int warps = quad64_warps(P.Bsz);
     const size_t smem = (size_t)warps * 8 * LQ_PS_F64 * sizeof(double);
     const unsigned grid = (unsigned)((P.Bsz + warps * 8 - 1) / (warps * 8));
     if (P.cost_diagonal && P.Q.st == 0 && P.R.st == 0) {
@@ -419,7 +432,7 @@ int32_t riccati_quad_launch(int32_t dtype, const LqrQuadP& P, cudaStream_t strea
 }
 
 int32_t mpc_closed_loop_quad64_launch(const ClosedLoopQuadP& P, cudaStream_t stream) {
-    const int warps = 2;
+    const int warps = quad64_warps(P.Bsz);
     const size_t smem = (size_t)warps * 8 * LQ_PS_F64 * sizeof(double);
     const unsigned grid = (unsigned)((P.Bsz + warps * 8 - 1) / (warps * 8));
     if (P.cost_diagonal) {
