@@ -832,7 +832,8 @@ inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
     // 35.5 -> 33.1 ms, cfg 5 71.8 -> 70.4 ms).  A batch below one wave keeps small CTAs (fp32: 4 warps, fp64: 2) spread over the SMs.
     const long long nsm = 148;
     const int maxw = (int)std::min<size_t>(8, (size_t)232448 / ((size_t)8 * PS * sizeof(T)));
-    auto waves = [&](int w) { const long long ctas = (P.Bsz + 8 * w - 1) / (8 * w); return (ctas + nsm - 1) / nsm; };
+    const long long nprob = (P.act.perm && P.active_hint > 0 && P.active_hint < P.Bsz) ? P.active_hint : P.Bsz;  // slots in use
+    auto waves = [&](int w) { const long long ctas = (nprob + 8 * w - 1) / (8 * w); return (ctas + nsm - 1) / nsm; };
     if (DDP) {
         // DDP: ONE CTA per SM whose warps meet at a barrier every step (see the kernel), also below one wave
         const int min_w = waves(maxw) == 1 ? 1 : (maxw + 1) / 2;
@@ -848,7 +849,7 @@ inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
     // fp32 DDP: two 4-warp CTAs per SM run faster than three (measured 65 vs 79 ms on cfg 5: the ~1,100-instruction Jacobi loop
     // of three CTAs in different phases thrashes the instruction cache), so the request is padded past a third of the SM
     if (DDP && sizeof(T) == 4 && smem < 80 * 1024) smem = 80 * 1024;
-    const unsigned grid = (unsigned)((P.Bsz + warps * 8 - 1) / (warps * 8));
+    const unsigned grid = (unsigned)((nprob + warps * 8 - 1) / (warps * 8));
     ZB_CUDA(cudaFuncSetAttribute(k_ilqr_backward_quad<T, CDIAG, DDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_ilqr_backward_quad<T, CDIAG, DDP><<<grid, warps * 32, smem, stream>>>(P);
     ZB_CUDA(cudaGetLastError());

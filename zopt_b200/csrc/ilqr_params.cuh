@@ -24,6 +24,7 @@ struct IlqrFastP {
     void *l, *L;
     double eps;  // ensurePositiveDefinite threshold (1e-3)
     ActiveP act;
+    long long active_hint;  // host-side upper bound on *act.count (Bsz when unknown): sizes the grid and the CTAs
     void* ev;    // DDP fp64: (Bsz,84) scratch, eigenvectors of the clamped 9x9 block carried from step to step (null: cold start every step)
 };
 
