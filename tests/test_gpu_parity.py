@@ -962,3 +962,42 @@ def test_pytree_constructors_and_building_block_pipeline():
     # unregistered callables are refused by the constructors too
     with pytest.raises(TypeError):
         pytrees.AffineDynamics.from_trajectory(lambda x, u: x + u, traj)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_ddp_warm_started_eigen_clamp_and_cta_size(dt, monkeypatch):
+    """DDP backward pass (csrc/ilqr_fast.cuh, round 2): the eigen-clamp of the 9x9 second-order block (ilqrUtils.py:217-219,
+    237-251) is warm-started from the eigenvectors of the previous step.  V max(L, eps) V' does not depend on how the
+    eigen-solve got there, so (i) the solver's iterates with the warm start agree with a cold start at every step (test
+    hook ZB_DDP_COLD_START) to the solver tolerance, (ii) the mapping of problems to CTAs (1..8 warps per CTA, chosen by the
+    launcher to fill the last wave) changes no bit, and (iii) both agree with the oracle's torch.linalg.eigh-based solver."""
+    from zopt_b200 import ilqrUtils
+    from zopt_b200.models import QuadcopterEuler, QuadraticCost, QuadraticTerminalCost
+    N, Bsz = 25, 77
+    rng = np.random.default_rng(41)
+    x0 = np.zeros((Bsz, 12))
+    x0[:, 9:12] = rng.uniform(-5, 5, (Bsz, 3))
+    x0[:, 6:9] = rng.uniform(-0.3, 0.3, (Bsz, 3))
+    uG = rep_np(configs.U_TRIM, N)
+    args = (QuadcopterEuler(0.1), QuadraticCost(np.eye(12), 0.2 * np.eye(4)), QuadraticTerminalCost(10 * np.eye(12)))
+    run = lambda: ilqrUtils.differentialDynamicProgramming(*args, cuda(x0, dt), torch.as_tensor(uG, dtype=dt), maxIter=4, tol=-1.0)
+    monkeypatch.delenv("ZB_DDP_WARPS", raising=False)
+    monkeypatch.delenv("ZB_DDP_COLD_START", raising=False)
+    traj, L, J, _ = run()
+    for w in (1, 2, 5, 8):
+        monkeypatch.setenv("ZB_DDP_WARPS", str(w))
+        t2, L2, J2, _ = run()
+        assert torch.equal(t2.xTraj, traj.xTraj) and torch.equal(t2.uTraj, traj.uTraj) and torch.equal(L2, L) and torch.equal(J2, J), w
+    monkeypatch.delenv("ZB_DDP_WARPS")
+    monkeypatch.setenv("ZB_DDP_COLD_START", "1")
+    tc, Lc, Jc, _ = run()
+    monkeypatch.delenv("ZB_DDP_COLD_START")
+    tol = 1e-10 if dt == torch.float64 else 2e-3  # fp32: four DDP iterations amplify the rounding of either path alike
+    assert per_problem_relerr(tc.xTraj, traj.xTraj.cpu().numpy()).max() < tol and per_problem_relerr(Lc, L.cpu().numpy()).max() < 10 * tol
+    if dt == torch.float64:
+        oac = OQuadcopter()
+        Q, R = torch.eye(12, dtype=torch.float64), 0.2 * torch.eye(4, dtype=torch.float64)
+        for b in (0, 33, 76):
+            to, Lo, Jo, _ = oilqr.differentialDynamicProgramming(oac.eulerStep(0.1), lambda x, u: x @ Q @ x + u @ R @ u, lambda x: 10 * x @ Q @ x,
+                                                                 torch.as_tensor(x0[b]), torch.as_tensor(uG), maxIter=4, tol=-1.0)
+            assert relerr(traj.xTraj[b], to.xTraj) < 1e-10 and relerr(traj.uTraj[b], to.uTraj) < 1e-10 and relerr(L[b], Lo) < 1e-9

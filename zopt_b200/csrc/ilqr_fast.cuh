@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(256) k_ilqr_backward_quad(IlqrFastP P) {
     // DDP warm start: fp32 keeps the eigenvectors of the previous step in its slab; the packed fp64 slab sends them through
     // a per-problem global scratch (648 bytes, L2-resident) and copies them back into the dead f_x region at the top of a step
     T* evg = (DDP && P.ev) ? reinterpret_cast<T*>(P.ev) + b * 84 : nullptr;
-    const bool warm_ok = DDP && (!PACK || P.ev != nullptr);
+    const bool warm_ok = DDP && !P.cold_start && (!PACK || P.ev != nullptr);
     for (int k = N - 1; k >= 0; --k) {
         T* xk = STAGE ? xk0 + (k & 1) * XK2 : xk0;
         // The DDP step is ~8,000 instructions (128 KB) of mostly straight-line code, far beyond the instruction cache: warps that
@@ -851,7 +851,9 @@ inline int32_t ilqr_fast_launch_impl(const IlqrFastP& P, cudaStream_t stream) {
     if (DDP && sizeof(T) == 4 && smem < 80 * 1024) smem = 80 * 1024;
     const unsigned grid = (unsigned)((nprob + warps * 8 - 1) / (warps * 8));
     ZB_CUDA(cudaFuncSetAttribute(k_ilqr_backward_quad<T, CDIAG, DDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_ilqr_backward_quad<T, CDIAG, DDP><<<grid, warps * 32, smem, stream>>>(P);
+    IlqrFastP Pl = P;
+    if (DDP && getenv("ZB_DDP_COLD_START")) Pl.cold_start = 1;
+    k_ilqr_backward_quad<T, CDIAG, DDP><<<grid, warps * 32, smem, stream>>>(Pl);
     ZB_CUDA(cudaGetLastError());
     return 0;
 }

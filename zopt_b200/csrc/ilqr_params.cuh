@@ -25,6 +25,7 @@ struct IlqrFastP {
     double eps;  // ensurePositiveDefinite threshold (1e-3)
     ActiveP act;
     long long active_hint;  // host-side upper bound on *act.count (Bsz when unknown): sizes the grid and the CTAs
+    int cold_start;  // DDP: every eigen-solve starts from the identity (test hook ZB_DDP_COLD_START; the warm start is the default)
     void* ev;    // DDP fp64: (Bsz,84) scratch, eigenvectors of the clamped 9x9 block carried from step to step (null: cold start every step)
 };
 

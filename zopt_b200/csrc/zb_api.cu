@@ -590,7 +590,7 @@ int32_t zb_ilqr_solve(int32_t dtype, int32_t device, void* stream, int64_t Bsz, 
     }
     SolveBackP Bk{Bsz, N, second_order, P.M, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3};
     const bool fast_bwd = N >= 1 && ilqr_fast_eligible(P.M, second_order, cost_diagonal) && aligned16(xTraj) && aligned16(uTraj) && aligned16(L_out);
-    IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3, ActiveP{nullptr, nullptr}, Bsz, ev_ws};
+    IlqrFastP Fb{Bsz, N, P.M.dt, P.C, xTraj, uTraj, Czz, Vfxx, converged_out, l_ws, L_out, 1e-3, ActiveP{nullptr, nullptr}, Bsz, 0, ev_ws};
     if (track) {
         rc = compact_active_launch(Bsz, converged_out, perm2[0], count2, s);
         if (rc) return rc;
