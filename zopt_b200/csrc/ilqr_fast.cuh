@@ -463,6 +463,7 @@ __global__ void __launch_bounds__(256) k_ilqr_backward_quad(IlqrFastP P) {
         // step keeps the warps of a CTA within one step of each other, so that they share the fetched lines.
         // (The iLQR instantiations are a third of the size and run 10-20 % SLOWER with the barrier: lockstep warps contend for the
         // same pipe at the same time.)
+        // (A barrier every second / fourth step measured slower: 68.8 / 70.2 ms against 67.2 ms on cfg 5.)
         if (DDP && blockDim.x > 32) __syncthreads();
         if (PACK && warm_ok && k < N - 1) {  // 81 words = 41 16-byte chunks (the scratch row is 84 words), 10-11 per thread
 #pragma unroll
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(256) k_ilqr_backward_quad(IlqrFastP P) {
                         for (int j = 0; j < i; ++j) o4[tri9(i, j) & 3] = fma(A9[tri9(i, j)], A9[tri9(i, j)], o4[tri9(i, j) & 3]);
                     }
                     const T off = (o4[0] + o4[1]) + (o4[2] + o4[3]), dg = d2[0] + d2[1];
-                    const T thr = (sizeof(T) == 8) ? T(1e-30) : T(1e-15), tiny = (sizeof(T) == 8) ? T(1e-300) : T(1e-37);
+                    const T thr = (sizeof(T) == 8) ? T(1e-29) : T(1e-15), tiny = (sizeof(T) == 8) ? T(1e-300) : T(1e-37);
                     if (off <= thr * dg || off < tiny) break;
                     jacobi_round<T, 0>(A9, Wr, csbuf, t, qmask);
                     jacobi_round<T, 1>(A9, Wr, csbuf + 24, t, qmask);  // alternate buffers: a round's stores never race the previous round's loads
@@ -749,13 +750,17 @@ __global__ void __launch_bounds__(256) k_ilqr_backward_quad(IlqrFastP P) {
         }
         // v_xx' is symmetric: of the 9 4x4 blocks only 6 are distinct.  Thread t computes (t, t) and ((t+1)%3, t) -- for t = 2
         // that is the UPPER block (0, 2), stored together with its transpose (2, 0) -- so every thread does 2 blocks, not 3.
-        // (The DDP instantiation keeps the 3-block loop with a compile-time row block: its clamped-block lookups and register
-        // budget are tuned around it -- measured 153 vs 197 ms on cfg 5.)
-        constexpr int NBLK = DDP ? 3 : 2;
+        // (Round 1's DDP instantiation kept a 3-block loop with a compile-time row block, 153 vs 197 ms then; with the eigen-solve
+        // restructured in round 2 the two-block form wins there too: cfg 5 69.6 -> 67.2 ms.  ZB_DDP_NBLK=3 restores it.)
+#ifndef ZB_DDP_NBLK
+#define ZB_DDP_NBLK 2
+#endif
+        constexpr bool B3 = DDP && ZB_DDP_NBLK == 3;
+        constexpr int NBLK = B3 ? 3 : 2;
 #pragma unroll
         for (int bi = 0; bi < NBLK; ++bi) {
             const int tb = t < 3 ? t : 0;  // thread 3 (the f_u tile) owns no block: it shadows thread 0 and stores nothing
-            const int sblk = DDP ? bi : ((bi == 0) ? tb : (tb == 2 ? 0 : tb + 1));  // rows 4*sblk .. 4*sblk+3 of the tile = block (sblk, t)
+            const int sblk = B3 ? bi : ((bi == 0) ? tb : (tb == 2 ? 0 : tb + 1));  // rows 4*sblk .. 4*sblk+3 of the tile = block (sblk, t)
             T acc[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -799,13 +804,13 @@ __global__ void __launch_bounds__(256) k_ilqr_backward_quad(IlqrFastP P) {
             }
             // write back, lower triangle wins: strictly-lower blocks are stored with their transpose,
             // diagonal blocks are mirrored, upper blocks are dropped (their transposes are authoritative)
-            if (DDP ? (sblk > t) : (t < 3 && sblk != t)) {
+            if (B3 ? (sblk > t) : (t < 3 && sblk != t)) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     stv4(Vs + (4 * sblk + r) * 12 + 4 * t, acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
                     stv4(Vs + (4 * t + r) * 12 + 4 * sblk, acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
                 }
-            } else if (DDP ? (sblk == t) : (t < 3)) {
+            } else if (B3 ? (sblk == t) : (t < 3)) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     T e[4];
