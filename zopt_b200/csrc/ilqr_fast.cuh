@@ -463,7 +463,9 @@ __global__ void __launch_bounds__(256) k_ilqr_backward_quad(IlqrFastP P) {
         // step keeps the warps of a CTA within one step of each other, so that they share the fetched lines.
         // (The iLQR instantiations are a third of the size and run 10-20 % SLOWER with the barrier: lockstep warps contend for the
         // same pipe at the same time.)
-        // (A barrier every second / fourth step measured slower: 68.8 / 70.2 ms against 67.2 ms on cfg 5.)
+        // (Measured alternatives on cfg 5, 66.6 ms as is: a barrier every second / fourth step 68.8 / 70.2 ms; a split-phase barrier
+        // -- two mbarriers, a warp enters step s once every warp has entered step s-1 -- 79 ms: one step of slack already spreads
+        // the warps over the 128 KB body; a second barrier between the eigen-solve and the Riccati step: no change.)
         if (DDP && blockDim.x > 32) __syncthreads();
         if (PACK && warm_ok && k < N - 1) {  // 81 words = 41 16-byte chunks (the scratch row is 84 words), 10-11 per thread
 #pragma unroll
