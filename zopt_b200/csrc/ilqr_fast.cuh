@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(256) k_ilqr_backward_quad(IlqrFastP P) {
                     }
                     const T off = (o4[0] + o4[1]) + (o4[2] + o4[3]), dg = d2[0] + d2[1];
                     const T thr = (sizeof(T) == 8) ? T(1e-29) : T(1e-15), tiny = (sizeof(T) == 8) ? T(1e-300) : T(1e-37);
-                    if (off <= thr * dg || off < tiny) break;
+                    if (!(off > thr * dg) || off < tiny) break;  // converged -- or NaN (a diverged problem must not hold its CTA for 270 rounds a step)
                     jacobi_round<T, 0>(A9, Wr, csbuf, t, qmask);
                     jacobi_round<T, 1>(A9, Wr, csbuf + 24, t, qmask);  // alternate buffers: a round's stores never race the previous round's loads
                 }
