@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_forward_commit(RollP P, const v
     if (S.converged && S.J && S.converged[b]) return;
     const T* Ja = reinterpret_cast<const T*>(Jall) + b * 16;
     const int idx = argmin16<T>(Ja);
-    const int n = P.M.n, m = P.M.m, N = P.N;
+    const int n = ZB_N_OF(P.M.n), m = ZB_M_OF(P.M.m), N = P.N;
     if (spec && idx < SPEC_N) {
         const long long per = (long long)(N + 1) * n + (long long)N * m;
         const T* base = reinterpret_cast<const T*>(spec) + (long long)idx * P.Bsz * per;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_solve_init(RollP P, const void*
                              int32_t* alpha_log, void* J_log, int maxIter) {
     long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (b >= P.Bsz) return;
-    const int n = P.M.n, m = P.M.m, N = P.N;
+    const int n = ZB_N_OF(P.M.n), m = ZB_M_OF(P.M.m), N = P.N;
     const T* x0 = reinterpret_cast<const T*>(P.x0) + b * n;
     const T* ug = reinterpret_cast<const T*>(uGuess) + b * (long long)N * m;
     T* xT = reinterpret_cast<T*>(P.xTraj) + b * (long long)(N + 1) * n;

@@ -105,12 +105,23 @@ ZB_HD void lu_solve(T* G, int m, T* RHS, int nrhs) {
 // ensurePositiveDefinite (zopt/ilqrUtils.py:217-219): S <- V max(Lambda, eps) V^T for symmetric S (p x p).
 // Cyclic Jacobi eigen-decomposition; the result is a spectral function of S, hence independent of the
 // eigenvector basis LAPACK syevd would have picked.  W is p x p scratch (eigenvectors).
+// In a user-model plug-in p is a compile-time constant at every call site (n or n + m of that model): for small blocks the
+// loops are unrolled after inlining, so S and W are indexed statically and live in registers instead of local memory.
+#if defined(ZB_USER_MODEL_HEADER) && ZB_PD_MAX <= 8  // (the header name comes on the plug-in's nvcc command line)
+#define ZB_PD_UNROLL _Pragma("unroll")
+#else
+#define ZB_PD_UNROLL
+#endif
 template <typename T>
 ZB_HD void pd_clamp(T* S, T* W, int p, T eps) {
+    ZB_PD_UNROLL
     for (int i = 0; i < p; ++i)
+        ZB_PD_UNROLL
         for (int j = 0; j < p; ++j) W[i * p + j] = (i == j) ? T(1) : T(0);
     // jnp.linalg.eigh symmetrises its input by default (symmetrize_input=True): (S + S^T)/2
+    ZB_PD_UNROLL
     for (int i = 0; i < p; ++i)
+        ZB_PD_UNROLL
         for (int j = i + 1; j < p; ++j) {
             T a = T(0.5) * (S[i * p + j] + S[j * p + i]);
             S[i * p + j] = a;
@@ -119,13 +130,17 @@ ZB_HD void pd_clamp(T* S, T* W, int p, T eps) {
     const T tiny = (sizeof(T) == 8) ? T(1e-300) : T(1e-37);
     for (int sweep = 0; sweep < 30; ++sweep) {
         T off = T(0), diag = T(0);
+        ZB_PD_UNROLL
         for (int i = 0; i < p; ++i) {
             diag += S[i * p + i] * S[i * p + i];
+            ZB_PD_UNROLL
             for (int j = 0; j < i; ++j) off += S[i * p + j] * S[i * p + j];
         }
         const T thr = (sizeof(T) == 8) ? T(1e-32) : T(1e-15);
         if (off <= thr * diag || off < tiny) break;
+        ZB_PD_UNROLL
         for (int a = 0; a < p - 1; ++a)
+            ZB_PD_UNROLL
             for (int b = a + 1; b < p; ++b) {
                 T apq = S[a * p + b];
                 if (apq == T(0)) continue;
@@ -133,16 +148,19 @@ ZB_HD void pd_clamp(T* S, T* W, int p, T eps) {
                 T tau = (aqq - app) / (T(2) * apq);
                 T t = (tau >= T(0) ? T(1) : T(-1)) / (fabs(tau) + sqrt(T(1) + tau * tau));
                 T c = T(1) / sqrt(T(1) + t * t), s = t * c;
+                ZB_PD_UNROLL
                 for (int k = 0; k < p; ++k) {  // columns a,b of S
                     T ska = S[k * p + a], skb = S[k * p + b];
                     S[k * p + a] = c * ska - s * skb;
                     S[k * p + b] = s * ska + c * skb;
                 }
+                ZB_PD_UNROLL
                 for (int k = 0; k < p; ++k) {  // rows a,b of S
                     T sak = S[a * p + k], sbk = S[b * p + k];
                     S[a * p + k] = c * sak - s * sbk;
                     S[b * p + k] = s * sak + c * sbk;
                 }
+                ZB_PD_UNROLL
                 for (int k = 0; k < p; ++k) {  // accumulate eigenvectors (columns of W)
                     T wka = W[k * p + a], wkb = W[k * p + b];
                     W[k * p + a] = c * wka - s * wkb;
@@ -152,10 +170,14 @@ ZB_HD void pd_clamp(T* S, T* W, int p, T eps) {
     }
     // eigenvalues on the diagonal of S; rebuild
     T lam[ZB_PD_MAX];
+    ZB_PD_UNROLL
     for (int i = 0; i < p; ++i) lam[i] = S[i * p + i] > eps ? S[i * p + i] : eps;
+    ZB_PD_UNROLL
     for (int i = 0; i < p; ++i)
+        ZB_PD_UNROLL
         for (int j = 0; j <= i; ++j) {
             T s = T(0);
+            ZB_PD_UNROLL
             for (int k = 0; k < p; ++k) s += W[i * p + k] * lam[k] * W[j * p + k];
             S[i * p + j] = s;
             S[j * p + i] = s;

@@ -245,7 +245,7 @@ struct RollP {
 
 template <typename T>
 ZB_HD T rollout_core(const RollP& P, long long b, T alpha, bool write) {
-    const int n = P.M.n, m = P.M.m, N = P.N;
+    const int n = ZB_N_OF(P.M.n), m = ZB_M_OF(P.M.m), N = P.N;
     const T* x0 = reinterpret_cast<const T*>(P.x0) + b * n;
     const T* lp = reinterpret_cast<const T*>(P.l) + b * (long long)N * m;
     const T* Lp = reinterpret_cast<const T*>(P.L) + b * (long long)N * m * n;
@@ -475,7 +475,7 @@ struct SolveBackP {
 template <typename T>
 ZB_HD void solve_backward_problem(const SolveBackP& P, long long b) {
     if (P.done && P.done[b]) return;
-    const int n = P.M.n, m = P.M.m, N = P.N, p = n + m;
+    const int n = ZB_N_OF(P.M.n), m = ZB_M_OF(P.M.m), N = P.N, p = n + m;
     const T* xT = reinterpret_cast<const T*>(P.xTraj) + b * (long long)(N + 1) * n;
     const T* uT = reinterpret_cast<const T*>(P.uTraj) + b * (long long)N * m;
     const T* Czz = reinterpret_cast<const T*>(P.Czz) + b * (long long)p * p;

@@ -14,10 +14,26 @@
 #define ZB_MAX_M 8
 #endif
 
+// A user-model plug-in (zb_user_model.cu) is compiled for ONE model: its (n, m) are compile-time constants there, so the
+// per-problem arrays are exactly as large as the model needs and every loop over states / controls has a constant trip
+// count (unrolled, arrays promoted to registers) -- the library's generic kernels size everything for (16, 8) in local memory.
+#ifdef ZB_USER_MODEL
+#define ZB_N_OF(x) (ZB_USER_N)
+#define ZB_M_OF(x) (ZB_USER_M)
+#else
+#define ZB_N_OF(x) (x)
+#define ZB_M_OF(x) (x)
+#endif
+
 namespace zb {
 
+#ifdef ZB_USER_MODEL
+constexpr int NX = ZB_USER_N;
+constexpr int NU = ZB_USER_M;
+#else
 constexpr int NX = ZB_MAX_N;
 constexpr int NU = ZB_MAX_M;
+#endif
 
 // ---- zopt/lqrUtils.py:167-170  riccatiStep (Joseph form, as written) -------------------------
 // V (n x n) in/out; L (m x n) out.  A,B,Q,R may live in global memory.

@@ -147,7 +147,7 @@ __attribute__((visibility("default"))) int32_t zb_user_ilqr_solve(int32_t dtype,
     if (rc) return rc;
     ZB_ARG(maxIter >= 0, "negative maxIter");
     ZB_ARG(x0 && uGuess && xTraj && uTraj && L_out && J_out && converged_out && iters_out, "NULL operand");
-    const int n = P.M.n, m = P.M.m, p = n + m;
+    const int n = ZB_N_OF(P.M.n), m = ZB_M_OF(P.M.m), p = n + m;
     const size_t need = zb_user_ilqr_workspace_bytes(dtype, Bsz, N);
     ZB_ARG(workspace && workspace_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
     if (Bsz == 0) return 0;

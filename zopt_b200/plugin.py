@@ -263,7 +263,7 @@ class SymbolicDynamics:
             with open(fn, "rb") as fh:
                 h.update(os.path.basename(fn).encode())
                 h.update(fh.read())
-        h.update(" ".join([NVCC] + self._NVCC_FLAGS).encode())
+        h.update(" ".join([NVCC] + self._NVCC_FLAGS + ["ZB_PD_MAX=n+m"]).encode())
         return h.hexdigest()[:16]
 
     def build(self):
@@ -281,7 +281,8 @@ class SymbolicDynamics:
             fd, tmp_so = tempfile.mkstemp(prefix=f"libzb_model_{key}.", suffix=".so.tmp", dir=CACHE_DIR)
             os.close(fd)
             try:
-                cmd = [NVCC] + self._NVCC_FLAGS + [f'-DZB_USER_MODEL_HEADER="{tmp_hdr}"', "-I", _CSRC, "-shared", "-o", tmp_so,
+                # the eigen-clamp scratch is sized for this model's stacked Hessian (n + m), not for the library's largest (24)
+                cmd = [NVCC] + self._NVCC_FLAGS + [f"-DZB_PD_MAX={self.n + self.m}", f'-DZB_USER_MODEL_HEADER="{tmp_hdr}"', "-I", _CSRC, "-shared", "-o", tmp_so,
                                                    os.path.join(_CSRC, "zb_user_model.cu")]
                 r = subprocess.run(cmd, capture_output=True, text=True)
                 if r.returncode != 0:
