@@ -129,17 +129,45 @@ def cpu_step(xbar, ubar, qd, rd, N, dt, threads):
     return torch.stack(xs, 1), torch.stack(us, 1)
 
 
+def c_oracle_or_none():
+    """oracle/c/zopt_oracle.c through ctypes (compiled for this host on first use), or None when it cannot be built here"""
+    try:
+        from oracle import c_oracle
+        c_oracle.load()
+        return c_oracle
+    except Exception as e:  # no gcc / no OpenMP on this box: the torch port below still runs
+        print(f"bench: C oracle unavailable ({type(e).__name__}: {str(e)[:200]}); falling back to the torch-CPU port", file=sys.stderr)
+        return None
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def time_cpu(sample, steps, warmup, rank=0):
+    """-> (solves/s, seconds per step, threads, description).  The compiled restatement (plain C + OpenMP over problems,
+    fp64) when it can be built on this host, else the torch-CPU port; both are checked against the reference's goldens
+    (tests/test_c_oracle.py, tests/test_golden.py)."""
     d = make_problem(sample, rank)
-    threads = os.cpu_count() or 1
-    args = (d["xbar"], d["ubar"], d["qdiag"], d["rdiag"], d["N"], d["dt"], threads)
+    threads = host_threads()
+    co = c_oracle_or_none()
+    if co is not None:
+        step = lambda: co.lqrMpcSolveBatch(d["xbar"], d["ubar"], d["qdiag"], d["rdiag"], d["N"], d["dt"], 10.0, threads)
+        how = "plain-C + OpenMP restatement of the reference's algorithm (oracle/c/zopt_oracle.c: forward-mode linearisation, Riccati step as written, plan rollout), fp64"
+    else:
+        args = (d["xbar"], d["ubar"], d["qdiag"], d["rdiag"], d["N"], d["dt"], threads)
+        step = lambda: cpu_step(*args)
+        how = "torch-CPU fp64 oracle port (a Python loop of batched small products)"
     for _ in range(warmup):
-        cpu_step(*args)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_step(*args)
+        step()
     el = time.perf_counter() - t0
-    return sample * steps / el, el / steps, threads
+    return sample * steps / el, el / steps, threads, how
 
 
 def try_real_reference(sample, steps, warmup):
@@ -186,13 +214,21 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    # bounded sample of the workload per step, scaled so that the whole run is ~20 full samples of CPU work whatever K is
-    sample = max(256, min(args.cpu_sample, args.cpu_sample * 20 // max(args.steps, 1)))
+    # bounded sample of the workload per step: sized from a probe so that the K steps take about a minute of CPU time, and
+    # never more than the full step (args.batch problems)
+    co = c_oracle_or_none()
+    probe = 2048 if co is not None else 512
+    rate = time_cpu(probe, 1, 1)[0]
+    sample = int(max(256, min(args.batch, rate * 60.0 / max(args.steps, 1))))
     real = try_real_reference(sample, args.steps, min(args.warmup, 1))
     kind = "reference" if real else "port"
-    val, sec, threads = real if real else time_cpu(sample, args.steps, min(args.warmup, 1))
+    if real:
+        val, sec, threads = real
+        how = "the reference's own jax.jit(jax.vmap(...)) on XLA:CPU"
+    else:
+        val, sec, threads, how = time_cpu(sample, args.steps, min(args.warmup, 1))
     cb = {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
-          "sample": f"{sample} problems of the same cfg-2 workload per step (torch-CPU fp64 oracle port; JAX is not installed)"}
+          "sample": f"{sample} problems of the same cfg-2 workload per step, {args.steps} steps; {how}; JAX is not installed"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -525,7 +561,15 @@ def run_ours(args):
                 "hbm_achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
                 "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                 "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
-        cpu_val, cpu_sec, threads = time_cpu(args.cpu_sample, 3, 1)
+        # the full step (Bsz problems) through the compiled restatement, about ten seconds of CPU work in all; the torch port
+        # (no compiler on the box) keeps its 16,384-problem sample
+        if c_oracle_or_none() is not None:
+            r0 = time_cpu(4096, 1, 1)[0]
+            cpu_n = Bsz
+            cpu_steps = int(max(3, min(50, 10.0 * r0 / cpu_n)))
+        else:
+            cpu_n, cpu_steps = args.cpu_sample, 3
+        cpu_val, cpu_sec, threads, cpu_how = time_cpu(cpu_n, cpu_steps, 1)
         # copy roof: all ranks moving the step's D2H payload at once; e2e as a fraction of it
         roof_gbs = d2h * world / (roof_ms * 1e-3) / 1e9
         e2e_gbs = e2e_val * (d2h / Bsz) / 1e9
@@ -607,7 +651,7 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(Bsz), "clocks": clocks, "e2e": e2e,
             "gpu_launches": 2 * args.steps, "roofline": roof, "extra": extra,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{args.cpu_sample} problems of the same workload per step, 3 steps of {cpu_sec:.2f} s after 1 warm-up, torch-CPU fp64 oracle port (JAX not installed)"},
+                             "sample": f"{cpu_n} problems of the same workload per step, {cpu_steps} steps of {cpu_sec:.2f} s after 1 warm-up; {cpu_how}; JAX is not installed"},
             "host": hostbind.host_topology(), "digest": tail,
         }
         print(json.dumps(line))
