@@ -27,4 +27,9 @@ Parity pinning (see DESIGN.md "Oracle"):
     the fixtures are used.
   * `lqrMpc` (cvxpy -> OSQP) has no numeric assertion in the reference:
     parity unpinned for the bound-active case.
+
+`oracle/c/zopt_oracle.c` (bound by `oracle/c_oracle.py`, built into
+`oracle/_build/`) is the same kind of thing in plain C + OpenMP for the
+headline path only -- what `bench.py` times on the host cores; it is pinned
+against the same goldens and against this package (tests/test_c_oracle.py).
 """
