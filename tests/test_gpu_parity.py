@@ -1001,3 +1001,26 @@ def test_ddp_warm_started_eigen_clamp_and_cta_size(dt, monkeypatch):
             to, Lo, Jo, _ = oilqr.differentialDynamicProgramming(oac.eulerStep(0.1), lambda x, u: x @ Q @ x + u @ R @ u, lambda x: 10 * x @ Q @ x,
                                                                  torch.as_tensor(x0[b]), torch.as_tensor(uG), maxIter=4, tol=-1.0)
             assert relerr(traj.xTraj[b], to.xTraj) < 1e-10 and relerr(traj.uTraj[b], to.uTraj) < 1e-10 and relerr(L[b], Lo) < 1e-9
+
+
+@pytest.mark.parametrize("per,chunk,Tsim", [(1, 4, 23), (1, 1, 9), (2, 7, 30)])
+def test_closed_loop_mpc_nine_lane_work_rotation_equals_static_mapping(per, chunk, Tsim, monkeypatch):
+    """k_mpc_closed_loop_quad_w9<QUEUE> (csrc/mpc_warp.cuh, round 2): when the batch is just past a whole number of warps per
+    scheduler the simulation is cut into chunks and a fixed set of one-warp workers draws (chunk, problem-triple) tickets, the
+    trajectory row written at the end of a chunk being the next chunk's initial state.  The arithmetic of a step is untouched,
+    so the result equals the static one-warp-per-triple mapping BIT FOR BIT -- ragged batch (last triple partly idle), chunk
+    lengths that do not divide the simulation, one and two workers per scheduler."""
+    from zopt_b200.mpcUtils import quadcopterClosedLoopMpc
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    Bsz = 3 * 4 * sms * per + 3 * 61 + 1  # per*4*sms full triples + 61 more + one problem alone in the last triple
+    d = configs.cfg3(Bsz=Bsz)
+    x = cuda(d["xbar"], torch.float32)
+    x[:, 9:12] *= 0.2
+    Q, R = torch.diag_embed(cuda(d["qdiag"], torch.float32)), torch.diag_embed(cuda(d["rdiag"], torch.float32))
+    monkeypatch.setenv("ZB_W9_WORKERS_PER_SCHED", "0")
+    xs0, us0 = quadcopterClosedLoopMpc(x, Q, R, 12, Tsim, Qf=10 * Q, variant="warp")[:2]
+    monkeypatch.setenv("ZB_W9_WORKERS_PER_SCHED", str(per))
+    monkeypatch.setenv("ZB_W9_CHUNK", str(chunk))
+    xs1, us1 = quadcopterClosedLoopMpc(x, Q, R, 12, Tsim, Qf=10 * Q, variant="warp")[:2]
+    assert torch.equal(xs0, xs1) and torch.equal(us0, us1)
+    assert torch.isfinite(xs1).all() and float((xs1[:, -1] - xs1[:, 0]).abs().max()) > 0

@@ -21,6 +21,7 @@
 // instruction sequence in both, t1_common.cuh).
 // Reference loop: demos/lqrMpc.py:42-47 around zopt/mpcUtils.py:47-59 with inactive bounds; step: zopt/lqrUtils.py:167-170.
 #pragma once
+#include <algorithm>
 #include "t1_common.cuh"
 #include "quad_model_gen.cuh"
 
@@ -38,7 +39,22 @@ __device__ __forceinline__ float rsq(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP P) {
+// QUEUE (round 2): the batch does not fit one warp per scheduler (more than 592 warps on a B200).  Measured: 1,776 problems
+// (592 warps) take 6.84 ms, 1,779 take 9.89 ms -- ONE scheduler with two warps sets the time for everybody, the other 591 idle for
+// the last third.  So the grid stays at `workers` one-warp CTAs (a multiple of the scheduler count) and the simulation is cut into
+// chunks of CH steps: a worker draws tickets (chunk-major: ticket = chunk * triples + triple) and advances WHICHEVER triple of
+// problems comes next by one chunk.  The state between chunks is the trajectory row the kernel writes anyway; done[triple] counts
+// the chunks completed (release / acquire through __threadfence).  A ticket only ever waits for a smaller ticket, and every drawn
+// ticket is held by a resident worker, so the scheme cannot deadlock.  All triples advance at the same pace and the run takes
+// triples / workers x (time of one warp alone) instead of the time of a doubled-up scheduler.
+struct W9Queue {
+    unsigned* ticket;  // next ticket
+    int* done;         // (triples) chunks completed
+    int chunk;         // simulation steps per chunk
+};
+
+template <bool QUEUE>
+__global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP P, W9Queue Wq) {
     __shared__ __align__(16) float sV[3 * SV];
     __shared__ __align__(16) float sW[3 * SW];
     __shared__ __align__(16) float sS[3 * 3 * 48];  // scratch tiles of the redundant upper lanes
@@ -49,7 +65,29 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
     const int g = ql / 9, q = ql - 9 * g;    // problem within the warp, lane within the problem
     const int r = q / 3, c = q - 3 * r;      // tile row / tile column
     const int base = 9 * g;                  // first lane of the problem
-    const long long b_raw = (long long)blockIdx.x * 3 + g;
+    const long long ntriples = (P.Bsz + 2) / 3;
+    const int nchunks = QUEUE ? (P.Tsim + Wq.chunk - 1) / Wq.chunk : 1;
+  for (;;) {  // QUEUE: one pass per ticket; otherwise a single pass (the loop is left at its end)
+    long long triple = blockIdx.x;
+    int ts_begin = 0, ts_end = P.Tsim, my_chunk = 0;
+    if (QUEUE) {
+        unsigned tk = 0;
+        if (lane == 0) tk = atomicAdd(Wq.ticket, 1u);
+        tk = __shfl_sync(FULL, tk, 0);
+        if ((long long)tk >= ntriples * nchunks) return;
+        my_chunk = (int)(tk / (unsigned)ntriples);
+        triple = tk - (unsigned)my_chunk * (unsigned)ntriples;
+        ts_begin = my_chunk * Wq.chunk;
+        ts_end = min(P.Tsim, ts_begin + Wq.chunk);
+        if (my_chunk > 0) {  // the previous chunk of this triple must have landed
+            // EVERY lane polls: with `if (lane == 0) spin; __syncwarp();` the warp stayed split for the rest of the pass and ran
+            // it at half speed (measured 17.3 against 8.4 ms at 2,048 problems)
+            const volatile int* d = Wq.done + triple;
+            while (*d < my_chunk) __nanosleep(100);
+            __threadfence();  // acquire: the trajectory row read below was written before the flag
+        }
+    }
+    const long long b_raw = triple * 3 + g;
     const bool active = b_raw < P.Bsz;
     const long long b = active ? b_raw : P.Bsz - 1;
     float* Vs = sV + g * SV;
@@ -81,8 +119,11 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
     }
     float x[12];
     {
-        const float4* gx = reinterpret_cast<const float4*>(P.x0 + b * 12);
-        const float4 x0 = __ldg(gx), x1 = __ldg(gx + 1), x2 = __ldg(gx + 2);
+        // chunk 0: the initial state; later chunks: the trajectory row the previous chunk ended on (written by another worker:
+        // read past L1).  Idle problem slots of the last triple keep re-reading the initial state of the problem they shadow.
+        const float4* gx = (QUEUE && my_chunk > 0 && active) ? reinterpret_cast<const float4*>(P.xSim + (b * (long long)(P.Tsim + 1) + ts_begin) * 12)
+                                                            : reinterpret_cast<const float4*>(P.x0 + b * 12);
+        const float4 x0 = __ldcg(gx), x1 = __ldcg(gx + 1), x2 = __ldcg(gx + 2);
         x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
         x[8] = x2.x; x[9] = x2.y; x[10] = x2.z; x[11] = x2.w;
     }
@@ -92,7 +133,7 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
     const bool out_lane = active && writer && q == 0;
 
 #pragma unroll 1
-    for (int ts = 0; ts < P.Tsim; ++ts) {
+    for (int ts = ts_begin; ts < ts_end; ++ts) {
         if (out_lane) {
             xS[(long long)ts * 3 + 0] = make_float4(x[0], x[1], x[2], x[3]);
             xS[(long long)ts * 3 + 1] = make_float4(x[4], x[5], x[6], x[7]);
@@ -283,19 +324,53 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
         if (out_lane) uS[ts] = make_float4(u[0], u[1], u[2], u[3]);
         t1::closed_loop_plant(x, ua, dt);
     }
-    if (out_lane) {
-        xS[(long long)P.Tsim * 3 + 0] = make_float4(x[0], x[1], x[2], x[3]);
-        xS[(long long)P.Tsim * 3 + 1] = make_float4(x[4], x[5], x[6], x[7]);
-        xS[(long long)P.Tsim * 3 + 2] = make_float4(x[8], x[9], x[10], x[11]);
+    if (out_lane) {  // the row after the last step of this pass: the final state, or the next chunk's starting point
+        xS[(long long)ts_end * 3 + 0] = make_float4(x[0], x[1], x[2], x[3]);
+        xS[(long long)ts_end * 3 + 1] = make_float4(x[4], x[5], x[6], x[7]);
+        xS[(long long)ts_end * 3 + 2] = make_float4(x[8], x[9], x[10], x[11]);
     }
+    if (!QUEUE) return;
+    __threadfence();  // the rows above are visible before the chunk is published
+    __syncwarp();
+    *reinterpret_cast<volatile int*>(Wq.done + triple) = my_chunk + 1;  // (every lane stores the same word: no divergent tail)
+  }
 }
 
 }  // namespace w9
 
 int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((P.Bsz + 2) / 3);
-    w9::k_mpc_closed_loop_quad_w9<<<grid, 32, 0, stream>>>(P);
+    const long long triples = (P.Bsz + 2) / 3;
+    int dev = 0, sms = 148;
+    ZB_CUDA(cudaGetDevice(&dev));
+    ZB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long sched = 4LL * sms;  // warp schedulers of the device
+    // Work rotation (W9Queue) pays when the batch is just past a whole number m of warps per scheduler: the static mapping then runs
+    // at the pace of m + 1 warps per scheduler although almost every scheduler holds m.  Measured on one B200 (200 x 50 steps):
+    // 1,779 problems 10.06 -> 7.7 ms, 2,048 (cfg 3 on 8 GPUs) 10.0 -> 8.3-9.2 ms, 4,096 (m = 2) 16.7 -> 13.1-13.8 ms; from ~1.3 m the
+    // waits for predecessor chunks eat the gain (2,400: 10.3 -> 10.2-12.0 ms) and the static mapping is kept.
+    // ZB_W9_WORKERS_PER_SCHED overrides m (0: static mapping), ZB_W9_CHUNK the chunk length.
+    int per = 0;
+    for (int m = 1; m <= 4; ++m)
+        if (triples > m * sched && 4 * triples <= 5 * m * sched) per = m;
+    if (const char* e = getenv("ZB_W9_WORKERS_PER_SCHED")) per = atoi(e);
+    if (per <= 0 || triples <= per * sched || P.Tsim < 2) {
+        w9::k_mpc_closed_loop_quad_w9<false><<<(unsigned)triples, 32, 0, stream>>>(P, w9::W9Queue{nullptr, nullptr, 0});
+        ZB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int chunk = 4;
+    if (const char* e = getenv("ZB_W9_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
+    // scratch: the ticket counter and one progress word per triple, stream-ordered so that concurrent calls do not share them
+    int* scratch = nullptr;
+    const size_t bytes = sizeof(int) * (size_t)(triples + 32);
+    ZB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, stream));
+    ZB_CUDA(cudaMemsetAsync(scratch, 0, bytes, stream));
+    const w9::W9Queue Wq{reinterpret_cast<unsigned*>(scratch), scratch + 32, chunk};
+    // `per` one-warp CTAs per scheduler; the block scheduler spreads them evenly over the SMs (measured: 592 CTAs run at the pace of
+    // one warp per scheduler)
+    w9::k_mpc_closed_loop_quad_w9<true><<<(unsigned)(per * sched), 32, 0, stream>>>(P, Wq);
     ZB_CUDA(cudaGetLastError());
+    ZB_CUDA(cudaFreeAsync(scratch, stream));
     return 0;
 }
 
