@@ -39,18 +39,21 @@ __device__ __forceinline__ float rsq(float x) {
     return y;
 }
 
-// QUEUE (round 2): the batch does not fit one warp per scheduler (more than 592 warps on a B200).  Measured: 1,776 problems
-// (592 warps) take 6.84 ms, 1,779 take 9.89 ms -- ONE scheduler with two warps sets the time for everybody, the other 591 idle for
-// the last third.  So the grid stays at `workers` one-warp CTAs (a multiple of the scheduler count) and the simulation is cut into
-// chunks of CH steps: a worker draws tickets (chunk-major: ticket = chunk * triples + triple) and advances WHICHEVER triple of
-// problems comes next by one chunk.  The state between chunks is the trajectory row the kernel writes anyway; done[triple] counts
-// the chunks completed (release / acquire through __threadfence).  A ticket only ever waits for a smaller ticket, and every drawn
-// ticket is held by a resident worker, so the scheme cannot deadlock.  All triples advance at the same pace and the run takes
-// triples / workers x (time of one warp alone) instead of the time of a doubled-up scheduler.
+// QUEUE (round 2): the batch does not fit a whole number of warps per scheduler.  Measured: 1,776 problems (592 warps on a B200's
+// 592 schedulers) take 6.84 ms, 1,779 take 9.89 ms -- ONE scheduler with two warps sets the time for everybody, the other 591
+// idle for the last third.  So the grid stays at `workers` one-warp CTAs (a multiple of the scheduler count) and the simulation
+// is cut into chunks of CH steps; ready problem-triples wait in a FIFO: a worker pops a triple, advances it by one chunk and
+// pushes it back.  A triple is in the queue only while nobody works on it, so no pass ever waits for another one, and the FIFO
+// order makes all triples advance at the same pace: the run takes triples / workers x (time of one warp alone) instead of the
+// time of a doubled-up scheduler.  The state between chunks is the trajectory row the kernel writes anyway; prog[triple] counts
+// the chunks completed (release / acquire through __threadfence).  The ring has one entry per push ever made (triples x chunks),
+// so it never wraps.
 struct W9Queue {
-    unsigned* ticket;  // next ticket
-    int* done;         // (triples) chunks completed
-    int chunk;         // simulation steps per chunk
+    unsigned* head;  // pops so far
+    unsigned* tail;  // pushes so far (starts at the number of triples: every triple is ready once)
+    int* ring;       // (triples * chunks) entries, -1 = not pushed yet; entry i is the i-th triple that became ready
+    int* prog;       // (triples) chunks completed
+    int chunk;       // simulation steps per chunk
 };
 
 template <bool QUEUE>
@@ -67,25 +70,27 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
     const int base = 9 * g;                  // first lane of the problem
     const long long ntriples = (P.Bsz + 2) / 3;
     const int nchunks = QUEUE ? (P.Tsim + Wq.chunk - 1) / Wq.chunk : 1;
-  for (;;) {  // QUEUE: one pass per ticket; otherwise a single pass (the loop is left at its end)
+    if (QUEUE) {  // seed the queue: every triple is ready for its first chunk (the pops below wait for their entry to appear)
+        for (long long j = blockIdx.x; j < ntriples; j += gridDim.x) *reinterpret_cast<volatile int*>(Wq.ring + j) = (int)j;
+    }
+  for (;;) {  // QUEUE: one pass per popped triple; otherwise a single pass (the loop is left at its end)
     long long triple = blockIdx.x;
     int ts_begin = 0, ts_end = P.Tsim, my_chunk = 0;
     if (QUEUE) {
-        unsigned tk = 0;
-        if (lane == 0) tk = atomicAdd(Wq.ticket, 1u);
-        tk = __shfl_sync(FULL, tk, 0);
-        if ((long long)tk >= ntriples * nchunks) return;
-        my_chunk = (int)(tk / (unsigned)ntriples);
-        triple = tk - (unsigned)my_chunk * (unsigned)ntriples;
+        unsigned h = 0;
+        if (lane == 0) h = atomicAdd(Wq.head, 1u);
+        h = __shfl_sync(FULL, h, 0);
+        if ((long long)h >= ntriples * nchunks) return;
+        // EVERY lane polls (uniform control flow): with `if (lane == 0) spin; __syncwarp();` the warp stayed split for the rest of
+        // the pass and ran it at half speed (measured 17.3 against 8.4 ms at 2,048 problems)
+        const volatile int* slot = Wq.ring + h;
+        int j;
+        while ((j = *slot) < 0) __nanosleep(100);
+        __threadfence();  // acquire: the progress word and the trajectory row read below were written before the push
+        triple = j;
+        my_chunk = *reinterpret_cast<const volatile int*>(Wq.prog + j);
         ts_begin = my_chunk * Wq.chunk;
         ts_end = min(P.Tsim, ts_begin + Wq.chunk);
-        if (my_chunk > 0) {  // the previous chunk of this triple must have landed
-            // EVERY lane polls: with `if (lane == 0) spin; __syncwarp();` the warp stayed split for the rest of the pass and ran
-            // it at half speed (measured 17.3 against 8.4 ms at 2,048 problems)
-            const volatile int* d = Wq.done + triple;
-            while (*d < my_chunk) __nanosleep(100);
-            __threadfence();  // acquire: the trajectory row read below was written before the flag
-        }
     }
     const long long b_raw = triple * 3 + g;
     const bool active = b_raw < P.Bsz;
@@ -330,9 +335,16 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
         xS[(long long)ts_end * 3 + 2] = make_float4(x[8], x[9], x[10], x[11]);
     }
     if (!QUEUE) return;
-    __threadfence();  // the rows above are visible before the chunk is published
+    __threadfence();  // the rows above are visible before the triple is handed on
     __syncwarp();
-    *reinterpret_cast<volatile int*>(Wq.done + triple) = my_chunk + 1;  // (every lane stores the same word: no divergent tail)
+    *reinterpret_cast<volatile int*>(Wq.prog + triple) = my_chunk + 1;  // (every lane stores the same word: no divergent tail)
+    if (my_chunk + 1 < nchunks) {  // back into the queue for its next chunk
+        unsigned tpos = 0;
+        if (lane == 0) tpos = atomicAdd(Wq.tail, 1u);
+        tpos = __shfl_sync(FULL, tpos, 0);
+        __threadfence();
+        *reinterpret_cast<volatile int*>(Wq.ring + tpos) = (int)triple;
+    }
   }
 }
 
@@ -346,26 +358,30 @@ int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream)
     const long long sched = 4LL * sms;  // warp schedulers of the device
     // Work rotation (W9Queue) pays when the batch is just past a whole number m of warps per scheduler: the static mapping then runs
     // at the pace of m + 1 warps per scheduler although almost every scheduler holds m.  Measured on one B200 (200 x 50 steps):
-    // 1,779 problems 10.06 -> 7.7 ms, 2,048 (cfg 3 on 8 GPUs) 10.0 -> 8.3-9.2 ms, 4,096 (m = 2) 16.7 -> 13.1-13.8 ms; from ~1.3 m the
-    // waits for predecessor chunks eat the gain (2,400: 10.3 -> 10.2-12.0 ms) and the static mapping is kept.
-    // ZB_W9_WORKERS_PER_SCHED overrides m (0: static mapping), ZB_W9_CHUNK the chunk length.
+    // 1,779 problems 10.1 -> 7.4 ms, 2,048 (cfg 3 on 8 GPUs) 10.1 -> 8.4 ms, 2,400 10.5 -> 9.7 ms, 4,096 (m = 2) 16.7 -> 12.9 ms;
+    // at 3,000 (1.7 warps per scheduler) the static mapping wins (10.8 against 12.0 ms).  The run takes triples / workers x the time
+    // of m warps per scheduler, + ~6 %.  ZB_W9_WORKERS_PER_SCHED overrides m (0: static mapping), ZB_W9_CHUNK the chunk length.
     int per = 0;
     for (int m = 1; m <= 4; ++m)
-        if (triples > m * sched && 4 * triples <= 5 * m * sched) per = m;
+        if (triples > m * sched && 20 * triples <= 27 * m * sched) per = m;
     if (const char* e = getenv("ZB_W9_WORKERS_PER_SCHED")) per = atoi(e);
     if (per <= 0 || triples <= per * sched || P.Tsim < 2) {
-        w9::k_mpc_closed_loop_quad_w9<false><<<(unsigned)triples, 32, 0, stream>>>(P, w9::W9Queue{nullptr, nullptr, 0});
+        w9::k_mpc_closed_loop_quad_w9<false><<<(unsigned)triples, 32, 0, stream>>>(P, w9::W9Queue{nullptr, nullptr, nullptr, nullptr, 0});
         ZB_CUDA(cudaGetLastError());
         return 0;
     }
-    int chunk = 4;
+    int chunk = 5;
     if (const char* e = getenv("ZB_W9_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
-    // scratch: the ticket counter and one progress word per triple, stream-ordered so that concurrent calls do not share them
+    // scratch: head / tail counters, one progress word per triple, the ring; stream-ordered so that concurrent calls do not share it
+    const long long nchunks = (P.Tsim + chunk - 1) / chunk;
     int* scratch = nullptr;
-    const size_t bytes = sizeof(int) * (size_t)(triples + 32);
-    ZB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, stream));
-    ZB_CUDA(cudaMemsetAsync(scratch, 0, bytes, stream));
-    const w9::W9Queue Wq{reinterpret_cast<unsigned*>(scratch), scratch + 32, chunk};
+    const size_t n_ints = (size_t)64 + (size_t)triples + (size_t)(triples * nchunks);
+    ZB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), n_ints * sizeof(int), stream));
+    ZB_CUDA(cudaMemsetAsync(scratch, 0, (64 + (size_t)triples) * sizeof(int), stream));
+    ZB_CUDA(cudaMemsetAsync(scratch + 64 + triples, 0xFF, (size_t)(triples * nchunks) * sizeof(int), stream));  // ring: all -1
+    const unsigned tail0 = (unsigned)triples;
+    ZB_CUDA(cudaMemcpyAsync(scratch + 32, &tail0, sizeof(unsigned), cudaMemcpyHostToDevice, stream));  // (pageable 4-byte source: copied at the call)
+    const w9::W9Queue Wq{reinterpret_cast<unsigned*>(scratch), reinterpret_cast<unsigned*>(scratch + 32), scratch + 64 + triples, scratch + 64, chunk};
     // `per` one-warp CTAs per scheduler; the block scheduler spreads them evenly over the SMs (measured: 592 CTAs run at the pace of
     // one warp per scheduler)
     w9::k_mpc_closed_loop_quad_w9<true><<<(unsigned)(per * sched), 32, 0, stream>>>(P, Wq);
