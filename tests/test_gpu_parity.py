@@ -1024,3 +1024,30 @@ def test_closed_loop_mpc_nine_lane_work_rotation_equals_static_mapping(per, chun
     xs1, us1 = quadcopterClosedLoopMpc(x, Q, R, 12, Tsim, Qf=10 * Q, variant="warp")[:2]
     assert torch.equal(xs0, xs1) and torch.equal(us0, us1)
     assert torch.isfinite(xs1).all() and float((xs1[:, -1] - xs1[:, 0]).abs().max()) > 0
+
+
+@pytest.mark.parametrize("chunk", [4, 5, 13])
+def test_time_varying_lqr_work_rotation_equals_static_mapping(chunk, monkeypatch):
+    """k_riccati_t1_tv<QUEUE> (csrc/lqr_t1.cuh, round 2): a fixed set of one-warp workers pops ready groups of 32 problems from a
+    FIFO, advances each by a chunk of the horizon and pushes it back, the value matrix travelling through a scratch array.
+    The step is untouched, so gains and the final value matrix equal the static mapping's BIT FOR BIT (ragged batch, chunk
+    lengths that do and do not divide the horizon), and the oracle's to the fp32 tolerance."""
+    from zopt_b200.lqrUtils import discreteFiniteHorizonLqr
+    rng = np.random.default_rng(37)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    Bsz, N = 32 * 4 * sms + 32 * 7 + 5, 13  # one full round of the workers + 7 groups + a ragged one
+    A = torch.as_tensor(np.eye(12) + 0.1 * rng.normal(size=(Bsz, N, 12, 12)), dtype=torch.float32, device="cuda")
+    B = torch.as_tensor(0.3 * rng.normal(size=(Bsz, N, 12, 4)), dtype=torch.float32, device="cuda")
+    Mq = torch.as_tensor(0.3 * rng.normal(size=(Bsz, N + 1, 12, 12)), dtype=torch.float32, device="cuda")
+    Mr = torch.as_tensor(0.3 * rng.normal(size=(Bsz, N, 4, 4)), dtype=torch.float32, device="cuda")
+    Q = torch.eye(12, device="cuda") + Mq @ Mq.transpose(-1, -2)
+    R = torch.eye(4, device="cuda") + Mr @ Mr.transpose(-1, -2)
+    monkeypatch.setenv("ZB_T1_ROTATE", "0")
+    L0 = discreteFiniteHorizonLqr(A, B, Q, R, N)
+    monkeypatch.setenv("ZB_T1_ROTATE", "1")
+    monkeypatch.setenv("ZB_T1_CHUNK", str(chunk))
+    L1 = discreteFiniteHorizonLqr(A, B, Q, R, N)
+    assert torch.equal(L0, L1)
+    for b in (0, Bsz // 2, Bsz - 1):
+        Lo = olqr.discreteFiniteHorizonLqr(A[b].double().cpu().numpy(), B[b].double().cpu().numpy(), Q[b].double().cpu().numpy(), R[b].double().cpu().numpy(), N)
+        assert relerr(L1[b], Lo) < 1e-4

@@ -19,6 +19,7 @@
 // slots -- the main loop needs no barrier.  One warp per CTA, 4 CTAs per SM (111 float4 = 1,776 B per problem).
 #pragma once
 #include <stdlib.h>
+#include <algorithm>
 #include "t1_common.cuh"
 
 namespace zb {
@@ -479,19 +480,103 @@ __device__ __forceinline__ void tv_prefetch_step(const FastP& P, long long b, in
     prefetch_l2(gR); prefetch_l2(gR + 48);
 }
 
-__global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P) {
+// Work rotation for the thread-per-problem kernels (round 2).  One warp owns 32 problems for the whole horizon and a B200 has
+// 592 warp schedulers: 65,536 problems are 2,048 warps = 3.46 rounds, run as FOUR (the last one 46 % full: 13 % of the launch).
+// With QUEUE the grid is a fixed set of one-warp workers (one per scheduler) and the horizon is cut into chunks of CH steps;
+// ready problem groups wait in a FIFO: a worker pops a group, advances it by one chunk and pushes it back (the last chunk also
+// does the group's epilogue).  A group is in the queue only while nobody works on it, so no pass waits for another, and FIFO
+// order makes all groups advance at the same pace: the launch takes groups / workers x (time of one warp alone).  Between
+// chunks the value matrix (78 words per problem) goes through a scratch array, [group][word][lane] so that every access is a
+// coalesced 128-byte row.  The step itself is untouched: results are bit-identical to the static mapping.
+struct T1Queue {
+    unsigned* head;  // pops so far
+    unsigned* tail;  // pushes so far (starts at the number of groups)
+    int* ring;       // (groups * chunks) entries, -1 = not pushed yet
+    int* prog;       // (groups) chunks completed
+    float* vst;      // (groups, 78, 32) value matrices between chunks
+    int chunk;       // steps per chunk
+};
+
+// pop the next ready group (every lane polls: a lane-0 spin followed by __syncwarp() leaves the warp split and the pass runs at
+// half speed, see mpc_warp.cuh); returns false when all passes have been handed out
+__device__ __forceinline__ bool t1q_pop(const T1Queue& Wq, long long total, int lane, long long& group, int& my_chunk) {
+    unsigned h = 0;
+    if (lane == 0) h = atomicAdd(Wq.head, 1u);
+    h = __shfl_sync(0xffffffffu, h, 0);
+    if ((long long)h >= total) return false;
+    const volatile int* slot = Wq.ring + h;
+    int j;
+    while ((j = *slot) < 0) __nanosleep(100);
+    __threadfence();  // acquire: progress word and value matrix were written before the push
+    group = j;
+    my_chunk = *reinterpret_cast<const volatile int*>(Wq.prog + j);
+    return true;
+}
+__device__ __forceinline__ void t1q_push(const T1Queue& Wq, long long group, int chunks_done, int nchunks, int lane) {
+    __threadfence();  // this pass's stores are visible before the group is handed on
+    __syncwarp();
+    *reinterpret_cast<volatile int*>(Wq.prog + group) = chunks_done;  // (every lane stores the same word)
+    if (chunks_done < nchunks) {
+        unsigned tpos = 0;
+        if (lane == 0) tpos = atomicAdd(Wq.tail, 1u);
+        tpos = __shfl_sync(0xffffffffu, tpos, 0);
+        __threadfence();
+        *reinterpret_cast<volatile int*>(Wq.ring + tpos) = (int)group;
+    }
+}
+__device__ __forceinline__ void t1q_seed(const T1Queue& Wq, long long ngroups) {
+    for (long long j = blockIdx.x; j < ngroups; j += gridDim.x) *reinterpret_cast<volatile int*>(Wq.ring + j) = (int)j;
+}
+
+// scratch of a rotating launch, stream-ordered (concurrent calls do not share it): counters, progress words, the ring, the value
+// matrices.  *scratch is released by the caller with cudaFreeAsync after the launch.
+inline cudaError_t t1q_alloc(T1Queue& Wq, long long groups, int N, int chunk, void** scratch, cudaStream_t stream) {
+    const long long nchunks = (N + chunk - 1) / chunk;
+    const size_t n_ints = (size_t)64 + (size_t)groups + (size_t)(groups * nchunks);
+    const size_t v_off = (n_ints * sizeof(int) + 255) & ~(size_t)255;
+    const size_t bytes = v_off + (size_t)groups * 78 * 32 * sizeof(float);
+    cudaError_t e = cudaMallocAsync(scratch, bytes, stream);
+    if (e != cudaSuccess) return e;
+    int* p = reinterpret_cast<int*>(*scratch);
+    if ((e = cudaMemsetAsync(p, 0, (64 + (size_t)groups) * sizeof(int), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(p + 64 + groups, 0xFF, (size_t)(groups * nchunks) * sizeof(int), stream)) != cudaSuccess) return e;  // ring: all -1
+    const unsigned tail0 = (unsigned)groups;
+    if ((e = cudaMemcpyAsync(p + 32, &tail0, sizeof(unsigned), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;  // (pageable source: copied at the call)
+    Wq = T1Queue{reinterpret_cast<unsigned*>(p), reinterpret_cast<unsigned*>(p + 32), p + 64 + groups, p + 64,
+                 reinterpret_cast<float*>(reinterpret_cast<char*>(*scratch) + v_off), chunk};
+    return cudaSuccess;
+}
+
+template <bool QUEUE>
+__global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P, T1Queue Wq) {
     extern __shared__ float4 sm[];
     const int lane = threadIdx.x;
-    const long long b0 = (long long)blockIdx.x * 32;
+    const long long ngroups = (P.Bsz + 31) / 32;
+    const int nchunks = QUEUE ? (P.N + Wq.chunk - 1) / Wq.chunk : 1;
+    float4* S = sm + lane;
+    if (QUEUE) t1q_seed(Wq, ngroups);
+  for (;;) {  // QUEUE: one pass per popped group; otherwise a single pass
+    long long group = blockIdx.x;
+    int my_chunk = 0;
+    if (QUEUE && !t1q_pop(Wq, ngroups * nchunks, lane, group, my_chunk)) return;
+    const int k_hi = QUEUE ? P.N - 1 - my_chunk * Wq.chunk : P.N - 1;
+    const int k_lo = QUEUE ? max(0, k_hi - Wq.chunk + 1) : 0;
+    const long long b0 = group * 32;
     const long long b_raw = b0 + lane;
     const bool active = b_raw < P.Bsz;
     const long long b = active ? b_raw : P.Bsz - 1;
-    float4* S = sm + lane;
     float v[78];
-    load_sym_lower(P.Q.at<float>(b, P.T - 1), v);  // lqrUtils.py:172: terminal value is Q[-1]
+    if (QUEUE && my_chunk > 0) {
+        const float* vs = Wq.vst + group * (78 * 32) + lane;
+#pragma unroll
+        for (int e = 0; e < 78; ++e) v[e] = __ldcg(vs + e * 32);
+    } else {
+        load_sym_lower(P.Q.at<float>(b, P.T - 1), v);  // lqrUtils.py:172: terminal value is Q[-1]
+    }
     float* gpub = P.gains + b0 * (long long)P.N * 48;
-    tv_load_step(S, P, b, P.N - 1);
-    for (int k = P.N - 1; k >= 0; --k) {
+    __syncwarp();  // (QUEUE: the previous pass's staging reads are over before the slab is refilled)
+    tv_load_step(S, P, b, k_hi);
+    for (int k = k_hi; k >= k_lo; --k) {
 #if ZB_TV_L2_PREFETCH
         if (k > 0) tv_prefetch_step(P, b, k - 1);  // HBM -> L2 while this step computes
 #endif
@@ -502,7 +587,7 @@ __global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P) {
         {
             const int kn = k > 0 ? k - 1 : 0;
             const TvHook hook{S, reinterpret_cast<const float4*>(P.A.at<float>(b, kn)), reinterpret_cast<const float4*>(P.B.at<float>(b, kn)),
-                              reinterpret_cast<const float4*>(P.Q.at<float>(b, kn)), reinterpret_cast<const float4*>(P.R.at<float>(b, kn)), k > 0};
+                              reinterpret_cast<const float4*>(P.Q.at<float>(b, kn)), reinterpret_cast<const float4*>(P.R.at<float>(b, kn)), k > k_lo};
             riccati_step<false, RS_TV, true, false, TvHook>(S, v, L, hook);
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
@@ -510,7 +595,7 @@ __global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P) {
         riccati_step<false, RS_TV, true>(S, v, L);
         // the operand slots are private to the lane and free from here on: the copies of step k-1 (L2 hits) overlap the
         // gain transposition and stores below
-        if (k > 0) tv_load_step(S, P, b, k - 1);
+        if (k > k_lo) tv_load_step(S, P, b, k - 1);
 #endif
         float4* stg = sm + W4 * RS_TV;  // W region is free now: transpose the gains for coalesced stores
         __syncwarp();
@@ -527,13 +612,21 @@ __global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P) {
             if (b0 + pr < P.Bsz) *reinterpret_cast<float4*>(gpub + ((long long)pr * P.N + k) * 48 + j4 * 4) = val;
         }
     }
-    if (P.V0 && active) {
+    if (k_lo == 0 && P.V0 && active) {
         float* o = P.V0 + b * 144;
 #pragma unroll
         for (int i = 0; i < 12; ++i)
 #pragma unroll
             for (int j = 0; j < 12; ++j) o[i * 12 + j] = v[tri(i, j)];
     }
+    if (!QUEUE) return;
+    if (k_lo > 0) {
+        float* vs = Wq.vst + group * (78 * 32) + lane;
+#pragma unroll
+        for (int e = 0; e < 78; ++e) __stcg(vs + e * 32, v[e]);
+    }
+    t1q_push(Wq, group, my_chunk + 1, nchunks, lane);
+  }
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -955,10 +1048,35 @@ inline int32_t riccati_t1_tv_launch(const FastP& F, cudaStream_t stream, bool bu
         return 0;
     }
     const size_t smem = (size_t)t1::NF4_TV * t1::RS_TV * sizeof(float4);
-    ZB_CUDA(cudaFuncSetAttribute(t1::k_riccati_t1_tv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((F.Bsz + 31) / 32);
-    t1::k_riccati_t1_tv<<<grid, 32, smem, stream>>>(F);
+    const long long groups = (F.Bsz + 31) / 32;
+    int dev = 0, sms = 148;
+    ZB_CUDA(cudaGetDevice(&dev));
+    ZB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long workers = 4LL * sms;  // one warp per scheduler = four of these 56 KB CTAs per SM
+    // Work rotation (T1Queue) is OPT-IN here (ZB_T1_ROTATE=1): measured on this kernel it is bit-identical but not reliably faster.
+    // 65,536 problems (3.46 rounds): 1.456 -> 1.44-1.47 ms -- the kernel is bound by the copy path, the 272 warps of its last round
+    // already run faster than a full round's, so there is no idle tail to recover.  20,000 problems (1.06 rounds): 0.72 -> 0.54 ms in
+    // one run, 0.71 ms in the next, 1.4 ms with two chunks per horizon: every pass starts with an exposed operand load.
+    // (The same rotation on the time-invariant headline kernel k_riccati_t1, with the value matrix AND a re-staging of A, B, Q, R
+    // per pass, was built and dropped: 0.827 -> 0.89 ms at two chunks per horizon, worse with more.  With five CTAs per SM the
+    // static mapping already runs 3.46 rounds in 0.885 of the time of four, so at most 2 % was there to gain.)
+    bool rotate = false;
+    if (const char* e = getenv("ZB_T1_ROTATE")) rotate = atoi(e) != 0 && groups > 1 && F.N >= 2;
+    if (!rotate) {
+        ZB_CUDA(cudaFuncSetAttribute(t1::k_riccati_t1_tv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        t1::k_riccati_t1_tv<false><<<(unsigned)groups, 32, smem, stream>>>(F, t1::T1Queue{nullptr, nullptr, nullptr, nullptr, nullptr, 0});
+        ZB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int chunk = (F.N + 3) / 4;  // four chunks per horizon
+    if (const char* e = getenv("ZB_T1_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
+    t1::T1Queue Wq;
+    void* scratch = nullptr;
+    ZB_CUDA(t1::t1q_alloc(Wq, groups, F.N, chunk, &scratch, stream));
+    ZB_CUDA(cudaFuncSetAttribute(t1::k_riccati_t1_tv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    t1::k_riccati_t1_tv<true><<<(unsigned)std::min<long long>(workers, groups), 32, smem, stream>>>(F, Wq);
     ZB_CUDA(cudaGetLastError());
+    ZB_CUDA(cudaFreeAsync(scratch, stream));
     return 0;
 }
 
