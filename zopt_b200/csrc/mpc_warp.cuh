@@ -362,7 +362,7 @@ int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream)
     // at 3,000 (1.7 warps per scheduler) the static mapping wins (10.8 against 12.0 ms).  The run takes triples / workers x the time
     // of m warps per scheduler, + ~6 %.  ZB_W9_WORKERS_PER_SCHED overrides m (0: static mapping), ZB_W9_CHUNK the chunk length.
     int per = 0;
-    for (int m = 1; m <= 4; ++m)
+    for (int m = 1; m <= 2; ++m)  // (m = 3, 4 not measured: left to the static mapping)
         if (triples > m * sched && 20 * triples <= 27 * m * sched) per = m;
     if (const char* e = getenv("ZB_W9_WORKERS_PER_SCHED")) per = atoi(e);
     if (per <= 0 || triples <= per * sched || P.Tsim < 2) {
