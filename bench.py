@@ -448,6 +448,15 @@ def run_ours(args):
             del x3w, Q3w, R3w, Qf3w
         else:
             X["clw"] = X["cl"]
+        # what ONE GPU does when cfg 3 is sharded over eight (2,048 problems): nine-lane kernel with work rotation (csrc/mpc_warp.cuh)
+        if world == 1:
+            xs_, Qs_, Rs_ = x3[:2048].contiguous(), Q3[:2048].contiguous(), R3[:2048].contiguous()
+            Qfs_ = 10 * Qs_
+            quadcopterClosedLoopMpc(xs_, Qs_, Rs_, 50, 200, dt=0.1, Qf=Qfs_)
+            X["cl_shard"] = timed(lambda: quadcopterClosedLoopMpc(xs_, Qs_, Rs_, 50, 200, dt=0.1, Qf=Qfs_), 3)
+            del xs_, Qs_, Rs_, Qfs_
+        else:
+            X["cl_shard"] = X["cl"]
         # cfg 3 in fp64, the reference's own precision: fused cooperative kernel (csrc/lqr_quad64.cuh)
         x3d, Q3d, R3d = x3.double(), Q3.double(), R3.double()
         quadcopterClosedLoopMpc(x3d, Q3d, R3d, 50, 200, dt=0.1, Qf=10 * Q3d)
@@ -595,6 +604,10 @@ def run_ours(args):
                                          "scaling": "strong", "roofline": dict(bound="fp32_fma", **fl(16384 * 200, FLOP_PER_SOLVE, cl, p32))},
                 "cfg3_closed_loop_mpc_weak": {"value": 16384 * world * 200 / (clw * 1e-3), "unit": "MPC solves/s", "ms": clw,
                                               "workload": "as cfg3 but 16,384 problems PER GPU", "scaling": "weak"},
+                "cfg3_one_shard_of_eight": {"value": 2048 * 200 / (X["cl_shard"] * 1e-3), "unit": "MPC solves/s", "ms": X["cl_shard"],
+                                            "workload": "the 2,048 problems ONE GPU gets when cfg3 is sharded over eight (measured at N=1 only; at N>1 it is "
+                                                        "cfg3_closed_loop_mpc itself): nine lanes per problem, work rotation over one-warp workers",
+                                            "strong_scaling_1_to_8_implied": cl / X["cl_shard"] if world == 1 else None, "scaling": "strong"},
                 "cfg3_closed_loop_mpc_fp64": {"value": 16384 * 200 / (cl64 * 1e-3), "unit": "MPC solves/s", "ms": cl64,
                                               "workload": "cfg3 (16,384 problems total, sharded over ranks) in fp64, the reference's own precision: "
                                                           "one fused cooperative kernel", "scaling": "strong",
@@ -642,8 +655,9 @@ def run_ours(args):
                                                                 "admm_iterations_per_solve_rank0": info["boxcl5_iters"], "optimal_fraction_rank0": info["boxcl5_opt"],
                                                                 "workload": "as above with check_termination=5 (OSQP default is 25)", "scaling": "strong"}}
             # compact digest as the LAST key of the line: the driver's record keeps the tail of stdout
+            shard_note = f" (one shard of eight: {X['cl_shard']:.2f} ms)" if world == 1 else ""
             tail = (f"N={world} e2e {e2e_val / 1e6:.1f}M/s ({e2e_gbs:.0f} of {roof_gbs:.0f} GB/s copy roof) | cfg3 strong 16384x200: {cl:.2f} ms "
-                    f"{16384 * 200 / cl / 1e3:.1f}M MPC/s; weak {clw:.2f} ms; fp64 {cl64:.1f} ms | cfg4 iLQR f64 {il:.1f} ms {16384 * 10 / il / 1e3:.2f}M it/s; "
+                    f"{16384 * 200 / cl / 1e3:.1f}M MPC/s{shard_note}; weak {clw:.2f} ms; fp64 {cl64:.1f} ms | cfg4 iLQR f64 {il:.1f} ms {16384 * 10 / il / 1e3:.2f}M it/s; "
                     f"defaults {ild:.1f} ms @{info['il_default_iters_mean']:.1f} it | cfg5 DDP {ddp:.1f} ms | tv {tv:.2f} ms | f64 {f64t:.2f} ms")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
