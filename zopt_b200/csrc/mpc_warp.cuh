@@ -186,6 +186,19 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
 #pragma unroll
                 for (int cc = 0; cc <= a; ++cc) G[t1::tri(a, cc)] = __ldg(gF + (2 + a) * 12 + 2 + cc) + Rl[t1::tri(a, cc)];
         }
+        // Cholesky Gt = C C^T: its dependent chain (four MUFU.RSQ + ~10 FMAs) is formed as soon as Gt is known -- at the END of a
+        // step, while the loads of the lane's new V rows are in flight -- instead of between the W product and the exchange
+        float d0, d1, d2, d3, c10, c20, c30, c21, c31, c32;
+        auto chol = [&]() {
+            d0 = rsq(G[0]);
+            c10 = G[1] * d0; c20 = G[3] * d0; c30 = G[6] * d0;
+            d1 = rsq(fmaf(-c10, c10, G[2]));
+            c21 = fmaf(-c20, c10, G[4]) * d1; c31 = fmaf(-c30, c10, G[7]) * d1;
+            d2 = rsq(fmaf(-c21, c21, fmaf(-c20, c20, G[5])));
+            c32 = fmaf(-c31, c21, fmaf(-c30, c20, G[8])) * d2;
+            d3 = rsq(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
+        };
+        chol();
 #pragma unroll 1
         for (int k = P.N - 1; k >= 0; --k) {
             // ---- 1. W tile = Vr Ac: two independent accumulator sets (even / odd k) = 16 FFMA2 chains in flight ----
@@ -207,14 +220,7 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 sts4(Wdst + i * 12, W0[i][0] + W1[i][0], W0[i][1] + W1[i][1], W0[i][2] + W1[i][2], W0[i][3] + W1[i][3]);
-            // ---- 2. Cholesky Gt = C C^T (overlaps the exchange) ----
-            const float d0 = rsq(G[0]);
-            const float c10 = G[1] * d0, c20 = G[3] * d0, c30 = G[6] * d0;
-            const float d1 = rsq(fmaf(-c10, c10, G[2]));
-            const float c21 = fmaf(-c20, c10, G[4]) * d1, c31 = fmaf(-c30, c10, G[7]) * d1;
-            const float d2 = rsq(fmaf(-c21, c21, fmaf(-c20, c20, G[5])));
-            const float c32 = fmaf(-c31, c21, fmaf(-c30, c20, G[8])) * d2;
-            const float d3 = rsq(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
+            // ---- 2. (the Cholesky factor of Gt was formed at the end of the previous step, see 5.) ----
             __syncwarp();
             // ---- 3. V' tile = Q + Ar^T Wc - Mr^T Lc, again as two accumulator sets ----
             // (lanes of one problem read 3 distinct 16 B segments at 0/16/32 B; neighbouring problems are 12 banks apart)
@@ -306,6 +312,7 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
                 G[0] = g2.x + Rl[0]; G[1] = g3.x + Rl[1]; G[2] = g3.y + Rl[2]; G[3] = g4a.x + Rl[3]; G[4] = g4a.y + Rl[4];
                 G[5] = g4b.x + Rl[5]; G[6] = g5a.x + Rl[6]; G[7] = g5a.y + Rl[7]; G[8] = g5b.x + Rl[8]; G[9] = g5b.y + Rl[9];
             }
+            chol();
         }
         // ---- u_t = -L_0 x_t: gather the three gain tiles from the problem's lanes (0,0), (0,1), (0,2) ----
         float u[4], ua[4];
@@ -358,7 +365,8 @@ int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream)
     const long long sched = 4LL * sms;  // warp schedulers of the device
     // Work rotation (W9Queue) pays when the batch is just past a whole number m of warps per scheduler: the static mapping then runs
     // at the pace of m + 1 warps per scheduler although almost every scheduler holds m.  Measured on one B200 (200 x 50 steps):
-    // 1,779 problems 10.1 -> 7.4 ms, 2,048 (cfg 3 on 8 GPUs) 10.1 -> 8.4 ms, 2,400 10.5 -> 9.7 ms, 4,096 (m = 2) 16.7 -> 12.9 ms;
+    // 1,779 problems 10.1 -> 7.4 ms, 2,048 (cfg 3 on 8 GPUs) 10.0 -> 8.0 ms (median of 15 runs, 8.0-8.7), 2,400 10.5 -> 9.7 ms,
+    // 4,096 (m = 2) 16.7 -> 12.9 ms;
     // at 3,000 (1.7 warps per scheduler) the static mapping wins (10.8 against 12.0 ms).  The run takes triples / workers x the time
     // of m warps per scheduler, + ~6 %.  ZB_W9_WORKERS_PER_SCHED overrides m (0: static mapping), ZB_W9_CHUNK the chunk length.
     int per = 0;
