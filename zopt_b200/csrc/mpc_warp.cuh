@@ -299,9 +299,9 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
             // ---- 5. this lane's rows of the new V (3 distinct row blocks per problem, 20 banks apart; problems 4 banks apart)
             //      and the block V[2..5, 2..5] of the next step's Gt (six 64-bit broadcast loads) ----
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int ch = 0; ch < 3; ++ch)  // chunk-major: the next step's product consumes columns 0..3 of all four rows first
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
+                for (int i = 0; i < 4; ++i) {
                     const float4 v4 = lds4(Vs + vrow(4 * r + i) + 4 * ch);
                     Vr[i][4 * ch + 0] = v4.x; Vr[i][4 * ch + 1] = v4.y; Vr[i][4 * ch + 2] = v4.z; Vr[i][4 * ch + 3] = v4.w;
                 }
