@@ -31,9 +31,12 @@ SO = os.path.join(_HERE, "_build", f"libzopt_oracle_{_cpu_key()}.so")
 
 
 def build():
-    r = subprocess.run(["make", "-C", os.path.join(_HERE, "c"), f"OUT={SO}"], capture_output=True, text=True)
+    """compile to a private name and publish with an atomic rename: several processes (ranks, xdist workers) may build at once"""
+    tmp = f"{SO}.{os.getpid()}.tmp"
+    r = subprocess.run(["make", "-B", "-C", os.path.join(_HERE, "c"), f"OUT={tmp}"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("building oracle/c failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    os.replace(tmp, SO)
     return SO
 
 
