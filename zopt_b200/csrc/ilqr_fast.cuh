@@ -57,8 +57,8 @@ constexpr int IDD_PS_F32 = 588;  // 588/4 = 147 odd
 // (In fp32 the kernel is register-limited to two 4-warp CTAs either way, and the packed variant measured 5 % slower.)
 constexpr int IDD_XK = ID_G;     // (x_k | u_k), 16 words
 constexpr int IDD_QU = 396;      // Q_u 4
-constexpr int IDD_PC = 400;      // packed lower triangle of the clamped 9x9 block (45 words); its first 16 words carry the
-                                 // rotations of a Jacobi round while the block is not yet rewritten
+constexpr int IDD_PC = 400;      // packed lower triangle of the clamped 9x9 block (45 words); during the eigen-solve rows 5..8 of
+                                 // Z = H V (warm start) -- the rotation exchange (48 words) lives in the dead f_x region, at word 84
 constexpr int IDD_PS_F64 = 446;  // 446/2 = 223 odd
 
 // Structure of the quadcopter's dF/dx as generated in quad_model_gen.cuh::quad_jac_x: '0' structurally zero, '1' state-
