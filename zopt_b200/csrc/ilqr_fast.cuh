@@ -467,7 +467,11 @@ __global__ void __launch_bounds__(256) k_ilqr_backward_quad(IlqrFastP P) {
         // -- two mbarriers, a warp enters step s once every warp has entered step s-1 -- 79 ms: one step of slack already spreads
         // the warps over the 128 KB body; a second barrier between the eigen-solve and the Riccati step: no change.)
         if (DDP && blockDim.x > 32) __syncthreads();
-        if (PACK && warm_ok && k < N - 1) {  // 81 words = 41 16-byte chunks (the scratch row is 84 words), 10-11 per thread
+        // warm start of this step's eigen-solve -- except on every 64th step, which starts cold: the carried eigenvectors are a
+        // product of thousands of rotations and their orthogonality drifts by ~1e-16 per rotation (1e-13 after 100 steps, measured);
+        // the restart bounds that whatever the horizon, for one cold solve (46 rounds instead of 25) in 64 steps
+        const bool warm_k = warm_ok && k < N - 1 && ((N - 1 - k) & 63) != 0;
+        if (PACK && warm_k) {  // 81 words = 41 16-byte chunks (the scratch row is 84 words), 10-11 per thread
 #pragma unroll
             for (int c = 0; c < 11; ++c) {
                 const int ch = t + 4 * c;
@@ -535,7 +539,7 @@ __global__ void __launch_bounds__(256) k_ilqr_backward_quad(IlqrFastP P) {
                 // scratch of the eigen-solve, all of it dead at this point of the step: the rotation exchange (48 words) and the
                 // gathered A' share one region; Z = H V lives where Q_ux and the clamped block will be written later
                 T* csbuf = PACK ? As + 84 : Ms;
-                if (k < N - 1 && warm_ok) {  // eigenvectors of step k+1 are in Wsm (PACK: just copied back from global)
+                if (warm_k) {  // eigenvectors of step k+1 are in Wsm (PACK: just copied back from global)
                     if (PACK) {
                         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
                         __syncwarp(qmask);
