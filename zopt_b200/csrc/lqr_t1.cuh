@@ -490,7 +490,7 @@ __device__ __forceinline__ void tv_prefetch_step(const FastP& P, long long b, in
 // coalesced 128-byte row.  The step itself is untouched: results are bit-identical to the static mapping.
 struct T1Queue {
     unsigned* head;  // pops so far
-    unsigned* tail;  // pushes so far (starts at the number of groups)
+    unsigned* tail;  // pushes so far (entry index = number of groups + this)
     int* ring;       // (groups * chunks) entries, -1 = not pushed yet
     int* prog;       // (groups) chunks completed
     float* vst;      // (groups, 78, 32) value matrices between chunks
@@ -512,13 +512,13 @@ __device__ __forceinline__ bool t1q_pop(const T1Queue& Wq, long long total, int 
     my_chunk = *reinterpret_cast<const volatile int*>(Wq.prog + j);
     return true;
 }
-__device__ __forceinline__ void t1q_push(const T1Queue& Wq, long long group, int chunks_done, int nchunks, int lane) {
+__device__ __forceinline__ void t1q_push(const T1Queue& Wq, long long group, int chunks_done, int nchunks, long long ngroups, int lane) {
     __threadfence();  // this pass's stores are visible before the group is handed on
     __syncwarp();
     *reinterpret_cast<volatile int*>(Wq.prog + group) = chunks_done;  // (every lane stores the same word)
     if (chunks_done < nchunks) {
         unsigned tpos = 0;
-        if (lane == 0) tpos = atomicAdd(Wq.tail, 1u);
+        if (lane == 0) tpos = (unsigned)ngroups + atomicAdd(Wq.tail, 1u);  // the first `ngroups` entries are the seeds
         tpos = __shfl_sync(0xffffffffu, tpos, 0);
         __threadfence();
         *reinterpret_cast<volatile int*>(Wq.ring + tpos) = (int)group;
@@ -540,8 +540,6 @@ inline cudaError_t t1q_alloc(T1Queue& Wq, long long groups, int N, int chunk, vo
     int* p = reinterpret_cast<int*>(*scratch);
     if ((e = cudaMemsetAsync(p, 0, (64 + (size_t)groups) * sizeof(int), stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p + 64 + groups, 0xFF, (size_t)(groups * nchunks) * sizeof(int), stream)) != cudaSuccess) return e;  // ring: all -1
-    const unsigned tail0 = (unsigned)groups;
-    if ((e = cudaMemcpyAsync(p + 32, &tail0, sizeof(unsigned), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;  // (pageable source: copied at the call)
     Wq = T1Queue{reinterpret_cast<unsigned*>(p), reinterpret_cast<unsigned*>(p + 32), p + 64 + groups, p + 64,
                  reinterpret_cast<float*>(reinterpret_cast<char*>(*scratch) + v_off), chunk};
     return cudaSuccess;
@@ -625,7 +623,7 @@ __global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P, T1Queue Wq) {
 #pragma unroll
         for (int e = 0; e < 78; ++e) __stcg(vs + e * 32, v[e]);
     }
-    t1q_push(Wq, group, my_chunk + 1, nchunks, lane);
+    t1q_push(Wq, group, my_chunk + 1, nchunks, ngroups, lane);
   }
 }
 

@@ -50,7 +50,7 @@ __device__ __forceinline__ float rsq(float x) {
 // so it never wraps.
 struct W9Queue {
     unsigned* head;  // pops so far
-    unsigned* tail;  // pushes so far (starts at the number of triples: every triple is ready once)
+    unsigned* tail;  // pushes so far (entry index = number of triples + this: every triple is seeded once)
     int* ring;       // (triples * chunks) entries, -1 = not pushed yet; entry i is the i-th triple that became ready
     int* prog;       // (triples) chunks completed
     int chunk;       // simulation steps per chunk
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
     *reinterpret_cast<volatile int*>(Wq.prog + triple) = my_chunk + 1;  // (every lane stores the same word: no divergent tail)
     if (my_chunk + 1 < nchunks) {  // back into the queue for its next chunk
         unsigned tpos = 0;
-        if (lane == 0) tpos = atomicAdd(Wq.tail, 1u);
+        if (lane == 0) tpos = (unsigned)ntriples + atomicAdd(Wq.tail, 1u);  // the first `ntriples` entries are the seeds
         tpos = __shfl_sync(FULL, tpos, 0);
         __threadfence();
         *reinterpret_cast<volatile int*>(Wq.ring + tpos) = (int)triple;
@@ -387,8 +387,6 @@ int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream)
     ZB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), n_ints * sizeof(int), stream));
     ZB_CUDA(cudaMemsetAsync(scratch, 0, (64 + (size_t)triples) * sizeof(int), stream));
     ZB_CUDA(cudaMemsetAsync(scratch + 64 + triples, 0xFF, (size_t)(triples * nchunks) * sizeof(int), stream));  // ring: all -1
-    const unsigned tail0 = (unsigned)triples;
-    ZB_CUDA(cudaMemcpyAsync(scratch + 32, &tail0, sizeof(unsigned), cudaMemcpyHostToDevice, stream));  // (pageable 4-byte source: copied at the call)
     const w9::W9Queue Wq{reinterpret_cast<unsigned*>(scratch), reinterpret_cast<unsigned*>(scratch + 32), scratch + 64 + triples, scratch + 64, chunk};
     // `per` one-warp CTAs per scheduler; the block scheduler spreads them evenly over the SMs (measured: 592 CTAs run at the pace of
     // one warp per scheduler)
