@@ -524,8 +524,11 @@ __device__ __forceinline__ void t1q_push(const T1Queue& Wq, long long group, int
         *reinterpret_cast<volatile int*>(Wq.ring + tpos) = (int)group;
     }
 }
-__device__ __forceinline__ void t1q_seed(const T1Queue& Wq, long long ngroups) {
-    for (long long j = blockIdx.x; j < ngroups; j += gridDim.x) *reinterpret_cast<volatile int*>(Wq.ring + j) = (int)j;
+// The first `n` ring entries (every group is ready for its first chunk) are written by a kernel of its own BEFORE the workers: a
+// worker-seeded ring deadlocks as soon as the grid exceeds what the device holds at once (see mpc_warp.cuh::k_queue_seed).
+__global__ void k_t1q_seed(int* ring, long long n) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j < n) ring[j] = (int)j;
 }
 
 // scratch of a rotating launch, stream-ordered (concurrent calls do not share it): counters, progress words, the ring, the value
@@ -552,7 +555,6 @@ __global__ void __launch_bounds__(32, 4) k_riccati_t1_tv(FastP P, T1Queue Wq) {
     const long long ngroups = (P.Bsz + 31) / 32;
     const int nchunks = QUEUE ? (P.N + Wq.chunk - 1) / Wq.chunk : 1;
     float4* S = sm + lane;
-    if (QUEUE) t1q_seed(Wq, ngroups);
   for (;;) {  // QUEUE: one pass per popped group; otherwise a single pass
     long long group = blockIdx.x;
     int my_chunk = 0;
@@ -1072,6 +1074,8 @@ inline int32_t riccati_t1_tv_launch(const FastP& F, cudaStream_t stream, bool bu
     void* scratch = nullptr;
     ZB_CUDA(t1::t1q_alloc(Wq, groups, F.N, chunk, &scratch, stream));
     ZB_CUDA(cudaFuncSetAttribute(t1::k_riccati_t1_tv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    t1::k_t1q_seed<<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>(Wq.ring, groups);
+    ZB_CUDA(cudaGetLastError());
     t1::k_riccati_t1_tv<true><<<(unsigned)std::min<long long>(workers, groups), 32, smem, stream>>>(F, Wq);
     ZB_CUDA(cudaGetLastError());
     ZB_CUDA(cudaFreeAsync(scratch, stream));

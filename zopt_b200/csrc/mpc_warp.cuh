@@ -56,6 +56,15 @@ struct W9Queue {
     int chunk;       // simulation steps per chunk
 };
 
+// The first `n` ring entries: every triple is ready for its first chunk.  A kernel of its own, BEFORE the workers: were the workers to
+// seed the ring themselves, a pop could wait for an entry owed by a CTA that is not resident yet -- with more workers than the device
+// holds at once that CTA never starts (measured: a hang with three workers per scheduler).  Seeded up front, the workers form a plain
+// work queue: every entry a pop waits for is owed by a RUNNING worker, whatever the grid size.
+__global__ void k_queue_seed(int* ring, long long n) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j < n) ring[j] = (int)j;
+}
+
 template <bool QUEUE>
 __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP P, W9Queue Wq) {
     __shared__ __align__(16) float sV[3 * SV];
@@ -70,9 +79,6 @@ __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP 
     const int base = 9 * g;                  // first lane of the problem
     const long long ntriples = (P.Bsz + 2) / 3;
     const int nchunks = QUEUE ? (P.Tsim + Wq.chunk - 1) / Wq.chunk : 1;
-    if (QUEUE) {  // seed the queue: every triple is ready for its first chunk (the pops below wait for their entry to appear)
-        for (long long j = blockIdx.x; j < ntriples; j += gridDim.x) *reinterpret_cast<volatile int*>(Wq.ring + j) = (int)j;
-    }
   for (;;) {  // QUEUE: one pass per popped triple; otherwise a single pass (the loop is left at its end)
     long long triple = blockIdx.x;
     int ts_begin = 0, ts_end = P.Tsim, my_chunk = 0;
@@ -369,9 +375,12 @@ int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream)
     // 4,096 (m = 2) 16.7 -> 12.9 ms;
     // at 3,000 (1.7 warps per scheduler) the static mapping wins (10.8 against 12.0 ms).  The run takes triples / workers x the time
     // of m warps per scheduler, + ~6 %.  ZB_W9_WORKERS_PER_SCHED overrides m (0: static mapping), ZB_W9_CHUNK the chunk length.
+    // Beyond two warps per scheduler, 1,184 workers (what the device holds at once: eight 248-register warps per SM) rotating over
+    // all triples still beat the hardware's own CTA dispatch: 6,000 problems 21.4 -> 18.7 ms, 8,192 26.7 -> 24.2 ms.  More workers
+    // than are resident lose (8,192 with three per scheduler: 49 ms).
     int per = 0;
-    for (int m = 1; m <= 2; ++m)  // (m = 3, 4 not measured: left to the static mapping)
-        if (triples > m * sched && 20 * triples <= 27 * m * sched) per = m;
+    if (triples > sched && 20 * triples <= 27 * sched) per = 1;
+    if (triples > 2 * sched) per = 2;
     if (const char* e = getenv("ZB_W9_WORKERS_PER_SCHED")) per = atoi(e);
     if (per <= 0 || triples <= per * sched || P.Tsim < 2) {
         w9::k_mpc_closed_loop_quad_w9<false><<<(unsigned)triples, 32, 0, stream>>>(P, w9::W9Queue{nullptr, nullptr, nullptr, nullptr, 0});
@@ -390,6 +399,8 @@ int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream)
     const w9::W9Queue Wq{reinterpret_cast<unsigned*>(scratch), reinterpret_cast<unsigned*>(scratch + 32), scratch + 64 + triples, scratch + 64, chunk};
     // `per` one-warp CTAs per scheduler; the block scheduler spreads them evenly over the SMs (measured: 592 CTAs run at the pace of
     // one warp per scheduler)
+    w9::k_queue_seed<<<(unsigned)((triples + 255) / 256), 256, 0, stream>>>(Wq.ring, triples);
+    ZB_CUDA(cudaGetLastError());
     w9::k_mpc_closed_loop_quad_w9<true><<<(unsigned)(per * sched), 32, 0, stream>>>(P, Wq);
     ZB_CUDA(cudaGetLastError());
     ZB_CUDA(cudaFreeAsync(scratch, stream));
