@@ -388,6 +388,7 @@ int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream)
         return 0;
     }
     int chunk = 5;
+    if (P.Tsim > 5 * 4096) chunk = (P.Tsim + 4095) / 4096;  // the ring has one entry per (triple, chunk): keep it small for long simulations
     if (const char* e = getenv("ZB_W9_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
     // scratch: head / tail counters, one progress word per triple, the ring; stream-ordered so that concurrent calls do not share it
     const long long nchunks = (P.Tsim + chunk - 1) / chunk;
