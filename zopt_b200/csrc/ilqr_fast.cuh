@@ -118,7 +118,16 @@ __device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, do
     float tf = af * approx_rcp(fabsf(df) + approx_sqrt(fmaf(df, df, af * af)));  // = sgn(tau) / (|tau| + sqrt(1 + tau^2)), tau = d / a2
     tf = __int_as_float(__float_as_int(tf) ^ (__double2hiint(d) & 0x80000000));  // * sgn(d), branch-free
     const double t = (apq != 0.0) ? (double)tf : 0.0;
-    c = rsqrt(fma(t, t, 1.0));
+    // c = 1 / sqrt(1 + t^2), 1 + t^2 in [1, 2]: fp32 MUFU.RSQ seed (23 bits) + two Newton steps in fp64 -- branch-free and on the
+    // chain's critical path ~8 FP64 instructions instead of the library rsqrt()'s range checks (6 % "branch resolving" here)
+    const double xx = fma(t, t, 1.0);
+    float y0f;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0f) : "f"((float)xx));
+    double y = (double)y0f;
+    const double hx = 0.5 * xx;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    c = y;
     s = t * c;
 }
 __device__ __forceinline__ void jacobi_cs(float app, float aqq, float apq, float& c, float& s) {
