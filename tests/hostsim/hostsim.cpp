@@ -282,3 +282,46 @@ EXPORT int hs_mpc_box_closed_loop(int dtype, int64_t Bsz, int N, int Tsim, const
     }
     return 0;
 }
+
+// ---- the (8,4) fp32 thread-per-problem kernel (zopt_b200/csrc/lqr_s84.cuh), run lane by lane on the host -------------------
+// The kernel body is compiled as is: CUDA's qualifiers are defined away, float4 / __ldg / rsqrtf / the packed FMA get host
+// equivalents, the shared-memory slab becomes a static array (each lane touches its own column only, so lanes can run one after
+// the other) and threadIdx / blockIdx are plain globals set by the driver loop below.
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+#define __device__
+#define __forceinline__ inline
+#define __global__
+#define __shared__ static
+#define __launch_bounds__(x)
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+using std::fmaf;
+struct HsDim { unsigned x; };
+static HsDim threadIdx, blockIdx;
+namespace zb {
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+namespace t1 {
+constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+inline void fma2(float& d0, float& d1, float a, float b0, float b1) { d0 = std::fmaf(a, b0, d0); d1 = std::fmaf(a, b1, d1); }
+}  // namespace t1
+}  // namespace zb
+#define ZB_F4(v, e) ((e) == 0 ? (v).x : (e) == 1 ? (v).y : (e) == 2 ? (v).z : (v).w)
+#include "../../zopt_b200/csrc/lqr_s84.cuh"
+
+EXPORT int hs_riccati_s84(int bilinear, int64_t Bsz, int N, int T, const zb_arr* A, const zb_arr* B, const zb_arr* d, const zb_arr* Q,
+                          const zb_arr* R, const zb_arr* H, const zb_arr* q, const zb_arr* r, float* L, float* l, float* V0) {
+    s84::S84P P{};
+    P.Bsz = Bsz; P.N = N; P.T = T;
+    P.A = A_(A); P.B = A_(B); P.Q = A_(Q); P.R = A_(R);
+    if (bilinear) { P.H = A_(H); P.d = A_(d); P.q = A_(q); P.r = A_(r); }
+    P.L = L; P.l = l; P.V0 = V0;
+    for (unsigned blk = 0; blk < (Bsz + 31) / 32; ++blk)
+        for (unsigned lane = 0; lane < 32; ++lane) {
+            blockIdx.x = blk;
+            threadIdx.x = lane;
+            if (bilinear) s84::k_riccati_s84<true>(P);
+            else s84::k_riccati_s84<false>(P);
+        }
+    return 0;
+}

@@ -200,6 +200,90 @@ def test_bilinear_random_vs_oracle():
     assert per_problem_relerr(L, Lr).max() < 1e-10
 
 
+def _s84_ops(rng, Bsz, T):
+    n, m = 8, 4
+    A = rng.normal(size=(Bsz, T, n, n)) * 0.5 / np.sqrt(n)
+    Bm = rng.normal(size=(Bsz, T, n, m))
+    spd = lambda k: (lambda M: M @ M.T / k + np.eye(k))(rng.normal(size=(k, k)))
+    Q = np.stack([[spd(n) for _ in range(T)] for _ in range(Bsz)])
+    R = np.stack([[spd(m) for _ in range(T)] for _ in range(Bsz)])
+    Hm = 0.2 * rng.normal(size=(Bsz, T, m, n))
+    d = 0.1 * rng.normal(size=(Bsz, T, n))
+    return A, Bm, d, Q, R, Hm, rng.normal(size=(Bsz, T, n)), rng.normal(size=(Bsz, T, m)), rng.normal(size=(Bsz, T))
+
+
+def test_lqr_8x4_fp32_kernel_vs_oracle(monkeypatch):
+    """k_riccati_s84 (lqr_s84.cuh), the fp32 kernel of the demos' shape (8,4), for discreteFiniteHorizonLqr and bilinearAffineLqr:
+    time-varying operands with T > N and a ragged last warp, operands constant in time (stride_t = 0: staged once), un-batched
+    operands shared by the batch; fp32 gate 1e-5 against the fp64 oracle.  The as-written compile-time-size kernel
+    (ZB_NO_S84=1) must agree with it, and non-symmetric weights must bypass it (it reads lower triangles only)."""
+    from zopt_b200.lqrUtils import bilinearAffineLqr, discreteFiniteHorizonLqr
+    rng = np.random.default_rng(11)
+    T, N, Bsz = 9, 7, 70
+    ops = _s84_ops(rng, Bsz, T)
+    A, Bm, d, Q, R, Hm, q, r, q0 = ops
+    f32 = lambda a: cuda(a, torch.float32)
+    Lref, Vref = olqr.discreteFiniteHorizonLqr_batched(A, Bm, Q, R, N, return_value=True)
+    L, V0 = discreteFiniteHorizonLqr(f32(A), f32(Bm), f32(Q), f32(R), N, return_value=True)
+    assert L.dtype == torch.float32 and per_problem_relerr(L, Lref).max() < 1e-5 and per_problem_relerr(V0, Vref).max() < 1e-5
+    assert float((V0 - V0.transpose(-1, -2)).abs().max()) == 0.0  # symmetric by construction
+    Lr, lr = olqr.bilinearAffineLqr_batched(*ops, N)
+    Lb, lb = bilinearAffineLqr(*(f32(t) for t in ops), N)
+    assert per_problem_relerr(Lb, Lr).max() < 1e-5 and per_problem_relerr(lb, lr).max() < 1e-5
+    # the as-written kernel on the same inputs (looser: it is the less accurate of the two in fp32)
+    monkeypatch.setenv("ZB_NO_S84", "1")
+    L_ct = discreteFiniteHorizonLqr(f32(A), f32(Bm), f32(Q), f32(R), N)
+    Lb_ct, lb_ct = bilinearAffineLqr(*(f32(t) for t in ops), N)
+    monkeypatch.delenv("ZB_NO_S84")
+    assert not torch.equal(L_ct, L)  # a different kernel really ran
+    assert per_problem_relerr(L_ct, Lref).max() < 1e-4 and per_problem_relerr(Lb_ct, Lr).max() < 1e-4 and per_problem_relerr(lb_ct, lr).max() < 1e-4
+    # operands constant in time, passed as stride-0 expansions; the terminal value is still Q[-1]
+    ti = [np.repeat(a[:, :1], T, axis=1) for a in ops]
+    ex = lambda a: f32(a[:, :1]).expand(*([-1, T] + [-1] * (a.ndim - 2)))
+    Lref_ti = olqr.discreteFiniteHorizonLqr_batched(ti[0], ti[1], ti[3], ti[4], N)
+    assert per_problem_relerr(discreteFiniteHorizonLqr(ex(A), ex(Bm), ex(Q), ex(R), N), Lref_ti).max() < 1e-5
+    Lr_ti, lr_ti = olqr.bilinearAffineLqr_batched(*ti, N)
+    Lb, lb = bilinearAffineLqr(*(ex(a) for a in ops), N)
+    assert per_problem_relerr(Lb, Lr_ti).max() < 1e-5 and per_problem_relerr(lb, lr_ti).max() < 1e-5
+    # shared (un-batched) A, B, Q, R with batched d, H, q, r
+    sh = [np.repeat(a[:1], Bsz, axis=0) if i in (0, 1, 3, 4) else a for i, a in enumerate(ops)]
+    Lr_sh, lr_sh = olqr.bilinearAffineLqr_batched(*sh, N)
+    Lb, lb = bilinearAffineLqr(*(f32(a[0]) if i in (0, 1, 3, 4) else f32(a) for i, a in enumerate(ops)), N)
+    assert per_problem_relerr(Lb, Lr_sh).max() < 1e-5 and per_problem_relerr(lb, lr_sh).max() < 1e-5
+    # non-symmetric weights are used as given (zopt/lqrUtils.py:168-169, :251-259): the as-written kernel takes them
+    Qn, Rn = Q.copy(), R.copy()
+    Qn[..., 0, 5] += 0.3
+    Rn[..., 1, 3] -= 0.2
+    Ln = discreteFiniteHorizonLqr(f32(A), f32(Bm), f32(Qn), f32(Rn), N)
+    assert per_problem_relerr(Ln, olqr.discreteFiniteHorizonLqr_batched(A, Bm, Qn, Rn, N)).max() < 1e-4
+    opsn = [A, Bm, d, Qn, Rn, Hm, q, r, q0]
+    Lrn, lrn = olqr.bilinearAffineLqr_batched(*opsn, N)
+    Lbn, lbn = bilinearAffineLqr(*(f32(t) for t in opsn), N)
+    assert per_problem_relerr(Lbn, Lrn).max() < 1e-4 and per_problem_relerr(lbn, lrn).max() < 1e-4
+    assert per_problem_relerr(Ln, Lref).max() > 1e-3  # and the perturbation mattered
+
+
+def test_lqr_8x4_fp32_kernel_demo_problems():
+    """the two demos at N = 100 in fp32 through k_riccati_s84 (demos/discreteFiniteHorizonLqr.py:29-35, demos/bilinearLqrControl.py:21-43)"""
+    from zopt_b200.lqrUtils import bilinearAffineLqr, discreteFiniteHorizonLqr
+    N = 100
+    A0, B0 = (t.numpy() for t in OQuadcopter().linearize(np.zeros(8), configs.U_TRIM, dt=0.1))
+    Qk, Rk = (np.asarray(a) for a in configs.cfg1_demo_weights(N))
+    f32 = lambda a: cuda(a, torch.float32)
+    K = discreteFiniteHorizonLqr(f32(rep_np(A0, N)), f32(rep_np(B0, N)), f32(Qk), f32(Rk), N)
+    assert K.shape == (N, 4, 8) and relerr(K, olqr.discreteFiniteHorizonLqr(rep_np(A0, N), rep_np(B0, N), Qk, Rk, N)) < 1e-5
+    rng = np.random.default_rng(1)
+    Bsz = 33
+    d, Hm = rng.normal(size=(Bsz, N, 8)) * 0.01, 0.2 * rng.normal(size=(Bsz, N, 4, 8))
+    q = 0.1 * np.array([1., -1, 0, 0, 0, 0, 0, 0])
+    r, q0 = rng.normal(size=(Bsz, N, 4)) * 0.1, rng.normal(size=(Bsz, N))
+    bat = lambda a: np.repeat(rep_np(a, N)[None], Bsz, axis=0)
+    Lr, lr = olqr.bilinearAffineLqr_batched(bat(A0), bat(B0), d, bat(np.eye(8)), bat(np.eye(4)), Hm, bat(q), r, q0, N)
+    L, l = bilinearAffineLqr(f32(rep_np(A0, N)), f32(rep_np(B0, N)), f32(d), f32(rep_np(np.eye(8), N)), f32(rep_np(np.eye(4), N)), f32(Hm),
+                             f32(rep_np(q, N)), f32(r), f32(q0), N)
+    assert per_problem_relerr(L, Lr).max() < 1e-5 and per_problem_relerr(l, lr).max() < 1e-5
+
+
 # =============================================================================================== quadcopter
 @pytest.mark.parametrize("wind", [None, (3.0, 1.0, 0.0)])
 @pytest.mark.parametrize("dt", DT)

@@ -374,3 +374,74 @@ def test_solve_quadcopter_vs_oracle(second_order, R_scale, spread):
         assert relerr(xT[b], tr.xTraj.numpy()) < 1e-10 and relerr(uT[b], tr.uTraj.numpy()) < 1e-10
         assert relerr(L[b], Lr.numpy()) < 1e-10
         assert not conv[b] and iters[b] == iters_n
+
+
+# ------------------------------------------------------------------------------------------------ (8,4) fp32 kernel body
+def _s84_problem(rng, Bsz, T, tv=True):
+    n, m = 8, 4
+    A = rng.normal(size=(Bsz, T, n, n)) * 0.5 / np.sqrt(n)
+    Bm = rng.normal(size=(Bsz, T, n, m))
+    spd = lambda k: (lambda M: M @ M.T / k + np.eye(k))(rng.normal(size=(k, k)))
+    Q = np.stack([[spd(n) for _ in range(T)] for _ in range(Bsz)])
+    R = np.stack([[spd(m) for _ in range(T)] for _ in range(Bsz)])
+    Hm = 0.2 * rng.normal(size=(Bsz, T, m, n))
+    d = 0.1 * rng.normal(size=(Bsz, T, n))
+    q, r, q0 = rng.normal(size=(Bsz, T, n)), rng.normal(size=(Bsz, T, m)), rng.normal(size=(Bsz, T))
+    ops = [A, Bm, d, Q, R, Hm, q, r, q0]
+    if not tv:  # every operand constant in time (stride_t = 0 on the device: staged once)
+        ops = [np.repeat(a[:, :1], T, axis=1) for a in ops]
+    return ops
+
+
+def _run_s84(bilinear, ops, N, time_invariant=False):
+    A, Bm, d, Q, R, Hm, q, r, _ = (np.ascontiguousarray(a, dtype=np.float32) for a in ops)
+    Bsz, T = Q.shape[0], Q.shape[1]
+    cut = (lambda a: np.ascontiguousarray(a[:, :1])) if time_invariant else (lambda a: a)
+    zs = [H.arr(cut(a), k) for a, k in ((A, 2), (Bm, 2), (d, 1), (Q, 2), (R, 2), (Hm, 2), (q, 1), (r, 1))]
+    L, l, V0 = np.zeros((Bsz, N, 4, 8), np.float32), np.zeros((Bsz, N, 4), np.float32), np.zeros((Bsz, 8, 8), np.float32)
+    H.hs.hs_riccati_s84(int(bilinear), C.c_int64(Bsz), N, 1 if time_invariant else T, *[C.byref(z) for z in zs], H.P(L), H.P(l), H.P(V0))
+    return L, l, V0
+
+
+def _pre(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float((np.abs(a - b).reshape(a.shape[0], -1).max(1) / np.abs(b).reshape(b.shape[0], -1).max(1)).max())
+
+
+@pytest.mark.parametrize("tv", [True, False])
+def test_s84_kernel_body_vs_oracle(tv):
+    """lqr_s84.cuh compiled for the host (fp32) against the fp64 oracle: time-varying operands with T > N and a ragged last warp,
+    and fully time-invariant operands staged once; the gate is BASELINE.md section 6's fp32 1e-5 (measured: below 1e-6)."""
+    rng = np.random.default_rng(7)
+    T, N, Bsz = 9, 7, 37
+    ops = _s84_problem(rng, Bsz, T, tv)
+    A, Bm, d, Q, R, Hm, q, r, q0 = ops
+    Lref, Vref = olqr.discreteFiniteHorizonLqr_batched(A, Bm, Q, R, N, return_value=True)
+    L, _, V0 = _run_s84(False, ops, N, time_invariant=not tv)
+    assert _pre(L, Lref) < 1e-5 and _pre(V0, Vref) < 1e-5
+    Lr, lr = olqr.bilinearAffineLqr_batched(A, Bm, d, Q, R, Hm, q, r, q0, N)
+    L, l, _ = _run_s84(True, ops, N, time_invariant=not tv)
+    assert _pre(L, Lr) < 1e-5 and _pre(l, lr) < 1e-5
+
+
+def test_s84_kernel_body_demo_horizon():
+    """the demos' problems at N = 100 (demos/discreteFiniteHorizonLqr.py:29-35 incl. the Q[-1] terminal quirk,
+    demos/bilinearLqrControl.py:21-43 with a seeded H): fp32 within 1e-5 of the fp64 oracle"""
+    N = 100
+    A0, B0 = (t.numpy() for t in Quadcopter().linearize(np.zeros(8), configs.U_TRIM, dt=0.1))
+    Qk, Rk = (np.asarray(a) for a in configs.cfg1_demo_weights(N))
+    rep = lambda a: np.repeat(a[None, None], N, axis=1)
+    Kref = olqr.discreteFiniteHorizonLqr(rep(A0)[0], rep(B0)[0], Qk, Rk, N)
+    z = np.zeros((1, N, 1))
+    L, _, _ = _run_s84(False, [rep(A0), rep(B0), z, Qk[None], Rk[None], z, z, z, z], N)
+    assert _pre(L, np.asarray(Kref)[None]) < 1e-5
+    rng = np.random.default_rng(1)
+    Bsz = 5
+    bat = lambda a: np.repeat(a, Bsz, axis=0)
+    d, Hm = rng.normal(size=(Bsz, N, 8)) * 0.01, 0.2 * rng.normal(size=(Bsz, N, 4, 8))
+    q = 0.1 * bat(rep(np.array([1., -1, 0, 0, 0, 0, 0, 0])))
+    r, q0 = rng.normal(size=(Bsz, N, 4)) * 0.1, rng.normal(size=(Bsz, N))
+    ops = [bat(rep(A0)), bat(rep(B0)), d, bat(rep(np.eye(8))), bat(rep(np.eye(4))), Hm, q, r, q0]
+    Lr, lr = olqr.bilinearAffineLqr_batched(*ops, N)
+    L, l, _ = _run_s84(True, ops, N)
+    assert _pre(L, Lr) < 1e-5 and _pre(l, lr) < 1e-5

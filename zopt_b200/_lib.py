@@ -51,6 +51,7 @@ SIGNATURES = {
     "zb_lqr_dfh_flags": (_i32, [_i32, _i32, _P, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _AP, _AP, _i32, _P, _P]),
     "zb_lqr_care_rk4": (_i32, [_i32, _i32, _P, _i64, _i32, _i32, _i32, _i32, _f64, _AP, _AP, _AP, _AP, _AP, _P]),
     "zb_lqr_bilinear": (_i32, [_i32, _i32, _P, _i64, _i32, _i32, _i32, _i32] + [_AP] * 9 + [_P, _P]),
+    "zb_lqr_bilinear_flags": (_i32, [_i32, _i32, _P, _i64, _i32, _i32, _i32, _i32] + [_AP] * 9 + [_i32, _P, _P]),
     "zb_quad_dynamics": (_i32, [_i32, _i32, _P, _i64, _P, _P, C.POINTER(_f64), _P]),
     "zb_quad_linearize": (_i32, [_i32, _i32, _P, _i64, _P, _P, C.POINTER(_f64), _f64, _P, _P]),
     "zb_quad_hess_contract": (_i32, [_i32, _i32, _P, _i64, _P, _P, C.POINTER(_f64), _f64, _P, _P]),

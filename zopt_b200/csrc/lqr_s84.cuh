@@ -1,0 +1,262 @@
+// Thread-per-problem Riccati kernel for the reference demos' shape (n, m) = (8, 4), fp32 (round 2, VERDICT r1 task 10):
+//   discreteFiniteHorizonLqr  (zopt/lqrUtils.py:144-173, demos/discreteFiniteHorizonLqr.py:29-35) and
+//   bilinearAffineLqr         (zopt/lqrUtils.py:207-262, demos/bilinearLqrControl.py:21-43).
+//
+// The compile-time-size kernels of zb_steps.cuh (k_lqr_ct / k_bilinear_ct) evaluate the recursion as written on full 8x8
+// matrices with scalar global loads: 255 registers + spills, ~176 scalar loads per step, 12 % of the FP32 peak by the dense count.
+// This kernel follows the (12,4) design of lqr_t1.cuh at the smaller size, where everything fits in registers:
+//   * the symmetric value matrix V is its lower triangle (36 registers) for the whole horizon;
+//   * pass 1: [W | VB] = V [A | B], one row of [A | B] (three 128-bit shared loads) feeding 96 FMAs; W (64) and VB (32) stay
+//     in registers, nothing goes back to shared memory;
+//   * G = R + B'(VB) (lower triangle), 4x4 Cholesky by reciprocal square roots;
+//   * pass 3: V' (lower, 36 accumulators) = Q + A'W and M = B'W (+ H) in one pass over the rows of [A | B];
+//   * L = G^-1 M by two triangular solves per column, V' -= M'L (lower): algebraically the reference's Joseph form
+//     (lqrUtils.py:169) resp. V = Q + A'VA - L'S_uu L (lqrUtils.py:259), symmetric by construction;
+//   * bilinear: v + V d rides pass 1, S_u = r + B'(v + V d) rides the G loop, v' = q + A'(v + V d) - S_ux' l rides pass 3.
+// ~1,700 FMA and ~270 loaded words per problem-step (6 FMA per word).  Operands live in shared memory interleaved by lane
+// ([float4 slot][lane]): every 128-bit access of a warp is one contiguous 512 B row (conflict-free), each lane stages and
+// reads ITS OWN problem only, so there is no barrier anywhere; operands with stride_t = 0 are staged once, the others
+// again at every step.  Q, R are read as symmetric (lower triangle): callers with non-symmetric weights pass
+// ZB_FORCE_GENERIC and get the as-written kernels.
+#pragma once
+#if defined(__CUDACC__)
+#include "t1_common.cuh"
+#endif  // else: tests/hostsim provides float4, tri, fma2, ZB_F4, Arr, aligned16 and runs the kernel body lane by lane on the host
+
+namespace zb {
+namespace s84 {
+
+using t1::fma2;
+using t1::tri;
+
+constexpr int RS = 32;    // row stride of the slab in float4 (one warp per CTA)
+constexpr int A4 = 0;     // A rows: 8 x 2 float4
+constexpr int B4 = 16;    // B rows: 8 x 1
+constexpr int Q4 = 24;    // Q rows: 8 x 2 (full rows; the lower-triangle-covering chunks are read)
+constexpr int R4 = 40;    // R rows: 4 x 1
+constexpr int NF4_LQR = 44;
+constexpr int H4 = 44;    // bilinear: H rows 4 x 2
+constexpr int D4 = 52;    // d (2), q (2), r (1)
+constexpr int QV4 = 54;
+constexpr int RV4 = 56;
+constexpr int NF4_BIL = 57;
+
+struct S84P {
+    long long Bsz;
+    int N, T;
+    Arr A, B, Q, R, H, d, q, r;
+    float *L, *l, *V0;  // gains (Bsz,N,4,8); bilinear offsets (Bsz,N,4); value at step 0 (Bsz,8,8) or null
+};
+
+template <int NSLOT>
+__device__ __forceinline__ void stage(float4* S, int slot, const float* g) {
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4 t[NSLOT];
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) t[j] = __ldg(g4 + j);
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) S[(slot + j) * RS] = t[j];
+}
+
+// lower triangle of the symmetric 8x8 staged at Q4 -> v[36]
+__device__ __forceinline__ void read_q_lower(const float4* S, float (&v)[36]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c <= i / 4; ++c) {
+            const float4 q = S[(Q4 + 2 * i + c) * RS];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * c + e <= i) v[tri(i, 4 * c + e)] = ZB_F4(q, e);
+        }
+}
+
+// One backward step for the problem owned by this thread.  v: lower triangle of V (in/out); vv: the linear term (bilinear, in/out).
+template <bool BILIN>
+__device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv)[8], float (&L)[4][8], float (&l)[4]) {
+    float W[8][8], VB[8][4], vVd[8], dd[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) W[i][j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) VB[i][j] = 0.f;
+        vVd[i] = BILIN ? vv[i] : 0.f;
+    }
+    if (BILIN) {
+        const float4 d0 = S[D4 * RS], d1 = S[(D4 + 1) * RS];
+        dd[0] = d0.x; dd[1] = d0.y; dd[2] = d0.z; dd[3] = d0.w; dd[4] = d1.x; dd[5] = d1.y; dd[6] = d1.z; dd[7] = d1.w;
+    }
+    // ---- 1. [W | VB] = V [A | B]  (+ v + V d) -------------------------------------------------------------------
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const float4 a0 = S[(A4 + 2 * kk) * RS], a1 = S[(A4 + 2 * kk + 1) * RS], b4 = S[(B4 + kk) * RS];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float vik = v[tri(i, kk)];
+            fma2(W[i][0], W[i][1], vik, a0.x, a0.y);
+            fma2(W[i][2], W[i][3], vik, a0.z, a0.w);
+            fma2(W[i][4], W[i][5], vik, a1.x, a1.y);
+            fma2(W[i][6], W[i][7], vik, a1.z, a1.w);
+            fma2(VB[i][0], VB[i][1], vik, b4.x, b4.y);
+            fma2(VB[i][2], VB[i][3], vik, b4.z, b4.w);
+            if (BILIN) vVd[i] = fmaf(vik, dd[kk], vVd[i]);
+        }
+    }
+    // ---- 2. G = R + B'(VB) (lower), S_u = r + B'(v + V d); Cholesky G = C C' ------------------------------------
+    float G[10], Su[4];
+    {
+        const float4 r0 = S[(R4 + 0) * RS], r1 = S[(R4 + 1) * RS], r2 = S[(R4 + 2) * RS], r3 = S[(R4 + 3) * RS];
+        G[0] = r0.x; G[1] = r1.x; G[2] = r1.y; G[3] = r2.x; G[4] = r2.y; G[5] = r2.z; G[6] = r3.x; G[7] = r3.y; G[8] = r3.z; G[9] = r3.w;
+        if (BILIN) {
+            const float4 rv = S[RV4 * RS];
+            Su[0] = rv.x; Su[1] = rv.y; Su[2] = rv.z; Su[3] = rv.w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 b4 = S[(B4 + i) * RS];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int c = 0; c <= a; ++c) G[tri(a, c)] = fmaf(ZB_F4(b4, a), VB[i][c], G[tri(a, c)]);
+            if (BILIN) Su[a] = fmaf(ZB_F4(b4, a), vVd[i], Su[a]);
+        }
+    }
+    const float d0 = rsqrtf(G[0]);
+    const float c10 = G[1] * d0, c20 = G[3] * d0, c30 = G[6] * d0;
+    const float d1 = rsqrtf(fmaf(-c10, c10, G[2]));
+    const float c21 = fmaf(-c20, c10, G[4]) * d1, c31 = fmaf(-c30, c10, G[7]) * d1;
+    const float d2 = rsqrtf(fmaf(-c21, c21, fmaf(-c20, c20, G[5])));
+    const float c32 = fmaf(-c31, c21, fmaf(-c30, c20, G[8])) * d2;
+    const float d3 = rsqrtf(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
+    // ---- 3. V' (lower) = Q + A'W, M = (H +) B'W, v' = q + A'(v + V d) in one pass over the rows of [A | B] -------
+    float M[4][8];
+    read_q_lower(S, v);  // V is dead from here on: its registers take the new value
+    if (BILIN) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float4 h0 = S[(H4 + 2 * a) * RS], h1 = S[(H4 + 2 * a + 1) * RS];
+            M[a][0] = h0.x; M[a][1] = h0.y; M[a][2] = h0.z; M[a][3] = h0.w; M[a][4] = h1.x; M[a][5] = h1.y; M[a][6] = h1.z; M[a][7] = h1.w;
+        }
+        const float4 q0 = S[QV4 * RS], q1 = S[(QV4 + 1) * RS];
+        vv[0] = q0.x; vv[1] = q0.y; vv[2] = q0.z; vv[3] = q0.w; vv[4] = q1.x; vv[5] = q1.y; vv[6] = q1.z; vv[7] = q1.w;
+    } else {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) M[a][j] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const float4 a0 = S[(A4 + 2 * kk) * RS], a1 = S[(A4 + 2 * kk + 1) * RS], b4 = S[(B4 + kk) * RS];
+        const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int j = 0; j + 1 <= i; j += 2) fma2(v[tri(i, j)], v[tri(i, j + 1)], ar[i], W[kk][j], W[kk][j + 1]);
+            if ((i & 1) == 0) v[tri(i, i)] = fmaf(ar[i], W[kk][i], v[tri(i, i)]);
+            if (BILIN) vv[i] = fmaf(ar[i], vVd[kk], vv[i]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) fma2(M[a][j], M[a][j + 1], ZB_F4(b4, a), W[kk][j], W[kk][j + 1]);
+    }
+    // ---- 4. L = G^-1 M (and l = G^-1 S_u): C y = rhs, C' x = y ---------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float y0 = M[0][j] * d0;
+        const float y1 = fmaf(-c10, y0, M[1][j]) * d1;
+        const float y2 = fmaf(-c21, y1, fmaf(-c20, y0, M[2][j])) * d2;
+        const float y3 = fmaf(-c32, y2, fmaf(-c31, y1, fmaf(-c30, y0, M[3][j]))) * d3;
+        const float x3 = y3 * d3;
+        const float x2 = fmaf(-c32, x3, y2) * d2;
+        const float x1 = fmaf(-c31, x3, fmaf(-c21, x2, y1)) * d1;
+        const float x0 = fmaf(-c30, x3, fmaf(-c20, x2, fmaf(-c10, x1, y0))) * d0;
+        L[0][j] = x0; L[1][j] = x1; L[2][j] = x2; L[3][j] = x3;
+    }
+    if (BILIN) {
+        const float y0 = Su[0] * d0;
+        const float y1 = fmaf(-c10, y0, Su[1]) * d1;
+        const float y2 = fmaf(-c21, y1, fmaf(-c20, y0, Su[2])) * d2;
+        const float y3 = fmaf(-c32, y2, fmaf(-c31, y1, fmaf(-c30, y0, Su[3]))) * d3;
+        l[3] = y3 * d3;
+        l[2] = fmaf(-c32, l[3], y2) * d2;
+        l[1] = fmaf(-c31, l[3], fmaf(-c21, l[2], y1)) * d1;
+        l[0] = fmaf(-c30, l[3], fmaf(-c20, l[2], fmaf(-c10, l[1], y0))) * d0;
+    }
+    // ---- 5. V' -= M'L (lower), v' -= M'l --------------------------------------------------------------------------
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float nm = -M[a][i];
+#pragma unroll
+            for (int j = 0; j + 1 <= i; j += 2) fma2(v[tri(i, j)], v[tri(i, j + 1)], nm, L[a][j], L[a][j + 1]);
+            if ((i & 1) == 0) v[tri(i, i)] = fmaf(nm, L[a][i], v[tri(i, i)]);
+            if (BILIN) vv[i] = fmaf(nm, l[a], vv[i]);
+        }
+    }
+}
+
+template <bool BILIN>
+__global__ void __launch_bounds__(32) k_riccati_s84(S84P P) {
+    __shared__ float4 slab[(BILIN ? NF4_BIL : NF4_LQR) * RS];
+    const int lane = threadIdx.x;
+    long long b = blockIdx.x * 32LL + lane;
+    const bool live = b < P.Bsz;
+    if (!live) b = P.Bsz - 1;  // tail lanes recompute the last problem and store nothing
+    float4* S = slab + lane;
+    float v[36], vv[8], L[4][8], l[4];
+    // terminal carry (lqrUtils.py:172 / :261): Q[T-1] (and q[T-1])
+    int qk = P.T - 1, qvk = P.T - 1;
+    stage<16>(S, Q4, P.Q.at<float>(b, qk));
+    read_q_lower(S, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vv[i] = 0.f;
+    if (BILIN) {
+        stage<2>(S, QV4, P.q.at<float>(b, qvk));
+        const float4 q0 = S[QV4 * RS], q1 = S[(QV4 + 1) * RS];
+        vv[0] = q0.x; vv[1] = q0.y; vv[2] = q0.z; vv[3] = q0.w; vv[4] = q1.x; vv[5] = q1.y; vv[6] = q1.z; vv[7] = q1.w;
+    }
+    float* Lout = P.L + b * (long long)P.N * 32;
+    float* lout = BILIN ? P.l + b * (long long)P.N * 4 : nullptr;
+#pragma unroll 1
+    for (int k = P.N - 1; k >= 0; --k) {
+        const bool first = (k == P.N - 1);
+        if (first || P.A.st) stage<16>(S, A4, P.A.at<float>(b, k));
+        if (first || P.B.st) stage<8>(S, B4, P.B.at<float>(b, k));
+        if (first || P.R.st) stage<4>(S, R4, P.R.at<float>(b, k));
+        if (P.Q.st && k != qk) { stage<16>(S, Q4, P.Q.at<float>(b, k)); qk = k; }
+        if (BILIN) {
+            if (first || P.H.st) stage<8>(S, H4, P.H.at<float>(b, k));
+            if (first || P.d.st) stage<2>(S, D4, P.d.at<float>(b, k));
+            if (first || P.r.st) stage<1>(S, RV4, P.r.at<float>(b, k));
+            if (P.q.st && k != qvk) { stage<2>(S, QV4, P.q.at<float>(b, k)); qvk = k; }
+        }
+        step<BILIN>(S, v, vv, L, l);
+        if (live) {
+            float4* o = reinterpret_cast<float4*>(Lout + (long long)k * 32);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                o[2 * a] = make_float4(L[a][0], L[a][1], L[a][2], L[a][3]);
+                o[2 * a + 1] = make_float4(L[a][4], L[a][5], L[a][6], L[a][7]);
+            }
+            if (BILIN) *reinterpret_cast<float4*>(lout + (long long)k * 4) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+    }
+    if (!BILIN && P.V0 && live) {
+        float* V0 = P.V0 + b * 64;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            reinterpret_cast<float4*>(V0 + i * 8)[0] = make_float4(v[tri(i, 0)], v[tri(i, 1)], v[tri(i, 2)], v[tri(i, 3)]);
+            reinterpret_cast<float4*>(V0 + i * 8)[1] = make_float4(v[tri(i, 4)], v[tri(i, 5)], v[tri(i, 6)], v[tri(i, 7)]);
+        }
+    }
+}
+
+inline bool s84_arr_ok(const Arr& a) { return aligned16(a.p) && (a.sb % 4 == 0) && (a.st % 4 == 0); }
+
+}  // namespace s84
+}  // namespace zb

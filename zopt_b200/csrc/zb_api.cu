@@ -7,6 +7,7 @@
 #include "ilqr_params.cuh"
 #include "ilqr_generic.cuh"
 #include "lqr_t1.cuh"
+#include "lqr_s84.cuh"
 #include "mpc_coop.cuh"
 #include "mpc_box.cuh"
 #include "mpc_box_quad.cuh"
@@ -282,8 +283,20 @@ int32_t zb_lqr_dfh_flags(int32_t dtype, int32_t device, void* stream, int64_t Bs
     DeviceGuard g(device);
     ZB_CUDA(g.err);
     LqrP P{Bsz, N, T, n, m, to_arr(A), to_arr(B), to_arr(Q), to_arr(R), L_out, V0_out};
-    if (flags & ZB_FORCE_GENERIC) {  // e.g. non-symmetric weights: the (12,4) kernels read the lower triangle only
+    if ((flags & ZB_FORCE_GENERIC) && n == 12) {  // e.g. non-symmetric weights: the (12,4) kernels read the lower triangle only
         ZB_DISPATCH(dtype, k_lqr_generic, gen_grid(Bsz), GEN_THREADS, stream, P);
+        return 0;
+    }
+    // the demos' shape (8,4) in fp32, symmetric weights: register-resident thread-per-problem kernel (lqr_s84.cuh); non-symmetric
+    // weights (ZB_FORCE_GENERIC) fall through to the as-written compile-time-size kernel below
+    if (dtype == ZB_F32 && n == 8 && m == 4 && N >= 1 && !(flags & ZB_FORCE_GENERIC) && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.Q) &&
+        arr_ok(P.R) && aligned16(P.L) && (!P.V0 || aligned16(P.V0)) && !getenv("ZB_FORCE_RUNTIME_SIZES") && !getenv("ZB_NO_S84")) {
+        s84::S84P F{};
+        F.Bsz = Bsz; F.N = N; F.T = T;
+        F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R;
+        F.L = reinterpret_cast<float*>(L_out); F.V0 = reinterpret_cast<float*>(V0_out);
+        s84::k_riccati_s84<false><<<(unsigned)((Bsz + 31) / 32), 32, 0, (cudaStream_t)stream>>>(F);
+        ZB_CUDA(cudaGetLastError());
         return 0;
     }
     // genuinely time-varying (12,4) fp32 problems: streamed thread-per-problem kernel (lqr_t1.cuh)
@@ -335,6 +348,13 @@ int32_t zb_lqr_bilinear(int32_t dtype, int32_t device, void* stream, int64_t Bsz
                         int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* d, const zb_arr* Q,
                         const zb_arr* R, const zb_arr* H, const zb_arr* q, const zb_arr* r, const zb_arr* q0,
                         void* L_out, void* l_out) {
+    return zb_lqr_bilinear_flags(dtype, device, stream, Bsz, N, T, n, m, A, B, d, Q, R, H, q, r, q0, 0, L_out, l_out);
+}
+
+int32_t zb_lqr_bilinear_flags(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
+                              int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* d, const zb_arr* Q,
+                              const zb_arr* R, const zb_arr* H, const zb_arr* q, const zb_arr* r, const zb_arr* q0,
+                              int32_t flags, void* L_out, void* l_out) {
     int32_t rc = check_dims(dtype, Bsz, n, m);
     if (rc) return rc;
     if (Bsz == 0) return 0;  // empty batch: nothing to read or write (pointers may be NULL)
@@ -347,6 +367,17 @@ int32_t zb_lqr_bilinear(int32_t dtype, int32_t device, void* stream, int64_t Bsz
     ZB_CUDA(g.err);
     BilinP P{Bsz, N, T, n, m, to_arr(A), to_arr(B), to_arr(d), to_arr(Q), to_arr(R), to_arr(H), to_arr(q), to_arr(r),
              to_arr(q0), L_out, l_out};
+    if (dtype == ZB_F32 && n == 8 && m == 4 && N >= 1 && !(flags & ZB_FORCE_GENERIC) && arr_ok(P.A) && arr_ok(P.B) && arr_ok(P.d) &&
+        arr_ok(P.Q) && arr_ok(P.R) && arr_ok(P.H) && arr_ok(P.q) && arr_ok(P.r) && aligned16(L_out) && aligned16(l_out) &&
+        !getenv("ZB_FORCE_RUNTIME_SIZES") && !getenv("ZB_NO_S84")) {  // lqr_s84.cuh (symmetric Q, R)
+        s84::S84P F{};
+        F.Bsz = Bsz; F.N = N; F.T = T;
+        F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R; F.H = P.H; F.d = P.d; F.q = P.q; F.r = P.r;
+        F.L = reinterpret_cast<float*>(L_out); F.l = reinterpret_cast<float*>(l_out);
+        s84::k_riccati_s84<true><<<(unsigned)((Bsz + 31) / 32), 32, 0, (cudaStream_t)stream>>>(F);
+        ZB_CUDA(cudaGetLastError());
+        return 0;
+    }
 #define ZB_CT_BIL(N_, M_)                                                                                        \
     if (n == N_ && m == M_ && (dtype == ZB_F32 || ZB_CT_F64_OK(N_)) && !getenv("ZB_FORCE_RUNTIME_SIZES")) {        \
         if (dtype == ZB_F32) k_bilinear_ct<float, N_, M_><<<gen_grid(Bsz), GEN_THREADS, 0, (cudaStream_t)stream>>>(P);   \
