@@ -15,8 +15,8 @@
 //   * bilinear: v + V d rides pass 1, S_u = r + B'(v + V d) rides the G loop, v' = q + A'(v + V d) - S_ux' l rides pass 3.
 // ~1,700 FMA and ~270 loaded words per problem-step (6 FMA per word).  Operands live in shared memory interleaved by lane
 // ([float4 slot][lane]): every 128-bit access of a warp is one contiguous 512 B row (conflict-free), each lane stages and
-// reads ITS OWN problem only, so there is no barrier anywhere; operands with stride_t = 0 are staged once, the others
-// again at every step.  Q, R are read as symmetric (lower triangle): callers with non-symmetric weights pass
+// reads ITS OWN problem only (16-byte cp.async, no registers in between), so there is no barrier anywhere; operands with
+// stride_t = 0 are staged once, the others are requested for step k-1 from inside step k as their slots fall free.  Q, R are read as symmetric (lower triangle): callers with non-symmetric weights pass
 // ZB_FORCE_GENERIC and get the as-written kernels.
 #pragma once
 #if defined(__CUDACC__)
@@ -48,15 +48,57 @@ struct S84P {
     float *L, *l, *V0;  // gains (Bsz,N,4,8); bilinear offsets (Bsz,N,4); value at step 0 (Bsz,8,8) or null
 };
 
+// Each lane copies ITS OWN problem's operand block into its column of the slab with 16-byte cp.async (global -> shared, no
+// registers in between), so every copy of a step is in flight at once and the slab needs no barrier.
 template <int NSLOT>
-__device__ __forceinline__ void stage(float4* S, int slot, const float* g) {
-    const float4* g4 = reinterpret_cast<const float4*>(g);
-    float4 t[NSLOT];
+__device__ __forceinline__ void copy_in(float4* S, int slot, const float* g) {
+#if defined(__CUDACC__)
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(S + slot * RS);
 #pragma unroll
-    for (int j = 0; j < NSLOT; ++j) t[j] = __ldg(g4 + j);
-#pragma unroll
-    for (int j = 0; j < NSLOT; ++j) S[(slot + j) * RS] = t[j];
+    for (int j = 0; j < NSLOT; ++j)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst + j * RS * 16), "l"(g + 4 * j) : "memory");
+#else
+    for (int j = 0; j < NSLOT; ++j) S[(slot + j) * RS] = reinterpret_cast<const float4*>(g)[j];
+#endif
 }
+__device__ __forceinline__ void copies_done() {
+#if defined(__CUDACC__)
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
+// Refill hooks: the step calls them as operand slots fall free, and the operands of step k-1 that vary in time are requested
+// right then, while step k still computes (a step that staged them at its start paid the L2 latency in full: long_scoreboard
+// 25 % of the stalls on the bilinear demo batch).  ROWS = A or B vary in time: only then does pass 3 carry a hook per row
+// (each hook is a compiler barrier for memory operations, which would serialise the row loads of the common case).
+template <bool BILIN, bool ROWS>
+struct Refill {
+    const S84P& P;
+    float4* S;
+    long long b;
+    int kn;  // the step being prefetched (k - 1); < 0: none
+    __device__ __forceinline__ void cost_free() const {  // R, d, r have been read
+        if (kn < 0) return;
+        if (P.R.st) copy_in<4>(S, R4, P.R.at<float>(b, kn));
+        if (BILIN) {
+            if (P.d.st) copy_in<2>(S, D4, P.d.at<float>(b, kn));
+            if (P.r.st) copy_in<1>(S, RV4, P.r.at<float>(b, kn));
+        }
+    }
+    __device__ __forceinline__ void q_free() const {  // Q, H, q have been read
+        if (kn < 0) return;
+        if (P.Q.st) copy_in<16>(S, Q4, P.Q.at<float>(b, kn));
+        if (BILIN) {
+            if (P.H.st) copy_in<8>(S, H4, P.H.at<float>(b, kn));
+            if (P.q.st) copy_in<2>(S, QV4, P.q.at<float>(b, kn));
+        }
+    }
+    __device__ __forceinline__ void row_free(int kk) const {  // row kk of [A | B] has been read for the last time
+        if (!ROWS || kn < 0) return;
+        if (P.A.st) copy_in<2>(S, A4 + 2 * kk, P.A.at<float>(b, kn) + 8 * kk);
+        if (P.B.st) copy_in<1>(S, B4 + kk, P.B.at<float>(b, kn) + 4 * kk);
+    }
+};
 
 // lower triangle of the symmetric 8x8 staged at Q4 -> v[36]
 __device__ __forceinline__ void read_q_lower(const float4* S, float (&v)[36]) {
@@ -72,8 +114,8 @@ __device__ __forceinline__ void read_q_lower(const float4* S, float (&v)[36]) {
 }
 
 // One backward step for the problem owned by this thread.  v: lower triangle of V (in/out); vv: the linear term (bilinear, in/out).
-template <bool BILIN>
-__device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv)[8], float (&L)[4][8], float (&l)[4]) {
+template <bool BILIN, typename Hook>
+__device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv)[8], float (&L)[4][8], float (&l)[4], const Hook& hook) {
     float W[8][8], VB[8][4], vVd[8], dd[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -123,6 +165,7 @@ __device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv
             if (BILIN) Su[a] = fmaf(ZB_F4(b4, a), vVd[i], Su[a]);
         }
     }
+    hook.cost_free();
     const float d0 = rsqrtf(G[0]);
     const float c10 = G[1] * d0, c20 = G[3] * d0, c30 = G[6] * d0;
     const float d1 = rsqrtf(fmaf(-c10, c10, G[2]));
@@ -147,9 +190,11 @@ __device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv
 #pragma unroll
             for (int j = 0; j < 8; ++j) M[a][j] = 0.f;
     }
+    hook.q_free();
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
         const float4 a0 = S[(A4 + 2 * kk) * RS], a1 = S[(A4 + 2 * kk + 1) * RS], b4 = S[(B4 + kk) * RS];
+        hook.row_free(kk);
         const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -200,7 +245,7 @@ __device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv
     }
 }
 
-template <bool BILIN>
+template <bool BILIN, bool ROWS>
 __global__ void __launch_bounds__(32) k_riccati_s84(S84P P) {
     __shared__ float4 slab[(BILIN ? NF4_BIL : NF4_LQR) * RS];
     const int lane = threadIdx.x;
@@ -210,32 +255,36 @@ __global__ void __launch_bounds__(32) k_riccati_s84(S84P P) {
     float4* S = slab + lane;
     float v[36], vv[8], L[4][8], l[4];
     // terminal carry (lqrUtils.py:172 / :261): Q[T-1] (and q[T-1])
-    int qk = P.T - 1, qvk = P.T - 1;
-    stage<16>(S, Q4, P.Q.at<float>(b, qk));
+    copy_in<16>(S, Q4, P.Q.at<float>(b, P.T - 1));
+    if (BILIN) copy_in<2>(S, QV4, P.q.at<float>(b, P.T - 1));
+    copies_done();
     read_q_lower(S, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) vv[i] = 0.f;
     if (BILIN) {
-        stage<2>(S, QV4, P.q.at<float>(b, qvk));
         const float4 q0 = S[QV4 * RS], q1 = S[(QV4 + 1) * RS];
         vv[0] = q0.x; vv[1] = q0.y; vv[2] = q0.z; vv[3] = q0.w; vv[4] = q1.x; vv[5] = q1.y; vv[6] = q1.z; vv[7] = q1.w;
+    }
+    // operands of the first step (k = N-1); those constant in time stay for the whole horizon
+    {
+        const int k = P.N - 1;
+        copy_in<16>(S, A4, P.A.at<float>(b, k));
+        copy_in<8>(S, B4, P.B.at<float>(b, k));
+        copy_in<4>(S, R4, P.R.at<float>(b, k));
+        if (P.Q.st && k != P.T - 1) copy_in<16>(S, Q4, P.Q.at<float>(b, k));
+        if (BILIN) {
+            copy_in<8>(S, H4, P.H.at<float>(b, k));
+            copy_in<2>(S, D4, P.d.at<float>(b, k));
+            copy_in<1>(S, RV4, P.r.at<float>(b, k));
+            if (P.q.st && k != P.T - 1) copy_in<2>(S, QV4, P.q.at<float>(b, k));
+        }
     }
     float* Lout = P.L + b * (long long)P.N * 32;
     float* lout = BILIN ? P.l + b * (long long)P.N * 4 : nullptr;
 #pragma unroll 1
     for (int k = P.N - 1; k >= 0; --k) {
-        const bool first = (k == P.N - 1);
-        if (first || P.A.st) stage<16>(S, A4, P.A.at<float>(b, k));
-        if (first || P.B.st) stage<8>(S, B4, P.B.at<float>(b, k));
-        if (first || P.R.st) stage<4>(S, R4, P.R.at<float>(b, k));
-        if (P.Q.st && k != qk) { stage<16>(S, Q4, P.Q.at<float>(b, k)); qk = k; }
-        if (BILIN) {
-            if (first || P.H.st) stage<8>(S, H4, P.H.at<float>(b, k));
-            if (first || P.d.st) stage<2>(S, D4, P.d.at<float>(b, k));
-            if (first || P.r.st) stage<1>(S, RV4, P.r.at<float>(b, k));
-            if (P.q.st && k != qvk) { stage<2>(S, QV4, P.q.at<float>(b, k)); qvk = k; }
-        }
-        step<BILIN>(S, v, vv, L, l);
+        copies_done();
+        step<BILIN>(S, v, vv, L, l, Refill<BILIN, ROWS>{P, S, b, k - 1});
         if (live) {
             float4* o = reinterpret_cast<float4*>(Lout + (long long)k * 32);
 #pragma unroll
@@ -256,7 +305,15 @@ __global__ void __launch_bounds__(32) k_riccati_s84(S84P P) {
     }
 }
 
-inline bool s84_arr_ok(const Arr& a) { return aligned16(a.p) && (a.sb % 4 == 0) && (a.st % 4 == 0); }
+#if defined(__CUDACC__)
+// ROWS (a hook per row of [A | B] in pass 3) only when A or B really vary in time
+template <bool BILIN>
+inline void launch(const S84P& F, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((F.Bsz + 31) / 32);
+    if (F.A.st || F.B.st) k_riccati_s84<BILIN, true><<<grid, 32, 0, stream>>>(F);
+    else k_riccati_s84<BILIN, false><<<grid, 32, 0, stream>>>(F);
+}
+#endif
 
 }  // namespace s84
 }  // namespace zb
