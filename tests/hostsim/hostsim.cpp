@@ -320,9 +320,8 @@ EXPORT int hs_riccati_s84(int bilinear, int64_t Bsz, int N, int T, const zb_arr*
         for (unsigned lane = 0; lane < 32; ++lane) {
             blockIdx.x = blk;
             threadIdx.x = lane;
-            const bool rows = P.A.st || P.B.st;  // as s84::launch picks the instantiation
-            if (bilinear) rows ? s84::k_riccati_s84<true, true>(P) : s84::k_riccati_s84<true, false>(P);
-            else rows ? s84::k_riccati_s84<false, true>(P) : s84::k_riccati_s84<false, false>(P);
+            if (bilinear) s84::k_riccati_s84<true>(P);
+            else s84::k_riccati_s84<false>(P);
         }
     return 0;
 }

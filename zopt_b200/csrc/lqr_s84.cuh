@@ -12,11 +12,14 @@
 //   * pass 3: V' (lower, 36 accumulators) = Q + A'W and M = B'W (+ H) in one pass over the rows of [A | B];
 //   * L = G^-1 M by two triangular solves per column, V' -= M'L (lower): algebraically the reference's Joseph form
 //     (lqrUtils.py:169) resp. V = Q + A'VA - L'S_uu L (lqrUtils.py:259), symmetric by construction;
-//   * bilinear: v + V d rides pass 1, S_u = r + B'(v + V d) rides the G loop, v' = q + A'(v + V d) - S_ux' l rides pass 3.
+//   * bilinear: H, d, q, r of the step are loaded from global memory straight into registers at the top of the step (they are
+//     used once, so shared memory would only add a hop; their latency hides behind pass 1: staged through the slab one after
+//     the other they cost 25 % of the stalls as long_scoreboard and two resident warps per SM); v + V d follows pass 1,
+//     S_u = r + B'(v + V d) rides the G loop, v' = q + A'(v + V d) - S_ux' l rides pass 3.
 // ~1,700 FMA and ~270 loaded words per problem-step (6 FMA per word).  Operands live in shared memory interleaved by lane
 // ([float4 slot][lane]): every 128-bit access of a warp is one contiguous 512 B row (conflict-free), each lane stages and
-// reads ITS OWN problem only (16-byte cp.async, no registers in between), so there is no barrier anywhere; operands with
-// stride_t = 0 are staged once, the others are requested for step k-1 from inside step k as their slots fall free.  Q, R are read as symmetric (lower triangle): callers with non-symmetric weights pass
+// reads ITS OWN problem only, so there is no barrier anywhere; operands with stride_t = 0 are staged once, the others
+// again at every step.  Q, R are read as symmetric (lower triangle): callers with non-symmetric weights pass
 // ZB_FORCE_GENERIC and get the as-written kernels.
 #pragma once
 #if defined(__CUDACC__)
@@ -34,12 +37,7 @@ constexpr int A4 = 0;     // A rows: 8 x 2 float4
 constexpr int B4 = 16;    // B rows: 8 x 1
 constexpr int Q4 = 24;    // Q rows: 8 x 2 (full rows; the lower-triangle-covering chunks are read)
 constexpr int R4 = 40;    // R rows: 4 x 1
-constexpr int NF4_LQR = 44;
-constexpr int H4 = 44;    // bilinear: H rows 4 x 2
-constexpr int D4 = 52;    // d (2), q (2), r (1)
-constexpr int QV4 = 54;
-constexpr int RV4 = 56;
-constexpr int NF4_BIL = 57;
+constexpr int NF4 = 44;   // float4 slots per problem (704 B); the bilinear operands H, d, q, r go from global memory to registers
 
 struct S84P {
     long long Bsz;
@@ -48,57 +46,24 @@ struct S84P {
     float *L, *l, *V0;  // gains (Bsz,N,4,8); bilinear offsets (Bsz,N,4); value at step 0 (Bsz,8,8) or null
 };
 
-// Each lane copies ITS OWN problem's operand block into its column of the slab with 16-byte cp.async (global -> shared, no
-// registers in between), so every copy of a step is in flight at once and the slab needs no barrier.
+// Each lane stages ITS OWN problem's operand block into its column of the slab: fetch() global -> registers, put() -> slab.
 template <int NSLOT>
-__device__ __forceinline__ void copy_in(float4* S, int slot, const float* g) {
-#if defined(__CUDACC__)
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(S + slot * RS);
+__device__ __forceinline__ void fetch(float4 (&t)[NSLOT], const float* g) {
+    const float4* g4 = reinterpret_cast<const float4*>(g);
 #pragma unroll
-    for (int j = 0; j < NSLOT; ++j)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst + j * RS * 16), "l"(g + 4 * j) : "memory");
-#else
-    for (int j = 0; j < NSLOT; ++j) S[(slot + j) * RS] = reinterpret_cast<const float4*>(g)[j];
-#endif
+    for (int j = 0; j < NSLOT; ++j) t[j] = __ldg(g4 + j);
 }
-__device__ __forceinline__ void copies_done() {
-#if defined(__CUDACC__)
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-#endif
+template <int NSLOT>
+__device__ __forceinline__ void put(float4* S, int slot, const float4 (&t)[NSLOT]) {
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) S[(slot + j) * RS] = t[j];
 }
-
-// Refill hooks: the step calls them as operand slots fall free, and the operands of step k-1 that vary in time are requested
-// right then, while step k still computes (a step that staged them at its start paid the L2 latency in full: long_scoreboard
-// 25 % of the stalls on the bilinear demo batch).  ROWS = A or B vary in time: only then does pass 3 carry a hook per row
-// (each hook is a compiler barrier for memory operations, which would serialise the row loads of the common case).
-template <bool BILIN, bool ROWS>
-struct Refill {
-    const S84P& P;
-    float4* S;
-    long long b;
-    int kn;  // the step being prefetched (k - 1); < 0: none
-    __device__ __forceinline__ void cost_free() const {  // R, d, r have been read
-        if (kn < 0) return;
-        if (P.R.st) copy_in<4>(S, R4, P.R.at<float>(b, kn));
-        if (BILIN) {
-            if (P.d.st) copy_in<2>(S, D4, P.d.at<float>(b, kn));
-            if (P.r.st) copy_in<1>(S, RV4, P.r.at<float>(b, kn));
-        }
-    }
-    __device__ __forceinline__ void q_free() const {  // Q, H, q have been read
-        if (kn < 0) return;
-        if (P.Q.st) copy_in<16>(S, Q4, P.Q.at<float>(b, kn));
-        if (BILIN) {
-            if (P.H.st) copy_in<8>(S, H4, P.H.at<float>(b, kn));
-            if (P.q.st) copy_in<2>(S, QV4, P.q.at<float>(b, kn));
-        }
-    }
-    __device__ __forceinline__ void row_free(int kk) const {  // row kk of [A | B] has been read for the last time
-        if (!ROWS || kn < 0) return;
-        if (P.A.st) copy_in<2>(S, A4 + 2 * kk, P.A.at<float>(b, kn) + 8 * kk);
-        if (P.B.st) copy_in<1>(S, B4 + kk, P.B.at<float>(b, kn) + 4 * kk);
-    }
-};
+template <int NSLOT>
+__device__ __forceinline__ void stage(float4* S, int slot, const float* g) {
+    float4 t[NSLOT];
+    fetch<NSLOT>(t, g);
+    put<NSLOT>(S, slot, t);
+}
 
 // lower triangle of the symmetric 8x8 staged at Q4 -> v[36]
 __device__ __forceinline__ void read_q_lower(const float4* S, float (&v)[36]) {
@@ -114,9 +79,24 @@ __device__ __forceinline__ void read_q_lower(const float4* S, float (&v)[36]) {
 }
 
 // One backward step for the problem owned by this thread.  v: lower triangle of V (in/out); vv: the linear term (bilinear, in/out).
-template <bool BILIN, typename Hook>
-__device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv)[8], float (&L)[4][8], float (&l)[4], const Hook& hook) {
-    float W[8][8], VB[8][4], vVd[8], dd[8];
+template <bool BILIN>
+__device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv)[8], float (&L)[4][8], float (&l)[4], const float* gH,
+                                     const float* gd, const float* gq, const float* gr) {
+    float W[8][8], VB[8][4], vVd[8], dd[8], M[4][8], Su[4], qn[8];
+    if (BILIN) {  // this step's H, d, q, r: global -> registers, in flight during pass 1
+        const float4* h4 = reinterpret_cast<const float4*>(gH);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float4 h0 = __ldg(h4 + 2 * a), h1 = __ldg(h4 + 2 * a + 1);
+            M[a][0] = h0.x; M[a][1] = h0.y; M[a][2] = h0.z; M[a][3] = h0.w; M[a][4] = h1.x; M[a][5] = h1.y; M[a][6] = h1.z; M[a][7] = h1.w;
+        }
+        const float4 d0 = __ldg(reinterpret_cast<const float4*>(gd)), d1 = __ldg(reinterpret_cast<const float4*>(gd) + 1);
+        dd[0] = d0.x; dd[1] = d0.y; dd[2] = d0.z; dd[3] = d0.w; dd[4] = d1.x; dd[5] = d1.y; dd[6] = d1.z; dd[7] = d1.w;
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(gq)), q1 = __ldg(reinterpret_cast<const float4*>(gq) + 1);
+        qn[0] = q0.x; qn[1] = q0.y; qn[2] = q0.z; qn[3] = q0.w; qn[4] = q1.x; qn[5] = q1.y; qn[6] = q1.z; qn[7] = q1.w;
+        const float4 rv = __ldg(reinterpret_cast<const float4*>(gr));
+        Su[0] = rv.x; Su[1] = rv.y; Su[2] = rv.z; Su[3] = rv.w;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
@@ -124,10 +104,6 @@ __device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv
 #pragma unroll
         for (int j = 0; j < 4; ++j) VB[i][j] = 0.f;
         vVd[i] = BILIN ? vv[i] : 0.f;
-    }
-    if (BILIN) {
-        const float4 d0 = S[D4 * RS], d1 = S[(D4 + 1) * RS];
-        dd[0] = d0.x; dd[1] = d0.y; dd[2] = d0.z; dd[3] = d0.w; dd[4] = d1.x; dd[5] = d1.y; dd[6] = d1.z; dd[7] = d1.w;
     }
     // ---- 1. [W | VB] = V [A | B]  (+ v + V d) -------------------------------------------------------------------
 #pragma unroll
@@ -142,18 +118,19 @@ __device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv
             fma2(W[i][6], W[i][7], vik, a1.z, a1.w);
             fma2(VB[i][0], VB[i][1], vik, b4.x, b4.y);
             fma2(VB[i][2], VB[i][3], vik, b4.z, b4.w);
-            if (BILIN) vVd[i] = fmaf(vik, dd[kk], vVd[i]);
         }
     }
+    if (BILIN) {  // v + V d
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vVd[i] = fmaf(v[tri(i, kk)], dd[kk], vVd[i]);
+    }
     // ---- 2. G = R + B'(VB) (lower), S_u = r + B'(v + V d); Cholesky G = C C' ------------------------------------
-    float G[10], Su[4];
+    float G[10];
     {
         const float4 r0 = S[(R4 + 0) * RS], r1 = S[(R4 + 1) * RS], r2 = S[(R4 + 2) * RS], r3 = S[(R4 + 3) * RS];
         G[0] = r0.x; G[1] = r1.x; G[2] = r1.y; G[3] = r2.x; G[4] = r2.y; G[5] = r2.z; G[6] = r3.x; G[7] = r3.y; G[8] = r3.z; G[9] = r3.w;
-        if (BILIN) {
-            const float4 rv = S[RV4 * RS];
-            Su[0] = rv.x; Su[1] = rv.y; Su[2] = rv.z; Su[3] = rv.w;
-        }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -165,7 +142,6 @@ __device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv
             if (BILIN) Su[a] = fmaf(ZB_F4(b4, a), vVd[i], Su[a]);
         }
     }
-    hook.cost_free();
     const float d0 = rsqrtf(G[0]);
     const float c10 = G[1] * d0, c20 = G[3] * d0, c30 = G[6] * d0;
     const float d1 = rsqrtf(fmaf(-c10, c10, G[2]));
@@ -174,27 +150,19 @@ __device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv
     const float c32 = fmaf(-c31, c21, fmaf(-c30, c20, G[8])) * d2;
     const float d3 = rsqrtf(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
     // ---- 3. V' (lower) = Q + A'W, M = (H +) B'W, v' = q + A'(v + V d) in one pass over the rows of [A | B] -------
-    float M[4][8];
     read_q_lower(S, v);  // V is dead from here on: its registers take the new value
     if (BILIN) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const float4 h0 = S[(H4 + 2 * a) * RS], h1 = S[(H4 + 2 * a + 1) * RS];
-            M[a][0] = h0.x; M[a][1] = h0.y; M[a][2] = h0.z; M[a][3] = h0.w; M[a][4] = h1.x; M[a][5] = h1.y; M[a][6] = h1.z; M[a][7] = h1.w;
-        }
-        const float4 q0 = S[QV4 * RS], q1 = S[(QV4 + 1) * RS];
-        vv[0] = q0.x; vv[1] = q0.y; vv[2] = q0.z; vv[3] = q0.w; vv[4] = q1.x; vv[5] = q1.y; vv[6] = q1.z; vv[7] = q1.w;
+        for (int i = 0; i < 8; ++i) vv[i] = qn[i];
     } else {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int j = 0; j < 8; ++j) M[a][j] = 0.f;
     }
-    hook.q_free();
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
         const float4 a0 = S[(A4 + 2 * kk) * RS], a1 = S[(A4 + 2 * kk + 1) * RS], b4 = S[(B4 + kk) * RS];
-        hook.row_free(kk);
         const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -245,9 +213,9 @@ __device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv
     }
 }
 
-template <bool BILIN, bool ROWS>
+template <bool BILIN>
 __global__ void __launch_bounds__(32) k_riccati_s84(S84P P) {
-    __shared__ float4 slab[(BILIN ? NF4_BIL : NF4_LQR) * RS];
+    __shared__ float4 slab[NF4 * RS];
     const int lane = threadIdx.x;
     long long b = blockIdx.x * 32LL + lane;
     const bool live = b < P.Bsz;
@@ -255,36 +223,41 @@ __global__ void __launch_bounds__(32) k_riccati_s84(S84P P) {
     float4* S = slab + lane;
     float v[36], vv[8], L[4][8], l[4];
     // terminal carry (lqrUtils.py:172 / :261): Q[T-1] (and q[T-1])
-    copy_in<16>(S, Q4, P.Q.at<float>(b, P.T - 1));
-    if (BILIN) copy_in<2>(S, QV4, P.q.at<float>(b, P.T - 1));
-    copies_done();
+    int qk = P.T - 1;
+    stage<16>(S, Q4, P.Q.at<float>(b, qk));
     read_q_lower(S, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) vv[i] = 0.f;
     if (BILIN) {
-        const float4 q0 = S[QV4 * RS], q1 = S[(QV4 + 1) * RS];
+        const float4* qf = reinterpret_cast<const float4*>(P.q.at<float>(b, P.T - 1));
+        const float4 q0 = __ldg(qf), q1 = __ldg(qf + 1);
         vv[0] = q0.x; vv[1] = q0.y; vv[2] = q0.z; vv[3] = q0.w; vv[4] = q1.x; vv[5] = q1.y; vv[6] = q1.z; vv[7] = q1.w;
-    }
-    // operands of the first step (k = N-1); those constant in time stay for the whole horizon
-    {
-        const int k = P.N - 1;
-        copy_in<16>(S, A4, P.A.at<float>(b, k));
-        copy_in<8>(S, B4, P.B.at<float>(b, k));
-        copy_in<4>(S, R4, P.R.at<float>(b, k));
-        if (P.Q.st && k != P.T - 1) copy_in<16>(S, Q4, P.Q.at<float>(b, k));
-        if (BILIN) {
-            copy_in<8>(S, H4, P.H.at<float>(b, k));
-            copy_in<2>(S, D4, P.d.at<float>(b, k));
-            copy_in<1>(S, RV4, P.r.at<float>(b, k));
-            if (P.q.st && k != P.T - 1) copy_in<2>(S, QV4, P.q.at<float>(b, k));
-        }
     }
     float* Lout = P.L + b * (long long)P.N * 32;
     float* lout = BILIN ? P.l + b * (long long)P.N * 4 : nullptr;
 #pragma unroll 1
     for (int k = P.N - 1; k >= 0; --k) {
-        copies_done();
-        step<BILIN>(S, v, vv, L, l, Refill<BILIN, ROWS>{P, S, b, k - 1});
+        const bool first = (k == P.N - 1);
+        // operands constant in time are staged once; the others again at every step, in two groups ([A | B] and [Q, R]) whose
+        // loads are all in flight before the first store waits (one L2 latency per group; re-staging a constant member of a
+        // group is harmless: the same block again)
+        if (first || P.A.st || P.B.st) {
+            float4 ta[16], tb[8];
+            fetch<16>(ta, P.A.at<float>(b, k));
+            fetch<8>(tb, P.B.at<float>(b, k));
+            put<16>(S, A4, ta);
+            put<8>(S, B4, tb);
+        }
+        if (first || P.R.st || (P.Q.st && k != qk)) {
+            float4 tq[16], tr[4];
+            fetch<16>(tq, P.Q.at<float>(b, P.Q.st ? k : qk));
+            fetch<4>(tr, P.R.at<float>(b, k));
+            put<16>(S, Q4, tq);
+            put<4>(S, R4, tr);
+            qk = P.Q.st ? k : qk;
+        }
+        if (BILIN) step<true>(S, v, vv, L, l, P.H.at<float>(b, k), P.d.at<float>(b, k), P.q.at<float>(b, k), P.r.at<float>(b, k));
+        else step<false>(S, v, vv, L, l, nullptr, nullptr, nullptr, nullptr);
         if (live) {
             float4* o = reinterpret_cast<float4*>(Lout + (long long)k * 32);
 #pragma unroll
@@ -305,15 +278,7 @@ __global__ void __launch_bounds__(32) k_riccati_s84(S84P P) {
     }
 }
 
-#if defined(__CUDACC__)
-// ROWS (a hook per row of [A | B] in pass 3) only when A or B really vary in time
-template <bool BILIN>
-inline void launch(const S84P& F, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((F.Bsz + 31) / 32);
-    if (F.A.st || F.B.st) k_riccati_s84<BILIN, true><<<grid, 32, 0, stream>>>(F);
-    else k_riccati_s84<BILIN, false><<<grid, 32, 0, stream>>>(F);
-}
-#endif
+inline bool s84_arr_ok(const Arr& a) { return aligned16(a.p) && (a.sb % 4 == 0) && (a.st % 4 == 0); }
 
 }  // namespace s84
 }  // namespace zb

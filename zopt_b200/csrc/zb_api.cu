@@ -295,7 +295,7 @@ int32_t zb_lqr_dfh_flags(int32_t dtype, int32_t device, void* stream, int64_t Bs
         F.Bsz = Bsz; F.N = N; F.T = T;
         F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R;
         F.L = reinterpret_cast<float*>(L_out); F.V0 = reinterpret_cast<float*>(V0_out);
-        s84::launch<false>(F, (cudaStream_t)stream);
+        s84::k_riccati_s84<false><<<(unsigned)((Bsz + 31) / 32), 32, 0, (cudaStream_t)stream>>>(F);
         ZB_CUDA(cudaGetLastError());
         return 0;
     }
@@ -374,7 +374,7 @@ int32_t zb_lqr_bilinear_flags(int32_t dtype, int32_t device, void* stream, int64
         F.Bsz = Bsz; F.N = N; F.T = T;
         F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R; F.H = P.H; F.d = P.d; F.q = P.q; F.r = P.r;
         F.L = reinterpret_cast<float*>(L_out); F.l = reinterpret_cast<float*>(l_out);
-        s84::launch<true>(F, (cudaStream_t)stream);
+        s84::k_riccati_s84<true><<<(unsigned)((Bsz + 31) / 32), 32, 0, (cudaStream_t)stream>>>(F);
         ZB_CUDA(cudaGetLastError());
         return 0;
     }
