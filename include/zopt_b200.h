@@ -80,7 +80,7 @@ ZB_API int32_t zb_lqr_dfh(int32_t dtype, int32_t device, void* stream, int64_t B
                    int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* Q, const zb_arr* R, void* L_out,
                    void* V0_out);
 
-/* Same with flags: ZB_FORCE_GENERIC = take the as-written kernels, which use Q and R exactly as given (the (12,4) and the fp32
+/* Same with flags: ZB_FORCE_GENERIC = take the as-written kernels, which use Q and R exactly as given (the (12,4) and the
  * (8,4) kernels read only the lower triangle of the symmetric weights; the Python mirror passes this flag when a weight is not
  * symmetric, so that results equal the reference's for any input, lqrUtils.py:168-169). */
 ZB_API int32_t zb_lqr_dfh_flags(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
@@ -104,7 +104,7 @@ ZB_API int32_t zb_lqr_bilinear(int32_t dtype, int32_t device, void* stream, int6
                         const zb_arr* R, const zb_arr* H, const zb_arr* q, const zb_arr* r, const zb_arr* q0,
                         void* L_out, void* l_out);
 
-/* Same with flags: ZB_FORCE_GENERIC = Q, R used exactly as given (the fp32 (8,4) kernel reads their lower triangles only;
+/* Same with flags: ZB_FORCE_GENERIC = Q, R used exactly as given (the (8,4) kernels read their lower triangles only;
  * zb_lqr_bilinear = flags 0). */
 ZB_API int32_t zb_lqr_bilinear_flags(int32_t dtype, int32_t device, void* stream, int64_t Bsz, int32_t N, int32_t T, int32_t n,
                               int32_t m, const zb_arr* A, const zb_arr* B, const zb_arr* d, const zb_arr* Q,

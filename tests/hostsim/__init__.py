@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libhostsim.so")
 _SRC = os.path.join(_HERE, "hostsim.cpp")
 _DEPS = [_SRC] + [os.path.join(_HERE, "..", "..", "zopt_b200", "csrc", f)
-                  for f in ("zb_problems.cuh", "zb_steps.cuh", "zb_math.cuh", "quad_model_gen.cuh", "mpc_box.cuh", "lqr_s84.cuh")]
+                  for f in ("zb_problems.cuh", "zb_steps.cuh", "zb_math.cuh", "quad_model_gen.cuh", "mpc_box.cuh", "lqr_s84.cuh", "lqr_s84d.cuh")]
 
 
 def _build():

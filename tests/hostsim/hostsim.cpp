@@ -308,6 +308,11 @@ inline void fma2(float& d0, float& d1, float a, float b0, float b1) { d0 = std::
 }  // namespace zb
 #define ZB_F4(v, e) ((e) == 0 ? (v).x : (e) == 1 ? (v).y : (e) == 2 ? (v).z : (v).w)
 #include "../../zopt_b200/csrc/lqr_s84.cuh"
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+#define __host__
+using std::fma;
+#include "../../zopt_b200/csrc/lqr_s84d.cuh"
 
 EXPORT int hs_riccati_s84(int bilinear, int64_t Bsz, int N, int T, const zb_arr* A, const zb_arr* B, const zb_arr* d, const zb_arr* Q,
                           const zb_arr* R, const zb_arr* H, const zb_arr* q, const zb_arr* r, float* L, float* l, float* V0) {
@@ -322,6 +327,23 @@ EXPORT int hs_riccati_s84(int bilinear, int64_t Bsz, int N, int T, const zb_arr*
             threadIdx.x = lane;
             if (bilinear) s84::k_riccati_s84<true>(P);
             else s84::k_riccati_s84<false>(P);
+        }
+    return 0;
+}
+
+EXPORT int hs_riccati_s84d(int bilinear, int64_t Bsz, int N, int T, const zb_arr* A, const zb_arr* B, const zb_arr* d, const zb_arr* Q,
+                           const zb_arr* R, const zb_arr* H, const zb_arr* q, const zb_arr* r, double* L, double* l, double* V0) {
+    s84d::S84DP P{};
+    P.Bsz = Bsz; P.N = N; P.T = T;
+    P.A = A_(A); P.B = A_(B); P.Q = A_(Q); P.R = A_(R);
+    if (bilinear) { P.H = A_(H); P.d = A_(d); P.q = A_(q); P.r = A_(r); }
+    P.L = L; P.l = l; P.V0 = V0;
+    for (unsigned blk = 0; blk < (Bsz + 31) / 32; ++blk)
+        for (unsigned lane = 0; lane < 32; ++lane) {
+            blockIdx.x = blk;
+            threadIdx.x = lane;
+            if (bilinear) s84d::k_riccati_s84d<true>(P);
+            else s84d::k_riccati_s84d<false>(P);
         }
     return 0;
 }

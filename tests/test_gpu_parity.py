@@ -212,54 +212,56 @@ def _s84_ops(rng, Bsz, T):
     return A, Bm, d, Q, R, Hm, rng.normal(size=(Bsz, T, n)), rng.normal(size=(Bsz, T, m)), rng.normal(size=(Bsz, T))
 
 
-def test_lqr_8x4_fp32_kernel_vs_oracle(monkeypatch):
-    """k_riccati_s84 (lqr_s84.cuh), the fp32 kernel of the demos' shape (8,4), for discreteFiniteHorizonLqr and bilinearAffineLqr:
+@pytest.mark.parametrize("dt,tol,tol_ct", [(torch.float32, 1e-5, 1e-4), (torch.float64, 1e-10, 1e-10)])
+def test_lqr_8x4_kernel_vs_oracle(monkeypatch, dt, tol, tol_ct):
+    """k_riccati_s84 (lqr_s84.cuh, fp32) and k_riccati_s84d (lqr_s84d.cuh, fp64), the kernels of the demos' shape (8,4), for
+    discreteFiniteHorizonLqr and bilinearAffineLqr:
     time-varying operands with T > N and a ragged last warp, operands constant in time (stride_t = 0: staged once), un-batched
-    operands shared by the batch; fp32 gate 1e-5 against the fp64 oracle.  The as-written compile-time-size kernel
+    operands shared by the batch; gates fp32 1e-5, fp64 1e-10 against the fp64 oracle.  The as-written compile-time-size kernel
     (ZB_NO_S84=1) must agree with it, and non-symmetric weights must bypass it (it reads lower triangles only)."""
     from zopt_b200.lqrUtils import bilinearAffineLqr, discreteFiniteHorizonLqr
     rng = np.random.default_rng(11)
     T, N, Bsz = 9, 7, 70
     ops = _s84_ops(rng, Bsz, T)
     A, Bm, d, Q, R, Hm, q, r, q0 = ops
-    f32 = lambda a: cuda(a, torch.float32)
+    f32 = lambda a: cuda(a, dt)
     Lref, Vref = olqr.discreteFiniteHorizonLqr_batched(A, Bm, Q, R, N, return_value=True)
     L, V0 = discreteFiniteHorizonLqr(f32(A), f32(Bm), f32(Q), f32(R), N, return_value=True)
-    assert L.dtype == torch.float32 and per_problem_relerr(L, Lref).max() < 1e-5 and per_problem_relerr(V0, Vref).max() < 1e-5
+    assert L.dtype == dt and per_problem_relerr(L, Lref).max() < tol and per_problem_relerr(V0, Vref).max() < tol
     assert float((V0 - V0.transpose(-1, -2)).abs().max()) == 0.0  # symmetric by construction
     Lr, lr = olqr.bilinearAffineLqr_batched(*ops, N)
     Lb, lb = bilinearAffineLqr(*(f32(t) for t in ops), N)
-    assert per_problem_relerr(Lb, Lr).max() < 1e-5 and per_problem_relerr(lb, lr).max() < 1e-5
+    assert per_problem_relerr(Lb, Lr).max() < tol and per_problem_relerr(lb, lr).max() < tol
     # the as-written kernel on the same inputs (looser: it is the less accurate of the two in fp32)
     monkeypatch.setenv("ZB_NO_S84", "1")
     L_ct = discreteFiniteHorizonLqr(f32(A), f32(Bm), f32(Q), f32(R), N)
     Lb_ct, lb_ct = bilinearAffineLqr(*(f32(t) for t in ops), N)
     monkeypatch.delenv("ZB_NO_S84")
     assert not torch.equal(L_ct, L)  # a different kernel really ran
-    assert per_problem_relerr(L_ct, Lref).max() < 1e-4 and per_problem_relerr(Lb_ct, Lr).max() < 1e-4 and per_problem_relerr(lb_ct, lr).max() < 1e-4
+    assert per_problem_relerr(L_ct, Lref).max() < tol_ct and per_problem_relerr(Lb_ct, Lr).max() < tol_ct and per_problem_relerr(lb_ct, lr).max() < tol_ct
     # operands constant in time, passed as stride-0 expansions; the terminal value is still Q[-1]
     ti = [np.repeat(a[:, :1], T, axis=1) for a in ops]
     ex = lambda a: f32(a[:, :1]).expand(*([-1, T] + [-1] * (a.ndim - 2)))
     Lref_ti = olqr.discreteFiniteHorizonLqr_batched(ti[0], ti[1], ti[3], ti[4], N)
-    assert per_problem_relerr(discreteFiniteHorizonLqr(ex(A), ex(Bm), ex(Q), ex(R), N), Lref_ti).max() < 1e-5
+    assert per_problem_relerr(discreteFiniteHorizonLqr(ex(A), ex(Bm), ex(Q), ex(R), N), Lref_ti).max() < tol
     Lr_ti, lr_ti = olqr.bilinearAffineLqr_batched(*ti, N)
     Lb, lb = bilinearAffineLqr(*(ex(a) for a in ops), N)
-    assert per_problem_relerr(Lb, Lr_ti).max() < 1e-5 and per_problem_relerr(lb, lr_ti).max() < 1e-5
+    assert per_problem_relerr(Lb, Lr_ti).max() < tol and per_problem_relerr(lb, lr_ti).max() < tol
     # shared (un-batched) A, B, Q, R with batched d, H, q, r
     sh = [np.repeat(a[:1], Bsz, axis=0) if i in (0, 1, 3, 4) else a for i, a in enumerate(ops)]
     Lr_sh, lr_sh = olqr.bilinearAffineLqr_batched(*sh, N)
     Lb, lb = bilinearAffineLqr(*(f32(a[0]) if i in (0, 1, 3, 4) else f32(a) for i, a in enumerate(ops)), N)
-    assert per_problem_relerr(Lb, Lr_sh).max() < 1e-5 and per_problem_relerr(lb, lr_sh).max() < 1e-5
+    assert per_problem_relerr(Lb, Lr_sh).max() < tol and per_problem_relerr(lb, lr_sh).max() < tol
     # non-symmetric weights are used as given (zopt/lqrUtils.py:168-169, :251-259): the as-written kernel takes them
     Qn, Rn = Q.copy(), R.copy()
     Qn[..., 0, 5] += 0.3
     Rn[..., 1, 3] -= 0.2
     Ln = discreteFiniteHorizonLqr(f32(A), f32(Bm), f32(Qn), f32(Rn), N)
-    assert per_problem_relerr(Ln, olqr.discreteFiniteHorizonLqr_batched(A, Bm, Qn, Rn, N)).max() < 1e-4
+    assert per_problem_relerr(Ln, olqr.discreteFiniteHorizonLqr_batched(A, Bm, Qn, Rn, N)).max() < tol_ct
     opsn = [A, Bm, d, Qn, Rn, Hm, q, r, q0]
     Lrn, lrn = olqr.bilinearAffineLqr_batched(*opsn, N)
     Lbn, lbn = bilinearAffineLqr(*(f32(t) for t in opsn), N)
-    assert per_problem_relerr(Lbn, Lrn).max() < 1e-4 and per_problem_relerr(lbn, lrn).max() < 1e-4
+    assert per_problem_relerr(Lbn, Lrn).max() < tol_ct and per_problem_relerr(lbn, lrn).max() < tol_ct
     assert per_problem_relerr(Ln, Lref).max() > 1e-3  # and the perturbation mattered
 
 

@@ -393,13 +393,14 @@ def _s84_problem(rng, Bsz, T, tv=True):
     return ops
 
 
-def _run_s84(bilinear, ops, N, time_invariant=False):
-    A, Bm, d, Q, R, Hm, q, r, _ = (np.ascontiguousarray(a, dtype=np.float32) for a in ops)
+def _run_s84(bilinear, ops, N, time_invariant=False, dt=np.float32):
+    A, Bm, d, Q, R, Hm, q, r, _ = (np.ascontiguousarray(a, dtype=dt) for a in ops)
     Bsz, T = Q.shape[0], Q.shape[1]
     cut = (lambda a: np.ascontiguousarray(a[:, :1])) if time_invariant else (lambda a: a)
     zs = [H.arr(cut(a), k) for a, k in ((A, 2), (Bm, 2), (d, 1), (Q, 2), (R, 2), (Hm, 2), (q, 1), (r, 1))]
-    L, l, V0 = np.zeros((Bsz, N, 4, 8), np.float32), np.zeros((Bsz, N, 4), np.float32), np.zeros((Bsz, 8, 8), np.float32)
-    H.hs.hs_riccati_s84(int(bilinear), C.c_int64(Bsz), N, 1 if time_invariant else T, *[C.byref(z) for z in zs], H.P(L), H.P(l), H.P(V0))
+    L, l, V0 = np.zeros((Bsz, N, 4, 8), dt), np.zeros((Bsz, N, 4), dt), np.zeros((Bsz, 8, 8), dt)
+    fn = H.hs.hs_riccati_s84 if dt == np.float32 else H.hs.hs_riccati_s84d  # lqr_s84.cuh / lqr_s84d.cuh
+    fn(int(bilinear), C.c_int64(Bsz), N, 1 if time_invariant else T, *[C.byref(z) for z in zs], H.P(L), H.P(l), H.P(V0))
     return L, l, V0
 
 
@@ -408,33 +409,36 @@ def _pre(a, b):
     return float((np.abs(a - b).reshape(a.shape[0], -1).max(1) / np.abs(b).reshape(b.shape[0], -1).max(1)).max())
 
 
+@pytest.mark.parametrize("dt,tol", [(np.float32, 1e-5), (np.float64, 1e-10)])
 @pytest.mark.parametrize("tv", [True, False])
-def test_s84_kernel_body_vs_oracle(tv):
-    """lqr_s84.cuh compiled for the host (fp32) against the fp64 oracle: time-varying operands with T > N and a ragged last warp,
-    and fully time-invariant operands staged once; the gate is BASELINE.md section 6's fp32 1e-5 (measured: below 1e-6)."""
+def test_s84_kernel_body_vs_oracle(tv, dt, tol):
+    """lqr_s84.cuh (fp32) and lqr_s84d.cuh (fp64) compiled for the host against the fp64 oracle: time-varying operands with T > N
+    and a ragged last warp, and fully time-invariant operands staged once; the gates are BASELINE.md section 6's fp32 1e-5
+    (measured: below 1e-6) and fp64 1e-10."""
     rng = np.random.default_rng(7)
     T, N, Bsz = 9, 7, 37
     ops = _s84_problem(rng, Bsz, T, tv)
     A, Bm, d, Q, R, Hm, q, r, q0 = ops
     Lref, Vref = olqr.discreteFiniteHorizonLqr_batched(A, Bm, Q, R, N, return_value=True)
-    L, _, V0 = _run_s84(False, ops, N, time_invariant=not tv)
-    assert _pre(L, Lref) < 1e-5 and _pre(V0, Vref) < 1e-5
+    L, _, V0 = _run_s84(False, ops, N, time_invariant=not tv, dt=dt)
+    assert _pre(L, Lref) < tol and _pre(V0, Vref) < tol
     Lr, lr = olqr.bilinearAffineLqr_batched(A, Bm, d, Q, R, Hm, q, r, q0, N)
-    L, l, _ = _run_s84(True, ops, N, time_invariant=not tv)
-    assert _pre(L, Lr) < 1e-5 and _pre(l, lr) < 1e-5
+    L, l, _ = _run_s84(True, ops, N, time_invariant=not tv, dt=dt)
+    assert _pre(L, Lr) < tol and _pre(l, lr) < tol
 
 
-def test_s84_kernel_body_demo_horizon():
+@pytest.mark.parametrize("dt,tol", [(np.float32, 1e-5), (np.float64, 1e-10)])
+def test_s84_kernel_body_demo_horizon(dt, tol):
     """the demos' problems at N = 100 (demos/discreteFiniteHorizonLqr.py:29-35 incl. the Q[-1] terminal quirk,
-    demos/bilinearLqrControl.py:21-43 with a seeded H): fp32 within 1e-5 of the fp64 oracle"""
+    demos/bilinearLqrControl.py:21-43 with a seeded H): fp32 within 1e-5, fp64 within 1e-10 of the fp64 oracle"""
     N = 100
     A0, B0 = (t.numpy() for t in Quadcopter().linearize(np.zeros(8), configs.U_TRIM, dt=0.1))
     Qk, Rk = (np.asarray(a) for a in configs.cfg1_demo_weights(N))
     rep = lambda a: np.repeat(a[None, None], N, axis=1)
     Kref = olqr.discreteFiniteHorizonLqr(rep(A0)[0], rep(B0)[0], Qk, Rk, N)
     z = np.zeros((1, N, 1))
-    L, _, _ = _run_s84(False, [rep(A0), rep(B0), z, Qk[None], Rk[None], z, z, z, z], N)
-    assert _pre(L, np.asarray(Kref)[None]) < 1e-5
+    L, _, _ = _run_s84(False, [rep(A0), rep(B0), z, Qk[None], Rk[None], z, z, z, z], N, dt=dt)
+    assert _pre(L, np.asarray(Kref)[None]) < tol
     rng = np.random.default_rng(1)
     Bsz = 5
     bat = lambda a: np.repeat(a, Bsz, axis=0)
@@ -443,5 +447,5 @@ def test_s84_kernel_body_demo_horizon():
     r, q0 = rng.normal(size=(Bsz, N, 4)) * 0.1, rng.normal(size=(Bsz, N))
     ops = [bat(rep(A0)), bat(rep(B0)), d, bat(rep(np.eye(8))), bat(rep(np.eye(4))), Hm, q, r, q0]
     Lr, lr = olqr.bilinearAffineLqr_batched(*ops, N)
-    L, l, _ = _run_s84(True, ops, N)
-    assert _pre(L, Lr) < 1e-5 and _pre(l, lr) < 1e-5
+    L, l, _ = _run_s84(True, ops, N, dt=dt)
+    assert _pre(L, Lr) < tol and _pre(l, lr) < tol

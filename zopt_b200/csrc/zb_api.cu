@@ -8,6 +8,7 @@
 #include "ilqr_generic.cuh"
 #include "lqr_t1.cuh"
 #include "lqr_s84.cuh"
+#include "lqr_s84d.cuh"
 #include "mpc_coop.cuh"
 #include "mpc_box.cuh"
 #include "mpc_box_quad.cuh"
@@ -331,6 +332,15 @@ int32_t zb_lqr_dfh_flags(int32_t dtype, int32_t device, void* stream, int64_t Bs
         F.L = L_out; F.V0 = V0_out;
         return riccati_quad_launch(dtype, F, (cudaStream_t)stream);
     }
+    if (dtype == ZB_F64 && n == 8 && m == 4 && N >= 1 && !(flags & ZB_FORCE_GENERIC) && s84d::arr_ok(P.A) && s84d::arr_ok(P.B) &&
+        s84d::arr_ok(P.Q) && s84d::arr_ok(P.R) && aligned16(P.L) && (!P.V0 || aligned16(P.V0)) && !getenv("ZB_FORCE_RUNTIME_SIZES") &&
+        !getenv("ZB_NO_S84")) {  // the same in fp64 (lqr_s84d.cuh)
+        s84d::S84DP F{};
+        F.Bsz = Bsz; F.N = N; F.T = T;
+        F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R;
+        F.L = reinterpret_cast<double*>(L_out); F.V0 = reinterpret_cast<double*>(V0_out);
+        return s84d::launch<false>(F, (cudaStream_t)stream);
+    }
 #define ZB_CT_LQR(N_, M_)                                                                                   \
     if (n == N_ && m == M_ && (dtype == ZB_F32 || ZB_CT_F64_OK(N_)) && !getenv("ZB_FORCE_RUNTIME_SIZES")) {   \
         if (dtype == ZB_F32) k_lqr_ct<float, N_, M_><<<gen_grid(Bsz), GEN_THREADS, 0, (cudaStream_t)stream>>>(P);   \
@@ -377,6 +387,15 @@ int32_t zb_lqr_bilinear_flags(int32_t dtype, int32_t device, void* stream, int64
         s84::k_riccati_s84<true><<<(unsigned)((Bsz + 31) / 32), 32, 0, (cudaStream_t)stream>>>(F);
         ZB_CUDA(cudaGetLastError());
         return 0;
+    }
+    if (dtype == ZB_F64 && n == 8 && m == 4 && N >= 1 && !(flags & ZB_FORCE_GENERIC) && s84d::arr_ok(P.A) && s84d::arr_ok(P.B) &&
+        s84d::arr_ok(P.d) && s84d::arr_ok(P.Q) && s84d::arr_ok(P.R) && s84d::arr_ok(P.H) && s84d::arr_ok(P.q) && s84d::arr_ok(P.r) &&
+        aligned16(L_out) && aligned16(l_out) && !getenv("ZB_FORCE_RUNTIME_SIZES") && !getenv("ZB_NO_S84")) {  // lqr_s84d.cuh
+        s84d::S84DP F{};
+        F.Bsz = Bsz; F.N = N; F.T = T;
+        F.A = P.A; F.B = P.B; F.Q = P.Q; F.R = P.R; F.H = P.H; F.d = P.d; F.q = P.q; F.r = P.r;
+        F.L = reinterpret_cast<double*>(L_out); F.l = reinterpret_cast<double*>(l_out);
+        return s84d::launch<true>(F, (cudaStream_t)stream);
     }
 #define ZB_CT_BIL(N_, M_)                                                                                        \
     if (n == N_ && m == M_ && (dtype == ZB_F32 || ZB_CT_F64_OK(N_)) && !getenv("ZB_FORCE_RUNTIME_SIZES")) {        \

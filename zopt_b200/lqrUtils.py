@@ -65,7 +65,7 @@ def discreteFiniteHorizonLqr(A, B, Q, R, N, return_value=False, kernel_flags=0):
     V0 = torch.empty((Bsz, n, n), dtype=dtype, device=device) if return_value else None
     # The (12,4) fast kernels keep the symmetric value matrix as a lower triangle and read the lower triangle of Q, R.  The
     # reference uses the weights exactly as given (lqrUtils.py:168-169), so non-symmetric ones take the generic kernel.
-    sym_kernel = (n, m) == (12, 4) or ((n, m) == (8, 4) and dtype == torch.float32)
+    sym_kernel = (n, m) in ((12, 4), (8, 4))
     flags = 0 if (not sym_kernel or (is_symmetric(Q) and is_symmetric(R))) else 128  # ZB_FORCE_GENERIC
     flags |= int(kernel_flags)  # e.g. 256 = ZB_TV_BULK_COPY (tests / experiments)
     check(lib.zb_lqr_dfh_flags(dcode(dtype), device.index, stream_ptr(device), Bsz, N, T, n, m, vA.ref(), vB.ref(), vQ.ref(),
@@ -109,8 +109,8 @@ def bilinearAffineLqr(A, B, d, Q, R, H, q, r, q0, N):
     views = [View(t, k, True, b) for t, k, b in zip(ts, blocks, batched)]
     L = torch.empty((Bsz, N, m, n), dtype=dtype, device=device)
     l = torch.empty((Bsz, N, m), dtype=dtype, device=device)
-    # the fp32 (8,4) kernel reads the lower triangles of Q and R (lqr_s84.cuh); non-symmetric weights take the as-written kernel
-    flags = 0 if ((n, m) != (8, 4) or dtype != torch.float32 or (is_symmetric(Q) and is_symmetric(R))) else 128  # ZB_FORCE_GENERIC
+    # the (8,4) kernels read the lower triangles of Q and R (lqr_s84.cuh, lqr_s84d.cuh); non-symmetric weights take the as-written kernel
+    flags = 0 if ((n, m) != (8, 4) or (is_symmetric(Q) and is_symmetric(R))) else 128  # ZB_FORCE_GENERIC
     check(lib.zb_lqr_bilinear_flags(dcode(dtype), device.index, stream_ptr(device), Bsz, N, T, n, m, *[v.ref() for v in views],
                                     flags, ptr(L), ptr(l)))
     if not any_b:
