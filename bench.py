@@ -496,6 +496,23 @@ def run_ours(args):
         discreteFiniteHorizonLqr(Atv, Btv, Qtv, Rtv, N)
         X["tv"] = timed(lambda: discreteFiniteHorizonLqr(Atv, Btv, Qtv, Rtv, N), 5)
         del Atv, Btv, Qtv, Rtv
+        # cfg 1's shape (the demos' (n, m) = (8, 4), N = 100) as a batch: discreteFiniteHorizonLqr and bilinearAffineLqr with per-problem
+        # A, B constant in time and H, d, q, r series shared by the batch, fp32 (k_riccati_s84) and fp64 (k_riccati_s84d)
+        from zopt_b200.lqrUtils import bilinearAffineLqr
+        g8 = torch.Generator(device="cpu").manual_seed(8)
+        for dt8, tag in ((f32, "f32"), (f64, "f64")):
+            c8 = lambda t: t.to(dtype=dt8, device=dev)
+            A8 = c8(torch.eye(8) + 0.1 * torch.randn(Bsz, 1, 8, 8, generator=g8)).expand(-1, 100, -1, -1)
+            B8 = c8(0.3 * torch.randn(Bsz, 1, 8, 4, generator=g8)).expand(-1, 100, -1, -1)
+            Q8, R8 = c8(torch.eye(8))[None, None].expand(Bsz, 100, -1, -1), c8(torch.eye(4))[None, None].expand(Bsz, 100, -1, -1)
+            H8 = c8(0.1 * torch.randn(1, 100, 4, 8, generator=g8)).expand(Bsz, -1, -1, -1)
+            d8, q8 = (c8(s8 * torch.randn(1, 100, 8, generator=g8)).expand(Bsz, -1, -1) for s8 in (0.01, 0.1))
+            r8, q08 = c8(0.05 * torch.randn(1, 100, 4, generator=g8)).expand(Bsz, -1, -1), c8(torch.zeros(1, 100)).expand(Bsz, -1)
+            discreteFiniteHorizonLqr(A8, B8, Q8, R8, 100)
+            X["dfh8_" + tag] = timed(lambda: discreteFiniteHorizonLqr(A8, B8, Q8, R8, 100), 5)
+            bilinearAffineLqr(A8, B8, d8, Q8, R8, H8, q8, r8, q08, 100)
+            X["bil8_" + tag] = timed(lambda: bilinearAffineLqr(A8, B8, d8, Q8, R8, H8, q8, r8, q08, 100), 5)
+        del A8, B8, Q8, R8, H8, d8, q8, r8, q08
         # the headline workload in the reference's own precision (fp64): cooperative four-threads-per-problem Riccati kernel
         step64(xb64)
         X["f64"] = timed(lambda: step64(xb64), 5)
@@ -641,6 +658,18 @@ def run_ours(args):
                                                   "algorithmic_bytes_per_problem_step": 1600,
                                                   "note": "SURVEY 8d: A 576 + B 192 + Q 576 + R 64 in, gains 192 out (fp32); the kernel "
                                                           "fetches only the lower-triangle chunks of Q (384 B)"}},
+                **{f"cfg1_shape_8x4_{name}_{tag}": {
+                    "value": Bsz * world / (X[key + tag] * 1e-3), "unit": "solves/s", "ms": X[key + tag],
+                    "workload": f"{fn} at the demos' shape (n, m) = (8, 4), N = 100, {Bsz} problems per GPU, {tag}: per-problem A, B constant in "
+                                "time" + (", H, d, q, r series shared by the batch" if name == "bilinear" else ""), "scaling": "weak",
+                    "roofline": {"bound": tag.replace("f", "fp") + "_fma", "achieved": Bsz * 100 * flop / (X[key + tag] * 1e-3) / 1e12, "peak": pk,
+                                 "unit": "TFLOP/s", "frac": Bsz * 100 * flop / (X[key + tag] * 1e-3) / 1e12 / pk,
+                                 "frac_executed": Bsz * 100 * flop_exec / (X[key + tag] * 1e-3) / 1e12 / pk,
+                                 "note": f"SURVEY 8d dense count at (8,4): {flop} flop per problem-step; the kernel executes {flop_exec} (symmetric V "
+                                         "as a lower triangle, V' = Q + A'W - M'L): frac_executed is the FMA pipe's share"}}
+                   for name, fn, key, flop, fe32, fe64 in (("dfh", "discreteFiniteHorizonLqr", "dfh8_", 5093, 3284, 3404),
+                                                           ("bilinear", "bilinearAffineLqr", "bil8_", 5493, 3692, 3812))
+                   for tag, pk, flop_exec in (("f32", p32, fe32), ("f64", p64, fe64))},
                 "cfg3_box_constrained_mpc": {"value": 16384 / (X["box"] * 1e-3), "unit": "solves/s", "ms": X["box"],
                                              "admm_iterations_mean_rank0": info["box_iters"], "optimal_fraction_rank0": info["box_opt"],
                                              "workload": "16,384 initial states total (sharded over ranks), the reference demo's box-constrained "
@@ -658,7 +687,8 @@ def run_ours(args):
             shard_note = f" (one shard of eight: {X['cl_shard']:.2f} ms)" if world == 1 else ""
             tail = (f"N={world} e2e {e2e_val / 1e6:.1f}M/s ({e2e_gbs:.0f} of {roof_gbs:.0f} GB/s copy roof) | cfg3 strong 16384x200: {cl:.2f} ms "
                     f"{16384 * 200 / cl / 1e3:.1f}M MPC/s{shard_note}; weak {clw:.2f} ms; fp64 {cl64:.1f} ms | cfg4 iLQR f64 {il:.1f} ms {16384 * 10 / il / 1e3:.2f}M it/s; "
-                    f"defaults {ild:.1f} ms @{info['il_default_iters_mean']:.1f} it | cfg5 DDP {ddp:.1f} ms | tv {tv:.2f} ms | f64 {f64t:.2f} ms")
+                    f"defaults {ild:.1f} ms @{info['il_default_iters_mean']:.1f} it | cfg5 DDP {ddp:.1f} ms | tv {tv:.2f} ms | f64 {f64t:.2f} ms | "
+                    f"(8,4) N=100 dfh/bilinear f32 {X['dfh8_f32']:.2f}/{X['bil8_f32']:.2f} ms f64 {X['dfh8_f64']:.2f}/{X['bil8_f64']:.2f} ms")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

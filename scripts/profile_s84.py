@@ -7,7 +7,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from zopt_b200.lqrUtils import bilinearAffineLqr, discreteFiniteHorizonLqr
 Bsz, n, m, N = 65536, 8, 4, 100
 rng = np.random.default_rng(3)
-c = lambda a: torch.as_tensor(a, dtype=torch.float32, device="cuda")
+DT = torch.float64 if (len(sys.argv) > 1 and sys.argv[1] == "f64") else torch.float32  # f64: k_riccati_s84d
+c = lambda a: torch.as_tensor(a, dtype=DT, device="cuda")
 A = c(np.eye(n) + 0.1 * rng.normal(size=(Bsz, 1, n, n))).expand(-1, N, -1, -1)
 B = c(0.3 * rng.normal(size=(Bsz, 1, n, m))).expand(-1, N, -1, -1)
 Q = c(np.eye(n))[None, None].expand(Bsz, N, -1, -1); R = c(np.eye(m))[None, None].expand(Bsz, N, -1, -1)

@@ -190,9 +190,10 @@ def test_bilinear_random_vs_oracle():
     r = rng.normal(size=(Bsz, N, m)) * 0.1
     q0 = rng.normal(size=(Bsz, N))
     Lr, lr = olqr.bilinearAffineLqr_batched(A, Bm, d, Q, R, Hm, q, r, q0, N)
-    # fp32 gate is 1e-4 here, not 1e-5: the as-written recursion (lqrUtils.py:251, no Joseph form) run in fp32 with
-    # NumPy/LAPACK on this very N=100 problem is itself 2.2e-5 (L) / 3.7e-5 (l) away from fp64 (DESIGN.md "Tolerances").
-    for dt, tol in ((torch.float64, 1e-10), (torch.float32, 1e-4)):
+    # fp32 gate: 1e-5 since the (8,4) kernel of lqr_s84.cuh carries V as a symmetric lower triangle (measured
+    # 7e-7); the as-written recursion (lqrUtils.py:251, no Joseph form) run in fp32 with NumPy/LAPACK on this very N=100 problem is
+    # itself 2.2e-5 (L) / 3.7e-5 (l) away from fp64 (DESIGN.md "Tolerances"), which is why the as-written kernels are gated at 1e-4.
+    for dt, tol in ((torch.float64, 1e-10), (torch.float32, 1e-5)):
         L, l = bilinearAffineLqr(*(cuda(t, dt) for t in (A, Bm, d, Q, R, Hm, q, r, q0)), N)
         assert per_problem_relerr(L, Lr).max() < tol and per_problem_relerr(l, lr).max() < tol
     # shared (un-batched) operands broadcast over a batched one
