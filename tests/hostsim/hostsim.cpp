@@ -296,6 +296,7 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 #define __launch_bounds__(x)
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 using std::fmaf;
 struct HsDim { unsigned x; };
 static HsDim threadIdx, blockIdx;

@@ -142,13 +142,9 @@ __device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv
             if (BILIN) Su[a] = fmaf(ZB_F4(b4, a), vVd[i], Su[a]);
         }
     }
-    const float d0 = rsqrtf(G[0]);
-    const float c10 = G[1] * d0, c20 = G[3] * d0, c30 = G[6] * d0;
-    const float d1 = rsqrtf(fmaf(-c10, c10, G[2]));
-    const float c21 = fmaf(-c20, c10, G[4]) * d1, c31 = fmaf(-c30, c10, G[7]) * d1;
-    const float d2 = rsqrtf(fmaf(-c21, c21, fmaf(-c20, c20, G[5])));
-    const float c32 = fmaf(-c31, c21, fmaf(-c30, c20, G[8])) * d2;
-    const float d3 = rsqrtf(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
+    // the Cholesky G = C C' (four dependent rsqrt chains) is written inside pass 3, one column of C after each of its first four rows,
+    // so that the scheduler can fill the chains' latency with the pass's independent FMAs
+    float d0, d1, d2, d3, c10, c20, c30, c21, c31, c32;
     // ---- 3. V' (lower) = Q + A'W, M = (H +) B'W, v' = q + A'(v + V d) in one pass over the rows of [A | B] -------
     read_q_lower(S, v);  // V is dead from here on: its registers take the new value
     if (BILIN) {
@@ -175,6 +171,18 @@ __device__ __forceinline__ void step(const float4* S, float (&v)[36], float (&vv
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int j = 0; j < 8; j += 2) fma2(M[a][j], M[a][j + 1], ZB_F4(b4, a), W[kk][j], W[kk][j + 1]);
+        if (kk == 0) {
+            d0 = rsqrtf(G[0]);
+            c10 = G[1] * d0; c20 = G[3] * d0; c30 = G[6] * d0;
+        } else if (kk == 1) {
+            d1 = rsqrtf(fmaf(-c10, c10, G[2]));
+            c21 = fmaf(-c20, c10, G[4]) * d1; c31 = fmaf(-c30, c10, G[7]) * d1;
+        } else if (kk == 2) {
+            d2 = rsqrtf(fmaf(-c21, c21, fmaf(-c20, c20, G[5])));
+            c32 = fmaf(-c31, c21, fmaf(-c30, c20, G[8])) * d2;
+        } else if (kk == 3) {
+            d3 = rsqrtf(fmaf(-c32, c32, fmaf(-c31, c31, fmaf(-c30, c30, G[9]))));
+        }
     }
     // ---- 4. L = G^-1 M (and l = G^-1 S_u): C y = rhs, C' x = y ---------------------------------------------------
 #pragma unroll

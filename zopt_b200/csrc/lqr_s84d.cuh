@@ -179,14 +179,21 @@ __device__ __forceinline__ void step(double2* S, double (&v)[36], double (&vv)[8
 #pragma unroll
             for (int j = 0; j < 8; ++j) M[a][j] = 0.0;
     }
-    // Cholesky G = C C' by reciprocal square roots
-    const double d0 = 1.0 / sqrt(G[0]);
-    const double c10 = G[1] * d0, c20 = G[3] * d0, c30 = G[6] * d0;
-    const double d1 = 1.0 / sqrt(fma(-c10, c10, G[2]));
-    const double c21 = fma(-c20, c10, G[4]) * d1, c31 = fma(-c30, c10, G[7]) * d1;
-    const double d2 = 1.0 / sqrt(fma(-c21, c21, fma(-c20, c20, G[5])));
-    const double c32 = fma(-c31, c21, fma(-c30, c20, G[8])) * d2;
-    const double d3 = 1.0 / sqrt(fma(-c32, c32, fma(-c31, c31, fma(-c30, c30, G[9]))));
+    // Cholesky G = C C' by reciprocal square roots: four dependent rsqrt chains, written INSIDE pass 3 (one column of C after each
+    // of its first four rows) so that the scheduler can fill their latency with the pass's independent FMAs -- with one warp per
+    // scheduler nothing else would
+    // (the bilinear instantiation has no registers to spare for that -- it spilled 600 B -- and keeps the chains ahead of the pass)
+    constexpr bool INTER = !BILIN;
+    double d0, d1, d2, d3, c10, c20, c30, c21, c31, c32;
+    if (!INTER) {
+        d0 = rsqrt(G[0]);
+        c10 = G[1] * d0; c20 = G[3] * d0; c30 = G[6] * d0;
+        d1 = rsqrt(fma(-c10, c10, G[2]));
+        c21 = fma(-c20, c10, G[4]) * d1; c31 = fma(-c30, c10, G[7]) * d1;
+        d2 = rsqrt(fma(-c21, c21, fma(-c20, c20, G[5])));
+        c32 = fma(-c31, c21, fma(-c30, c20, G[8])) * d2;
+        d3 = rsqrt(fma(-c32, c32, fma(-c31, c31, fma(-c30, c30, G[9]))));
+    }
     // ---- 3. V' (lower) = Q + A'W, M = (H +) B'W, v' = q + A'(v + V d) in one pass over the rows of A, W, B ---------------
     read_q_lower(S, v);
     if (BILIN) {
@@ -216,6 +223,19 @@ __device__ __forceinline__ void step(double2* S, double (&v)[36], double (&vv)[8
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int j = 0; j < 8; ++j) M[a][j] = fma(br[a], wr[j], M[a][j]);
+        if (!INTER) {
+        } else if (kk == 0) {
+            d0 = rsqrt(G[0]);
+            c10 = G[1] * d0; c20 = G[3] * d0; c30 = G[6] * d0;
+        } else if (kk == 1) {
+            d1 = rsqrt(fma(-c10, c10, G[2]));
+            c21 = fma(-c20, c10, G[4]) * d1; c31 = fma(-c30, c10, G[7]) * d1;
+        } else if (kk == 2) {
+            d2 = rsqrt(fma(-c21, c21, fma(-c20, c20, G[5])));
+            c32 = fma(-c31, c21, fma(-c30, c20, G[8])) * d2;
+        } else if (kk == 3) {
+            d3 = rsqrt(fma(-c32, c32, fma(-c31, c31, fma(-c30, c30, G[9]))));
+        }
     }
     // ---- 4. L = G^-1 M (and l = G^-1 S_u): C y = rhs, C' x = y -------------------------------------------------------------
 #pragma unroll
