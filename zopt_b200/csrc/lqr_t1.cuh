@@ -538,8 +538,9 @@ inline cudaError_t t1q_alloc(T1Queue& Wq, long long groups, int N, int chunk, vo
     const size_t n_ints = (size_t)64 + (size_t)groups + (size_t)(groups * nchunks);
     const size_t v_off = (n_ints * sizeof(int) + 255) & ~(size_t)255;
     const size_t bytes = v_off + (size_t)groups * 78 * 32 * sizeof(float);
-    cudaError_t e = cudaMallocAsync(scratch, bytes, stream);
+    cudaError_t e = keep_pool_memory();
     if (e != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(scratch, bytes, stream)) != cudaSuccess) return e;
     int* p = reinterpret_cast<int*>(*scratch);
     if ((e = cudaMemsetAsync(p, 0, (64 + (size_t)groups) * sizeof(int), stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p + 64 + groups, 0xFF, (size_t)(groups * nchunks) * sizeof(int), stream)) != cudaSuccess) return e;  // ring: all -1

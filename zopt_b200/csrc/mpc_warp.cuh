@@ -64,6 +64,14 @@ __global__ void k_queue_seed(int* ring, long long n) {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (j < n) ring[j] = (int)j;
 }
+// The whole scratch in one launch (instead of two memsets + the seed kernel: three host calls less per solve): counters and progress
+// words 0, the first `n` ring entries seeded, the rest -1 (not pushed yet).
+__global__ void k_queue_init(int* scratch, long long head_ints, long long n, long long total) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= total) return;
+    const long long r = j - head_ints;
+    scratch[j] = (r < 0) ? 0 : (r < n ? (int)r : -1);
+}
 
 template <bool QUEUE>
 __global__ void __launch_bounds__(32) k_mpc_closed_loop_quad_w9(t1::ClosedLoopP P, W9Queue Wq) {
@@ -394,13 +402,12 @@ int32_t mpc_closed_loop_w9_launch(const t1::ClosedLoopP& P, cudaStream_t stream)
     const long long nchunks = (P.Tsim + chunk - 1) / chunk;
     int* scratch = nullptr;
     const size_t n_ints = (size_t)64 + (size_t)triples + (size_t)(triples * nchunks);
+    ZB_CUDA(keep_pool_memory());
     ZB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), n_ints * sizeof(int), stream));
-    ZB_CUDA(cudaMemsetAsync(scratch, 0, (64 + (size_t)triples) * sizeof(int), stream));
-    ZB_CUDA(cudaMemsetAsync(scratch + 64 + triples, 0xFF, (size_t)(triples * nchunks) * sizeof(int), stream));  // ring: all -1
     const w9::W9Queue Wq{reinterpret_cast<unsigned*>(scratch), reinterpret_cast<unsigned*>(scratch + 32), scratch + 64 + triples, scratch + 64, chunk};
     // `per` one-warp CTAs per scheduler; the block scheduler spreads them evenly over the SMs (measured: 592 CTAs run at the pace of
     // one warp per scheduler)
-    w9::k_queue_seed<<<(unsigned)((triples + 255) / 256), 256, 0, stream>>>(Wq.ring, triples);
+    w9::k_queue_init<<<(unsigned)((n_ints + 255) / 256), 256, 0, stream>>>(scratch, 64 + triples, triples, (long long)n_ints);
     ZB_CUDA(cudaGetLastError());
     w9::k_mpc_closed_loop_quad_w9<true><<<(unsigned)(per * sched), 32, 0, stream>>>(P, Wq);
     ZB_CUDA(cudaGetLastError());
