@@ -231,8 +231,25 @@ __global__ void __launch_bounds__(32) k_riccati_s84(S84P P) {
     float4* S = slab + lane;
     float v[36], vv[8], L[4][8], l[4];
     // terminal carry (lqrUtils.py:172 / :261): Q[T-1] (and q[T-1])
+    // The terminal Q with the first step's A, then B with R: two DRAM round trips at the start of the warp instead of four (all four
+    // at once would raise the kernel to 255 registers and cost a resident warp per SM)
+    // (every warp of a wave starts at the same time, so nothing hides them: the staging lines held 11 % of the samples, long_scoreboard)
     int qk = P.T - 1;
-    stage<16>(S, Q4, P.Q.at<float>(b, qk));
+    const int k0 = P.N - 1;
+    {
+        float4 tq[16], ta[16];
+        fetch<16>(tq, P.Q.at<float>(b, qk));
+        fetch<16>(ta, P.A.at<float>(b, k0));
+        put<16>(S, Q4, tq);
+        put<16>(S, A4, ta);
+    }
+    {
+        float4 tb[8], tr[4];
+        fetch<8>(tb, P.B.at<float>(b, k0));
+        fetch<4>(tr, P.R.at<float>(b, k0));
+        put<8>(S, B4, tb);
+        put<4>(S, R4, tr);
+    }
     read_q_lower(S, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) vv[i] = 0.f;
@@ -245,18 +262,17 @@ __global__ void __launch_bounds__(32) k_riccati_s84(S84P P) {
     float* lout = BILIN ? P.l + b * (long long)P.N * 4 : nullptr;
 #pragma unroll 1
     for (int k = P.N - 1; k >= 0; --k) {
-        const bool first = (k == P.N - 1);
-        // operands constant in time are staged once; the others again at every step, in two groups ([A | B] and [Q, R]) whose
+        // operands constant in time are staged once (above); the others again at every step, in two groups ([A | B] and [Q, R]) whose
         // loads are all in flight before the first store waits (one L2 latency per group; re-staging a constant member of a
         // group is harmless: the same block again)
-        if (first || P.A.st || P.B.st) {
+        if (k != k0 && (P.A.st || P.B.st)) {
             float4 ta[16], tb[8];
             fetch<16>(ta, P.A.at<float>(b, k));
             fetch<8>(tb, P.B.at<float>(b, k));
             put<16>(S, A4, ta);
             put<8>(S, B4, tb);
         }
-        if (first || P.R.st || (P.Q.st && k != qk)) {
+        if ((k != k0 && P.R.st) || (P.Q.st && k != qk)) {
             float4 tq[16], tr[4];
             fetch<16>(tq, P.Q.at<float>(b, P.Q.st ? k : qk));
             fetch<4>(tr, P.R.at<float>(b, k));
